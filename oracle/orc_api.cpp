@@ -1,0 +1,246 @@
+// ORACLE (test infrastructure, NOT product code): C entry points of the CPU restatement, loaded with ctypes by
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs ONLY.
+// Mirrors MegaverseGym (src/libs/bindings/megaverse.cpp:36-243) + VectorEnv (src/libs/env/src/vector_env.cpp:89-120).
+#include <array>
+#include <atomic>
+#include <thread>
+
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "orc_raster.hpp"
+
+using namespace orc;
+
+// minimal parallel-for over envs (libgomp is not available in this image)
+template <typename F> static void parallelFor(int n, int threads, F &&f) {
+    if (threads <= 1 || n <= 1) { for (int i = 0; i < n; ++i) f(i); return; }
+    std::atomic<int> next{0};
+    auto worker = [&]() { for (int i = next++; i < n; i = next++) f(i); };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
+
+struct OrcVec {
+    std::vector<std::unique_ptr<Env>> envs;
+    int w, h, numEnvs, numAgents;
+    std::vector<uint8_t> obs;
+    std::vector<float> depth;
+    std::vector<float> rewards, trueObjectives;
+    std::vector<uint8_t> dones;
+    Rng rng{std::random_device{}()};
+    bool renderEnabled = true;
+    bool wantDepth = false;
+    int threads = 1;
+    std::string error;
+
+    void renderEnv(int e) {
+        Env &env = *envs[size_t(e)];
+        const auto inst = env.instances();
+        for (int a = 0; a < numAgents; ++a) {
+            const size_t view = size_t(e) * numAgents + a;
+            renderView(env.viewMatrix(a), inst, w, h, obs.data() + view * size_t(w) * h * 4, wantDepth ? depth.data() + view * size_t(w) * h : nullptr);
+        }
+    }
+};
+
+extern "C" {
+
+void *orc_create(const char *scenario, int w, int h, int numEnvs, int numAgents, const char **keys, const float *vals, int nparams) {
+    auto *v = new OrcVec;
+    try {
+        FloatParams fp;
+        for (int i = 0; i < nparams; ++i) fp[keys[i]] = vals[i];
+        for (int i = 0; i < numEnvs; ++i) v->envs.emplace_back(std::make_unique<Env>(scenario, numAgents, fp));
+    } catch (const std::exception &) {
+        delete v;
+        return nullptr;
+    }
+    v->w = w; v->h = h; v->numEnvs = numEnvs; v->numAgents = numAgents;
+    const size_t N = size_t(numEnvs) * numAgents;
+    v->obs.assign(N * w * h * 4, 0);
+    v->depth.assign(N * w * h, 0.0f);
+    v->rewards.assign(N, 0.0f);
+    v->trueObjectives.assign(N, 0.0f);
+    v->dones.assign(size_t(numEnvs), 0);
+    return v;
+}
+void orc_destroy(void *p) { delete static_cast<OrcVec *>(p); }
+void orc_set_options(void *p, int render, int depth, int threads) {
+    auto *v = static_cast<OrcVec *>(p);
+    v->renderEnabled = render != 0; v->wantDepth = depth != 0; v->threads = threads < 1 ? 1 : threads;
+}
+// MegaverseGym::seed (megaverse.cpp:60-69)
+void orc_seed(void *p, int seedValue) {
+    auto *v = static_cast<OrcVec *>(p);
+    v->rng.seed((unsigned long)seedValue);
+    for (auto &e : v->envs) e->seed(randRange(0, 1 << 30, v->rng));
+}
+// megaverse_test_app.cpp:250-254 seeds env i with 42+i directly
+void orc_seed_env(void *p, int env, int seedValue) { static_cast<OrcVec *>(p)->envs[size_t(env)]->seed(seedValue); }
+
+// VectorEnv::reset (vector_env.cpp:110-120)
+void orc_reset(void *p) {
+    auto *v = static_cast<OrcVec *>(p);
+    parallelFor(v->numEnvs, v->threads, [&](int e) {
+        v->envs[size_t(e)]->reset();
+        if (v->renderEnabled) v->renderEnv(e);
+    });
+    std::fill(v->rewards.begin(), v->rewards.end(), 0.0f);
+    std::fill(v->dones.begin(), v->dones.end(), 0);
+}
+void orc_set_actions(void *p, const int32_t *masks) {
+    auto *v = static_cast<OrcVec *>(p);
+    for (int e = 0; e < v->numEnvs; ++e)
+        for (int a = 0; a < v->numAgents; ++a) v->envs[size_t(e)]->setAction(a, masks[e * v->numAgents + a]);
+}
+// VectorEnv::step (vector_env.cpp:89-108) + getLastRewards (megaverse.cpp:128-137)
+void orc_step(void *p) {
+    auto *v = static_cast<OrcVec *>(p);
+    parallelFor(v->numEnvs, v->threads, [&](int e) {
+        Env &env = *v->envs[size_t(e)];
+        env.step();
+        if (env.done) {
+            v->dones[size_t(e)] = 1;
+            for (int a = 0; a < v->numAgents; ++a) v->trueObjectives[size_t(e) * v->numAgents + a] = env.trueObjective(a);
+            env.reset();
+        } else {
+            v->dones[size_t(e)] = 0;
+        }
+        for (int a = 0; a < v->numAgents; ++a) v->rewards[size_t(e) * v->numAgents + a] = env.lastReward[size_t(a)];
+        if (v->renderEnabled) v->renderEnv(e);
+    });
+}
+const uint8_t *orc_obs(void *p) { return static_cast<OrcVec *>(p)->obs.data(); }
+const float *orc_depth(void *p) { return static_cast<OrcVec *>(p)->depth.data(); }
+const float *orc_rewards(void *p) { return static_cast<OrcVec *>(p)->rewards.data(); }
+const uint8_t *orc_dones(void *p) { return static_cast<OrcVec *>(p)->dones.data(); }
+const float *orc_true_objectives(void *p) { return static_cast<OrcVec *>(p)->trueObjectives.data(); }
+void orc_render_now(void *p) {
+    auto *v = static_cast<OrcVec *>(p);
+    parallelFor(v->numEnvs, v->threads, [&](int e) { v->renderEnv(e); });
+}
+
+int orc_get_reward_shaping(void *p, int env, int agent, const char *key, float *out) {
+    auto &rs = static_cast<OrcVec *>(p)->envs[size_t(env)]->rewardShaping[size_t(agent)];
+    auto it = rs.find(key);
+    if (it == rs.end()) return 1;
+    *out = it->second;
+    return 0;
+}
+void orc_set_reward_shaping(void *p, int env, int agent, const char *key, float val) {
+    static_cast<OrcVec *>(p)->envs[size_t(env)]->rewardShaping[size_t(agent)][key] = val;
+}
+
+// ---- introspection for parity tests -------------------------------------------------------------------------------
+// level: ints.  [0]=numStaticBoxes [1]=numTerrain [2]=numObjects [3..8]=buildingZone min/max, then per static box 8 ints
+// (min3,max3(inclusive),type,color), per terrain slab 7 ints (terrain,min3,max3), per object 3 ints (spawn voxel),
+// then per agent 3 ints (spawn voxel)
+int orc_get_level(void *p, int envIdx, int32_t *out, int cap) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(envIdx)];
+    std::vector<int32_t> o;
+    o.push_back(int(env.staticBoxes.size()));
+    o.push_back(int(env.terrainSlabs.size()));
+    o.push_back(int(env.platform->objectSpawnCoords.size()));
+    const BoundingBox &bz = env.buildingZone;
+    for (int x : {bz.min.x, bz.min.y, bz.min.z, bz.max.x, bz.max.y, bz.max.z}) o.push_back(x);
+    for (auto &sb : env.staticBoxes)
+        for (int x : {sb.bb.min.x, sb.bb.min.y, sb.bb.min.z, sb.bb.max.x, sb.bb.max.y, sb.bb.max.z, int(sb.type), int(sb.color)}) o.push_back(x);
+    for (auto &ts : env.terrainSlabs)
+        for (int x : {ts.terrain, ts.bb.min.x, ts.bb.min.y, ts.bb.min.z, ts.bb.max.x, ts.bb.max.y, ts.bb.max.z}) o.push_back(x);
+    for (auto &c : env.platform->objectSpawnCoords)
+        for (int x : {c.x, c.y, c.z}) o.push_back(x);
+    for (auto &c : env.platform->agentSpawnCoords)
+        for (int x : {int(c.x), int(c.y), int(c.z)}) o.push_back(x);
+    if (int(o.size()) > cap) return -int(o.size());
+    std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    return int(o.size());
+}
+
+// state: floats.  header 8: currEpisodeSec, episodeLengthSec, numFrames, highestTower, currBuildingZoneReward, numObjects,
+// numColliders, done.  Per agent 28: pos3, basis9(row major), hvel3, vVel, vOffset, currentStepOffset, wasOnGround,
+// wasJumping, jumpSpeed, currXRotation, carrying, totalReward, lastReward, pad.  Per object 9: translation3 (abs),
+// scale3 (local), parentAgent, colliderEnabled, pad
+int orc_get_state(void *p, int envIdx, float *out, int cap) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(envIdx)];
+    std::vector<float> o;
+    o.push_back(env.currEpisodeSec); o.push_back(env.episodeLengthSec()); o.push_back(float(env.numFrames)); o.push_back(float(env.highestTower));
+    o.push_back(env.currBuildingZoneReward); o.push_back(float(env.objects.size())); o.push_back(float(env.colliders.size())); o.push_back(env.done ? 1.f : 0.f);
+    for (int i = 0; i < env.numAgents; ++i) {
+        const Agent &a = env.agents[size_t(i)];
+        const KCC &k = a.kcc;
+        for (float x : {k.pos.x, k.pos.y, k.pos.z}) o.push_back(x);
+        for (int r = 0; r < 3; ++r) for (float x : {k.basis.r[r].x, k.basis.r[r].y, k.basis.r[r].z}) o.push_back(x);
+        for (float x : {k.horizontalVelocity.x, k.horizontalVelocity.y, k.horizontalVelocity.z, k.verticalVelocity, k.verticalOffset, k.currentStepOffset,
+                        k.wasOnGround ? 1.f : 0.f, k.wasJumping ? 1.f : 0.f, k.jumpSpeed, a.currXRotation, float(env.carryingObject[size_t(i)]),
+                        env.totalReward[size_t(i)], env.lastReward[size_t(i)], 0.f})
+            o.push_back(x);
+    }
+    for (int i = 0; i < int(env.objects.size()); ++i) {
+        const MovableObject &ob = env.objects[size_t(i)];
+        const Vec3 t = translationOf(env.objectAbs(i));
+        for (float x : {t.x, t.y, t.z, ob.local.c[0][0], ob.local.c[1][1], ob.local.c[2][2], float(ob.parentAgent),
+                        env.colliders[size_t(ob.collider)].enabled ? 1.f : 0.f, 0.f})
+            o.push_back(x);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::memcpy(out, o.data(), o.size() * sizeof(float));
+    return int(o.size());
+}
+
+// solid/object occupancy: sorted list of (x,y,z,flags) with flags bit0 solid, bit1 opaque, bit2 holds object; terrain in bits 8..
+int orc_get_voxels(void *p, int envIdx, int32_t *out, int cap) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(envIdx)];
+    std::vector<std::array<int32_t, 4>> v;
+    for (auto &kv : env.vg.grid.getHashMap()) {
+        const int flags = int(kv.second.voxelType) | (kv.second.physicsObject >= 0 ? 4 : 0) | (int(kv.second.terrain) << 8);
+        if (flags == 0) continue;  // an entry that became empty again is indistinguishable from no entry
+        v.push_back({kv.first.x, kv.first.y, kv.first.z, flags});
+    }
+    std::sort(v.begin(), v.end());
+    if (int(v.size()) * 4 > cap) return -int(v.size()) * 4;
+    for (size_t i = 0; i < v.size(); ++i) std::memcpy(out + i * 4, v[i].data(), 16);
+    return int(v.size()) * 4;
+}
+
+// instances of one env in draw order: per instance 18 floats (mesh, color, 16 model matrix column-major); view matrices
+int orc_get_instances(void *p, int envIdx, float *out, int cap) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(envIdx)];
+    const auto inst = env.instances();
+    if (int(inst.size()) * 18 > cap) return -int(inst.size()) * 18;
+    for (size_t i = 0; i < inst.size(); ++i) {
+        out[i * 18] = float(inst[i].mesh); out[i * 18 + 1] = float(inst[i].color);
+        std::memcpy(out + i * 18 + 2, &inst[i].model.c[0][0], 64);
+    }
+    return int(inst.size()) * 18;
+}
+void orc_get_view(void *p, int envIdx, int agent, float *out16) {
+    const Mat4 m = static_cast<OrcVec *>(p)->envs[size_t(envIdx)]->viewMatrix(agent);
+    std::memcpy(out16, &m.c[0][0], 64);
+}
+// stand-alone rasteriser entry: render given instances + view (for renderer-only parity tests)
+void orc_render_instances(const float *view16, const float *inst18, int n, int w, int h, uint8_t *rgba, float *depth) {
+    Mat4 view;
+    std::memcpy(&view.c[0][0], view16, 64);
+    std::vector<Instance> inst(static_cast<size_t>(n));
+    for (int i = 0; i < n; ++i) {
+        inst[size_t(i)].mesh = int(inst18[i * 18]); inst[size_t(i)].color = int(inst18[i * 18 + 1]);
+        std::memcpy(&inst[size_t(i)].model.c[0][0], inst18 + i * 18 + 2, 64);
+    }
+    renderView(view, inst, w, h, rgba, depth);
+}
+// mesh tables (float bit patterns) so tests can compare the product's own tables with the reference's Magnum
+int orc_get_mesh(int type, uint32_t *vtx, int capV, uint16_t *idx, int capI) {
+    const MeshRef m = meshRef(type);
+    if (m.nv * 6 > capV || m.ni > capI) return -1;
+    std::memcpy(vtx, m.vtx, size_t(m.nv) * 24);
+    std::memcpy(idx, m.idx, size_t(m.ni) * 2);
+    return m.nv * 65536 + m.ni;
+}
+int orc_max_threads() { return int(std::thread::hardware_concurrency()); }
+
+}  // extern "C"

@@ -1,0 +1,572 @@
+// ORACLE (test infrastructure, NOT product code): one environment = state + agents + scenario logic.
+// Restated from
+//   src/libs/env/src/env.cpp:36-152 (ctor, reset, step)      src/libs/env/include/env/env.hpp:124-170 (EnvState)
+//   src/libs/env/src/agent.cpp:26-170 (DefaultKinematicAgent)  src/libs/env/include/env/physics.hpp:58-85 (RigidBody)
+//   src/libs/env/include/env/scenario.hpp:94-117,184-307 (reward shaping, rewardAgent/Team/All, doneWithTimer)
+//   src/libs/scenarios/include/scenarios/scenario_default.hpp:80-186 (spawnAgents, agent drawables, HUD)
+//   src/libs/scenarios/include/scenarios/component_object_stacking.hpp:45-198
+//   src/libs/scenarios/include/scenarios/component_fall_detection.hpp:33-56
+//   src/libs/scenarios/src/layout_utils.cpp:17-68 (addBoundingBoxes, addTerrain)
+//   src/libs/scenarios/src/scenario_tower_building.cpp:8-266 (+ scenario_tower_building.hpp:42-52)
+//   src/libs/env/src/vector_env.cpp:89-120 (done handling)   src/libs/bindings/megaverse.cpp:60-69,100-137
+#pragma once
+#include <cfloat>
+#include <cstdio>
+#include <stdexcept>
+
+#include "orc_level.hpp"
+#include "orc_physics.hpp"
+
+namespace orc {
+
+enum Action {
+    A_Idle = 0, A_Left = 1 << 1, A_Right = 1 << 2, A_Forward = 1 << 3, A_Backward = 1 << 4, A_LookLeft = 1 << 5, A_LookRight = 1 << 6,
+    A_Jump = 1 << 7, A_Interact = 1 << 8, A_LookDown = 1 << 9, A_LookUp = 1 << 10,
+};
+enum MeshType { MESH_BOX = 0, MESH_CAPSULE = 1, MESH_SPHERE = 2, MESH_CONE = 3, MESH_CYLINDER = 4, MESH_NUM = 5 };
+
+struct Instance {  // one drawable: mesh type, palette colour, model matrix (absoluteTransformationMatrix)
+    int mesh;
+    int color;  // palette index
+    Mat4 model;
+};
+
+struct Agent {
+    KCC kcc;
+    float currXRotation = 0.0f;
+    float verticalLookLimitRad = 0.2f;
+    Mat4 objectT = mat4Identity();      // the agent Object3D transformation
+    Mat4 cameraLocal = mat4Identity();  // cameraObject, child of agent
+    Mat4 pickupLocal = mat4Identity();  // pickupSpot, child of cameraObject
+    Mat4 bodyLocal, eyesLocal, uiLocal, barAnchorLocal, barLocal;
+    int color = 0;
+
+    static constexpr float rotateRadians = 3.5f, rotateXRadians = 1.5f, agentHeight = 1.75f;
+
+    void init(Vec3 startingPosition, float rotationRad, float lookLimit) {  // agent.cpp:26-67
+        *this = Agent{};
+        verticalLookLimitRad = lookLimit;
+        cameraLocal = mul(mat4Translation({0, 0.41f, 0}), cameraLocal);
+        pickupLocal = mul(mat4Translation({0.0f, -0.44f, -1.0f}), pickupLocal);
+        kcc.basis = mat3FromQuat(quatAxisAngle({0, 1, 0}, rotationRad));
+        kcc.pos = {startingPosition.x, startingPosition.y + agentHeight, startingPosition.z};
+    }
+    void updateTransform() {  // agent.cpp:73-98
+        const Quat q = quatFromMat3(kcc.basis);
+        Vec3 position = kcc.pos;
+        const Vec3 axis = quatAxis(q);
+        const Vec3 normalizedAxis = mgNormalized(axis);
+        const float rotation = quatAngle(q);
+        if (std::isnan(position.x) || std::isnan(position.y) || std::isnan(position.z) || std::isnan(rotation)) return;
+        if (std::isnan(normalizedAxis.x) || std::isnan(normalizedAxis.y) || std::isnan(normalizedAxis.z)) return;
+        position += Vec3{0, 0.05f, 0.0f};
+        objectT = mul(mat4Translation(position), mul(mat4Rotation(rotation, normalizedAxis), mat4Identity()));
+    }
+    void rotateYAxis(float radians) { kcc.basis = mul(kcc.basis, mat3FromQuat(quatAxisAngle({0, 1, 0}, radians))); }  // agent.cpp:128-133
+    void lookLeft(float dt) { rotateYAxis(rotateRadians * dt); }
+    void lookRight(float dt) { rotateYAxis(-rotateRadians * dt); }
+    void lookUp(float dt) {  // agent.cpp:110-116
+        cameraLocal = mul(cameraLocal, mat4RotationX(-currXRotation));
+        currXRotation += rotateXRadians * dt;
+        currXRotation = std::min(verticalLookLimitRad, currXRotation);
+        cameraLocal = mul(cameraLocal, mat4RotationX(currXRotation));
+    }
+    void lookDown(float dt) {  // agent.cpp:118-126
+        cameraLocal = mul(cameraLocal, mat4RotationX(-currXRotation));
+        currXRotation -= rotateXRadians * dt * 1.1f;
+        currXRotation = std::max(-verticalLookLimitRad, currXRotation);
+        cameraLocal = mul(cameraLocal, mat4RotationX(currXRotation));
+    }
+    Vec3 forwardDirection() const { Vec3 f = kcc.basis.r[2]; f.z = -f.z; return btNormalized(f); }      // agent.cpp:135-142
+    Vec3 strafeLeftDirection() const { Vec3 s = kcc.basis.r[0]; s.x = -s.x; return btNormalized(s); }  // agent.cpp:144-150
+    bool onGround() const { return kcc.onGround(); }
+    void jump() { if (onGround()) kcc.jump({0, 6.2f, 0}); }
+    Mat4 cameraAbs() const { return mul(objectT, cameraLocal); }                         // Object::absoluteTransformation, left to right
+    Mat4 pickupAbs() const { return mul(mul(objectT, cameraLocal), pickupLocal); }
+};
+
+struct MovableObject {
+    Mat4 local;            // transformation relative to parent
+    int parentAgent = -1;  // -1: scene; else child of that agent's pickupSpot
+    Vec3 collisionScale{1.15f, 1.15f, 1.15f}, collisionOffset{0, -0.05f, 0};
+    int collider = -1;
+    int color = 0;
+};
+
+struct StaticBox { BoundingBox bb; uint8_t type; ColorRgb color; };
+struct TerrainSlab { int terrain; BoundingBox bb; };
+
+using RewardShaping = std::map<std::string, float>;
+
+class Env {
+public:
+    enum Scenario { S_TOWER = 0 };
+
+    Env(const std::string &scenarioName, int numAgents, const FloatParams &custom) : numAgents(numAgents) {
+        std::string n;
+        for (char ch : scenarioName) n.push_back(char(tolower(ch)));
+        if (n == "towerbuilding") scenario = S_TOWER;
+        else throw std::runtime_error("oracle: unknown scenario " + n);
+        // Scenario::init (scenario.hpp:98-107) + initializeDefaultParameters (:225-231)
+        floatParams["episodeLengthSec"] = 60.0f;
+        floatParams["verticalLookLimitRad"] = 0.2f;
+        floatParams["useUIRewardIndicators"] = 0.0f;
+        rewardShaping.assign(size_t(numAgents), RewardShaping{{"teamSpirit", 0.0f}});
+        for (auto &rs : rewardShaping)
+            for (auto &[k, v] : defaultRewardShaping()) rs[k] = v;
+        for (auto &[k, v] : custom) floatParams[k] = v;
+        currAction.assign(size_t(numAgents), 0);
+        lastReward.assign(size_t(numAgents), 0.0f);
+        totalReward.assign(size_t(numAgents), 0.0f);
+        agentState.assign(size_t(numAgents), TowerAgentState{});
+    }
+
+    RewardShaping defaultRewardShaping() const {  // scenario_tower_building.hpp:44-52
+        return {{"teamSpirit", 0.1f}, {"towerPickedUpObject", 0.1f}, {"towerVisitedBuildingZoneWithObject", 0.1f}, {"towerBuildingReward", 1.0f}};
+    }
+
+    void seed(int s) { rng.seed((unsigned long)s); }
+
+    // ---------------------------------------------------------------- reset (env.cpp:57-76)
+    void reset() {
+        done = false; currEpisodeSec = 0; numFrames = 0;
+        std::fill(currAction.begin(), currAction.end(), 0);
+        std::fill(lastReward.begin(), lastReward.end(), 0.0f);
+        std::fill(totalReward.begin(), totalReward.end(), 0.0f);
+        agents.clear(); colliders.clear(); objects.clear(); staticBoxes.clear(); terrainSlabs.clear();
+
+        auto sd = randRange(0, 1 << 30, rng);
+        rng.seed((unsigned long)sd);
+
+        towerReset();
+        spawnAgents();
+        towerAddEpisodeDrawables();
+        addAgentsAndUI();
+    }
+
+    // TowerBuildingPlatform (scenario_tower_building.cpp:8-115)
+    struct TowerPlatform : EmptyPlatform {
+        TowerPlatform(Node *parent, Rng &rng, int walls, const FloatParams &p, int numAgents) : EmptyPlatform(parent, rng, walls, p), numAgents(numAgents) {}
+        void init() override {
+            height = randRange(5, 7, rng);
+            length = randRange(12, 30, rng);
+            width = randRange(12, 25, rng);
+            buildZoneLength = randRange(3, 9, rng);
+            buildZoneWidth = randRange(3, 9, rng);
+            materialsLength = randRange(2, 8, rng);
+            materialsWidth = randRange(2, 8, rng);
+            length = std::max(buildZoneLength + materialsLength + 3, length);
+            width = std::max(buildZoneWidth + materialsWidth + 3, width);
+            buildZoneXOffset = randRange(1, length - buildZoneLength - 1, rng);
+            buildZoneZOffset = randRange(1, width - buildZoneWidth - 1, rng);
+            materialsXOffset = randRange(1, length - materialsLength - 1, rng);
+            materialsZOffset = randRange(1, width - materialsWidth - 1, rng);
+            std::vector<VoxelCoords> spawnCandidates;
+            for (int x = 1; x < length - 1; ++x)
+                for (int z = 1; z < width - 1; ++z) spawnCandidates.emplace_back(x, 2, z);
+            std::shuffle(spawnCandidates.begin(), spawnCandidates.end(), rng);
+            agentSpawnCoords.clear();
+            for (int i = 0; i < std::min(numAgents, int(spawnCandidates.size())); ++i)
+                agentSpawnCoords.emplace_back(float(spawnCandidates[i].x), float(spawnCandidates[i].y), float(spawnCandidates[i].z));
+            auto spawnIdx = int(agentSpawnCoords.size());
+            const auto maxRandomObjects = std::min(int(spawnCandidates.size()) - numAgents, 25);
+            const auto spawnObjects = randRange(0, std::max(1, maxRandomObjects), rng);
+            objectSpawnCoords = std::vector<VoxelCoords>(spawnCandidates.begin() + spawnIdx, spawnCandidates.begin() + spawnIdx + spawnObjects);
+            for (auto &c : objectSpawnCoords) {
+                if (c.x >= materialsXOffset && c.x < materialsXOffset + materialsLength && c.z >= materialsZOffset && c.z < materialsZOffset + materialsWidth) continue;
+                c.y -= 1;
+            }
+            for (int x = materialsXOffset; x < materialsXOffset + materialsLength; ++x)
+                for (int y = 1; y <= 1; ++y)
+                    for (int z = materialsZOffset; z < materialsZOffset + materialsWidth; ++z) objectSpawnCoords.emplace_back(x, y, z);
+            while (int(agentSpawnCoords.size()) < numAgents) agentSpawnCoords.emplace_back(agentSpawnCoords[0]);
+        }
+        void generate() override {
+            EmptyPlatform::generate();
+            const VoxelCoords minCoord{buildZoneXOffset, 1, buildZoneZOffset}, maxCoord{buildZoneXOffset + buildZoneLength, 1, buildZoneZOffset + buildZoneWidth};
+            terrainBoxes[TERRAIN_BUILDING_ZONE].emplace_back(makeAABB({minCoord, maxCoord}));
+        }
+        std::vector<Vec3> agentSpawnCoords;
+        std::vector<VoxelCoords> objectSpawnCoords;
+        int buildZoneLength{}, buildZoneWidth{}, materialsLength{}, materialsWidth{};
+        int buildZoneXOffset{}, buildZoneZOffset{}, materialsXOffset{}, materialsZOffset{};
+        int numAgents{};
+    };
+
+    void towerReset() {  // scenario_tower_building.cpp:129-154
+        std::fill(carryingObject.begin(), carryingObject.end(), -1);
+        carryingObject.assign(size_t(numAgents), -1);
+        vg.reset();
+        agentInitialPositions.clear();
+        levelRoot = std::make_unique<Node>();
+        std::fill(agentState.begin(), agentState.end(), TowerAgentState{});
+
+        auto layoutColor = randomLayoutColor(rng);
+        while (layoutColor == BUILDING_ZONE) layoutColor = randomLayoutColor(rng);
+
+        platform = std::make_unique<TowerPlatform>(levelRoot.get(), rng, WALLS_ALL, floatParams, numAgents);
+        platform->init(), platform->generate();
+        // GCC evaluates call arguments right to left: randomBool (drawWalls) BEFORE randomLayoutColor (wall colour)
+        const bool drawWalls = randomBool(rng);
+        const ColorRgb wallColor = randomLayoutColor(rng);
+        vg.addPlatform(*platform, layoutColor, wallColor, drawWalls);
+
+        buildingZone = platform->terrainBoxes[TERRAIN_BUILDING_ZONE].front().boundingBox();
+        currBuildingZoneReward = 0.0f;
+        objectsInBuildingZone.clear();
+        highestTower = 0;
+        agentInitialPositions = platform->agentSpawnCoords;
+    }
+
+    void spawnAgents() {  // scenario_default.hpp:80-97
+        const float lookLimit = floatParams["verticalLookLimitRad"];
+        const auto agentPositions = platform->agentSpawnCoords;
+        agents.resize(size_t(numAgents));
+        for (int i = 0; i < numAgents; ++i) {
+            auto randomRotation = frand(rng) * 3.14159265358979323846f * 2;
+            agents[i].init(agentPositions[i] + Vec3{0.5f, 0.0f, 0.5f}, randomRotation, lookLimit);
+            agents[i].updateTransform();
+        }
+    }
+
+    // layout_utils.cpp:17-50 for every group of toBoundingBoxes (layout_utils.hpp:14-19), then terrain, then objects
+    void towerAddEpisodeDrawables() {
+        addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
+        for (auto &[terrainType, boxes] : platform->terrainBoxes)
+            for (auto &bb : boxes) terrainSlabs.push_back({terrainType, bb.boundingBox()});
+        const auto objectPositions = platform->objectSpawnCoords;
+        for (const auto &pos : objectPositions)
+            if (isInBuildingZone(pos)) objectsInBuildingZone.insert(pos);
+        currBuildingZoneReward = calculateTowerReward();
+        addObjects(objectPositions);
+    }
+
+    void addDrawablesAndCollisionObjectsFromVoxelGrid(float voxelSize) {
+        auto byType = vg.toBoundingBoxes();
+        for (auto &[info, boxes] : byType) {
+            if (info.type == VOXEL_EMPTY) continue;
+            for (auto &box : boxes) {
+                staticBoxes.push_back({box, info.type, info.color});
+                if (info.type & VOXEL_SOLID) {
+                    Collider c;
+                    c.kind = 0;
+                    c.h = staticBoxScale(box, voxelSize);
+                    c.c = staticBoxTranslation(box, voxelSize);
+                    colliders.push_back(c);
+                }
+            }
+        }
+    }
+    static Vec3 staticBoxScale(const BoundingBox &b, float vs) {
+        return Vec3{float(b.max.x - b.min.x + 1) / 2, float(b.max.y - b.min.y + 1) / 2, float(b.max.z - b.min.z + 1) / 2} * vs;
+    }
+    static Vec3 staticBoxTranslation(const BoundingBox &b, float vs) {
+        return Vec3{float(b.min.x + b.max.x) / 2 + 0.5f, float(b.min.y + b.max.y) / 2 + 0.5f, float(b.min.z + b.max.z) / 2 + 0.5f} * vs;
+    }
+
+    void addObjects(const std::vector<VoxelCoords> &positions) {  // component_object_stacking.hpp:170-198
+        const float objSize = 0.39f;
+        for (const auto &pos : positions) {
+            MovableObject o;
+            const Vec3 translation{float(pos.x) + 0.5f, float(pos.y) + 0.5f, float(pos.z) + 0.5f};
+            o.local = mul(mat4Translation(translation), mul(mat4Scaling({objSize, objSize, objSize}), mat4Identity()));
+            o.color = paletteIndex(MOVABLE_BOX);
+            o.collider = int(colliders.size());
+            colliders.push_back(Collider{});
+            objects.push_back(o);
+            syncPose(int(objects.size()) - 1);
+            if (!vg.grid.hasVoxel(pos)) vg.grid.set(pos, Voxel{});
+            vg.grid.get(pos)->physicsObject = int(objects.size()) - 1;
+        }
+    }
+    Mat4 objectAbs(int idx) const {  // Object::absoluteTransformation (left-to-right composition)
+        const MovableObject &o = objects[idx];
+        if (o.parentAgent < 0) return o.local;
+        return mul(agents[o.parentAgent].pickupAbs(), o.local);
+    }
+    void syncPose(int idx) {  // physics.hpp:69-74
+        const Mat4 m = objectAbs(idx);
+        Collider &c = colliders[objects[idx].collider];
+        c.kind = 0;
+        c.c = translationOf(m) + objects[idx].collisionOffset;
+        c.h = scalingOf(m) * objects[idx].collisionScale;
+    }
+
+    void addAgentsAndUI() {  // scenario_default.hpp:99-162 ; ghost objects join the collision world (agent.cpp:63)
+        for (int i = 0; i < numAgents; ++i) {
+            Agent &a = agents[i];
+            a.color = paletteIndex(agentColors[i % numAgentColors]);
+            a.bodyLocal = mul(mat4Translation({0, 0.09f, 0}), mul(mat4Scaling({0.35f, 0.36f, 0.35f}), mat4Identity()));
+            a.eyesLocal = mul(mat4Translation({0.0f, 0.0f, -0.19f}), mul(mat4Scaling({0.25f, 0.12f, 0.2f}), mat4Identity()));
+            a.uiLocal = mul(mat4Translation({0, 0, -0.2f}), mat4Identity());
+            a.barAnchorLocal = mul(mat4Translation({0, -0.131f, 0}), mat4Identity());
+            a.barLocal = mul(mat4Identity(), mat4Scaling({0.24f, float(0.0015), float(0.001)}));
+        }
+        agentColliderBase = int(colliders.size());
+        for (int i = 0; i < numAgents; ++i) {
+            Collider c;
+            c.kind = 1;
+            c.c = agents[i].kcc.pos;
+            colliders.push_back(c);
+        }
+    }
+
+    // ---------------------------------------------------------------- step (env.cpp:83-152)
+    void setAction(int agentIdx, int mask) { currAction[agentIdx] = mask; }
+
+    void step() {
+        std::fill(lastReward.begin(), lastReward.end(), 0.0f);
+        const float dt = lastFrameDurationSec;
+        for (int i = 0; i < numAgents; ++i) {
+            const int a = currAction[i];
+            Agent &agent = agents[i];
+            Vec3 acceleration{0, 0, 0};
+            if (a & A_Forward) acceleration += agent.forwardDirection();
+            else if (a & A_Backward) acceleration -= agent.forwardDirection();
+            if (a & A_Left) acceleration += agent.strafeLeftDirection();
+            else if (a & A_Right) acceleration -= agent.strafeLeftDirection();
+            if (a & A_LookLeft) agent.lookLeft(dt);
+            else if (a & A_LookRight) agent.lookRight(dt);
+            if (a & A_LookUp) agent.lookUp(dt);
+            else if (a & A_LookDown) agent.lookDown(dt);
+            agent.kcc.setAcceleration(acceleration, dt);
+            if (a & A_Jump) agent.jump();
+        }
+        // stepSimulation(dt, 1, dt): action interfaces in insertion (agent) order (env.cpp:126)
+        for (int i = 0; i < numAgents; ++i) {
+            agents[i].kcc.playerStep(colliders, agentColliderBase + i, simulationStepSeconds);
+            colliders[agentColliderBase + i].c = agents[i].kcc.pos;
+        }
+        for (auto &a : agents) a.updateTransform();
+
+        towerStep();
+
+        currEpisodeSec += lastFrameDurationSec;
+        updateUI();
+        if (currEpisodeSec >= episodeLengthSec()) done = true;
+        for (int i = 0; i < numAgents; ++i) currAction[i] = 0;
+        for (int i = 0; i < numAgents; ++i) totalReward[i] += lastReward[i];
+        ++numFrames;
+    }
+
+    float episodeLengthSec() const { return floatParams.at("episodeLengthSec") + 4.0f * float(platform->objectSpawnCoords.size()); }  // scenario_tower_building.cpp:263-266
+    float remainingTimeFraction() const { const float len = episodeLengthSec(); return std::max(0.0f, (len - currEpisodeSec) / len); }  // env.hpp:224-228
+    float trueObjective(int) const { return float(highestTower); }
+    void doneWithTimer(float remaining = 0.3f) { currEpisodeSec = std::max(currEpisodeSec, episodeLengthSec() - remaining); }
+
+    void updateUI() {  // scenario_default.hpp:164-186 ; UIElement::rescale :33-37
+        for (int i = 0; i < numAgents; ++i) {
+            Agent &a = agents[i];
+            const Vec3 required{remainingTimeFraction() * 0.24f, float(0.0015), float(0.001)};
+            const Vec3 scale = scalingOf(a.barLocal);
+            a.barLocal = mul(a.barLocal, mat4Scaling({required.x / scale.x, required.y / scale.y, required.z / scale.z}));
+        }
+    }
+
+    // reward plumbing (scenario.hpp:251-307)
+    float getReward(const std::string &name, int agentIdx) const { return rewardShaping[agentIdx].at(name); }
+    void rewardAgent(const std::string &name, int agentIdx, float multiplier) { lastReward[agentIdx] += getReward(name, agentIdx) * multiplier; }
+    float teamSpirit(int agentIdx) const { return getReward("teamSpirit", agentIdx); }
+    void rewardTeam(const std::string &name, int agentIdx, float multiplier) {
+        rewardAgent(name, agentIdx, multiplier * (1 - teamSpirit(agentIdx)));
+        for (int i = 0; i < numAgents; ++i) lastReward[i] += getReward(name, i) * teamSpirit(i) * multiplier / numAgents;
+    }
+
+    // ---------------------------------------------------------------- TowerBuilding step (scenario_tower_building.cpp:179-260)
+    void towerStep() {
+        for (int i = 0; i < numAgents; ++i)
+            if (currAction[i] & A_Interact) onInteractAction(i);
+        fallDetectionStep();
+        for (int i = 0; i < numAgents; ++i) {
+            if (carryingObject[i] >= 0) {
+                const Vec3 t = translationOf(agents[i].objectT);
+                VoxelCoords voxel = vg.grid.getCoords(t);
+                if (isInBuildingZone(voxel)) {
+                    if (!agentState[i].visitedBuildingZoneWithObject) {
+                        rewardTeam("towerVisitedBuildingZoneWithObject", i, 1);
+                        agentState[i].visitedBuildingZoneWithObject = true;
+                    }
+                }
+            }
+        }
+    }
+    bool isInBuildingZone(const VoxelCoords &c) const {
+        return c.x >= buildingZone.min.x && c.x < buildingZone.max.x && c.z >= buildingZone.min.z && c.z < buildingZone.max.z;
+    }
+    static float buildingRewardCoeffForHeight(float height) {
+        auto res = height * 0.05f;
+        res += std::min(0.05f * powf(2, height), 20.0f);
+        return res;
+    }
+    float calculateTowerReward() const {
+        float reward = 0.0f;
+        for (auto &pos : objectsInBuildingZone) reward += buildingRewardCoeffForHeight(float(pos.y));
+        return reward;
+    }
+    void placedObject(int agentIdx, const VoxelCoords &voxel) {
+        if (isInBuildingZone(voxel)) objectsInBuildingZone.insert(voxel);
+        auto newReward = calculateTowerReward();
+        auto rewardDelta = newReward - currBuildingZoneReward;
+        currBuildingZoneReward = newReward;
+        rewardTeam("towerBuildingReward", agentIdx, rewardDelta);
+        highestTower = std::max(highestTower, voxel.y - buildingZone.min.y + 1);
+    }
+    void pickedObject(int agentIdx, const VoxelCoords &voxel) {
+        if (isInBuildingZone(voxel)) objectsInBuildingZone.erase(voxel);
+        if (!agentState[agentIdx].pickedUpObject) {
+            rewardAgent("towerPickedUpObject", agentIdx, 1);
+            agentState[agentIdx].pickedUpObject = true;
+        }
+    }
+
+    void onInteractAction(int agentIdx) {  // component_object_stacking.hpp:58-168
+        Agent &agent = agents[agentIdx];
+        const float carryingScale = 0.78f, carryingScaleInverse = 1.0f / carryingScale;
+        if (carryingObject[agentIdx] >= 0) {
+            const int obj = carryingObject[agentIdx];
+            const Vec3 t = translationOf(objectAbs(obj));
+            VoxelCoords voxel = vg.grid.getCoords(t);
+            auto voxelPtr = vg.grid.get(voxel);
+            bool collidesWithAgent = false;
+            for (int j = 0; j < numAgents; ++j) {
+                if (j == agentIdx) continue;
+                VoxelCoords c = vg.grid.getCoords(translationOf(agents[j].objectT));
+                if (voxel == c) { collidesWithAgent = true; break; }
+            }
+            const bool empty = !voxelPtr || (voxelPtr->empty() && voxelPtr->physicsObject < 0);
+            if (empty && !collidesWithAgent && isInBuildingZone(voxel)) {  // canPlaceObject: scenario_tower_building.cpp:201-204
+                while (true) {
+                    VoxelCoords below{voxel.x, voxel.y - 1, voxel.z};
+                    if (below.y < -30) break;
+                    auto belowPtr = vg.grid.get(below);
+                    if (belowPtr && (belowPtr->solid() || belowPtr->physicsObject >= 0)) break;
+                    else voxel = below;
+                }
+                if (!vg.grid.hasVoxel(voxel)) vg.grid.set(voxel, Voxel{});
+                vg.grid.get(voxel)->physicsObject = obj;
+                MovableObject &o = objects[obj];
+                o.parentAgent = -1;
+                const Vec3 scaling = scalingOf(o.local);
+                o.local = mat4Identity();
+                o.local = mul(mat4Scaling({scaling.x * carryingScaleInverse, scaling.y * carryingScaleInverse, scaling.z * carryingScaleInverse}), o.local);
+                o.local = mul(mat4Translation({float(voxel.x) + 0.5f, float(voxel.y) + 0.5f, float(voxel.z) + 0.5f}), o.local);
+                syncPose(obj);
+                colliders[o.collider].enabled = !colliders[o.collider].enabled;  // toggleCollision
+                carryingObject[agentIdx] = -1;
+                placedObject(agentIdx, voxel);
+            }
+        } else {
+            const Vec3 pickup = translationOf(agent.pickupAbs());
+            VoxelCoords voxel = toVoxel(pickup);
+            VoxelCoords voxelAbove{voxel.x, voxel.y + 1, voxel.z};
+            int pickupHeight = 0, maxPickupHeight = 1;
+            while (pickupHeight <= maxPickupHeight) {
+                auto voxelPtr = vg.grid.get(voxel), voxelAbovePtr = vg.grid.get(voxelAbove);
+                bool hasObjectAbove = voxelAbovePtr && voxelAbovePtr->physicsObject >= 0;
+                if (voxelPtr && voxelPtr->physicsObject >= 0 && !hasObjectAbove) {
+                    const int obj = voxelPtr->physicsObject;
+                    MovableObject &o = objects[obj];
+                    colliders[o.collider].enabled = !colliders[o.collider].enabled;
+                    const Vec3 scaling = scalingOf(o.local);
+                    o.local = mat4Identity();
+                    o.local = mul(mat4Scaling({scaling.x * carryingScale, scaling.y * carryingScale, scaling.z * carryingScale}), o.local);
+                    o.local = mul(mat4Translation({0.0f, -0.3f, 0.0f}), o.local);
+                    o.parentAgent = agentIdx;
+                    carryingObject[agentIdx] = obj;
+                    voxelPtr->physicsObject = -1;
+                    pickedObject(agentIdx, voxel);
+                    break;
+                } else {
+                    voxel = voxelAbove;
+                    voxelAbove = VoxelCoords{voxel.x, voxel.y + 1, voxel.z};
+                }
+                ++pickupHeight;
+            }
+        }
+    }
+
+    void fallDetectionStep() {  // component_fall_detection.hpp:33-56
+        for (int i = 0; i < numAgents; ++i) {
+            if (translationOf(agents[i].objectT).y < -20) {
+                Vec3 p = agentInitialPositions[i];
+                auto v = vg.grid.getWithVector(p);
+                while (v && !v->empty() && p.y < 1000) { p.y += 1; v = vg.grid.getWithVector(p); }
+                const float halfVoxel = vg.grid.getVoxelSize() / 2;
+                agents[i].kcc.warp({p.x + halfVoxel, p.y + halfVoxel, p.z + halfVoxel});
+                colliders[agentColliderBase + i].c = agents[i].kcc.pos;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- render interface
+    // Instances in V4R draw order: mesh type major (meshIndices is a std::map<DrawableType,int>), insertion order minor
+    // (v4r_env_renderer.cpp:267-279). Model matrices are the drawables' absoluteTransformationMatrix() as computed by
+    // SceneGraph::Object::setClean(objects) (right-to-left composition up the parent chain, v4r_env_renderer.cpp:319-335).
+    std::vector<Instance> instances() const {
+        std::vector<Instance> out;
+        for (auto &sb : staticBoxes)
+            if (sb.type & VOXEL_OPAQUE)
+                out.push_back({MESH_BOX, paletteIndex(sb.color), mul(mat4Translation(staticBoxTranslation(sb.bb, 1.0f)), mul(mat4Scaling(staticBoxScale(sb.bb, 1.0f)), mat4Identity()))});
+        for (auto &ts : terrainSlabs) {  // layout_utils.cpp:53-68
+            const Vec3 scale = Vec3{float(ts.bb.max.x - ts.bb.min.x), 1.0f, float(ts.bb.max.z - ts.bb.min.z)} * 1.0f;
+            if (scale.x > 0) {
+                const Vec3 pos{ts.bb.min.x * 1.0f + scale.x / 2, ts.bb.min.y * 1.0f, ts.bb.min.z * 1.0f + scale.z / 2};
+                Mat4 m = mul(mat4Scaling({0.5f, 0.025f, 0.5f}), mat4Identity());
+                m = mul(mat4Scaling(scale), m);
+                m = mul(mat4Translation({0.0f, 0.025f, 0.0f}), m);
+                m = mul(mat4Translation(pos), m);
+                out.push_back({MESH_BOX, paletteIndex(terrainColor(ts.terrain)), m});
+            }
+        }
+        for (int i = 0; i < int(objects.size()); ++i) {
+            const MovableObject &o = objects[i];
+            Mat4 m = o.local;
+            if (o.parentAgent >= 0) {
+                const Agent &a = agents[o.parentAgent];
+                m = mul(a.objectT, mul(a.cameraLocal, mul(a.pickupLocal, o.local)));
+            }
+            out.push_back({MESH_BOX, o.color, m});
+        }
+        for (auto &a : agents) out.push_back({MESH_BOX, paletteIndex(AGENT_EYES), mul(a.objectT, mul(a.cameraLocal, a.eyesLocal))});
+        for (auto &a : agents) out.push_back({MESH_BOX, paletteIndex(BLUE), mul(a.objectT, mul(a.cameraLocal, mul(a.uiLocal, mul(a.barAnchorLocal, a.barLocal))))});
+        for (auto &a : agents) out.push_back({MESH_CAPSULE, a.color, mul(a.objectT, a.bodyLocal)});
+        return out;
+    }
+    Mat4 viewMatrix(int agentIdx) const { return inverted(agents[agentIdx].cameraAbs()); }  // Camera::cameraMatrix
+
+public:
+    int scenario = S_TOWER;
+    int numAgents;
+    FloatParams floatParams;
+    std::vector<RewardShaping> rewardShaping;
+    Rng rng{std::random_device{}()};
+
+    bool done = false;
+    int numFrames = 0;
+    float currEpisodeSec = 0;
+    float simulationStepSeconds = 1.0f / 15.0f, lastFrameDurationSec = 1.0f / 15.0f;
+    std::vector<int> currAction;
+    std::vector<float> lastReward, totalReward;
+
+    std::vector<Agent> agents;
+    std::vector<Collider> colliders;
+    int agentColliderBase = 0;
+    std::vector<MovableObject> objects;
+    std::vector<StaticBox> staticBoxes;
+    std::vector<TerrainSlab> terrainSlabs;
+
+    VoxelGridComponent vg;
+    std::vector<int> carryingObject;
+    std::vector<Vec3> agentInitialPositions;
+    std::unique_ptr<Node> levelRoot;
+    std::unique_ptr<TowerPlatform> platform;
+
+    struct TowerAgentState { bool pickedUpObject = false, visitedBuildingZoneWithObject = false; };
+    std::vector<TowerAgentState> agentState;
+    int highestTower = 0;
+    BoundingBox buildingZone;
+    std::unordered_set<VoxelCoords, VoxelHash> objectsInBuildingZone;  // persists across episodes (clear() keeps the buckets)
+    float currBuildingZoneReward = 0.0f;
+};
+
+}  // namespace orc
