@@ -1,0 +1,112 @@
+/* megaverse_b200 -- thin C ABI of the B200 batched voxel-world step + render engine.
+ *
+ * Drop-in boundary for the reference's per-step hot path.  Each entry point replaces what the reference's pybind11
+ * class MegaverseGym (src/libs/bindings/megaverse.cpp:36-263) reaches through VectorEnv (src/libs/env/src/vector_env.cpp)
+ * and EnvRenderer (src/libs/env/include/env/env_renderer.hpp:12-32).  Plain pointers and sizes only; no torch / pybind
+ * types.  Every call returns 0 on success or a negative MV_ERR_* code; mv_last_error() gives the message.  The engine
+ * never calls exit() (the reference's TLOG(FATAL) does, src/libs/util/src/tiny_logger.cpp:109-113).
+ *
+ * Threading: calls on one handle must be serialised by the caller (the reference holds the GIL for every call).
+ * Observation memory is owned by the engine and reused every step, exactly like the reference's renderer buffer
+ * (megaverse.cpp:139-143): pointers stay valid until mv_close, contents until the next mv_step / mv_reset.
+ */
+#ifndef MEGAVERSE_B200_H
+#define MEGAVERSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mv_engine *mv_handle;
+
+#define MV_OK 0
+#define MV_ERR_ARG -1          /* bad argument (unknown scenario, bad sizes, unknown reward key -> std::out_of_range in the reference) */
+#define MV_ERR_CUDA -2         /* CUDA runtime failure, or no CUDA device: the product has NO CPU fallback */
+#define MV_ERR_CAPACITY -3     /* a generated level exceeds the engine's fixed capacities */
+#define MV_ERR_STATE -4        /* call order (e.g. step before reset) */
+
+/* MegaverseGym::MegaverseGym (megaverse.cpp:38-58).  num_threads = host level-generation workers (the reference's
+ * numSimulationThreads drove Bullet on the CPU, vector_env.cpp:6-40).  device = CUDA ordinal. */
+int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents_per_env, int num_threads, int device,
+              const char *const *param_keys, const float *param_vals, int nparams, mv_handle *out);
+/* message of the last failed call; pass NULL for a failed mv_create */
+const char *mv_last_error(mv_handle h);
+
+/* MegaverseGym::seed (megaverse.cpp:60-69): master mt19937 -> one randRange(0,1<<30) per env */
+int mv_seed(mv_handle h, int seed);
+/* Env::seed for one env (megaverse_test_app.cpp:250-254 seeds env i with 42+i) */
+int mv_seed_env(mv_handle h, int env, int seed);
+
+/* MegaverseGym::reset -> VectorEnv::reset (vector_env.cpp:110-120): new episode in every env + first render */
+int mv_reset(mv_handle h);
+
+/* MegaverseGym::setActions for all agents at once: masks[env*A + agent] = Action bit mask (env.hpp:22-42).
+ * mv_encode_action converts one 6-tuple of Discrete heads {3,3,3,2,2,3} exactly like megaverse.cpp:100-116. */
+int mv_set_actions(mv_handle h, const int32_t *masks);
+int32_t mv_encode_action(const int32_t *heads6);
+
+/* MegaverseGym::step -> VectorEnv::step (vector_env.cpp:89-108): physics + scenario logic, reset of finished envs, render.
+ * Synchronous: on return observations / rewards / dones are in host memory. */
+int mv_step(mv_handle h);
+
+/* MegaverseGym::getObservation (megaverse.cpp:139-143): uint8[N][h][w][4] RGBA, view index env*A+agent, host memory */
+int mv_obs_host(mv_handle h, const uint8_t **out);
+/* float32[N][h][w] view-space depth (V4R depth output definition), only when option "depth" is 1 */
+int mv_depth_host(mv_handle h, const float **out);
+/* MegaverseGym::getLastRewards (megaverse.cpp:128-137): float[N] */
+int mv_rewards(mv_handle h, const float **out);
+/* VectorEnv::done (vector_env.hpp): uint8[num_envs] */
+int mv_dones(mv_handle h, const uint8_t **out);
+/* VectorEnv::trueObjectives / MegaverseGym::trueObjective (megaverse.cpp:209-212): float[N] */
+int mv_true_objectives(mv_handle h, const float **out);
+
+/* MegaverseGym::getRewardShaping / setRewardShaping (megaverse.cpp:214-222).  get: fills up to cap entries, returns the
+ * number of keys in *n.  Key strings are owned by the engine. */
+int mv_get_reward_shaping(mv_handle h, int env, int agent, const char **keys, float *vals, int cap, int *n);
+int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *keys, const float *vals, int n);
+
+/* options: "depth" (0/1, before first reset), "tri_cap" (rasteriser triangle capacity), "obs_to_host" (0/1: whether
+ * mv_step copies the observation tensor to host memory; 1 by default) */
+int mv_set_option(mv_handle h, const char *key, int value);
+
+/* Device-resident path: the caller's consumer reads the tensors in HBM.
+ * mv_step_device: like mv_step but takes the action masks from DEVICE memory (NULL = the engine's own buffer, see
+ * mv_actions_device) and leaves the observation tensor on the device; rewards/dones still land on the host. */
+int mv_step_device(mv_handle h, const int32_t *d_masks);
+int mv_actions_device(mv_handle h, int32_t **d_masks);
+int mv_obs_device(mv_handle h, uint8_t **d_obs);
+int mv_depth_device(mv_handle h, float **d_depth);
+int mv_rewards_device(mv_handle h, float **d_rewards);
+int mv_dones_device(mv_handle h, uint8_t **d_dones);
+/* the CUDA stream (cudaStream_t) all engine work is ordered on */
+int mv_stream(mv_handle h, void **stream);
+
+/* sticky per-env fault bits ORed over all envs (MV_FAULT_* in mv_types.h); 0 = healthy */
+int mv_faults(mv_handle h, int32_t *out);
+/* number of kernels the engine launched since creation */
+int mv_kernel_launches(mv_handle h, int64_t *out);
+/* device time of the last step's kernels in milliseconds: [0] step kernel, [1] raster kernel (CUDA events) */
+int mv_last_kernel_ms(mv_handle h, float *out2);
+
+/* MegaverseGym::close (megaverse.cpp:224-243) */
+int mv_close(mv_handle h);
+
+/* ---- introspection for parity tests (same layouts as the oracle's orc_get_* in oracle/orc_api.cpp) ---- */
+int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap);
+int mv_debug_get_state(mv_handle h, int env, float *out, int cap);
+int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap);
+int mv_debug_get_instances(mv_handle h, int env, float *out, int cap);
+int mv_debug_get_view(mv_handle h, int env, int agent, float *out16);
+/* render caller-supplied instances (18 floats each: mesh, colour, 16 model) with one view matrix through the CUDA
+ * rasteriser: rgba uint8[h][w][4], depth float[h][w] or NULL.  Host pointers. */
+int mv_debug_render_instances(const float *view16, const float *inst18, int n, int w, int h, uint8_t *rgba, float *depth);
+/* libstdc++ unordered_set iteration-order emulation (bzset.h): ops[i] = {op(0 insert,1 erase,2 clear), x, y, z};
+ * writes the final iteration order as xyz triples, returns the element count */
+int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

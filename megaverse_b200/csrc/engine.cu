@@ -1,0 +1,748 @@
+// Host engine behind the C ABI (include/megaverse_b200.h): owns the HBM state, the host level generators and their
+// worker pool, and launches the two kernels of a step on one CUDA stream.
+//
+//   mv_step  =  [H2D actions] -> stepKernel (physics + scenario + in-kernel reset + instance lists)
+//                             -> rasterKernel (obs tensor) -> [D2H obs/rewards/dones] -> schedule next-level generation
+//
+// There is no host synchronisation between physics, episode reset and rendering (the reference resets finished envs
+// serially on the caller thread between the two, vector_env.cpp:94-105): every env always has its NEXT level pre-staged
+// in HBM (no RNG draw happens during an episode, so the next level only depends on the env's RNG state after the
+// previous generation), and the step kernel flips to it by itself when the episode ends.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <queue>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/megaverse_b200.h"
+#include "hostmath.hpp"
+#include "levelgen.hpp"
+#include "raster_kernel.cuh"
+#include "step_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_createError;
+
+#define MV_CUDA(call)                                                                                             \
+    do {                                                                                                          \
+        cudaError_t err__ = (call);                                                                               \
+        if (err__ != cudaSuccess) {                                                                               \
+            setError(std::string(#call) + ": " + cudaGetErrorString(err__));                                      \
+            return MV_ERR_CUDA;                                                                                   \
+        }                                                                                                         \
+    } while (0)
+
+class WorkerPool {
+public:
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; ++i)
+            threads_.emplace_back([this] {
+                for (;;) {
+                    std::function<void()> job;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                        if (stop_ && q_.empty()) return;
+                        job = std::move(q_.front());
+                        q_.pop();
+                    }
+                    job();
+                    {
+                        std::lock_guard<std::mutex> lk(m_);
+                        --pending_;
+                    }
+                    done_.notify_all();
+                }
+            });
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> lk(m_); q_.push(std::move(f)); ++pending_; }
+        cv_.notify_one();
+    }
+    void waitAll() {
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+    }
+
+private:
+    std::vector<std::thread> threads_;
+    std::queue<std::function<void()>> q_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) { n = count; return cudaMalloc(reinterpret_cast<void **>(&p), sizeof(T) * (count ? count : 1)); }
+    void free() { if (p) cudaFree(p); p = nullptr; }
+};
+template <typename T> struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) { n = count; return cudaMallocHost(reinterpret_cast<void **>(&p), sizeof(T) * (count ? count : 1)); }
+    void free() { if (p) cudaFreeHost(p); p = nullptr; }
+};
+
+}  // namespace
+
+struct mv_engine {
+    std::string error;
+    void setError(const std::string &e) { error = e; }
+
+    int scenario = 0, W = 0, H = 0, E = 0, A = 0, N = 0, threads = 1, device = 0;
+    mv::FloatParams params;
+    std::vector<std::vector<std::pair<std::string, float>>> shaping;  // per agent view: ordered key list (std::map order)
+    std::vector<mv::LevelGenerator> gens;
+    std::mt19937 master{std::random_device{}()};
+    std::unique_ptr<WorkerPool> pool;
+
+    int gridCells = 0, gridWords = 0;
+    int triCap = 608;
+    bool wantDepth = false, obsToHost = true, didReset = false;
+    MvConsts consts{};
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float lastMs[2] = {0, 0};
+    int64_t launches = 0;
+
+    DevBuf<MvLevel> d_levels;
+    DevBuf<uint32_t> d_solid;
+    DevBuf<uint8_t> d_objGrid;
+    DevBuf<MvEnvState> d_envs;
+    DevBuf<MvAgent> d_agents;
+    DevBuf<MvObject> d_objects;
+    DevBuf<MvInstance> d_inst;
+    DevBuf<int32_t> d_instCounts;
+    DevBuf<float> d_views;
+    DevBuf<int32_t> d_actions;
+    DevBuf<float> d_rtable;
+    DevBuf<float> d_rewards;
+    DevBuf<uint8_t> d_dones;
+    DevBuf<float> d_trueObj;
+    DevBuf<uint8_t> d_obs;
+    DevBuf<float> d_depth;
+    DevBuf<int32_t> d_faults;
+
+    PinBuf<MvLevel> h_levels;      // [E][2] staging mirror
+    PinBuf<uint32_t> h_solid;      // [E][2][gridWords]
+    PinBuf<int32_t> h_actions;
+    PinBuf<float> h_rtable;
+    PinBuf<float> h_rewards;
+    PinBuf<uint8_t> h_dones;
+    PinBuf<float> h_trueObj;
+    PinBuf<uint8_t> h_obs;
+    PinBuf<float> h_depth;
+    PinBuf<int32_t> h_faults;
+
+    std::vector<int> hostSlot, hostEpisode;   // mirrors of the device's live slot / episode index
+    std::vector<int> pendingUpload;           // env ids whose freshly generated next level waits for H2D
+    std::vector<std::string> genErrors;
+    std::mutex genMutex;
+    bool rtableDirty = true;
+
+    // ------------------------------------------------------------------ level generation scheduling
+    // generate the level for episode `serial` of env e into staging slot s (worker thread)
+    void scheduleGen(int e, int s, int serial) {
+        pool->submit([this, e, s, serial] {
+            mv::LevelOut out;
+            try {
+                gens[size_t(e)].generate(out, serial, gridCells);
+            } catch (const std::exception &ex) {
+                std::lock_guard<std::mutex> lk(genMutex);
+                genErrors.push_back(ex.what());
+                return;
+            }
+            std::memcpy(&h_levels.p[size_t(e) * 2 + s], &out.level, sizeof(MvLevel));
+            uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * gridWords;
+            std::memset(dst, 0, sizeof(uint32_t) * gridWords);
+            std::memcpy(dst, out.solid.data(), sizeof(uint32_t) * std::min(out.solid.size(), size_t(gridWords)));
+            std::lock_guard<std::mutex> lk(genMutex);
+            pendingUpload.push_back(e * 2 + s);
+        });
+    }
+    int flushUploads() {
+        pool->waitAll();
+        std::vector<int> todo;
+        {
+            std::lock_guard<std::mutex> lk(genMutex);
+            if (!genErrors.empty()) { setError("level generation failed: " + genErrors.front()); genErrors.clear(); return MV_ERR_CAPACITY; }
+            todo.swap(pendingUpload);
+        }
+        for (int id : todo) {
+            MV_CUDA(cudaMemcpyAsync(&d_levels.p[id], &h_levels.p[id], sizeof(MvLevel), cudaMemcpyHostToDevice, stream));
+            MV_CUDA(cudaMemcpyAsync(d_solid.p + size_t(id) * gridWords, h_solid.p + size_t(id) * gridWords, sizeof(uint32_t) * gridWords, cudaMemcpyHostToDevice, stream));
+        }
+        return MV_OK;
+    }
+
+    void fillRtableRow(int view) {
+        float *row = h_rtable.p + size_t(view) * MV_R_COUNT;
+        for (int i = 0; i < MV_R_COUNT; ++i) row[i] = 0.0f;
+        for (auto &kv : shaping[size_t(view)]) {
+            const int slot = mv::rewardSlot(scenario, kv.first);
+            if (slot >= 0) row[slot] = kv.second;
+        }
+    }
+
+    int launchStep(const int32_t *dActions, bool forceReset) {
+        mvk::StepParams sp;
+        sp.levels = d_levels.p; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
+        sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
+        sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
+        sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
+        sp.k = consts;
+        const int warpsPerBlock = 2;
+        const int blocks = (E + warpsPerBlock - 1) / warpsPerBlock;
+        const size_t smem = sizeof(mvk::WarpShared) * warpsPerBlock;
+        MV_CUDA(cudaEventRecord(ev[0], stream));
+        mvk::stepKernel<<<blocks, warpsPerBlock * 32, smem, stream>>>(sp);
+        MV_CUDA(cudaGetLastError());
+        MV_CUDA(cudaEventRecord(ev[1], stream));
+        mvr::RasterParams rp;
+        rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = MV_MAX_INSTANCES;
+        rp.obs = d_obs.p; rp.depth = wantDepth ? d_depth.p : nullptr; rp.faults = d_faults.p;
+        rp.E = E; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
+        rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
+        mvr::rasterKernel<<<N, 256, rasterSmem(), stream>>>(rp);
+        MV_CUDA(cudaGetLastError());
+        MV_CUDA(cudaEventRecord(ev[2], stream));
+        launches += 2;
+        return MV_OK;
+    }
+    size_t rasterSmem() const {
+        const int tiles = (W / 32) * (H / 4);
+        return size_t(triCap) * sizeof(mvr::TriRec) + size_t(tiles) * size_t((triCap + 31) / 32) * 4;
+    }
+
+    // after a step (or forced reset): flip host mirrors for finished envs and start generating the level after next
+    void afterFlip(const uint8_t *flipped) {
+        for (int e = 0; e < E; ++e) {
+            if (!flipped || flipped[e]) {
+                hostSlot[size_t(e)] ^= 1;
+                hostEpisode[size_t(e)] += 1;
+                scheduleGen(e, hostSlot[size_t(e)] ^ 1, hostEpisode[size_t(e)] + 1);
+            }
+        }
+    }
+
+    int finishStep(bool copyObs) {
+        MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
+        MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
+        MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
+        if (copyObs) {
+            MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
+            if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
+        }
+        MV_CUDA(cudaStreamSynchronize(stream));
+        cudaEventElapsedTime(&lastMs[0], ev[0], ev[1]);
+        cudaEventElapsedTime(&lastMs[1], ev[1], ev[2]);
+        return MV_OK;
+    }
+
+    int stepCommon(const int32_t *dActions, bool copyObs) {
+        if (!didReset) { setError("mv_step before mv_reset"); return MV_ERR_STATE; }
+        int rc = flushUploads();
+        if (rc) return rc;
+        if (rtableDirty) {
+            MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
+            rtableDirty = false;
+        }
+        rc = launchStep(dActions, false);
+        if (rc) return rc;
+        rc = finishStep(copyObs);
+        if (rc) return rc;
+        afterFlip(h_dones.p);
+        return MV_OK;
+    }
+
+    void freeAll() {
+        if (pool) { pool->waitAll(); pool.reset(); }
+        d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
+        d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
+        h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
+        h_faults.free();
+        for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    }
+};
+
+namespace {
+
+const uint32_t kPaletteRgb[22] = {0xffdd3c, 0x3bb372, 0x50c878, 0x2eb5d0, 0xadd8e6, 0x3a7fa6, 0x2c3e50, 0xffb400, 0xb3b3b3, 0x555555, 0x222222,
+                                  0xffffff, 0xff0000, 0xffa770, 0xd468ee, 0xffe6e6, 0xffffe6, 0xccffcc, 0xe6ecff, 0xd9d9d9, 0xf2e6ff, 0xffebcc};
+
+int uploadPalette(mv_engine *h) {
+    float pal[22][3];
+    for (int i = 0; i < 22; ++i) {  // toRgbf: byte / 255 (util/magnum.hpp:25-32)
+        pal[i][0] = float((kPaletteRgb[i] >> 16) & 255) / 255.0f;
+        pal[i][1] = float((kPaletteRgb[i] >> 8) & 255) / 255.0f;
+        pal[i][2] = float(kPaletteRgb[i] & 255) / 255.0f;
+    }
+    cudaError_t err = cudaMemcpyToSymbol(mvr::c_palette, pal, sizeof(pal));
+    if (err != cudaSuccess) { h->setError(std::string("palette upload: ") + cudaGetErrorString(err)); return MV_ERR_CUDA; }
+    return MV_OK;
+}
+
+void fillConsts(MvConsts &k, int W, int H) {
+    k.dt = 1.0f / 15.0f;                              // env.hpp:160-161
+    mvh::yawBasis(3.5f * k.dt, k.look_left);          // agent.cpp:100-108,128-133
+    mvh::yawBasis(-3.5f * k.dt, k.look_right);
+    k.max_slope_cos = mvh::crcos(45.0f * (3.14159265358979323846f / 180.0f));
+    const float aspect = float(W) / float(H);
+    const float halfTan = mvh::crtan((100.0f * 0.01745329251994329576923690768489f) / 2.0f);
+    const float nearZ = 0.01f, farZ = 120.0f;
+    k.p00 = 1.0f / halfTan;
+    k.p11 = -aspect / halfTan;
+    k.p22 = farZ / (nearZ - farZ);
+    k.p32 = farZ * nearZ / (nearZ - farZ);
+}
+
+int setKernelAttrs(mv_engine *h) {
+    cudaError_t err = cudaFuncSetAttribute(mvk::stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(mvk::WarpShared) * 4));
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(mvr::rasterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->rasterSmem()));
+    if (err != cudaSuccess) { h->setError(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err)); return MV_ERR_CUDA; }
+    return MV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mv_last_error(mv_handle h) { return h ? h->error.c_str() : g_createError.c_str(); }
+
+int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, int num_threads, int device, const char *const *keys, const float *vals,
+              int nparams, mv_handle *out) {
+    if (!out) return MV_ERR_ARG;
+    *out = nullptr;
+    const int sc = scenario ? mv::scenarioFromName(scenario) : -1;
+    if (sc < 0) { g_createError = std::string("unknown scenario ") + (scenario ? scenario : "(null)"); return MV_ERR_ARG; }
+    if (w <= 0 || h <= 0 || w % 32 != 0 || h % 4 != 0 || (w / 32) * (h / 4) > 128) { g_createError = "render size must be a multiple of 32x4 with at most 128 tiles"; return MV_ERR_ARG; }
+    if (num_envs <= 0 || num_agents <= 0 || num_agents > MV_MAX_AGENTS) { g_createError = "bad num_envs / num_agents_per_env"; return MV_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_createError = "no CUDA device: megaverse_b200 has no CPU fallback"; return MV_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { g_createError = "bad CUDA device ordinal"; return MV_ERR_ARG; }
+    auto *e = new mv_engine;
+    auto fail = [&](int code) { g_createError = e->error; e->freeAll(); delete e; return code; };
+    if (cudaSetDevice(device) != cudaSuccess) { e->setError("cudaSetDevice failed"); return fail(MV_ERR_CUDA); }
+    e->scenario = sc; e->W = w; e->H = h; e->E = num_envs; e->A = num_agents; e->N = num_envs * num_agents; e->device = device;
+    e->threads = num_threads < 1 ? 1 : num_threads;
+    e->params = mv::defaultFloatParams(sc);
+    for (int i = 0; i < nparams; ++i) e->params[keys[i]] = vals[i];
+    {
+        auto def = mv::defaultRewardShaping(sc);
+        std::map<std::string, float> m{{"teamSpirit", 0.0f}};
+        for (auto &kv : def) m[kv.first] = kv.second;
+        std::vector<std::pair<std::string, float>> ordered(m.begin(), m.end());
+        e->shaping.assign(size_t(e->N), ordered);
+    }
+    for (int i = 0; i < e->E; ++i) e->gens.emplace_back(sc, e->A, e->params);
+    e->pool.reset(new WorkerPool(e->threads));
+    // dense grid capacity: TowerBuilding rooms are at most 29 x (6+18) x 24 (scenario_tower_building.cpp:21-34)
+    e->gridCells = ((30 * 25 * 25 + 127) / 128) * 128;
+    e->gridWords = e->gridCells / 32;
+    fillConsts(e->consts, w, h);
+
+    auto ck = [&](cudaError_t err, const char *what) { if (err != cudaSuccess) { e->setError(std::string(what) + ": " + cudaGetErrorString(err)); return false; } return true; };
+    const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
+    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream");
+    for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
+    ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
+         ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
+         ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 2), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
+         ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
+         ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults");
+    ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
+         ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
+         ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults");
+    if (!ok) return fail(MV_ERR_CUDA);
+    std::memset(e->h_actions.p, 0, sizeof(int32_t) * N);
+    std::memset(e->h_rewards.p, 0, sizeof(float) * N);
+    std::memset(e->h_dones.p, 0, E);
+    std::memset(e->h_trueObj.p, 0, sizeof(float) * N);
+    std::memset(e->h_obs.p, 0, N * px * 4);
+    for (size_t v = 0; v < N; ++v) e->fillRtableRow(int(v));
+    ok = ck(cudaMemset(e->d_trueObj.p, 0, sizeof(float) * N), "memset") && ck(cudaMemset(e->d_faults.p, 0, sizeof(int32_t) * E), "memset") &&
+         ck(cudaMemset(e->d_actions.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_agents.p, 0, sizeof(MvAgent) * N), "memset") &&
+         ck(cudaMemset(e->d_objects.p, 0, sizeof(MvObject) * E * MV_MAX_OBJECTS), "memset");
+    if (!ok) return fail(MV_ERR_CUDA);
+    if (uploadPalette(e) != MV_OK) return fail(MV_ERR_CUDA);
+    if (setKernelAttrs(e) != MV_OK) return fail(MV_ERR_CUDA);
+    *out = e;
+    return MV_OK;
+}
+
+int mv_set_option(mv_handle h, const char *key, int value) {
+    if (!h || !key) return MV_ERR_ARG;
+    const std::string k = key;
+    if (k == "depth") {
+        if (h->didReset) { h->setError("option depth must be set before the first reset"); return MV_ERR_STATE; }
+        h->wantDepth = value != 0;
+        if (h->wantDepth && !h->d_depth.p) {
+            const size_t cnt = size_t(h->N) * h->W * h->H;
+            if (h->d_depth.alloc(cnt) != cudaSuccess || h->h_depth.alloc(cnt) != cudaSuccess) { h->setError("depth allocation failed"); return MV_ERR_CUDA; }
+        }
+        return MV_OK;
+    }
+    if (k == "tri_cap") {
+        if (value < 64 || value > 1280) { h->setError("tri_cap out of range [64,1280]"); return MV_ERR_ARG; }
+        h->triCap = value;
+        return setKernelAttrs(h);
+    }
+    if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
+    h->setError("unknown option " + k);
+    return MV_ERR_ARG;
+}
+
+static void regenerateNext(mv_handle h) {
+    // (re)build every env's pre-staged next level from its current RNG state
+    for (int e = 0; e < h->E; ++e) h->scheduleGen(e, h->hostSlot[size_t(e)] ^ 1, h->hostEpisode[size_t(e)] + 1);
+}
+
+static void ensureMirrors(mv_handle h) {
+    if (h->hostSlot.empty()) {
+        h->hostSlot.assign(size_t(h->E), 1);      // first flip lands on slot 0
+        h->hostEpisode.assign(size_t(h->E), -1);  // ... as episode 0
+    }
+}
+
+int mv_seed(mv_handle h, int seed) {
+    if (!h) return MV_ERR_ARG;
+    h->pool->waitAll();
+    h->master.seed((unsigned long)seed);
+    for (int e = 0; e < h->E; ++e) h->gens[size_t(e)].seed((unsigned long)std::uniform_int_distribution<>{0, (1 << 30) - 1}(h->master));
+    if (h->didReset) {  // the staged next levels were drawn from the old streams: redo them
+        { std::lock_guard<std::mutex> lk(h->genMutex); h->pendingUpload.clear(); }
+        regenerateNext(h);
+    }
+    return MV_OK;
+}
+
+int mv_seed_env(mv_handle h, int env, int seed) {
+    if (!h || env < 0 || env >= h->E) return MV_ERR_ARG;
+    h->pool->waitAll();
+    h->gens[size_t(env)].seed((unsigned long)seed);
+    if (h->didReset) h->scheduleGen(env, h->hostSlot[size_t(env)] ^ 1, h->hostEpisode[size_t(env)] + 1);
+    return MV_OK;
+}
+
+int mv_reset(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    ensureMirrors(h);
+    if (!h->didReset) {
+        // initial device state: slot 1 / episode -1 so that the forced flip lands on (slot 0, episode 0)
+        std::vector<MvEnvState> init(size_t(h->E));
+        std::memset(init.data(), 0, sizeof(MvEnvState) * init.size());
+        for (auto &s : init) { s.slot = 1; s.episode_idx = -1; mvBzInit(s); }
+        if (cudaMemcpy(h->d_envs.p, init.data(), sizeof(MvEnvState) * init.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->setError("env init upload failed"); return MV_ERR_CUDA; }
+        regenerateNext(h);
+        h->didReset = true;
+    }
+    int rc = h->flushUploads();
+    if (rc) return rc;
+    if (h->rtableDirty) {
+        if (cudaMemcpyAsync(h->d_rtable.p, h->h_rtable.p, sizeof(float) * h->N * MV_R_COUNT, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("rtable upload failed"); return MV_ERR_CUDA; }
+        h->rtableDirty = false;
+    }
+    rc = h->launchStep(h->d_actions.p, true);
+    if (rc) return rc;
+    rc = h->finishStep(h->obsToHost);
+    if (rc) return rc;
+    h->afterFlip(nullptr);
+    return MV_OK;
+}
+
+int32_t mv_encode_action(const int32_t *heads6) {  // megaverse.cpp:100-116 with Env::actionSpaceSizes {3,3,3,2,2,3}
+    static const int sizes[6] = {3, 3, 3, 2, 2, 3};
+    int idx = 0, mask = 0;
+    for (int i = 0; i < 6; ++i) {
+        if (heads6[i] > 0) mask |= 1 << (idx + heads6[i]);
+        idx += sizes[i] - 1;
+    }
+    return mask;
+}
+
+int mv_set_actions(mv_handle h, const int32_t *masks) {
+    if (!h || !masks) return MV_ERR_ARG;
+    std::memcpy(h->h_actions.p, masks, sizeof(int32_t) * h->N);
+    return MV_OK;
+}
+
+int mv_step(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    if (cudaMemcpyAsync(h->d_actions.p, h->h_actions.p, sizeof(int32_t) * h->N, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("actions upload failed"); return MV_ERR_CUDA; }
+    const int rc = h->stepCommon(h->d_actions.p, h->obsToHost);
+    std::memset(h->h_actions.p, 0, sizeof(int32_t) * h->N);  // env.cpp:140-142: actions are cleared after every step
+    return rc;
+}
+
+int mv_step_device(mv_handle h, const int32_t *d_masks) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    return h->stepCommon(d_masks ? d_masks : h->d_actions.p, false);
+}
+
+int mv_obs_host(mv_handle h, const uint8_t **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_obs.p; return MV_OK; }
+int mv_depth_host(mv_handle h, const float **out) { if (!h || !out || !h->wantDepth) return MV_ERR_ARG; *out = h->h_depth.p; return MV_OK; }
+int mv_rewards(mv_handle h, const float **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_rewards.p; return MV_OK; }
+int mv_dones(mv_handle h, const uint8_t **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_dones.p; return MV_OK; }
+int mv_true_objectives(mv_handle h, const float **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_trueObj.p; return MV_OK; }
+int mv_actions_device(mv_handle h, int32_t **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_actions.p; return MV_OK; }
+int mv_obs_device(mv_handle h, uint8_t **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_obs.p; return MV_OK; }
+int mv_depth_device(mv_handle h, float **p) { if (!h || !p || !h->wantDepth) return MV_ERR_ARG; *p = h->d_depth.p; return MV_OK; }
+int mv_rewards_device(mv_handle h, float **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_rewards.p; return MV_OK; }
+int mv_dones_device(mv_handle h, uint8_t **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_dones.p; return MV_OK; }
+int mv_stream(mv_handle h, void **s) { if (!h || !s) return MV_ERR_ARG; *s = h->stream; return MV_OK; }
+
+int mv_get_reward_shaping(mv_handle h, int env, int agent, const char **keys, float *vals, int cap, int *n) {
+    if (!h || env < 0 || env >= h->E || agent < 0 || agent >= h->A || !n) return MV_ERR_ARG;
+    auto &rs = h->shaping[size_t(env) * h->A + agent];
+    *n = int(rs.size());
+    for (int i = 0; i < int(rs.size()) && i < cap; ++i) { keys[i] = rs[size_t(i)].first.c_str(); vals[i] = rs[size_t(i)].second; }
+    return MV_OK;
+}
+
+int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *keys, const float *vals, int n) {
+    if (!h || env < 0 || env >= h->E || agent < 0 || agent >= h->A) return MV_ERR_ARG;
+    // Scenario::setRewardShaping replaces the whole map (scenario.hpp:215); a scheme lacking a key the scenario reads
+    // makes the reference throw std::out_of_range at the next reward event (scenario.hpp:253) -> reject it up front
+    std::map<std::string, float> m;
+    for (int i = 0; i < n; ++i) m[keys[i]] = vals[i];
+    for (auto &kv : mv::defaultRewardShaping(h->scenario))
+        if (!m.count(kv.first)) { h->setError("reward shaping lacks key " + kv.first); return MV_ERR_ARG; }
+    const size_t view = size_t(env) * h->A + agent;
+    h->shaping[view].assign(m.begin(), m.end());
+    h->fillRtableRow(int(view));
+    h->rtableDirty = true;
+    return MV_OK;
+}
+
+int mv_faults(mv_handle h, int32_t *out) {
+    if (!h || !out) return MV_ERR_ARG;
+    std::vector<MvEnvState> st(size_t(h->E));
+    if (cudaMemcpy(st.data(), h->d_envs.p, sizeof(MvEnvState) * st.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (cudaMemcpy(h->h_faults.p, h->d_faults.p, sizeof(int32_t) * h->E, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    int32_t f = 0;
+    for (int e = 0; e < h->E; ++e) f |= st[size_t(e)].faults | h->h_faults.p[e];
+    *out = f;
+    return MV_OK;
+}
+int mv_kernel_launches(mv_handle h, int64_t *out) { if (!h || !out) return MV_ERR_ARG; *out = h->launches; return MV_OK; }
+int mv_last_kernel_ms(mv_handle h, float *out2) { if (!h || !out2) return MV_ERR_ARG; out2[0] = h->lastMs[0]; out2[1] = h->lastMs[1]; return MV_OK; }
+
+int mv_close(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->freeAll();
+    delete h;
+    return MV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ introspection (tests)
+int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
+    if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
+    const MvLevel &L = h->h_levels.p[size_t(env) * 2 + h->hostSlot[size_t(env)]];
+    std::vector<int32_t> o;
+    o.push_back(L.n_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
+    for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
+    for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
+    static const uint32_t pal[22] = {0xffdd3c, 0x3bb372, 0x50c878, 0x2eb5d0, 0xadd8e6, 0x3a7fa6, 0x2c3e50, 0xffb400, 0xb3b3b3, 0x555555, 0x222222,
+                                     0xffffff, 0xff0000, 0xffa770, 0xd468ee, 0xffe6e6, 0xffffe6, 0xccffcc, 0xe6ecff, 0xd9d9d9, 0xf2e6ff, 0xffebcc};
+    for (int i = 0; i < L.n_static; ++i) {
+        const MvBox &b = L.statics[i];
+        // invert centre/half back to inclusive voxel bounds: min = c - h, max = c + h - 1
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
+        o.push_back(b.flags); o.push_back(int(pal[b.color]));
+    }
+    for (int i = 0; i < L.n_terrain; ++i) {  // TowerBuilding: the single building-zone slab
+        o.push_back(4);
+        for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
+        for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
+    }
+    for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
+    for (int i = 0; i < h->A; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
+    if (int(o.size()) > cap) return -int(o.size());
+    std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    return int(o.size());
+}
+
+int mv_debug_get_state(mv_handle h, int env, float *out, int cap) {
+    if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
+    MvEnvState es;
+    std::vector<MvAgent> ag(size_t(h->A));
+    std::vector<MvObject> ob(MV_MAX_OBJECTS);
+    cudaStreamSynchronize(h->stream);
+    if (cudaMemcpy(&es, &h->d_envs.p[env], sizeof es, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (cudaMemcpy(ag.data(), &h->d_agents.p[size_t(env) * h->A], sizeof(MvAgent) * h->A, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (cudaMemcpy(ob.data(), &h->d_objects.p[size_t(env) * MV_MAX_OBJECTS], sizeof(MvObject) * MV_MAX_OBJECTS, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    const MvLevel &L = h->h_levels.p[size_t(env) * 2 + es.slot];
+    std::vector<float> o;
+    int ncol = h->A + L.n_obj;
+    for (int i = 0; i < L.n_static; ++i) ncol += (L.statics[i].flags & MV_SOLID) ? 1 : 0;
+    const float len = L.episode_len_base + 4.0f * float(L.n_movable);
+    o.push_back(es.episode_sec); o.push_back(len); o.push_back(float(es.num_frames)); o.push_back(float(es.highest_tower));
+    o.push_back(es.bz_reward); o.push_back(float(L.n_obj)); o.push_back(float(ncol)); o.push_back(0.f);
+    for (int i = 0; i < h->A; ++i) {
+        const MvAgent &a = ag[size_t(i)];
+        for (int k = 0; k < 3; ++k) o.push_back(a.pos[k]);
+        for (int k = 0; k < 9; ++k) o.push_back(a.basis[k]);
+        for (int k = 0; k < 3; ++k) o.push_back(a.hvel[k]);
+        for (float x : {a.vvel, a.voff, a.step_off, a.was_on_ground ? 1.f : 0.f, a.was_jumping ? 1.f : 0.f, a.jump_speed, a.cur_x, float(a.carrying), a.total_reward,
+                        h->h_rewards.p[size_t(env) * h->A + i], 0.f})
+            o.push_back(x);
+    }
+    for (int i = 0; i < L.n_obj; ++i) {
+        const MvObject &b = ob[size_t(i)];
+        float t[3] = {b.t[0], b.t[1], b.t[2]};
+        if (b.parent >= 0) {  // absolute translation of a carried object: ((agent*camera)*pickup)*local, as the oracle reports it
+            const MvAgent &a = ag[size_t(b.parent)];
+            mvh::M4 objT, cam;
+            std::memcpy(&objT.c[0][0], a.object_t, 64); std::memcpy(&cam.c[0][0], a.cam_local, 64);
+            const mvh::M4 pick = mvh::mul(mvh::translation(0.0f, -0.44f, -1.0f), mvh::identity());
+            const mvh::M4 local = mvh::mul(mvh::translation(b.t[0], b.t[1], b.t[2]), mvh::mul(mvh::scaling(b.s[0], b.s[1], b.s[2]), mvh::identity()));
+            const mvh::M4 abs = mvh::mul(mvh::mul(mvh::mul(objT, cam), pick), local);
+            t[0] = abs.c[3][0]; t[1] = abs.c[3][1]; t[2] = abs.c[3][2];
+        }
+        for (float x : {t[0], t[1], t[2], b.s[0], b.s[1], b.s[2], float(b.parent), b.enabled ? 1.f : 0.f, 0.f}) o.push_back(x);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::memcpy(out, o.data(), o.size() * sizeof(float));
+    return int(o.size());
+}
+
+int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
+    if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
+    MvEnvState es;
+    cudaStreamSynchronize(h->stream);
+    if (cudaMemcpy(&es, &h->d_envs.p[env], sizeof es, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    const MvLevel &L = h->h_levels.p[size_t(env) * 2 + es.slot];
+    const uint32_t *sol = h->h_solid.p + (size_t(env) * 2 + es.slot) * h->gridWords;
+    std::vector<uint8_t> og(size_t(h->gridCells));
+    if (cudaMemcpy(og.data(), h->d_objGrid.p + size_t(env) * h->gridCells, og.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    // opacity is a property of the box a solid voxel belongs to
+    std::vector<std::array<int32_t, 4>> v;
+    for (int x = 0; x < L.grid_dim[0]; ++x)
+        for (int y = 0; y < L.grid_dim[1]; ++y)
+            for (int z = 0; z < L.grid_dim[2]; ++z) {
+                const int idx = (x * L.grid_dim[1] + y) * L.grid_dim[2] + z;
+                int flags = 0;
+                if ((sol[idx >> 5] >> (idx & 31)) & 1u) {
+                    flags |= 1;
+                    const float cx = x + L.grid_org[0] + 0.5f, cy = y + L.grid_org[1] + 0.5f, cz = z + L.grid_org[2] + 0.5f;
+                    for (int i = 0; i < L.n_static; ++i) {
+                        const MvBox &b = L.statics[i];
+                        if (fabsf(cx - b.c[0]) < b.h[0] && fabsf(cy - b.c[1]) < b.h[1] && fabsf(cz - b.c[2]) < b.h[2]) { flags |= (b.flags & MV_OPAQUE); break; }
+                    }
+                }
+                if (og[size_t(idx)] != MV_NO_OBJECT) flags |= 4;
+                if (flags) v.push_back({x + L.grid_org[0], y + L.grid_org[1], z + L.grid_org[2], flags});
+            }
+    std::sort(v.begin(), v.end());
+    if (int(v.size()) * 4 > cap) return -int(v.size()) * 4;
+    for (size_t i = 0; i < v.size(); ++i) std::memcpy(out + i * 4, v[i].data(), 16);
+    return int(v.size()) * 4;
+}
+
+int mv_debug_get_instances(mv_handle h, int env, float *out, int cap) {
+    if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
+    int32_t cnt[2];
+    cudaStreamSynchronize(h->stream);
+    if (cudaMemcpy(cnt, h->d_instCounts.p + size_t(env) * 2, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    std::vector<MvInstance> inst(static_cast<size_t>(cnt[1] > 0 ? cnt[1] : 1));
+    if (cudaMemcpy(inst.data(), h->d_inst.p + size_t(env) * MV_MAX_INSTANCES, sizeof(MvInstance) * inst.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (cnt[1] * 18 > cap) return -cnt[1] * 18;
+    for (int i = 0; i < cnt[1]; ++i) {
+        out[i * 18] = float(inst[size_t(i)].mesh); out[i * 18 + 1] = float(inst[size_t(i)].color);
+        std::memcpy(out + i * 18 + 2, inst[size_t(i)].model, 64);
+    }
+    return cnt[1] * 18;
+}
+
+int mv_debug_get_view(mv_handle h, int env, int agent, float *out16) {
+    if (!h || env < 0 || env >= h->E || agent < 0 || agent >= h->A || !h->didReset) return MV_ERR_ARG;
+    cudaStreamSynchronize(h->stream);
+    if (cudaMemcpy(out16, h->d_views.p + (size_t(env) * h->A + agent) * 16, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    return MV_OK;
+}
+
+int mv_debug_render_instances(const float *view16, const float *inst18, int n, int w, int h, uint8_t *rgba, float *depth) {
+    if (!view16 || !inst18 || n < 0 || n > 4096 || w % 32 || h % 4 || (w / 32) * (h / 4) > 128) return MV_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return MV_ERR_CUDA;
+    // instances must arrive boxes-first (draw order); count the leading boxes
+    std::vector<MvInstance> inst(size_t(n ? n : 1));
+    int nBox = 0;
+    for (int i = 0; i < n; ++i) {
+        inst[size_t(i)].mesh = int(inst18[i * 18]); inst[size_t(i)].color = int(inst18[i * 18 + 1]);
+        std::memcpy(inst[size_t(i)].model, inst18 + i * 18 + 2, 64);
+        if (inst[size_t(i)].mesh == 0) { if (nBox != i) return MV_ERR_ARG; ++nBox; }
+    }
+    mv_engine tmp;  // only for the constants / palette
+    MvConsts k;
+    fillConsts(k, w, h);
+    if (uploadPalette(&tmp) != MV_OK) return MV_ERR_CUDA;
+    const int triCap = 1024;
+    const size_t smem = size_t(triCap) * sizeof(mvr::TriRec) + size_t((w / 32) * (h / 4)) * size_t((triCap + 31) / 32) * 4;
+    if (cudaFuncSetAttribute(mvr::rasterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return MV_ERR_CUDA;
+    MvInstance *dInst = nullptr; int32_t *dCnt = nullptr, *dFault = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
+    const int32_t cnt[2] = {nBox, n};
+    bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 8) == cudaSuccess && cudaMalloc(&dFault, 4) == cudaSuccess &&
+              cudaMalloc(&dView, 64) == cudaSuccess && cudaMalloc(&dObs, size_t(w) * h * 4) == cudaSuccess && cudaMalloc(&dDepth, size_t(w) * h * 4) == cudaSuccess;
+    if (ok) {
+        cudaMemcpy(dInst, inst.data(), sizeof(MvInstance) * inst.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(dCnt, cnt, 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(dView, view16, 64, cudaMemcpyHostToDevice);
+        cudaMemset(dFault, 0, 4);
+        mvr::RasterParams rp;
+        rp.instances = dInst; rp.instCounts = dCnt; rp.views = dView; rp.instStride = int(inst.size()); rp.obs = dObs; rp.depth = depth ? dDepth : nullptr;
+        rp.faults = dFault; rp.E = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
+        mvr::rasterKernel<<<1, 256, smem>>>(rp);
+        ok = cudaDeviceSynchronize() == cudaSuccess;
+        if (ok) {
+            cudaMemcpy(rgba, dObs, size_t(w) * h * 4, cudaMemcpyDeviceToHost);
+            if (depth) cudaMemcpy(depth, dDepth, size_t(w) * h * 4, cudaMemcpyDeviceToHost);
+            int32_t f = 0;
+            cudaMemcpy(&f, dFault, 4, cudaMemcpyDeviceToHost);
+            if (f) ok = false;
+        }
+    }
+    cudaFree(dInst); cudaFree(dCnt); cudaFree(dFault); cudaFree(dView); cudaFree(dObs); cudaFree(dDepth);
+    return ok ? MV_OK : MV_ERR_CUDA;
+}
+
+int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap) {
+    MvEnvState s;
+    std::memset(&s, 0, sizeof s);
+    mvBzInit(s);
+    for (int i = 0; i < nops; ++i) {
+        const int32_t *o = ops + i * 4;
+        if (o[0] == 0) mvBzInsert(s, o[1], o[2], o[3]);
+        else if (o[0] == 1) mvBzErase(s, o[1], o[2], o[3]);
+        else mvBzClear(s);
+    }
+    if (s.bz_count * 3 > cap) return -s.bz_count;
+    for (int i = 0; i < s.bz_count; ++i) for (int a = 0; a < 3; ++a) out_xyz[i * 3 + a] = s.bz_items[i][a];
+    return s.bz_count;
+}
+
+}  // extern "C"

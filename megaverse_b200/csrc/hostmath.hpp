@@ -1,0 +1,52 @@
+// Host-side float math for level generation (product code).  Column-major 4x4 products keep the accumulation order of
+// Magnum's RectangularMatrix::operator* (src/3rdparty/magnum/src/Magnum/Math/RectangularMatrix.h:753-764) so model
+// matrices built here carry the same bits the reference's scene graph would produce.  Transcendentals are evaluated in
+// double and rounded once (see DESIGN.md "numerics").
+#pragma once
+#include <cmath>
+#include <cstring>
+
+namespace mvh {
+
+inline float crsin(float x) { return float(std::sin(double(x))); }
+inline float crcos(float x) { return float(std::cos(double(x))); }
+inline float crtan(float x) { return float(std::tan(double(x))); }
+
+struct M4 { float c[4][4]; };
+inline M4 identity() { M4 m; std::memset(&m, 0, sizeof m); m.c[0][0] = m.c[1][1] = m.c[2][2] = m.c[3][3] = 1.0f; return m; }
+inline M4 mul(const M4 &a, const M4 &b) {
+    M4 o;
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 4; ++row) {
+            float acc = 0.0f;
+            for (int pos = 0; pos < 4; ++pos) acc += a.c[pos][row] * b.c[col][pos];
+            o.c[col][row] = acc;
+        }
+    return o;
+}
+inline M4 translation(float x, float y, float z) { M4 m = identity(); m.c[3][0] = x; m.c[3][1] = y; m.c[3][2] = z; return m; }
+inline M4 scaling(float x, float y, float z) { M4 m = identity(); m.c[0][0] = x; m.c[1][1] = y; m.c[2][2] = z; return m; }
+inline M4 rotationY(float a) {
+    const float s = crsin(a), c = crcos(a);
+    M4 m = identity();
+    m.c[0][0] = c; m.c[0][2] = -s; m.c[2][0] = s; m.c[2][2] = c;
+    return m;
+}
+
+// rows of btMatrix3x3(btQuaternion(Y axis, angle))  -- agent.cpp:44,128-133
+inline void yawBasis(float angle, float rows[9]) {
+    const float d = sqrtf(0.0f * 0.0f + 1.0f * 1.0f + 0.0f * 0.0f);
+    const float s = crsin(angle * 0.5f) / d;
+    const float qx = 0.0f * s, qy = 1.0f * s, qz = 0.0f * s, qw = crcos(angle * 0.5f);
+    const float dd = qx * qx + qy * qy + qz * qz + qw * qw;
+    const float k = 2.0f / dd;
+    const float xs = qx * k, ys = qy * k, zs = qz * k;
+    const float wx = qw * xs, wy = qw * ys, wz = qw * zs;
+    const float xx = qx * xs, xy = qx * ys, xz = qx * zs;
+    const float yy = qy * ys, yz = qy * zs, zz = qz * zs;
+    rows[0] = 1.0f - (yy + zz); rows[1] = xy - wz; rows[2] = xz + wy;
+    rows[3] = xy + wz; rows[4] = 1.0f - (xx + zz); rows[5] = yz - wx;
+    rows[6] = xz - wy; rows[7] = yz + wx; rows[8] = 1.0f - (xx + yy);
+}
+
+}  // namespace mvh

@@ -1,0 +1,45 @@
+// Host-side procedural level generation (product code).
+//
+// Level layout depends on libstdc++'s mt19937 / uniform_int_distribution / uniform_real_distribution<float> /
+// std::shuffle streams and on std::unordered_map iteration order, so it stays on the host, compiled with the same
+// libstdc++ the reference uses.  Each generator consumes the env's RNG in exactly the order
+// Env::reset does (src/libs/env/src/env.cpp:57-76) and emits a flat MvLevel + bit-packed solid grid for the device.
+#pragma once
+#include <map>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "mv_types.h"
+
+namespace mv {
+
+using FloatParams = std::map<std::string, float>;
+
+struct LevelOut {
+    MvLevel level;
+    std::vector<uint32_t> solid;  // grid_dim product bits, x-major: idx = (x*dimY + y)*dimZ + z
+};
+
+class LevelGenerator {
+public:
+    LevelGenerator(int scenario, int numAgents, const FloatParams &params);
+    void seed(unsigned long s) { rng_.seed(s); }
+    // Generates the next episode's level.  gridCells = capacity of the dense grid (cells); throws std::runtime_error
+    // if the level does not fit the engine's fixed capacities.
+    void generate(LevelOut &out, int serial, int gridCells);
+
+private:
+    void generateTower(LevelOut &out);
+    int scenario_, numAgents_;
+    FloatParams params_;
+    std::mt19937 rng_{std::random_device{}()};
+};
+
+int scenarioFromName(const std::string &name);  // -1 if unknown
+FloatParams defaultFloatParams(int scenario);
+// default reward table for the scenario (MV_R_* slots) and its key names
+std::vector<std::pair<std::string, float>> defaultRewardShaping(int scenario);
+int rewardSlot(int scenario, const std::string &key);  // -1 if unknown
+
+}  // namespace mv

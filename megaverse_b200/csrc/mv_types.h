@@ -1,0 +1,153 @@
+// Shared host/device plain-old-data layouts for the B200 voxel-world engine.
+//
+// HBM layout (one GPU, E envs, A agents per env, N = E*A views):
+//   levels   MvLevel[E][2]          double-buffered immutable level description (host-generated, H2D on reset only)
+//   solid    uint32[E][2][GW]       bit-packed solid-voxel occupancy over the level's bounding grid
+//   objGrid  uint8[E][GC]           dynamic voxel -> movable-object id map (0xFF = none)
+//   envs     MvEnvState[E]          per-env scalars + the building-zone set
+//   agents   MvAgent[E*A]           kinematic controller + camera state
+//   objects  MvObject[E][MAX_OBJ]   movable boxes
+//   inst     MvInstance[E][MAX_INST] per-env drawable list in draw order (static part written at reset, dynamic part per step)
+//   instCnt  int32[E][2]            {number of box instances, total instances}
+//   views    float[N][16]           per-view camera matrices, written by the step kernel
+//   obs      uint8[N][H][W][4]      the observation tensor (reference layout, megaverse.cpp:139-143)
+//   depth    float[N][H][W]         optional
+//   rewards float[N], dones uint8[E], trueObjectives float[N]
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#define MV_MAX_AGENTS 8
+#define MV_MAX_STATIC 96
+#define MV_MAX_TERRAIN 16
+#define MV_MAX_OBJECTS 128
+#define MV_NO_OBJECT 0xFF
+
+#define MV_SCENARIO_TOWER 0
+
+// voxel / box flags (voxel_state.hpp:10-15)
+#define MV_SOLID 1
+#define MV_OPAQUE 2
+
+// action bits (env.hpp:22-42)
+#define MV_A_LEFT (1 << 1)
+#define MV_A_RIGHT (1 << 2)
+#define MV_A_FORWARD (1 << 3)
+#define MV_A_BACKWARD (1 << 4)
+#define MV_A_LOOKLEFT (1 << 5)
+#define MV_A_LOOKRIGHT (1 << 6)
+#define MV_A_JUMP (1 << 7)
+#define MV_A_INTERACT (1 << 8)
+#define MV_A_LOOKDOWN (1 << 9)
+#define MV_A_LOOKUP (1 << 10)
+
+// reward table slots (scenario_tower_building.hpp:44-52)
+#define MV_R_TEAM_SPIRIT 0
+#define MV_R_TOWER_PICKED_UP 1
+#define MV_R_TOWER_VISITED_BZ 2
+#define MV_R_TOWER_BUILDING 3
+#define MV_R_COUNT 8
+
+// fault bits (per env, sticky): the engine never exit()s, it reports
+#define MV_FAULT_LEVEL_NOT_READY 1   // episode ended before the host delivered the next level
+#define MV_FAULT_TRI_OVERFLOW 2      // a view produced more triangles than the rasteriser's shared-memory list holds
+#define MV_FAULT_GRID_RANGE 4        // an object was placed outside the dense voxel grid
+#define MV_FAULT_NAN 8               // NaN position (agent.cpp:82-93 guard)
+
+struct MvBox {       // static layout box: drawable (OPAQUE) and/or collider (SOLID)
+    float c[3];      // centre  = ((min+max)/2 + 0.5) * voxelSize        (layout_utils.cpp:30-34)
+    float h[3];      // half extents = (max-min+1)/2 * voxelSize          (layout_utils.cpp:24-28)
+    int32_t flags;   // MV_SOLID | MV_OPAQUE
+    int32_t color;   // palette index
+};
+
+struct MvTerrain {
+    float model[16];  // column-major model matrix (layout_utils.cpp:53-68)
+    int32_t color;
+    int32_t pad[3];
+};
+
+struct MvLevel {
+    int32_t serial;       // episode index this level belongs to (checked by the device reset)
+    int32_t scenario;
+    int32_t n_static, n_terrain, n_obj;
+    int32_t n_movable;    // numMovableBoxes() for episodeLengthSec (scenario_tower_building.cpp:263-266)
+    int32_t grid_org[3], grid_dim[3];
+    int32_t bz_min[3], bz_max[3];  // building zone (x,z used)
+    float episode_len_base;        // floatParams["episodeLengthSec"]
+    float look_limit;              // floatParams["verticalLookLimitRad"]
+    int32_t pad0[4];               // statics[] must start 16-byte aligned (TMA bulk copy source)
+    MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
+    MvTerrain terrain[MV_MAX_TERRAIN];
+    int16_t obj_voxel[MV_MAX_OBJECTS][4];  // x,y,z,color
+    float spawn_pos[MV_MAX_AGENTS][4];     // ghost origin at spawn (agent.cpp:45)
+    float spawn_basis[MV_MAX_AGENTS][12];  // ghost basis rows (btMatrix3x3(btQuaternion(Y, yaw)))
+    float init_pos[MV_MAX_AGENTS][4];      // FallDetection agentInitialPositions
+};
+
+struct MvAgent {
+    float pos[3];
+    float basis[9];  // rows
+    float hvel[3];
+    float vvel, voff, step_off, jump_speed;
+    float jump_axis[3];
+    float cur_x;
+    float cam_local[16];
+    float bar_scale[3];
+    float total_reward;
+    float object_t[16];  // agent Object3D transformation (updateTransform)
+    int32_t was_on_ground, was_jumping, carrying, picked_up, visited_bz;
+    int32_t pad[2];
+};
+
+struct MvObject {
+    float t[3];      // local translation
+    float s[3];      // local scale (matrix diagonal)
+    float col_c[3];  // collider centre / half extents (RigidBody::syncPose, physics.hpp:69-74)
+    float col_h[3];
+    int32_t parent;  // -1 scene, else agent index (child of its pickupSpot)
+    int32_t enabled; // collider responds (CF_NO_CONTACT_RESPONSE cleared)
+    int32_t color;
+    int32_t pad;
+};
+
+struct MvEnvState {
+    float episode_sec;
+    int32_t num_frames;
+    int32_t episode_idx;
+    int32_t slot;            // which MvLevel[2] is live
+    int32_t highest_tower;
+    float bz_reward;         // currBuildingZoneReward
+    int32_t faults;
+    // std::unordered_set<VoxelCoords> objectsInBuildingZone, emulated in libstdc++ iteration order (bzset.h)
+    int32_t bz_count, bz_nb, bz_next_resize;
+    int16_t bz_items[MV_MAX_OBJECTS][4];
+    int32_t pad[2];
+};
+
+// One drawable of an env, in the reference's draw order (mesh type major, insertion order minor,
+// v4r_env_renderer.cpp:267-279): boxes first (static layout, terrain slabs, movable objects, agents' eyes, HUD bars),
+// then capsules (agent bodies), spheres, cones, cylinders.  Static entries are written at episode reset, dynamic ones
+// every step by the step kernel; the rasteriser is scenario-agnostic and only reads this list + the view matrices.
+struct MvInstance {
+    float model[16];  // column-major absoluteTransformationMatrix()
+    int32_t mesh;     // 0 box, 1 capsule, 2 sphere, 3 cone, 4 cylinder (DrawableType, env.hpp:57-67)
+    int32_t color;    // palette index
+    int32_t pad[2];
+};
+#define MV_MAX_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS)
+
+struct MvConsts {        // host-computed constants (so host libm decides their bits once, identically for oracle and device)
+    float look_left[9];  // btMatrix3x3(btQuaternion(Y, +3.5*dt)) rows
+    float look_right[9];
+    float max_slope_cos; // btCos(btRadians(45))
+    float p00, p11, p22, p32;  // V4R projection (v4r.cpp:35-45)
+    float dt;
+    float reward_default[MV_R_COUNT];
+};
+
+#ifdef __cplusplus
+static_assert(sizeof(MvBox) == 32 && sizeof(MvObject) == 64, "TMA bulk copies need 16-byte multiples");
+static_assert(offsetof(MvLevel, statics) % 16 == 0 && sizeof(MvLevel) % 16 == 0, "MvLevel alignment");
+static_assert(sizeof(MvInstance) == 80, "MvInstance layout");
+#endif

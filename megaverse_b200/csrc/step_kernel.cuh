@@ -1,0 +1,981 @@
+// K1+K2+K3: one env per warp.  Agent kinematics + capsule-vs-box/capsule collision, carry/place, reward/done, in-kernel
+// episode reset from the pre-staged next level, and the per-view render inputs (view + dynamic instance matrices).
+//
+// Replaces (file:line under /root/reference):
+//   Env::step                                   src/libs/env/src/env.cpp:83-152
+//   btDiscreteDynamicsWorld::stepSimulation +
+//   KinematicCharacterController                src/libs/env/src/kinematic_character_controller.cpp:156-442,509-602,625-644,753-792
+//   DefaultKinematicAgent                       src/libs/env/src/agent.cpp:73-161
+//   ObjectStackingComponent                     src/libs/scenarios/include/scenarios/component_object_stacking.hpp:45-198
+//   FallDetectionComponent                      src/libs/scenarios/include/scenarios/component_fall_detection.hpp:33-56
+//   TowerBuildingScenario::step / rewards       src/libs/scenarios/src/scenario_tower_building.cpp:179-266
+//   Scenario::rewardAgent/rewardTeam            src/libs/env/include/env/scenario.hpp:251-307
+//   DefaultScenario::updateUI                   src/libs/scenarios/include/scenarios/scenario_default.hpp:164-186
+//   VectorEnv::step done handling               src/libs/env/src/vector_env.cpp:94-105 (reset is done in-kernel)
+//   V4REnvRenderer::preDraw                     src/libs/v4r_rendering/src/v4r_env_renderer.cpp:299-336
+//
+// Execution model: the 32 lanes run the controller's scalar state machine redundantly on warp-uniform values held in
+// shared memory; every collision query fans the env's colliders out over the lanes and reduces with warp shuffles
+// (min hit fraction, lowest collider index on ties).  Static colliders and movable-object records are staged into shared
+// memory with one TMA bulk copy each (cp.async.bulk + mbarrier).  Lane 0 commits state changes.
+#pragma once
+#include "bzset.h"
+#include "dev_math.cuh"
+#include "mv_types.h"
+
+namespace mvk {
+using namespace dm;
+
+constexpr float kCapsuleRadius = 0.33f;
+constexpr float kCapsuleHalfHeight = 1.05f / 2;
+constexpr float kAllowedCcdPenetration = 0.04f;
+constexpr float kSimdEpsilon = 1.1920929e-07f;
+constexpr float kMaxPenetrationDepth = 0.041f;
+constexpr float kStepHeight = 0.2f;
+constexpr float kGravity = 1.4f * 9.8f;
+constexpr float kFallSpeed = 55.0f;
+constexpr float kMaxHorizontalSpeed = 4.5f, kMaxAirSpeed = 1.0f, kNormalDeceleration = 15.0f;
+constexpr float kMaxAcceleration = 35.0f + 15.0f, kMaxAirAcceleration = 3.0f, kExceedDecel = (35.0f + 15.0f) * 2;
+constexpr unsigned FULL = 0xffffffffu;
+
+struct StepParams {
+    const MvLevel *levels;       // [E][2]
+    const uint32_t *solid;       // [E][2][gridWords]
+    uint8_t *objGrid;            // [E][gridCells]
+    MvEnvState *envs;            // [E]
+    MvAgent *agents;             // [E*A]
+    MvObject *objects;           // [E][MV_MAX_OBJECTS]
+    MvInstance *instances;       // [E][MV_MAX_INSTANCES]
+    int32_t *instCounts;         // [E][2]
+    float *views;                // [E*A][16]
+    const int32_t *actions;      // [E*A]
+    const float *rtable;         // [E*A][MV_R_COUNT]
+    float *rewards;              // [E*A]
+    uint8_t *dones;              // [E]
+    float *trueObjectives;       // [E*A]
+    int E, A, gridCells, gridWords;
+    int forceReset;              // mv_reset(): re-initialise every env from its live level slot, no physics
+    MvConsts k;
+};
+
+struct WarpShared {  // one per warp
+    alignas(16) MvBox statics[MV_MAX_STATIC];
+    alignas(16) MvObject objects[MV_MAX_OBJECTS];
+    alignas(16) MvAgent agents[MV_MAX_AGENTS];
+    alignas(16) MvEnvState env;
+    alignas(8) unsigned long long mbar;
+    float lastReward[MV_MAX_AGENTS];
+    int objDirty[MV_MAX_AGENTS * 2];
+    int nDirty;
+    int doneFlag;
+};
+
+// ---------------------------------------------------------------- TMA (1-D bulk async copy) helpers
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbarInit(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkG2S(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)), "l"(src), "r"(bytes),
+                 "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smemAddr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+// ---------------------------------------------------------------- collision primitives (exact analytic)
+__device__ __forceinline__ float pointBoxDistance(V3 o, V3 H, V3 &n) {
+    const V3 q = v3(fabsf(o.x) - H.x, fabsf(o.y) - H.y, fabsf(o.z) - H.z);
+    if (q.x <= 0.0f && q.y <= 0.0f && q.z <= 0.0f) {
+        int ax = 0;
+        float best = q.x;
+        if (q.y > best) { best = q.y; ax = 1; }
+        if (q.z > best) { best = q.z; ax = 2; }
+        n = v3(0, 0, 0);
+        setComp(n, ax, comp(o, ax) < 0.0f ? -1.0f : 1.0f);
+        return best;
+    }
+    const V3 e = v3(q.x > 0.0f ? q.x : 0.0f, q.y > 0.0f ? q.y : 0.0f, q.z > 0.0f ? q.z : 0.0f);
+    const float d = sqrtf(e.x * e.x + e.y * e.y + e.z * e.z);
+    n = v3(o.x < 0.0f ? -e.x : e.x, o.y < 0.0f ? -e.y : e.y, o.z < 0.0f ? -e.z : e.z);
+    n = n * (1.0f / d);
+    return d;
+}
+
+__device__ bool rayRoundedBox(V3 o, V3 d, V3 H, float rho, float &tOut, V3 &nOut) {
+    V3 n0;
+    const float d0 = pointBoxDistance(o, H, n0);
+    if (d0 - rho <= 0.0f) {
+        if (dot(d, n0) < -kSimdEpsilon) { tOut = 0.0f; nOut = n0; return true; }
+        return false;
+    }
+    float best = 2.0f;
+    V3 bestN = v3(0, 0, 0);
+    for (int i = 0; i < 3; ++i) {  // 6 faces
+        const float di = comp(d, i);
+        if (di == 0.0f) continue;
+        const float s = di < 0.0f ? 1.0f : -1.0f;
+        const float t = (s * (comp(H, i) + rho) - comp(o, i)) / di;
+        if (t < 0.0f || t > 1.0f || t >= best) continue;
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        const float qj = comp(o, j) + t * comp(d, j), qk = comp(o, k) + t * comp(d, k);
+        if (fabsf(qj) <= comp(H, j) && fabsf(qk) <= comp(H, k)) { best = t; bestN = v3(0, 0, 0); setComp(bestN, i, s); }
+    }
+    for (int k = 0; k < 3; ++k) {  // 12 edges
+        const int i = (k + 1) % 3, j = (k + 2) % 3;
+        const float di = comp(d, i), dj = comp(d, j);
+        const float a = di * di + dj * dj;
+        if (a == 0.0f) continue;
+        for (int si = -1; si <= 1; si += 2)
+            for (int sj = -1; sj <= 1; sj += 2) {
+                const float oi = comp(o, i) - si * comp(H, i), oj = comp(o, j) - sj * comp(H, j);
+                const float b = oi * di + oj * dj;
+                const float c = oi * oi + oj * oj - rho * rho;
+                const float disc = b * b - a * c;
+                if (disc < 0.0f) continue;
+                const float t = (-b - sqrtf(disc)) / a;
+                if (t < 0.0f || t > 1.0f || t >= best) continue;
+                const float qi = oi + t * di, qj = oj + t * dj, qk = comp(o, k) + t * comp(d, k);
+                if (si * qi >= 0.0f && sj * qj >= 0.0f && fabsf(qk) <= comp(H, k)) {
+                    best = t;
+                    bestN = v3(0, 0, 0);
+                    setComp(bestN, i, qi / rho);
+                    setComp(bestN, j, qj / rho);
+                }
+            }
+    }
+    {  // 8 corners
+        const float a = dot(d, d);
+        if (a != 0.0f)
+            for (int sx = -1; sx <= 1; sx += 2)
+                for (int sy = -1; sy <= 1; sy += 2)
+                    for (int sz = -1; sz <= 1; sz += 2) {
+                        const V3 oc = v3(o.x - sx * H.x, o.y - sy * H.y, o.z - sz * H.z);
+                        const float b = dot(oc, d);
+                        const float c = dot(oc, oc) - rho * rho;
+                        const float disc = b * b - a * c;
+                        if (disc < 0.0f) continue;
+                        const float t = (-b - sqrtf(disc)) / a;
+                        if (t < 0.0f || t > 1.0f || t >= best) continue;
+                        const V3 q = oc + d * t;
+                        if (sx * q.x >= 0.0f && sy * q.y >= 0.0f && sz * q.z >= 0.0f) { best = t; bestN = q * (1.0f / rho); }
+                    }
+    }
+    if (best > 1.0f) return false;
+    tOut = best;
+    nOut = bestN;
+    return true;
+}
+
+__device__ __forceinline__ float pointSegDistance(V3 o, float L, V3 &n) {
+    const float cy = o.y < -L ? -L : (o.y > L ? L : o.y);
+    const V3 e = v3(o.x, o.y - cy, o.z);
+    const float d = length(e);
+    if (d > 0.0f) n = e * (1.0f / d); else n = v3(1, 0, 0);
+    return d;
+}
+__device__ bool rayCapsule(V3 o, V3 d, float L, float R, float &tOut, V3 &nOut) {
+    V3 n0;
+    const float d0 = pointSegDistance(o, L, n0);
+    if (d0 - R <= 0.0f) {
+        if (dot(d, n0) < -kSimdEpsilon) { tOut = 0.0f; nOut = n0; return true; }
+        return false;
+    }
+    float best = 2.0f;
+    V3 bestN = v3(0, 0, 0);
+    {
+        const float a = d.x * d.x + d.z * d.z;
+        if (a != 0.0f) {
+            const float b = o.x * d.x + o.z * d.z, c = o.x * o.x + o.z * o.z - R * R;
+            const float disc = b * b - a * c;
+            if (disc >= 0.0f) {
+                const float t = (-b - sqrtf(disc)) / a;
+                if (t >= 0.0f && t <= 1.0f) {
+                    const float qy = o.y + t * d.y;
+                    if (fabsf(qy) <= L) { best = t; bestN = v3((o.x + t * d.x) / R, 0.0f, (o.z + t * d.z) / R); }
+                }
+            }
+        }
+    }
+    const float a = dot(d, d);
+    if (a != 0.0f)
+        for (int s = -1; s <= 1; s += 2) {
+            const V3 oc = v3(o.x, o.y - s * L, o.z);
+            const float b = dot(oc, d), c = dot(oc, oc) - R * R;
+            const float disc = b * b - a * c;
+            if (disc < 0.0f) continue;
+            const float t = (-b - sqrtf(disc)) / a;
+            if (t < 0.0f || t > 1.0f || t >= best) continue;
+            const V3 q = oc + d * t;
+            if (s * q.y >= 0.0f) { best = t; bestN = q * (1.0f / R); }
+        }
+    if (best > 1.0f) return false;
+    tOut = best;
+    nOut = bestN;
+    return true;
+}
+
+// collider index space: [0,ns) statics, [ns,ns+no) objects, [ns+no, ns+no+A) agent capsules
+struct ColliderView {
+    const WarpShared *S;
+    int ns, no, A;
+    __device__ __forceinline__ int count() const { return ns + no + A; }
+    __device__ __forceinline__ bool fetch(int i, int &kind, V3 &c, V3 &h) const {
+        if (i < ns) {
+            const MvBox &b = S->statics[i];
+            if (!(b.flags & MV_SOLID)) return false;
+            kind = 0; c = v3(b.c[0], b.c[1], b.c[2]); h = v3(b.h[0], b.h[1], b.h[2]);
+            return true;
+        }
+        if (i < ns + no) {
+            const MvObject &o = S->objects[i - ns];
+            if (!o.enabled) return false;
+            kind = 0; c = v3(o.col_c[0], o.col_c[1], o.col_c[2]); h = v3(o.col_h[0], o.col_h[1], o.col_h[2]);
+            return true;
+        }
+        const MvAgent &a = S->agents[i - ns - no];
+        kind = 1; c = v3(a.pos[0], a.pos[1], a.pos[2]); h = v3(0, 0, 0);
+        return true;
+    }
+};
+
+struct SweepHit { bool hit; float fraction; V3 normal; };
+
+// KinematicClosestNotMeConvexResultCallback over all colliders, lanes strided over the collider list
+__device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, V3 filterDir, float minSlopeDot, int lane) {
+    const V3 d = to - from;
+    float bt = 1.0f;
+    int bi = 0x7fffffff;
+    V3 bn = v3(0, 0, 0);
+    const int n = cv.count();
+    for (int i = lane; i < n; i += 32) {
+        if (i == self) continue;
+        int kind; V3 c, h;
+        if (!cv.fetch(i, kind, c, h)) continue;
+        const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
+                                 : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
+        bool miss = false;
+        {
+            const float lx = from.x < to.x ? from.x : to.x, hx = from.x < to.x ? to.x : from.x;
+            const float ly = from.y < to.y ? from.y : to.y, hy = from.y < to.y ? to.y : from.y;
+            const float lz = from.z < to.z ? from.z : to.z, hz = from.z < to.z ? to.z : from.z;
+            if (hx < c.x - ext.x || lx > c.x + ext.x) miss = true;
+            if (hy < c.y - ext.y || ly > c.y + ext.y) miss = true;
+            if (hz < c.z - ext.z || lz > c.z + ext.z) miss = true;
+        }
+        if (miss) continue;
+        float t; V3 nn; bool hit;
+        if (kind == 0) hit = rayRoundedBox(from - c, d, v3(h.x, h.y + kCapsuleHalfHeight, h.z), kCapsuleRadius - kAllowedCcdPenetration, t, nn);
+        else hit = rayCapsule(from - c, d, 2.0f * kCapsuleHalfHeight, 2.0f * kCapsuleRadius - kAllowedCcdPenetration, t, nn);
+        if (!hit) continue;
+        if (!(t < bt)) continue;
+        if (dot(filterDir, nn) < minSlopeDot) continue;
+        bt = t; bi = i; bn = nn;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float ot = __shfl_xor_sync(FULL, bt, off);
+        const int oi = __shfl_xor_sync(FULL, bi, off);
+        const float ox = __shfl_xor_sync(FULL, bn.x, off), oy = __shfl_xor_sync(FULL, bn.y, off), oz = __shfl_xor_sync(FULL, bn.z, off);
+        if (ot < bt || (ot == bt && oi < bi)) { bt = ot; bi = oi; bn = v3(ox, oy, oz); }
+    }
+    SweepHit r;
+    r.hit = bi != 0x7fffffff;
+    r.fraction = r.hit ? bt : 1.0f;
+    r.normal = bn;
+    return r;
+}
+
+// first collider (index order) penetrating deeper than maxPenetrationDepth; returns push-out delta
+__device__ bool warpRecover(const ColliderView &cv, int self, V3 p, V3 &delta, int lane) {
+    const int n = cv.count();
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool pen = false;
+        V3 dl = v3(0, 0, 0);
+        if (i < n && i != self) {
+            int kind; V3 c, h;
+            if (cv.fetch(i, kind, c, h)) {
+                V3 nn;
+                float dist;
+                if (kind == 0) dist = pointBoxDistance(p - c, v3(h.x, h.y + kCapsuleHalfHeight, h.z), nn) - kCapsuleRadius;
+                else dist = pointSegDistance(p - c, 2.0f * kCapsuleHalfHeight, nn) - 2.0f * kCapsuleRadius;
+                if (dist < -kMaxPenetrationDepth) { pen = true; dl = nn * (-dist); }
+            }
+        }
+        const unsigned m = __ballot_sync(FULL, pen);
+        if (m) {
+            const int src = __ffs(m) - 1;
+            delta = v3(__shfl_sync(FULL, dl.x, src), __shfl_sync(FULL, dl.y, src), __shfl_sync(FULL, dl.z, src));
+            return true;
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- kinematic character controller (uniform across lanes)
+struct Kcc {
+    V3 pos, hvel, jumpAxis, cur, tgt;
+    float vvel, voff, stepOff, jumpSpeed;
+    bool wasOnGround, wasJumping;
+    __device__ __forceinline__ bool onGround() const { return (fabsf(vvel) < kSimdEpsilon) && (fabsf(voff) < kSimdEpsilon); }
+};
+
+__device__ __forceinline__ V3 lerp3(V3 a, V3 b, float rt) {  // btVector3::setInterpolate3
+    const float s = 1.0f - rt;
+    return v3(s * a.x + rt * b.x, s * a.y + rt * b.y, s * a.z + rt * b.z);
+}
+
+__device__ void kccSetAcceleration(Kcc &k, V3 acc, float dt) {
+    const bool isOnGround = k.onGround();
+    const float accelerationMagnitude = length(acc);
+    const float currMax = isOnGround ? kMaxAcceleration : kMaxAirAcceleration;
+    if (!(length2(acc) < kSimdEpsilon * kSimdEpsilon)) acc = acc * (currMax / accelerationMagnitude);
+    if (isOnGround) {
+        k.hvel = k.hvel + acc * dt;
+        const float sp = length(k.hvel);
+        if (sp > kMaxHorizontalSpeed) {
+            const float dv = kExceedDecel * dt;
+            if (sp - dv > kMaxHorizontalSpeed) k.hvel = k.hvel * ((sp - dv) / sp);
+            else k.hvel = k.hvel * (kMaxHorizontalSpeed / sp);
+        }
+    } else {
+        const float sp = length(k.hvel);
+        const V3 nv = k.hvel + acc * dt;
+        const float nsp = length(nv);
+        if (nsp <= kMaxAirSpeed || nsp < sp) k.hvel = nv;
+    }
+}
+
+__device__ bool kccRecover(Kcc &k, const ColliderView &cv, int self, int lane) {
+    k.cur = k.pos;
+    V3 delta;
+    const bool pen = warpRecover(cv, self, k.cur, delta, lane);
+    if (pen) k.cur = k.cur + delta;
+    k.pos = k.cur;
+    return pen;
+}
+
+__device__ void kccPlayerStep(Kcc &k, const ColliderView &cv, int self, float dt, float maxSlopeCos, int lane) {
+    const V3 up = v3(0, 1, 0);
+    k.cur = k.pos;
+    k.tgt = k.cur;
+    const V3 original = k.cur;
+    k.wasOnGround = k.onGround();
+    k.vvel -= kGravity * dt;
+    if (k.vvel > 0.0f && k.vvel > k.jumpSpeed) k.vvel = k.jumpSpeed;
+    if (k.vvel < 0.0f && fabsf(k.vvel) > fabsf(kFallSpeed)) k.vvel = -fabsf(kFallSpeed);
+    k.voff = k.vvel * dt;
+    {  // stepUp
+        float stepH = 0.0f;
+        if (k.vvel < 0.0f) stepH = kStepHeight;
+        const V3 start = k.cur;
+        k.tgt = k.cur + up * stepH + k.jumpAxis * (k.voff > 0.f ? k.voff : 0.f);
+        k.cur = k.tgt;
+        const SweepHit cb = warpSweep(cv, self, start, k.tgt, -up, maxSlopeCos, lane);
+        if (cb.hit) {
+            if (dot(cb.normal, up) > 0.0f) {
+                k.stepOff = stepH * cb.fraction;
+                k.cur = lerp3(k.cur, k.tgt, cb.fraction);
+            }
+            k.pos = k.cur;
+            int loops = 0;
+            while (kccRecover(k, cv, self, lane)) {
+                loops++;
+                if (loops > 4) break;
+            }
+            k.tgt = k.pos;
+            k.cur = k.tgt;
+            if (k.voff > 0) { k.voff = 0.0f; k.vvel = 0.0f; k.stepOff = kStepHeight; }
+        } else {
+            k.stepOff = stepH;
+            k.cur = k.tgt;
+        }
+    }
+    {  // stepForwardAndStrafe
+        const V3 hv = k.hvel;
+        k.tgt = k.cur + hv * dt;
+        int maxIter = 10;
+        while (maxIter-- > 0) {
+            const V3 sweepDirNegative = k.cur - k.tgt;
+            SweepHit cb;
+            cb.hit = false; cb.fraction = 1.0f; cb.normal = v3(0, 0, 0);
+            const bool same = k.cur.x == k.tgt.x && k.cur.y == k.tgt.y && k.cur.z == k.tgt.z;
+            if (!same) cb = warpSweep(cv, self, k.cur, k.tgt, sweepDirNegative, 0.0f, lane);
+            if (cb.hit) {
+                {  // updateTargetPositionBasedOnCollision
+                    V3 md = k.tgt - k.cur;
+                    const float ml = length(md);
+                    if (ml > kSimdEpsilon) {
+                        md = btNormalized(md);
+                        const V3 par = cb.normal * dot(md, cb.normal);
+                        const V3 perp = md - par;
+                        k.tgt = k.cur;
+                        k.tgt = k.tgt + perp * ml;
+                        k.tgt = k.tgt + par * (ml * cb.fraction);
+                    }
+                }
+                V3 cd = k.tgt - k.cur;
+                const float d2 = length2(cd);
+                if (d2 > 0.0001f) {
+                    cd = btNormalized(cd);
+                    if (dot(cd, hv) <= 0.0f) { k.tgt = k.cur; break; }
+                } else { k.tgt = k.cur; break; }
+            } else break;
+        }
+        k.cur = k.tgt;
+    }
+    {  // stepDown
+        float down = (k.vvel < 0.f ? -k.vvel : 0.f);
+        if (down > 0.0f && down > kFallSpeed && (k.wasOnGround || !k.wasJumping)) down = kFallSpeed;
+        const V3 drop = up * (k.stepOff + down * dt);
+        k.tgt = k.tgt - drop;
+        const SweepHit cb = warpSweep(cv, self, k.cur, k.tgt, up, maxSlopeCos, lane);
+        if (cb.hit) {
+            k.cur = lerp3(k.cur, k.tgt, cb.fraction);
+            k.vvel = 0.0f; k.voff = 0.0f; k.wasJumping = false;
+        } else k.cur = k.tgt;
+    }
+    k.pos = k.cur;
+    k.hvel = (k.cur - original) * (1.0f / dt);
+    k.hvel.y = 0;
+    int loops = 0;
+    while (kccRecover(k, cv, self, lane)) {
+        loops++;
+        if (loops > 4) break;
+    }
+    const float sp = length(k.hvel);
+    if (k.onGround()) {
+        if (sp - kNormalDeceleration * dt < 0) k.hvel = v3(0, 0, 0);
+        else k.hvel = k.hvel * ((sp - kNormalDeceleration * dt) / sp);
+    }
+}
+
+// ---------------------------------------------------------------- helpers on shared state
+__device__ __forceinline__ M4 loadM4(const float *p) { M4 m;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m.c[i] = p[i];
+    return m; }
+__device__ __forceinline__ void storeM4(float *p, const M4 &m) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = m.c[i]; }
+__device__ __forceinline__ M4 pickupLocal() { return mul4(translation4(v3(0.0f, -0.44f, -1.0f)), identity4()); }
+
+// DefaultKinematicAgent::updateTransform (agent.cpp:73-98).  Returns false (and leaves object_t) on NaN.
+__device__ bool updateTransform(MvAgent &a, M4 &out) {
+    // btMatrix3x3::getRotation
+    const float *m = a.basis;
+    const float trace = m[0] + m[4] + m[8];
+    float t[4];
+    if (trace > 0.0f) {
+        float s = sqrtf(trace + 1.0f);
+        t[3] = s * 0.5f;
+        s = 0.5f / s;
+        t[0] = (m[7] - m[5]) * s;
+        t[1] = (m[2] - m[6]) * s;
+        t[2] = (m[3] - m[1]) * s;
+    } else {
+        const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        float s = sqrtf(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0f);
+        t[i] = s * 0.5f;
+        s = 0.5f / s;
+        t[3] = (m[k * 3 + j] - m[j * 3 + k]) * s;
+        t[j] = (m[j * 3 + i] + m[i * 3 + j]) * s;
+        t[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+    }
+    V3 position = v3(a.pos[0], a.pos[1], a.pos[2]);
+    V3 axis;
+    {
+        const float s2 = 1.0f - t[3] * t[3];
+        if (s2 < 10.0f * kSimdEpsilon) axis = v3(1, 0, 0);
+        else { const float s = 1.0f / sqrtf(s2); axis = v3(t[0] * s, t[1] * s, t[2] * s); }
+    }
+    const V3 na = mgNormalized(axis);
+    const float rotation = 2.0f * cracos(t[3]);
+    if (isnan(position.x) || isnan(position.y) || isnan(position.z) || isnan(rotation)) return false;
+    if (isnan(na.x) || isnan(na.y) || isnan(na.z)) return false;
+    position = position + v3(0, 0.05f, 0.0f);
+    out = mul4(translation4(position), mul4(rotation4(rotation, na), identity4()));
+    return true;
+}
+
+__device__ __forceinline__ int gridIndex(const MvLevel &L, int x, int y, int z) {
+    const int gx = x - L.grid_org[0], gy = y - L.grid_org[1], gz = z - L.grid_org[2];
+    if (gx < 0 || gy < 0 || gz < 0 || gx >= L.grid_dim[0] || gy >= L.grid_dim[1] || gz >= L.grid_dim[2]) return -1;
+    return (gx * L.grid_dim[1] + gy) * L.grid_dim[2] + gz;
+}
+// voxel_grid.hpp:18-21,144-149 with origin 0, voxelSize 1
+__device__ __forceinline__ void toVoxel(V3 v, int &x, int &y, int &z) {
+    x = int(lroundf(floorf((v.x - 0.0f) / 1.0f))); y = int(lroundf(floorf((v.y - 0.0f) / 1.0f))); z = int(lroundf(floorf((v.z - 0.0f) / 1.0f)));
+}
+
+__device__ __forceinline__ bool inBuildingZone(const MvLevel &L, int x, int z) {
+    return x >= L.bz_min[0] && x < L.bz_max[0] && z >= L.bz_min[2] && z < L.bz_max[2];
+}
+__device__ __forceinline__ float towerCoeff(float height) {  // buildingRewardCoeffForHeight
+    float res = height * 0.05f;
+    const float p2 = ldexpf(1.0f, int(height));  // powf(2, height) for integral heights, exact
+    const float v = 0.05f * p2;
+    res += v < 20.0f ? v : 20.0f;
+    return res;
+}
+__device__ float towerReward(const MvEnvState &e) {
+    float r = 0.0f;
+    for (int i = 0; i < e.bz_count; ++i) r += towerCoeff(float(e.bz_items[i][1]));
+    return r;
+}
+
+// RigidBody::syncPose for an object resting in the scene (identity parent): centre = t + offset, half = |s| * 1.15
+__device__ __forceinline__ void syncPoseScene(MvObject &o) {
+    o.col_c[0] = o.t[0] + 0.0f; o.col_c[1] = o.t[1] + -0.05f; o.col_c[2] = o.t[2] + 0.0f;
+    o.col_h[0] = sqrtf(o.s[0] * o.s[0] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.15f;
+    o.col_h[1] = sqrtf(0.0f * 0.0f + o.s[1] * o.s[1] + 0.0f * 0.0f) * 1.15f;
+    o.col_h[2] = sqrtf(0.0f * 0.0f + 0.0f * 0.0f + o.s[2] * o.s[2]) * 1.15f;
+}
+
+// ---------------------------------------------------------------- episode (re)initialisation from a level slot
+__device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int gridCells, int A, int lane) {
+    // voxel -> object map
+    {
+        uint32_t *g32 = reinterpret_cast<uint32_t *>(objGrid);
+        for (int i = lane; i < gridCells / 4; i += 32) g32[i] = 0xffffffffu;
+        __syncwarp();
+    }
+    for (int i = lane; i < L.n_obj; i += 32) {
+        MvObject &o = S.objects[i];
+        const int x = L.obj_voxel[i][0], y = L.obj_voxel[i][1], z = L.obj_voxel[i][2];
+        o.t[0] = float(x) + 0.5f; o.t[1] = float(y) + 0.5f; o.t[2] = float(z) + 0.5f;
+        o.s[0] = 0.39f; o.s[1] = 0.39f; o.s[2] = 0.39f;
+        o.parent = -1; o.enabled = 1; o.color = L.obj_voxel[i][3]; o.pad = 0;
+        syncPoseScene(o);
+        const int gi = gridIndex(L, x, y, z);
+        if (gi >= 0) objGrid[gi] = uint8_t(i);
+    }
+    for (int i = lane; i < A; i += 32) {
+        MvAgent &a = S.agents[i];
+        for (int k = 0; k < 3; ++k) { a.pos[k] = L.spawn_pos[i][k]; a.hvel[k] = 0.0f; }
+        for (int k = 0; k < 9; ++k) a.basis[k] = L.spawn_basis[i][k];
+        a.vvel = 0; a.voff = 0; a.step_off = 0; a.jump_speed = 10.0f;
+        a.jump_axis[0] = 0; a.jump_axis[1] = 1; a.jump_axis[2] = 0;
+        a.cur_x = 0.0f;
+        storeM4(a.cam_local, mul4(translation4(v3(0, 0.41f, 0)), identity4()));
+        a.bar_scale[0] = 0.24f; a.bar_scale[1] = float(0.0015); a.bar_scale[2] = float(0.001);
+        a.total_reward = 0.0f;
+        a.was_on_ground = 0; a.was_jumping = 0; a.carrying = -1; a.picked_up = 0; a.visited_bz = 0;
+        M4 ot;
+        if (updateTransform(a, ot)) storeM4(a.object_t, ot); else storeM4(a.object_t, identity4());
+    }
+    __syncwarp();
+    if (lane == 0) {
+        MvEnvState &e = S.env;
+        e.episode_sec = 0.0f; e.num_frames = 0; e.highest_tower = 0;
+        mvBzClear(e);
+        for (int i = 0; i < L.n_obj; ++i) {
+            const int x = L.obj_voxel[i][0], y = L.obj_voxel[i][1], z = L.obj_voxel[i][2];
+            if (inBuildingZone(L, x, z)) mvBzInsert(e, x, y, z);
+        }
+        e.bz_reward = towerReward(e);
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------- render inputs (K3): instance list + view matrices
+// Model matrices are the drawables' absoluteTransformationMatrix() as SceneGraph::Object::setClean(objects) composes
+// them: right to left up the parent chain (v4r_env_renderer.cpp:319-335).
+__device__ __forceinline__ void putInstance(MvInstance &d, const M4 &m, int mesh, int color) {
+    storeM4(d.model, m);
+    d.mesh = mesh; d.color = color; d.pad[0] = 0; d.pad[1] = 0;
+}
+__device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
+    // static part: opaque layout boxes in order, then terrain slabs.  The opaque count is recomputed uniformly.
+    int nOpaque = 0;
+    for (int i = 0; i < L.n_static; ++i) nOpaque += (L.statics[i].flags & MV_OPAQUE) ? 1 : 0;
+    if (writeStatic) {
+        for (int i = lane; i < L.n_static; i += 32) {
+            const MvBox &b = L.statics[i];
+            if (!(b.flags & MV_OPAQUE)) continue;
+            int slotI = 0;
+            for (int j = 0; j < i; ++j) slotI += (L.statics[j].flags & MV_OPAQUE) ? 1 : 0;
+            putInstance(inst[slotI], mul4(translation4(v3(b.c[0], b.c[1], b.c[2])), mul4(scaling4(v3(b.h[0], b.h[1], b.h[2])), identity4())), 0, b.color);
+        }
+        for (int i = lane; i < L.n_terrain; i += 32) putInstance(inst[nOpaque + i], loadM4(L.terrain[i].model), 0, L.terrain[i].color);
+    }
+    const int base = nOpaque + L.n_terrain;
+    const int no = L.n_obj;
+    for (int i = lane; i < no; i += 32) {
+        const MvObject &o = S.objects[i];
+        M4 m = mul4(translation4(v3(o.t[0], o.t[1], o.t[2])), mul4(scaling4(v3(o.s[0], o.s[1], o.s[2])), identity4()));
+        if (o.parent >= 0) {
+            const MvAgent &a = S.agents[o.parent];
+            m = mul4(loadM4(a.object_t), mul4(loadM4(a.cam_local), mul4(pickupLocal(), m)));
+        }
+        putInstance(inst[base + i], m, 0, o.color);
+    }
+    for (int i = lane; i < A; i += 32) {
+        const MvAgent &a = S.agents[i];
+        const M4 objT = loadM4(a.object_t), cam = loadM4(a.cam_local);
+        storeM4(views + i * 16, inverted4(mul4(objT, cam)));  // Camera::cameraMatrix: inverse of the left-to-right absolute transform
+        const M4 eyesLocal = mul4(translation4(v3(0.0f, 0.0f, -0.19f)), mul4(scaling4(v3(0.25f, 0.12f, 0.2f)), identity4()));
+        putInstance(inst[base + no + i], mul4(objT, mul4(cam, eyesLocal)), 0, 6);  // AGENT_EYES = DARK_NAVY
+        const M4 ui = mul4(translation4(v3(0, 0, -0.2f)), identity4());
+        const M4 anchor = mul4(translation4(v3(0, -0.131f, 0)), identity4());
+        const M4 bar = scaling4(v3(a.bar_scale[0], a.bar_scale[1], a.bar_scale[2]));
+        putInstance(inst[base + no + A + i], mul4(objT, mul4(cam, mul4(ui, mul4(anchor, bar)))), 0, 3);  // BLUE
+        const M4 bodyLocal = mul4(translation4(v3(0, 0.09f, 0)), mul4(scaling4(v3(0.35f, 0.36f, 0.35f)), identity4()));
+        const int agentColors[7] = {0, 1, 3, 7, 14, 10, 12};  // const.hpp:85 as palette indices
+        putInstance(inst[base + no + 2 * A + i], mul4(objT, bodyLocal), 1, agentColors[i % 7]);
+    }
+    if (lane == 0) { counts[0] = base + no + 2 * A; counts[1] = base + no + 3 * A; }
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(128) stepKernel(StepParams P) {
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
+    if (env >= P.E) return;
+    WarpShared &S = reinterpret_cast<WarpShared *>(smemRaw)[warpInBlock];
+    const int A = P.A;
+    const float dt = P.k.dt;
+
+    // ---- stage state: env + agents by plain loads, statics + objects by TMA bulk copies
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&P.envs[env]);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&S.env);
+        for (int i = lane; i < int(sizeof(MvEnvState) / 4); i += 32) dst[i] = src[i];
+        const uint32_t *asrc = reinterpret_cast<const uint32_t *>(&P.agents[size_t(env) * A]);
+        uint32_t *adst = reinterpret_cast<uint32_t *>(&S.agents[0]);
+        for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
+        if (lane == 0) { S.nDirty = 0; mbarInit(&S.mbar, 1); }
+        for (int i = lane; i < MV_MAX_AGENTS; i += 32) S.lastReward[i] = 0.0f;
+    }
+    __syncwarp();
+    int slot = S.env.slot;
+    const MvLevel *L = &P.levels[size_t(env) * 2 + slot];
+    uint8_t *objGrid = P.objGrid + size_t(env) * P.gridCells;
+    MvObject *gObjects = P.objects + size_t(env) * MV_MAX_OBJECTS;
+    int ns = L->n_static, no = L->n_obj;
+    if (!P.forceReset) {
+        if (lane == 0) {
+            const uint32_t bytes = uint32_t(ns) * uint32_t(sizeof(MvBox)) + uint32_t(no) * uint32_t(sizeof(MvObject));
+            mbarExpectTx(&S.mbar, bytes);
+            if (ns) bulkG2S(S.statics, L->statics, uint32_t(ns) * uint32_t(sizeof(MvBox)), &S.mbar);
+            if (no) bulkG2S(S.objects, gObjects, uint32_t(no) * uint32_t(sizeof(MvObject)), &S.mbar);
+        }
+        __syncwarp();
+        mbarWait(&S.mbar, 0);
+    }
+
+    bool resetNow = P.forceReset != 0;
+    bool doneFlag = false;
+
+    if (!P.forceReset) {
+        ColliderView cv;
+        cv.S = &S; cv.ns = ns; cv.no = no; cv.A = A;
+
+        // ---- action phase (env.cpp:89-122)
+        for (int i = 0; i < A; ++i) {
+            MvAgent &a = S.agents[i];
+            const int act = P.actions[size_t(env) * A + i];
+            M3 basis;
+            for (int k = 0; k < 9; ++k) basis.r[k] = a.basis[k];
+            // forwardDirection / strafeLeftDirection use the basis BEFORE this step's look rotation? No: acceleration terms
+            // are gathered first, then look is applied (env.cpp:95-113) -- same order here.
+            V3 acc = v3(0, 0, 0);
+            const V3 fwd = btNormalized(v3(basis.r[6], basis.r[7], -basis.r[8]));
+            const V3 left = btNormalized(v3(-basis.r[0], basis.r[1], basis.r[2]));
+            if (act & MV_A_FORWARD) acc = acc + fwd;
+            else if (act & MV_A_BACKWARD) acc = acc - fwd;
+            if (act & MV_A_LEFT) acc = acc + left;
+            else if (act & MV_A_RIGHT) acc = acc - left;
+            if (act & (MV_A_LOOKLEFT | MV_A_LOOKRIGHT)) {
+                M3 rot;
+                const float *src = (act & MV_A_LOOKLEFT) ? P.k.look_left : P.k.look_right;
+                for (int k = 0; k < 9; ++k) rot.r[k] = src[k];
+                basis = mul3(basis, rot);
+            }
+            float curX = a.cur_x;
+            M4 cam = loadM4(a.cam_local);
+            const float lim = L->look_limit;
+            if (act & MV_A_LOOKUP) {
+                cam = mul4(cam, rotationX4(-curX));
+                curX += 1.5f * dt;
+                curX = lim < curX ? lim : curX;
+                cam = mul4(cam, rotationX4(curX));
+            } else if (act & MV_A_LOOKDOWN) {
+                cam = mul4(cam, rotationX4(-curX));
+                curX -= 1.5f * dt * 1.1f;
+                curX = -lim < curX ? curX : -lim;
+                cam = mul4(cam, rotationX4(curX));
+            }
+            Kcc k;
+            k.pos = v3(a.pos[0], a.pos[1], a.pos[2]); k.hvel = v3(a.hvel[0], a.hvel[1], a.hvel[2]);
+            k.jumpAxis = v3(a.jump_axis[0], a.jump_axis[1], a.jump_axis[2]);
+            k.vvel = a.vvel; k.voff = a.voff; k.stepOff = a.step_off; k.jumpSpeed = a.jump_speed;
+            k.wasOnGround = a.was_on_ground != 0; k.wasJumping = a.was_jumping != 0;
+            kccSetAcceleration(k, acc, dt);
+            if ((act & MV_A_JUMP) && k.onGround()) {  // agent.cpp:157-161, KCC::jump :625-644
+                const V3 jv = v3(0, 6.2f, 0);
+                k.jumpSpeed = length(jv);
+                k.vvel = k.jumpSpeed;
+                k.wasJumping = true;
+                k.jumpAxis = btNormalized(jv);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int q = 0; q < 9; ++q) a.basis[q] = basis.r[q];
+                a.cur_x = curX;
+                storeM4(a.cam_local, cam);
+                a.hvel[0] = k.hvel.x; a.hvel[1] = k.hvel.y; a.hvel[2] = k.hvel.z;
+                a.vvel = k.vvel; a.jump_speed = k.jumpSpeed; a.was_jumping = k.wasJumping;
+                a.jump_axis[0] = k.jumpAxis.x; a.jump_axis[1] = k.jumpAxis.y; a.jump_axis[2] = k.jumpAxis.z;
+            }
+            __syncwarp();
+        }
+
+        // ---- stepSimulation: action interfaces in agent order (env.cpp:126)
+        for (int i = 0; i < A; ++i) {
+            MvAgent &a = S.agents[i];
+            Kcc k;
+            k.pos = v3(a.pos[0], a.pos[1], a.pos[2]); k.hvel = v3(a.hvel[0], a.hvel[1], a.hvel[2]);
+            k.jumpAxis = v3(a.jump_axis[0], a.jump_axis[1], a.jump_axis[2]);
+            k.vvel = a.vvel; k.voff = a.voff; k.stepOff = a.step_off; k.jumpSpeed = a.jump_speed;
+            k.wasOnGround = a.was_on_ground != 0; k.wasJumping = a.was_jumping != 0;
+            kccPlayerStep(k, cv, ns + no + i, dt, P.k.max_slope_cos, lane);
+            __syncwarp();
+            if (lane == 0) {
+                a.pos[0] = k.pos.x; a.pos[1] = k.pos.y; a.pos[2] = k.pos.z;
+                a.hvel[0] = k.hvel.x; a.hvel[1] = k.hvel.y; a.hvel[2] = k.hvel.z;
+                a.vvel = k.vvel; a.voff = k.voff; a.step_off = k.stepOff;
+                a.was_on_ground = k.wasOnGround; a.was_jumping = k.wasJumping;
+            }
+            __syncwarp();
+        }
+        // agent->updateTransform() (env.cpp:128-129)
+        for (int i = lane; i < A; i += 32) {
+            M4 ot;
+            if (updateTransform(S.agents[i], ot)) storeM4(S.agents[i].object_t, ot);
+            else S.env.faults |= MV_FAULT_NAN;
+        }
+        __syncwarp();
+
+        // ---- scenario step: interact, fall detection, shaping rewards -- scalar work, lane 0
+        if (lane == 0) {
+            MvEnvState &e = S.env;
+            const float *rt = P.rtable + size_t(env) * A * MV_R_COUNT;
+            auto rewardAgent = [&](int slotR, int ai, float mult) { S.lastReward[ai] += rt[ai * MV_R_COUNT + slotR] * mult; };
+            auto rewardTeam = [&](int slotR, int ai, float mult) {
+                rewardAgent(slotR, ai, mult * (1 - rt[ai * MV_R_COUNT + MV_R_TEAM_SPIRIT]));
+                for (int j = 0; j < A; ++j) S.lastReward[j] += rt[j * MV_R_COUNT + slotR] * rt[j * MV_R_COUNT + MV_R_TEAM_SPIRIT] * mult / A;
+            };
+            const float carryingScale = 0.78f, carryingScaleInverse = 1.0f / carryingScale;
+            for (int i = 0; i < A; ++i) {
+                if (!(P.actions[size_t(env) * A + i] & MV_A_INTERACT)) continue;
+                MvAgent &a = S.agents[i];
+                const M4 objT = loadM4(a.object_t), cam = loadM4(a.cam_local);
+                const M4 pickAbs = mul4(mul4(objT, cam), pickupLocal());
+                if (a.carrying >= 0) {
+                    const int oi = a.carrying;
+                    MvObject &o = S.objects[oi];
+                    const M4 local = mul4(translation4(v3(o.t[0], o.t[1], o.t[2])), mul4(scaling4(v3(o.s[0], o.s[1], o.s[2])), identity4()));
+                    const V3 t = translationOf(mul4(pickAbs, local));
+                    int vx, vy, vz;
+                    toVoxel(t, vx, vy, vz);
+                    const int gi = gridIndex(*L, vx, vy, vz);
+                    bool collidesWithAgent = false;
+                    for (int j = 0; j < A; ++j) {
+                        if (j == i) continue;
+                        int cx, cy, cz;
+                        toVoxel(v3(S.agents[j].object_t[12], S.agents[j].object_t[13], S.agents[j].object_t[14]), cx, cy, cz);
+                        if (cx == vx && cy == vy && cz == vz) { collidesWithAgent = true; break; }
+                    }
+                    const uint32_t *sol = P.solid + (size_t(env) * 2 + slot) * P.gridWords;
+                    auto solidAt = [&](int g) { return g >= 0 && ((sol[g >> 5] >> (g & 31)) & 1u); };
+                    auto objAt = [&](int g) { return g >= 0 ? int(objGrid[g]) : int(MV_NO_OBJECT); };
+                    const bool empty = !solidAt(gi) && objAt(gi) == MV_NO_OBJECT;
+                    if (empty && !collidesWithAgent && inBuildingZone(*L, vx, vz)) {
+                        while (true) {
+                            const int by = vy - 1;
+                            if (by < -30) break;
+                            const int gb = gridIndex(*L, vx, by, vz);
+                            if (solidAt(gb) || objAt(gb) != MV_NO_OBJECT) break;
+                            vy = by;
+                        }
+                        const int gp = gridIndex(*L, vx, vy, vz);
+                        if (gp >= 0) objGrid[gp] = uint8_t(oi); else e.faults |= MV_FAULT_GRID_RANGE;
+                        const V3 sc = scalingOf(local);
+                        o.parent = -1;
+                        o.s[0] = sc.x * carryingScaleInverse; o.s[1] = sc.y * carryingScaleInverse; o.s[2] = sc.z * carryingScaleInverse;
+                        o.t[0] = float(vx) + 0.5f; o.t[1] = float(vy) + 0.5f; o.t[2] = float(vz) + 0.5f;
+                        syncPoseScene(o);
+                        o.enabled = !o.enabled;
+                        a.carrying = -1;
+                        S.objDirty[S.nDirty++] = oi;
+                        // placedObject (scenario_tower_building.cpp:206-214)
+                        if (inBuildingZone(*L, vx, vz)) mvBzInsert(e, vx, vy, vz);
+                        const float newReward = towerReward(e);
+                        const float delta = newReward - e.bz_reward;
+                        e.bz_reward = newReward;
+                        rewardTeam(MV_R_TOWER_BUILDING, i, delta);
+                        const int hgt = vy - L->bz_min[1] + 1;
+                        e.highest_tower = e.highest_tower > hgt ? e.highest_tower : hgt;
+                    }
+                } else {
+                    const V3 pickup = translationOf(pickAbs);
+                    int vx, vy, vz;
+                    vx = int(lroundf(floorf(pickup.x))); vy = int(lroundf(floorf(pickup.y))); vz = int(lroundf(floorf(pickup.z)));
+                    int pickupHeight = 0;
+                    while (pickupHeight <= 1) {
+                        const int g = gridIndex(*L, vx, vy, vz), ga = gridIndex(*L, vx, vy + 1, vz);
+                        const int here = g >= 0 ? int(objGrid[g]) : int(MV_NO_OBJECT);
+                        const bool hasAbove = ga >= 0 && objGrid[ga] != MV_NO_OBJECT;
+                        if (here != MV_NO_OBJECT && !hasAbove) {
+                            MvObject &o = S.objects[here];
+                            o.enabled = !o.enabled;
+                            const M4 local = mul4(translation4(v3(o.t[0], o.t[1], o.t[2])), mul4(scaling4(v3(o.s[0], o.s[1], o.s[2])), identity4()));
+                            const V3 sc = scalingOf(local);
+                            o.s[0] = sc.x * carryingScale; o.s[1] = sc.y * carryingScale; o.s[2] = sc.z * carryingScale;
+                            o.t[0] = 0.0f; o.t[1] = -0.3f; o.t[2] = 0.0f;
+                            o.parent = i;
+                            a.carrying = here;
+                            objGrid[g] = MV_NO_OBJECT;
+                            S.objDirty[S.nDirty++] = here;
+                            // pickedObject (scenario_tower_building.cpp:216-225)
+                            if (inBuildingZone(*L, vx, vz)) mvBzErase(e, vx, vy, vz);
+                            if (!a.picked_up) { rewardAgent(MV_R_TOWER_PICKED_UP, i, 1); a.picked_up = 1; }
+                            break;
+                        } else vy += 1;
+                        ++pickupHeight;
+                    }
+                }
+            }
+            // FallDetectionComponent::step
+            for (int i = 0; i < A; ++i) {
+                MvAgent &a = S.agents[i];
+                if (a.object_t[13] < -20) {
+                    V3 p = v3(L->init_pos[i][0], L->init_pos[i][1], L->init_pos[i][2]);
+                    const uint32_t *sol = P.solid + (size_t(env) * 2 + slot) * P.gridWords;
+                    while (p.y < 1000) {
+                        int x, y, z;
+                        toVoxel(p, x, y, z);
+                        const int g = gridIndex(*L, x, y, z);
+                        const bool solid = g >= 0 && ((sol[g >> 5] >> (g & 31)) & 1u);
+                        if (!solid) break;
+                        p.y += 1;
+                    }
+                    const float halfVoxel = 1.0f / 2;
+                    a.pos[0] = p.x + halfVoxel; a.pos[1] = p.y + halfVoxel; a.pos[2] = p.z + halfVoxel;
+                    for (int q = 0; q < 9; ++q) a.basis[q] = (q % 4 == 0) ? 1.0f : 0.0f;  // warp(): rotation reset to identity
+                    a.hvel[0] = a.hvel[1] = a.hvel[2] = 0.0f;
+                    a.vvel = 0;
+                }
+            }
+            // shaping: carrying an object inside the building zone
+            for (int i = 0; i < A; ++i) {
+                MvAgent &a = S.agents[i];
+                if (a.carrying >= 0) {
+                    int x, y, z;
+                    toVoxel(v3(a.object_t[12], a.object_t[13], a.object_t[14]), x, y, z);
+                    if (inBuildingZone(*L, x, z) && !a.visited_bz) {
+                        rewardTeam(MV_R_TOWER_VISITED_BZ, i, 1);
+                        a.visited_bz = 1;
+                    }
+                }
+            }
+            // env.cpp:133-152
+            e.episode_sec += dt;
+            const float len = L->episode_len_base + 4.0f * float(L->n_movable);
+            {
+                const float frac0 = (len - e.episode_sec) / len;
+                const float frac = frac0 > 0.0f ? frac0 : 0.0f;
+                for (int i = 0; i < A; ++i) {
+                    MvAgent &a = S.agents[i];
+                    const float req[3] = {frac * 0.24f, float(0.0015), float(0.001)};
+                    for (int q = 0; q < 3; ++q) {
+                        const float sc = sqrtf(a.bar_scale[q] * a.bar_scale[q] + 0.0f * 0.0f + 0.0f * 0.0f);
+                        a.bar_scale[q] = a.bar_scale[q] * (req[q] / sc);
+                    }
+                }
+            }
+            for (int i = 0; i < A; ++i) S.agents[i].total_reward += S.lastReward[i];
+            e.num_frames += 1;
+            S.doneFlag = (e.episode_sec >= len) ? 1 : 0;
+        }
+        __syncwarp();
+        doneFlag = S.doneFlag != 0;
+        resetNow = doneFlag;
+    }
+
+    // ---- outputs of the finished step; VectorEnv::step captures trueObjective BEFORE reset and the rewards AFTER it (zeroed)
+    if (!P.forceReset) {
+        for (int i = lane; i < A; i += 32) {
+            if (doneFlag) P.trueObjectives[size_t(env) * A + i] = float(S.env.highest_tower);
+            P.rewards[size_t(env) * A + i] = doneFlag ? 0.0f : S.lastReward[i];
+        }
+        if (lane == 0) P.dones[env] = doneFlag ? 1 : 0;
+    } else {
+        for (int i = lane; i < A; i += 32) P.rewards[size_t(env) * A + i] = 0.0f;
+        if (lane == 0) P.dones[env] = 0;
+    }
+
+    if (resetNow) {
+        // flip to the pre-staged next level (episode end, or mv_reset forcing a new episode everywhere)
+        slot ^= 1;
+        L = &P.levels[size_t(env) * 2 + slot];
+        if (lane == 0) {
+            S.env.slot = slot;
+            S.env.episode_idx += 1;
+            if (L->serial != S.env.episode_idx) S.env.faults |= MV_FAULT_LEVEL_NOT_READY;
+        }
+        __syncwarp();
+        ns = L->n_static; no = L->n_obj;
+        resetEnv(S, *L, objGrid, P.gridCells, A, lane);
+        // all objects are fresh: write the whole array back
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&S.objects[0]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(gObjects);
+            for (int i = lane; i < int(sizeof(MvObject) / 4) * no; i += 32) dst[i] = src[i];
+        }
+    } else {
+        // write back the (at most 2A) objects touched this step
+        const int nd = S.nDirty;
+        for (int d = 0; d < nd; ++d) {
+            const int oi = S.objDirty[d];
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&S.objects[oi]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&gObjects[oi]);
+            for (int i = lane; i < int(sizeof(MvObject) / 4); i += 32) dst[i] = src[i];
+        }
+    }
+    __syncwarp();
+
+    writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 2, P.views + size_t(env) * A * 16, A, resetNow, lane);
+
+    // ---- commit env + agents
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&S.env);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&P.envs[env]);
+        for (int i = lane; i < int(sizeof(MvEnvState) / 4); i += 32) dst[i] = src[i];
+        const uint32_t *asrc = reinterpret_cast<const uint32_t *>(&S.agents[0]);
+        uint32_t *adst = reinterpret_cast<uint32_t *>(&P.agents[size_t(env) * A]);
+        for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
+    }
+}
+
+}  // namespace mvk

@@ -241,6 +241,24 @@ int orc_get_mesh(int type, uint32_t *vtx, int capV, uint16_t *idx, int capI) {
     std::memcpy(idx, m.idx, size_t(m.ni) * 2);
     return m.nv * 65536 + m.ni;
 }
+// iteration order of a REAL std::unordered_set<VoxelCoords> (the reference's objectsInBuildingZone type) after a sequence
+// of ops {op(0 insert, 1 erase, 2 clear), x, y, z}: pins the product's libstdc++-order emulation (csrc/bzset.h)
+int orc_unordered_set_order(const int32_t *ops, int nops, int32_t *out, int cap) {
+    std::unordered_set<VoxelCoords, VoxelHash> s;
+    for (int i = 0; i < nops; ++i) {
+        const int32_t *o = ops + i * 4;
+        if (o[0] == 0) s.insert({o[1], o[2], o[3]});
+        else if (o[0] == 1) s.erase({o[1], o[2], o[3]});
+        else s.clear();
+    }
+    int n = 0;
+    for (auto &v : s) {
+        if (n * 3 + 3 > cap) return -1;
+        out[n * 3] = v.x; out[n * 3 + 1] = v.y; out[n * 3 + 2] = v.z;
+        ++n;
+    }
+    return n;
+}
 int orc_max_threads() { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"

@@ -18,6 +18,16 @@
 
 namespace orc {
 
+// Transcendentals are evaluated in double and rounded once to float ("correctly rounded" up to ~1e-9 of inputs).
+// The reference calls glibc's float sinf/cosf/acosf (Magnum: std::sin(Float); Bullet: btSin/btAcos -> sinf/acosf),
+// which are NOT correctly rounded (measured here: 2-8 % of inputs differ by 1 ulp from the rounded double result) and
+// differ between glibc versions, so they cannot be reproduced bit-for-bit on a GPU.  Oracle and device both use
+// float(fn(double(x))): the reference's value is within 1 ulp of it.
+inline float crsin(float x) { return float(std::sin(double(x))); }
+inline float crcos(float x) { return float(std::cos(double(x))); }
+inline float cracos(float x) { return float(std::acos(double(x))); }
+inline float crtan(float x) { return float(std::tan(double(x))); }
+
 struct Vec3 {
     float x = 0, y = 0, z = 0;
     Vec3() = default;
@@ -62,8 +72,8 @@ struct Quat { float x = 0, y = 0, z = 0, w = 1; };
 // btQuaternion(axis, angle)::setRotation
 inline Quat quatAxisAngle(Vec3 axis, float angle) {
     float d = length(axis);
-    float s = sinf(angle * 0.5f) / d;
-    return {axis.x * s, axis.y * s, axis.z * s, cosf(angle * 0.5f)};
+    float s = crsin(angle * 0.5f) / d;
+    return {axis.x * s, axis.y * s, axis.z * s, crcos(angle * 0.5f)};
 }
 // btMatrix3x3::setRotation(q)
 inline Mat3 mat3FromQuat(const Quat &q) {
@@ -103,7 +113,7 @@ inline Quat quatFromMat3(const Mat3 &m) {
     return {t[0], t[1], t[2], t[3]};
 }
 // btQuaternion::getAngle: 2*acos(w);  getAxis: s2 = 1-w*w; if (s2 < 10*eps) (1,0,0) else xyz/sqrt(s2)
-inline float quatAngle(const Quat &q) { return 2.0f * acosf(q.w); }
+inline float quatAngle(const Quat &q) { return 2.0f * cracos(q.w); }
 inline Vec3 quatAxis(const Quat &q) {
     float s2 = 1.0f - q.w * q.w;
     if (s2 < 10.0f * 1.1920929e-07f) return {1, 0, 0};
@@ -133,19 +143,19 @@ inline Mat4 mul(const Mat4 &a, const Mat4 &b) {
 inline Mat4 mat4Translation(Vec3 t) { Mat4 m = mat4Identity(); m.c[3][0] = t.x; m.c[3][1] = t.y; m.c[3][2] = t.z; return m; }
 inline Mat4 mat4Scaling(Vec3 s) { Mat4 m = mat4Identity(); m.c[0][0] = s.x; m.c[1][1] = s.y; m.c[2][2] = s.z; return m; }
 inline Mat4 mat4RotationX(float a) {
-    float s = sinf(a), c = cosf(a);
+    float s = crsin(a), c = crcos(a);
     Mat4 m = mat4Identity();
     m.c[1][1] = c; m.c[1][2] = s; m.c[2][1] = -s; m.c[2][2] = c;
     return m;
 }
 inline Mat4 mat4RotationY(float a) {
-    float s = sinf(a), c = cosf(a);
+    float s = crsin(a), c = crcos(a);
     Mat4 m = mat4Identity();
     m.c[0][0] = c; m.c[0][2] = -s; m.c[2][0] = s; m.c[2][2] = c;
     return m;
 }
 inline Mat4 mat4Rotation(float angle, Vec3 ax) {
-    float sine = sinf(angle), cosine = cosf(angle), omc = 1.0f - cosine;
+    float sine = crsin(angle), cosine = crcos(angle), omc = 1.0f - cosine;
     float xx = ax.x * ax.x, xy = ax.x * ax.y, xz = ax.x * ax.z, yy = ax.y * ax.y, yz = ax.y * ax.z, zz = ax.z * ax.z;
     Mat4 m = mat4Identity();
     m.c[0][0] = cosine + xx * omc; m.c[0][1] = xy * omc + ax.z * sine; m.c[0][2] = xz * omc - ax.y * sine;

@@ -189,6 +189,17 @@ inline SweepHit convexSweep(const std::vector<Collider> &cols, int self, Vec3 fr
     for (int i = 0; i < int(cols.size()); ++i) {
         const Collider &c = cols[i];
         if (i == self || !c.enabled) continue;
+        {   // broadphase, the role btRayAabb plays in btGhostObject::convexSweepTest: skip colliders whose bounds grown by
+            // the capsule extents (full radius: 0.04 more than the narrow phase needs) miss the sweep segment's box
+            const Vec3 ext = c.kind == 0 ? Vec3{c.h.x + kCapsuleRadius, c.h.y + (kCapsuleHalfHeight + kCapsuleRadius), c.h.z + kCapsuleRadius}
+                                         : Vec3{2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius};
+            bool miss = false;
+            for (int ax = 0; ax < 3; ++ax) {
+                const float lo = from[ax] < to[ax] ? from[ax] : to[ax], hi = from[ax] < to[ax] ? to[ax] : from[ax];
+                if (hi < c.c[ax] - ext[ax] || lo > c.c[ax] + ext[ax]) miss = true;
+            }
+            if (miss) continue;
+        }
         float t;
         Vec3 n;
         bool hit;
@@ -223,7 +234,7 @@ struct KCC {
     float fallSpeed = 55.0f, jumpSpeed = 10.0f;
     float stepHeight = 0.2f;
     float gravity = 1.4f * 9.8f;
-    float maxSlopeCosine = cosf(45.0f * (3.14159265358979323846f / 180.0f));  // btCos(btRadians(45))
+    float maxSlopeCosine = crcos(45.0f * (3.14159265358979323846f / 180.0f));  // btCos(btRadians(45))
     float maxPenetrationDepth = 0.041f;
     float currentStepOffset = 0;
     bool wasOnGround = false, wasJumping = false;

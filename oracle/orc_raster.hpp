@@ -35,7 +35,7 @@ struct Projection {
     float p00, p11, p22, p32;
     Projection(int W, int H, float hfovDeg = 100.0f, float nearZ = 0.01f, float farZ = 120.0f) {
         const float aspect = float(W) / float(H);
-        const float halfTan = tanf((hfovDeg * 0.01745329251994329576923690768489f) / 2.0f);  // glm::radians(hfov)/2
+        const float halfTan = crtan((hfovDeg * 0.01745329251994329576923690768489f) / 2.0f);  // glm::radians(hfov)/2
         p00 = 1.0f / halfTan;
         p11 = -aspect / halfTan;
         p22 = farZ / (nearZ - farZ);
@@ -166,9 +166,6 @@ inline void renderView(const Mat4 &view, const std::vector<Instance> &instances,
         // pixel px has its centre at px*256+128
         int px0 = std::max(0, (minx - 128 + 255) >> 8), px1 = std::min(W - 1, (maxx - 128) >> 8);
         int py0 = std::max(0, (miny - 128 + 255) >> 8), py1 = std::min(H - 1, (maxy - 128) >> 8);
-        if (minx - 128 + 255 < 0) px0 = 0;
-        if (miny - 128 + 255 < 0) py0 = 0;
-        if (maxx < 128 || maxy < 128) continue;
         // edges: e0 = v1->v2 (weight of v0), e1 = v2->v0 (v1), e2 = v0->v1 (v2)
         bool topleft[3];
         int64_t A[3], B[3], C[3];
@@ -179,7 +176,7 @@ inline void renderView(const Mat4 &view, const std::vector<Instance> &instances,
             A[e] = dy; B[e] = -dx; C[e] = dx * t.y[a] - dy * t.x[a];
             topleft[e] = (dy == 0 && dx < 0) || dy > 0;
         }
-        const float fArea = float(t.area);
+        const float invArea = 1.0f / float(t.area);
         for (int py = py0; py <= py1; ++py)
             for (int px = px0; px <= px1; ++px) {
                 const int64_t sx = int64_t(px) * 256 + 128, sy = int64_t(py) * 256 + 128;
@@ -190,7 +187,7 @@ inline void renderView(const Mat4 &view, const std::vector<Instance> &instances,
                     if (F[e] < 0 || (F[e] == 0 && !topleft[e])) { inside = false; break; }
                 }
                 if (!inside) continue;
-                const float l0 = float(F[0]) / fArea, l1 = float(F[1]) / fArea, l2 = float(F[2]) / fArea;
+                const float l0 = float(F[0]) * invArea, l1 = float(F[1]) * invArea, l2 = float(F[2]) * invArea;
                 const float z = (l0 * t.z[0] + l1 * t.z[1]) + l2 * t.z[2];
                 const size_t pi = size_t(py) * W + px;
                 if (z <= zbuf[pi]) {
