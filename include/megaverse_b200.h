@@ -102,6 +102,10 @@ int mv_debug_get_view(mv_handle h, int env, int agent, float *out16);
 /* render caller-supplied instances (18 floats each: mesh, colour, 16 model) with one view matrix through the CUDA
  * rasteriser: rgba uint8[h][w][4], depth float[h][w] or NULL.  Host pointers. */
 int mv_debug_render_instances(const float *view16, const float *inst18, int n, int w, int h, uint8_t *rgba, float *depth);
+/* host-only (no CUDA needed): run the level generator for the env RNG stream seeded with env_seed and dump the level of
+ * episode `episode` (mv_debug_get_level layout, followed by each agent's 9 spawn-basis floats as bit patterns) */
+int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, int episode, const char *const *param_keys,
+                            const float *param_vals, int nparams, int32_t *out, int cap);
 /* libstdc++ unordered_set iteration-order emulation (bzset.h): ops[i] = {op(0 insert,1 erase,2 clear), x, y, z};
  * writes the final iteration order as xyz triples, returns the element count */
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);

@@ -50,6 +50,7 @@ def lib():
         L.mv_debug_get_view.argtypes = [vp, ci, ci, vp]
         L.mv_debug_render_instances.argtypes = [vp, vp, ci, ci, ci, vp, vp]
         L.mv_debug_bzset.argtypes = [vp, ci, vp, ci]
+        L.mv_debug_generate_level.argtypes = [C.c_char_p, ci, ci, ci, C.POINTER(C.c_char_p), C.POINTER(cf), ci, vp, ci]
         _lib = L
     return _lib
 
@@ -59,7 +60,7 @@ EXPORTS = [
     "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device",
     "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
-    "mv_debug_render_instances", "mv_debug_bzset",
+    "mv_debug_render_instances", "mv_debug_bzset", "mv_debug_generate_level",
 ]
 
 
@@ -205,6 +206,18 @@ def render_instances(view16, inst18, w, h, want_depth=False):
     if rc != MV_OK:
         raise MegaverseError(rc, "mv_debug_render_instances failed")
     return (rgba, depth) if want_depth else rgba
+
+
+def generate_level(scenario, num_agents, env_seed, episode, params=None):
+    """host-only level generation (no CUDA): int32 dump of episode `episode` of the env stream seeded with env_seed"""
+    params = params or {}
+    keys = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+    vals = (C.c_float * max(1, len(params)))(*[float(v) for v in params.values()])
+    out = np.zeros(1 << 14, dtype=np.int32)
+    n = lib().mv_debug_generate_level(scenario.encode(), num_agents, env_seed, episode, keys, vals, len(params), out.ctypes.data, out.size)
+    if n < 0:
+        raise MegaverseError(n, "mv_debug_generate_level failed")
+    return out[:n].copy()
 
 
 def bzset_order(ops):

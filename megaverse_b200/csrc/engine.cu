@@ -730,6 +730,45 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
     return ok ? MV_OK : MV_ERR_CUDA;
 }
 
+// host-only (no CUDA): run the product's level generator for env stream `env_seed` and dump episode `episode`'s level in
+// the mv_debug_get_level layout.  Lets the CPU test-suite compare level generation with the oracle without a GPU.
+int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, int episode, const char *const *keys, const float *vals, int nparams,
+                            int32_t *out, int cap) {
+    const int sc = scenario ? mv::scenarioFromName(scenario) : -1;
+    if (sc < 0 || num_agents < 1 || num_agents > MV_MAX_AGENTS || episode < 0) return MV_ERR_ARG;
+    mv::FloatParams params = mv::defaultFloatParams(sc);
+    for (int i = 0; i < nparams; ++i) params[keys[i]] = vals[i];
+    mv::LevelGenerator gen(sc, num_agents, params);
+    gen.seed((unsigned long)env_seed);
+    mv::LevelOut lo;
+    try {
+        for (int ep = 0; ep <= episode; ++ep) gen.generate(lo, ep, 1 << 30);
+    } catch (const std::exception &) { return MV_ERR_CAPACITY; }
+    const MvLevel &L = lo.level;
+    std::vector<int32_t> o;
+    o.push_back(L.n_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
+    for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
+    for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
+    for (int i = 0; i < L.n_static; ++i) {
+        const MvBox &b = L.statics[i];
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
+        o.push_back(b.flags); o.push_back(int(kPaletteRgb[b.color]));
+    }
+    for (int i = 0; i < L.n_terrain; ++i) {
+        o.push_back(4);
+        for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
+        for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
+    }
+    for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
+    for (int i = 0; i < num_agents; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
+    // spawn yaw basis bits, so the float side of spawnAgents is pinned too
+    for (int i = 0; i < num_agents; ++i) for (int k = 0; k < 9; ++k) { int32_t u; std::memcpy(&u, &L.spawn_basis[i][k], 4); o.push_back(u); }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    return int(o.size());
+}
+
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap) {
     MvEnvState s;
     std::memset(&s, 0, sizeof s);

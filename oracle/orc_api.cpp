@@ -259,6 +259,39 @@ int orc_unordered_set_order(const int32_t *ops, int nops, int32_t *out, int cap)
     }
     return n;
 }
+// restated math, exposed so tests/test_ref_shim.py can pin it against the real Magnum / util headers (oracle/_ref)
+static Mat4 loadM(const float *p) { Mat4 m; std::memcpy(&m.c[0][0], p, 64); return m; }
+void orc_mat4_mul(const float *a, const float *b, float *out) { const Mat4 m = mul(loadM(a), loadM(b)); std::memcpy(out, &m.c[0][0], 64); }
+void orc_mat4_inverted(const float *a, float *out) { const Mat4 m = inverted(loadM(a)); std::memcpy(out, &m.c[0][0], 64); }
+void orc_mat4_rotation(float angle, const float *ax, float *out) { const Mat4 m = mat4Rotation(angle, {ax[0], ax[1], ax[2]}); std::memcpy(out, &m.c[0][0], 64); }
+void orc_mat4_rotation_x(float angle, float *out) { const Mat4 m = mat4RotationX(angle); std::memcpy(out, &m.c[0][0], 64); }
+void orc_mat4_rotation_y(float angle, float *out) { const Mat4 m = mat4RotationY(angle); std::memcpy(out, &m.c[0][0], 64); }
+void orc_mat4_scaling_of(const float *a, float *out3) { const Vec3 s = scalingOf(loadM(a)); out3[0] = s.x; out3[1] = s.y; out3[2] = s.z; }
+void orc_mat4_transform_point(const float *a, const float *p, float *out3) { const Vec3 r = transformPoint(loadM(a), {p[0], p[1], p[2]}); out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; }
+void orc_vec3_normalized(const float *v, float *out3) { const Vec3 r = mgNormalized({v[0], v[1], v[2]}); out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; }
+unsigned long long orc_voxel_hash(int x, int y, int z) { return VoxelHash{}(VoxelCoords{x, y, z}); }
+void orc_rng_stream(unsigned seed, int lo, int hi, int n, int *ints, float *floats) {
+    Rng rng(seed);
+    for (int i = 0; i < n; ++i) ints[i] = randRange(lo, hi, rng);
+    for (int i = 0; i < n; ++i) floats[i] = frand(rng);
+}
+int orc_voxel_grid_order(const int *xyz, int n, int *out_xyz) {
+    VoxelGrid grid(100, {0, 0, 0}, 1);
+    for (int i = 0; i < n; ++i) grid.set({xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]}, Voxel{});
+    int k = 0;
+    const auto copy = grid.getHashMap();
+    for (auto &kv : copy) { out_xyz[k * 3] = kv.first.x; out_xyz[k * 3 + 1] = kv.first.y; out_xyz[k * 3 + 2] = kv.first.z; ++k; }
+    return k;
+}
+void orc_to_voxel(float x, float y, float z, int32_t *out) { const VoxelCoords v = toVoxel({x, y, z}); out[0] = v.x; out[1] = v.y; out[2] = v.z; }
+// libstdc++ stream probe: mt19937(42) first raw, uniform_int{0,9}, then frand
+void orc_rng_probe(double *out3) {
+    Rng raw(42);
+    out3[0] = double(raw());
+    Rng r(42);
+    out3[1] = double(std::uniform_int_distribution<>{0, 9}(r));
+    out3[2] = double(frand(r));
+}
 int orc_max_threads() { return int(std::thread::hardware_concurrency()); }
 
 }  // extern "C"

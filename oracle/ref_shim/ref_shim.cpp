@@ -1,0 +1,60 @@
+// ORACLE tooling (test infrastructure): C entry points into pieces of the REAL reference compiled in place from
+// /root/reference by oracle/Makefile (`make ref` -> oracle/_ref/libmvref.so): vendored Magnum math / primitives and the
+// reference's own util headers (voxel hash, RNG helpers).  Used by tests/test_ref_shim.py to pin the restatement in
+// oracle/orc_math.hpp and oracle/orc_level.hpp.  Nothing here is copied: the reference sources are #included where they lie.
+#include <cstring>
+#include <random>
+
+#include <Magnum/Magnum.h>
+#include <Magnum/Math/Matrix4.h>
+#include <Magnum/Math/Vector3.h>
+#include <Magnum/Primitives/Cube.h>
+#include <Magnum/Trade/MeshData.h>
+
+#include <util/util.hpp>        // src/libs/util/include/util/util.hpp: Rng, randRange, frand
+#include <util/voxel_grid.hpp>  // src/libs/util/include/util/voxel_grid.hpp: VoxelCoords hash, toVoxel, VoxelGrid
+
+using namespace Magnum;
+
+static Matrix4 load(const float *p) { return Matrix4::from(p); }
+static void store(const Matrix4 &m, float *p) { std::memcpy(p, m.data(), 64); }
+
+extern "C" {
+
+void ref_mat4_mul(const float *a, const float *b, float *out) { store(load(a) * load(b), out); }
+void ref_mat4_inverted(const float *a, float *out) { store(load(a).inverted(), out); }
+void ref_mat4_rotation(float angle, const float *axis3, float *out) { store(Matrix4::rotation(Rad(angle), Vector3{axis3[0], axis3[1], axis3[2]}), out); }
+void ref_mat4_rotation_x(float angle, float *out) { store(Matrix4::rotationX(Rad(angle)), out); }
+void ref_mat4_rotation_y(float angle, float *out) { store(Matrix4::rotationY(Rad(angle)), out); }
+void ref_mat4_scaling_of(const float *a, float *out3) { const Vector3 s = load(a).scaling(); out3[0] = s.x(); out3[1] = s.y(); out3[2] = s.z(); }
+void ref_mat4_transform_point(const float *a, const float *p3, float *out3) {
+    const Vector3 r = load(a).transformPoint({p3[0], p3[1], p3[2]});
+    out3[0] = r.x(); out3[1] = r.y(); out3[2] = r.z();
+}
+void ref_vec3_normalized(const float *v3, float *out3) {
+    const Vector3 r = Vector3{v3[0], v3[1], v3[2]}.normalized();
+    out3[0] = r.x(); out3[1] = r.y(); out3[2] = r.z();
+}
+// the reference's voxel hash (voxel_grid.hpp:39-49) and point -> voxel (voxel_grid.hpp:18-21)
+unsigned long long ref_voxel_hash(int x, int y, int z) { return std::hash<Megaverse::VoxelCoords>{}(Megaverse::VoxelCoords{x, y, z}); }
+void ref_to_voxel(float x, float y, float z, int *out3) {
+    const Megaverse::VoxelCoords v = Megaverse::toVoxel({x, y, z});
+    out3[0] = v.x(); out3[1] = v.y(); out3[2] = v.z();
+}
+// the reference's RNG helpers (util.hpp:25-49): n draws of randRange(lo,hi) then n of frand from mt19937(seed)
+void ref_rng_stream(unsigned seed, int lo, int hi, int n, int *ints, float *floats) {
+    Megaverse::Rng rng(seed);
+    for (int i = 0; i < n; ++i) ints[i] = Megaverse::randRange(lo, hi, rng);
+    for (int i = 0; i < n; ++i) floats[i] = Megaverse::frand(rng);
+}
+// iteration order of the reference's VoxelGrid hash map after inserting the given coords (component_voxel_grid.hpp:114)
+int ref_voxel_grid_order(const int *xyz, int n, int *out_xyz) {
+    Megaverse::VoxelGrid<int> grid(100, {0, 0, 0}, 1);
+    for (int i = 0; i < n; ++i) grid.set({xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2]}, i);
+    int k = 0;
+    const auto copy = grid.getHashMap();
+    for (auto &kv : copy) { out_xyz[k * 3] = kv.first.x(); out_xyz[k * 3 + 1] = kv.first.y(); out_xyz[k * 3 + 2] = kv.first.z(); ++k; }
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""CPU-only tests (`-m "not gpu"`): the oracle against the reference's own pins, host level generation against the oracle,
+the libstdc++ hash-set order emulation, and the C ABI's exported symbols.  No compute call needs a GPU here."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(built):
+    """every function include/megaverse_b200.h declares is exported by the in-tree .so, and the list in capi.py is complete"""
+    import re
+    from megaverse_b200 import capi
+
+    hdr = open(os.path.join(ROOT, "include", "megaverse_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(mv_[a-z0-9_]+)\s*\(", hdr)))
+    assert sorted(capi.EXPORTS) == declared
+    L = C.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_no_cpu_fallback(built):
+    """without a CUDA device the product must fail loudly (no oracle / CPU path behind the ABI)"""
+    import torch
+    from megaverse_b200 import capi
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.MegaverseError) as ei:
+        capi.Engine("TowerBuilding", 1, 1)
+    assert ei.value.code == capi.MV_ERR_CUDA
+    with pytest.raises(capi.MegaverseError) as ei:
+        capi.Engine("NoSuchScenario", 1, 1)
+    assert ei.value.code == capi.MV_ERR_ARG
+
+
+def test_product_does_not_link_or_import_the_oracle(built):
+    from megaverse_b200 import capi
+
+    out = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "liborc" not in out
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "megaverse_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle/" not in txt.replace("oracle/ref_shim/dump_primitives.cpp", "").replace("oracle/orc_api.cpp", "").replace("`make -C oracle meshes`", ""), f
+                assert "liborc" not in txt and "import orc" not in txt, f
+
+
+def test_action_encoding(built):
+    """megaverse.cpp:100-116 / env.hpp:22-42: Left=1<<1 ... LookUp=1<<10"""
+    from megaverse_b200 import capi
+
+    assert capi.encode_action([1, 0, 0, 0, 0, 0]) == 1 << 1
+    assert capi.encode_action([2, 0, 0, 0, 0, 0]) == 1 << 2
+    assert capi.encode_action([0, 1, 0, 0, 0, 0]) == 1 << 3
+    assert capi.encode_action([0, 2, 0, 0, 0, 0]) == 1 << 4
+    assert capi.encode_action([0, 0, 1, 0, 0, 0]) == 1 << 5
+    assert capi.encode_action([0, 0, 2, 0, 0, 0]) == 1 << 6
+    assert capi.encode_action([0, 0, 0, 1, 0, 0]) == 1 << 7
+    assert capi.encode_action([0, 0, 0, 0, 1, 0]) == 1 << 8
+    assert capi.encode_action([0, 0, 0, 0, 0, 1]) == 1 << 9
+    assert capi.encode_action([0, 0, 0, 0, 0, 2]) == 1 << 10
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        heads = [int(rng.integers(0, s)) for s in helpers.SIZES]
+        assert capi.encode_action(heads) == helpers.encode(heads)
+
+
+def test_unordered_set_order_emulation(built):
+    """csrc/bzset.h reproduces the iteration order of a real std::unordered_set<VoxelCoords> (insert / erase / clear,
+    rehashes 1->13->29->59->127): the order TowerBuilding's float reward sum runs in"""
+    import orc
+    from megaverse_b200 import capi
+
+    L = orc.lib()
+    L.orc_unordered_set_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        ops, present = [], []
+        for _ in range(int(rng.integers(1, 220))):
+            r = rng.random()
+            if r < 0.6 or not present:
+                v = (int(rng.integers(0, 30)), int(rng.integers(0, 8)), int(rng.integers(0, 25)))
+                ops.append((0,) + v)
+                if v not in present:
+                    present.append(v)
+            elif r < 0.95:
+                v = present[int(rng.integers(0, len(present)))]
+                ops.append((1,) + v)
+                present.remove(v)
+            else:
+                ops.append((2, 0, 0, 0))
+                present = []
+            if len(present) > 110:
+                ops.append((2, 0, 0, 0))
+                present = []
+        ops = np.array(ops, dtype=np.int32)
+        out = np.zeros(3 * 256, dtype=np.int32)
+        k = L.orc_unordered_set_order(ops.ctypes.data, len(ops), out.ctypes.data, out.size)
+        assert np.array_equal(out[: k * 3].reshape(k, 3), capi.bzset_order(ops))
+
+
+@pytest.mark.parametrize("num_agents", [1, 4])
+def test_level_generation_matches_oracle(built, num_agents):
+    """the product's flat host level generator against the oracle's reference-style one: same RNG draws, same merged
+    boxes in the same order, same objects, spawn cells and spawn yaw bits -- over consecutive episodes of one stream"""
+    import orc
+    from megaverse_b200 import capi
+
+    for seed in range(40, 70):
+        o = orc.Oracle("TowerBuilding", 1, num_agents, render=False)
+        o.seed_env(0, seed)
+        for episode in range(3):
+            o.reset()
+            want = o.level(0)
+            got = capi.generate_level("TowerBuilding", num_agents, seed, episode)
+            n = len(want)
+            assert np.array_equal(want, got[:n]), "seed %d episode %d" % (seed, episode)
+            st = o.state(0)
+            basis = np.concatenate([st[8 + 26 * a + 3: 8 + 26 * a + 12] for a in range(num_agents)]).view(np.int32)
+            assert np.array_equal(basis, got[n:]), "spawn basis seed %d episode %d" % (seed, episode)
+        o.close()
+
+
+def test_oracle_reference_pins(built):
+    """the pins the reference's own tests hold for this path"""
+    import orc
+
+    L = orc.lib()
+    # src/test/src/voxel_grid_tests.cpp:25  getCoords({1.5,2.3,3.2}) == {1,2,3}  -- exercised through the pick-up voxel maths:
+    # the oracle's toVoxel is lround(floor(v)); check the documented example and a negative coordinate
+    L.orc_to_voxel.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
+    out = np.zeros(3, dtype=np.int32)
+    L.orc_to_voxel(1.5, 2.3, 3.2, out.ctypes.data)
+    assert out.tolist() == [1, 2, 3]
+    L.orc_to_voxel(-0.5, -1.0, 0.999, out.ctypes.data)
+    assert out.tolist() == [-1, -1, 0]
+    # megaverse/tests/test_env.py:42-53  same seed => identical first observation
+    a = orc.Oracle("TowerBuilding", 2, 2); b = orc.Oracle("TowerBuilding", 2, 2)
+    a.seed(42); b.seed(42); a.reset(); b.reset()
+    assert np.array_equal(a.obs(), b.obs())
+    c = orc.Oracle("TowerBuilding", 2, 2); c.seed(43); c.reset()
+    assert not np.array_equal(a.obs(), c.obs())
+    # megaverse/tests/test_env.py:123-140  reward shaping is per actor
+    v = C.c_float()
+    assert L.orc_get_reward_shaping(a.h_, 0, 0, b"teamSpirit", C.byref(v)) == 0 and abs(v.value - 0.1) < 1e-7
+    L.orc_set_reward_shaping(a.h_, 0, 1, b"teamSpirit", 0.5)
+    L.orc_get_reward_shaping(a.h_, 0, 0, b"teamSpirit", C.byref(v)); assert abs(v.value - 0.1) < 1e-7
+    L.orc_get_reward_shaping(a.h_, 0, 1, b"teamSpirit", C.byref(v)); assert abs(v.value - 0.5) < 1e-7
+    # libstdc++ stream pins probed by SURVEY.md Appendix C
+    L.orc_rng_probe.argtypes = [C.c_void_p]
+    pr = np.zeros(3, dtype=np.float64)
+    L.orc_rng_probe(pr.ctypes.data)
+    assert pr[0] == 1608637542 and pr[1] == 3 and abs(pr[2] - 0.796543002) < 1e-8
+    for x in (a, b, c):
+        x.close()
+
+
+def test_oracle_golden_trajectory(built):
+    """the oracle against committed golden vectors (tests/golden/tower_golden.npz, made by tests/golden/make_golden.py)"""
+    import orc
+
+    path = os.path.join(ROOT, "tests", "golden", "tower_golden.npz")
+    g = np.load(path)
+    o = orc.Oracle("TowerBuilding", int(g["E"]), int(g["A"]))
+    o.seed(int(g["seed"]))
+    o.reset()
+    assert np.array_equal(o.obs()[0], g["first_frame"])
+    for t, acts in enumerate(g["actions"]):
+        o.step(acts)
+        assert np.array_equal(o.rewards().view(np.uint32), g["rewards"][t].view(np.uint32)), t
+        assert np.array_equal(o.dones(), g["dones"][t]), t
+    assert np.array_equal(o.state(0).view(np.uint32), g["final_state0"].view(np.uint32))
+    assert np.array_equal(o.obs()[0], g["last_frame"])
+    o.close()
+
+
+def test_mesh_tables_match_reference_magnum(built):
+    """the oracle's mesh tables are the reference's Magnum primitives (counts from SURVEY.md 2.1) and the product's
+    __constant__ tables hold the same bits"""
+    import re
+    import orc
+
+    counts = {0: (24, 36), 1: (66, 384), 2: (42, 240), 3: (12, 36), 4: (26, 72)}
+    names = {0: "box", 1: "capsule", 2: "sphere", 3: "cone", 4: "cylinder"}
+    inc = open(os.path.join(ROOT, "megaverse_b200", "csrc", "mesh_tables.inc")).read()
+    for t, (nv, ni) in counts.items():
+        vtx, idx = orc.mesh(t)
+        assert vtx.shape == (nv, 6) and idx.shape == (ni,)
+        body = inc[inc.index("c_%sVerts" % names[t]):]
+        body = body[: body.index("};")]
+        vals = np.array([float.fromhex(x.rstrip("f")) for x in re.findall(r"-?0x[0-9a-f.]+p[+-]\d+f", body)], dtype=np.float32)
+        assert np.array_equal(vals.view(np.uint32).reshape(nv, 6), vtx), names[t]
+        ibody = inc[inc.index("c_%sIdx" % names[t]):]
+        ibody = ibody[ibody.index("{") + 1: ibody.index("};")]
+        assert np.array_equal(np.array([int(x) for x in ibody.replace("\n", " ").split(",") if x.strip()]), idx), names[t]
+    # unit normals, box is the +-1 cube
+    v, _ = orc.mesh(0)
+    assert set(np.unique(v[:, :3].view(np.float32)).tolist()) == {-1.0, 1.0}
+    for t in counts:
+        v, _ = orc.mesh(t)
+        nrm = np.linalg.norm(v[:, 3:].view(np.float32), axis=1)
+        assert np.allclose(nrm, 1.0, atol=1e-5)

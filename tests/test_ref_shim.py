@@ -1,0 +1,126 @@
+"""Pins the oracle's restated math against the pieces of the REAL reference that compile in place (oracle/_ref/libmvref.so,
+built by `make -C oracle ref` from /root/reference: vendored Magnum + the reference's util headers).  The .so travels to
+the GPU box; where it is absent (no /root/reference and never built) these tests skip."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libmvref.so")
+
+
+@pytest.fixture(scope="module")
+def libs(built):
+    import orc
+
+    if not os.path.exists(REF):
+        if os.path.isdir("/root/reference/src/3rdparty/magnum"):
+            import subprocess
+
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        else:
+            pytest.skip("oracle/_ref/libmvref.so not built and /root/reference absent")
+    R, O = C.CDLL(REF), orc.lib()
+    return R, O
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _rand_affine(rng):
+    """scene-graph style matrices: rotation * non-uniform scale + translation"""
+    ang = rng.uniform(-3, 3)
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    c, s = np.cos(ang), np.sin(ang)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    Rm = np.eye(3) + s * K + (1 - c) * K @ K
+    M = np.eye(4)
+    M[:3, :3] = Rm @ np.diag(rng.uniform(0.1, 20, size=3))
+    M[:3, 3] = rng.uniform(-30, 30, size=3)
+    return _f(M.T.reshape(-1))  # column-major
+
+
+def test_matrix_product_and_inverse_bit_exact(libs):
+    """Magnum RectangularMatrix::operator* and Matrix::inverted() (adjugate / determinant)"""
+    R, O = libs
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        a, b = _rand_affine(rng), _rand_affine(rng)
+        ro, oo = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        R.ref_mat4_mul(a.ctypes.data, b.ctypes.data, ro.ctypes.data)
+        O.orc_mat4_mul(a.ctypes.data, b.ctypes.data, oo.ctypes.data)
+        assert np.array_equal(ro.view(np.uint32), oo.view(np.uint32))
+        R.ref_mat4_inverted(a.ctypes.data, ro.ctypes.data)
+        O.orc_mat4_inverted(a.ctypes.data, oo.ctypes.data)
+        assert np.array_equal(ro.view(np.uint32), oo.view(np.uint32))
+        p = _f(rng.uniform(-5, 5, size=3))
+        r3, o3 = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        R.ref_mat4_transform_point(a.ctypes.data, p.ctypes.data, r3.ctypes.data)
+        O.orc_mat4_transform_point(a.ctypes.data, p.ctypes.data, o3.ctypes.data)
+        assert np.array_equal(r3.view(np.uint32), o3.view(np.uint32))
+        R.ref_mat4_scaling_of(a.ctypes.data, r3.ctypes.data)
+        O.orc_mat4_scaling_of(a.ctypes.data, o3.ctypes.data)
+        assert np.array_equal(r3.view(np.uint32), o3.view(np.uint32))
+        R.ref_vec3_normalized(p.ctypes.data, r3.ctypes.data)
+        O.orc_vec3_normalized(p.ctypes.data, o3.ctypes.data)
+        assert np.array_equal(r3.view(np.uint32), o3.view(np.uint32))
+
+
+def test_rotations_within_one_ulp(libs):
+    """Matrix4::rotation / rotationX / rotationY: identical structure; entries within 1 ulp because the reference calls
+    glibc's sinf/cosf while oracle and device use the correctly rounded value (DESIGN.md 'numerics')"""
+    R, O = libs
+    R.ref_mat4_rotation.argtypes = [C.c_float, C.c_void_p, C.c_void_p]
+    O.orc_mat4_rotation.argtypes = [C.c_float, C.c_void_p, C.c_void_p]
+    for f in (R.ref_mat4_rotation_x, R.ref_mat4_rotation_y, O.orc_mat4_rotation_x, O.orc_mat4_rotation_y):
+        f.argtypes = [C.c_float, C.c_void_p]
+    rng = np.random.default_rng(1)
+    exact = total = 0
+    for _ in range(2000):
+        ang = float(np.float32(rng.uniform(-3.2, 3.2)))
+        ax = rng.normal(size=3); ax = _f(ax / np.linalg.norm(ax))
+        ro, oo = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        for rf, of, args in ((R.ref_mat4_rotation, O.orc_mat4_rotation, (ax.ctypes.data,)), (R.ref_mat4_rotation_x, O.orc_mat4_rotation_x, ()),
+                             (R.ref_mat4_rotation_y, O.orc_mat4_rotation_y, ())):
+            rf(ang, *args, ro.ctypes.data)
+            of(ang, *args, oo.ctypes.data)
+            assert np.array_equal(ro == 0, oo == 0)
+            assert np.allclose(ro, oo, rtol=0, atol=2.5e-7), (ro, oo)
+            exact += int(np.array_equal(ro.view(np.uint32), oo.view(np.uint32))); total += 1
+    assert exact / total > 0.5
+
+
+def test_voxel_hash_rng_and_hash_map_order(libs):
+    """voxel_grid.hpp hash + toVoxel, util.hpp RNG helpers, and the iteration order of the voxel hash map that decides the
+    greedy box decomposition (component_voxel_grid.hpp:114-118)"""
+    R, O = libs
+    R.ref_voxel_hash.restype = C.c_ulonglong
+    O.orc_voxel_hash.restype = C.c_ulonglong
+    rng = np.random.default_rng(2)
+    for _ in range(300):
+        x, y, z = (int(v) for v in rng.integers(-500, 500, size=3))
+        assert R.ref_voxel_hash(x, y, z) == O.orc_voxel_hash(x, y, z)
+    R.ref_to_voxel.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
+    O.orc_to_voxel.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
+    for _ in range(300):
+        p = rng.uniform(-40, 40, size=3)
+        a, b = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        R.ref_to_voxel(*map(float, p), a.ctypes.data)
+        O.orc_to_voxel(*map(float, p), b.ctypes.data)
+        assert np.array_equal(a, b)
+    for seed in (1, 42, 12345):
+        ia, fa, ib, fb = np.zeros(64, np.int32), np.zeros(64, np.float32), np.zeros(64, np.int32), np.zeros(64, np.float32)
+        R.ref_rng_stream(seed, 3, 30, 64, ia.ctypes.data, fa.ctypes.data)
+        O.orc_rng_stream(seed, 3, 30, 64, ib.ctypes.data, fb.ctypes.data)
+        assert np.array_equal(ia, ib) and np.array_equal(fa.view(np.uint32), fb.view(np.uint32))
+    for _ in range(10):
+        L, Hh, Wd = int(rng.integers(12, 30)), int(rng.integers(5, 7)), int(rng.integers(12, 25))
+        pts = [(x, 0, z) for x in range(L) for z in range(Wd)] + [(0, y, z) for y in range(Hh) for z in range(Wd)] + [(x, y, 0) for x in range(L) for y in range(Hh)]
+        xyz = np.array(pts, dtype=np.int32)
+        oa, ob = np.zeros_like(xyz), np.zeros_like(xyz)
+        ka = R.ref_voxel_grid_order(xyz.ctypes.data, len(pts), oa.ctypes.data)
+        kb = O.orc_voxel_grid_order(xyz.ctypes.data, len(pts), ob.ctypes.data)
+        assert ka == kb and np.array_equal(oa[:ka], ob[:kb])
