@@ -113,8 +113,11 @@ struct mv_engine {
     std::unique_ptr<WorkerPool> pool;
 
     int gridCells = 0, gridWords = 0;
-    int triCap = 608;
-    bool wantDepth = false, obsToHost = true, didReset = false;
+    int triCap = 1024, chunkViews = 0;
+    std::atomic<int> maxItemsSeen{0};
+    bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
+    int numSMs = 148;
+    int tune = getenv("MV_TUNE") ? atoi(getenv("MV_TUNE")) : 0;
     MvConsts consts{};
 
     cudaStream_t stream = nullptr;
@@ -139,6 +142,11 @@ struct mv_engine {
     DevBuf<uint8_t> d_obs;
     DevBuf<float> d_depth;
     DevBuf<int32_t> d_faults;
+    DevBuf<int32_t> d_triCounts;
+    DevBuf<int32_t> d_tileCounter;
+    DevBuf<mvr::TriCover> d_cover;
+    DevBuf<mvr::TriShade> d_shade;
+    DevBuf<short4> d_bbox;
 
     PinBuf<MvLevel> h_levels;      // [E][2] staging mirror
     PinBuf<uint32_t> h_solid;      // [E][2][gridWords]
@@ -168,6 +176,13 @@ struct mv_engine {
                 std::lock_guard<std::mutex> lk(genMutex);
                 genErrors.push_back(ex.what());
                 return;
+            }
+            {
+                int boxes = out.level.n_terrain + out.level.n_obj + 2 * A;
+                for (int i = 0; i < out.level.n_static; ++i) boxes += (out.level.statics[i].flags & MV_OPAQUE) ? 1 : 0;
+                const int items = boxes * 6 + A * 128;
+                int cur = maxItemsSeen.load();
+                while (items > cur && !maxItemsSeen.compare_exchange_weak(cur, items)) {}
             }
             std::memcpy(&h_levels.p[size_t(e) * 2 + s], &out.level, sizeof(MvLevel));
             uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * gridWords;
@@ -206,6 +221,7 @@ struct mv_engine {
         sp.levels = d_levels.p; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
         sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
+        sp.triCounts = d_triCounts.p;
         sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
         sp.k = consts;
         const int warpsPerBlock = 2;
@@ -215,20 +231,43 @@ struct mv_engine {
         mvk::stepKernel<<<blocks, warpsPerBlock * 32, smem, stream>>>(sp);
         MV_CUDA(cudaGetLastError());
         MV_CUDA(cudaEventRecord(ev[1], stream));
+        launches += 1;
+        int rc = launchRaster();
+        if (rc) return rc;
+        MV_CUDA(cudaEventRecord(ev[2], stream));
+        return MV_OK;
+    }
+    // geometry + tile kernels over view chunks; the triangle scratch of a chunk is reused by the next one, so it stays
+    // L2 resident instead of growing with N
+    int launchRaster() {
         mvr::RasterParams rp;
         rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = MV_MAX_INSTANCES;
         rp.obs = d_obs.p; rp.depth = wantDepth ? d_depth.p : nullptr; rp.faults = d_faults.p;
-        rp.E = E; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
+        rp.cover = d_cover.p; rp.shade = d_shade.p; rp.bbox = d_bbox.p; rp.triCounts = d_triCounts.p;
+        rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.tune = tune;
+        rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
-        mvr::rasterKernel<<<N, 256, rasterSmem(), stream>>>(rp);
-        MV_CUDA(cudaGetLastError());
-        MV_CUDA(cudaEventRecord(ev[2], stream));
-        launches += 2;
+        const int nTiles = (W / 32) * (H / 4);
+        const int maxItems = MV_MAX_INSTANCES * 6 + A * 128;  // blocks past a view's real item count exit at once
+        const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
+        for (int base = 0; base < N; base += chunkViews) {
+            const int cv = std::min(chunkViews, N - base);
+            rp.viewBase = base; rp.chunkViews = cv;
+            mvr::geomKernel<<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+            MV_CUDA(cudaGetLastError());
+            const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * 8);  // persistent: 8 blocks of 4 warps per SM
+            if (fastShading) mvr::tileKernel<true><<<tileBlocks, 128, 0, stream>>>(rp);
+            else mvr::tileKernel<false><<<tileBlocks, 128, 0, stream>>>(rp);
+            MV_CUDA(cudaGetLastError());
+            launches += 2;
+        }
         return MV_OK;
     }
-    size_t rasterSmem() const {
-        const int tiles = (W / 32) * (H / 4);
-        return size_t(triCap) * sizeof(mvr::TriRec) + size_t(tiles) * size_t((triCap + 31) / 32) * 4;
+    int allocTriScratch() {
+        d_cover.free(); d_shade.free(); d_bbox.free();
+        const size_t cnt = size_t(chunkViews) * size_t(triCap);
+        if (d_cover.alloc(cnt) != cudaSuccess || d_shade.alloc(cnt) != cudaSuccess || d_bbox.alloc(cnt) != cudaSuccess) { setError("triangle scratch allocation failed"); return MV_ERR_CUDA; }
+        return MV_OK;
     }
 
     // after a step (or forced reset): flip host mirrors for finished envs and start generating the level after next
@@ -276,6 +315,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
+        d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_bbox.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -316,7 +356,6 @@ void fillConsts(MvConsts &k, int W, int H) {
 
 int setKernelAttrs(mv_engine *h) {
     cudaError_t err = cudaFuncSetAttribute(mvk::stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(mvk::WarpShared) * 4));
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(mvr::rasterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(h->rasterSmem()));
     if (err != cudaSuccess) { h->setError(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err)); return MV_ERR_CUDA; }
     return MV_OK;
 }
@@ -367,7 +406,11 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
          ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 2), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
-         ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults");
+         ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
+         ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter");
+    { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
+    e->chunkViews = int(std::min<size_t>(N, 512));
+    if (ok && e->allocTriScratch() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
          ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults");
@@ -379,7 +422,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     std::memset(e->h_obs.p, 0, N * px * 4);
     for (size_t v = 0; v < N; ++v) e->fillRtableRow(int(v));
     ok = ck(cudaMemset(e->d_trueObj.p, 0, sizeof(float) * N), "memset") && ck(cudaMemset(e->d_faults.p, 0, sizeof(int32_t) * E), "memset") &&
-         ck(cudaMemset(e->d_actions.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_agents.p, 0, sizeof(MvAgent) * N), "memset") &&
+         ck(cudaMemset(e->d_actions.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_triCounts.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_agents.p, 0, sizeof(MvAgent) * N), "memset") &&
          ck(cudaMemset(e->d_objects.p, 0, sizeof(MvObject) * E * MV_MAX_OBJECTS), "memset");
     if (!ok) return fail(MV_ERR_CUDA);
     if (uploadPalette(e) != MV_OK) return fail(MV_ERR_CUDA);
@@ -401,11 +444,13 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         return MV_OK;
     }
     if (k == "tri_cap") {
-        if (value < 64 || value > 1280) { h->setError("tri_cap out of range [64,1280]"); return MV_ERR_ARG; }
+        if (value < 64 || value > 16384) { h->setError("tri_cap out of range [64,16384]"); return MV_ERR_ARG; }
+        if (h->stream) cudaStreamSynchronize(h->stream);
         h->triCap = value;
-        return setKernelAttrs(h);
+        return h->allocTriScratch();
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
+    if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
     h->setError("unknown option " + k);
     return MV_ERR_ARG;
 }
@@ -701,22 +746,27 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
     MvConsts k;
     fillConsts(k, w, h);
     if (uploadPalette(&tmp) != MV_OK) return MV_ERR_CUDA;
-    const int triCap = 1024;
-    const size_t smem = size_t(triCap) * sizeof(mvr::TriRec) + size_t((w / 32) * (h / 4)) * size_t((triCap + 31) / 32) * 4;
-    if (cudaFuncSetAttribute(mvr::rasterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return MV_ERR_CUDA;
-    MvInstance *dInst = nullptr; int32_t *dCnt = nullptr, *dFault = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
+    const int triCap = 4096;
+    MvInstance *dInst = nullptr; int32_t *dCnt = nullptr, *dFault = nullptr, *dTri = nullptr, *dTileCtr = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
+    mvr::TriCover *dCover = nullptr; mvr::TriShade *dShade = nullptr; short4 *dBox = nullptr;
     const int32_t cnt[2] = {nBox, n};
     bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 8) == cudaSuccess && cudaMalloc(&dFault, 4) == cudaSuccess &&
-              cudaMalloc(&dView, 64) == cudaSuccess && cudaMalloc(&dObs, size_t(w) * h * 4) == cudaSuccess && cudaMalloc(&dDepth, size_t(w) * h * 4) == cudaSuccess;
+              cudaMalloc(&dView, 64) == cudaSuccess && cudaMalloc(&dObs, size_t(w) * h * 4) == cudaSuccess && cudaMalloc(&dDepth, size_t(w) * h * 4) == cudaSuccess &&
+              cudaMalloc(&dTri, 4) == cudaSuccess && cudaMalloc(&dTileCtr, 4) == cudaSuccess && cudaMalloc(&dCover, sizeof(mvr::TriCover) * triCap) == cudaSuccess &&
+              cudaMalloc(&dShade, sizeof(mvr::TriShade) * triCap) == cudaSuccess && cudaMalloc(&dBox, sizeof(short4) * triCap) == cudaSuccess;
     if (ok) {
         cudaMemcpy(dInst, inst.data(), sizeof(MvInstance) * inst.size(), cudaMemcpyHostToDevice);
         cudaMemcpy(dCnt, cnt, 8, cudaMemcpyHostToDevice);
         cudaMemcpy(dView, view16, 64, cudaMemcpyHostToDevice);
         cudaMemset(dFault, 0, 4);
+        cudaMemset(dTri, 0, 4);
         mvr::RasterParams rp;
         rp.instances = dInst; rp.instCounts = dCnt; rp.views = dView; rp.instStride = int(inst.size()); rp.obs = dObs; rp.depth = depth ? dDepth : nullptr;
-        rp.faults = dFault; rp.E = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
-        mvr::rasterKernel<<<1, 256, smem>>>(rp);
+        rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.bbox = dBox; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.tune = 0; rp.viewBase = 0; rp.chunkViews = 1;
+        rp.N = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
+        const int items = nBox * 6 + (n - nBox) * 128;
+        mvr::geomKernel<<<dim3(unsigned((items + 127) / 128 + 1), 1), 128>>>(rp);
+        mvr::tileKernel<false><<<((w / 32) * (h / 4) + 3) / 4, 128>>>(rp);
         ok = cudaDeviceSynchronize() == cudaSuccess;
         if (ok) {
             cudaMemcpy(rgba, dObs, size_t(w) * h * 4, cudaMemcpyDeviceToHost);
@@ -726,6 +776,7 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
             if (f) ok = false;
         }
     }
+    cudaFree(dTri); cudaFree(dTileCtr); cudaFree(dCover); cudaFree(dShade); cudaFree(dBox);
     cudaFree(dInst); cudaFree(dCnt); cudaFree(dFault); cudaFree(dView); cudaFree(dObs); cudaFree(dDepth);
     return ok ? MV_OK : MV_ERR_CUDA;
 }

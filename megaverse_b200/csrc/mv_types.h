@@ -53,6 +53,7 @@
 #define MV_FAULT_TRI_OVERFLOW 2      // a view produced more triangles than the rasteriser's shared-memory list holds
 #define MV_FAULT_GRID_RANGE 4        // an object was placed outside the dense voxel grid
 #define MV_FAULT_NAN 8               // NaN position (agent.cpp:82-93 guard)
+#define MV_FAULT_ENVELOPE 16         // an agent left the per-step collision envelope the candidate colliders were culled against
 
 struct MvBox {       // static layout box: drawable (OPAQUE) and/or collider (SOLID)
     float c[3];      // centre  = ((min+max)/2 + 0.5) * voxelSize        (layout_utils.cpp:30-34)

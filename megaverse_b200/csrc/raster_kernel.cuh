@@ -1,7 +1,12 @@
-// K4: batched first-person rasteriser.  One CTA per agent view; geometry set-up into shared memory, per-tile triangle
-// bit masks, one warp per 32x4-pixel tile, exact integer coverage (8-bit sub-pixel, top-left rule), perspective-correct
-// varyings, deferred Phong-clone shading, packed RGBA8 rows written with one 128-bit store per lane (8 lanes = one full
-// 128-byte line).
+// K4: batched first-person rasteriser, two kernels per view chunk.
+//
+//   geomKernel   one thread per (view, instance face | mesh triangle): model-view transform, near/far clip, projection,
+//                8-bit sub-pixel snap, back-face cull, edge/plane set-up -> per-view triangle list in global scratch
+//                (a few MB per chunk: stays L2 resident, never meant to reach HBM)
+//   tileKernel   one warp per 32x4-pixel tile of a view: lanes scan the view's triangle boxes 32 at a time (ballot), the
+//                surviving triangles are evaluated with exact integer edge functions (top-left rule), perspective-correct
+//                varyings, nearest fragment kept in registers (depth LESS_OR_EQUAL, later draw wins ties), deferred
+//                Phong-clone shading, packed RGBA8 written with one 128-bit store per lane (8 lanes = one 128-byte line)
 //
 // Replaces (file:line under /root/reference):
 //   V4R CommandStreamState::render        src/3rdparty/v4r/src/vulkan_state.inl:10-160
@@ -18,33 +23,45 @@
 namespace mvr {
 using namespace dm;
 
-struct RasterParams {
-    const MvInstance *instances; // [E][instStride] drawables in draw order (boxes first)
-    const int32_t *instCounts;   // [E][2] {boxes, total}
-    const float *views;          // [E*A][16]
-    int instStride;
-    uint8_t *obs;               // [N][H][W][4]
-    float *depth;               // [N][H][W] or nullptr
-    int32_t *faults;            // [E] (ORed)
-    int E, A, W, H;
-    int triCap;                 // shared-memory triangle capacity
-    float p00, p11, p22, p32;
-};
-
-struct __align__(8) TriRec {
+struct __align__(16) TriCover {  // what the coverage / depth loop reads (broadcast loads)
     long long C[3];     // edge constant terms, top-left bias already applied
     int32_t A[3], B[3];
     float z[3];
     float invArea;
     uint32_t key;       // draw order + 1 (later wins depth ties: LESS_OR_EQUAL)
-    int16_t px0, px1, py0, py1;
+    int32_t tl;         // bit e set: edge e is top-left (no bias was applied)
+    int32_t pad[2];
+};
+struct __align__(16) TriShade {  // what deferred shading reads for the winning fragment
     float rw[3];
     float p[9];
     float n[9];
     int32_t color;
-    int32_t tl;         // bit e set: edge e is top-left (no bias was applied)
+    int32_t pad[2];
 };
-static_assert(sizeof(TriRec) == 168, "TriRec layout");
+static_assert(sizeof(TriCover) == 80 && sizeof(TriShade) == 96, "triangle record layout");
+
+struct RasterParams {
+    const MvInstance *instances; // [E][instStride] drawables in draw order (boxes first)
+    const int32_t *instCounts;   // [E][2] {boxes, total}
+    const float *views;          // [E*A][16]
+    int instStride;
+    uint8_t *obs;                // [N][H][W][4]
+    float *depth;                // [N][H][W] or nullptr
+    int32_t *faults;             // [E] (ORed)
+    // triangle scratch for views [viewBase, viewBase + chunkViews)
+    TriCover *cover;             // [chunkViews][triCap]
+    TriShade *shade;             // [chunkViews][triCap]
+    short4 *bbox;                // [chunkViews][triCap] pixel boxes {x0, x1, y0, y1} inclusive
+    int32_t *triCounts;          // [N], zeroed before geomKernel (the step kernel does it)
+    int32_t *tileCounter;        // dynamic tile queue of the persistent tile warps (reset by geomKernel)
+    int tune;                    // experiment switches (MV_TUNE env var): bit0 adaptive lane-parallel chunks, bit1 view-minor tile order
+    int fastShading;             // 1: approximate rsqrt / fused multiply-add in the fragment stage (+-1 LSB), 0: bit-exact
+    int viewBase, chunkViews;
+    int N, A, W, H;
+    int triCap;
+    float p00, p11, p22, p32;
+};
 
 struct ClipVert { float cx, cy, cz, cw, px, py, pz, nx, ny, nz; };
 
@@ -58,41 +75,99 @@ __device__ __forceinline__ ClipVert lerpVert(const ClipVert &a, const ClipVert &
 __device__ __forceinline__ int32_t snapSub(float v) { return int32_t(floorf(v * 256.0f + 0.5f)); }
 
 struct SetupCtx {
-    TriRec *tris;
-    int *nTris;
+    TriCover *cover;
+    TriShade *shade;
+    short4 *bbox;
+    int32_t *nTris;
+    int32_t *fault;
     int triCap;
     int W, H;
-    int *overflow;
 };
+
+// one projected triangle: cull, box, edge / plane set-up, append to the view's list
+__device__ __forceinline__ void emitTri(const SetupCtx &cx, const ClipVert &va, const ClipVert &vb, const ClipVert &vc, const int32_t sxs[3], const int32_t sys[3],
+                                        const float szs[3], const float rws[3], int color, uint32_t key) {
+    const long long area2 = (long long)(sxs[1] - sxs[0]) * (long long)(sys[2] - sys[0]) - (long long)(sys[1] - sys[0]) * (long long)(sxs[2] - sxs[0]);
+    if (area2 >= 0) return;  // back-facing (visually clockwise with y down) or degenerate
+    const int32_t minx = min(sxs[0], min(sxs[1], sxs[2])), maxx = max(sxs[0], max(sxs[1], sxs[2]));
+    const int32_t miny = min(sys[0], min(sys[1], sys[2])), maxy = max(sys[0], max(sys[1], sys[2]));
+    const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(cx.W - 1, (maxx - 128) >> 8);
+    const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(cx.H - 1, (maxy - 128) >> 8);
+    if (px0 > px1 || py0 > py1) return;  // covers no pixel centre of the viewport
+    const int slot = atomicAdd(cx.nTris, 1);
+    if (slot >= cx.triCap) { atomicOr(cx.fault, MV_FAULT_TRI_OVERFLOW); return; }
+    TriCover c;
+    TriShade s;
+    const ClipVert *vs[3] = {&va, &vb, &vc};
+    int tl = 0;
+    long long worst = 0;
+    const long long wsub = (long long)cx.W * 256, hsub = (long long)cx.H * 256;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int a = (e + 1) % 3, b = (e + 2) % 3;
+        const long long dx = (long long)sxs[b] - sxs[a], dy = (long long)sys[b] - sys[a];
+        const bool topleft = (dy == 0 && dx < 0) || dy > 0;
+        c.A[e] = int32_t(dy);
+        c.B[e] = int32_t(-dx);
+        c.C[e] = dx * sys[a] - dy * sxs[a] - (topleft ? 0 : 1);
+        tl |= topleft ? (1 << e) : 0;
+        const long long bound = llabs(dy) * wsub + llabs(dx) * hsub + llabs(c.C[e]);
+        worst = bound > worst ? bound : worst;
+        c.z[e] = szs[e]; s.rw[e] = rws[e];
+        s.p[e * 3 + 0] = vs[e]->px; s.p[e * 3 + 1] = vs[e]->py; s.p[e * 3 + 2] = vs[e]->pz;
+        s.n[e * 3 + 0] = vs[e]->nx; s.n[e * 3 + 1] = vs[e]->ny; s.n[e * 3 + 2] = vs[e]->nz;
+    }
+    c.tl = tl;
+    c.invArea = 1.0f / float(-area2);
+    c.key = key;
+    c.pad[0] = worst < (1ll << 30) ? 1 : 0;  // every edge function fits int32 anywhere in the viewport
+    c.pad[1] = 0;
+    s.color = color; s.pad[0] = 0; s.pad[1] = 0;
+    cx.cover[slot] = c;
+    cx.shade[slot] = s;
+    cx.bbox[slot] = make_short4(short(px0), short(px1), short(py0), short(py1));
+}
 
 // clip against z >= 0 and z <= w, project, snap, cull, emit
 __device__ void clipAndSetup(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, int color, uint32_t keyBase) {
+    const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
+    const bool allIn = v0.cz >= 0.0f && v1.cz >= 0.0f && v2.cz >= 0.0f && (v0.cw - v0.cz) >= 0.0f && (v1.cw - v1.cz) >= 0.0f && (v2.cw - v2.cz) >= 0.0f;
+    if (allIn) {  // the common case stays in registers
+        const ClipVert *vs[3] = {&v0, &v1, &v2};
+        int32_t sxs[3], sys[3];
+        float szs[3], rws[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float r = 1.0f / vs[i]->cw;
+            rws[i] = r;
+            sxs[i] = snapSub((vs[i]->cx * r) * hw + hw);
+            sys[i] = snapSub((vs[i]->cy * r) * hh + hh);
+            szs[i] = vs[i]->cz * r;
+        }
+        emitTri(cx, v0, v1, v2, sxs, sys, szs, rws, color, keyBase + 1u);
+        return;
+    }
     ClipVert poly[6], tmp[6];
     int n = 3;
     poly[0] = v0; poly[1] = v1; poly[2] = v2;
-    // fast accept: all three inside both planes
-    const bool allIn = v0.cz >= 0.0f && v1.cz >= 0.0f && v2.cz >= 0.0f && (v0.cw - v0.cz) >= 0.0f && (v1.cw - v1.cz) >= 0.0f && (v2.cw - v2.cz) >= 0.0f;
-    if (!allIn) {
-        for (int plane = 0; plane < 2; ++plane) {
-            int m = 0;
-            for (int i = 0; i < n; ++i) {
-                const ClipVert &a = poly[i];
-                const ClipVert &b = poly[(i + 1) % n];
-                const float da = plane == 0 ? a.cz : a.cw - a.cz;
-                const float db = plane == 0 ? b.cz : b.cw - b.cz;
-                const bool ina = da >= 0.0f, inb = db >= 0.0f;
-                if (ina) tmp[m++] = a;
-                if (ina != inb) {
-                    if (ina) tmp[m++] = lerpVert(a, b, da / (da - db));
-                    else tmp[m++] = lerpVert(b, a, db / (db - da));
-                }
+    for (int plane = 0; plane < 2; ++plane) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const ClipVert &a = poly[i];
+            const ClipVert &b = poly[(i + 1) % n];
+            const float da = plane == 0 ? a.cz : a.cw - a.cz;
+            const float db = plane == 0 ? b.cz : b.cw - b.cz;
+            const bool ina = da >= 0.0f, inb = db >= 0.0f;
+            if (ina) tmp[m++] = a;
+            if (ina != inb) {
+                if (ina) tmp[m++] = lerpVert(a, b, da / (da - db));
+                else tmp[m++] = lerpVert(b, a, db / (db - da));
             }
-            n = m;
-            for (int i = 0; i < n; ++i) poly[i] = tmp[i];
-            if (n < 3) return;
         }
+        n = m;
+        for (int i = 0; i < n; ++i) poly[i] = tmp[i];
+        if (n < 3) return;
     }
-    const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
     int32_t sx[6], sy[6];
     float sz[6], rw[6];
     for (int i = 0; i < n; ++i) {
@@ -103,38 +178,9 @@ __device__ void clipAndSetup(const SetupCtx &cx, const ClipVert &v0, const ClipV
         sz[i] = poly[i].cz * r;
     }
     for (int k = 1; k + 1 < n; ++k) {
-        const int id0 = 0, id1 = k, id2 = k + 1;
-        const long long area2 = (long long)(sx[id1] - sx[id0]) * (long long)(sy[id2] - sy[id0]) - (long long)(sy[id1] - sy[id0]) * (long long)(sx[id2] - sx[id0]);
-        if (area2 >= 0) continue;
-        const int32_t minx = min(sx[id0], min(sx[id1], sx[id2])), maxx = max(sx[id0], max(sx[id1], sx[id2]));
-        const int32_t miny = min(sy[id0], min(sy[id1], sy[id2])), maxy = max(sy[id0], max(sy[id1], sy[id2]));
-        const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min(cx.W - 1, (maxx - 128) >> 8);
-        const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min(cx.H - 1, (maxy - 128) >> 8);
-        if (px0 > px1 || py0 > py1) continue;  // covers no pixel centre of the viewport
-        const int slot = atomicAdd(cx.nTris, 1);
-        if (slot >= cx.triCap) { *cx.overflow = 1; continue; }
-        TriRec &t = cx.tris[slot];
-        const int ids[3] = {id0, id1, id2};
-        int tl = 0;
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-            const int a = ids[(e + 1) % 3], b = ids[(e + 2) % 3];
-            const long long dx = (long long)sx[b] - sx[a], dy = (long long)sy[b] - sy[a];
-            const bool topleft = (dy == 0 && dx < 0) || dy > 0;
-            t.A[e] = int32_t(dy);
-            t.B[e] = int32_t(-dx);
-            t.C[e] = dx * sy[a] - dy * sx[a] - (topleft ? 0 : 1);
-            tl |= topleft ? (1 << e) : 0;
-            const int v = ids[e];
-            t.z[e] = sz[v]; t.rw[e] = rw[v];
-            t.p[e * 3 + 0] = poly[v].px; t.p[e * 3 + 1] = poly[v].py; t.p[e * 3 + 2] = poly[v].pz;
-            t.n[e * 3 + 0] = poly[v].nx; t.n[e * 3 + 1] = poly[v].ny; t.n[e * 3 + 2] = poly[v].nz;
-        }
-        t.tl = tl;
-        t.invArea = 1.0f / float(-area2);
-        t.key = keyBase + uint32_t(k);
-        t.px0 = int16_t(px0); t.px1 = int16_t(px1); t.py0 = int16_t(py0); t.py1 = int16_t(py1);
-        t.color = color;
+        const int32_t sxs[3] = {sx[0], sx[k], sx[k + 1]}, sys[3] = {sy[0], sy[k], sy[k + 1]};
+        const float szs[3] = {sz[0], sz[k], sz[k + 1]}, rws[3] = {rw[0], rw[k], rw[k + 1]};
+        emitTri(cx, poly[0], poly[k], poly[k + 1], sxs, sys, szs, rws, color, keyBase + uint32_t(k));
     }
 }
 
@@ -152,88 +198,37 @@ __device__ __forceinline__ ClipVert makeVert(const M4 &mv, const float nm[9], V3
     return cv;
 }
 
-__device__ __forceinline__ float pow300(float x) {
-    const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16, x64 = x32 * x32, x128 = x64 * x64, x256 = x128 * x128;
-    return ((x256 * x32) * x8) * x4;
-}
-__device__ __forceinline__ uint32_t toUnorm8(float c) {
-    c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
-    return uint32_t(floorf(c * 255.0f + 0.5f));
-}
-
-__constant__ float c_palette[22][3];
-
-__device__ __forceinline__ uint32_t shadePixel(const TriRec &t, float l0, float l1, float l2, float &wOut) {
-    const float k0 = l0 * t.rw[0], k1 = l1 * t.rw[1], k2 = l2 * t.rw[2];
-    const float s = (k0 + k1) + k2;
-    const float r = 1.0f / s;
-    const float q0 = k0 * r, q1 = k1 * r, q2 = k2 * r;
-    float P[3], N[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        P[c] = (q0 * t.p[c] + q1 * t.p[3 + c]) + q2 * t.p[6 + c];
-        N[c] = (q0 * t.n[c] + q1 * t.n[3 + c]) + q2 * t.n[6 + c];
-    }
-    wOut = r;
-    const float cd0 = -P[0], cd1 = -P[1], cd2 = -P[2];
-    const float ld0 = 0.0f + cd0, ld1 = 4.0f + cd1, ld2 = 2.0f + cd2;
-    const float ldi = 1.0f / sqrtf((ld0 * ld0 + ld1 * ld1) + ld2 * ld2);
-    const float nl0 = ld0 * ldi, nl1 = ld1 * ldi, nl2 = ld2 * ldi;
-    const float nni = 1.0f / sqrtf((N[0] * N[0] + N[1] * N[1]) + N[2] * N[2]);
-    const float nn0 = N[0] * nni, nn1 = N[1] * nni, nn2 = N[2] * nni;
-    const float ndl = (nn0 * nl0 + nn1 * nl1) + nn2 * nl2;
-    const float intensity = ndl > 0.0f ? ndl : 0.0f;
-    float spec = 0.0f;
-    if (intensity > 0.001f) {
-        const float dni = -ndl;
-        const float r0 = -nl0 - (2.0f * dni) * nn0, r1 = -nl1 - (2.0f * dni) * nn1, r2 = -nl2 - (2.0f * dni) * nn2;
-        const float cdi = 1.0f / sqrtf((cd0 * cd0 + cd1 * cd1) + cd2 * cd2);
-        const float vdr = ((cd0 * cdi) * r0 + (cd1 * cdi) * r1) + (cd2 * cdi) * r2;
-        const float base = vdr > 0.0f ? vdr : 0.0f;
-        spec = pow300(base);
-        spec = spec < 0.0f ? 0.0f : (spec > 1.0f ? 1.0f : spec);
-    }
-    uint32_t out = 0xff000000u;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float diffuse = c_palette[t.color][c];
-        float Lo = 0.33f * diffuse;
-        Lo = Lo + ((0.73f * diffuse) * 0.66f) * intensity;
-        Lo = Lo + 1.0f * spec;
-        out |= toUnorm8(Lo) << (8 * c);
-    }
-    return out;
-}
-
-// dynamic shared memory layout: [TriRec tris[triCap]] [uint32 bins[tiles][nWords]] ; static: counters
-__global__ void __launch_bounds__(256) rasterKernel(RasterParams P) {
-    extern __shared__ __align__(16) unsigned char smemRaw[];
-    __shared__ int s_nTris, s_overflow;
-    const int view = blockIdx.x;
-    const int env = view / P.A, agentIdx = view % P.A;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = blockDim.x >> 5;
-    TriRec *tris = reinterpret_cast<TriRec *>(smemRaw);
-    const int nWordsCap = (P.triCap + 31) / 32;
-    uint32_t *bins = reinterpret_cast<uint32_t *>(smemRaw + size_t(P.triCap) * sizeof(TriRec));
-    const int tilesX = P.W / 32, tilesY = P.H / 4, nTiles = tilesX * tilesY;
-
-    if (tid == 0) { s_nTris = 0; s_overflow = 0; }
-    __syncthreads();
-
+// ---------------------------------------------------------------------------------------------------- geometry kernel
+// grid = (ceil(maxItems / blockDim.x), chunkViews); blockIdx.y selects the view
+__global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
+    const int vslot = blockIdx.y;
+    const int view = P.viewBase + vslot;
+    if (view >= P.N) return;
+    const int env = view / P.A;
+    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.tileCounter = 0;  // for the tile kernel that follows in-stream
     const MvInstance *inst = P.instances + size_t(env) * P.instStride;
     const int nBoxInst = P.instCounts[env * 2 + 0], nInst = P.instCounts[env * 2 + 1];
-    M4 viewM;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) viewM.c[i] = P.views[size_t(view) * 16 + i];
+    const int nBoxItems = nBoxInst * 6;
+    if (item >= nBoxItems + (nInst - nBoxInst) * 128) return;
 
     SetupCtx cx;
-    cx.tris = tris; cx.nTris = &s_nTris; cx.triCap = P.triCap; cx.W = P.W; cx.H = P.H; cx.overflow = &s_overflow;
-    // ---------------- geometry: box instances, one work item per (instance, face)
-    for (int item = tid; item < nBoxInst * 6; item += blockDim.x) {
+    cx.cover = P.cover + size_t(vslot) * P.triCap;
+    cx.shade = P.shade + size_t(vslot) * P.triCap;
+    cx.bbox = P.bbox + size_t(vslot) * P.triCap;
+    cx.nTris = P.triCounts + view;
+    cx.fault = P.faults + env;
+    cx.triCap = P.triCap; cx.W = P.W; cx.H = P.H;
+
+    M4 viewM;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) viewM.c[i] = __ldg(P.views + size_t(view) * 16 + i);
+
+    if (item < nBoxItems) {
         const int ii = item / 6, face = item % 6;
         M4 model;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) model.c[i] = inst[ii].model[i];
+        for (int i = 0; i < 16; ++i) model.c[i] = __ldg(inst[ii].model + i);
         const int color = inst[ii].color;
         const M4 mv = mul4(viewM, model);
         float nm[9];
@@ -247,16 +242,16 @@ __global__ void __launch_bounds__(256) rasterKernel(RasterParams P) {
         const uint32_t keyBase = (uint32_t(ii) * 128u + uint32_t(face) * 2u) * 4u + 1u;
         clipAndSetup(cx, cvt[0], cvt[1], cvt[2], color, keyBase);       // cube indices f*4+{0,1,2}
         clipAndSetup(cx, cvt[0], cvt[2], cvt[3], color, keyBase + 4u);  // cube indices f*4+{0,2,3}
-    }
-    // ---------------- other meshes: one work item per (instance, triangle slot); capsule 128, sphere 80, cone 12, cylinder 24
-    for (int item = tid; item < (nInst - nBoxInst) * 128; item += blockDim.x) {
-        const int ii = nBoxInst + item / 128, tri = item % 128;
+    } else {
+        // other meshes: one item per (instance, triangle slot); capsule 128, sphere 80, cone 12, cylinder 24
+        const int rest = item - nBoxItems;
+        const int ii = nBoxInst + rest / 128, tri = rest % 128;
         const int mesh = inst[ii].mesh;
         const int ntri = mesh == 1 ? MV_CAPSULE_TRIS : (mesh == 2 ? MV_SPHERE_TRIS : (mesh == 3 ? MV_CONE_TRIS : MV_CYLINDER_TRIS));
-        if (tri >= ntri) continue;
+        if (tri >= ntri) return;
         M4 model;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) model.c[i] = inst[ii].model[i];
+        for (int i = 0; i < 16; ++i) model.c[i] = __ldg(inst[ii].model + i);
         const M4 mv = mul4(viewM, model);
         float nm[9];
         normalMatrix(mv, nm);
@@ -273,76 +268,268 @@ __global__ void __launch_bounds__(256) rasterKernel(RasterParams P) {
         const uint32_t keyBase = (uint32_t(ii) * 128u + uint32_t(tri)) * 4u + 1u;
         clipAndSetup(cx, cvt[0], cvt[1], cvt[2], inst[ii].color, keyBase);
     }
-    __syncthreads();
-    const int nTris = min(s_nTris, P.triCap);
-    const int nWords = (nTris + 31) / 32;
-    if (tid == 0 && s_overflow) atomicOr(&P.faults[env], MV_FAULT_TRI_OVERFLOW);
+}
 
-    // ---------------- binning: bit (tile, triangle) set when the triangle's pixel box touches the tile
-    for (int pair = warp; pair < nTiles * nWords; pair += nWarps) {
-        const int tile = pair / nWords, w = pair % nWords;
-        const int tx0 = (tile % tilesX) * 32, ty0 = (tile / tilesX) * 4;
-        const int t = w * 32 + lane;
-        bool ov = false;
-        if (t < nTris) {
-            const TriRec &tr = tris[t];
-            ov = tr.px0 <= tx0 + 31 && tr.px1 >= tx0 && tr.py0 <= ty0 + 3 && tr.py1 >= ty0;
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, ov);
-        if (lane == 0) bins[tile * nWordsCap + w] = m;
-    }
-    __syncthreads();
+// ---------------------------------------------------------------------------------------------------- shading
+__device__ __forceinline__ float pow300(float x) {
+    const float x2 = x * x, x4 = x2 * x2, x8 = x4 * x4, x16 = x8 * x8, x32 = x16 * x16, x64 = x32 * x32, x128 = x64 * x64, x256 = x128 * x128;
+    return ((x256 * x32) * x8) * x4;
+}
+__device__ __forceinline__ uint32_t toUnorm8(float c) {
+    c = c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+    return uint32_t(floorf(c * 255.0f + 0.5f));
+}
 
-    // ---------------- raster + shade: one warp per 32x4 tile, one lane per 4 horizontal pixels
-    uint8_t *obsView = P.obs + size_t(view) * P.W * P.H * 4;
-    float *depthView = P.depth ? P.depth + size_t(view) * P.W * P.H : nullptr;
-    for (int tile = warp; tile < nTiles; tile += nWarps) {
-        const int px = (tile % tilesX) * 32 + (lane & 7) * 4, py = (tile / tilesX) * 4 + (lane >> 3);
-        const long long sx = (long long)px * 256 + 128, sy = (long long)py * 256 + 128;
-        float bz[4] = {1.0f, 1.0f, 1.0f, 1.0f};
-        uint32_t bkey[4] = {0u, 0u, 0u, 0u};
-        int bt[4] = {-1, -1, -1, -1};
-        float bl0[4], bl1[4], bl2[4];
-        for (int w = 0; w < nWords; ++w) {
-            uint32_t bits = bins[tile * nWordsCap + w];
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int ti = w * 32 + b;
-                const TriRec &t = tris[ti];
-                if (px + 3 < t.px0 || px > t.px1 || py < t.py0 || py > t.py1) continue;
-                long long F0 = t.C[0] + (long long)t.A[0] * sx + (long long)t.B[0] * sy;
-                long long F1 = t.C[1] + (long long)t.A[1] * sx + (long long)t.B[1] * sy;
-                long long F2 = t.C[2] + (long long)t.A[2] * sx + (long long)t.B[2] * sy;
-                const long long d0 = (long long)t.A[0] * 256, d1 = (long long)t.A[1] * 256, d2 = (long long)t.A[2] * 256;
-                const int tl = t.tl;
+__constant__ float c_palette[22][3];
+
+template <bool FAST> __device__ __forceinline__ float invLen3(float x, float y, float z) {
+    if (FAST) return rsqrtf(__fmaf_rn(z, z, __fmaf_rn(y, y, x * x)));
+    return 1.0f / sqrtf((x * x + y * y) + z * z);
+}
+template <bool FAST> __device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    if (FAST) return __fmaf_rn(az, bz, __fmaf_rn(ay, by, ax * bx));
+    return (ax * bx + ay * by) + az * bz;
+}
+
+// uber.frag:112-141.  FAST keeps the structure but uses rsqrt.approx + FMA: colours move by at most 1 LSB (the tolerance the
+// north star grants for RGB); the exact variant reproduces the oracle byte for byte.  The depth output is exact in both.
+template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const TriShade *tp, float l0, float l1, float l2, float &wOut) {
+    const float4 *q = reinterpret_cast<const float4 *>(tp);  // 96-byte record as six 128-bit read-only loads
+    const float4 a0 = __ldg(q + 0), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3), a4 = __ldg(q + 4), a5 = __ldg(q + 5);
+    const float rw0 = a0.x, rw1 = a0.y, rw2 = a0.z;
+    const float p[9] = {a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+    const float n[9] = {a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w, a5.x};
+    const int color = __float_as_int(a5.y);
+    const float k0 = l0 * rw0, k1 = l1 * rw1, k2 = l2 * rw2;
+    const float s = (k0 + k1) + k2;
+    const float r = 1.0f / s;
+    const float q0 = k0 * r, q1 = k1 * r, q2 = k2 * r;
+    float Pc[3], N[3];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if ((F0 | F1 | F2) >= 0) {
-                        // undo the top-left bias before converting to barycentrics
-                        const float l0 = float(F0 + ((tl & 1) ? 0 : 1)) * t.invArea;
-                        const float l1 = float(F1 + ((tl & 2) ? 0 : 1)) * t.invArea;
-                        const float l2 = float(F2 + ((tl & 4) ? 0 : 1)) * t.invArea;
-                        const float z = (l0 * t.z[0] + l1 * t.z[1]) + l2 * t.z[2];
-                        if (z < bz[k] || (z == bz[k] && t.key > bkey[k])) {
-                            bz[k] = z; bkey[k] = t.key; bt[k] = ti; bl0[k] = l0; bl1[k] = l1; bl2[k] = l2;
+    for (int c = 0; c < 3; ++c) {
+        Pc[c] = dot3<FAST>(q0, q1, q2, p[c], p[3 + c], p[6 + c]);
+        N[c] = dot3<FAST>(q0, q1, q2, n[c], n[3 + c], n[6 + c]);
+    }
+    wOut = r;
+    const float cd0 = -Pc[0], cd1 = -Pc[1], cd2 = -Pc[2];
+    const float ld0 = 0.0f + cd0, ld1 = 4.0f + cd1, ld2 = 2.0f + cd2;
+    const float ldi = invLen3<FAST>(ld0, ld1, ld2);
+    const float nl0 = ld0 * ldi, nl1 = ld1 * ldi, nl2 = ld2 * ldi;
+    const float nni = invLen3<FAST>(N[0], N[1], N[2]);
+    const float nn0 = N[0] * nni, nn1 = N[1] * nni, nn2 = N[2] * nni;
+    const float ndl = dot3<FAST>(nn0, nn1, nn2, nl0, nl1, nl2);
+    const float intensity = ndl > 0.0f ? ndl : 0.0f;
+    float spec = 0.0f;
+    if (intensity > 0.001f) {
+        const float dni = -ndl;
+        const float r0 = -nl0 - (2.0f * dni) * nn0, r1 = -nl1 - (2.0f * dni) * nn1, r2 = -nl2 - (2.0f * dni) * nn2;
+        const float cdi = invLen3<FAST>(cd0, cd1, cd2);
+        const float vdr = dot3<FAST>(cd0 * cdi, cd1 * cdi, cd2 * cdi, r0, r1, r2);
+        const float base = vdr > 0.0f ? vdr : 0.0f;
+        spec = pow300(base);
+        spec = spec < 0.0f ? 0.0f : (spec > 1.0f ? 1.0f : spec);
+    }
+    uint32_t out = 0xff000000u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float diffuse = c_palette[color][c];
+        float Lo;
+        if (FAST) {
+            Lo = __fmaf_rn((0.73f * diffuse) * 0.66f, intensity, 0.33f * diffuse) + spec;
+            out |= __float2uint_rn(__saturatef(Lo) * 255.0f) << (8 * c);
+        } else {
+            Lo = 0.33f * diffuse;
+            Lo = Lo + ((0.73f * diffuse) * 0.66f) * intensity;
+            Lo = Lo + 1.0f * spec;
+            out |= toUnorm8(Lo) << (8 * c);
+        }
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------- tile raster kernel
+// Persistent warps pull (view, 32x4 tile) work items from a global counter.  Inside a tile the view's triangle list is
+// scanned 32 boxes at a time; triangles that touch the tile take one of two paths:
+//   * small (at most kSmallArea pixels of the tile): ONE LANE PER TRIANGLE walks its few pixels and publishes fragments
+//     with a packed 64-bit shared-memory atomicMax  ->  dense clusters of tiny triangles cost ~1/32 of the serial path
+//   * large: the whole warp evaluates it, lane = 4 horizontally adjacent pixels, best fragment kept in registers
+// A fragment is the 64-bit key (~depth bits << 32) | (draw order << 13) | list index: max == nearest depth, and on equal
+// depth the later draw (LESS_OR_EQUAL).  Barycentrics are recomputed for the single winner at shading time.
+constexpr int kSmallArea = 24;
+
+struct EdgeEval {  // one triangle's edge functions at a pixel centre
+    int A0, A1, A2, B0, B1, B2, u0, u1, u2, small;
+    long long C0, C1, C2;
+    float z0, z1, z2, invArea;
+    uint32_t key;
+};
+__device__ __forceinline__ EdgeEval loadCover(const TriCover *c) {
+    const int4 *cq = reinterpret_cast<const int4 *>(c);
+    const int4 q0 = __ldg(cq + 0), q1 = __ldg(cq + 1), q2 = __ldg(cq + 2), q3 = __ldg(cq + 3), q4 = __ldg(cq + 4);
+    EdgeEval e;
+    e.C0 = (long long)(((unsigned long long)(unsigned)q0.y << 32) | (unsigned)q0.x);
+    e.C1 = (long long)(((unsigned long long)(unsigned)q0.w << 32) | (unsigned)q0.z);
+    e.C2 = (long long)(((unsigned long long)(unsigned)q1.y << 32) | (unsigned)q1.x);
+    e.A0 = q1.z; e.A1 = q1.w; e.A2 = q2.x; e.B0 = q2.y; e.B1 = q2.z; e.B2 = q2.w;
+    e.z0 = __int_as_float(q3.x); e.z1 = __int_as_float(q3.y); e.z2 = __int_as_float(q3.z); e.invArea = __int_as_float(q3.w);
+    e.key = uint32_t(q4.x);
+    const int tl = q4.y;
+    e.u0 = (tl & 1) ? 0 : 1; e.u1 = (tl & 2) ? 0 : 1; e.u2 = (tl & 4) ? 0 : 1;  // undo the top-left bias for the barycentrics
+    e.small = q4.z;
+    return e;
+}
+__device__ __forceinline__ unsigned long long packFrag(float z, uint32_t key, int idx) {
+    const uint32_t b = __float_as_uint(z);
+    const uint32_t asc = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);  // monotonic in z over all floats (tiny negative z can come out of the clipper)
+    return ((unsigned long long)(~asc) << 32) | (unsigned long long)((key << 13) | uint32_t(idx));
+}
+
+template <bool FAST> __global__ void __launch_bounds__(128, 8) tileKernel(RasterParams P) {
+    __shared__ unsigned long long s_frag[4][128];
+    const int lane = threadIdx.x & 31;
+    unsigned long long *frag = s_frag[threadIdx.x >> 5];
+    const int tilesX = P.W / 32, nTiles = tilesX * (P.H / 4);
+    const int totalTiles = min(P.chunkViews, P.N - P.viewBase) * nTiles;
+    for (;;) {
+        int gw = 0;
+        if (lane == 0) gw = atomicAdd(P.tileCounter, 1);
+        gw = __shfl_sync(0xffffffffu, gw, 0);
+        if (gw >= totalTiles) return;
+        // view-minor order: consecutive work items belong to different views, so a heavy view's tiles are spread over the
+        // whole queue instead of forming the tail
+        const int chunkN = totalTiles / nTiles;
+        int tile, vslot;
+        if (P.tune & 2) { tile = gw / chunkN; vslot = gw - tile * chunkN; }
+        else { vslot = gw / nTiles; tile = gw - vslot * nTiles; }
+        const int view = P.viewBase + vslot;
+        const TriCover *cover = P.cover + size_t(vslot) * P.triCap;
+        const TriShade *shade = P.shade + size_t(vslot) * P.triCap;
+        const short4 *bbox = P.bbox + size_t(vslot) * P.triCap;
+        const int nTris = min(__ldg(P.triCounts + view), P.triCap);
+
+        const int ty = tile / tilesX;
+        const int tx0 = (tile - ty * tilesX) * 32, ty0 = ty * 4;
+        const int px = tx0 + (lane & 7) * 4, py = ty0 + (lane >> 3);
+        const int sx32 = px * 256 + 128, sy32 = py * 256 + 128;
+        unsigned long long best[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) frag[lane * 4 + k] = 0ull;
+        __syncwarp();
+
+        for (int base = 0; base < nTris; base += 32) {
+            const int tmine = base + lane;
+            bool ov = false, small = false;
+            int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+            if (tmine < nTris) {
+                const short4 b = __ldg(bbox + tmine);
+                ov = b.x <= tx0 + 31 && b.y >= tx0 && b.z <= ty0 + 3 && b.w >= ty0;
+                bx0 = max(int(b.x), tx0); bx1 = min(int(b.y), tx0 + 31); by0 = max(int(b.z), ty0); by1 = min(int(b.w), ty0 + 3);
+                small = ov && (bx1 - bx0 + 1) * (by1 - by0 + 1) <= kSmallArea;
+            }
+            {   // adaptive: when many mid-sized triangles share this chunk, one lane each beats ~100 warp instructions each
+                const int area = (ov && !small) ? (bx1 - bx0 + 1) * (by1 - by0 + 1) : 0;
+                const unsigned big = __ballot_sync(0xffffffffu, area > 0);
+                if (big && (P.tune & 1)) {
+                    int maxArea = area;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) maxArea = max(maxArea, __shfl_xor_sync(0xffffffffu, maxArea, off));
+                    if (__popc(big) * 8 > maxArea) small = ov;
+                }
+            }
+            // ---- small triangles: one lane each
+            if (small) {
+                const EdgeEval e = loadCover(cover + tmine);
+                for (int y = by0; y <= by1; ++y) {
+                    const int sy = y * 256 + 128, sx0 = bx0 * 256 + 128;
+                    if (e.small) {
+                        int F0 = int(e.C0) + e.A0 * sx0 + e.B0 * sy, F1 = int(e.C1) + e.A1 * sx0 + e.B1 * sy, F2 = int(e.C2) + e.A2 * sx0 + e.B2 * sy;
+                        for (int x = bx0; x <= bx1; ++x) {
+                            if ((F0 | F1 | F2) >= 0) {
+                                const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
+                                const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
+                                if (z <= 1.0f) atomicMax(&frag[(y - ty0) * 32 + (x - tx0)], packFrag(z, e.key, tmine));
+                            }
+                            F0 += e.A0 * 256; F1 += e.A1 * 256; F2 += e.A2 * 256;
+                        }
+                    } else {
+                        long long F0 = e.C0 + (long long)e.A0 * sx0 + (long long)e.B0 * sy, F1 = e.C1 + (long long)e.A1 * sx0 + (long long)e.B1 * sy,
+                                  F2 = e.C2 + (long long)e.A2 * sx0 + (long long)e.B2 * sy;
+                        for (int x = bx0; x <= bx1; ++x) {
+                            if ((F0 | F1 | F2) >= 0) {
+                                const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
+                                const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
+                                if (z <= 1.0f) atomicMax(&frag[(y - ty0) * 32 + (x - tx0)], packFrag(z, e.key, tmine));
+                            }
+                            F0 += (long long)e.A0 * 256; F1 += (long long)e.A1 * 256; F2 += (long long)e.A2 * 256;
                         }
                     }
-                    F0 += d0; F1 += d1; F2 += d2;
+                }
+            }
+            // ---- large triangles: whole warp, lane = 4 pixels
+            unsigned bits = __ballot_sync(0xffffffffu, ov && !small);
+            while (bits) {
+                const int bsel = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int ti = base + bsel;
+                const short4 tb = __ldg(bbox + ti);
+                if (px + 3 < tb.x || px > tb.y || py < tb.z || py > tb.w) continue;
+                const EdgeEval e = loadCover(cover + ti);
+                if (e.small) {
+                    int F0 = int(e.C0) + e.A0 * sx32 + e.B0 * sy32, F1 = int(e.C1) + e.A1 * sx32 + e.B1 * sy32, F2 = int(e.C2) + e.A2 * sx32 + e.B2 * sy32;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if ((F0 | F1 | F2) >= 0) {
+                            const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
+                            const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
+                            if (z <= 1.0f) { const unsigned long long f = packFrag(z, e.key, ti); best[k] = f > best[k] ? f : best[k]; }
+                        }
+                        F0 += e.A0 * 256; F1 += e.A1 * 256; F2 += e.A2 * 256;
+                    }
+                } else {
+                    long long F0 = e.C0 + (long long)e.A0 * sx32 + (long long)e.B0 * sy32, F1 = e.C1 + (long long)e.A1 * sx32 + (long long)e.B1 * sy32,
+                              F2 = e.C2 + (long long)e.A2 * sx32 + (long long)e.B2 * sy32;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if ((F0 | F1 | F2) >= 0) {
+                            const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
+                            const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
+                            if (z <= 1.0f) { const unsigned long long f = packFrag(z, e.key, ti); best[k] = f > best[k] ? f : best[k]; }
+                        }
+                        F0 += (long long)e.A0 * 256; F1 += (long long)e.A1 * 256; F2 += (long long)e.A2 * 256;
+                    }
                 }
             }
         }
+        __syncwarp();
+        // ---- merge both paths, recompute the winner's barycentrics, shade, store
         uint4 out;
         float wv[4];
         uint32_t o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (bt[k] < 0) { o[k] = 0xff000000u; wv[k] = 0.0f; }
-            else o[k] = shadePixel(tris[bt[k]], bl0[k], bl1[k], bl2[k], wv[k]);
+            const unsigned long long fs = frag[(lane >> 3) * 32 + (lane & 7) * 4 + k];
+            const unsigned long long f = fs > best[k] ? fs : best[k];
+            if (f == 0ull) { o[k] = 0xff000000u; wv[k] = 0.0f; continue; }
+            const int ti = int(uint32_t(f) & 8191u);
+            const EdgeEval e = loadCover(cover + ti);
+            const int sx = sx32 + k * 256;
+            float l0, l1, l2;
+            if (e.small) {
+                l0 = float(int(e.C0) + e.A0 * sx + e.B0 * sy32 + e.u0) * e.invArea;
+                l1 = float(int(e.C1) + e.A1 * sx + e.B1 * sy32 + e.u1) * e.invArea;
+                l2 = float(int(e.C2) + e.A2 * sx + e.B2 * sy32 + e.u2) * e.invArea;
+            } else {
+                l0 = float(e.C0 + (long long)e.A0 * sx + (long long)e.B0 * sy32 + e.u0) * e.invArea;
+                l1 = float(e.C1 + (long long)e.A1 * sx + (long long)e.B1 * sy32 + e.u1) * e.invArea;
+                l2 = float(e.C2 + (long long)e.A2 * sx + (long long)e.B2 * sy32 + e.u2) * e.invArea;
+            }
+            o[k] = shadePixel<FAST>(shade + ti, l0, l1, l2, wv[k]);
         }
         out.x = o[0]; out.y = o[1]; out.z = o[2]; out.w = o[3];
+        uint8_t *obsView = P.obs + size_t(view) * P.W * P.H * 4;
         *reinterpret_cast<uint4 *>(obsView + (size_t(py) * P.W + px) * 4) = out;
-        if (depthView) *reinterpret_cast<float4 *>(depthView + size_t(py) * P.W + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        if (P.depth) *reinterpret_cast<float4 *>(P.depth + size_t(view) * P.W * P.H + size_t(py) * P.W + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        __syncwarp();
     }
 }
 

@@ -48,6 +48,7 @@ struct StepParams {
     MvInstance *instances;       // [E][MV_MAX_INSTANCES]
     int32_t *instCounts;         // [E][2]
     float *views;                // [E*A][16]
+    int32_t *triCounts;          // [E*A] rasteriser triangle counters, zeroed here for the geometry kernel that follows
     const int32_t *actions;      // [E*A]
     const float *rtable;         // [E*A][MV_R_COUNT]
     float *rewards;              // [E*A]
@@ -68,6 +69,7 @@ struct WarpShared {  // one per warp
     int objDirty[MV_MAX_AGENTS * 2];
     int nDirty;
     int doneFlag;
+    uint16_t cand[MV_MAX_STATIC + MV_MAX_OBJECTS + MV_MAX_AGENTS];
 };
 
 // ---------------------------------------------------------------- TMA (1-D bulk async copy) helpers
@@ -235,6 +237,8 @@ __device__ bool rayCapsule(V3 o, V3 d, float L, float R, float &tOut, V3 &nOut) 
 struct ColliderView {
     const WarpShared *S;
     int ns, no, A;
+    const uint16_t *cand;  // this agent's candidate colliders for the current step, ascending collider index
+    int nc;
     __device__ __forceinline__ int count() const { return ns + no + A; }
     __device__ __forceinline__ bool fetch(int i, int &kind, V3 &c, V3 &h) const {
         if (i < ns) {
@@ -263,9 +267,8 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
     float bt = 1.0f;
     int bi = 0x7fffffff;
     V3 bn = v3(0, 0, 0);
-    const int n = cv.count();
-    for (int i = lane; i < n; i += 32) {
-        if (i == self) continue;
+    for (int j = lane; j < cv.nc; j += 32) {
+        const int i = cv.cand[j];
         int kind; V3 c, h;
         if (!cv.fetch(i, kind, c, h)) continue;
         const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
@@ -304,12 +307,12 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
 
 // first collider (index order) penetrating deeper than maxPenetrationDepth; returns push-out delta
 __device__ bool warpRecover(const ColliderView &cv, int self, V3 p, V3 &delta, int lane) {
-    const int n = cv.count();
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
+    for (int base = 0; base < cv.nc; base += 32) {
+        const int j = base + lane;
         bool pen = false;
         V3 dl = v3(0, 0, 0);
-        if (i < n && i != self) {
+        if (j < cv.nc) {
+            const int i = cv.cand[j];
             int kind; V3 c, h;
             if (cv.fetch(i, kind, c, h)) {
                 V3 nn;
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
 
     if (!P.forceReset) {
         ColliderView cv;
-        cv.S = &S; cv.ns = ns; cv.no = no; cv.A = A;
+        cv.S = &S; cv.ns = ns; cv.no = no; cv.A = A; cv.cand = S.cand; cv.nc = 0;
 
         // ---- action phase (env.cpp:89-122)
         for (int i = 0; i < A; ++i) {
@@ -758,7 +761,36 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
             k.jumpAxis = v3(a.jump_axis[0], a.jump_axis[1], a.jump_axis[2]);
             k.vvel = a.vvel; k.voff = a.voff; k.stepOff = a.step_off; k.jumpSpeed = a.jump_speed;
             k.wasOnGround = a.was_on_ground != 0; k.wasJumping = a.was_jumping != 0;
+            // candidate colliders of this agent for the whole step: everything whose bounds (grown by the capsule) reach
+            // the envelope the controller can move in within one step (0.2 step-up + jump, <= 55/15 fall, <= 5 push-outs)
+            const V3 envLo = v3(k.pos.x - 3.0f, k.pos.y - 6.0f, k.pos.z - 3.0f), envHi = v3(k.pos.x + 3.0f, k.pos.y + 3.0f, k.pos.z + 3.0f);
+            {
+                const int self = ns + no + i;
+                int nc = 0;
+                const int n = cv.count();
+                for (int base = 0; base < n; base += 32) {
+                    const int ci = base + lane;
+                    bool keep = false;
+                    if (ci < n && ci != self) {
+                        int kind; V3 c, h;
+                        if (cv.fetch(ci, kind, c, h)) {
+                            const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
+                                                     : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
+                            keep = !(envHi.x < c.x - ext.x || envLo.x > c.x + ext.x || envHi.y < c.y - ext.y || envLo.y > c.y + ext.y ||
+                                     envHi.z < c.z - ext.z || envLo.z > c.z + ext.z);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    if (keep) S.cand[nc + __popc(m & ((1u << lane) - 1u))] = uint16_t(ci);
+                    nc += __popc(m);
+                }
+                __syncwarp();
+                cv.cand = S.cand; cv.nc = nc;
+            }
             kccPlayerStep(k, cv, ns + no + i, dt, P.k.max_slope_cos, lane);
+            if (k.pos.x < envLo.x + 0.5f || k.pos.x > envHi.x - 0.5f || k.pos.y < envLo.y + 0.5f || k.pos.y > envHi.y - 0.5f || k.pos.z < envLo.z + 0.5f ||
+                k.pos.z > envHi.z - 0.5f)
+                S.env.faults |= MV_FAULT_ENVELOPE;
             __syncwarp();
             if (lane == 0) {
                 a.pos[0] = k.pos.x; a.pos[1] = k.pos.y; a.pos[2] = k.pos.z;
@@ -966,6 +998,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     __syncwarp();
 
     writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 2, P.views + size_t(env) * A * 16, A, resetNow, lane);
+    for (int i = lane; i < A; i += 32) P.triCounts[size_t(env) * A + i] = 0;
 
     // ---- commit env + agents
     {

@@ -8,12 +8,14 @@ import helpers
 pytestmark = pytest.mark.gpu
 
 
-def _pair(scenario, E, A, seed, w=128, h=72, params=None, depth=False):
+def _pair(scenario, E, A, seed, w=128, h=72, params=None, depth=False, fast_shading=False):
     import orc
     from megaverse_b200 import capi
 
     o = orc.Oracle(scenario, E, A, w, h, params=params, depth=depth)
     g = capi.Engine(scenario, E, A, w, h, num_threads=2, params=params, depth=depth)
+    # the bit-exact fragment stage for the byte-exact checks; fast_shading=True is the default production mode (+-1 LSB)
+    g.set_option("fast_shading", 1 if fast_shading else 0)
     o.seed(seed)
     g.seed(seed)
     o.reset()
@@ -162,3 +164,27 @@ def test_seed_determinism(built):
     g1.reset(); g2.reset()
     assert np.array_equal(np.array(g1.obs()), np.array(g2.obs()))
     g1.close(); g2.close()
+
+
+def test_fast_shading_within_one_lsb(built):
+    """the production fragment stage (rsqrt.approx + FMA) against the oracle: every channel within +-1 LSB (north-star
+    tolerance for RGB); physics / rewards stay bit-exact because only the fragment colour arithmetic changes"""
+    E = 16
+    o, g = _pair("TowerBuilding", E, 1, 4321, fast_shading=True)
+    rng = np.random.default_rng(17)
+    worst_exact = 1.0
+    for t in range(200):
+        acts = helpers.purposeful_actions(rng, E, t)
+        o.step(acts)
+        g.step(acts)
+        assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), "step %d" % t
+        if t % 10 == 0:
+            a, b = o.obs(), np.array(g.obs())
+            diff = np.abs(a.astype(np.int16) - b.astype(np.int16))
+            assert diff.max() <= 1, "step %d: max RGB diff %d" % (t, diff.max())
+            assert np.array_equal(a[..., 3], b[..., 3])
+            worst_exact = min(worst_exact, float((diff == 0).mean()))
+    _assert_same_state(o, g, E, "end")
+    assert worst_exact > 0.9, worst_exact
+    print("fast shading: worst exact-byte fraction %.5f" % worst_exact)
+    o.close(); g.close()
