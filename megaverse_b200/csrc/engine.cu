@@ -105,6 +105,7 @@ struct mv_engine {
     std::string error;
     void setError(const std::string &e) { error = e; }
 
+    std::string scenarioName;
     int scenario = 0, W = 0, H = 0, E = 0, A = 0, N = 0, threads = 1, device = 0;
     mv::FloatParams params;
     std::vector<std::vector<std::pair<std::string, float>>> shaping;  // per agent view: ordered key list (std::map order)
@@ -160,6 +161,7 @@ struct mv_engine {
     PinBuf<int32_t> h_faults;
 
     std::vector<int> hostSlot, hostEpisode;   // mirrors of the device's live slot / episode index
+    std::vector<int> levelWords;              // [E*2] words of the bit planes a staged level uses
     std::vector<int> pendingUpload;           // env ids whose freshly generated next level waits for H2D
     std::vector<std::string> genErrors;
     std::mutex genMutex;
@@ -180,14 +182,17 @@ struct mv_engine {
             {
                 int boxes = out.level.n_terrain + out.level.n_obj + 2 * A;
                 for (int i = 0; i < out.level.n_static; ++i) boxes += (out.level.statics[i].flags & MV_OPAQUE) ? 1 : 0;
-                const int items = boxes * 6 + A * 128;
+                const int items = boxes * 6 + (A + 2 * out.level.n_reward) * 128;  // non-box meshes take 128 triangle slots each
                 int cur = maxItemsSeen.load();
                 while (items > cur && !maxItemsSeen.compare_exchange_weak(cur, items)) {}
             }
             std::memcpy(&h_levels.p[size_t(e) * 2 + s], &out.level, sizeof(MvLevel));
-            uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * gridWords;
-            std::memset(dst, 0, sizeof(uint32_t) * gridWords);
-            std::memcpy(dst, out.solid.data(), sizeof(uint32_t) * std::min(out.solid.size(), size_t(gridWords)));
+            uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * 3 * gridWords;  // planes: solid, exit, lava
+            const size_t nw = std::min(out.solid.size(), size_t(gridWords));
+            std::memcpy(dst, out.solid.data(), sizeof(uint32_t) * nw);
+            std::memcpy(dst + gridWords, out.exitBits.data(), sizeof(uint32_t) * nw);
+            std::memcpy(dst + 2 * size_t(gridWords), out.lavaBits.data(), sizeof(uint32_t) * nw);
+            levelWords[size_t(e) * 2 + s] = int(nw);
             std::lock_guard<std::mutex> lk(genMutex);
             pendingUpload.push_back(e * 2 + s);
         });
@@ -202,7 +207,9 @@ struct mv_engine {
         }
         for (int id : todo) {
             MV_CUDA(cudaMemcpyAsync(&d_levels.p[id], &h_levels.p[id], sizeof(MvLevel), cudaMemcpyHostToDevice, stream));
-            MV_CUDA(cudaMemcpyAsync(d_solid.p + size_t(id) * gridWords, h_solid.p + size_t(id) * gridWords, sizeof(uint32_t) * gridWords, cudaMemcpyHostToDevice, stream));
+            const size_t nw = size_t(levelWords[size_t(id)]);  // only the words this level's grid uses
+            for (int plane = 0; plane < (scenario == MV_SCENARIO_TOWER ? 1 : 3); ++plane)
+                MV_CUDA(cudaMemcpyAsync(d_solid.p + (size_t(id) * 3 + plane) * gridWords, h_solid.p + (size_t(id) * 3 + plane) * gridWords, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, stream));
         }
         return MV_OK;
     }
@@ -248,7 +255,7 @@ struct mv_engine {
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
         const int nTiles = (W / 32) * (H / 4);
-        const int maxItems = MV_MAX_INSTANCES * 6 + A * 128;  // blocks past a view's real item count exit at once
+        const int maxItems = MV_MAX_INSTANCES * 6 + (A + 2 * MV_MAX_REWARD) * 128;  // blocks past a view's real item count exit at once
         const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
         for (int base = 0; base < N; base += chunkViews) {
             const int cv = std::min(chunkViews, N - base);
@@ -382,19 +389,20 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     if (cudaSetDevice(device) != cudaSuccess) { e->setError("cudaSetDevice failed"); return fail(MV_ERR_CUDA); }
     e->scenario = sc; e->W = w; e->H = h; e->E = num_envs; e->A = num_agents; e->N = num_envs * num_agents; e->device = device;
     e->threads = num_threads < 1 ? 1 : num_threads;
-    e->params = mv::defaultFloatParams(sc);
+    e->scenarioName = scenario;
+    e->params = mv::defaultFloatParams(e->scenarioName);
     for (int i = 0; i < nparams; ++i) e->params[keys[i]] = vals[i];
     {
-        auto def = mv::defaultRewardShaping(sc);
+        auto def = mv::defaultRewardShaping(e->scenarioName);
         std::map<std::string, float> m{{"teamSpirit", 0.0f}};
         for (auto &kv : def) m[kv.first] = kv.second;
         std::vector<std::pair<std::string, float>> ordered(m.begin(), m.end());
         e->shaping.assign(size_t(e->N), ordered);
     }
-    for (int i = 0; i < e->E; ++i) e->gens.emplace_back(sc, e->A, e->params);
+    for (int i = 0; i < e->E; ++i) e->gens.emplace_back(e->scenarioName, e->A, e->params);
+    e->levelWords.assign(size_t(e->E) * 2, 0);
     e->pool.reset(new WorkerPool(e->threads));
-    // dense grid capacity: TowerBuilding rooms are at most 29 x (6+18) x 24 (scenario_tower_building.cpp:21-34)
-    e->gridCells = ((30 * 25 * 25 + 127) / 128) * 128;
+    e->gridCells = mv::gridCapacity(sc);
     e->gridWords = e->gridCells / 32;
     fillConsts(e->consts, w, h);
 
@@ -402,7 +410,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
     bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream");
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
-    ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
+    ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
          ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 2), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
@@ -411,7 +419,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     e->chunkViews = int(std::min<size_t>(N, 512));
     if (ok && e->allocTriScratch() != MV_OK) return fail(MV_ERR_CUDA);
-    ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
+    ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
          ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults");
     if (!ok) return fail(MV_ERR_CUDA);
@@ -571,7 +579,7 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
     // makes the reference throw std::out_of_range at the next reward event (scenario.hpp:253) -> reject it up front
     std::map<std::string, float> m;
     for (int i = 0; i < n; ++i) m[keys[i]] = vals[i];
-    for (auto &kv : mv::defaultRewardShaping(h->scenario))
+    for (auto &kv : mv::defaultRewardShaping(h->scenarioName))
         if (!m.count(kv.first)) { h->setError("reward shaping lacks key " + kv.first); return MV_ERR_ARG; }
     const size_t view = size_t(env) * h->A + agent;
     h->shaping[view].assign(m.begin(), m.end());
@@ -619,13 +627,17 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
         o.push_back(b.flags); o.push_back(int(pal[b.color]));
     }
-    for (int i = 0; i < L.n_terrain; ++i) {  // TowerBuilding: the single building-zone slab
-        o.push_back(4);
-        for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
-        for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
+    for (int i = 0; i < L.n_terrain; ++i) {
+        o.push_back(L.terrain[i].type);
+        for (int a = 0; a < 6; ++a) o.push_back(L.terrain[i].bb[a]);
     }
     for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
     for (int i = 0; i < h->A; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
+    if (L.scenario == MV_SCENARIO_OBSTACLES) {
+        o.push_back(L.n_movable);  // numPlatforms
+        o.push_back(L.n_reward);
+        for (int i = 0; i < L.n_reward; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
+    }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
     return int(o.size());
@@ -644,7 +656,7 @@ int mv_debug_get_state(mv_handle h, int env, float *out, int cap) {
     std::vector<float> o;
     int ncol = h->A + L.n_obj;
     for (int i = 0; i < L.n_static; ++i) ncol += (L.statics[i].flags & MV_SOLID) ? 1 : 0;
-    const float len = L.episode_len_base + 4.0f * float(L.n_movable);
+    const float len = L.episode_len;
     o.push_back(es.episode_sec); o.push_back(len); o.push_back(float(es.num_frames)); o.push_back(float(es.highest_tower));
     o.push_back(es.bz_reward); o.push_back(float(L.n_obj)); o.push_back(float(ncol)); o.push_back(0.f);
     for (int i = 0; i < h->A; ++i) {
@@ -670,6 +682,7 @@ int mv_debug_get_state(mv_handle h, int env, float *out, int cap) {
         }
         for (float x : {t[0], t[1], t[2], b.s[0], b.s[1], b.s[2], float(b.parent), b.enabled ? 1.f : 0.f, 0.f}) o.push_back(x);
     }
+    if (L.scenario == MV_SCENARIO_OBSTACLES) { o.push_back(float(es.solved)); o.push_back(float(es.reached_exit)); o.push_back(float(es.reward_alive)); }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(float));
     return int(o.size());
@@ -681,7 +694,7 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
     cudaStreamSynchronize(h->stream);
     if (cudaMemcpy(&es, &h->d_envs.p[env], sizeof es, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     const MvLevel &L = h->h_levels.p[size_t(env) * 2 + es.slot];
-    const uint32_t *sol = h->h_solid.p + (size_t(env) * 2 + es.slot) * h->gridWords;
+    const uint32_t *sol = h->h_solid.p + (size_t(env) * 2 + es.slot) * 3 * h->gridWords;
     std::vector<uint8_t> og(size_t(h->gridCells));
     if (cudaMemcpy(og.data(), h->d_objGrid.p + size_t(env) * h->gridCells, og.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     // opacity is a property of the box a solid voxel belongs to
@@ -700,6 +713,8 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
                     }
                 }
                 if (og[size_t(idx)] != MV_NO_OBJECT) flags |= 4;
+                if ((sol[size_t(h->gridWords) + (idx >> 5)] >> (idx & 31)) & 1u) flags |= 1 << 8;
+                if ((sol[2 * size_t(h->gridWords) + (idx >> 5)] >> (idx & 31)) & 1u) flags |= 2 << 8;
                 if (flags) v.push_back({x + L.grid_org[0], y + L.grid_org[1], z + L.grid_org[2], flags});
             }
     std::sort(v.begin(), v.end());
@@ -787,9 +802,9 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
                             int32_t *out, int cap) {
     const int sc = scenario ? mv::scenarioFromName(scenario) : -1;
     if (sc < 0 || num_agents < 1 || num_agents > MV_MAX_AGENTS || episode < 0) return MV_ERR_ARG;
-    mv::FloatParams params = mv::defaultFloatParams(sc);
+    mv::FloatParams params = mv::defaultFloatParams(scenario);
     for (int i = 0; i < nparams; ++i) params[keys[i]] = vals[i];
-    mv::LevelGenerator gen(sc, num_agents, params);
+    mv::LevelGenerator gen(scenario, num_agents, params);
     gen.seed((unsigned long)env_seed);
     mv::LevelOut lo;
     try {
@@ -807,12 +822,16 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
         o.push_back(b.flags); o.push_back(int(kPaletteRgb[b.color]));
     }
     for (int i = 0; i < L.n_terrain; ++i) {
-        o.push_back(4);
-        for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
-        for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
+        o.push_back(L.terrain[i].type);
+        for (int a = 0; a < 6; ++a) o.push_back(L.terrain[i].bb[a]);
     }
     for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
     for (int i = 0; i < num_agents; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
+    if (L.scenario == MV_SCENARIO_OBSTACLES) {
+        o.push_back(L.n_movable);
+        o.push_back(L.n_reward);
+        for (int i = 0; i < L.n_reward; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
+    }
     // spawn yaw basis bits, so the float side of spawnAgents is pinned too
     for (int i = 0; i < num_agents; ++i) for (int k = 0; k < 9; ++k) { int32_t u; std::memcpy(&u, &L.spawn_basis[i][k], 4); o.push_back(u); }
     if (int(o.size()) > cap) return -int(o.size());

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <unordered_map>
 #include <unordered_set>
@@ -133,25 +134,59 @@ void setTerrainModel(MvTerrain &t, const IBox &bb, uint32_t color) {
     m = mul(translation(px, py, pz), m);
     std::memcpy(t.model, &m.c[0][0], 64);
     t.color = paletteIndex(color);
+    for (int a = 0; a < 3; ++a) { t.bb[a] = bb.mn[a]; t.bb[3 + a] = bb.mx[a]; }
 }
 
 }  // namespace
 
-int scenarioFromName(const std::string &name) {
+static std::string lower(const std::string &name) {
     std::string n;
     for (char ch : name) n.push_back(char(std::tolower(ch)));
+    return n;
+}
+
+// registered names (src/libs/scenarios/include/scenarios/init.hpp:33-56) that are implemented
+int scenarioFromName(const std::string &name) {
+    const std::string n = lower(name);
     if (n == "towerbuilding") return MV_SCENARIO_TOWER;
+    if (n == "obstacleseasy" || n == "obstaclesmedium" || n == "obstacleshard" || n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava" || n == "test")
+        return MV_SCENARIO_OBSTACLES;
     return -1;
 }
 
-FloatParams defaultFloatParams(int) {  // scenario.hpp:225-231
-    return {{"episodeLengthSec", 60.0f}, {"verticalLookLimitRad", 0.2f}, {"useUIRewardIndicators", 0.0f}};
+// Scenario::initializeDefaultParameters (scenario.hpp:225-231) + ObstaclesScenario and its variants (scenario_obstacles.hpp:48-270)
+FloatParams defaultFloatParams(const std::string &name) {
+    const std::string n = lower(name);
+    FloatParams fp{{"episodeLengthSec", 60.0f}, {"verticalLookLimitRad", 0.2f}, {"useUIRewardIndicators", 0.0f}};
+    if (scenarioFromName(n) == MV_SCENARIO_OBSTACLES) {
+        fp["obstaclesMinNumPlatforms"] = 1; fp["obstaclesMaxNumPlatforms"] = 2; fp["obstaclesMinGap"] = 1; fp["obstaclesMaxGap"] = 2;
+        fp["obstaclesMinLava"] = 1; fp["obstaclesMaxLava"] = 4; fp["obstaclesMinHeight"] = 1; fp["obstaclesMaxHeight"] = 3;
+        fp["obstaclesNumAllowedMaxDifficulty"] = 1;
+        if (n == "obstaclesmedium") {
+            fp["obstaclesMinNumPlatforms"] = 2; fp["obstaclesMaxNumPlatforms"] = 4; fp["obstaclesMinLava"] = 2; fp["obstaclesMaxLava"] = 5;
+        } else if (n == "obstacleshard") {
+            fp["obstaclesMinNumPlatforms"] = 2; fp["obstaclesMaxNumPlatforms"] = 7; fp["obstaclesMinGap"] = 2; fp["obstaclesMaxGap"] = 3;
+            fp["obstaclesMinLava"] = 3; fp["obstaclesMaxLava"] = 10; fp["obstaclesMinHeight"] = 2; fp["obstaclesMaxHeight"] = 4;
+        } else if (n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava") {
+            fp["obstaclesMinNumPlatforms"] = 1; fp["obstaclesMaxNumPlatforms"] = 4; fp["obstaclesMinGap"] = 1; fp["obstaclesMaxGap"] = 3;
+            fp["obstaclesMinLava"] = 2; fp["obstaclesMaxLava"] = 10; fp["obstaclesMinHeight"] = 1; fp["obstaclesMaxHeight"] = 3;
+        } else if (n == "test") {
+            fp["obstaclesMinNumPlatforms"] = 0; fp["obstaclesMaxNumPlatforms"] = 0; fp["episodeLengthSec"] = 6.0f;
+        }
+    }
+    return fp;
 }
 
-std::vector<std::pair<std::string, float>> defaultRewardShaping(int scenario) {
+std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::string &name) {
+    const std::string n = lower(name);
+    const int scenario = scenarioFromName(n);
     if (scenario == MV_SCENARIO_TOWER)  // scenario_tower_building.hpp:44-52
         return {{"teamSpirit", 0.1f}, {"towerPickedUpObject", 0.1f}, {"towerVisitedBuildingZoneWithObject", 0.1f}, {"towerBuildingReward", 1.0f}};
-    return {{"teamSpirit", 0.0f}};
+    if (scenario == MV_SCENARIO_OBSTACLES) {  // scenario_obstacles.hpp:37-45,201-206
+        const bool oneType = n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava";
+        return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f}, {"obstaclesAgentCarriedObjectToExit", oneType ? 1.0f : 0.0f}};
+    }
+    return {};
 }
 
 int rewardSlot(int scenario, const std::string &key) {
@@ -161,10 +196,24 @@ int rewardSlot(int scenario, const std::string &key) {
         if (key == "towerVisitedBuildingZoneWithObject") return MV_R_TOWER_VISITED_BZ;
         if (key == "towerBuildingReward") return MV_R_TOWER_BUILDING;
     }
+    if (scenario == MV_SCENARIO_OBSTACLES) {
+        if (key == "obstaclesAgentAtExit") return MV_R_OBST_AGENT_AT_EXIT;
+        if (key == "obstaclesAllAgentsAtExit") return MV_R_OBST_ALL_AT_EXIT;
+        if (key == "obstaclesExtraReward") return MV_R_OBST_EXTRA;
+        if (key == "obstaclesAgentCarriedObjectToExit") return MV_R_OBST_CARRIED_TO_EXIT;
+    }
     return -1;
 }
 
-LevelGenerator::LevelGenerator(int scenario, int numAgents, const FloatParams &params) : scenario_(scenario), numAgents_(numAgents), params_(params) {}
+int gridCapacity(int scenario) {
+    // TowerBuilding rooms are at most 29 x (6+18) x 24; Obstacles chains of up to 7 platforms (+ transitions, start, exit)
+    // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
+    const int cells = scenario == MV_SCENARIO_TOWER ? 30 * 25 * 25 : 512 * 1024;
+    return ((cells + 127) / 128) * 128;
+}
+
+LevelGenerator::LevelGenerator(const std::string &scenarioName, int numAgents, const FloatParams &params)
+    : scenario_(scenarioFromName(scenarioName)), name_(lower(scenarioName)), numAgents_(numAgents), params_(params) {}
 
 void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     std::memset(&out.level, 0, sizeof(MvLevel));
@@ -173,10 +222,10 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     rng_.seed((unsigned long)sd);
     out.level.serial = serial;
     out.level.scenario = scenario_;
-    out.level.episode_len_base = params_.at("episodeLengthSec");
     out.level.look_limit = params_.at("verticalLookLimitRad");
     switch (scenario_) {
         case MV_SCENARIO_TOWER: generateTower(out); break;
+        case MV_SCENARIO_OBSTACLES: generateObstacles(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
     const MvLevel &L = out.level;
@@ -262,10 +311,11 @@ void LevelGenerator::generateTower(LevelOut &out) {
     }
     L.n_static = ns;
     L.n_terrain = 0;
-    if (bz.mx[0] - bz.mn[0] > 0) setTerrainModel(L.terrain[L.n_terrain++], bz, C_DARK_GREY);
+    if (bz.mx[0] - bz.mn[0] > 0) { setTerrainModel(L.terrain[L.n_terrain], bz, C_DARK_GREY); L.terrain[L.n_terrain++].type = 4; }
     if (int(objs.size()) > MV_MAX_OBJECTS - 1) throw std::runtime_error("too many movable objects");
     L.n_obj = int(objs.size());
     L.n_movable = int(objs.size());
+    L.episode_len = params_.at("episodeLengthSec") + 4.0f * float(objs.size());  // scenario_tower_building.cpp:263-266
     for (int i = 0; i < L.n_obj; ++i) {
         L.obj_voxel[i][0] = int16_t(objs[i].x); L.obj_voxel[i][1] = int16_t(objs[i].y); L.obj_voxel[i][2] = int16_t(objs[i].z);
         L.obj_voxel[i][3] = int16_t(paletteIndex(C_LIGHT_BLUE));
@@ -275,14 +325,450 @@ void LevelGenerator::generateTower(LevelOut &out) {
     // dense grid: the room's bounding box, with head-room above the walls for stacked objects
     L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
     L.grid_dim[0] = length; L.grid_dim[1] = height + 18; L.grid_dim[2] = width;
+    fillPlanes(out, &grid);
+}
+
+// three bit planes over the dense grid: solid, exit terrain, lava terrain
+void LevelGenerator::fillPlanes(LevelOut &out, const void *gridPtr) {
+    const VoxMap &grid = *static_cast<const VoxMap *>(gridPtr);
+    const MvLevel &L = out.level;
     const int cells = L.grid_dim[0] * L.grid_dim[1] * L.grid_dim[2];
-    out.solid.assign(size_t(cells + 31) / 32, 0u);
+    const size_t words = size_t(cells + 31) / 32;
+    out.solid.assign(words, 0u); out.exitBits.assign(words, 0u); out.lavaBits.assign(words, 0u);
     for (const auto &kv : grid) {
-        if (!(kv.second.type & MV_SOLID)) continue;
         const I3 c = voxUnkey(kv.first);
-        const int idx = ((c.x - L.grid_org[0]) * L.grid_dim[1] + (c.y - L.grid_org[1])) * L.grid_dim[2] + (c.z - L.grid_org[2]);
-        out.solid[size_t(idx >> 5)] |= 1u << (idx & 31);
+        const int gx = c.x - L.grid_org[0], gy = c.y - L.grid_org[1], gz = c.z - L.grid_org[2];
+        if (gx < 0 || gy < 0 || gz < 0 || gx >= L.grid_dim[0] || gy >= L.grid_dim[1] || gz >= L.grid_dim[2]) throw std::runtime_error("voxel outside the dense grid");
+        const int idx = (gx * L.grid_dim[1] + gy) * L.grid_dim[2] + gz;
+        if (kv.second.type & MV_SOLID) out.solid[size_t(idx >> 5)] |= 1u << (idx & 31);
+        if (kv.second.terrain & 1) out.exitBits[size_t(idx >> 5)] |= 1u << (idx & 31);
+        if (kv.second.terrain & 2) out.lavaBits[size_t(idx >> 5)] |= 1u << (idx & 31);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------- Obstacles
+// Platforms live in integer frames: origin + quarter turns about Y.  The reference pushes integer boxes through float
+// scene-graph matrices (90 degree turns, integer translations) and recovers integers with lround / floor(x+0.5)
+// (platforms.hpp:113-134,153-163,268-276); the accumulated float error over a chain is << 0.5, so exact integer frames
+// give the same voxels, and tests/test_cpu.py checks that against the oracle's float scene graph.
+namespace {
+
+struct Frame {
+    int o[3] = {0, 0, 0};
+    int r = 0;  // quarter turns, Magnum rotationY(+90 deg): x' = z, z' = -x
+    void rot(int x, int z, int &xo, int &zo) const {
+        switch (r & 3) {
+            case 0: xo = x; zo = z; break;
+            case 1: xo = z; zo = -x; break;
+            case 2: xo = -x; zo = -z; break;
+            default: xo = -z; zo = x; break;
+        }
+    }
+    I3 apply(int x, int y, int z) const { int xr, zr; rot(x, z, xr, zr); return {xr + o[0], y + o[1], zr + o[2]}; }
+    // voxel of the transformed cell centre (x+0.5, y+0.5, z+0.5): done on doubled coordinates, exact
+    I3 applyCentre(int x, int y, int z) const {
+        int xr, zr;
+        rot(2 * x + 1, 2 * z + 1, xr, zr);
+        const int X = xr + 2 * o[0], Z = zr + 2 * o[2];
+        return {(X - 1) / 2 + ((X - 1) % 2 != 0 && X - 1 < 0 ? -1 : 0), y + o[1], (Z - 1) / 2 + ((Z - 1) % 2 != 0 && Z - 1 < 0 ? -1 : 0)};
+    }
+    Frame child(int tx, int ty, int tz, int turns) const {  // this * (RotY(turns) then translateLocal(t)) == rotation first, then t in the rotated frame
+        Frame c;
+        c.r = (r + turns) & 3;
+        // origin of the child = this(RotY(turns) * t)
+        Frame local;
+        local.r = turns & 3;
+        int xr, zr;
+        local.rot(tx, tz, xr, zr);
+        const I3 p = apply(xr, ty, zr);
+        c.o[0] = p.x; c.o[1] = p.y; c.o[2] = p.z;
+        return c;
+    }
+};
+
+enum { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP, PT_START, PT_EXIT, PT_TRANSITION };
+enum { W_SOUTH = 1, W_NORTH = 2, W_WEST = 4, W_EAST = 8 };
+
+struct Plat {
+    int type = PT_EMPTY, walls = 0;
+    int length = 0, height = 0, width = -1;
+    Frame parent, root, anchor;
+    std::vector<IBox> layout, wallBoxes;            // local, max exclusive
+    std::vector<std::pair<int, IBox>> terrain;      // (terrain type, local box), std::map order = type order
+    std::map<std::pair<int, int>, int> occupancy;
+    int wallHeight = 0, lavaLength = 0, stepHeight = 0, gap = 0, gapX = 0;
+    int anchorLocal[3] = {0, 0, 0};  // nextPlatformAnchor relative to the root
+
+    IBox world(const IBox &b) const {  // MagnumAABB::boundingBox: transform both corners, sort
+        const I3 a = root.apply(b.mn[0], b.mn[1], b.mn[2]), c = root.apply(b.mx[0], b.mx[1], b.mx[2]);
+        IBox o;
+        o.mn[0] = std::min(a.x, c.x); o.mx[0] = std::max(a.x, c.x);
+        o.mn[1] = std::min(a.y, c.y); o.mx[1] = std::max(a.y, c.y);
+        o.mn[2] = std::min(a.z, c.z); o.mx[2] = std::max(a.z, c.z);
+        return o;
+    }
+    void addFloor() { layout.push_back({{0, 0, 0}, {length, 1, width}}); anchorLocal[0] = length; anchorLocal[1] = 0; anchorLocal[2] = 0; }
+    void addWalls() {
+        if (walls & W_SOUTH) wallBoxes.push_back({{0, 0, 0}, {1, height, width}});
+        if (walls & W_NORTH) wallBoxes.push_back({{length - 1, 0, 0}, {length, height, width}});
+        if (walls & W_EAST) wallBoxes.push_back({{0, 0, 0}, {length, height, 1}});
+        if (walls & W_WEST) wallBoxes.push_back({{0, 0, width - 1}, {length, height, width}});
+    }
+    IBox outer() const {  // Platform::platformBoundingBox
+        IBox o{};
+        bool have = false;
+        auto add = [&](const IBox &w) {
+            if (!have) { o = w; have = true; return; }
+            for (int a = 0; a < 3; ++a) { o.mn[a] = std::min(o.mn[a], std::min(w.mn[a], w.mx[a])); o.mx[a] = std::max(o.mx[a], std::max(w.mn[a], w.mx[a])); }
+        };
+        if (!layout.empty()) add(world(layout.front())); else if (!wallBoxes.empty()) add(world(wallBoxes.front()));
+        for (auto &b : layout) add(world(b));
+        for (auto &b : wallBoxes) add(world(b));
+        return o;
+    }
+};
+
+int P(const FloatParams &p, const char *k) { return int(lroundf(p.at(k))); }
+int tri(int n) { return n * (n + 1) / 2; }
+
+void platInit(Plat &p, Rng &rng, const FloatParams &fp) {
+    if (p.type == PT_TRANSITION) { p.height = 5; return; }
+    // EmptyPlatform::init
+    p.length = randRange(4, 10, rng);
+    if (p.width == -1) p.width = randRange(5, 9, rng);
+    p.height = 5;
+    switch (p.type) {
+        case PT_WALL:
+            p.wallHeight = randRange(P(fp, "obstaclesMinHeight"), P(fp, "obstaclesMaxHeight") + 1, rng);
+            p.height = randRange(p.wallHeight + 4, p.wallHeight + 6, rng);
+            break;
+        case PT_LAVA: {
+            p.length = randRange(6, 12, rng);
+            const int minLava = std::min(P(fp, "obstaclesMinLava"), p.length - 2), maxLava = std::min(P(fp, "obstaclesMaxLava") + 1, p.length - 1);
+            p.lavaLength = randRange(minLava, maxLava, rng);
+            break;
+        }
+        case PT_STEP:
+            p.stepHeight = randRange(P(fp, "obstaclesMinHeight"), P(fp, "obstaclesMaxHeight") + 1, rng);
+            p.height = randRange(p.stepHeight + 2, p.stepHeight + 5, rng);
+            break;
+        case PT_GAP:
+            p.gap = randRange(P(fp, "obstaclesMinGap"), std::min(P(fp, "obstaclesMaxGap") + 1, p.length - 1), rng);
+            p.gapX = randRange(1, p.length - p.gap, rng);
+            break;
+        default: break;
+    }
+}
+
+bool platMaxDifficulty(const Plat &p, const FloatParams &fp) {
+    switch (p.type) {
+        case PT_WALL: return p.wallHeight >= P(fp, "obstaclesMaxHeight");
+        case PT_LAVA: return p.lavaLength >= P(fp, "obstaclesMaxLava");
+        case PT_STEP: return p.stepHeight >= P(fp, "obstaclesMaxHeight");
+        default: return false;
+    }
+}
+
+int platRequiredBoxes(const Plat &p) {
+    switch (p.type) {
+        case PT_WALL: return tri(p.wallHeight - 1);
+        case PT_LAVA: return std::max(1, p.lavaLength - 1);
+        case PT_STEP: return tri(p.stepHeight - 1);
+        case PT_GAP: return tri(std::max(0, p.gap - 2));
+        default: return 0;
+    }
+}
+
+void platGenerate(Plat &p, Rng &rng) {
+    switch (p.type) {
+        case PT_WALL: {
+            p.addFloor(); p.addWalls();
+            const int wallX = randRange(1, p.length, rng);
+            const int wallThickness = randRange(1, p.length - wallX + 1, rng);
+            p.layout.push_back({{wallX, 1, 1}, {wallX + wallThickness, 1 + p.wallHeight, p.width - 1}});
+            for (int x = wallX; x < wallX + wallThickness; ++x)
+                for (int z = 1; z < p.width; ++z) p.occupancy[{x, z}] = p.wallHeight;
+            break;
+        }
+        case PT_LAVA: {
+            p.addFloor(); p.addWalls();
+            const int lavaX = randRange(1, p.length - p.lavaLength, rng);
+            p.terrain.push_back({2, {{lavaX, 1, 1}, {lavaX + p.lavaLength, 2, p.width - 1}}});
+            break;
+        }
+        case PT_STEP: {
+            const int stepX = randRange(1, p.length, rng);
+            p.layout.push_back({{0, 0, 0}, {stepX + 1, 1, p.width}});
+            p.layout.push_back({{stepX, p.stepHeight, 0}, {p.length, p.stepHeight + 1, p.width}});
+            p.layout.push_back({{stepX, 0, 0}, {stepX + 1, p.stepHeight + 1, p.width}});
+            p.anchorLocal[0] = p.length; p.anchorLocal[1] = p.stepHeight; p.anchorLocal[2] = 0;
+            p.addWalls();
+            for (int x = stepX + 1; x < p.length; ++x)
+                for (int z = 1; z < p.width; ++z) p.occupancy[{x, z}] = p.stepHeight;
+            break;
+        }
+        case PT_GAP:
+            p.layout.push_back({{0, 0, 0}, {p.gapX, 1, p.width}});
+            p.layout.push_back({{p.gapX + p.gap, 0, 0}, {p.length, 1, p.width}});
+            p.anchorLocal[0] = p.length; p.anchorLocal[1] = 0; p.anchorLocal[2] = 0;
+            p.addWalls();
+            break;
+        case PT_EXIT:
+            p.addFloor(); p.addWalls();
+            p.terrain.push_back({1, {{p.length - 3, 1, 1}, {p.length - 1, 3, p.width - 1}}});
+            break;
+        default:
+            p.addFloor(); p.addWalls();
+            break;
+    }
+}
+
+// Platform::generateObjectPositions / GapPlatform override (platforms.hpp:248-276,489-508)
+std::vector<I3> platObjectPositions(Plat &p, int n, Rng &rng) {
+    std::vector<I3> boxes;
+    if (p.type == PT_GAP) {
+        std::vector<I3> candidates;
+        for (int x = 0; x < p.length; ++x)
+            for (int z = 1; z < p.width - 1; ++z) {
+                if (x >= p.gapX && x < p.gapX + p.gap) continue;
+                candidates.push_back({x, 1, z});
+            }
+        for (int i = 0; i < n; ++i) {
+            const I3 v = candidates[size_t(randRange(0, int(candidates.size()), rng))];
+            const int y = ++p.occupancy[{v.x, v.z}];
+            boxes.push_back({v.x, y, v.z});
+        }
+    } else {
+        for (int i = 0; i < n; ++i)
+            for (int attempt = 0; attempt < 10; ++attempt) {
+                const int x = randRange(1, p.length - 1, rng);
+                const int z = randRange(1, p.width - 1, rng);
+                if (p.occupancy[{x, z}] < 2 || attempt >= 9) {
+                    const int y = ++p.occupancy[{x, z}];
+                    boxes.push_back({x, y, z});
+                    break;
+                }
+            }
+    }
+    for (auto &c : boxes) c = p.root.applyCentre(c.x, c.y, c.z);  // adjustTransformation
+    return boxes;
+}
+
+bool boxesCollide(const IBox &a, const IBox &b) {  // BoundingBox::collidesWith
+    for (int k = 0; k < 3; ++k) {
+        if (a.mx[k] <= b.mn[k]) return false;
+        if (a.mn[k] >= b.mx[k]) return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+void LevelGenerator::generateObstacles(LevelOut &out) {
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    const FloatParams &fp = params_;
+    std::vector<int> platformTypes = {PT_WALL, PT_LAVA, PT_STEP, PT_GAP};
+    if (name_ == "obstacleswalls") platformTypes = {PT_WALL};
+    else if (name_ == "obstaclessteps") platformTypes = {PT_STEP};
+    else if (name_ == "obstacleslava") platformTypes = {PT_LAVA};
+
+    const bool drawWalls = randRange(0, 2, rng);
+    std::vector<Plat> platforms;
+    int numPlatforms = 0;
+    for (int attempt = 0; attempt < 20; ++attempt) {
+        platforms.clear();
+        numPlatforms = randRange(int(lroundf(fp.at("obstaclesMinNumPlatforms"))), int(lroundf(fp.at("obstaclesMaxNumPlatforms"))) + 1, rng);
+        Plat start;
+        start.type = PT_START; start.walls = W_SOUTH | W_EAST | W_WEST;
+        platInit(start, rng, fp);
+        platGenerate(start, rng);
+        start.anchor = start.root.child(start.anchorLocal[0], start.anchorLocal[1], start.anchorLocal[2], 0);
+        int requiredWidth = start.width;
+        platforms.push_back(start);
+        int prev = 0;
+        int numMax = 0;
+        const int allowedMax = int(fp.at("obstaclesNumAllowedMaxDifficulty"));
+        for (int i = 0; i < numPlatforms; ++i) {
+            const int orientation = randRange(0, 3, rng);  // STRAIGHT, TURN_LEFT, TURN_RIGHT
+            requiredWidth = orientation == 0 ? requiredWidth : -1;
+            Plat np;
+            bool have = false;
+            while (!have || (platMaxDifficulty(np, fp) && numMax >= allowedMax)) {
+                np = Plat();
+                np.type = platformTypes[size_t(randRange(0, int(platformTypes.size()), rng))];
+                np.walls = W_WEST | W_EAST;
+                np.width = requiredWidth;
+                np.parent = platforms[size_t(prev)].anchor;
+                np.root = np.parent;
+                platInit(np, rng, fp);
+                have = true;
+            }
+            if (platMaxDifficulty(np, fp)) ++numMax;
+            platGenerate(np, rng);
+            const int prevWidth = platforms[size_t(prev)].width;
+            // rotateCCW: rotateYLocal(+90) then translateLocal(-1,0,-1); rotateCW: rotateYLocal(-90) then translateLocal(prevW-1, 0, -width+1)
+            if (orientation == 1) np.root = np.parent.child(-1, 0, -1, 1);
+            else if (orientation == 2) np.root = np.parent.child(prevWidth - 1, 0, -np.width + 1, 3);
+            np.anchor = np.root.child(np.anchorLocal[0], np.anchorLocal[1], np.anchorLocal[2], 0);
+            platforms.push_back(np);
+            const int cur = int(platforms.size()) - 1;
+            if (orientation != 0) {
+                Plat tp;
+                tp.type = PT_TRANSITION;
+                tp.walls = W_NORTH | (orientation == 1 ? W_WEST : W_EAST);
+                tp.length = platforms[size_t(cur)].width - 1; tp.width = prevWidth;
+                tp.parent = platforms[size_t(prev)].anchor; tp.root = tp.parent;
+                platInit(tp, rng, fp);
+                platGenerate(tp, rng);
+                tp.anchor = tp.root.child(tp.anchorLocal[0], tp.anchorLocal[1], tp.anchorLocal[2], 0);
+                platforms.push_back(tp);
+            }
+            prev = cur;
+            requiredWidth = platforms[size_t(cur)].width;
+        }
+        Plat ex;
+        ex.type = PT_EXIT; ex.walls = W_NORTH | W_EAST | W_WEST; ex.width = requiredWidth;
+        ex.parent = platforms[size_t(prev)].anchor; ex.root = ex.parent;
+        platInit(ex, rng, fp);
+        platGenerate(ex, rng);
+        platforms.push_back(ex);
+
+        bool selfCollision = false;
+        for (int j = 0; j < int(platforms.size()) && !selfCollision; ++j)
+            for (int k = 0; k < j - 2; ++k)
+                if (boxesCollide(platforms[size_t(j)].outer(), platforms[size_t(k)].outer())) { selfCollision = true; break; }
+        if (!selfCollision) break;
+    }
+    const uint32_t layoutColor = randomLayoutColor(rng);
+    const uint32_t wallColor = randomLayoutColor(rng);
+
+    VoxMap grid{100};
+    const uint8_t wallType = uint8_t(MV_SOLID | (drawWalls ? MV_OPAQUE : 0));
+    for (auto &p : platforms) {
+        for (auto &b : p.layout) fillBox(grid, p.world(b), MV_SOLID | MV_OPAQUE, layoutColor);
+        for (auto &b : p.wallBoxes) fillBox(grid, p.world(b), wallType, wallColor);
+        std::vector<std::pair<int, IBox>> ts = p.terrain;
+        std::stable_sort(ts.begin(), ts.end(), [](const std::pair<int, IBox> &a, const std::pair<int, IBox> &b) { return a.first < b.first; });
+        for (auto &t : ts) fillTerrain(grid, p.world(t.second), t.first);
+    }
+
+    // StartPlatform::agentSpawnPoints (platforms.hpp:221-244)
+    std::vector<I3> agentSpawn;
+    {
+        Plat &sp = platforms[0];
+        std::set<std::pair<int, int>> used;
+        for (int i = 0; i < A; ++i)
+            for (int attempt = 0; attempt < 10; ++attempt) {
+                const int x = randRange(1, sp.length - 1, rng);
+                const int z = randRange(1, sp.width - 1, rng);
+                if (used.count({x, z})) continue;
+                const int y = sp.occupancy[{x, z}] + 1;
+                sp.occupancy[{x, z}] += 2;
+                agentSpawn.push_back({x, y, z});
+                used.emplace(x, z);
+                break;
+            }
+    }
+    if (int(agentSpawn.size()) < A) throw std::runtime_error("start platform too small for the agents");
+
+    std::vector<int> numBoxes(platforms.size(), 0);
+    for (int i = 1; i < int(platforms.size()); ++i) {
+        const int n = platRequiredBoxes(platforms[size_t(i)]);
+        for (int box = 0; box < n; ++box) ++numBoxes[size_t(randRange(std::max(0, i - 2), i, rng))];
+    }
+    std::vector<I3> objs, rewards;
+    for (int i = 0; i < int(platforms.size()); ++i) {
+        const float randomBoxesFraction = frand(rng) * 0.5f;
+        const int randomBoxes = int(lroundf(randomBoxesFraction * numBoxes[size_t(i)])) + randRange(0, 2, rng);
+        const auto coords = platObjectPositions(platforms[size_t(i)], numBoxes[size_t(i)] + randomBoxes, rng);
+        objs.insert(objs.end(), coords.begin(), coords.end());
+    }
+    for (int i = 1; i < int(platforms.size()) - 1; ++i) {
+        const int numRewardObjects = randRange(0, 2, rng);
+        const auto coords = platObjectPositions(platforms[size_t(i)], numRewardObjects, rng);
+        rewards.insert(rewards.end(), coords.begin(), coords.end());
+    }
+
+    // DefaultScenario::spawnAgents
+    for (int i = 0; i < A; ++i) {
+        const float yaw = frand(rng) * 3.14159265358979323846f * 2;
+        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        const float sx = float(agentSpawn[size_t(i)].x) + 0.5f, sy = float(agentSpawn[size_t(i)].y) + 0.0f, sz = float(agentSpawn[size_t(i)].z) + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        L.init_pos[i][0] = float(agentSpawn[size_t(i)].x); L.init_pos[i][1] = float(agentSpawn[size_t(i)].y); L.init_pos[i][2] = float(agentSpawn[size_t(i)].z);
+    }
+
+    // addEpisodeDrawables: merged boxes, terrain slabs (per platform, terrain-type order), objects, reward diamonds
+    int ns = 0;
+    for (const auto &g : mergeVoxels(grid)) {
+        if (g.type == 0) continue;
+        for (const auto &b : g.boxes) {
+            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
+            MvBox &sb = L.statics[ns++];
+            for (int a = 0; a < 3; ++a) {
+                sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
+                sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;
+            }
+            sb.flags = g.type;
+            sb.color = paletteIndex(g.color);
+        }
+    }
+    L.n_static = ns;
+    L.n_terrain = 0;
+    for (auto &p : platforms) {
+        std::vector<std::pair<int, IBox>> ts = p.terrain;
+        std::stable_sort(ts.begin(), ts.end(), [](const std::pair<int, IBox> &a, const std::pair<int, IBox> &b) { return a.first < b.first; });
+        for (auto &t : ts) {
+            const IBox w = p.world(t.second);
+            if (w.mx[0] - w.mn[0] > 0) {
+                if (L.n_terrain >= MV_MAX_TERRAIN) throw std::runtime_error("too many terrain slabs");
+                setTerrainModel(L.terrain[L.n_terrain], w, t.first == 1 ? C_LIGHT_GREEN : C_RED);
+                L.terrain[L.n_terrain++].type = t.first;
+            }
+        }
+    }
+    if (int(objs.size()) > MV_MAX_OBJECTS - 1) throw std::runtime_error("too many movable objects");
+    L.n_obj = int(objs.size());
+    L.n_movable = int(objs.size());
+    for (int i = 0; i < L.n_obj; ++i) {
+        L.obj_voxel[i][0] = int16_t(objs[size_t(i)].x); L.obj_voxel[i][1] = int16_t(objs[size_t(i)].y); L.obj_voxel[i][2] = int16_t(objs[size_t(i)].z);
+        L.obj_voxel[i][3] = int16_t(paletteIndex(C_LIGHT_BLUE));
+    }
+    if (int(rewards.size()) > MV_MAX_REWARD) throw std::runtime_error("too many reward objects");
+    L.n_reward = int(rewards.size());
+    {
+        using namespace mvh;
+        // bottomHalf.rotateXLocal(180 deg).translate({0,-1,0})
+        const float ang = 180.0f * 3.14159265358979323846f / 180.0f;
+        M4 rx = identity();
+        const float s = crsin(ang), c = crcos(ang);
+        rx.c[1][1] = c; rx.c[1][2] = s; rx.c[2][1] = -s; rx.c[2][2] = c;
+        const M4 bottom = mul(translation(0.0f, -1.0f, 0.0f), mul(identity(), rx));
+        std::memcpy(L.cone_bottom_local, &bottom.c[0][0], 64);
+        for (int i = 0; i < L.n_reward; ++i) {
+            const I3 r = rewards[size_t(i)];
+            L.reward_voxel[i][0] = int16_t(r.x); L.reward_voxel[i][1] = int16_t(r.y); L.reward_voxel[i][2] = int16_t(r.z);
+            L.reward_voxel[i][3] = int16_t(paletteIndex(C_GREEN));
+            const float tx = float(r.x) + 0.5f, ty = float(r.y) + 0.7f, tz = float(r.z) + 0.5f;
+            const M4 root = mul(translation(tx, ty, tz), mul(scaling(0.17f * 0.8f, 0.45f * 0.8f, 0.17f * 0.8f), identity()));
+            std::memcpy(L.reward_root[i], &root.c[0][0], 64);
+        }
+    }
+    // ObstaclesScenario::episodeLengthSec (scenario_obstacles.cpp:262-266)
+    L.episode_len = std::max(fp.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objs.size()) * 1);
+    L.n_movable = numPlatforms;  // reported by the level dump
+
+    // dense grid bounds: every voxel entry, objects, rewards; y from -30 (objects dropped into gaps sink there)
+    int mn[3] = {1 << 20, -30, 1 << 20}, mx[3] = {-(1 << 20), -(1 << 20), -(1 << 20)};
+    auto grow = [&](int x, int y, int z) { mn[0] = std::min(mn[0], x); mn[2] = std::min(mn[2], z); mx[0] = std::max(mx[0], x); mx[1] = std::max(mx[1], y); mx[2] = std::max(mx[2], z); };
+    for (const auto &kv : grid) { const I3 c = voxUnkey(kv.first); grow(c.x, c.y, c.z); }
+    for (auto &c : objs) grow(c.x, c.y, c.z);
+    for (auto &c : rewards) grow(c.x, c.y, c.z);
+    L.grid_org[0] = mn[0] - 1; L.grid_org[1] = mn[1]; L.grid_org[2] = mn[2] - 1;
+    L.grid_dim[0] = mx[0] - mn[0] + 3; L.grid_dim[1] = mx[1] - mn[1] + 1 + 12; L.grid_dim[2] = mx[2] - mn[2] + 3;
+    fillPlanes(out, &grid);
 }
 
 }  // namespace mv

@@ -19,11 +19,12 @@ using FloatParams = std::map<std::string, float>;
 struct LevelOut {
     MvLevel level;
     std::vector<uint32_t> solid;  // grid_dim product bits, x-major: idx = (x*dimY + y)*dimZ + z
+    std::vector<uint32_t> exitBits, lavaBits;  // terrain planes, same indexing
 };
 
 class LevelGenerator {
 public:
-    LevelGenerator(int scenario, int numAgents, const FloatParams &params);
+    LevelGenerator(const std::string &scenarioName, int numAgents, const FloatParams &params);
     void seed(unsigned long s) { rng_.seed(s); }
     // Generates the next episode's level.  gridCells = capacity of the dense grid (cells); throws std::runtime_error
     // if the level does not fit the engine's fixed capacities.
@@ -31,15 +32,20 @@ public:
 
 private:
     void generateTower(LevelOut &out);
-    int scenario_, numAgents_;
+    void generateObstacles(LevelOut &out);
+    void fillPlanes(LevelOut &out, const void *voxMap);
+    int scenario_;
+    std::string name_;
+    int numAgents_;
     FloatParams params_;
     std::mt19937 rng_{std::random_device{}()};
 };
 
 int scenarioFromName(const std::string &name);  // -1 if unknown
-FloatParams defaultFloatParams(int scenario);
-// default reward table for the scenario (MV_R_* slots) and its key names
-std::vector<std::pair<std::string, float>> defaultRewardShaping(int scenario);
+FloatParams defaultFloatParams(const std::string &scenarioName);
+// default reward shaping of the (registered) scenario name
+std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::string &scenarioName);
+int gridCapacity(int scenario);  // dense voxel grid capacity in cells
 int rewardSlot(int scenario, const std::string &key);  // -1 if unknown
 
 }  // namespace mv

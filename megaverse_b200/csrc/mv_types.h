@@ -2,7 +2,7 @@
 //
 // HBM layout (one GPU, E envs, A agents per env, N = E*A views):
 //   levels   MvLevel[E][2]          double-buffered immutable level description (host-generated, H2D on reset only)
-//   solid    uint32[E][2][GW]       bit-packed solid-voxel occupancy over the level's bounding grid
+//   solid    uint32[E][2][3][GW]    bit-packed voxel planes over the level's bounding grid: solid, exit terrain, lava terrain
 //   objGrid  uint8[E][GC]           dynamic voxel -> movable-object id map (0xFF = none)
 //   envs     MvEnvState[E]          per-env scalars + the building-zone set
 //   agents   MvAgent[E*A]           kinematic controller + camera state
@@ -18,12 +18,14 @@
 #include <stdint.h>
 
 #define MV_MAX_AGENTS 8
-#define MV_MAX_STATIC 96
+#define MV_MAX_STATIC 160
 #define MV_MAX_TERRAIN 16
 #define MV_MAX_OBJECTS 128
+#define MV_MAX_REWARD 16
 #define MV_NO_OBJECT 0xFF
 
 #define MV_SCENARIO_TOWER 0
+#define MV_SCENARIO_OBSTACLES 1
 
 // voxel / box flags (voxel_state.hpp:10-15)
 #define MV_SOLID 1
@@ -46,6 +48,11 @@
 #define MV_R_TOWER_PICKED_UP 1
 #define MV_R_TOWER_VISITED_BZ 2
 #define MV_R_TOWER_BUILDING 3
+// Obstacles (scenario_obstacles.hpp:37-45)
+#define MV_R_OBST_AGENT_AT_EXIT 1
+#define MV_R_OBST_ALL_AT_EXIT 2
+#define MV_R_OBST_EXTRA 3
+#define MV_R_OBST_CARRIED_TO_EXIT 4
 #define MV_R_COUNT 8
 
 // fault bits (per env, sticky): the engine never exit()s, it reports
@@ -65,7 +72,8 @@ struct MvBox {       // static layout box: drawable (OPAQUE) and/or collider (SO
 struct MvTerrain {
     float model[16];  // column-major model matrix (layout_utils.cpp:53-68)
     int32_t color;
-    int32_t pad[3];
+    int32_t type;     // TerrainType bit (platforms.hpp:28-34)
+    int32_t bb[6];    // world voxel box min3, max3 (exclusive)
 };
 
 struct MvLevel {
@@ -75,15 +83,19 @@ struct MvLevel {
     int32_t n_movable;    // numMovableBoxes() for episodeLengthSec (scenario_tower_building.cpp:263-266)
     int32_t grid_org[3], grid_dim[3];
     int32_t bz_min[3], bz_max[3];  // building zone (x,z used)
-    float episode_len_base;        // floatParams["episodeLengthSec"]
+    float episode_len;             // episodeLengthSec() of this level (scenario_tower_building.cpp:263-266, scenario_obstacles.cpp:262-266)
     float look_limit;              // floatParams["verticalLookLimitRad"]
-    int32_t pad0[4];               // statics[] must start 16-byte aligned (TMA bulk copy source)
+    int32_t n_reward;              // Obstacles: reward diamonds
+    int32_t pad0[3];               // statics[] must start 16-byte aligned (TMA bulk copy source)
     MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
     MvTerrain terrain[MV_MAX_TERRAIN];
     int16_t obj_voxel[MV_MAX_OBJECTS][4];  // x,y,z,color
     float spawn_pos[MV_MAX_AGENTS][4];     // ghost origin at spawn (agent.cpp:45)
     float spawn_basis[MV_MAX_AGENTS][12];  // ghost basis rows (btMatrix3x3(btQuaternion(Y, yaw)))
     float init_pos[MV_MAX_AGENTS][4];      // FallDetection agentInitialPositions
+    int16_t reward_voxel[MV_MAX_REWARD][4];  // Obstacles reward objects: voxel + palette colour
+    float reward_root[MV_MAX_REWARD][16];    // addDiamond root model matrix (layout_utils.cpp:114-126)
+    float cone_bottom_local[16];             // the lower cone's local transform (rotateXLocal(180 deg), translate(0,-1,0))
 };
 
 struct MvAgent {
@@ -121,6 +133,10 @@ struct MvEnvState {
     float bz_reward;         // currBuildingZoneReward
     int32_t faults;
     // std::unordered_set<VoxelCoords> objectsInBuildingZone, emulated in libstdc++ iteration order (bzset.h)
+    int32_t solved;          // Obstacles: all agents reached the exit
+    uint32_t reached_exit;   // Obstacles: bit per agent
+    uint32_t reward_alive;   // Obstacles: bit per reward object still in place
+    int32_t pad1;
     int32_t bz_count, bz_nb, bz_next_resize;
     int16_t bz_items[MV_MAX_OBJECTS][4];
     int32_t pad[2];
@@ -136,7 +152,7 @@ struct MvInstance {
     int32_t color;    // palette index
     int32_t pad[2];
 };
-#define MV_MAX_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS)
+#define MV_MAX_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 2 * MV_MAX_REWARD)
 
 struct MvConsts {        // host-computed constants (so host libm decides their bits once, identically for oracle and device)
     float look_left[9];  // btMatrix3x3(btQuaternion(Y, +3.5*dt)) rows
@@ -151,4 +167,5 @@ struct MvConsts {        // host-computed constants (so host libm decides their 
 static_assert(sizeof(MvBox) == 32 && sizeof(MvObject) == 64, "TMA bulk copies need 16-byte multiples");
 static_assert(offsetof(MvLevel, statics) % 16 == 0 && sizeof(MvLevel) % 16 == 0, "MvLevel alignment");
 static_assert(sizeof(MvInstance) == 80, "MvInstance layout");
+static_assert(sizeof(MvEnvState) % 4 == 0 && sizeof(MvAgent) % 4 == 0, "word copies");
 #endif

@@ -40,7 +40,7 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct StepParams {
     const MvLevel *levels;       // [E][2]
-    const uint32_t *solid;       // [E][2][gridWords]
+    const uint32_t *solid;       // [E][2][3][gridWords] planes: solid, exit terrain, lava terrain
     uint8_t *objGrid;            // [E][gridCells]
     MvEnvState *envs;            // [E]
     MvAgent *agents;             // [E*A]
@@ -589,12 +589,15 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
     if (lane == 0) {
         MvEnvState &e = S.env;
         e.episode_sec = 0.0f; e.num_frames = 0; e.highest_tower = 0;
+        e.solved = 0; e.reached_exit = 0u; e.reward_alive = L.n_reward >= 32 ? 0xffffffffu : ((1u << L.n_reward) - 1u);
         mvBzClear(e);
-        for (int i = 0; i < L.n_obj; ++i) {
-            const int x = L.obj_voxel[i][0], y = L.obj_voxel[i][1], z = L.obj_voxel[i][2];
-            if (inBuildingZone(L, x, z)) mvBzInsert(e, x, y, z);
-        }
-        e.bz_reward = towerReward(e);
+        if (L.scenario == MV_SCENARIO_TOWER) {
+            for (int i = 0; i < L.n_obj; ++i) {
+                const int x = L.obj_voxel[i][0], y = L.obj_voxel[i][1], z = L.obj_voxel[i][2];
+                if (inBuildingZone(L, x, z)) mvBzInsert(e, x, y, z);
+            }
+            e.bz_reward = towerReward(e);
+        } else e.bz_reward = 0.0f;
     }
     __syncwarp();
 }
@@ -645,7 +648,15 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
         const int agentColors[7] = {0, 1, 3, 7, 14, 10, 12};  // const.hpp:85 as palette indices
         putInstance(inst[base + no + 2 * A + i], mul4(objT, bodyLocal), 1, agentColors[i % 7]);
     }
-    if (lane == 0) { counts[0] = base + no + 2 * A; counts[1] = base + no + 3 * A; }
+    // reward diamonds: two cones each (layout_utils.cpp:114-126); a collected one has been translated by (1000,1000,1000)
+    const int nr = L.n_reward;
+    for (int i = lane; i < nr; i += 32) {
+        M4 root = loadM4(L.reward_root[i]);
+        if (!((S.env.reward_alive >> i) & 1u)) root = mul4(translation4(v3(1000, 1000, 1000)), root);
+        putInstance(inst[base + no + 3 * A + 2 * i], root, 3, L.reward_voxel[i][3]);
+        putInstance(inst[base + no + 3 * A + 2 * i + 1], mul4(root, loadM4(L.cone_bottom_local)), 3, L.reward_voxel[i][3]);
+    }
+    if (lane == 0) { counts[0] = base + no + 2 * A; counts[1] = base + no + 3 * A + 2 * nr; }
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -838,11 +849,12 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                         toVoxel(v3(S.agents[j].object_t[12], S.agents[j].object_t[13], S.agents[j].object_t[14]), cx, cy, cz);
                         if (cx == vx && cy == vy && cz == vz) { collidesWithAgent = true; break; }
                     }
-                    const uint32_t *sol = P.solid + (size_t(env) * 2 + slot) * P.gridWords;
+                    const uint32_t *sol = P.solid + (size_t(env) * 2 + slot) * 3 * P.gridWords;
                     auto solidAt = [&](int g) { return g >= 0 && ((sol[g >> 5] >> (g & 31)) & 1u); };
                     auto objAt = [&](int g) { return g >= 0 ? int(objGrid[g]) : int(MV_NO_OBJECT); };
                     const bool empty = !solidAt(gi) && objAt(gi) == MV_NO_OBJECT;
-                    if (empty && !collidesWithAgent && inBuildingZone(*L, vx, vz)) {
+                    // canPlaceObject: TowerBuilding only inside the building zone, default true elsewhere
+                    if (empty && !collidesWithAgent && (L->scenario != MV_SCENARIO_TOWER || inBuildingZone(*L, vx, vz))) {
                         while (true) {
                             const int by = vy - 1;
                             if (by < -30) break;
@@ -860,14 +872,15 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                         o.enabled = !o.enabled;
                         a.carrying = -1;
                         S.objDirty[S.nDirty++] = oi;
-                        // placedObject (scenario_tower_building.cpp:206-214)
-                        if (inBuildingZone(*L, vx, vz)) mvBzInsert(e, vx, vy, vz);
-                        const float newReward = towerReward(e);
-                        const float delta = newReward - e.bz_reward;
-                        e.bz_reward = newReward;
-                        rewardTeam(MV_R_TOWER_BUILDING, i, delta);
-                        const int hgt = vy - L->bz_min[1] + 1;
-                        e.highest_tower = e.highest_tower > hgt ? e.highest_tower : hgt;
+                        if (L->scenario == MV_SCENARIO_TOWER) {  // placedObject (scenario_tower_building.cpp:206-214)
+                            if (inBuildingZone(*L, vx, vz)) mvBzInsert(e, vx, vy, vz);
+                            const float newReward = towerReward(e);
+                            const float delta = newReward - e.bz_reward;
+                            e.bz_reward = newReward;
+                            rewardTeam(MV_R_TOWER_BUILDING, i, delta);
+                            const int hgt = vy - L->bz_min[1] + 1;
+                            e.highest_tower = e.highest_tower > hgt ? e.highest_tower : hgt;
+                        }
                     }
                 } else {
                     const V3 pickup = translationOf(pickAbs);
@@ -889,51 +902,82 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                             a.carrying = here;
                             objGrid[g] = MV_NO_OBJECT;
                             S.objDirty[S.nDirty++] = here;
-                            // pickedObject (scenario_tower_building.cpp:216-225)
-                            if (inBuildingZone(*L, vx, vz)) mvBzErase(e, vx, vy, vz);
-                            if (!a.picked_up) { rewardAgent(MV_R_TOWER_PICKED_UP, i, 1); a.picked_up = 1; }
+                            if (L->scenario == MV_SCENARIO_TOWER) {  // pickedObject (scenario_tower_building.cpp:216-225)
+                                if (inBuildingZone(*L, vx, vz)) mvBzErase(e, vx, vy, vz);
+                                if (!a.picked_up) { rewardAgent(MV_R_TOWER_PICKED_UP, i, 1); a.picked_up = 1; }
+                            }
                             break;
                         } else vy += 1;
                         ++pickupHeight;
                     }
                 }
             }
-            // FallDetectionComponent::step
-            for (int i = 0; i < A; ++i) {
+            const uint32_t *planes = P.solid + (size_t(env) * 2 + slot) * 3 * P.gridWords;
+            auto planeBit = [&](int plane, int g) { return g >= 0 && ((planes[size_t(plane) * P.gridWords + (g >> 5)] >> (g & 31)) & 1u); };
+            // FallDetectionComponent::resetAgent (component_fall_detection.hpp:44-56) -> KinematicCharacterController::warp
+            auto resetAgent = [&](int i) {
                 MvAgent &a = S.agents[i];
-                if (a.object_t[13] < -20) {
-                    V3 p = v3(L->init_pos[i][0], L->init_pos[i][1], L->init_pos[i][2]);
-                    const uint32_t *sol = P.solid + (size_t(env) * 2 + slot) * P.gridWords;
-                    while (p.y < 1000) {
-                        int x, y, z;
-                        toVoxel(p, x, y, z);
-                        const int g = gridIndex(*L, x, y, z);
-                        const bool solid = g >= 0 && ((sol[g >> 5] >> (g & 31)) & 1u);
-                        if (!solid) break;
-                        p.y += 1;
-                    }
-                    const float halfVoxel = 1.0f / 2;
-                    a.pos[0] = p.x + halfVoxel; a.pos[1] = p.y + halfVoxel; a.pos[2] = p.z + halfVoxel;
-                    for (int q = 0; q < 9; ++q) a.basis[q] = (q % 4 == 0) ? 1.0f : 0.0f;  // warp(): rotation reset to identity
-                    a.hvel[0] = a.hvel[1] = a.hvel[2] = 0.0f;
-                    a.vvel = 0;
+                V3 p = v3(L->init_pos[i][0], L->init_pos[i][1], L->init_pos[i][2]);
+                while (p.y < 1000) {
+                    int x, y, z;
+                    toVoxel(p, x, y, z);
+                    if (!planeBit(0, gridIndex(*L, x, y, z))) break;
+                    p.y += 1;
                 }
-            }
-            // shaping: carrying an object inside the building zone
-            for (int i = 0; i < A; ++i) {
-                MvAgent &a = S.agents[i];
-                if (a.carrying >= 0) {
+                const float halfVoxel = 1.0f / 2;
+                a.pos[0] = p.x + halfVoxel; a.pos[1] = p.y + halfVoxel; a.pos[2] = p.z + halfVoxel;
+                for (int q = 0; q < 9; ++q) a.basis[q] = (q % 4 == 0) ? 1.0f : 0.0f;  // warp(): rotation reset to identity
+                a.hvel[0] = a.hvel[1] = a.hvel[2] = 0.0f;
+                a.vvel = 0;
+            };
+            for (int i = 0; i < A; ++i)  // FallDetectionComponent::step
+                if (S.agents[i].object_t[13] < -20) resetAgent(i);
+            if (L->scenario == MV_SCENARIO_TOWER) {
+                // shaping: carrying an object inside the building zone (scenario_tower_building.cpp:184-198)
+                for (int i = 0; i < A; ++i) {
+                    MvAgent &a = S.agents[i];
+                    if (a.carrying >= 0) {
+                        int x, y, z;
+                        toVoxel(v3(a.object_t[12], a.object_t[13], a.object_t[14]), x, y, z);
+                        if (inBuildingZone(*L, x, z) && !a.visited_bz) {
+                            rewardTeam(MV_R_TOWER_VISITED_BZ, i, 1);
+                            a.visited_bz = 1;
+                        }
+                    }
+                }
+            } else if (L->scenario == MV_SCENARIO_OBSTACLES) {
+                // ObstaclesScenario::step (scenario_obstacles.cpp:202-238)
+                int numAgentsAtExit = 0;
+                for (int i = 0; i < A; ++i) {
+                    MvAgent &a = S.agents[i];
                     int x, y, z;
                     toVoxel(v3(a.object_t[12], a.object_t[13], a.object_t[14]), x, y, z);
-                    if (inBuildingZone(*L, x, z) && !a.visited_bz) {
-                        rewardTeam(MV_R_TOWER_VISITED_BZ, i, 1);
-                        a.visited_bz = 1;
-                    }
+                    const int g = gridIndex(*L, x, y, z);
+                    if (planeBit(1, g)) {
+                        ++numAgentsAtExit;
+                        if (!((e.reached_exit >> i) & 1u)) {
+                            e.reached_exit |= 1u << i;
+                            rewardTeam(MV_R_OBST_AGENT_AT_EXIT, i, 1);
+                            if (a.carrying >= 0) rewardTeam(MV_R_OBST_CARRIED_TO_EXIT, i, 1);
+                        }
+                    } else if (planeBit(2, g))
+                        resetAgent(i);  // agentTouchedLava
+                    for (int r = 0; r < L->n_reward; ++r)
+                        if (((e.reward_alive >> r) & 1u) && L->reward_voxel[r][0] == x && L->reward_voxel[r][1] == y && L->reward_voxel[r][2] == z) {
+                            e.reward_alive &= ~(1u << r);
+                            rewardTeam(MV_R_OBST_EXTRA, i, 1);
+                        }
+                }
+                if (numAgentsAtExit == A && !e.solved) {
+                    e.solved = 1;
+                    const float t = L->episode_len - 0.3f;  // doneWithTimer() (scenario.hpp:114-117)
+                    e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
+                    for (int i = 0; i < A; ++i) rewardAgent(MV_R_OBST_ALL_AT_EXIT, i, 1);  // rewardAll
                 }
             }
             // env.cpp:133-152
             e.episode_sec += dt;
-            const float len = L->episode_len_base + 4.0f * float(L->n_movable);
+            const float len = L->episode_len;
             {
                 const float frac0 = (len - e.episode_sec) / len;
                 const float frac = frac0 > 0.0f ? frac0 : 0.0f;
@@ -958,7 +1002,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     // ---- outputs of the finished step; VectorEnv::step captures trueObjective BEFORE reset and the rewards AFTER it (zeroed)
     if (!P.forceReset) {
         for (int i = lane; i < A; i += 32) {
-            if (doneFlag) P.trueObjectives[size_t(env) * A + i] = float(S.env.highest_tower);
+            if (doneFlag) P.trueObjectives[size_t(env) * A + i] = L->scenario == MV_SCENARIO_OBSTACLES ? float(S.env.solved) : float(S.env.highest_tower);
             P.rewards[size_t(env) * A + i] = doneFlag ? 0.0f : S.lastReward[i];
         }
         if (lane == 0) P.dones[env] = doneFlag ? 1 : 0;

@@ -145,17 +145,23 @@ int orc_get_level(void *p, int envIdx, int32_t *out, int cap) {
     std::vector<int32_t> o;
     o.push_back(int(env.staticBoxes.size()));
     o.push_back(int(env.terrainSlabs.size()));
-    o.push_back(int(env.platform->objectSpawnCoords.size()));
-    const BoundingBox &bz = env.buildingZone;
+    o.push_back(int(env.objectSpawnPositions.size()));
+    const BoundingBox bz = env.scenario == Env::S_TOWER ? env.buildingZone : BoundingBox{};
     for (int x : {bz.min.x, bz.min.y, bz.min.z, bz.max.x, bz.max.y, bz.max.z}) o.push_back(x);
     for (auto &sb : env.staticBoxes)
         for (int x : {sb.bb.min.x, sb.bb.min.y, sb.bb.min.z, sb.bb.max.x, sb.bb.max.y, sb.bb.max.z, int(sb.type), int(sb.color)}) o.push_back(x);
     for (auto &ts : env.terrainSlabs)
         for (int x : {ts.terrain, ts.bb.min.x, ts.bb.min.y, ts.bb.min.z, ts.bb.max.x, ts.bb.max.y, ts.bb.max.z}) o.push_back(x);
-    for (auto &c : env.platform->objectSpawnCoords)
+    for (auto &c : env.objectSpawnPositions)
         for (int x : {c.x, c.y, c.z}) o.push_back(x);
-    for (auto &c : env.platform->agentSpawnCoords)
+    for (auto &c : env.agentSpawnPositions)
         for (int x : {int(c.x), int(c.y), int(c.z)}) o.push_back(x);
+    if (env.scenario == Env::S_OBSTACLES) {  // scenario extras: numPlatforms, reward-object voxels
+        o.push_back(env.numPlatforms);
+        o.push_back(int(env.rewardSpawnPositions.size()));
+        for (auto &c : env.rewardSpawnPositions)
+            for (int x : {c.x, c.y, c.z}) o.push_back(x);
+    }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
     return int(o.size());
@@ -186,6 +192,15 @@ int orc_get_state(void *p, int envIdx, float *out, int cap) {
         for (float x : {t.x, t.y, t.z, ob.local.c[0][0], ob.local.c[1][1], ob.local.c[2][2], float(ob.parentAgent),
                         env.colliders[size_t(ob.collider)].enabled ? 1.f : 0.f, 0.f})
             o.push_back(x);
+    }
+    if (env.scenario == Env::S_OBSTACLES) {
+        uint32_t reached = 0, alive = 0;
+        for (int i = 0; i < env.numAgents; ++i) reached |= env.agentReachedExit[size_t(i)] ? (1u << i) : 0u;
+        for (size_t r = 0; r < env.rewardSpawnPositions.size(); ++r) {
+            const Voxel *v = env.vg.grid.get(env.rewardSpawnPositions[r]);
+            if (v && v->rewardObject == int(r)) alive |= 1u << r;
+        }
+        o.push_back(float(env.solved)); o.push_back(float(reached)); o.push_back(float(alive));
     }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(float));

@@ -100,17 +100,40 @@ using RewardShaping = std::map<std::string, float>;
 
 class Env {
 public:
-    enum Scenario { S_TOWER = 0 };
+    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1 };
+    enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
 
     Env(const std::string &scenarioName, int numAgents, const FloatParams &custom) : numAgents(numAgents) {
         std::string n;
         for (char ch : scenarioName) n.push_back(char(tolower(ch)));
-        if (n == "towerbuilding") scenario = S_TOWER;
-        else throw std::runtime_error("oracle: unknown scenario " + n);
         // Scenario::init (scenario.hpp:98-107) + initializeDefaultParameters (:225-231)
         floatParams["episodeLengthSec"] = 60.0f;
         floatParams["verticalLookLimitRad"] = 0.2f;
         floatParams["useUIRewardIndicators"] = 0.0f;
+        if (n == "towerbuilding") scenario = S_TOWER;
+        else if (n.rfind("obstacles", 0) == 0 || n == "test") {
+            // ObstaclesScenario::initializeDefaultParameters + the registered variants (scenario_obstacles.hpp:48-270, init.hpp:33-56)
+            scenario = S_OBSTACLES;
+            platformTypes = {PT_WALL, PT_LAVA, PT_STEP, PT_GAP};
+            auto &fp = floatParams;
+            fp["obstaclesMinNumPlatforms"] = 1; fp["obstaclesMaxNumPlatforms"] = 2; fp["obstaclesMinGap"] = 1; fp["obstaclesMaxGap"] = 2;
+            fp["obstaclesMinLava"] = 1; fp["obstaclesMaxLava"] = 4; fp["obstaclesMinHeight"] = 1; fp["obstaclesMaxHeight"] = 3;
+            fp["obstaclesNumAllowedMaxDifficulty"] = 1;
+            if (n == "obstacleseasy" || n == "obstacles") {
+            } else if (n == "obstaclesmedium") {
+                fp["obstaclesMinNumPlatforms"] = 2; fp["obstaclesMaxNumPlatforms"] = 4; fp["obstaclesMinLava"] = 2; fp["obstaclesMaxLava"] = 5;
+            } else if (n == "obstacleshard") {
+                fp["obstaclesMinNumPlatforms"] = 2; fp["obstaclesMaxNumPlatforms"] = 7; fp["obstaclesMinGap"] = 2; fp["obstaclesMaxGap"] = 3;
+                fp["obstaclesMinLava"] = 3; fp["obstaclesMaxLava"] = 10; fp["obstaclesMinHeight"] = 2; fp["obstaclesMaxHeight"] = 4;
+            } else if (n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava") {
+                fp["obstaclesMinNumPlatforms"] = 1; fp["obstaclesMaxNumPlatforms"] = 4; fp["obstaclesMinGap"] = 1; fp["obstaclesMaxGap"] = 3;
+                fp["obstaclesMinLava"] = 2; fp["obstaclesMaxLava"] = 10; fp["obstaclesMinHeight"] = 1; fp["obstaclesMaxHeight"] = 3;
+                platformTypes = {n == "obstacleswalls" ? PT_WALL : (n == "obstaclessteps" ? PT_STEP : PT_LAVA)};
+                onePlatformType = true;
+            } else if (n == "test") {
+                fp["obstaclesMinNumPlatforms"] = 0; fp["obstaclesMaxNumPlatforms"] = 0; fp["episodeLengthSec"] = 6.0f;
+            } else throw std::runtime_error("oracle: unknown scenario " + n);
+        } else throw std::runtime_error("oracle: unknown scenario " + n);
         rewardShaping.assign(size_t(numAgents), RewardShaping{{"teamSpirit", 0.0f}});
         for (auto &rs : rewardShaping)
             for (auto &[k, v] : defaultRewardShaping()) rs[k] = v;
@@ -121,7 +144,11 @@ public:
         agentState.assign(size_t(numAgents), TowerAgentState{});
     }
 
-    RewardShaping defaultRewardShaping() const {  // scenario_tower_building.hpp:44-52
+    RewardShaping defaultRewardShaping() const {
+        if (scenario == S_OBSTACLES)  // scenario_obstacles.hpp:37-45,201-206
+            return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f},
+                    {"obstaclesAgentCarriedObjectToExit", onePlatformType ? 1.0f : 0.0f}};
+        // scenario_tower_building.hpp:44-52
         return {{"teamSpirit", 0.1f}, {"towerPickedUpObject", 0.1f}, {"towerVisitedBuildingZoneWithObject", 0.1f}, {"towerBuildingReward", 1.0f}};
     }
 
@@ -133,15 +160,168 @@ public:
         std::fill(currAction.begin(), currAction.end(), 0);
         std::fill(lastReward.begin(), lastReward.end(), 0.0f);
         std::fill(totalReward.begin(), totalReward.end(), 0.0f);
-        agents.clear(); colliders.clear(); objects.clear(); staticBoxes.clear(); terrainSlabs.clear();
+        agents.clear(); colliders.clear(); objects.clear(); staticBoxes.clear(); terrainSlabs.clear(); rewardObjects.clear();
 
         auto sd = randRange(0, 1 << 30, rng);
         rng.seed((unsigned long)sd);
 
-        towerReset();
+        if (scenario == S_TOWER) towerReset(); else obstaclesReset();
         spawnAgents();
-        towerAddEpisodeDrawables();
+        if (scenario == S_TOWER) towerAddEpisodeDrawables(); else obstaclesAddEpisodeDrawables();
         addAgentsAndUI();
+    }
+
+    // ---------------------------------------------------------------- Obstacles (scenario_obstacles.cpp:51-278)
+    std::unique_ptr<Platform> makePlatform(Node *parent, int walls, int width) {  // :17-37
+        const auto platformType = randomSample(platformTypes, rng);
+        switch (platformType) {
+            case PT_STEP: return std::make_unique<StepPlatform>(parent, rng, walls, floatParams, width);
+            case PT_GAP: return std::make_unique<GapPlatform>(parent, rng, walls, floatParams, width);
+            case PT_LAVA: return std::make_unique<LavaPlatform>(parent, rng, walls, floatParams, width);
+            case PT_WALL: return std::make_unique<WallPlatform>(parent, rng, walls, floatParams, width);
+            default: return std::make_unique<EmptyPlatform>(parent, rng, walls, floatParams, width);
+        }
+    }
+
+    void obstaclesReset() {
+        vg.reset();
+        platforms.clear();
+        levelRoot = std::make_unique<Node>();
+        carryingObject.assign(size_t(numAgents), -1);
+        agentSpawnPositions.clear(); objectSpawnPositions.clear(); rewardSpawnPositions.clear();
+        agentReachedExit.assign(size_t(numAgents), false);
+        solved = false;
+
+        const bool drawWalls = randRange(0, 2, rng);
+        Platform *startPlatform = nullptr;
+        for (int attempt = 0; attempt < 20; ++attempt) {
+            platforms.clear();
+            numPlatforms = randRange(int(lroundf(floatParams["obstaclesMinNumPlatforms"])), int(lroundf(floatParams["obstaclesMaxNumPlatforms"])) + 1, rng);
+            static const std::vector<int> orientations = {0, 1, 2};  // STRAIGHT, TURN_LEFT, TURN_RIGHT
+            auto startPlatformPtr = std::make_unique<StartPlatform>(levelRoot.get(), rng, floatParams);
+            startPlatformPtr->init(), startPlatformPtr->generate();
+            int requiredWidth = startPlatformPtr->width;
+            startPlatform = startPlatformPtr.get();
+            Platform *previousPlatform = startPlatform;
+            platforms.emplace_back(std::move(startPlatformPtr));
+            int numMaxDifficultyObstacles = 0;
+            const int numAllowedMaxDifficultyObstacles = int(floatParams.at("obstaclesNumAllowedMaxDifficulty"));
+            for (int i = 0; i < numPlatforms; ++i) {
+                auto orientation = randomSample(orientations, rng);
+                requiredWidth = orientation == 0 ? requiredWidth : -1;
+                std::unique_ptr<Platform> newPlatform;
+                while (!newPlatform || (newPlatform->isMaxDifficulty() && numMaxDifficultyObstacles >= numAllowedMaxDifficultyObstacles)) {
+                    newPlatform = makePlatform(previousPlatform->nextPlatformAnchor, WALLS_WEST | WALLS_EAST, requiredWidth);
+                    newPlatform->init();
+                }
+                if (newPlatform->isMaxDifficulty()) ++numMaxDifficultyObstacles;
+                platforms.emplace_back(std::move(newPlatform));
+                auto platform = platforms.back().get();
+                platform->generate();
+                if (orientation == 1) platform->rotateCCW(previousPlatform->width);
+                else if (orientation == 2) platform->rotateCW(previousPlatform->width);
+                if (orientation != 0) {
+                    int walls = WALLS_NORTH;
+                    walls |= orientation == 1 ? WALLS_WEST : WALLS_EAST;
+                    const int w = previousPlatform->width, l = platform->width - 1;
+                    platforms.emplace_back(std::make_unique<TransitionPlatform>(previousPlatform->nextPlatformAnchor, rng, walls, floatParams, l, w));
+                    auto transitionPlatform = platforms.back().get();
+                    transitionPlatform->init();
+                    transitionPlatform->generate();
+                }
+                previousPlatform = platform;
+                requiredWidth = platform->width;
+            }
+            auto exitPlatformPtr = std::make_unique<ExitPlatform>(previousPlatform->nextPlatformAnchor, rng, floatParams, requiredWidth);
+            exitPlatformPtr->init(), exitPlatformPtr->generate();
+            platforms.emplace_back(std::move(exitPlatformPtr));
+            bool selfCollision = false;
+            for (int j = 0; j < int(platforms.size()) && !selfCollision; ++j)
+                for (int k = 0; k < j - 2; ++k)
+                    if (platforms[j]->collidesWith(*platforms[k])) { selfCollision = true; break; }
+            if (!selfCollision) break;
+        }
+        auto layoutColor = randomLayoutColor(rng);
+        auto wallColor = randomLayoutColor(rng);
+        for (auto &p : platforms) vg.addPlatform(*p, layoutColor, wallColor, drawWalls);
+
+        agentSpawnPositions = startPlatform->agentSpawnPoints(numAgents);
+        agentInitialPositions = agentSpawnPositions;
+
+        std::vector<int> numBoxes(platforms.size());
+        for (int i = 1; i < int(platforms.size()); ++i) {
+            const auto n = platforms[i]->requiresMovableBoxesToTraverse();
+            for (int box = 0; box < n; ++box) {
+                const auto platformIdx = randRange(std::max(0, i - 2), i, rng);
+                ++numBoxes[platformIdx];
+            }
+        }
+        for (int i = 0; i < int(platforms.size()); ++i) {
+            float randomBoxesFraction = frand(rng) * 0.5f;
+            auto randomBoxes = int(lroundf(randomBoxesFraction * numBoxes[i])) + randRange(0, 2, rng);
+            const auto coords = platforms[i]->generateObjectPositions(numBoxes[i] + randomBoxes);
+            objectSpawnPositions.insert(objectSpawnPositions.end(), coords.cbegin(), coords.cend());
+        }
+        for (int i = 1; i < int(platforms.size()) - 1; ++i) {
+            auto numRewardObjects = randRange(0, 2, rng);
+            const auto coords = platforms[i]->generateObjectPositions(numRewardObjects);
+            rewardSpawnPositions.insert(rewardSpawnPositions.end(), coords.cbegin(), coords.cend());
+        }
+    }
+
+    void obstaclesAddEpisodeDrawables() {  // scenario_obstacles.cpp:241-260
+        addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
+        for (auto &platform : platforms)
+            for (auto &[terrainType, boxes] : platform->terrainBoxes)
+                for (auto &bb : boxes) terrainSlabs.push_back({terrainType, bb.boundingBox()});
+        addObjects(objectSpawnPositions);
+        for (const auto &pos : rewardSpawnPositions) {
+            // addDiamond (layout_utils.cpp:114-126): two cones, the lower one rotated 180 deg about X and shifted -1 in y
+            RewardObject ro;
+            const Vec3 translation = Vec3{float(pos.x), float(pos.y), float(pos.z)} + Vec3{0.5f, 0.7f, 0.5f};
+            const Vec3 scale = Vec3{0.17f, 0.45f, 0.17f} * 0.8f;
+            ro.bottomLocal = mul(mat4Translation({0.0f, -1.0f, 0.0f}), mul(mat4Identity(), mat4RotationX(180.0f * 3.14159265358979323846f / 180.0f)));
+            ro.root = mul(mat4Translation(translation), mul(mat4Scaling(scale), mat4Identity()));
+            ro.color = paletteIndex(GREEN);
+            if (!vg.grid.hasVoxel(pos)) vg.grid.set(pos, Voxel{});
+            vg.grid.get(pos)->rewardObject = int(rewardObjects.size());
+            rewardObjects.push_back(ro);
+        }
+    }
+
+    void obstaclesStep() {  // scenario_obstacles.cpp:197-239
+        for (int i = 0; i < numAgents; ++i)
+            if (currAction[i] & A_Interact) onInteractAction(i);
+        fallDetectionStep();
+        int numAgentsAtExit = 0;
+        for (int i = 0; i < numAgents; ++i) {
+            const Vec3 t = translationOf(agents[i].objectT);
+            const auto voxel = vg.grid.getCoords(t);
+            if (vg.grid.hasVoxel(voxel)) {
+                const auto terrainType = vg.grid.get(voxel)->terrain;
+                if (terrainType & TERRAIN_EXIT) {
+                    ++numAgentsAtExit;
+                    if (!agentReachedExit[i]) {
+                        agentReachedExit[i] = true;
+                        rewardTeam("obstaclesAgentAtExit", i, 1);
+                        if (carryingObject[i] >= 0) rewardTeam("obstaclesAgentCarriedObjectToExit", i, 1);
+                    }
+                } else if (terrainType & TERRAIN_LAVA)
+                    resetAgent(i);  // agentTouchedLava -> fallDetection.resetAgent; agentFell() gives no penalty
+                auto voxelData = vg.grid.get(voxel);
+                if (voxelData->rewardObject >= 0) {
+                    RewardObject &ro = rewardObjects[voxelData->rewardObject];
+                    ro.root = mul(mat4Translation({1000, 1000, 1000}), ro.root);
+                    voxelData->rewardObject = -1;
+                    rewardTeam("obstaclesExtraReward", i, 1);
+                }
+            }
+        }
+        if (numAgentsAtExit == numAgents && !solved) {
+            solved = true;
+            doneWithTimer();
+            for (int i = 0; i < numAgents; ++i) rewardAgent("obstaclesAllAgentsAtExit", i, 1);  // rewardAll
+        }
     }
 
     // TowerBuildingPlatform (scenario_tower_building.cpp:8-115)
@@ -215,12 +395,14 @@ public:
         currBuildingZoneReward = 0.0f;
         objectsInBuildingZone.clear();
         highestTower = 0;
-        agentInitialPositions = platform->agentSpawnCoords;
+        agentSpawnPositions = platform->agentSpawnCoords;
+        objectSpawnPositions = platform->objectSpawnCoords;
+        agentInitialPositions = agentSpawnPositions;
     }
 
     void spawnAgents() {  // scenario_default.hpp:80-97
         const float lookLimit = floatParams["verticalLookLimitRad"];
-        const auto agentPositions = platform->agentSpawnCoords;
+        const auto agentPositions = agentSpawnPositions;
         agents.resize(size_t(numAgents));
         for (int i = 0; i < numAgents; ++i) {
             auto randomRotation = frand(rng) * 3.14159265358979323846f * 2;
@@ -234,7 +416,7 @@ public:
         addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
         for (auto &[terrainType, boxes] : platform->terrainBoxes)
             for (auto &bb : boxes) terrainSlabs.push_back({terrainType, bb.boundingBox()});
-        const auto objectPositions = platform->objectSpawnCoords;
+        const auto objectPositions = objectSpawnPositions;
         for (const auto &pos : objectPositions)
             if (isInBuildingZone(pos)) objectsInBuildingZone.insert(pos);
         currBuildingZoneReward = calculateTowerReward();
@@ -339,7 +521,7 @@ public:
         }
         for (auto &a : agents) a.updateTransform();
 
-        towerStep();
+        if (scenario == S_TOWER) towerStep(); else obstaclesStep();
 
         currEpisodeSec += lastFrameDurationSec;
         updateUI();
@@ -349,9 +531,13 @@ public:
         ++numFrames;
     }
 
-    float episodeLengthSec() const { return floatParams.at("episodeLengthSec") + 4.0f * float(platform->objectSpawnCoords.size()); }  // scenario_tower_building.cpp:263-266
+    float episodeLengthSec() const {
+        if (scenario == S_OBSTACLES)  // scenario_obstacles.cpp:262-266
+            return std::max(floatParams.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objectSpawnPositions.size()) * 1);
+        return floatParams.at("episodeLengthSec") + 4.0f * float(objectSpawnPositions.size());  // scenario_tower_building.cpp:263-266
+    }
     float remainingTimeFraction() const { const float len = episodeLengthSec(); return std::max(0.0f, (len - currEpisodeSec) / len); }  // env.hpp:224-228
-    float trueObjective(int) const { return float(highestTower); }
+    float trueObjective(int) const { return scenario == S_OBSTACLES ? float(solved) : float(highestTower); }
     void doneWithTimer(float remaining = 0.3f) { currEpisodeSec = std::max(currEpisodeSec, episodeLengthSec() - remaining); }
 
     void updateUI() {  // scenario_default.hpp:164-186 ; UIElement::rescale :33-37
@@ -434,7 +620,8 @@ public:
                 if (voxel == c) { collidesWithAgent = true; break; }
             }
             const bool empty = !voxelPtr || (voxelPtr->empty() && voxelPtr->physicsObject < 0);
-            if (empty && !collidesWithAgent && isInBuildingZone(voxel)) {  // canPlaceObject: scenario_tower_building.cpp:201-204
+            // canPlaceObject: TowerBuilding only inside the building zone (scenario_tower_building.cpp:201-204), else the default (true)
+            if (empty && !collidesWithAgent && (scenario != S_TOWER || isInBuildingZone(voxel))) {
                 while (true) {
                     VoxelCoords below{voxel.x, voxel.y - 1, voxel.z};
                     if (below.y < -30) break;
@@ -453,7 +640,7 @@ public:
                 syncPose(obj);
                 colliders[o.collider].enabled = !colliders[o.collider].enabled;  // toggleCollision
                 carryingObject[agentIdx] = -1;
-                placedObject(agentIdx, voxel);
+                if (scenario == S_TOWER) placedObject(agentIdx, voxel);
             }
         } else {
             const Vec3 pickup = translationOf(agent.pickupAbs());
@@ -474,7 +661,7 @@ public:
                     o.parentAgent = agentIdx;
                     carryingObject[agentIdx] = obj;
                     voxelPtr->physicsObject = -1;
-                    pickedObject(agentIdx, voxel);
+                    if (scenario == S_TOWER) pickedObject(agentIdx, voxel);
                     break;
                 } else {
                     voxel = voxelAbove;
@@ -485,17 +672,17 @@ public:
         }
     }
 
-    void fallDetectionStep() {  // component_fall_detection.hpp:33-56
-        for (int i = 0; i < numAgents; ++i) {
-            if (translationOf(agents[i].objectT).y < -20) {
-                Vec3 p = agentInitialPositions[i];
-                auto v = vg.grid.getWithVector(p);
-                while (v && !v->empty() && p.y < 1000) { p.y += 1; v = vg.grid.getWithVector(p); }
-                const float halfVoxel = vg.grid.getVoxelSize() / 2;
-                agents[i].kcc.warp({p.x + halfVoxel, p.y + halfVoxel, p.z + halfVoxel});
-                colliders[agentColliderBase + i].c = agents[i].kcc.pos;
-            }
-        }
+    void resetAgent(int i) {  // FallDetectionComponent::resetAgent, component_fall_detection.hpp:44-56
+        Vec3 p = agentInitialPositions[i];
+        auto v = vg.grid.getWithVector(p);
+        while (v && !v->empty() && p.y < 1000) { p.y += 1; v = vg.grid.getWithVector(p); }
+        const float halfVoxel = vg.grid.getVoxelSize() / 2;
+        agents[i].kcc.warp({p.x + halfVoxel, p.y + halfVoxel, p.z + halfVoxel});
+        colliders[agentColliderBase + i].c = agents[i].kcc.pos;
+    }
+    void fallDetectionStep() {  // component_fall_detection.hpp:33-42
+        for (int i = 0; i < numAgents; ++i)
+            if (translationOf(agents[i].objectT).y < -20) resetAgent(i);
     }
 
     // ---------------------------------------------------------------- render interface
@@ -530,6 +717,10 @@ public:
         for (auto &a : agents) out.push_back({MESH_BOX, paletteIndex(AGENT_EYES), mul(a.objectT, mul(a.cameraLocal, a.eyesLocal))});
         for (auto &a : agents) out.push_back({MESH_BOX, paletteIndex(BLUE), mul(a.objectT, mul(a.cameraLocal, mul(a.uiLocal, mul(a.barAnchorLocal, a.barLocal))))});
         for (auto &a : agents) out.push_back({MESH_CAPSULE, a.color, mul(a.objectT, a.bodyLocal)});
+        for (auto &ro : rewardObjects) {  // DrawableType::Cone, insertion order: root then its bottom half (layout_utils.cpp:122-123)
+            out.push_back({MESH_CONE, ro.color, ro.root});
+            out.push_back({MESH_CONE, ro.color, mul(ro.root, ro.bottomLocal)});
+        }
         return out;
     }
     Mat4 viewMatrix(int agentIdx) const { return inverted(agents[agentIdx].cameraAbs()); }  // Camera::cameraMatrix
@@ -560,6 +751,19 @@ public:
     std::vector<Vec3> agentInitialPositions;
     std::unique_ptr<Node> levelRoot;
     std::unique_ptr<TowerPlatform> platform;
+
+    // generic level products
+    std::vector<Vec3> agentSpawnPositions;
+    std::vector<VoxelCoords> objectSpawnPositions, rewardSpawnPositions;
+    // Obstacles
+    std::vector<int> platformTypes;
+    bool onePlatformType = false;
+    std::vector<std::unique_ptr<Platform>> platforms;
+    std::vector<bool> agentReachedExit;
+    bool solved = false;
+    int numPlatforms = 0;
+    struct RewardObject { Mat4 root, bottomLocal; int color; };
+    std::vector<RewardObject> rewardObjects;
 
     struct TowerAgentState { bool pickedUpObject = false, visitedBuildingZoneWithObject = false; };
     std::vector<TowerAgentState> agentState;

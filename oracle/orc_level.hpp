@@ -177,9 +177,10 @@ public:
         a.max->translateLocal({float(bb.max.x), float(bb.max.y), float(bb.max.z)});
         return a;
     }
-    virtual void rotateCCW(int) { root->rotateYLocal(90.0f * (3.14159265358979323846f / 180.0f)); root->translateLocal({-1, 0, -1}); }
+    // degrees(90.0) -> Rad: T(value)*pi/T(180)  (Magnum Math/Angle.h)
+    virtual void rotateCCW(int) { root->rotateYLocal(90.0f * 3.14159265358979323846f / 180.0f); root->translateLocal({-1, 0, -1}); }
     virtual void rotateCW(int previousPlatformWidth) {
-        root->rotateYLocal(-90.0f * (3.14159265358979323846f / 180.0f));
+        root->rotateYLocal(-90.0f * 3.14159265358979323846f / 180.0f);
         root->translateLocal({float(previousPlatformWidth) - 1, 0, -float(width) + 1});
     }
     virtual void addFloor() {
@@ -274,6 +275,126 @@ public:
         height = 5;
     }
     void generate() override { addFloor(); addWalls(); }
+};
+
+template <typename T> T triangularNumber(T n) { return n * (n + 1) / 2; }  // util/math_utils.hpp
+
+class WallPlatform : public EmptyPlatform {  // platforms.hpp:332-373
+public:
+    WallPlatform(Node *parent, Rng &rng, int walls, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, walls, params, w) {}
+    void init() override {
+        EmptyPlatform::init();
+        wallHeight = randRange(param("obstaclesMinHeight"), param("obstaclesMaxHeight") + 1, rng);
+        height = randRange(wallHeight + 4, wallHeight + 6, rng);
+    }
+    void generate() override {
+        EmptyPlatform::generate();
+        const auto wallX = randRange(1, length, rng);
+        const auto wallThickness = randRange(1, length - wallX + 1, rng);
+        layoutBoxes.emplace_back(makeAABB({wallX, 1, 1, wallX + wallThickness, 1 + wallHeight, width - 1}));
+        for (int x = wallX; x < wallX + wallThickness; ++x)
+            for (int z = 1; z < width; ++z) occupancy[{x, z}] = wallHeight;
+    }
+    int requiresMovableBoxesToTraverse() override { return triangularNumber(wallHeight - 1); }
+    bool isMaxDifficulty() const override { return wallHeight >= param("obstaclesMaxHeight"); }
+    int wallHeight{};
+};
+
+class LavaPlatform : public EmptyPlatform {  // platforms.hpp:375-407
+public:
+    LavaPlatform(Node *parent, Rng &rng, int walls, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, walls, params, w) {}
+    void init() override {
+        EmptyPlatform::init();
+        length = randRange(6, 12, rng);
+        auto minLava = std::min(param("obstaclesMinLava"), length - 2);
+        auto maxLava = std::min(param("obstaclesMaxLava") + 1, length - 1);
+        lavaLength = randRange(minLava, maxLava, rng);
+    }
+    void generate() override {
+        EmptyPlatform::generate();
+        const auto lavaX = randRange(1, length - lavaLength, rng);
+        terrainBoxes[TERRAIN_LAVA].emplace_back(makeAABB({lavaX, 1, 1, lavaX + lavaLength, 2, width - 1}));
+    }
+    int requiresMovableBoxesToTraverse() override { return std::max(1, lavaLength - 1); }
+    bool isMaxDifficulty() const override { return lavaLength >= param("obstaclesMaxLava"); }
+    int lavaLength{};
+};
+
+class StepPlatform : public EmptyPlatform {  // platforms.hpp:409-456
+public:
+    StepPlatform(Node *parent, Rng &rng, int walls, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, walls, params, w) {}
+    void init() override {
+        EmptyPlatform::init();
+        stepHeight = randRange(param("obstaclesMinHeight"), param("obstaclesMaxHeight") + 1, rng);
+        height = randRange(stepHeight + 2, stepHeight + 5, rng);
+    }
+    void generate() override {
+        const auto stepX = randRange(1, length, rng);
+        layoutBoxes.emplace_back(makeAABB({0, 0, 0, stepX + 1, 1, width}));
+        layoutBoxes.emplace_back(makeAABB({stepX, stepHeight, 0, length, stepHeight + 1, width}));
+        layoutBoxes.emplace_back(makeAABB({stepX, 0, 0, stepX + 1, stepHeight + 1, width}));
+        nextPlatformAnchor = newNode(root);
+        nextPlatformAnchor->translateLocal({float(length), float(stepHeight), 0});
+        addWalls();
+        for (int x = stepX + 1; x < length; ++x)
+            for (int z = 1; z < width; ++z) occupancy[{x, z}] = stepHeight;
+    }
+    int requiresMovableBoxesToTraverse() override { return triangularNumber(stepHeight - 1); }
+    bool isMaxDifficulty() const override { return stepHeight >= param("obstaclesMaxHeight"); }
+    int stepHeight{};
+};
+
+class GapPlatform : public EmptyPlatform {  // platforms.hpp:459-514
+public:
+    GapPlatform(Node *parent, Rng &rng, int walls, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, walls, params, w) {}
+    void init() override {
+        EmptyPlatform::init();
+        gap = randRange(param("obstaclesMinGap"), std::min(param("obstaclesMaxGap") + 1, length - 1), rng);
+        gapX = randRange(1, length - gap, rng);
+    }
+    void generate() override {
+        layoutBoxes.emplace_back(makeAABB({0, 0, 0, gapX, 1, width}));
+        layoutBoxes.emplace_back(makeAABB({gapX + gap, 0, 0, length, 1, width}));
+        nextPlatformAnchor = newNode(root);
+        nextPlatformAnchor->translateLocal({float(length), 0, 0});
+        addWalls();
+    }
+    int requiresMovableBoxesToTraverse() override { return triangularNumber(std::max(0, gap - 2)); }
+    std::vector<VoxelCoords> generateObjectPositions(int n) override {
+        std::vector<VoxelCoords> boxes, candidates;
+        for (int x = 0; x < length; ++x)
+            for (int z = 1; z < width - 1; ++z) {
+                if (x >= gapX && x < gapX + gap) continue;
+                candidates.emplace_back(x, 1, z);
+            }
+        for (int i = 0; i < n; ++i) {
+            const auto v = randomSample(candidates, rng);
+            const int y = ++occupancy[{v.x, v.z}];
+            boxes.emplace_back(v.x, y, v.z);
+        }
+        return adjustTransformation(boxes);
+    }
+    int gap{}, gapX{};
+};
+
+class StartPlatform : public EmptyPlatform {  // platforms.hpp:516-528
+public:
+    StartPlatform(Node *parent, Rng &rng, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, WALLS_SOUTH | WALLS_EAST | WALLS_WEST, params, w) {}
+};
+
+class ExitPlatform : public EmptyPlatform {  // platforms.hpp:530-546
+public:
+    ExitPlatform(Node *parent, Rng &rng, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, WALLS_NORTH | WALLS_EAST | WALLS_WEST, params, w) {}
+    void generate() override {
+        EmptyPlatform::generate();
+        terrainBoxes[TERRAIN_EXIT].emplace_back(makeAABB({length - 3, 1, 1, length - 1, 3, width - 1}));
+    }
+};
+
+class TransitionPlatform : public EmptyPlatform {  // platforms.hpp:548-558
+public:
+    TransitionPlatform(Node *parent, Rng &rng, int walls, const FloatParams &params, int l, int w) : EmptyPlatform(parent, rng, walls, params, -1) { length = l; width = w; }
+    void init() override { height = 5; }
 };
 
 struct BBoxInfo {  // component_voxel_grid.hpp:33-50

@@ -107,22 +107,23 @@ def test_unordered_set_order_emulation(built):
         assert np.array_equal(out[: k * 3].reshape(k, 3), capi.bzset_order(ops))
 
 
-@pytest.mark.parametrize("num_agents", [1, 4])
-def test_level_generation_matches_oracle(built, num_agents):
+@pytest.mark.parametrize("scenario,num_agents", [("TowerBuilding", 1), ("TowerBuilding", 4), ("ObstaclesHard", 1), ("ObstaclesEasy", 2), ("ObstaclesMedium", 3),
+                                                 ("ObstaclesWalls", 1), ("ObstaclesSteps", 2), ("ObstaclesLava", 1)])
+def test_level_generation_matches_oracle(built, scenario, num_agents):
     """the product's flat host level generator against the oracle's reference-style one: same RNG draws, same merged
     boxes in the same order, same objects, spawn cells and spawn yaw bits -- over consecutive episodes of one stream"""
     import orc
     from megaverse_b200 import capi
 
     for seed in range(40, 70):
-        o = orc.Oracle("TowerBuilding", 1, num_agents, render=False)
+        o = orc.Oracle(scenario, 1, num_agents, render=False)
         o.seed_env(0, seed)
         for episode in range(3):
             o.reset()
             want = o.level(0)
-            got = capi.generate_level("TowerBuilding", num_agents, seed, episode)
+            got = capi.generate_level(scenario, num_agents, seed, episode)
             n = len(want)
-            assert np.array_equal(want, got[:n]), "seed %d episode %d" % (seed, episode)
+            assert np.array_equal(want, got[:n]), "%s seed %d episode %d: first diff at %s" % (scenario, seed, episode, np.nonzero(want != got[:n])[0][:5])
             st = o.state(0)
             basis = np.concatenate([st[8 + 26 * a + 3: 8 + 26 * a + 12] for a in range(num_agents)]).view(np.int32)
             assert np.array_equal(basis, got[n:]), "spawn basis seed %d episode %d" % (seed, episode)

@@ -188,3 +188,52 @@ def test_fast_shading_within_one_lsb(built):
     assert worst_exact > 0.9, worst_exact
     print("fast shading: worst exact-byte fraction %.5f" % worst_exact)
     o.close(); g.close()
+
+
+# ------------------------------------------------------------------------------------------------ Obstacles family
+@pytest.mark.parametrize("scenario,A", [("ObstaclesHard", 1), ("ObstaclesEasy", 2), ("ObstaclesLava", 1)])
+def test_obstacles_reset_parity(built, scenario, A):
+    E = 8
+    o, g = _pair(scenario, E, A, 11)
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.voxels(e), g.voxels(e)), "voxels %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("scenario,A,policy", [("ObstaclesHard", 1, "purposeful"), ("ObstaclesHard", 1, "bits"), ("ObstaclesMedium", 2, "purposeful"), ("Test", 2, "forward")])
+def test_obstacles_trajectory_parity(built, scenario, A, policy):
+    """BASELINE config 3 scenario (with the float32 depth output): physics incl. steps / gaps / lava teleports, exit + extra
+    rewards, doneWithTimer; the Test variant (start + exit platform only) makes agents reach the exit quickly"""
+    E, steps = 12, 500
+    o, g = _pair(scenario, E, A, 2024, depth=True)
+    rng = np.random.default_rng(5)
+    total = 0.0
+    ndone = 0
+    for t in range(steps):
+        if policy == "bits":
+            acts = helpers.random_bit_actions(rng, E * A)
+        elif policy == "forward":
+            acts = np.where(rng.random(E * A) < 0.85, 1 << 3, 1 << 5).astype(np.int32)
+        else:
+            acts = helpers.purposeful_actions(rng, E * A, t)
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        total += float(np.abs(ro).sum())
+        ndone += int(o.dones().sum())
+        if t % 25 == 0 or t == steps - 1 or o.dones().any():
+            _assert_same_state(o, g, E, "step %d" % t)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+            assert np.array_equal(o.depth().view(np.uint32), np.array(g.depth()).view(np.uint32)), "step %d depth" % t
+    if policy == "forward":
+        assert total > 0 and ndone > 0, "the Test variant should be solved by walking forward (reward %.2f, dones %d)" % (total, ndone)
+    assert g.faults() == 0
+    o.close(); g.close()
