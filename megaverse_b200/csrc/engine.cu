@@ -182,7 +182,7 @@ struct mv_engine {
             {
                 int boxes = out.level.n_terrain + out.level.n_obj + 2 * A;
                 for (int i = 0; i < out.level.n_static; ++i) boxes += (out.level.statics[i].flags & MV_OPAQUE) ? 1 : 0;
-                const int items = boxes * 6 + (A + 2 * out.level.n_reward) * 128;  // non-box meshes take 128 triangle slots each
+                const int items = boxes * 6 + A * 128 + 2 * out.level.n_reward * 12;  // capsule 128 triangles, cone 12
                 int cur = maxItemsSeen.load();
                 while (items > cur && !maxItemsSeen.compare_exchange_weak(cur, items)) {}
             }
@@ -255,7 +255,7 @@ struct mv_engine {
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
         const int nTiles = (W / 32) * (H / 4);
-        const int maxItems = MV_MAX_INSTANCES * 6 + (A + 2 * MV_MAX_REWARD) * 128;  // blocks past a view's real item count exit at once
+        const int maxItems = MV_MAX_INSTANCES * 6 + A * 128 + 2 * MV_MAX_REWARD * 12;  // blocks past a view's real item count exit at once
         const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
         for (int base = 0; base < N; base += chunkViews) {
             const int cv = std::min(chunkViews, N - base);
@@ -412,12 +412,14 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
     ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
-         ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 2), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
+         ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
          ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
-    e->chunkViews = int(std::min<size_t>(N, 512));
+    // rasteriser scratch: Collect's Perlin landscapes merge into up to ~500 boxes (+ up to 86 reward diamonds)
+    e->triCap = sc == MV_SCENARIO_COLLECT ? 4096 : (sc == MV_SCENARIO_OBSTACLES ? 2048 : 1024);
+    e->chunkViews = int(std::min<size_t>(N, sc == MV_SCENARIO_COLLECT ? 256 : 512));
     if (ok && e->allocTriScratch() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
@@ -452,7 +454,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         return MV_OK;
     }
     if (k == "tri_cap") {
-        if (value < 64 || value > 16384) { h->setError("tri_cap out of range [64,16384]"); return MV_ERR_ARG; }
+        if (value < 64 || value > 8192) { h->setError("tri_cap out of range [64,8192]"); return MV_ERR_ARG; }
         if (h->stream) cudaStreamSynchronize(h->stream);
         h->triCap = value;
         return h->allocTriScratch();
@@ -633,7 +635,7 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     }
     for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
     for (int i = 0; i < h->A; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
-    if (L.scenario == MV_SCENARIO_OBSTACLES) {
+    if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);  // numPlatforms
         o.push_back(L.n_reward);
         for (int i = 0; i < L.n_reward; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
@@ -682,7 +684,10 @@ int mv_debug_get_state(mv_handle h, int env, float *out, int cap) {
         }
         for (float x : {t[0], t[1], t[2], b.s[0], b.s[1], b.s[2], float(b.parent), b.enabled ? 1.f : 0.f, 0.f}) o.push_back(x);
     }
-    if (L.scenario == MV_SCENARIO_OBSTACLES) { o.push_back(float(es.solved)); o.push_back(float(es.reached_exit)); o.push_back(float(es.reward_alive)); }
+    if (L.scenario != MV_SCENARIO_TOWER) {
+        o.push_back(float(es.solved)); o.push_back(float(es.reached_exit));
+        for (int w = 0; w < 3; ++w) o.push_back(float(es.reward_alive[w] & 0xffffffu)), o.push_back(float(es.reward_alive[w] >> 24));
+    }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(float));
     return int(o.size());
@@ -725,9 +730,9 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
 
 int mv_debug_get_instances(mv_handle h, int env, float *out, int cap) {
     if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
-    int32_t cnt[2];
+    int32_t cnt[8];
     cudaStreamSynchronize(h->stream);
-    if (cudaMemcpy(cnt, h->d_instCounts.p + size_t(env) * 2, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (cudaMemcpy(cnt, h->d_instCounts.p + size_t(env) * 8, 32, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     std::vector<MvInstance> inst(static_cast<size_t>(cnt[1] > 0 ? cnt[1] : 1));
     if (cudaMemcpy(inst.data(), h->d_inst.p + size_t(env) * MV_MAX_INSTANCES, sizeof(MvInstance) * inst.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     if (cnt[1] * 18 > cap) return -cnt[1] * 18;
@@ -761,17 +766,26 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
     MvConsts k;
     fillConsts(k, w, h);
     if (uploadPalette(&tmp) != MV_OK) return MV_ERR_CUDA;
-    const int triCap = 4096;
+    const int triCap = 8192;
     MvInstance *dInst = nullptr; int32_t *dCnt = nullptr, *dFault = nullptr, *dTri = nullptr, *dTileCtr = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
     mvr::TriCover *dCover = nullptr; mvr::TriShade *dShade = nullptr; short4 *dBox = nullptr;
-    const int32_t cnt[2] = {nBox, n};
-    bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 8) == cudaSuccess && cudaMalloc(&dFault, 4) == cudaSuccess &&
+    int32_t cnt[8] = {nBox, n, 0, 0, 0, 0, 0, 0};
+    {   // instances must be sorted by mesh type (draw order)
+        int last = 0;
+        for (int i = 0; i < n; ++i) {
+            const int m = inst[size_t(i)].mesh;
+            if (m < last || m > 4) return MV_ERR_ARG;
+            last = m;
+            if (m >= 1) cnt[1 + m] += 1;
+        }
+    }
+    bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 32) == cudaSuccess && cudaMalloc(&dFault, 4) == cudaSuccess &&
               cudaMalloc(&dView, 64) == cudaSuccess && cudaMalloc(&dObs, size_t(w) * h * 4) == cudaSuccess && cudaMalloc(&dDepth, size_t(w) * h * 4) == cudaSuccess &&
               cudaMalloc(&dTri, 4) == cudaSuccess && cudaMalloc(&dTileCtr, 4) == cudaSuccess && cudaMalloc(&dCover, sizeof(mvr::TriCover) * triCap) == cudaSuccess &&
               cudaMalloc(&dShade, sizeof(mvr::TriShade) * triCap) == cudaSuccess && cudaMalloc(&dBox, sizeof(short4) * triCap) == cudaSuccess;
     if (ok) {
         cudaMemcpy(dInst, inst.data(), sizeof(MvInstance) * inst.size(), cudaMemcpyHostToDevice);
-        cudaMemcpy(dCnt, cnt, 8, cudaMemcpyHostToDevice);
+        cudaMemcpy(dCnt, cnt, 32, cudaMemcpyHostToDevice);
         cudaMemcpy(dView, view16, 64, cudaMemcpyHostToDevice);
         cudaMemset(dFault, 0, 4);
         cudaMemset(dTri, 0, 4);
@@ -779,7 +793,7 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
         rp.instances = dInst; rp.instCounts = dCnt; rp.views = dView; rp.instStride = int(inst.size()); rp.obs = dObs; rp.depth = depth ? dDepth : nullptr;
         rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.bbox = dBox; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.tune = 0; rp.viewBase = 0; rp.chunkViews = 1;
         rp.N = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
-        const int items = nBox * 6 + (n - nBox) * 128;
+        const int items = nBox * 6 + (n - nBox) * 128;  // upper bound
         mvr::geomKernel<<<dim3(unsigned((items + 127) / 128 + 1), 1), 128>>>(rp);
         mvr::tileKernel<false><<<((w / 32) * (h / 4) + 3) / 4, 128>>>(rp);
         ok = cudaDeviceSynchronize() == cudaSuccess;
@@ -827,7 +841,7 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     }
     for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
     for (int i = 0; i < num_agents; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
-    if (L.scenario == MV_SCENARIO_OBSTACLES) {
+    if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);
         o.push_back(L.n_reward);
         for (int i = 0; i < L.n_reward; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);

@@ -149,6 +149,7 @@ static std::string lower(const std::string &name) {
 int scenarioFromName(const std::string &name) {
     const std::string n = lower(name);
     if (n == "towerbuilding") return MV_SCENARIO_TOWER;
+    if (n == "collect") return MV_SCENARIO_COLLECT;
     if (n == "obstacleseasy" || n == "obstaclesmedium" || n == "obstacleshard" || n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava" || n == "test")
         return MV_SCENARIO_OBSTACLES;
     return -1;
@@ -182,6 +183,8 @@ std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::strin
     const int scenario = scenarioFromName(n);
     if (scenario == MV_SCENARIO_TOWER)  // scenario_tower_building.hpp:44-52
         return {{"teamSpirit", 0.1f}, {"towerPickedUpObject", 0.1f}, {"towerVisitedBuildingZoneWithObject", 0.1f}, {"towerBuildingReward", 1.0f}};
+    if (scenario == MV_SCENARIO_COLLECT)  // scenario_collect.hpp:42-50
+        return {{"collectSingleGood", 1.0f}, {"collectSingleBad", -1.0f}, {"collectAll", 5.0f}, {"collectAbyss", -0.5f}};
     if (scenario == MV_SCENARIO_OBSTACLES) {  // scenario_obstacles.hpp:37-45,201-206
         const bool oneType = n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava";
         return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f}, {"obstaclesAgentCarriedObjectToExit", oneType ? 1.0f : 0.0f}};
@@ -196,6 +199,12 @@ int rewardSlot(int scenario, const std::string &key) {
         if (key == "towerVisitedBuildingZoneWithObject") return MV_R_TOWER_VISITED_BZ;
         if (key == "towerBuildingReward") return MV_R_TOWER_BUILDING;
     }
+    if (scenario == MV_SCENARIO_COLLECT) {
+        if (key == "collectSingleGood") return MV_R_COLLECT_GOOD;
+        if (key == "collectSingleBad") return MV_R_COLLECT_BAD;
+        if (key == "collectAll") return MV_R_COLLECT_ALL;
+        if (key == "collectAbyss") return MV_R_COLLECT_ABYSS;
+    }
     if (scenario == MV_SCENARIO_OBSTACLES) {
         if (key == "obstaclesAgentAtExit") return MV_R_OBST_AGENT_AT_EXIT;
         if (key == "obstaclesAllAgentsAtExit") return MV_R_OBST_ALL_AT_EXIT;
@@ -208,7 +217,8 @@ int rewardSlot(int scenario, const std::string &key) {
 int gridCapacity(int scenario) {
     // TowerBuilding rooms are at most 29 x (6+18) x 24; Obstacles chains of up to 7 platforms (+ transitions, start, exit)
     // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
-    const int cells = scenario == MV_SCENARIO_TOWER ? 30 * 25 * 25 : 512 * 1024;
+    // Collect: <= 41 x 41 landscape, heights <= 17, 3 cells of margin (objects can be put down beyond the edge), y from -30
+    const int cells = scenario == MV_SCENARIO_TOWER ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 48 * 64 * 48 : 512 * 1024);
     return ((cells + 127) / 128) * 128;
 }
 
@@ -226,6 +236,7 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     switch (scenario_) {
         case MV_SCENARIO_TOWER: generateTower(out); break;
         case MV_SCENARIO_OBSTACLES: generateObstacles(out); break;
+        case MV_SCENARIO_COLLECT: generateCollect(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
     const MvLevel &L = out.level;
@@ -344,6 +355,178 @@ void LevelGenerator::fillPlanes(LevelOut &out, const void *gridPtr) {
         if (kv.second.terrain & 1) out.exitBits[size_t(idx >> 5)] |= 1u << (idx & 31);
         if (kv.second.terrain & 2) out.lavaBits[size_t(idx >> 5)] |= 1u << (idx & 31);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------- Collect
+// scenario_collect.cpp:35-143 (createLandscape), :185-212 (reward diamonds); terrain from siv::PerlinNoise
+// (src/libs/util/include/util/perlin_noise.hpp: Ken Perlin's improved noise in double precision, permutation = std::shuffle
+// of 0..255 with std::default_random_engine(seed))
+namespace {
+
+class Perlin {
+public:
+    explicit Perlin(std::uint32_t seed) {
+        for (size_t i = 0; i < 256; ++i) p[i] = static_cast<std::uint8_t>(i);
+        std::shuffle(std::begin(p), std::begin(p) + 256, std::default_random_engine(seed));
+        for (size_t i = 0; i < 256; ++i) p[256 + i] = p[i];
+    }
+    double octaves01(double x, double y, int octaves) const {  // accumulatedOctaveNoise2D_0_1
+        double result = 0, amp = 1;
+        for (int i = 0; i < octaves; ++i) {
+            result += noise(x, y, 0) * amp;
+            x *= 2; y *= 2; amp /= 2;
+        }
+        return std::clamp<double>(result * 0.5 + 0.5, 0, 1);
+    }
+
+private:
+    static double fade(double t) { return t * t * t * (t * (t * 6 - 15) + 10); }
+    static double lerp(double t, double a, double b) { return a + t * (b - a); }
+    static double grad(std::uint8_t hash, double x, double y, double z) {
+        const std::uint8_t h = hash & 15;
+        const double u = h < 8 ? x : y;
+        const double v = h < 4 ? y : h == 12 || h == 14 ? x : z;
+        return ((h & 1) == 0 ? u : -u) + ((h & 2) == 0 ? v : -v);
+    }
+    double noise(double x, double y, double z) const {
+        const int X = static_cast<int>(std::floor(x)) & 255, Y = static_cast<int>(std::floor(y)) & 255, Z = static_cast<int>(std::floor(z)) & 255;
+        x -= std::floor(x); y -= std::floor(y); z -= std::floor(z);
+        const double u = fade(x), v = fade(y), w = fade(z);
+        const int A = p[X] + Y, AA = p[A] + Z, AB = p[A + 1] + Z, B = p[X + 1] + Y, BA = p[B] + Z, BB = p[B + 1] + Z;
+        return lerp(w, lerp(v, lerp(u, grad(p[AA], x, y, z), grad(p[BA], x - 1, y, z)), lerp(u, grad(p[AB], x, y - 1, z), grad(p[BB], x - 1, y - 1, z))),
+                    lerp(v, lerp(u, grad(p[AA + 1], x, y, z - 1), grad(p[BA + 1], x - 1, y, z - 1)),
+                         lerp(u, grad(p[AB + 1], x, y - 1, z - 1), grad(p[BB + 1], x - 1, y - 1, z - 1))));
+    }
+    std::uint8_t p[512];
+};
+
+}  // namespace
+
+void LevelGenerator::generateCollect(LevelOut &out) {
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    static const uint32_t landscapeColors[7] = {C_WHITE, C_VL_GREEN, C_VL_BLUE, C_VL_GREY, C_VL_ORANGE, C_GREY, C_DARK_GREY};
+    static const uint32_t floorColors[3] = {C_GREY, C_DARK_GREY, C_DARK_GREY};
+    const uint32_t landscapeColor = landscapeColors[randRange(0, 7, rng)];
+    const uint32_t floorColor = floorColors[randRange(0, 3, rng)];
+    constexpr int maxWidth = 42, maxLength = maxWidth;
+    const int width = randRange(8, maxWidth, rng);
+    const int length = randRange(8, maxWidth, rng);
+    std::vector<int> spawnHeight(size_t(length * width), 1);
+    const double frequency = double(randRange(1, 100, rng)) / 10.0;
+    const int octaves = randRange(1, 10, rng);
+    const std::uint32_t seed = std::uint32_t(randRange(0, 1000000000, rng));
+    const Perlin perlin(seed);
+    const double fx = maxLength / frequency, fz = maxWidth / frequency;
+    const int intensity = randRange(5, 18, rng);
+    const float groundLevel = frand(rng) * 0.5f + 0.2f;
+
+    VoxMap grid{100};
+    auto setVox = [&](int x, int y, int z, uint32_t color) { Vox v; v.type = MV_SOLID | MV_OPAQUE; v.terrain = 0; v.color = color; grid[voxKey(x, y, z)] = v; };
+    for (int x = 1; x < length - 1; ++x)
+        for (int z = 1; z < width - 1; ++z) {
+            const double noise = perlin.octaves01(x / fx, z / fz, octaves);
+            const double yCoord = intensity * (noise - groundLevel);
+            if (yCoord >= 1) {
+                const int yr = int(lround(yCoord));
+                for (int y = yr; y >= 1; --y) setVox(x, y, z, landscapeColor);
+                spawnHeight[size_t(x * width + z)] = yr + 1;
+            }
+        }
+    for (int x = 0; x < length; ++x)
+        for (int z = 0; z < width; ++z) setVox(x, 0, z, floorColor);
+
+    std::vector<I3> spawn;
+    for (int x = 1; x < length - 1; ++x)
+        for (int z = 1; z < width - 1; ++z) spawn.push_back({x, spawnHeight[size_t(x * width + z)], z});
+    std::shuffle(spawn.begin(), spawn.end(), rng);
+    int offset = 0;
+    if (int(spawn.size()) < A + 1) throw std::runtime_error("landscape too small for the agents");
+    std::vector<I3> agentSpawn(spawn.begin(), spawn.begin() + A);
+    offset += A;
+    int numRewards = randRange(1, int(lround(0.05 * width * length)) + 2, rng);
+    numRewards = std::min(numRewards, int(spawn.size()) - offset);
+    const int numRandom = std::max(numRewards / 2, 1);
+    std::vector<I3> rewards(spawn.begin() + offset, spawn.begin() + offset + numRandom);
+    offset += numRandom;
+    // same (unstable) std::sort call on the same data as the reference: equal-height order is libstdc++'s introsort order
+    std::sort(spawn.begin() + offset, spawn.end(), [&](const I3 &a, const I3 &b) {
+        const int ha = spawnHeight[size_t(a.x * width + a.z)], hb = spawnHeight[size_t(b.x * width + b.z)];
+        if (ha != hb) return ha > hb;
+        else return false;
+    });
+    rewards.insert(rewards.end(), spawn.begin() + offset, spawn.begin() + offset + (numRewards - numRandom));
+    offset += numRewards - numRandom;
+    std::shuffle(spawn.begin() + offset, spawn.end(), rng);
+    const int objectsMin = std::max(3, int(length * width * 0.04));
+    const int objectsMax = std::min(objectsMin + 1, int(lround(0.07 * width * length)) + 2);
+    const int numObjects = std::min(randRange(objectsMin, objectsMax, rng), int(spawn.size()) - offset);
+    std::vector<I3> objs;
+    if (offset + numObjects < int(spawn.size())) objs.assign(spawn.begin() + offset, spawn.begin() + offset + numObjects);
+
+    // DefaultScenario::spawnAgents
+    for (int i = 0; i < A; ++i) {
+        const float yaw = frand(rng) * 3.14159265358979323846f * 2;
+        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        const float sx = float(agentSpawn[size_t(i)].x) + 0.5f, sy = float(agentSpawn[size_t(i)].y) + 0.0f, sz = float(agentSpawn[size_t(i)].z) + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        L.init_pos[i][0] = float(agentSpawn[size_t(i)].x); L.init_pos[i][1] = float(agentSpawn[size_t(i)].y); L.init_pos[i][2] = float(agentSpawn[size_t(i)].z);
+    }
+
+    int ns = 0;
+    for (const auto &g : mergeVoxels(grid)) {
+        if (g.type == 0) continue;
+        for (const auto &b : g.boxes) {
+            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
+            MvBox &sb = L.statics[ns++];
+            for (int a = 0; a < 3; ++a) {
+                sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
+                sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;
+            }
+            sb.flags = g.type;
+            sb.color = paletteIndex(g.color);
+        }
+    }
+    L.n_static = ns;
+    L.n_terrain = 0;
+    if (int(objs.size()) > MV_MAX_OBJECTS - 1) throw std::runtime_error("too many movable objects");
+    L.n_obj = int(objs.size());
+    for (int i = 0; i < L.n_obj; ++i) {
+        L.obj_voxel[i][0] = int16_t(objs[size_t(i)].x); L.obj_voxel[i][1] = int16_t(objs[size_t(i)].y); L.obj_voxel[i][2] = int16_t(objs[size_t(i)].z);
+        L.obj_voxel[i][3] = int16_t(paletteIndex(C_LIGHT_BLUE));
+    }
+    if (int(rewards.size()) > MV_MAX_REWARD) throw std::runtime_error("too many reward objects");
+    L.n_reward = int(rewards.size());
+    L.n_positive = 0;
+    {
+        using namespace mvh;
+        const float ang = 180.0f * 3.14159265358979323846f / 180.0f;
+        M4 rx = identity();
+        const float s = crsin(ang), c = crcos(ang);
+        rx.c[1][1] = c; rx.c[1][2] = s; rx.c[2][1] = -s; rx.c[2][2] = c;
+        const M4 bottom = mul(translation(0.0f, -1.0f, 0.0f), mul(identity(), rx));
+        std::memcpy(L.cone_bottom_local, &bottom.c[0][0], 64);
+        for (int i = 0; i < L.n_reward; ++i) {
+            const I3 r = rewards[size_t(i)];
+            const bool good = frand(rng) > 0.3f;  // drawn in addEpisodeDrawables, i.e. after the agents' yaw draws
+            if (good) ++L.n_positive;
+            L.reward_voxel[i][0] = int16_t(r.x); L.reward_voxel[i][1] = int16_t(r.y); L.reward_voxel[i][2] = int16_t(r.z);
+            L.reward_voxel[i][3] = int16_t(paletteIndex(good ? C_GREEN : C_RED));
+            const M4 root = mul(translation(float(r.x) + 0.5f, float(r.y) + 0.8f, float(r.z) + 0.5f), mul(scaling(0.17f, 0.45f, 0.17f), identity()));
+            std::memcpy(L.reward_root[i], &root.c[0][0], 64);
+        }
+    }
+    L.episode_len = params_.at("episodeLengthSec") + 2.0f * rewards.size();  // scenario_collect.hpp:52-56
+    L.n_movable = 0;
+
+    int maxY = 0;
+    for (const auto &kv : grid) maxY = std::max(maxY, voxUnkey(kv.first).y);
+    for (auto &c : objs) maxY = std::max(maxY, c.y);
+    for (auto &c : rewards) maxY = std::max(maxY, c.y);
+    L.grid_org[0] = -3; L.grid_org[1] = -30; L.grid_org[2] = -3;
+    L.grid_dim[0] = length + 6; L.grid_dim[1] = maxY + 30 + 1 + 12; L.grid_dim[2] = width + 6;
+    fillPlanes(out, &grid);
 }
 
 // ---------------------------------------------------------------------------------------------------- Obstacles

@@ -33,6 +33,7 @@ public:
 private:
     void generateTower(LevelOut &out);
     void generateObstacles(LevelOut &out);
+    void generateCollect(LevelOut &out);
     void fillPlanes(LevelOut &out, const void *voxMap);
     int scenario_;
     std::string name_;

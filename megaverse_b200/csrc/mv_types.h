@@ -8,7 +8,7 @@
 //   agents   MvAgent[E*A]           kinematic controller + camera state
 //   objects  MvObject[E][MAX_OBJ]   movable boxes
 //   inst     MvInstance[E][MAX_INST] per-env drawable list in draw order (static part written at reset, dynamic part per step)
-//   instCnt  int32[E][2]            {number of box instances, total instances}
+//   instCnt  int32[E][8]            {boxes, total, capsules, spheres, cones, cylinders, -, -}
 //   views    float[N][16]           per-view camera matrices, written by the step kernel
 //   obs      uint8[N][H][W][4]      the observation tensor (reference layout, megaverse.cpp:139-143)
 //   depth    float[N][H][W]         optional
@@ -18,14 +18,16 @@
 #include <stdint.h>
 
 #define MV_MAX_AGENTS 8
-#define MV_MAX_STATIC 160
+#define MV_MAX_STATIC 768
 #define MV_MAX_TERRAIN 16
 #define MV_MAX_OBJECTS 128
-#define MV_MAX_REWARD 16
+#define MV_MAX_REWARD 96
+#define MV_MAX_CAND 96      // per-agent collision candidates per step
 #define MV_NO_OBJECT 0xFF
 
 #define MV_SCENARIO_TOWER 0
 #define MV_SCENARIO_OBSTACLES 1
+#define MV_SCENARIO_COLLECT 2
 
 // voxel / box flags (voxel_state.hpp:10-15)
 #define MV_SOLID 1
@@ -53,6 +55,11 @@
 #define MV_R_OBST_ALL_AT_EXIT 2
 #define MV_R_OBST_EXTRA 3
 #define MV_R_OBST_CARRIED_TO_EXIT 4
+// Collect (scenario_collect.hpp:42-50)
+#define MV_R_COLLECT_GOOD 1
+#define MV_R_COLLECT_BAD 2
+#define MV_R_COLLECT_ALL 3
+#define MV_R_COLLECT_ABYSS 4
 #define MV_R_COUNT 8
 
 // fault bits (per env, sticky): the engine never exit()s, it reports
@@ -60,6 +67,7 @@
 #define MV_FAULT_TRI_OVERFLOW 2      // a view produced more triangles than the rasteriser's shared-memory list holds
 #define MV_FAULT_GRID_RANGE 4        // an object was placed outside the dense voxel grid
 #define MV_FAULT_NAN 8               // NaN position (agent.cpp:82-93 guard)
+#define MV_FAULT_CAND_OVERFLOW 32     // more than MV_MAX_CAND colliders near one agent
 #define MV_FAULT_ENVELOPE 16         // an agent left the per-step collision envelope the candidate colliders were culled against
 
 struct MvBox {       // static layout box: drawable (OPAQUE) and/or collider (SOLID)
@@ -85,15 +93,16 @@ struct MvLevel {
     int32_t bz_min[3], bz_max[3];  // building zone (x,z used)
     float episode_len;             // episodeLengthSec() of this level (scenario_tower_building.cpp:263-266, scenario_obstacles.cpp:262-266)
     float look_limit;              // floatParams["verticalLookLimitRad"]
-    int32_t n_reward;              // Obstacles: reward diamonds
-    int32_t pad0[3];               // statics[] must start 16-byte aligned (TMA bulk copy source)
+    int32_t n_reward;              // Obstacles / Collect: reward diamonds
+    int32_t n_positive;            // Collect: numPositiveRewards
+    int32_t pad0[2];               // statics[] must start 16-byte aligned
     MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
     MvTerrain terrain[MV_MAX_TERRAIN];
     int16_t obj_voxel[MV_MAX_OBJECTS][4];  // x,y,z,color
     float spawn_pos[MV_MAX_AGENTS][4];     // ghost origin at spawn (agent.cpp:45)
     float spawn_basis[MV_MAX_AGENTS][12];  // ghost basis rows (btMatrix3x3(btQuaternion(Y, yaw)))
     float init_pos[MV_MAX_AGENTS][4];      // FallDetection agentInitialPositions
-    int16_t reward_voxel[MV_MAX_REWARD][4];  // Obstacles reward objects: voxel + palette colour
+    int16_t reward_voxel[MV_MAX_REWARD][4];  // reward objects: voxel + palette colour (Collect: GREEN = +1, RED = -1)
     float reward_root[MV_MAX_REWARD][16];    // addDiamond root model matrix (layout_utils.cpp:114-126)
     float cone_bottom_local[16];             // the lower cone's local transform (rotateXLocal(180 deg), translate(0,-1,0))
 };
@@ -135,8 +144,8 @@ struct MvEnvState {
     // std::unordered_set<VoxelCoords> objectsInBuildingZone, emulated in libstdc++ iteration order (bzset.h)
     int32_t solved;          // Obstacles: all agents reached the exit
     uint32_t reached_exit;   // Obstacles: bit per agent
-    uint32_t reward_alive;   // Obstacles: bit per reward object still in place
-    int32_t pad1;
+    uint32_t reward_alive[3];  // bit per reward object still in place
+    int32_t positive_collected;  // Collect
     int32_t bz_count, bz_nb, bz_next_resize;
     int16_t bz_items[MV_MAX_OBJECTS][4];
     int32_t pad[2];

@@ -28,7 +28,7 @@ struct __align__(16) TriCover {  // what the coverage / depth loop reads (broadc
     int32_t A[3], B[3];
     float z[3];
     float invArea;
-    uint32_t key;       // draw order + 1 (later wins depth ties: LESS_OR_EQUAL)
+    uint32_t key;       // draw order + 1, < 2^18 (later wins depth ties: LESS_OR_EQUAL)
     int32_t tl;         // bit e set: edge e is top-left (no bias was applied)
     int32_t pad[2];
 };
@@ -43,7 +43,7 @@ static_assert(sizeof(TriCover) == 80 && sizeof(TriShade) == 96, "triangle record
 
 struct RasterParams {
     const MvInstance *instances; // [E][instStride] drawables in draw order (boxes first)
-    const int32_t *instCounts;   // [E][2] {boxes, total}
+    const int32_t *instCounts;   // [E][8] {boxes, total, capsules, spheres, cones, cylinders, -, -}
     const float *views;          // [E*A][16]
     int instStride;
     uint8_t *obs;                // [N][H][W][4]
@@ -144,7 +144,7 @@ __device__ void clipAndSetup(const SetupCtx &cx, const ClipVert &v0, const ClipV
             sys[i] = snapSub((vs[i]->cy * r) * hh + hh);
             szs[i] = vs[i]->cz * r;
         }
-        emitTri(cx, v0, v1, v2, sxs, sys, szs, rws, color, keyBase + 1u);
+        emitTri(cx, v0, v1, v2, sxs, sys, szs, rws, color, keyBase);
         return;
     }
     ClipVert poly[6], tmp[6];
@@ -180,7 +180,7 @@ __device__ void clipAndSetup(const SetupCtx &cx, const ClipVert &v0, const ClipV
     for (int k = 1; k + 1 < n; ++k) {
         const int32_t sxs[3] = {sx[0], sx[k], sx[k + 1]}, sys[3] = {sy[0], sy[k], sy[k + 1]};
         const float szs[3] = {sz[0], sz[k], sz[k + 1]}, rws[3] = {rw[0], rw[k], rw[k + 1]};
-        emitTri(cx, poly[0], poly[k], poly[k + 1], sxs, sys, szs, rws, color, keyBase + uint32_t(k));
+        emitTri(cx, poly[0], poly[k], poly[k + 1], sxs, sys, szs, rws, color, keyBase);
     }
 }
 
@@ -208,9 +208,12 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.tileCounter = 0;  // for the tile kernel that follows in-stream
     const MvInstance *inst = P.instances + size_t(env) * P.instStride;
-    const int nBoxInst = P.instCounts[env * 2 + 0], nInst = P.instCounts[env * 2 + 1];
+    // work items: 6 faces per box, then one per triangle of the other meshes (instances are sorted by mesh type)
+    const int *cnt = P.instCounts + env * 8;
+    const int nBoxInst = cnt[0];
     const int nBoxItems = nBoxInst * 6;
-    if (item >= nBoxItems + (nInst - nBoxInst) * 128) return;
+    const int capItems = cnt[2] * MV_CAPSULE_TRIS, sphItems = cnt[3] * MV_SPHERE_TRIS, coneItems = cnt[4] * MV_CONE_TRIS, cylItems = cnt[5] * MV_CYLINDER_TRIS;
+    if (item >= nBoxItems + capItems + sphItems + coneItems + cylItems) return;
 
     SetupCtx cx;
     cx.cover = P.cover + size_t(vslot) * P.triCap;
@@ -239,16 +242,17 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
             const float *vp = c_boxVerts[face * 4 + k];
             cvt[k] = makeVert(mv, nm, v3(vp[0], vp[1], vp[2]), v3(vp[3], vp[4], vp[5]), P.p00, P.p11, P.p22, P.p32);
         }
-        const uint32_t keyBase = (uint32_t(ii) * 128u + uint32_t(face) * 2u) * 4u + 1u;
+        // draw-order key: instance, then triangle within the mesh (the fan pieces of one clipped triangle share a key: they are
+        // coplanar and disjoint, so they never tie on a pixel).  18 bits + 13 bits of list index fill the fragment's low word.
+        const uint32_t keyBase = uint32_t(ii) * 128u + uint32_t(face) * 2u + 1u;
         clipAndSetup(cx, cvt[0], cvt[1], cvt[2], color, keyBase);       // cube indices f*4+{0,1,2}
-        clipAndSetup(cx, cvt[0], cvt[2], cvt[3], color, keyBase + 4u);  // cube indices f*4+{0,2,3}
+        clipAndSetup(cx, cvt[0], cvt[2], cvt[3], color, keyBase + 1u);  // cube indices f*4+{0,2,3}
     } else {
-        // other meshes: one item per (instance, triangle slot); capsule 128, sphere 80, cone 12, cylinder 24
-        const int rest = item - nBoxItems;
-        const int ii = nBoxInst + rest / 128, tri = rest % 128;
-        const int mesh = inst[ii].mesh;
-        const int ntri = mesh == 1 ? MV_CAPSULE_TRIS : (mesh == 2 ? MV_SPHERE_TRIS : (mesh == 3 ? MV_CONE_TRIS : MV_CYLINDER_TRIS));
-        if (tri >= ntri) return;
+        int rest = item - nBoxItems, ii = nBoxInst, tri, mesh;
+        if (rest < capItems) { mesh = 1; ii += rest / MV_CAPSULE_TRIS; tri = rest % MV_CAPSULE_TRIS; }
+        else if ((rest -= capItems) < sphItems) { mesh = 2; ii += cnt[2] + rest / MV_SPHERE_TRIS; tri = rest % MV_SPHERE_TRIS; }
+        else if ((rest -= sphItems) < coneItems) { mesh = 3; ii += cnt[2] + cnt[3] + rest / MV_CONE_TRIS; tri = rest % MV_CONE_TRIS; }
+        else { rest -= coneItems; mesh = 4; ii += cnt[2] + cnt[3] + cnt[4] + rest / MV_CYLINDER_TRIS; tri = rest % MV_CYLINDER_TRIS; }
         M4 model;
 #pragma unroll
         for (int i = 0; i < 16; ++i) model.c[i] = __ldg(inst[ii].model + i);
@@ -265,7 +269,7 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
             else vp = c_cylinderVerts[c_cylinderIdx[tri * 3 + k]];
             cvt[k] = makeVert(mv, nm, v3(vp[0], vp[1], vp[2]), v3(vp[3], vp[4], vp[5]), P.p00, P.p11, P.p22, P.p32);
         }
-        const uint32_t keyBase = (uint32_t(ii) * 128u + uint32_t(tri)) * 4u + 1u;
+        const uint32_t keyBase = uint32_t(ii) * 128u + uint32_t(tri) + 1u;
         clipAndSetup(cx, cvt[0], cvt[1], cvt[2], inst[ii].color, keyBase);
     }
 }

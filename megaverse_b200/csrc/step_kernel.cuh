@@ -46,7 +46,7 @@ struct StepParams {
     MvAgent *agents;             // [E*A]
     MvObject *objects;           // [E][MV_MAX_OBJECTS]
     MvInstance *instances;       // [E][MV_MAX_INSTANCES]
-    int32_t *instCounts;         // [E][2]
+    int32_t *instCounts;         // [E][8]
     float *views;                // [E*A][16]
     int32_t *triCounts;          // [E*A] rasteriser triangle counters, zeroed here for the geometry kernel that follows
     const int32_t *actions;      // [E*A]
@@ -60,7 +60,6 @@ struct StepParams {
 };
 
 struct WarpShared {  // one per warp
-    alignas(16) MvBox statics[MV_MAX_STATIC];
     alignas(16) MvObject objects[MV_MAX_OBJECTS];
     alignas(16) MvAgent agents[MV_MAX_AGENTS];
     alignas(16) MvEnvState env;
@@ -69,7 +68,10 @@ struct WarpShared {  // one per warp
     int objDirty[MV_MAX_AGENTS * 2];
     int nDirty;
     int doneFlag;
-    uint16_t cand[MV_MAX_STATIC + MV_MAX_OBJECTS + MV_MAX_AGENTS];
+    // this agent's collision candidates for the current step, ascending collider index: boxes are copied here (static
+    // layout boxes straight from the level in global memory, movable objects from the staged records), agents are looked
+    // up live because they move within the step
+    struct Cand { float c[3]; float h[3]; int32_t kind; int32_t agent; } cand[MV_MAX_CAND];
 };
 
 // ---------------------------------------------------------------- TMA (1-D bulk async copy) helpers
@@ -236,26 +238,15 @@ __device__ bool rayCapsule(V3 o, V3 d, float L, float R, float &tOut, V3 &nOut) 
 // collider index space: [0,ns) statics, [ns,ns+no) objects, [ns+no, ns+no+A) agent capsules
 struct ColliderView {
     const WarpShared *S;
+    const MvLevel *L;
     int ns, no, A;
-    const uint16_t *cand;  // this agent's candidate colliders for the current step, ascending collider index
-    int nc;
-    __device__ __forceinline__ int count() const { return ns + no + A; }
-    __device__ __forceinline__ bool fetch(int i, int &kind, V3 &c, V3 &h) const {
-        if (i < ns) {
-            const MvBox &b = S->statics[i];
-            if (!(b.flags & MV_SOLID)) return false;
-            kind = 0; c = v3(b.c[0], b.c[1], b.c[2]); h = v3(b.h[0], b.h[1], b.h[2]);
-            return true;
-        }
-        if (i < ns + no) {
-            const MvObject &o = S->objects[i - ns];
-            if (!o.enabled) return false;
-            kind = 0; c = v3(o.col_c[0], o.col_c[1], o.col_c[2]); h = v3(o.col_h[0], o.col_h[1], o.col_h[2]);
-            return true;
-        }
-        const MvAgent &a = S->agents[i - ns - no];
-        kind = 1; c = v3(a.pos[0], a.pos[1], a.pos[2]); h = v3(0, 0, 0);
-        return true;
+    int nc;  // candidates in S->cand
+    // candidate j -> kind, centre, half extents
+    __device__ __forceinline__ void fetch(int j, int &kind, V3 &c, V3 &h) const {
+        const WarpShared::Cand &cd = S->cand[j];
+        kind = cd.kind;
+        if (kind == 0) { c = v3(cd.c[0], cd.c[1], cd.c[2]); h = v3(cd.h[0], cd.h[1], cd.h[2]); }
+        else { const MvAgent &a = S->agents[cd.agent]; c = v3(a.pos[0], a.pos[1], a.pos[2]); h = v3(0, 0, 0); }
     }
 };
 
@@ -268,9 +259,9 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
     int bi = 0x7fffffff;
     V3 bn = v3(0, 0, 0);
     for (int j = lane; j < cv.nc; j += 32) {
-        const int i = cv.cand[j];
+        const int i = j;  // candidates are stored in ascending collider order, so the candidate slot is the tie-break key
         int kind; V3 c, h;
-        if (!cv.fetch(i, kind, c, h)) continue;
+        cv.fetch(j, kind, c, h);
         const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
                                  : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
         bool miss = false;
@@ -312,15 +303,13 @@ __device__ bool warpRecover(const ColliderView &cv, int self, V3 p, V3 &delta, i
         bool pen = false;
         V3 dl = v3(0, 0, 0);
         if (j < cv.nc) {
-            const int i = cv.cand[j];
             int kind; V3 c, h;
-            if (cv.fetch(i, kind, c, h)) {
-                V3 nn;
-                float dist;
-                if (kind == 0) dist = pointBoxDistance(p - c, v3(h.x, h.y + kCapsuleHalfHeight, h.z), nn) - kCapsuleRadius;
-                else dist = pointSegDistance(p - c, 2.0f * kCapsuleHalfHeight, nn) - 2.0f * kCapsuleRadius;
-                if (dist < -kMaxPenetrationDepth) { pen = true; dl = nn * (-dist); }
-            }
+            cv.fetch(j, kind, c, h);
+            V3 nn;
+            float dist;
+            if (kind == 0) dist = pointBoxDistance(p - c, v3(h.x, h.y + kCapsuleHalfHeight, h.z), nn) - kCapsuleRadius;
+            else dist = pointSegDistance(p - c, 2.0f * kCapsuleHalfHeight, nn) - 2.0f * kCapsuleRadius;
+            if (dist < -kMaxPenetrationDepth) { pen = true; dl = nn * (-dist); }
         }
         const unsigned m = __ballot_sync(FULL, pen);
         if (m) {
@@ -589,7 +578,8 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
     if (lane == 0) {
         MvEnvState &e = S.env;
         e.episode_sec = 0.0f; e.num_frames = 0; e.highest_tower = 0;
-        e.solved = 0; e.reached_exit = 0u; e.reward_alive = L.n_reward >= 32 ? 0xffffffffu : ((1u << L.n_reward) - 1u);
+        e.solved = 0; e.reached_exit = 0u; e.positive_collected = 0;
+        for (int w = 0; w < 3; ++w) { const int nb = L.n_reward - 32 * w; e.reward_alive[w] = nb >= 32 ? 0xffffffffu : (nb > 0 ? ((1u << nb) - 1u) : 0u); }
         mvBzClear(e);
         if (L.scenario == MV_SCENARIO_TOWER) {
             for (int i = 0; i < L.n_obj; ++i) {
@@ -652,11 +642,17 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
     const int nr = L.n_reward;
     for (int i = lane; i < nr; i += 32) {
         M4 root = loadM4(L.reward_root[i]);
-        if (!((S.env.reward_alive >> i) & 1u)) root = mul4(translation4(v3(1000, 1000, 1000)), root);
+        if (!((S.env.reward_alive[i >> 5] >> (i & 31)) & 1u)) {  // collected: Obstacles moves it by 1000, Collect by 500 (scenario_obstacles.cpp:224, scenario_collect.cpp:157)
+            const float far = L.scenario == MV_SCENARIO_COLLECT ? 500.0f : 1000.0f;
+            root = mul4(translation4(v3(far, far, far)), root);
+        }
         putInstance(inst[base + no + 3 * A + 2 * i], root, 3, L.reward_voxel[i][3]);
         putInstance(inst[base + no + 3 * A + 2 * i + 1], mul4(root, loadM4(L.cone_bottom_local)), 3, L.reward_voxel[i][3]);
     }
-    if (lane == 0) { counts[0] = base + no + 2 * A; counts[1] = base + no + 3 * A + 2 * nr; }
+    if (lane == 0) {
+        counts[0] = base + no + 2 * A; counts[1] = base + no + 3 * A + 2 * nr;
+        counts[2] = A; counts[3] = 0; counts[4] = 2 * nr; counts[5] = 0; counts[6] = 0; counts[7] = 0;  // capsules, spheres, cones, cylinders
+    }
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -688,10 +684,9 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     int ns = L->n_static, no = L->n_obj;
     if (!P.forceReset) {
         if (lane == 0) {
-            const uint32_t bytes = uint32_t(ns) * uint32_t(sizeof(MvBox)) + uint32_t(no) * uint32_t(sizeof(MvObject));
+            const uint32_t bytes = uint32_t(no) * uint32_t(sizeof(MvObject));
             mbarExpectTx(&S.mbar, bytes);
-            if (ns) bulkG2S(S.statics, L->statics, uint32_t(ns) * uint32_t(sizeof(MvBox)), &S.mbar);
-            if (no) bulkG2S(S.objects, gObjects, uint32_t(no) * uint32_t(sizeof(MvObject)), &S.mbar);
+            if (no) bulkG2S(S.objects, gObjects, bytes, &S.mbar);
         }
         __syncwarp();
         mbarWait(&S.mbar, 0);
@@ -702,7 +697,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
 
     if (!P.forceReset) {
         ColliderView cv;
-        cv.S = &S; cv.ns = ns; cv.no = no; cv.A = A; cv.cand = S.cand; cv.nc = 0;
+        cv.S = &S; cv.L = L; cv.ns = ns; cv.no = no; cv.A = A; cv.nc = 0;
 
         // ---- action phase (env.cpp:89-122)
         for (int i = 0; i < A; ++i) {
@@ -776,27 +771,42 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
             // the envelope the controller can move in within one step (0.2 step-up + jump, <= 55/15 fall, <= 5 push-outs)
             const V3 envLo = v3(k.pos.x - 3.0f, k.pos.y - 6.0f, k.pos.z - 3.0f), envHi = v3(k.pos.x + 3.0f, k.pos.y + 3.0f, k.pos.z + 3.0f);
             {
-                const int self = ns + no + i;
                 int nc = 0;
-                const int n = cv.count();
+                const int n = ns + no + A;
                 for (int base = 0; base < n; base += 32) {
                     const int ci = base + lane;
                     bool keep = false;
-                    if (ci < n && ci != self) {
-                        int kind; V3 c, h;
-                        if (cv.fetch(ci, kind, c, h)) {
-                            const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
-                                                     : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
-                            keep = !(envHi.x < c.x - ext.x || envLo.x > c.x + ext.x || envHi.y < c.y - ext.y || envLo.y > c.y + ext.y ||
-                                     envHi.z < c.z - ext.z || envLo.z > c.z + ext.z);
-                        }
+                    int kind = 0, agentIdx = 0;
+                    V3 c = v3(0, 0, 0), h = v3(0, 0, 0);
+                    if (ci < ns) {
+                        const MvBox &sb = L->statics[ci];  // global memory (L2 resident): scanned once per agent per step
+                        if (sb.flags & MV_SOLID) { keep = true; c = v3(sb.c[0], sb.c[1], sb.c[2]); h = v3(sb.h[0], sb.h[1], sb.h[2]); }
+                    } else if (ci < ns + no) {
+                        const MvObject &ob = S.objects[ci - ns];
+                        if (ob.enabled) { keep = true; c = v3(ob.col_c[0], ob.col_c[1], ob.col_c[2]); h = v3(ob.col_h[0], ob.col_h[1], ob.col_h[2]); }
+                    } else if (ci < n && ci - ns - no != i) {
+                        agentIdx = ci - ns - no;
+                        const MvAgent &oa = S.agents[agentIdx];
+                        keep = true; kind = 1; c = v3(oa.pos[0], oa.pos[1], oa.pos[2]);
+                    }
+                    if (keep) {
+                        // agents may move up to an envelope of their own within this step: give capsules the same slack
+                        const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
+                                                 : v3(2.0f * kCapsuleRadius + 3.0f, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius) + 6.0f, 2.0f * kCapsuleRadius + 3.0f);
+                        keep = !(envHi.x < c.x - ext.x || envLo.x > c.x + ext.x || envHi.y < c.y - ext.y || envLo.y > c.y + ext.y ||
+                                 envHi.z < c.z - ext.z || envLo.z > c.z + ext.z);
                     }
                     const unsigned m = __ballot_sync(FULL, keep);
-                    if (keep) S.cand[nc + __popc(m & ((1u << lane) - 1u))] = uint16_t(ci);
+                    const int slotC = nc + __popc(m & ((1u << lane) - 1u));
+                    if (keep && slotC < MV_MAX_CAND) {
+                        WarpShared::Cand &cd = S.cand[slotC];
+                        cd.c[0] = c.x; cd.c[1] = c.y; cd.c[2] = c.z; cd.h[0] = h.x; cd.h[1] = h.y; cd.h[2] = h.z; cd.kind = kind; cd.agent = agentIdx;
+                    }
                     nc += __popc(m);
                 }
+                if (nc > MV_MAX_CAND) { nc = MV_MAX_CAND; S.env.faults |= MV_FAULT_CAND_OVERFLOW; }
                 __syncwarp();
-                cv.cand = S.cand; cv.nc = nc;
+                cv.nc = nc;
             }
             kccPlayerStep(k, cv, ns + no + i, dt, P.k.max_slope_cos, lane);
             if (k.pos.x < envLo.x + 0.5f || k.pos.x > envHi.x - 0.5f || k.pos.y < envLo.y + 0.5f || k.pos.y > envHi.y - 0.5f || k.pos.z < envLo.z + 0.5f ||
@@ -931,7 +941,10 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 a.vvel = 0;
             };
             for (int i = 0; i < A; ++i)  // FallDetectionComponent::step
-                if (S.agents[i].object_t[13] < -20) resetAgent(i);
+                if (S.agents[i].object_t[13] < -20) {
+                    resetAgent(i);
+                    if (L->scenario == MV_SCENARIO_COLLECT) rewardAgent(MV_R_COLLECT_BAD, i, 1);  // agentFell (scenario_collect.cpp:214-218)
+                }
             if (L->scenario == MV_SCENARIO_TOWER) {
                 // shaping: carrying an object inside the building zone (scenario_tower_building.cpp:184-198)
                 for (int i = 0; i < A; ++i) {
@@ -944,6 +957,28 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                             a.visited_bz = 1;
                         }
                     }
+                }
+            } else if (L->scenario == MV_SCENARIO_COLLECT) {
+                // CollectScenario::step (scenario_collect.cpp:150-177)
+                for (int i = 0; i < A; ++i) {
+                    MvAgent &a = S.agents[i];
+                    int x, y, z;
+                    toVoxel(v3(a.object_t[12], a.object_t[13], a.object_t[14]), x, y, z);
+                    for (int r = 0; r < L->n_reward; ++r)
+                        if (((e.reward_alive[r >> 5] >> (r & 31)) & 1u) && L->reward_voxel[r][0] == x && L->reward_voxel[r][1] == y && L->reward_voxel[r][2] == z) {
+                            e.reward_alive[r >> 5] &= ~(1u << (r & 31));
+                            const bool good = L->reward_voxel[r][3] == 1;  // GREEN palette index
+                            if (good) { ++e.positive_collected; rewardTeam(MV_R_COLLECT_GOOD, i, 1); }
+                            else rewardTeam(MV_R_COLLECT_BAD, i, 1);
+                            if (e.positive_collected >= L->n_positive && !e.solved) {
+                                e.solved = 1;
+                                const float t = L->episode_len - 0.3f;  // doneWithTimer()
+                                e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
+                                rewardTeam(MV_R_COLLECT_ALL, i, 1);
+                            }
+                            const int g = gridIndex(*L, x, y, z);  // vg.grid.remove(voxel): the whole entry goes, incl. an object parked in it
+                            if (g >= 0) objGrid[g] = MV_NO_OBJECT;
+                        }
                 }
             } else if (L->scenario == MV_SCENARIO_OBSTACLES) {
                 // ObstaclesScenario::step (scenario_obstacles.cpp:202-238)
@@ -963,8 +998,8 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     } else if (planeBit(2, g))
                         resetAgent(i);  // agentTouchedLava
                     for (int r = 0; r < L->n_reward; ++r)
-                        if (((e.reward_alive >> r) & 1u) && L->reward_voxel[r][0] == x && L->reward_voxel[r][1] == y && L->reward_voxel[r][2] == z) {
-                            e.reward_alive &= ~(1u << r);
+                        if (((e.reward_alive[r >> 5] >> (r & 31)) & 1u) && L->reward_voxel[r][0] == x && L->reward_voxel[r][1] == y && L->reward_voxel[r][2] == z) {
+                            e.reward_alive[r >> 5] &= ~(1u << (r & 31));
                             rewardTeam(MV_R_OBST_EXTRA, i, 1);
                         }
                 }
@@ -1002,7 +1037,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     // ---- outputs of the finished step; VectorEnv::step captures trueObjective BEFORE reset and the rewards AFTER it (zeroed)
     if (!P.forceReset) {
         for (int i = lane; i < A; i += 32) {
-            if (doneFlag) P.trueObjectives[size_t(env) * A + i] = L->scenario == MV_SCENARIO_OBSTACLES ? float(S.env.solved) : float(S.env.highest_tower);
+            if (doneFlag) P.trueObjectives[size_t(env) * A + i] = L->scenario == MV_SCENARIO_TOWER ? float(S.env.highest_tower) : float(S.env.solved);
             P.rewards[size_t(env) * A + i] = doneFlag ? 0.0f : S.lastReward[i];
         }
         if (lane == 0) P.dones[env] = doneFlag ? 1 : 0;
@@ -1041,7 +1076,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     }
     __syncwarp();
 
-    writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 2, P.views + size_t(env) * A * 16, A, resetNow, lane);
+    writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
     for (int i = lane; i < A; i += 32) P.triCounts[size_t(env) * A + i] = 0;
 
     // ---- commit env + agents

@@ -156,8 +156,8 @@ int orc_get_level(void *p, int envIdx, int32_t *out, int cap) {
         for (int x : {c.x, c.y, c.z}) o.push_back(x);
     for (auto &c : env.agentSpawnPositions)
         for (int x : {int(c.x), int(c.y), int(c.z)}) o.push_back(x);
-    if (env.scenario == Env::S_OBSTACLES) {  // scenario extras: numPlatforms, reward-object voxels
-        o.push_back(env.numPlatforms);
+    if (env.scenario != Env::S_TOWER) {  // scenario extras: numPlatforms, reward-object voxels
+        o.push_back(env.scenario == Env::S_OBSTACLES ? env.numPlatforms : 0);
         o.push_back(int(env.rewardSpawnPositions.size()));
         for (auto &c : env.rewardSpawnPositions)
             for (int x : {c.x, c.y, c.z}) o.push_back(x);
@@ -193,14 +193,16 @@ int orc_get_state(void *p, int envIdx, float *out, int cap) {
                         env.colliders[size_t(ob.collider)].enabled ? 1.f : 0.f, 0.f})
             o.push_back(x);
     }
-    if (env.scenario == Env::S_OBSTACLES) {
-        uint32_t reached = 0, alive = 0;
+    if (env.scenario != Env::S_TOWER) {
+        uint32_t reached = 0, alive[3] = {0, 0, 0};
+        env.agentReachedExit.resize(size_t(env.numAgents), false);
         for (int i = 0; i < env.numAgents; ++i) reached |= env.agentReachedExit[size_t(i)] ? (1u << i) : 0u;
-        for (size_t r = 0; r < env.rewardSpawnPositions.size(); ++r) {
+        for (size_t r = 0; r < env.rewardSpawnPositions.size() && r < 96; ++r) {
             const Voxel *v = env.vg.grid.get(env.rewardSpawnPositions[r]);
-            if (v && v->rewardObject == int(r)) alive |= 1u << r;
+            if (v && v->rewardObject == int(r)) alive[r >> 5] |= 1u << (r & 31);
         }
-        o.push_back(float(env.solved)); o.push_back(float(reached)); o.push_back(float(alive));
+        o.push_back(float(env.solved)); o.push_back(float(reached));
+        for (int w = 0; w < 3; ++w) o.push_back(float(alive[w] & 0xffffffu)), o.push_back(float(alive[w] >> 24));
     }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(float));

@@ -100,7 +100,7 @@ using RewardShaping = std::map<std::string, float>;
 
 class Env {
 public:
-    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1 };
+    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2 };
     enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
 
     Env(const std::string &scenarioName, int numAgents, const FloatParams &custom) : numAgents(numAgents) {
@@ -111,6 +111,7 @@ public:
         floatParams["verticalLookLimitRad"] = 0.2f;
         floatParams["useUIRewardIndicators"] = 0.0f;
         if (n == "towerbuilding") scenario = S_TOWER;
+        else if (n == "collect") scenario = S_COLLECT;
         else if (n.rfind("obstacles", 0) == 0 || n == "test") {
             // ObstaclesScenario::initializeDefaultParameters + the registered variants (scenario_obstacles.hpp:48-270, init.hpp:33-56)
             scenario = S_OBSTACLES;
@@ -145,6 +146,8 @@ public:
     }
 
     RewardShaping defaultRewardShaping() const {
+        if (scenario == S_COLLECT)  // scenario_collect.hpp:42-50
+            return {{"collectSingleGood", 1.0f}, {"collectSingleBad", -1.0f}, {"collectAll", 5.0f}, {"collectAbyss", -0.5f}};
         if (scenario == S_OBSTACLES)  // scenario_obstacles.hpp:37-45,201-206
             return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f},
                     {"obstaclesAgentCarriedObjectToExit", onePlatformType ? 1.0f : 0.0f}};
@@ -165,10 +168,118 @@ public:
         auto sd = randRange(0, 1 << 30, rng);
         rng.seed((unsigned long)sd);
 
-        if (scenario == S_TOWER) towerReset(); else obstaclesReset();
+        if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else collectReset();
         spawnAgents();
-        if (scenario == S_TOWER) towerAddEpisodeDrawables(); else obstaclesAddEpisodeDrawables();
+        if (scenario == S_TOWER) towerAddEpisodeDrawables(); else if (scenario == S_OBSTACLES) obstaclesAddEpisodeDrawables(); else collectAddEpisodeDrawables();
         addAgentsAndUI();
+    }
+
+    // ---------------------------------------------------------------- Collect (scenario_collect.cpp:20-218)
+    void collectReset() {
+        solved = false;
+        vg.reset();
+        carryingObject.assign(size_t(numAgents), -1);
+        numPositiveRewards = positiveRewardsCollected = 0;
+        agentSpawnPositions.clear(); objectSpawnPositions.clear(); rewardSpawnPositions.clear();
+        static const std::vector<ColorRgb> landscapeColors = {LAYOUT_DEFAULT, VERY_LIGHT_GREEN, VERY_LIGHT_BLUE, VERY_LIGHT_GREY, VERY_LIGHT_ORANGE, GREY, DARK_GREY};
+        static const std::vector<ColorRgb> floorColors = {GREY, DARK_GREY, DARK_GREY};
+        auto landscapeColor = randomSample(landscapeColors, rng);
+        auto floorColor = randomSample(floorColors, rng);
+        constexpr int maxWidth = 42, maxLength = maxWidth;
+        const int width = randRange(8, maxWidth, rng);
+        const int length = randRange(8, maxWidth, rng);
+        std::vector<int> spawnHeight(size_t(length * width), 1);
+        double frequency = double(randRange(1, 100, rng)) / 10.0;
+        const std::int32_t octaves = randRange(1, 10, rng);
+        const std::uint32_t seed = randRange(0, 1000000000, rng);
+        const PerlinNoise perlin(seed);
+        const double fx = maxLength / frequency;
+        const double fz = maxWidth / frequency;
+        const int intensity = randRange(5, 18, rng);
+        const float groundLevel = frand(rng) * 0.5f + 0.2f;
+        for (int x = 1; x < length - 1; ++x)
+            for (int z = 1; z < width - 1; ++z) {
+                const double noise = perlin.accumulatedOctaveNoise2D_0_1(x / fx, z / fz, octaves);
+                const double yCoord = intensity * (noise - groundLevel);
+                if (yCoord >= 1) {
+                    const int yCoordRound = int(lround(yCoord));
+                    for (int y = yCoordRound; y >= 1; --y) vg.grid.set({x, y, z}, VoxelGridComponent::makeVoxel(VOXEL_SOLID | VOXEL_OPAQUE, TERRAIN_NONE, landscapeColor));
+                    spawnHeight[size_t(x * width + z)] = yCoordRound + 1;
+                }
+            }
+        for (int x = 0; x < length; ++x)
+            for (int z = 0; z < width; ++z) vg.grid.set({x, 0, z}, VoxelGridComponent::makeVoxel(VOXEL_SOLID | VOXEL_OPAQUE, TERRAIN_NONE, floorColor));
+        std::vector<VoxelCoords> spawnPositions;
+        for (int x = 1; x < length - 1; ++x)
+            for (int z = 1; z < width - 1; ++z) spawnPositions.emplace_back(x, spawnHeight[size_t(x * width + z)], z);
+        std::shuffle(spawnPositions.begin(), spawnPositions.end(), rng);
+        int offset = 0;
+        for (int i = 0; i < numAgents; ++i) agentSpawnPositions.emplace_back(float(spawnPositions[size_t(i)].x), float(spawnPositions[size_t(i)].y), float(spawnPositions[size_t(i)].z));
+        offset += numAgents;
+        int numRewards = randRange(1, int(lround(0.05 * width * length)) + 2, rng);
+        numRewards = std::min(numRewards, int(spawnPositions.size()) - offset);
+        int numRewardsPlacedRandomly = std::max(numRewards / 2, 1);
+        rewardSpawnPositions = std::vector<VoxelCoords>(spawnPositions.begin() + offset, spawnPositions.begin() + offset + numRewardsPlacedRandomly);
+        offset += numRewardsPlacedRandomly;
+        std::sort(spawnPositions.begin() + offset, spawnPositions.end(), [&](const VoxelCoords &a, const VoxelCoords &b) {
+            int heightA = spawnHeight[size_t(a.x * width + a.z)];
+            int heightB = spawnHeight[size_t(b.x * width + b.z)];
+            if (heightA != heightB) return heightA > heightB;
+            else return false;
+        });
+        rewardSpawnPositions.insert(rewardSpawnPositions.end(), spawnPositions.begin() + offset, spawnPositions.begin() + offset + (numRewards - numRewardsPlacedRandomly));
+        offset += numRewards - numRewardsPlacedRandomly;
+        std::shuffle(spawnPositions.begin() + offset, spawnPositions.end(), rng);
+        auto objectsMin = std::max(3, int(length * width * 0.04));
+        auto objectsMax = std::min(objectsMin + 1, int(lround(0.07 * width * length)) + 2);
+        const int numObjects = std::min(randRange(objectsMin, objectsMax, rng), int(spawnPositions.size()) - offset);
+        if (offset + numObjects < int(spawnPositions.size())) {
+            objectSpawnPositions = std::vector<VoxelCoords>(spawnPositions.begin() + offset, spawnPositions.begin() + offset + numObjects);
+            offset += numObjects;
+        }
+        agentInitialPositions = agentSpawnPositions;
+    }
+
+    void collectAddEpisodeDrawables() {  // scenario_collect.cpp:185-212
+        addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
+        addObjects(objectSpawnPositions);
+        for (const auto &pos : rewardSpawnPositions) {
+            RewardObject ro;
+            const Vec3 translation{float(pos.x) + 0.5f, float(pos.y) + 0.8f, float(pos.z) + 0.5f};
+            Voxel voxel;
+            if (frand(rng) > 0.3f) { voxel.reward = +1; ro.color = paletteIndex(GREEN); ++numPositiveRewards; }
+            else { voxel.reward = -1; ro.color = paletteIndex(RED); }
+            ro.bottomLocal = mul(mat4Translation({0.0f, -1.0f, 0.0f}), mul(mat4Identity(), mat4RotationX(180.0f * 3.14159265358979323846f / 180.0f)));
+            ro.root = mul(mat4Translation(translation), mul(mat4Scaling({0.17f, 0.45f, 0.17f}), mat4Identity()));
+            voxel.rewardObject = int(rewardObjects.size());
+            rewardObjects.push_back(ro);
+            vg.grid.set(pos, voxel);
+        }
+    }
+
+    void collectStep() {  // scenario_collect.cpp:145-178,214-218
+        for (int i = 0; i < numAgents; ++i)
+            if (currAction[i] & A_Interact) onInteractAction(i);
+        for (int i = 0; i < numAgents; ++i)  // FallDetectionComponent::step with the agentFell callback
+            if (translationOf(agents[i].objectT).y < -20) { resetAgent(i); rewardAgent("collectSingleBad", i, 1); }
+        for (int i = 0; i < numAgents; ++i) {
+            const Vec3 t = translationOf(agents[i].objectT);
+            VoxelCoords voxel = vg.grid.getCoords(t);
+            auto voxelPtr = vg.grid.get(voxel);
+            if (voxelPtr && voxelPtr->rewardObject >= 0) {
+                RewardObject &ro = rewardObjects[size_t(voxelPtr->rewardObject)];
+                ro.root = mul(mat4Translation({500, 500, 500}), ro.root);
+                if (voxelPtr->reward > 0) ++positiveRewardsCollected;
+                if (voxelPtr->reward > 0) rewardTeam("collectSingleGood", i, 1);
+                else if (voxelPtr->reward < 0) rewardTeam("collectSingleBad", i, 1);
+                if (positiveRewardsCollected >= numPositiveRewards && !solved) {
+                    solved = true;
+                    doneWithTimer();
+                    rewardTeam("collectAll", i, 1);
+                }
+                vg.grid.remove(voxel);
+            }
+        }
     }
 
     // ---------------------------------------------------------------- Obstacles (scenario_obstacles.cpp:51-278)
@@ -521,7 +632,7 @@ public:
         }
         for (auto &a : agents) a.updateTransform();
 
-        if (scenario == S_TOWER) towerStep(); else obstaclesStep();
+        if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else collectStep();
 
         currEpisodeSec += lastFrameDurationSec;
         updateUI();
@@ -532,12 +643,13 @@ public:
     }
 
     float episodeLengthSec() const {
+        if (scenario == S_COLLECT) return floatParams.at("episodeLengthSec") + 2.0f * rewardSpawnPositions.size();  // scenario_collect.hpp:52-56
         if (scenario == S_OBSTACLES)  // scenario_obstacles.cpp:262-266
             return std::max(floatParams.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objectSpawnPositions.size()) * 1);
         return floatParams.at("episodeLengthSec") + 4.0f * float(objectSpawnPositions.size());  // scenario_tower_building.cpp:263-266
     }
     float remainingTimeFraction() const { const float len = episodeLengthSec(); return std::max(0.0f, (len - currEpisodeSec) / len); }  // env.hpp:224-228
-    float trueObjective(int) const { return scenario == S_OBSTACLES ? float(solved) : float(highestTower); }
+    float trueObjective(int) const { return scenario == S_TOWER ? float(highestTower) : float(solved); }
     void doneWithTimer(float remaining = 0.3f) { currEpisodeSec = std::max(currEpisodeSec, episodeLengthSec() - remaining); }
 
     void updateUI() {  // scenario_default.hpp:164-186 ; UIElement::rescale :33-37
@@ -763,6 +875,7 @@ public:
     bool solved = false;
     int numPlatforms = 0;
     struct RewardObject { Mat4 root, bottomLocal; int color; };
+    int numPositiveRewards = 0, positiveRewardsCollected = 0;  // Collect
     std::vector<RewardObject> rewardObjects;
 
     struct TowerAgentState { bool pickedUpObject = false, visitedBuildingZoneWithObject = false; };

@@ -237,3 +237,43 @@ def test_obstacles_trajectory_parity(built, scenario, A, policy):
         assert total > 0 and ndone > 0, "the Test variant should be solved by walking forward (reward %.2f, dones %d)" % (total, ndone)
     assert g.faults() == 0
     o.close(); g.close()
+
+
+# ------------------------------------------------------------------------------------------------ Collect (BASELINE config 4: 4 agents / env)
+def test_collect_reset_parity(built):
+    E, A = 6, 4
+    o, g = _pair("Collect", E, A, 21)
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.voxels(e), g.voxels(e)), "voxels %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("policy", ["purposeful", "heads"])
+def test_collect_trajectory_parity(built, policy):
+    """multi-agent Perlin landscapes: agent-agent capsule collisions, reward diamonds (+1/-1), falling off the edge
+    (teleport + penalty), collectAll + doneWithTimer"""
+    E, A, steps = 8, 4, 700
+    o, g = _pair("Collect", E, A, 99)
+    rng = np.random.default_rng(8)
+    total, ndone = 0.0, 0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t) if policy == "purposeful" else helpers.random_head_actions(rng, E * A)
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        total += float(np.abs(ro).sum()); ndone += int(o.dones().sum())
+        if t % 50 == 0 or t == steps - 1 or o.dones().any():
+            _assert_same_state(o, g, E, "step %d" % t)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+    if policy == "purposeful":
+        assert total > 0.0
+    assert g.faults() == 0
+    o.close(); g.close()
