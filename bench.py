@@ -184,7 +184,7 @@ def main():
     ptr0 = acts_dev.data_ptr()
 
     def dev_step(t):
-        eng.step_device(ptr0 + t * step_bytes)
+        eng.step_device(ptr0 + t * step_bytes)  # asynchronous: the timed region ends with barrier() = device synchronize
 
     def host_step(t):
         eng.step(acts_host[t])
@@ -196,6 +196,7 @@ def main():
     sampler.start()
     l0 = eng.kernel_launches()
     ms = timed(dev_step, K, Wm)
+    eng.sync()
     launches = eng.kernel_launches() - l0
     clocks = sampler.stop()
     value = N * world * K / (ms / 1e3)
@@ -215,11 +216,12 @@ def main():
         with torch.cuda.stream(stream):
             flush.zero_()
         dev_step(Wm + (t % K))
+        eng.sync()
         s_ms, r_ms = eng.last_kernel_ms()
         stp.append(s_ms); ras.append(r_ms)
     ras_ms, stp_ms = float(np.mean(ras[10:])), float(np.mean(stp[10:]))
     achieved = N * OBS_BYTES / (ras_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "mvr::rasterKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": "mvr::geomKernel + mvr::tileKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": N * OBS_BYTES, "kernel_ms": ras_ms, "step_kernel_ms": stp_ms,
                 "note": "obs-write bytes / rasteriser duration; the kernel is FP32-issue bound (per-pixel Phong shading), see DESIGN.md"}
     faults = eng.faults()

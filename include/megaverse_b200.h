@@ -68,13 +68,23 @@ int mv_get_reward_shaping(mv_handle h, int env, int agent, const char **keys, fl
 int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *keys, const float *vals, int n);
 
 /* options: "depth" (0/1, before first reset), "tri_cap" (rasteriser triangle capacity), "obs_to_host" (0/1: whether
- * mv_step copies the observation tensor to host memory; 1 by default) */
+ * mv_step delivers the observation tensor to host memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps
+ * let the rasteriser store rows straight into the pinned host buffer instead of copying afterwards; the HBM copy returned
+ * by mv_obs_device is then only refreshed by mv_step_device), "fast_shading" (0/1, default 1: +-1 LSB fragment maths) */
 int mv_set_option(mv_handle h, const char *key, int value);
 
 /* Device-resident path: the caller's consumer reads the tensors in HBM.
  * mv_step_device: like mv_step but takes the action masks from DEVICE memory (NULL = the engine's own buffer, see
  * mv_actions_device) and leaves the observation tensor on the device; rewards/dones still land on the host. */
 int mv_step_device(mv_handle h, const int32_t *d_masks);
+/* mv_step_device is ASYNCHRONOUS: it returns after enqueueing the step on the engine stream (device tensors are valid in
+ * stream order).  mv_sync waits for everything enqueued and publishes the last step's rewards/dones/true objectives to the
+ * host pointers.  Episode bookkeeping lags the device by two steps on this path, so it needs episodes of >= 4 steps
+ * (always true with the scenarios' own parameters); a violation raises MV_FAULT_LEVEL_NOT_READY in mv_faults. */
+int mv_sync(mv_handle h);
+/* after mv_step_device steps: waits, then copies the device obs (and depth, when enabled) into the host buffers that
+ * mv_obs_host / mv_depth_host return */
+int mv_fetch_obs(mv_handle h);
 int mv_actions_device(mv_handle h, int32_t **d_masks);
 int mv_obs_device(mv_handle h, uint8_t **d_obs);
 int mv_depth_device(mv_handle h, float **d_depth);
@@ -108,6 +118,9 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
                             const float *param_vals, int nparams, int32_t *out, int cap);
 /* libstdc++ unordered_set iteration-order emulation (bzset.h): ops[i] = {op(0 insert,1 erase,2 clear), x, y, z};
  * writes the final iteration order as xyz triples, returns the element count */
+/* per-env cycle stamps of the step kernel's phases: out = uint32[E][16] (0 staged, 1 actions, 2 candidate list, 3 controllers,
+ * 4 transforms, 5 scenario, 6 outputs/reset, 7 instance list, 8 commit, 12 candidate count); enable=1 arms it, 0 frees it */
+int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);
 
 #ifdef __cplusplus

@@ -42,7 +42,8 @@ def build_lib(force=False, verbose=False):
     if not force and _newer(LIB, srcs):
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "levelgen.cpp")]
+    extra = os.environ.get("MV_NVCC_EXTRA", "").split()  # developer switches, e.g. -DMV_KCC_COUNTERS
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "levelgen.cpp")]
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB
 

@@ -29,7 +29,7 @@ def lib():
         L.mv_create.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, C.POINTER(C.c_char_p), C.POINTER(cf), ci, C.POINTER(vp)]
         L.mv_last_error.argtypes = [vp]
         L.mv_last_error.restype = C.c_char_p
-        for name in ("mv_reset", "mv_step", "mv_close"):
+        for name in ("mv_reset", "mv_step", "mv_close", "mv_sync", "mv_fetch_obs"):
             getattr(L, name).argtypes = [vp]
         L.mv_seed.argtypes = [vp, ci]
         L.mv_seed_env.argtypes = [vp, ci, ci]
@@ -58,9 +58,9 @@ def lib():
 EXPORTS = [
     "mv_create", "mv_last_error", "mv_seed", "mv_seed_env", "mv_reset", "mv_set_actions", "mv_encode_action", "mv_step", "mv_obs_host", "mv_depth_host",
     "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device",
-    "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
+    "mv_sync", "mv_fetch_obs", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
-    "mv_debug_render_instances", "mv_debug_bzset", "mv_debug_generate_level",
+    "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_bzset", "mv_debug_generate_level",
 ]
 
 
@@ -109,6 +109,12 @@ class Engine:
 
     def step_device(self, d_masks_ptr=None):
         self._ck(lib().mv_step_device(self._h, C.c_void_p(d_masks_ptr) if d_masks_ptr else None))
+
+    def sync(self):
+        self._ck(lib().mv_sync(self._h))
+
+    def fetch_obs(self):
+        self._ck(lib().mv_fetch_obs(self._h))
 
     def _host(self, fn, shape, dtype):
         p = C.c_void_p()
@@ -163,6 +169,12 @@ class Engine:
         n = C.c_int64()
         self._ck(lib().mv_kernel_launches(self._h, C.byref(n)))
         return n.value
+
+    def step_profile(self, enable=True, read=True):
+        out = np.zeros((self.E, 16), dtype=np.uint32)
+        lib().mv_debug_step_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._ck(lib().mv_debug_step_profile(self._h, out.ctypes.data if read else None, 1 if enable else 0))
+        return out
 
     def last_kernel_ms(self):
         out = (C.c_float * 2)()

@@ -115,8 +115,10 @@ struct mv_engine {
 
     int gridCells = 0, gridWords = 0;
     int triCap = 1024, chunkViews = 0;
-    std::atomic<int> maxItemsSeen{0};
+    std::atomic<int> maxItemsSeen{0}, maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
+    bool zeroCopy = true;  // host-facing steps: the tile kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
+    bool rasterToHost = false;
     int numSMs = 148;
     int tune = getenv("MV_TUNE") ? atoi(getenv("MV_TUNE")) : 0;
     MvConsts consts{};
@@ -160,6 +162,12 @@ struct mv_engine {
     PinBuf<float> h_depth;
     PinBuf<int32_t> h_faults;
 
+    // mv_step_device pipeline: results of step k are consumed by the host while steps k+1, k+2 already run
+    struct Pending { bool valid = false; cudaEvent_t ev = nullptr; PinBuf<float> rewards, trueObj; PinBuf<uint8_t> dones; };
+    Pending ring[3];
+    DevBuf<uint32_t> d_prof;  // mv_debug_step_profile only
+    uint64_t asyncSteps = 0;
+
     std::vector<int> hostSlot, hostEpisode;   // mirrors of the device's live slot / episode index
     std::vector<int> levelWords;              // [E*2] words of the bit planes a staged level uses
     std::vector<int> pendingUpload;           // env ids whose freshly generated next level waits for H2D
@@ -185,6 +193,8 @@ struct mv_engine {
                 const int items = boxes * 6 + A * 128 + 2 * out.level.n_reward * 12;  // capsule 128 triangles, cone 12
                 int cur = maxItemsSeen.load();
                 while (items > cur && !maxItemsSeen.compare_exchange_weak(cur, items)) {}
+                int curO = maxObjSeen.load();
+                while (out.level.n_obj > curO && !maxObjSeen.compare_exchange_weak(curO, out.level.n_obj)) {}
             }
             std::memcpy(&h_levels.p[size_t(e) * 2 + s], &out.level, sizeof(MvLevel));
             uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * 3 * gridWords;  // planes: solid, exit, lava
@@ -229,6 +239,8 @@ struct mv_engine {
         sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
         sp.triCounts = d_triCounts.p;
+        sp.prof = d_prof.p;
+        sp.maxObj = std::min(int(MV_MAX_OBJECTS), maxObjSeen.load());
         sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
         sp.k = consts;
         const int warpsPerBlock = 2;
@@ -249,7 +261,8 @@ struct mv_engine {
     int launchRaster() {
         mvr::RasterParams rp;
         rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = MV_MAX_INSTANCES;
-        rp.obs = d_obs.p; rp.depth = wantDepth ? d_depth.p : nullptr; rp.faults = d_faults.p;
+        // pinned allocations are mapped into the device address space (UVA), so the kernel can store through the host pointer
+        rp.obs = rasterToHost ? h_obs.p : d_obs.p; rp.depth = wantDepth ? (rasterToHost ? h_depth.p : d_depth.p) : nullptr; rp.faults = d_faults.p;
         rp.cover = d_cover.p; rp.shade = d_shade.p; rp.bbox = d_bbox.p; rp.triCounts = d_triCounts.p;
         rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.tune = tune;
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
@@ -292,7 +305,7 @@ struct mv_engine {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        if (copyObs) {
+        if (copyObs && !rasterToHost) {
             MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
@@ -302,14 +315,65 @@ struct mv_engine {
         return MV_OK;
     }
 
-    int stepCommon(const int32_t *dActions, bool copyObs) {
-        if (!didReset) { setError("mv_step before mv_reset"); return MV_ERR_STATE; }
+    // consume one finished asynchronous step: publish its host copies, flip mirrors, schedule level generation
+    int retire(Pending &p) {
+        if (!p.valid) return MV_OK;
+        MV_CUDA(cudaEventSynchronize(p.ev));
+        std::memcpy(h_rewards.p, p.rewards.p, sizeof(float) * N);
+        std::memcpy(h_dones.p, p.dones.p, E);
+        std::memcpy(h_trueObj.p, p.trueObj.p, sizeof(float) * N);
+        p.valid = false;
+        afterFlip(h_dones.p);
+        return MV_OK;
+    }
+    int drain() {
+        for (int k = 0; k < 3; ++k) {  // oldest first
+            const int rc = retire(ring[(asyncSteps + k) % 3]);
+            if (rc) return rc;
+        }
+        return MV_OK;
+    }
+    // asynchronous device-resident step: returns after enqueueing.  Episode bookkeeping lags two steps, which is safe
+    // because an env cannot finish twice within four steps (doneWithTimer leaves 0.3 s = 4.5 steps, scenario.hpp:114-117)
+    int stepAsync(const int32_t *dActions) {
+        if (!didReset) { setError("mv_step_device before mv_reset"); return MV_ERR_STATE; }
+        Pending &slotP = ring[asyncSteps % 3];
+        // levels generated since the previous call go up first (done at step k-3 -> retired at call k-1 -> uploaded ahead
+        // of kernel k; that env cannot flip again before step k+1), then step k-2 is retired and its regeneration jobs
+        // run on the worker pool while this call's kernels are enqueued
         int rc = flushUploads();
+        if (rc) return rc;
+        rc = retire(ring[(asyncSteps + 1) % 3]);
+        if (rc) return rc;
+        rc = retire(slotP);  // only if the ring wrapped without retiring
         if (rc) return rc;
         if (rtableDirty) {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
+        rasterToHost = false;
+        rc = launchStep(dActions, false);
+        if (rc) return rc;
+        MV_CUDA(cudaMemcpyAsync(slotP.rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
+        MV_CUDA(cudaMemcpyAsync(slotP.dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
+        MV_CUDA(cudaMemcpyAsync(slotP.trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
+        MV_CUDA(cudaEventRecord(slotP.ev, stream));
+        slotP.valid = true;
+        ++asyncSteps;
+        return MV_OK;
+    }
+
+    int stepCommon(const int32_t *dActions, bool copyObs) {
+        if (!didReset) { setError("mv_step before mv_reset"); return MV_ERR_STATE; }
+        int rc = drain();
+        if (rc) return rc;
+        rc = flushUploads();
+        if (rc) return rc;
+        if (rtableDirty) {
+            MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
+            rtableDirty = false;
+        }
+        rasterToHost = copyObs && zeroCopy;
         rc = launchStep(dActions, false);
         if (rc) return rc;
         rc = finishStep(copyObs);
@@ -322,10 +386,11 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_bbox.free();
+        d_prof.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_bbox.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        for (auto &p : ring) { if (p.ev) { cudaEventDestroy(p.ev); p.ev = nullptr; } p.rewards.free(); p.trueObj.free(); p.dones.free(); }
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 };
@@ -424,6 +489,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
          ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults");
+    for (auto &p : e->ring) ok = ok && ck(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming), "event") && ck(p.rewards.alloc(N), "ring") && ck(p.trueObj.alloc(N), "ring") && ck(p.dones.alloc(E), "ring");
     if (!ok) return fail(MV_ERR_CUDA);
     std::memset(e->h_actions.p, 0, sizeof(int32_t) * N);
     std::memset(e->h_rewards.p, 0, sizeof(float) * N);
@@ -460,6 +526,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         return h->allocTriScratch();
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
+    if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
     if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
     h->setError("unknown option " + k);
     return MV_ERR_ARG;
@@ -501,6 +568,7 @@ int mv_reset(mv_handle h) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     ensureMirrors(h);
+    if (h->didReset) { const int rcd = h->drain(); if (rcd) return rcd; }
     if (!h->didReset) {
         // initial device state: slot 1 / episode -1 so that the forced flip lands on (slot 0, episode 0)
         std::vector<MvEnvState> init(size_t(h->E));
@@ -516,6 +584,7 @@ int mv_reset(mv_handle h) {
         if (cudaMemcpyAsync(h->d_rtable.p, h->h_rtable.p, sizeof(float) * h->N * MV_R_COUNT, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("rtable upload failed"); return MV_ERR_CUDA; }
         h->rtableDirty = false;
     }
+    h->rasterToHost = h->obsToHost && h->zeroCopy;
     rc = h->launchStep(h->d_actions.p, true);
     if (rc) return rc;
     rc = h->finishStep(h->obsToHost);
@@ -552,7 +621,43 @@ int mv_step(mv_handle h) {
 int mv_step_device(mv_handle h, const int32_t *d_masks) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
-    return h->stepCommon(d_masks ? d_masks : h->d_actions.p, false);
+    return h->stepAsync(d_masks ? d_masks : h->d_actions.p);
+}
+
+int mv_fetch_obs(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    const int rc = h->drain();
+    if (rc) return rc;
+    const size_t px = size_t(h->N) * h->W * h->H;
+    if (cudaMemcpyAsync(h->h_obs.p, h->d_obs.p, px * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { h->setError("obs download failed"); return MV_ERR_CUDA; }
+    if (h->wantDepth && cudaMemcpyAsync(h->h_depth.p, h->d_depth.p, px * sizeof(float), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { h->setError("depth download failed"); return MV_ERR_CUDA; }
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->setError("stream sync failed"); return MV_ERR_CUDA; }
+    return MV_OK;
+}
+
+int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return MV_ERR_CUDA;
+    cudaStreamSynchronize(h->stream);
+    if (enable && !h->d_prof.p) {
+        if (h->d_prof.alloc(size_t(h->E) * 16) != cudaSuccess) { h->setError("profile buffer allocation failed"); return MV_ERR_CUDA; }
+        cudaMemset(h->d_prof.p, 0, sizeof(uint32_t) * size_t(h->E) * 16);
+    }
+    if (out && h->d_prof.p && cudaMemcpy(out, h->d_prof.p, sizeof(uint32_t) * size_t(h->E) * 16, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (!enable) h->d_prof.free();
+    return MV_OK;
+}
+
+int mv_sync(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    const int rc = h->drain();
+    if (rc) return rc;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->setError("stream sync failed"); return MV_ERR_CUDA; }
+    cudaEventElapsedTime(&h->lastMs[0], h->ev[0], h->ev[1]);
+    cudaEventElapsedTime(&h->lastMs[1], h->ev[1], h->ev[2]);
+    return MV_OK;
 }
 
 int mv_obs_host(mv_handle h, const uint8_t **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_obs.p; return MV_OK; }
@@ -592,6 +697,7 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
 
 int mv_faults(mv_handle h, int32_t *out) {
     if (!h || !out) return MV_ERR_ARG;
+    if (h->stream) cudaStreamSynchronize(h->stream);
     std::vector<MvEnvState> st(size_t(h->E));
     if (cudaMemcpy(st.data(), h->d_envs.p, sizeof(MvEnvState) * st.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     if (cudaMemcpy(h->h_faults.p, h->d_faults.p, sizeof(int32_t) * h->E, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
@@ -627,7 +733,7 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
         // invert centre/half back to inclusive voxel bounds: min = c - h, max = c + h - 1
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
-        o.push_back(b.flags); o.push_back(int(pal[b.color]));
+        o.push_back(b.flags & 255); o.push_back(int(pal[b.color]));
     }
     for (int i = 0; i < L.n_terrain; ++i) {
         o.push_back(L.terrain[i].type);
@@ -833,7 +939,7 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
         const MvBox &b = L.statics[i];
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
-        o.push_back(b.flags); o.push_back(int(kPaletteRgb[b.color]));
+        o.push_back(b.flags & 255); o.push_back(int(kPaletteRgb[b.color]));
     }
     for (int i = 0; i < L.n_terrain; ++i) {
         o.push_back(L.terrain[i].type);

@@ -217,8 +217,8 @@ int rewardSlot(int scenario, const std::string &key) {
 int gridCapacity(int scenario) {
     // TowerBuilding rooms are at most 29 x (6+18) x 24; Obstacles chains of up to 7 platforms (+ transitions, start, exit)
     // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
-    // Collect: <= 41 x 41 landscape, heights <= 17, 3 cells of margin (objects can be put down beyond the edge), y from -30
-    const int cells = scenario == MV_SCENARIO_TOWER ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 48 * 64 * 48 : 512 * 1024);
+    // Collect: <= 41 x 41 landscape, heights <= 18, 16 cells of margin (objects can be put down beyond the edge), y from -30
+    const int cells = scenario == MV_SCENARIO_TOWER ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
     return ((cells + 127) / 128) * 128;
 }
 
@@ -239,7 +239,10 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
         case MV_SCENARIO_COLLECT: generateCollect(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
-    const MvLevel &L = out.level;
+    MvLevel &L = out.level;
+    L.n_opaque = 0;
+    for (int i = 0; i < L.n_static; ++i)
+        if (L.statics[i].flags & MV_OPAQUE) L.statics[i].flags |= (L.n_opaque++) << 8;
     if (L.grid_dim[0] * L.grid_dim[1] * L.grid_dim[2] > gridCells) throw std::runtime_error("level exceeds the dense grid capacity");
 }
 
@@ -524,8 +527,10 @@ void LevelGenerator::generateCollect(LevelOut &out) {
     for (const auto &kv : grid) maxY = std::max(maxY, voxUnkey(kv.first).y);
     for (auto &c : objs) maxY = std::max(maxY, c.y);
     for (auto &c : rewards) maxY = std::max(maxY, c.y);
-    L.grid_org[0] = -3; L.grid_org[1] = -30; L.grid_org[2] = -3;
-    L.grid_dim[0] = length + 6; L.grid_dim[1] = maxY + 30 + 1 + 12; L.grid_dim[2] = width + 6;
+    // margin: an agent that walks off the edge keeps its horizontal speed while it falls to y = -20 and can still put
+    // an object down out there (it sinks to y = -30)
+    L.grid_org[0] = -16; L.grid_org[1] = -30; L.grid_org[2] = -16;
+    L.grid_dim[0] = length + 32; L.grid_dim[1] = maxY + 30 + 1 + 12; L.grid_dim[2] = width + 32;
     fillPlanes(out, &grid);
 }
 

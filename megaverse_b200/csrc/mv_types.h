@@ -73,7 +73,7 @@
 struct MvBox {       // static layout box: drawable (OPAQUE) and/or collider (SOLID)
     float c[3];      // centre  = ((min+max)/2 + 0.5) * voxelSize        (layout_utils.cpp:30-34)
     float h[3];      // half extents = (max-min+1)/2 * voxelSize          (layout_utils.cpp:24-28)
-    int32_t flags;   // MV_SOLID | MV_OPAQUE
+    int32_t flags;   // MV_SOLID | MV_OPAQUE | (instance slot among the opaque boxes << 8)
     int32_t color;   // palette index
 };
 
@@ -95,7 +95,8 @@ struct MvLevel {
     float look_limit;              // floatParams["verticalLookLimitRad"]
     int32_t n_reward;              // Obstacles / Collect: reward diamonds
     int32_t n_positive;            // Collect: numPositiveRewards
-    int32_t pad0[2];               // statics[] must start 16-byte aligned
+    int32_t n_opaque;              // number of drawable static boxes (their instance slot is flags >> 8)
+    int32_t pad0[1];               // statics[] must start 16-byte aligned
     MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
     MvTerrain terrain[MV_MAX_TERRAIN];
     int16_t obj_voxel[MV_MAX_OBJECTS][4];  // x,y,z,color

@@ -56,6 +56,8 @@ struct StepParams {
     float *trueObjectives;       // [E*A]
     int E, A, gridCells, gridWords;
     int forceReset;              // mv_reset(): re-initialise every env from its live level slot, no physics
+    int maxObj;                  // upper bound of n_obj over the live and staged levels (sizes the staging copy)
+    uint32_t *prof;              // optional [E][16] per-phase cycle stamps (mv_debug_step_profile); nullptr in production
     MvConsts k;
 };
 
@@ -68,10 +70,14 @@ struct WarpShared {  // one per warp
     int objDirty[MV_MAX_AGENTS * 2];
     int nDirty;
     int doneFlag;
+    uint32_t rewardDirty[3];  // reward objects collected this step (their instances need rewriting)
     // this agent's collision candidates for the current step, ascending collider index: boxes are copied here (static
     // layout boxes straight from the level in global memory, movable objects from the staged records), agents are looked
     // up live because they move within the step
     struct Cand { float c[3]; float h[3]; int32_t kind; int32_t agent; } cand[MV_MAX_CAND];
+    alignas(16) float mtx[8][16];                // cooperative 4x4 products: one element per lane (writeInstances)
+    alignas(8) unsigned long long sweepKey[32];  // warpSweep: per live candidate, min over features of (t bits << 32 | feature)
+    uint8_t sweepList[32];                       // warpSweep: lanes of the candidates that passed the swept-bounds cull
 };
 
 // ---------------------------------------------------------------- TMA (1-D bulk async copy) helpers
@@ -122,69 +128,76 @@ __device__ __forceinline__ float pointBoxDistance(V3 o, V3 H, V3 &n) {
     return d;
 }
 
-__device__ bool rayRoundedBox(V3 o, V3 d, V3 H, float rho, float &tOut, V3 &nOut) {
+// Ray (capsule-axis midpoint path) against the box inflated by rho, split into its 23 boundary features so that the
+// warp can test (candidate, feature) pairs in parallel: f 0..2 = the face pair of axis f (the one facing the ray),
+// 3..14 = the 12 edge cylinders (axis k, then the two signs), 15..22 = the 8 corner spheres.  The closest hit of the
+// whole shape is the minimum over the features with ties going to the lowest f -- the order a serial scan that only
+// accepts strictly closer hits would produce.  A start point already inside the inflated shape is reported by f == 0
+// alone (t = 0 along the separating normal, only when moving inwards).
+constexpr int kBoxFeatures = 23;
+__device__ bool rayRoundedBoxFeatureOutside(V3 o, V3 d, V3 H, float rho, int f, float &tOut, V3 &nOut);
+__device__ __forceinline__ bool rayRoundedBoxFeature(V3 o, V3 d, V3 H, float rho, int f, float &tOut, V3 &nOut) {
     V3 n0;
     const float d0 = pointBoxDistance(o, H, n0);
     if (d0 - rho <= 0.0f) {
-        if (dot(d, n0) < -kSimdEpsilon) { tOut = 0.0f; nOut = n0; return true; }
+        if (f == 0 && dot(d, n0) < -kSimdEpsilon) { tOut = 0.0f; nOut = n0; return true; }
         return false;
     }
-    float best = 2.0f;
-    V3 bestN = v3(0, 0, 0);
-    for (int i = 0; i < 3; ++i) {  // 6 faces
+    return rayRoundedBoxFeatureOutside(o, d, H, rho, f, tOut, nOut);
+}
+// the feature tests proper, for a start point known to lie outside the inflated shape
+__device__ bool rayRoundedBoxFeatureOutside(V3 o, V3 d, V3 H, float rho, int f, float &tOut, V3 &nOut) {
+    if (f < 3) {
+        const int i = f;
         const float di = comp(d, i);
-        if (di == 0.0f) continue;
+        if (di == 0.0f) return false;
         const float s = di < 0.0f ? 1.0f : -1.0f;
         const float t = (s * (comp(H, i) + rho) - comp(o, i)) / di;
-        if (t < 0.0f || t > 1.0f || t >= best) continue;
+        if (t < 0.0f || t > 1.0f) return false;
         const int j = (i + 1) % 3, k = (i + 2) % 3;
         const float qj = comp(o, j) + t * comp(d, j), qk = comp(o, k) + t * comp(d, k);
-        if (fabsf(qj) <= comp(H, j) && fabsf(qk) <= comp(H, k)) { best = t; bestN = v3(0, 0, 0); setComp(bestN, i, s); }
+        if (!(fabsf(qj) <= comp(H, j) && fabsf(qk) <= comp(H, k))) return false;
+        tOut = t; nOut = v3(0, 0, 0); setComp(nOut, i, s);
+        return true;
     }
-    for (int k = 0; k < 3; ++k) {  // 12 edges
+    if (f < 15) {
+        const int e = f - 3, k = e >> 2;
+        const float si = (e & 2) ? 1.0f : -1.0f, sj = (e & 1) ? 1.0f : -1.0f;
         const int i = (k + 1) % 3, j = (k + 2) % 3;
         const float di = comp(d, i), dj = comp(d, j);
         const float a = di * di + dj * dj;
-        if (a == 0.0f) continue;
-        for (int si = -1; si <= 1; si += 2)
-            for (int sj = -1; sj <= 1; sj += 2) {
-                const float oi = comp(o, i) - si * comp(H, i), oj = comp(o, j) - sj * comp(H, j);
-                const float b = oi * di + oj * dj;
-                const float c = oi * oi + oj * oj - rho * rho;
-                const float disc = b * b - a * c;
-                if (disc < 0.0f) continue;
-                const float t = (-b - sqrtf(disc)) / a;
-                if (t < 0.0f || t > 1.0f || t >= best) continue;
-                const float qi = oi + t * di, qj = oj + t * dj, qk = comp(o, k) + t * comp(d, k);
-                if (si * qi >= 0.0f && sj * qj >= 0.0f && fabsf(qk) <= comp(H, k)) {
-                    best = t;
-                    bestN = v3(0, 0, 0);
-                    setComp(bestN, i, qi / rho);
-                    setComp(bestN, j, qj / rho);
-                }
-            }
+        if (a == 0.0f) return false;
+        const float oi = comp(o, i) - si * comp(H, i), oj = comp(o, j) - sj * comp(H, j);
+        const float b = oi * di + oj * dj;
+        const float c = oi * oi + oj * oj - rho * rho;
+        const float disc = b * b - a * c;
+        if (disc < 0.0f) return false;
+        const float t = (-b - sqrtf(disc)) / a;
+        if (t < 0.0f || t > 1.0f) return false;
+        const float qi = oi + t * di, qj = oj + t * dj, qk = comp(o, k) + t * comp(d, k);
+        if (!(si * qi >= 0.0f && sj * qj >= 0.0f && fabsf(qk) <= comp(H, k))) return false;
+        tOut = t; nOut = v3(0, 0, 0);
+        setComp(nOut, i, qi / rho);
+        setComp(nOut, j, qj / rho);
+        return true;
     }
-    {  // 8 corners
+    {
+        const int e = f - 15;
+        const float sx = (e & 4) ? 1.0f : -1.0f, sy = (e & 2) ? 1.0f : -1.0f, sz = (e & 1) ? 1.0f : -1.0f;
         const float a = dot(d, d);
-        if (a != 0.0f)
-            for (int sx = -1; sx <= 1; sx += 2)
-                for (int sy = -1; sy <= 1; sy += 2)
-                    for (int sz = -1; sz <= 1; sz += 2) {
-                        const V3 oc = v3(o.x - sx * H.x, o.y - sy * H.y, o.z - sz * H.z);
-                        const float b = dot(oc, d);
-                        const float c = dot(oc, oc) - rho * rho;
-                        const float disc = b * b - a * c;
-                        if (disc < 0.0f) continue;
-                        const float t = (-b - sqrtf(disc)) / a;
-                        if (t < 0.0f || t > 1.0f || t >= best) continue;
-                        const V3 q = oc + d * t;
-                        if (sx * q.x >= 0.0f && sy * q.y >= 0.0f && sz * q.z >= 0.0f) { best = t; bestN = q * (1.0f / rho); }
-                    }
+        if (a == 0.0f) return false;
+        const V3 oc = v3(o.x - sx * H.x, o.y - sy * H.y, o.z - sz * H.z);
+        const float b = dot(oc, d);
+        const float c = dot(oc, oc) - rho * rho;
+        const float disc = b * b - a * c;
+        if (disc < 0.0f) return false;
+        const float t = (-b - sqrtf(disc)) / a;
+        if (t < 0.0f || t > 1.0f) return false;
+        const V3 q = oc + d * t;
+        if (!(sx * q.x >= 0.0f && sy * q.y >= 0.0f && sz * q.z >= 0.0f)) return false;
+        tOut = t; nOut = q * (1.0f / rho);
+        return true;
     }
-    if (best > 1.0f) return false;
-    tOut = best;
-    nOut = bestN;
-    return true;
 }
 
 __device__ __forceinline__ float pointSegDistance(V3 o, float L, V3 &n) {
@@ -252,35 +265,76 @@ struct ColliderView {
 
 struct SweepHit { bool hit; float fraction; V3 normal; };
 
-// KinematicClosestNotMeConvexResultCallback over all colliders, lanes strided over the collider list
+// KinematicClosestNotMeConvexResultCallback over this agent's candidates.  Lanes first cull candidates against the swept
+// bounds (the broadphase), then the warp tests (surviving candidate, boundary feature) pairs in parallel; each
+// candidate's closest feature is found with a packed shared-memory atomicMin (t bits | feature), its lane re-evaluates
+// that one feature for the exact fraction and normal, applies the callback's slope filter, and a shuffle reduction picks
+// the closest candidate (ties: lowest collider index, i.e. the order a serial scan would have kept).
 __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, V3 filterDir, float minSlopeDot, int lane) {
     const V3 d = to - from;
     float bt = 1.0f;
     int bi = 0x7fffffff;
     V3 bn = v3(0, 0, 0);
-    for (int j = lane; j < cv.nc; j += 32) {
-        const int i = j;  // candidates are stored in ascending collider order, so the candidate slot is the tie-break key
-        int kind; V3 c, h;
-        cv.fetch(j, kind, c, h);
-        const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
-                                 : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
-        bool miss = false;
-        {
-            const float lx = from.x < to.x ? from.x : to.x, hx = from.x < to.x ? to.x : from.x;
-            const float ly = from.y < to.y ? from.y : to.y, hy = from.y < to.y ? to.y : from.y;
-            const float lz = from.z < to.z ? from.z : to.z, hz = from.z < to.z ? to.z : from.z;
-            if (hx < c.x - ext.x || lx > c.x + ext.x) miss = true;
-            if (hy < c.y - ext.y || ly > c.y + ext.y) miss = true;
-            if (hz < c.z - ext.z || lz > c.z + ext.z) miss = true;
+    WarpShared &S = *const_cast<WarpShared *>(cv.S);
+    const float lx = from.x < to.x ? from.x : to.x, hx = from.x < to.x ? to.x : from.x;
+    const float ly = from.y < to.y ? from.y : to.y, hy = from.y < to.y ? to.y : from.y;
+    const float lz = from.z < to.z ? from.z : to.z, hz = from.z < to.z ? to.z : from.z;
+    const float rhoBox = kCapsuleRadius - kAllowedCcdPenetration, rhoCap = 2.0f * kCapsuleRadius - kAllowedCcdPenetration;
+    for (int base = 0; base < cv.nc; base += 32) {
+        const int j = base + lane;  // candidates are stored in ascending collider order, so the slot is the tie-break key
+        bool live = false;
+        int kind = 0; V3 c = v3(0, 0, 0), h = v3(0, 0, 0);
+        if (j < cv.nc) {
+            cv.fetch(j, kind, c, h);
+            const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
+                                     : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
+            live = !(hx < c.x - ext.x || lx > c.x + ext.x || hy < c.y - ext.y || ly > c.y + ext.y || hz < c.z - ext.z || lz > c.z + ext.z);
         }
-        if (miss) continue;
-        float t; V3 nn; bool hit;
-        if (kind == 0) hit = rayRoundedBox(from - c, d, v3(h.x, h.y + kCapsuleHalfHeight, h.z), kCapsuleRadius - kAllowedCcdPenetration, t, nn);
-        else hit = rayCapsule(from - c, d, 2.0f * kCapsuleHalfHeight, 2.0f * kCapsuleRadius - kAllowedCcdPenetration, t, nn);
-        if (!hit) continue;
-        if (!(t < bt)) continue;
-        if (dot(filterDir, nn) < minSlopeDot) continue;
-        bt = t; bi = i; bn = nn;
+        if (!__ballot_sync(FULL, live)) continue;
+        // a start point already inside a box's inflated shape is settled by its own lane (hit at t = 0 when moving inwards,
+        // nothing otherwise); only the rest go through the feature tests
+        bool needFeatures = live;
+        if (live) {
+            unsigned long long key0 = ~0ull;
+            if (kind == 0) {
+                V3 n0;
+                const float d0 = pointBoxDistance(from - c, v3(h.x, h.y + kCapsuleHalfHeight, h.z), n0);
+                if (d0 - rhoBox <= 0.0f) {
+                    needFeatures = false;
+                    if (dot(d, n0) < -kSimdEpsilon) key0 = 0ull;  // t = 0, feature 0
+                }
+            }
+            S.sweepKey[lane] = key0;
+        }
+        const unsigned m = __ballot_sync(FULL, needFeatures);
+        const int nlive = __popc(m);
+        if (needFeatures) S.sweepList[__popc(m & ((1u << lane) - 1u))] = uint8_t(lane);
+        __syncwarp();
+        // feature-major item order: neighbouring lanes run the same kind of test on different candidates
+        const float invLive = 1.0f / float(nlive > 0 ? nlive : 1);
+        for (int item = lane; item < nlive * kBoxFeatures; item += 32) {
+            int f = int((float(item) + 0.5f) * invLive);
+            int q = item - f * nlive;
+            if (q < 0) { f -= 1; q += nlive; } else if (q >= nlive) { f += 1; q -= nlive; }
+            const int src = S.sweepList[q];
+            int k2; V3 c2, h2;
+            cv.fetch(base + src, k2, c2, h2);
+            float t; V3 nn; bool hit = false;
+            if (k2 == 0) hit = rayRoundedBoxFeatureOutside(from - c2, d, v3(h2.x, h2.y + kCapsuleHalfHeight, h2.z), rhoBox, f, t, nn);
+            else if (f == 0) hit = rayCapsule(from - c2, d, 2.0f * kCapsuleHalfHeight, rhoCap, t, nn);
+            if (hit) atomicMin(&S.sweepKey[src], (static_cast<unsigned long long>(__float_as_uint(t + 0.0f)) << 32) | unsigned(f));
+        }
+        __syncwarp();
+        if (live) {
+            const unsigned long long key = S.sweepKey[lane];
+            if (key != ~0ull) {
+                float t; V3 nn;
+                if (kind == 0) rayRoundedBoxFeature(from - c, d, v3(h.x, h.y + kCapsuleHalfHeight, h.z), rhoBox, int(key & 31u), t, nn);
+                else rayCapsule(from - c, d, 2.0f * kCapsuleHalfHeight, rhoCap, t, nn);
+                if (t < bt && !(dot(filterDir, nn) < minSlopeDot)) { bt = t; bi = j; bn = nn; }
+            }
+        }
+        __syncwarp();
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -326,6 +380,9 @@ struct Kcc {
     V3 pos, hvel, jumpAxis, cur, tgt;
     float vvel, voff, stepOff, jumpSpeed;
     bool wasOnGround, wasJumping;
+#ifdef MV_KCC_COUNTERS
+    uint32_t dbg[4] = {0, 0, 0, 0};  // sweeps, recovers, cycles in sweeps, cycles in recovers
+#endif
     __device__ __forceinline__ bool onGround() const { return (fabsf(vvel) < kSimdEpsilon) && (fabsf(voff) < kSimdEpsilon); }
 };
 
@@ -358,12 +415,21 @@ __device__ void kccSetAcceleration(Kcc &k, V3 acc, float dt) {
 __device__ bool kccRecover(Kcc &k, const ColliderView &cv, int self, int lane) {
     k.cur = k.pos;
     V3 delta;
+#ifdef MV_KCC_COUNTERS
+    const long long tr0 = clock64();
+#endif
     const bool pen = warpRecover(cv, self, k.cur, delta, lane);
+#ifdef MV_KCC_COUNTERS
+    k.dbg[1]++; k.dbg[3] += uint32_t(clock64() - tr0);
+#endif
     if (pen) k.cur = k.cur + delta;
     k.pos = k.cur;
     return pen;
 }
 
+#ifdef MV_KCC_COUNTERS
+#define warpSweep(...) ([&] { const long long ts0 = clock64(); const SweepHit r_ = warpSweep(__VA_ARGS__); k.dbg[0]++; k.dbg[2] += uint32_t(clock64() - ts0); return r_; }())
+#endif
 __device__ void kccPlayerStep(Kcc &k, const ColliderView &cv, int self, float dt, float maxSlopeCos, int lane) {
     const V3 up = v3(0, 1, 0);
     k.cur = k.pos;
@@ -458,6 +524,10 @@ __device__ void kccPlayerStep(Kcc &k, const ColliderView &cv, int self, float dt
         else k.hvel = k.hvel * ((sp - kNormalDeceleration * dt) / sp);
     }
 }
+
+#ifdef MV_KCC_COUNTERS
+#undef warpSweep
+#endif
 
 // ---------------------------------------------------------------- helpers on shared state
 __device__ __forceinline__ M4 loadM4(const float *p) { M4 m;
@@ -592,6 +662,35 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
     __syncwarp();
 }
 
+// ---------------------------------------------------------------- cooperative 4x4 algebra: one output element per lane
+// Same operation order per element as mul4 / inverted4 (dev_math.cuh), so results are bit-identical to the serial forms;
+// sixteen lanes produce one matrix, the warp two at a time.
+__device__ __forceinline__ float mul4Elem(const float *a, const float *b, int e) {
+    const int row = e & 3, col = e >> 2;
+    float acc = 0.0f;
+#pragma unroll
+    for (int pos = 0; pos < 4; ++pos) acc += a[pos * 4 + row] * b[col * 4 + pos];
+    return acc;
+}
+__device__ __forceinline__ float det3skipP(const float *m, int skipCol, int skipRow) {
+#define MV_E(ci, ri) m[((ci) + ((ci) >= skipCol)) * 4 + ((ri) + ((ri) >= skipRow))]
+    return MV_E(0, 0) * ((MV_E(1, 1) * MV_E(2, 2)) - (MV_E(2, 1) * MV_E(1, 2))) - MV_E(0, 1) * (MV_E(1, 0) * MV_E(2, 2) - MV_E(2, 0) * MV_E(1, 2)) +
+           MV_E(0, 2) * (MV_E(1, 0) * MV_E(2, 1) - MV_E(2, 0) * MV_E(1, 1));
+#undef MV_E
+}
+__device__ __forceinline__ float cofactor4P(const float *m, int col, int row) { return (((row + col) & 1) ? -1 : 1) * det3skipP(m, col, row); }
+__device__ __forceinline__ float inv4Elem(const float *m, int e) {
+    const int row = e & 3, col = e >> 2;
+    float d = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) d += m[c * 4] * cofactor4P(m, c, 0);
+    return cofactor4P(m, row, col) / d;
+}
+// T(t) * S(s) element e (see tsMatrix)
+__device__ __forceinline__ float tsElem(float tx, float ty, float tz, float sx, float sy, float sz, int e) {
+    return e == 0 ? sx : e == 5 ? sy : e == 10 ? sz : e == 12 ? tx : e == 13 ? ty : e == 14 ? tz : e == 15 ? 1.0f : 0.0f;
+}
+
 // ---------------------------------------------------------------- render inputs (K3): instance list + view matrices
 // Model matrices are the drawables' absoluteTransformationMatrix() as SceneGraph::Object::setClean(objects) composes
 // them: right to left up the parent chain (v4r_env_renderer.cpp:319-335).
@@ -599,50 +698,101 @@ __device__ __forceinline__ void putInstance(MvInstance &d, const M4 &m, int mesh
     storeM4(d.model, m);
     d.mesh = mesh; d.color = color; d.pad[0] = 0; d.pad[1] = 0;
 }
+// T(t) * (S(s) * I) built directly: every product in the generic 4x4 chain is x*1 or x*0 and every partial sum adds +0, so
+// this is bit-identical to the multiplied-out matrix (scale and translation components are positive or zero terms)
+__device__ __forceinline__ M4 tsMatrix(V3 t, V3 sc) {
+    M4 m;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m.c[i] = 0.0f;
+    m.c[0] = sc.x; m.c[5] = sc.y; m.c[10] = sc.z; m.c[12] = t.x; m.c[13] = t.y; m.c[14] = t.z; m.c[15] = 1.0f;
+    return m;
+}
+
 __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
-    // static part: opaque layout boxes in order, then terrain slabs.  The opaque count is recomputed uniformly.
-    int nOpaque = 0;
-    for (int i = 0; i < L.n_static; ++i) nOpaque += (L.statics[i].flags & MV_OPAQUE) ? 1 : 0;
+    // static part: opaque layout boxes in order (their slot is precomputed by the host), then terrain slabs
+    const int nOpaque = L.n_opaque;
     if (writeStatic) {
         for (int i = lane; i < L.n_static; i += 32) {
             const MvBox &b = L.statics[i];
             if (!(b.flags & MV_OPAQUE)) continue;
-            int slotI = 0;
-            for (int j = 0; j < i; ++j) slotI += (L.statics[j].flags & MV_OPAQUE) ? 1 : 0;
-            putInstance(inst[slotI], mul4(translation4(v3(b.c[0], b.c[1], b.c[2])), mul4(scaling4(v3(b.h[0], b.h[1], b.h[2])), identity4())), 0, b.color);
+            putInstance(inst[b.flags >> 8], tsMatrix(v3(b.c[0], b.c[1], b.c[2]), v3(b.h[0], b.h[1], b.h[2])), 0, b.color);
         }
         for (int i = lane; i < L.n_terrain; i += 32) putInstance(inst[nOpaque + i], loadM4(L.terrain[i].model), 0, L.terrain[i].color);
     }
     const int base = nOpaque + L.n_terrain;
     const int no = L.n_obj;
-    for (int i = lane; i < no; i += 32) {
+    // movable objects: everything at reset, afterwards only what can have moved -- carried objects (they follow their
+    // agent's camera) and the objects picked up / put down this step
+    const int nTouch = writeStatic ? no : A + S.nDirty;
+    for (int idx = lane; idx < nTouch; idx += 32) {
+        const int i = writeStatic ? idx : (idx < A ? S.agents[idx].carrying : S.objDirty[idx - A]);
+        if (i < 0) continue;
         const MvObject &o = S.objects[i];
-        M4 m = mul4(translation4(v3(o.t[0], o.t[1], o.t[2])), mul4(scaling4(v3(o.s[0], o.s[1], o.s[2])), identity4()));
+        M4 m = tsMatrix(v3(o.t[0], o.t[1], o.t[2]), v3(o.s[0], o.s[1], o.s[2]));
         if (o.parent >= 0) {
             const MvAgent &a = S.agents[o.parent];
             m = mul4(loadM4(a.object_t), mul4(loadM4(a.cam_local), mul4(pickupLocal(), m)));
         }
         putInstance(inst[base + i], m, 0, o.color);
     }
-    for (int i = lane; i < A; i += 32) {
-        const MvAgent &a = S.agents[i];
-        const M4 objT = loadM4(a.object_t), cam = loadM4(a.cam_local);
-        storeM4(views + i * 16, inverted4(mul4(objT, cam)));  // Camera::cameraMatrix: inverse of the left-to-right absolute transform
-        const M4 eyesLocal = mul4(translation4(v3(0.0f, 0.0f, -0.19f)), mul4(scaling4(v3(0.25f, 0.12f, 0.2f)), identity4()));
-        putInstance(inst[base + no + i], mul4(objT, mul4(cam, eyesLocal)), 0, 6);  // AGENT_EYES = DARK_NAVY
-        const M4 ui = mul4(translation4(v3(0, 0, -0.2f)), identity4());
-        const M4 anchor = mul4(translation4(v3(0, -0.131f, 0)), identity4());
-        const M4 bar = scaling4(v3(a.bar_scale[0], a.bar_scale[1], a.bar_scale[2]));
-        putInstance(inst[base + no + A + i], mul4(objT, mul4(cam, mul4(ui, mul4(anchor, bar)))), 0, 3);  // BLUE
-        const M4 bodyLocal = mul4(translation4(v3(0, 0.09f, 0)), mul4(scaling4(v3(0.35f, 0.36f, 0.35f)), identity4()));
-        const int agentColors[7] = {0, 1, 3, 7, 14, 10, 12};  // const.hpp:85 as palette indices
-        putInstance(inst[base + no + 2 * A + i], mul4(objT, bodyLocal), 1, agentColors[i % 7]);
+    // per agent: view matrix, eyes, HUD bar, body.  Every chain keeps the scene graph's right-to-left association;
+    // products are formed cooperatively (sixteen lanes per matrix, two matrices per round):
+    //   r1  T0 = cam * eyes            T1 = anchor * bar
+    //   r2  eyes instance = objT * T0  T2 = ui * T1
+    //   r3  T3 = objT * cam            T4 = cam * T2
+    //   r4  view = inverse(T3)         bar instance = objT * T4
+    //   r5  body instance = objT * body
+    {
+        float (*T)[16] = const_cast<float (*)[16]>(S.mtx);
+        const int half = lane >> 4, e = lane & 15;
+        const float eyesE = tsElem(0.0f, 0.0f, -0.19f, 0.25f, 0.12f, 0.2f, e), uiE = tsElem(0, 0, -0.2f, 1, 1, 1, e);
+        const float anchorE = tsElem(0, -0.131f, 0, 1, 1, 1, e), bodyE = tsElem(0, 0.09f, 0, 0.35f, 0.36f, 0.35f, e);
+        // constant locals: slots 5 (eyes), 6 (ui / body after r2), 7 (anchor)
+        if (half == 0) { T[5][e] = eyesE; T[6][e] = uiE; } else { T[7][e] = anchorE; }
+        for (int i = 0; i < A; ++i) {
+            const MvAgent &a = S.agents[i];
+            const float *objT = a.object_t, *cam = a.cam_local;
+            if (half == 1) T[4][e] = tsElem(0, 0, 0, a.bar_scale[0], a.bar_scale[1], a.bar_scale[2], e);  // scaling4(bar)
+            __syncwarp();
+            {  // r1
+                const float v = half == 0 ? mul4Elem(cam, T[5], e) : mul4Elem(T[7], T[4], e);
+                T[half][e] = v;
+            }
+            __syncwarp();
+            {  // r2
+                const float v = half == 0 ? mul4Elem(objT, T[0], e) : mul4Elem(T[6], T[1], e);
+                if (half == 0) inst[base + no + i].model[e] = v; else T[2][e] = v;
+            }
+            __syncwarp();
+            {  // r3
+                const float v = half == 0 ? mul4Elem(objT, cam, e) : mul4Elem(cam, T[2], e);
+                T[3 + half][e] = v;
+            }
+            __syncwarp();
+            {  // r4
+                if (half == 0) views[i * 16 + e] = inv4Elem(T[3], e);  // Camera::cameraMatrix: inverse of the absolute transform
+                else inst[base + no + A + i].model[e] = mul4Elem(objT, T[4], e);
+            }
+            if (half == 0) T[0][e] = bodyE;
+            __syncwarp();
+            if (half == 0) inst[base + no + 2 * A + i].model[e] = mul4Elem(objT, T[0], e);  // r5
+            if (lane >= 16 && lane < 28) {  // mesh / colour / padding words of the three instances
+                const int which = (lane - 16) >> 2, w = (lane - 16) & 3;
+                const int agentColors[7] = {0, 1, 3, 7, 14, 10, 12};  // const.hpp:85 as palette indices
+                MvInstance &d = inst[base + no + which * A + i];
+                const int mesh = which == 2 ? 1 : 0, color = which == 0 ? 6 : (which == 1 ? 3 : agentColors[i % 7]);  // AGENT_EYES = DARK_NAVY, bar BLUE
+                if (w == 0) d.mesh = mesh; else if (w == 1) d.color = color; else d.pad[w - 2] = 0;
+            }
+            __syncwarp();
+        }
     }
-    // reward diamonds: two cones each (layout_utils.cpp:114-126); a collected one has been translated by (1000,1000,1000)
+    // reward diamonds: two cones each (layout_utils.cpp:114-126), rewritten only at reset and when one is collected
     const int nr = L.n_reward;
     for (int i = lane; i < nr; i += 32) {
+        const bool alive = (S.env.reward_alive[i >> 5] >> (i & 31)) & 1u;
+        if (!writeStatic && !((S.rewardDirty[i >> 5] >> (i & 31)) & 1u)) continue;
         M4 root = loadM4(L.reward_root[i]);
-        if (!((S.env.reward_alive[i >> 5] >> (i & 31)) & 1u)) {  // collected: Obstacles moves it by 1000, Collect by 500 (scenario_obstacles.cpp:224, scenario_collect.cpp:157)
+        if (!alive) {  // collected: Obstacles moves it by 1000, Collect by 500 (scenario_obstacles.cpp:224, scenario_collect.cpp:157)
             const float far = L.scenario == MV_SCENARIO_COLLECT ? 500.0f : 1000.0f;
             root = mul4(translation4(v3(far, far, far)), root);
         }
@@ -664,8 +814,21 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     WarpShared &S = reinterpret_cast<WarpShared *>(smemRaw)[warpInBlock];
     const int A = P.A;
     const float dt = P.k.dt;
+    const long long tProf0 = P.prof ? clock64() : 0;
+#define MV_PROBE(id) do { if (P.prof && lane == 0) P.prof[size_t(env) * 16 + (id)] = uint32_t(clock64() - tProf0); } while (0)
 
-    // ---- stage state: env + agents by plain loads, statics + objects by TMA bulk copies
+    // ---- stage state.  The movable-object records travel by one TMA bulk copy issued before anything else (its size is
+    // the host-known bound on live object counts, so it does not wait for the env record); env + agents by plain loads.
+    uint8_t *objGrid = P.objGrid + size_t(env) * P.gridCells;
+    MvObject *gObjects = P.objects + size_t(env) * MV_MAX_OBJECTS;
+    if (lane == 0) {
+        mbarInit(&S.mbar, 1);
+        if (!P.forceReset) {
+            const uint32_t bytes = uint32_t(P.maxObj) * uint32_t(sizeof(MvObject));
+            mbarExpectTx(&S.mbar, bytes);
+            if (bytes) bulkG2S(S.objects, gObjects, bytes, &S.mbar);
+        }
+    }
     {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&P.envs[env]);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&S.env);
@@ -673,27 +836,18 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         const uint32_t *asrc = reinterpret_cast<const uint32_t *>(&P.agents[size_t(env) * A]);
         uint32_t *adst = reinterpret_cast<uint32_t *>(&S.agents[0]);
         for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
-        if (lane == 0) { S.nDirty = 0; mbarInit(&S.mbar, 1); }
+        if (lane == 0) { S.nDirty = 0; S.rewardDirty[0] = S.rewardDirty[1] = S.rewardDirty[2] = 0u; }
         for (int i = lane; i < MV_MAX_AGENTS; i += 32) S.lastReward[i] = 0.0f;
     }
     __syncwarp();
     int slot = S.env.slot;
     const MvLevel *L = &P.levels[size_t(env) * 2 + slot];
-    uint8_t *objGrid = P.objGrid + size_t(env) * P.gridCells;
-    MvObject *gObjects = P.objects + size_t(env) * MV_MAX_OBJECTS;
     int ns = L->n_static, no = L->n_obj;
-    if (!P.forceReset) {
-        if (lane == 0) {
-            const uint32_t bytes = uint32_t(no) * uint32_t(sizeof(MvObject));
-            mbarExpectTx(&S.mbar, bytes);
-            if (no) bulkG2S(S.objects, gObjects, bytes, &S.mbar);
-        }
-        __syncwarp();
-        mbarWait(&S.mbar, 0);
-    }
+    if (!P.forceReset) mbarWait(&S.mbar, 0);
 
     bool resetNow = P.forceReset != 0;
     bool doneFlag = false;
+    MV_PROBE(0);  // state staged
 
     if (!P.forceReset) {
         ColliderView cv;
@@ -759,6 +913,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
             __syncwarp();
         }
 
+        MV_PROBE(1);  // action phase
         // ---- stepSimulation: action interfaces in agent order (env.cpp:126)
         for (int i = 0; i < A; ++i) {
             MvAgent &a = S.agents[i];
@@ -808,7 +963,11 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 __syncwarp();
                 cv.nc = nc;
             }
+            if (i == 0) { MV_PROBE(2); if (P.prof && lane == 0) P.prof[size_t(env) * 16 + 12] = uint32_t(cv.nc); }  // candidate list of agent 0
             kccPlayerStep(k, cv, ns + no + i, dt, P.k.max_slope_cos, lane);
+#ifdef MV_KCC_COUNTERS
+            if (i == 0 && P.prof && lane == 0) { P.prof[size_t(env) * 16 + 9] = k.dbg[0]; P.prof[size_t(env) * 16 + 10] = k.dbg[1]; P.prof[size_t(env) * 16 + 11] = k.dbg[2]; P.prof[size_t(env) * 16 + 13] = k.dbg[3]; }
+#endif
             if (k.pos.x < envLo.x + 0.5f || k.pos.x > envHi.x - 0.5f || k.pos.y < envLo.y + 0.5f || k.pos.y > envHi.y - 0.5f || k.pos.z < envLo.z + 0.5f ||
                 k.pos.z > envHi.z - 0.5f)
                 S.env.faults |= MV_FAULT_ENVELOPE;
@@ -821,6 +980,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
             }
             __syncwarp();
         }
+        MV_PROBE(3);  // character controllers
         // agent->updateTransform() (env.cpp:128-129)
         for (int i = lane; i < A; i += 32) {
             M4 ot;
@@ -829,6 +989,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         }
         __syncwarp();
 
+        MV_PROBE(4);  // updateTransform
         // ---- scenario step: interact, fall detection, shaping rewards -- scalar work, lane 0
         if (lane == 0) {
             MvEnvState &e = S.env;
@@ -847,7 +1008,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 if (a.carrying >= 0) {
                     const int oi = a.carrying;
                     MvObject &o = S.objects[oi];
-                    const M4 local = mul4(translation4(v3(o.t[0], o.t[1], o.t[2])), mul4(scaling4(v3(o.s[0], o.s[1], o.s[2])), identity4()));
+                    const M4 local = tsMatrix(v3(o.t[0], o.t[1], o.t[2]), v3(o.s[0], o.s[1], o.s[2]));
                     const V3 t = translationOf(mul4(pickAbs, local));
                     int vx, vy, vz;
                     toVoxel(t, vx, vy, vz);
@@ -904,7 +1065,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                         if (here != MV_NO_OBJECT && !hasAbove) {
                             MvObject &o = S.objects[here];
                             o.enabled = !o.enabled;
-                            const M4 local = mul4(translation4(v3(o.t[0], o.t[1], o.t[2])), mul4(scaling4(v3(o.s[0], o.s[1], o.s[2])), identity4()));
+                            const M4 local = tsMatrix(v3(o.t[0], o.t[1], o.t[2]), v3(o.s[0], o.s[1], o.s[2]));
                             const V3 sc = scalingOf(local);
                             o.s[0] = sc.x * carryingScale; o.s[1] = sc.y * carryingScale; o.s[2] = sc.z * carryingScale;
                             o.t[0] = 0.0f; o.t[1] = -0.3f; o.t[2] = 0.0f;
@@ -967,6 +1128,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     for (int r = 0; r < L->n_reward; ++r)
                         if (((e.reward_alive[r >> 5] >> (r & 31)) & 1u) && L->reward_voxel[r][0] == x && L->reward_voxel[r][1] == y && L->reward_voxel[r][2] == z) {
                             e.reward_alive[r >> 5] &= ~(1u << (r & 31));
+                            S.rewardDirty[r >> 5] |= 1u << (r & 31);
                             const bool good = L->reward_voxel[r][3] == 1;  // GREEN palette index
                             if (good) { ++e.positive_collected; rewardTeam(MV_R_COLLECT_GOOD, i, 1); }
                             else rewardTeam(MV_R_COLLECT_BAD, i, 1);
@@ -1000,6 +1162,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     for (int r = 0; r < L->n_reward; ++r)
                         if (((e.reward_alive[r >> 5] >> (r & 31)) & 1u) && L->reward_voxel[r][0] == x && L->reward_voxel[r][1] == y && L->reward_voxel[r][2] == z) {
                             e.reward_alive[r >> 5] &= ~(1u << (r & 31));
+                            S.rewardDirty[r >> 5] |= 1u << (r & 31);
                             rewardTeam(MV_R_OBST_EXTRA, i, 1);
                         }
                 }
@@ -1032,6 +1195,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         __syncwarp();
         doneFlag = S.doneFlag != 0;
         resetNow = doneFlag;
+        MV_PROBE(5);  // scenario logic
     }
 
     // ---- outputs of the finished step; VectorEnv::step captures trueObjective BEFORE reset and the rewards AFTER it (zeroed)
@@ -1075,9 +1239,11 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         }
     }
     __syncwarp();
+    MV_PROBE(6);  // outputs, flip/reset, object write-back
 
     writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
     for (int i = lane; i < A; i += 32) P.triCounts[size_t(env) * A + i] = 0;
+    MV_PROBE(7);  // instance list + views
 
     // ---- commit env + agents
     {
@@ -1088,6 +1254,8 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         uint32_t *adst = reinterpret_cast<uint32_t *>(&P.agents[size_t(env) * A]);
         for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
     }
+    MV_PROBE(8);  // commit
+#undef MV_PROBE
 }
 
 }  // namespace mvk

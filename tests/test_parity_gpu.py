@@ -277,3 +277,41 @@ def test_collect_trajectory_parity(built, policy):
         assert total > 0.0
     assert g.faults() == 0
     o.close(); g.close()
+
+
+def test_async_device_loop_matches_oracle(built):
+    """mv_step_device (asynchronous, action masks resident in HBM, obs left in HBM, host bookkeeping two steps late):
+    after mv_sync the state, the last step's rewards/dones and the device obs tensor equal the oracle's, across episode
+    turnovers (in-kernel flip to the pre-staged level while the host regenerates in the background)"""
+    import torch
+
+    E, A, steps = 32, 1, 420
+    params = {"episodeLengthSec": -33.0}  # base + 4 * #boxes: episodes of a few dozen to a few hundred steps (>= 4 steps each)
+    o, g = _pair("TowerBuilding", E, A, 21, params=params)
+    rng = np.random.default_rng(5)
+    acts = np.stack([helpers.purposeful_actions(rng, E * A, t) for t in range(steps)]).astype(np.int32)
+    dacts = torch.from_numpy(acts).cuda()
+    torch.cuda.synchronize()
+    ndone = 0
+    for t in range(steps):
+        o.step(acts[t])
+        ndone += int(o.dones().sum())
+        g.step_device(dacts.data_ptr() + t * E * A * 4)
+        if t % 97 == 96:  # mid-run synchronisation points must not disturb the pipeline
+            g.sync()
+            assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), "step %d" % t
+            assert np.array_equal(o.dones(), np.array(g.dones())), "step %d" % t
+    g.sync()
+    assert ndone >= 3
+    assert g.faults() == 0
+    assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32))
+    assert np.array_equal(o.dones(), np.array(g.dones()))
+    assert np.array_equal(o.true_objectives(), np.array(g.true_objectives()))
+    _assert_same_state(o, g, E, "after %d async steps" % steps)
+    g.fetch_obs()  # device obs tensor -> host buffer on demand
+    assert _assert_same_frame(o, g, "after %d async steps" % steps) == 1.0
+    g.step(acts[0])  # the synchronous call drains the pipeline and carries on from the same state
+    o.step(acts[0])
+    _assert_same_state(o, g, E, "sync step after async")
+    assert _assert_same_frame(o, g, "sync step after async") == 1.0
+    o.close(); g.close()
