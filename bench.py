@@ -187,7 +187,7 @@ def main():
         eng.step_device(ptr0 + t * step_bytes)  # asynchronous: the timed region ends with barrier() = device synchronize
 
     def host_step(t):
-        eng.step(acts_host[t])
+        eng.step(acts_host[t % len(acts_host)])
 
     # ---- device-resident value
     for t in range(Wm):
@@ -211,6 +211,7 @@ def main():
     # ---- roofline of the dominant kernel (rasteriser): CUDA events around the kernel on its own stream, L2 flushed before
     peak, peak_src = measured_peaks()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    eng.set_option("overlap", 0)  # kernels back to back so that each can be timed on its own
     ras, stp = [], []
     for t in range(60):
         with torch.cuda.stream(stream):

@@ -70,7 +70,9 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
 /* options: "depth" (0/1, before first reset), "tri_cap" (rasteriser triangle capacity), "obs_to_host" (0/1: whether
  * mv_step delivers the observation tensor to host memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps
  * let the rasteriser store rows straight into the pinned host buffer instead of copying afterwards; the HBM copy returned
- * by mv_obs_device is then only refreshed by mv_step_device), "fast_shading" (0/1, default 1: +-1 LSB fragment maths) */
+ * by mv_obs_device is then only refreshed by mv_step_device), "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
+ * "overlap" (0/1, default 1: the geometry kernel is a programmatic dependent launch of the step kernel and synchronises per env;
+ * 0 serialises the kernels so that mv_last_kernel_ms can time them separately) */
 int mv_set_option(mv_handle h, const char *key, int value);
 
 /* Device-resident path: the caller's consumer reads the tensors in HBM.
@@ -121,6 +123,8 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 /* per-env cycle stamps of the step kernel's phases: out = uint32[E][16] (0 staged, 1 actions, 2 candidate list, 3 controllers,
  * 4 transforms, 5 scenario, 6 outputs/reset, 7 instance list, 8 commit, 12 candidate count); enable=1 arms it, 0 frees it */
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
+/* per-tile cost of the tile kernel: out = uint32[N][tiles][4] {cycles, overlapping triangles, lane-per-triangle count, warp-per-triangle count} */
+int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable);
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);
 
 #ifdef __cplusplus

@@ -120,7 +120,6 @@ struct mv_engine {
     bool zeroCopy = true;  // host-facing steps: the tile kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
     bool rasterToHost = false;
     int numSMs = 148;
-    int tune = getenv("MV_TUNE") ? atoi(getenv("MV_TUNE")) : 0;
     MvConsts consts{};
 
     cudaStream_t stream = nullptr;
@@ -149,7 +148,10 @@ struct mv_engine {
     DevBuf<int32_t> d_tileCounter;
     DevBuf<mvr::TriCover> d_cover;
     DevBuf<mvr::TriShade> d_shade;
-    DevBuf<short4> d_bbox;
+    DevBuf<int32_t> d_binCounts, d_wideCounts;
+    DevBuf<uint16_t> d_binList;
+    DevBuf<int4> d_wideList;
+    int binCap = 512;
 
     PinBuf<MvLevel> h_levels;      // [E][2] staging mirror
     PinBuf<uint32_t> h_solid;      // [E][2][gridWords]
@@ -166,6 +168,10 @@ struct mv_engine {
     struct Pending { bool valid = false; cudaEvent_t ev = nullptr; PinBuf<float> rewards, trueObj; PinBuf<uint8_t> dones; };
     Pending ring[3];
     DevBuf<uint32_t> d_prof;  // mv_debug_step_profile only
+    DevBuf<uint32_t> d_tileProf;
+    DevBuf<uint32_t> d_ready; // per-env step completion stamps (step kernel -> geometry kernel)
+    uint32_t readyStamp = 0;
+    bool overlap = true;      // geometry kernel launched as a programmatic dependent of the step kernel
     uint64_t asyncSteps = 0;
 
     std::vector<int> hostSlot, hostEpisode;   // mirrors of the device's live slot / episode index
@@ -233,27 +239,31 @@ struct mv_engine {
         }
     }
 
-    int launchStep(const int32_t *dActions, bool forceReset) {
+    int launchStep(const int32_t *dActions, bool forceReset, Pending *mirror = nullptr) {
         mvk::StepParams sp;
+        sp.hostRewards = mirror ? mirror->rewards.p : nullptr; sp.hostTrueObjectives = mirror ? mirror->trueObj.p : nullptr;
+        sp.hostDones = mirror ? mirror->dones.p : nullptr;
         sp.levels = d_levels.p; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
         sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
-        sp.triCounts = d_triCounts.p;
+        sp.triCounts = d_triCounts.p; sp.wideCounts = d_wideCounts.p;
         sp.prof = d_prof.p;
+        sp.ready = d_ready.p; sp.readyStamp = ++readyStamp;
         sp.maxObj = std::min(int(MV_MAX_OBJECTS), maxObjSeen.load());
         sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
         sp.k = consts;
         const int warpsPerBlock = 2;
         const int blocks = (E + warpsPerBlock - 1) / warpsPerBlock;
         const size_t smem = sizeof(mvk::WarpShared) * warpsPerBlock;
-        MV_CUDA(cudaEventRecord(ev[0], stream));
+        const bool timing = !(mirror && overlap);  // the asynchronous fast path carries no timing events
+        if (timing) MV_CUDA(cudaEventRecord(ev[0], stream));
         mvk::stepKernel<<<blocks, warpsPerBlock * 32, smem, stream>>>(sp);
         MV_CUDA(cudaGetLastError());
-        MV_CUDA(cudaEventRecord(ev[1], stream));
+        if (!overlap) MV_CUDA(cudaEventRecord(ev[1], stream));  // an event between the two kernels would serialise them
         launches += 1;
         int rc = launchRaster();
         if (rc) return rc;
-        MV_CUDA(cudaEventRecord(ev[2], stream));
+        if (timing) MV_CUDA(cudaEventRecord(ev[2], stream));
         return MV_OK;
     }
     // geometry + tile kernels over view chunks; the triangle scratch of a chunk is reused by the next one, so it stays
@@ -263,8 +273,10 @@ struct mv_engine {
         rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = MV_MAX_INSTANCES;
         // pinned allocations are mapped into the device address space (UVA), so the kernel can store through the host pointer
         rp.obs = rasterToHost ? h_obs.p : d_obs.p; rp.depth = wantDepth ? (rasterToHost ? h_depth.p : d_depth.p) : nullptr; rp.faults = d_faults.p;
-        rp.cover = d_cover.p; rp.shade = d_shade.p; rp.bbox = d_bbox.p; rp.triCounts = d_triCounts.p;
-        rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.tune = tune;
+        rp.cover = d_cover.p; rp.shade = d_shade.p; rp.triCounts = d_triCounts.p;
+        rp.binCounts = d_binCounts.p; rp.binList = d_binList.p; rp.wideCounts = d_wideCounts.p; rp.wideList = d_wideList.p; rp.binCap = binCap;
+        rp.tileProf = d_tileProf.p;
+        rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0;
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
         const int nTiles = (W / 32) * (H / 4);
@@ -273,9 +285,23 @@ struct mv_engine {
         for (int base = 0; base < N; base += chunkViews) {
             const int cv = std::min(chunkViews, N - base);
             rp.viewBase = base; rp.chunkViews = cv;
-            mvr::geomKernel<<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+            if (overlap && base == 0) {
+                // programmatic dependent launch: the grid may start before the step kernel has drained; its blocks wait
+                // for their env's stamp
+                rp.ready = d_ready.p; rp.readyStamp = readyStamp;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(unsigned(itemBlocks), unsigned(cv)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::geomKernel, rp));
+            } else {
+                rp.ready = nullptr; rp.readyStamp = 0;
+                mvr::geomKernel<<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+            }
             MV_CUDA(cudaGetLastError());
-            const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * 8);  // persistent: 8 blocks of 4 warps per SM
+            const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * mvr::kTileBlocksPerSM);  // persistent blocks of 4 warps
             if (fastShading) mvr::tileKernel<true><<<tileBlocks, 128, 0, stream>>>(rp);
             else mvr::tileKernel<false><<<tileBlocks, 128, 0, stream>>>(rp);
             MV_CUDA(cudaGetLastError());
@@ -284,9 +310,16 @@ struct mv_engine {
         return MV_OK;
     }
     int allocTriScratch() {
-        d_cover.free(); d_shade.free(); d_bbox.free();
+        d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free();
         const size_t cnt = size_t(chunkViews) * size_t(triCap);
-        if (d_cover.alloc(cnt) != cudaSuccess || d_shade.alloc(cnt) != cudaSuccess || d_bbox.alloc(cnt) != cudaSuccess) { setError("triangle scratch allocation failed"); return MV_ERR_CUDA; }
+        const size_t tiles = size_t(chunkViews) * size_t((W / 32) * (H / 4));
+        binCap = std::max(256, std::min(1024, triCap / 4));
+        if (d_cover.alloc(cnt) != cudaSuccess || d_shade.alloc(cnt) != cudaSuccess || d_binCounts.alloc(tiles) != cudaSuccess ||
+            d_binList.alloc(tiles * size_t(binCap)) != cudaSuccess || d_wideList.alloc(size_t(chunkViews) * mvr::kWideCap) != cudaSuccess ||
+            cudaMemset(d_binCounts.p, 0, sizeof(int32_t) * tiles) != cudaSuccess) {
+            setError("triangle scratch allocation failed");
+            return MV_ERR_CUDA;
+        }
         return MV_OK;
     }
 
@@ -301,6 +334,14 @@ struct mv_engine {
         }
     }
 
+    // per-kernel times exist only when the kernels run back to back (overlap off); with the dependent launch the step and
+    // geometry kernels overlap and only their union is meaningful: {-1, whole step}
+    void readKernelTimes() {
+        if (cudaEventQuery(ev[2]) != cudaSuccess) return;
+        if (overlap) { lastMs[0] = -1.0f; cudaEventElapsedTime(&lastMs[1], ev[0], ev[2]); }
+        else { cudaEventElapsedTime(&lastMs[0], ev[0], ev[1]); cudaEventElapsedTime(&lastMs[1], ev[1], ev[2]); }
+    }
+
     int finishStep(bool copyObs) {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
@@ -310,8 +351,7 @@ struct mv_engine {
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
         MV_CUDA(cudaStreamSynchronize(stream));
-        cudaEventElapsedTime(&lastMs[0], ev[0], ev[1]);
-        cudaEventElapsedTime(&lastMs[1], ev[1], ev[2]);
+        readKernelTimes();
         return MV_OK;
     }
 
@@ -352,11 +392,8 @@ struct mv_engine {
             rtableDirty = false;
         }
         rasterToHost = false;
-        rc = launchStep(dActions, false);
+        rc = launchStep(dActions, false, &slotP);  // rewards / dones / true objectives land in the ring slot straight from the kernel
         if (rc) return rc;
-        MV_CUDA(cudaMemcpyAsync(slotP.rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        MV_CUDA(cudaMemcpyAsync(slotP.dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
-        MV_CUDA(cudaMemcpyAsync(slotP.trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
         slotP.valid = true;
         ++asyncSteps;
@@ -386,7 +423,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        d_prof.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_bbox.free();
+        d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -480,7 +517,8 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
-         ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter");
+         ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_wideCounts.alloc(N), "wideCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter") && ck(e->d_ready.alloc(E), "ready") &&
+         ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     // rasteriser scratch: Collect's Perlin landscapes merge into up to ~500 boxes (+ up to 86 reward diamonds)
     e->triCap = sc == MV_SCENARIO_COLLECT ? 4096 : (sc == MV_SCENARIO_OBSTACLES ? 2048 : 1024);
@@ -528,6 +566,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
     if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
+    if (k == "overlap") { cudaStreamSynchronize(h->stream); h->overlap = value != 0; return MV_OK; }
     h->setError("unknown option " + k);
     return MV_ERR_ARG;
 }
@@ -624,6 +663,20 @@ int mv_step_device(mv_handle h, const int32_t *d_masks) {
     return h->stepAsync(d_masks ? d_masks : h->d_actions.p);
 }
 
+int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return MV_ERR_CUDA;
+    cudaStreamSynchronize(h->stream);
+    const size_t n = size_t(h->N) * size_t((h->W / 32) * (h->H / 4)) * 4;
+    if (enable && !h->d_tileProf.p) {
+        if (h->d_tileProf.alloc(n) != cudaSuccess) { h->setError("tile profile buffer allocation failed"); return MV_ERR_CUDA; }
+        cudaMemset(h->d_tileProf.p, 0, sizeof(uint32_t) * n);
+    }
+    if (out && h->d_tileProf.p && cudaMemcpy(out, h->d_tileProf.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (!enable) h->d_tileProf.free();
+    return MV_OK;
+}
+
 int mv_fetch_obs(mv_handle h) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
@@ -655,8 +708,7 @@ int mv_sync(mv_handle h) {
     const int rc = h->drain();
     if (rc) return rc;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->setError("stream sync failed"); return MV_ERR_CUDA; }
-    cudaEventElapsedTime(&h->lastMs[0], h->ev[0], h->ev[1]);
-    cudaEventElapsedTime(&h->lastMs[1], h->ev[1], h->ev[2]);
+    h->readKernelTimes();
     return MV_OK;
 }
 
@@ -874,7 +926,9 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
     if (uploadPalette(&tmp) != MV_OK) return MV_ERR_CUDA;
     const int triCap = 8192;
     MvInstance *dInst = nullptr; int32_t *dCnt = nullptr, *dFault = nullptr, *dTri = nullptr, *dTileCtr = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
-    mvr::TriCover *dCover = nullptr; mvr::TriShade *dShade = nullptr; short4 *dBox = nullptr;
+    mvr::TriCover *dCover = nullptr; mvr::TriShade *dShade = nullptr;
+    int32_t *dBinCounts = nullptr, *dWideCount = nullptr; uint16_t *dBinList = nullptr; int4 *dWideList = nullptr;
+    const int binCap = 2048, tilesV = (w / 32) * (h / 4);
     int32_t cnt[8] = {nBox, n, 0, 0, 0, 0, 0, 0};
     {   // instances must be sorted by mesh type (draw order)
         int last = 0;
@@ -888,16 +942,22 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
     bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 32) == cudaSuccess && cudaMalloc(&dFault, 4) == cudaSuccess &&
               cudaMalloc(&dView, 64) == cudaSuccess && cudaMalloc(&dObs, size_t(w) * h * 4) == cudaSuccess && cudaMalloc(&dDepth, size_t(w) * h * 4) == cudaSuccess &&
               cudaMalloc(&dTri, 4) == cudaSuccess && cudaMalloc(&dTileCtr, 4) == cudaSuccess && cudaMalloc(&dCover, sizeof(mvr::TriCover) * triCap) == cudaSuccess &&
-              cudaMalloc(&dShade, sizeof(mvr::TriShade) * triCap) == cudaSuccess && cudaMalloc(&dBox, sizeof(short4) * triCap) == cudaSuccess;
+              cudaMalloc(&dShade, sizeof(mvr::TriShade) * triCap) == cudaSuccess && cudaMalloc(&dBinCounts, sizeof(int32_t) * tilesV) == cudaSuccess &&
+              cudaMalloc(&dWideCount, 4) == cudaSuccess && cudaMalloc(&dBinList, sizeof(uint16_t) * size_t(tilesV) * binCap) == cudaSuccess &&
+              cudaMalloc(&dWideList, sizeof(int4) * mvr::kWideCap) == cudaSuccess;
     if (ok) {
         cudaMemcpy(dInst, inst.data(), sizeof(MvInstance) * inst.size(), cudaMemcpyHostToDevice);
         cudaMemcpy(dCnt, cnt, 32, cudaMemcpyHostToDevice);
         cudaMemcpy(dView, view16, 64, cudaMemcpyHostToDevice);
         cudaMemset(dFault, 0, 4);
         cudaMemset(dTri, 0, 4);
+        cudaMemset(dWideCount, 0, 4);
+        cudaMemset(dBinCounts, 0, sizeof(int32_t) * tilesV);
         mvr::RasterParams rp;
+        rp.binCounts = dBinCounts; rp.binList = dBinList; rp.wideCounts = dWideCount; rp.wideList = dWideList; rp.binCap = binCap; rp.tileProf = nullptr;
+        rp.ready = nullptr; rp.readyStamp = 0;
         rp.instances = dInst; rp.instCounts = dCnt; rp.views = dView; rp.instStride = int(inst.size()); rp.obs = dObs; rp.depth = depth ? dDepth : nullptr;
-        rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.bbox = dBox; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.tune = 0; rp.viewBase = 0; rp.chunkViews = 1;
+        rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.viewBase = 0; rp.chunkViews = 1;
         rp.N = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
         const int items = nBox * 6 + (n - nBox) * 128;  // upper bound
         mvr::geomKernel<<<dim3(unsigned((items + 127) / 128 + 1), 1), 128>>>(rp);
@@ -911,7 +971,7 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
             if (f) ok = false;
         }
     }
-    cudaFree(dTri); cudaFree(dTileCtr); cudaFree(dCover); cudaFree(dShade); cudaFree(dBox);
+    cudaFree(dTri); cudaFree(dTileCtr); cudaFree(dCover); cudaFree(dShade); cudaFree(dBinCounts); cudaFree(dWideCount); cudaFree(dBinList); cudaFree(dWideList);
     cudaFree(dInst); cudaFree(dCnt); cudaFree(dFault); cudaFree(dView); cudaFree(dObs); cudaFree(dDepth);
     return ok ? MV_OK : MV_ERR_CUDA;
 }

@@ -29,8 +29,8 @@ struct __align__(16) TriCover {  // what the coverage / depth loop reads (broadc
     float z[3];
     float invArea;
     uint32_t key;       // draw order + 1, < 2^18 (later wins depth ties: LESS_OR_EQUAL)
-    int32_t tl;         // bit e set: edge e is top-left (no bias was applied)
-    int32_t pad[2];
+    int32_t flags;      // bits 0..2: edge e is top-left (no bias was applied); bit 3: every edge function fits int32 in the viewport
+    uint32_t bx, by;    // pixel box, inclusive: x0 | x1 << 16, y0 | y1 << 16
 };
 struct __align__(16) TriShade {  // what deferred shading reads for the winning fragment
     float rw[3];
@@ -52,10 +52,18 @@ struct RasterParams {
     // triangle scratch for views [viewBase, viewBase + chunkViews)
     TriCover *cover;             // [chunkViews][triCap]
     TriShade *shade;             // [chunkViews][triCap]
-    short4 *bbox;                // [chunkViews][triCap] pixel boxes {x0, x1, y0, y1} inclusive
+    // binning: a triangle whose box touches at most kWideTiles tiles is appended to each of those tiles' bins; wider ones
+    // go to the view's wide list (box + index), which every tile of the view checks
+    int32_t *binCounts;          // [chunkViews][tiles]; every tile warp zeroes its own counter after reading it
+    uint16_t *binList;           // [chunkViews][tiles][binCap] triangle indices
+    int32_t *wideCounts;         // [N], zeroed before geomKernel (the step kernel does it)
+    int4 *wideList;              // [chunkViews][kWideCap] {bx, by, index, 0}
+    int binCap;
     int32_t *triCounts;          // [N], zeroed before geomKernel (the step kernel does it)
     int32_t *tileCounter;        // dynamic tile queue of the persistent tile warps (reset by geomKernel)
-    int tune;                    // experiment switches (MV_TUNE env var): bit0 adaptive lane-parallel chunks, bit1 view-minor tile order
+    const uint32_t *ready;       // [E] step-kernel completion stamps (nullptr: plain stream order)
+    uint32_t readyStamp;         // value ready[env] holds once this step's state, instances and views of env are written
+    uint32_t *tileProf;          // optional [views][tiles][4] {cycles, triangles overlapping, small-path lanes, big-path triangles} (debug)
     int fastShading;             // 1: approximate rsqrt / fused multiply-add in the fragment stage (+-1 LSB), 0: bit-exact
     int viewBase, chunkViews;
     int N, A, W, H;
@@ -74,10 +82,17 @@ __device__ __forceinline__ ClipVert lerpVert(const ClipVert &a, const ClipVert &
 }
 __device__ __forceinline__ int32_t snapSub(float v) { return int32_t(floorf(v * 256.0f + 0.5f)); }
 
+constexpr int kWideTiles = 8;   // more tiles than this: the triangle goes to the view's wide list
+constexpr int kWideCap = 512;
+
 struct SetupCtx {
     TriCover *cover;
     TriShade *shade;
-    short4 *bbox;
+    int32_t *binCounts;   // this view's [tiles]
+    uint16_t *binList;    // this view's [tiles][binCap]
+    int32_t *wideCount;
+    int4 *wideList;
+    int binCap;
     int32_t *nTris;
     int32_t *fault;
     int triCap;
@@ -117,15 +132,30 @@ __device__ __forceinline__ void emitTri(const SetupCtx &cx, const ClipVert &va, 
         s.p[e * 3 + 0] = vs[e]->px; s.p[e * 3 + 1] = vs[e]->py; s.p[e * 3 + 2] = vs[e]->pz;
         s.n[e * 3 + 0] = vs[e]->nx; s.n[e * 3 + 1] = vs[e]->ny; s.n[e * 3 + 2] = vs[e]->nz;
     }
-    c.tl = tl;
     c.invArea = 1.0f / float(-area2);
     c.key = key;
-    c.pad[0] = worst < (1ll << 30) ? 1 : 0;  // every edge function fits int32 anywhere in the viewport
-    c.pad[1] = 0;
+    c.flags = tl | (worst < (1ll << 30) ? 8 : 0);  // bit 3: every edge function fits int32 anywhere in the viewport
+    c.bx = uint32_t(px0) | (uint32_t(px1) << 16);
+    c.by = uint32_t(py0) | (uint32_t(py1) << 16);
     s.color = color; s.pad[0] = 0; s.pad[1] = 0;
     cx.cover[slot] = c;
     cx.shade[slot] = s;
-    cx.bbox[slot] = make_short4(short(px0), short(px1), short(py0), short(py1));
+    // bin it
+    const int tilesX = cx.W >> 5;
+    const int tx0 = px0 >> 5, tx1 = px1 >> 5, ty0 = py0 >> 2, ty1 = py1 >> 2;
+    if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > kWideTiles) {
+        const int w = atomicAdd(cx.wideCount, 1);
+        if (w < kWideCap) cx.wideList[w] = make_int4(int(c.bx), int(c.by), slot, 0);
+        else atomicOr(cx.fault, MV_FAULT_TRI_OVERFLOW);
+    } else {
+        for (int ty = ty0; ty <= ty1; ++ty)
+            for (int tx = tx0; tx <= tx1; ++tx) {
+                const int t = ty * tilesX + tx;
+                const int b = atomicAdd(cx.binCounts + t, 1);
+                if (b < cx.binCap) cx.binList[size_t(t) * cx.binCap + b] = uint16_t(slot);
+                else atomicOr(cx.fault, MV_FAULT_TRI_OVERFLOW);
+            }
+    }
 }
 
 // clip against z >= 0 and z <= w, project, snap, cull, emit
@@ -207,9 +237,30 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
     const int env = view / P.A;
     const int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.tileCounter = 0;  // for the tile kernel that follows in-stream
+    // Launched with programmatic stream serialisation this grid starts while the step kernel is still running: each block
+    // waits for its own env's completion stamp (release/acquire through L2) instead of for the whole step grid, so the
+    // geometry of finished envs overlaps the step kernel's long-tail envs.  Everything the step kernel produced is then
+    // read with L2-coherent loads (ld.global.cg), never through the non-coherent path.
+    if (P.ready) {
+        if (threadIdx.x == 0) {
+            const uint32_t *flag = P.ready + env;
+            uint32_t v;
+            while (true) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                if (v == P.readyStamp) break;
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
     const MvInstance *inst = P.instances + size_t(env) * P.instStride;
     // work items: 6 faces per box, then one per triangle of the other meshes (instances are sorted by mesh type)
-    const int *cnt = P.instCounts + env * 8;
+    int cnt[6];
+    {
+        const int4 c03 = __ldcg(reinterpret_cast<const int4 *>(P.instCounts + env * 8));
+        const int2 c45 = __ldcg(reinterpret_cast<const int2 *>(P.instCounts + env * 8 + 4));
+        cnt[0] = c03.x; cnt[1] = c03.y; cnt[2] = c03.z; cnt[3] = c03.w; cnt[4] = c45.x; cnt[5] = c45.y;
+    }
     const int nBoxInst = cnt[0];
     const int nBoxItems = nBoxInst * 6;
     const int capItems = cnt[2] * MV_CAPSULE_TRIS, sphItems = cnt[3] * MV_SPHERE_TRIS, coneItems = cnt[4] * MV_CONE_TRIS, cylItems = cnt[5] * MV_CYLINDER_TRIS;
@@ -218,21 +269,34 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
     SetupCtx cx;
     cx.cover = P.cover + size_t(vslot) * P.triCap;
     cx.shade = P.shade + size_t(vslot) * P.triCap;
-    cx.bbox = P.bbox + size_t(vslot) * P.triCap;
+    {
+        const int nTilesV = (P.W >> 5) * (P.H >> 2);
+        cx.binCounts = P.binCounts + size_t(vslot) * nTilesV;
+        cx.binList = P.binList + size_t(vslot) * nTilesV * P.binCap;
+        cx.wideCount = P.wideCounts + view;
+        cx.wideList = P.wideList + size_t(vslot) * kWideCap;
+        cx.binCap = P.binCap;
+    }
     cx.nTris = P.triCounts + view;
     cx.fault = P.faults + env;
     cx.triCap = P.triCap; cx.W = P.W; cx.H = P.H;
 
     M4 viewM;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) viewM.c[i] = __ldg(P.views + size_t(view) * 16 + i);
+    for (int i = 0; i < 4; ++i) {
+        const float4 col = __ldcg(reinterpret_cast<const float4 *>(P.views + size_t(view) * 16) + i);
+        viewM.c[i * 4 + 0] = col.x; viewM.c[i * 4 + 1] = col.y; viewM.c[i * 4 + 2] = col.z; viewM.c[i * 4 + 3] = col.w;
+    }
 
     if (item < nBoxItems) {
         const int ii = item / 6, face = item % 6;
         M4 model;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) model.c[i] = __ldg(inst[ii].model + i);
-        const int color = inst[ii].color;
+        for (int i = 0; i < 4; ++i) {
+            const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
+            model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
+        }
+        const int color = __ldcg(&inst[ii].color);
         const M4 mv = mul4(viewM, model);
         float nm[9];
         normalMatrix(mv, nm);
@@ -255,7 +319,10 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
         else { rest -= coneItems; mesh = 4; ii += cnt[2] + cnt[3] + cnt[4] + rest / MV_CYLINDER_TRIS; tri = rest % MV_CYLINDER_TRIS; }
         M4 model;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) model.c[i] = __ldg(inst[ii].model + i);
+        for (int i = 0; i < 4; ++i) {
+            const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
+            model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
+        }
         const M4 mv = mul4(viewM, model);
         float nm[9];
         normalMatrix(mv, nm);
@@ -270,7 +337,7 @@ __global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
             cvt[k] = makeVert(mv, nm, v3(vp[0], vp[1], vp[2]), v3(vp[3], vp[4], vp[5]), P.p00, P.p11, P.p22, P.p32);
         }
         const uint32_t keyBase = uint32_t(ii) * 128u + uint32_t(tri) + 1u;
-        clipAndSetup(cx, cvt[0], cvt[1], cvt[2], inst[ii].color, keyBase);
+        clipAndSetup(cx, cvt[0], cvt[1], cvt[2], __ldcg(&inst[ii].color), keyBase);
     }
 }
 
@@ -297,9 +364,15 @@ template <bool FAST> __device__ __forceinline__ float dot3(float ax, float ay, f
 
 // uber.frag:112-141.  FAST keeps the structure but uses rsqrt.approx + FMA: colours move by at most 1 LSB (the tolerance the
 // north star grants for RGB); the exact variant reproduces the oracle byte for byte.  The depth output is exact in both.
-template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const TriShade *tp, float l0, float l1, float l2, float &wOut) {
+struct ShadeRec { float4 a0, a1, a2, a3, a4, a5; };
+__device__ __forceinline__ ShadeRec loadShade(const TriShade *tp) {
     const float4 *q = reinterpret_cast<const float4 *>(tp);  // 96-byte record as six 128-bit read-only loads
-    const float4 a0 = __ldg(q + 0), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3), a4 = __ldg(q + 4), a5 = __ldg(q + 5);
+    ShadeRec r;
+    r.a0 = __ldg(q + 0); r.a1 = __ldg(q + 1); r.a2 = __ldg(q + 2); r.a3 = __ldg(q + 3); r.a4 = __ldg(q + 4); r.a5 = __ldg(q + 5);
+    return r;
+}
+template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const ShadeRec &rec, float l0, float l1, float l2, float &wOut) {
+    const float4 a0 = rec.a0, a1 = rec.a1, a2 = rec.a2, a3 = rec.a3, a4 = rec.a4, a5 = rec.a5;
     const float rw0 = a0.x, rw1 = a0.y, rw2 = a0.z;
     const float p[9] = {a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
     const float n[9] = {a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w, a5.x};
@@ -367,9 +440,7 @@ struct EdgeEval {  // one triangle's edge functions at a pixel centre
     float z0, z1, z2, invArea;
     uint32_t key;
 };
-__device__ __forceinline__ EdgeEval loadCover(const TriCover *c) {
-    const int4 *cq = reinterpret_cast<const int4 *>(c);
-    const int4 q0 = __ldg(cq + 0), q1 = __ldg(cq + 1), q2 = __ldg(cq + 2), q3 = __ldg(cq + 3), q4 = __ldg(cq + 4);
+__device__ __forceinline__ EdgeEval unpackCover(const int4 q0, const int4 q1, const int4 q2, const int4 q3, const int4 q4) {
     EdgeEval e;
     e.C0 = (long long)(((unsigned long long)(unsigned)q0.y << 32) | (unsigned)q0.x);
     e.C1 = (long long)(((unsigned long long)(unsigned)q0.w << 32) | (unsigned)q0.z);
@@ -377,10 +448,18 @@ __device__ __forceinline__ EdgeEval loadCover(const TriCover *c) {
     e.A0 = q1.z; e.A1 = q1.w; e.A2 = q2.x; e.B0 = q2.y; e.B1 = q2.z; e.B2 = q2.w;
     e.z0 = __int_as_float(q3.x); e.z1 = __int_as_float(q3.y); e.z2 = __int_as_float(q3.z); e.invArea = __int_as_float(q3.w);
     e.key = uint32_t(q4.x);
-    const int tl = q4.y;
-    e.u0 = (tl & 1) ? 0 : 1; e.u1 = (tl & 2) ? 0 : 1; e.u2 = (tl & 4) ? 0 : 1;  // undo the top-left bias for the barycentrics
-    e.small = q4.z;
+    const int fl = q4.y;
+    e.u0 = (fl & 1) ? 0 : 1; e.u1 = (fl & 2) ? 0 : 1; e.u2 = (fl & 4) ? 0 : 1;  // undo the top-left bias for the barycentrics
+    e.small = (fl >> 3) & 1;
     return e;
+}
+__device__ __forceinline__ EdgeEval loadCover(const TriCover *c) {  // global memory, read-only path
+    const int4 *cq = reinterpret_cast<const int4 *>(c);
+    return unpackCover(__ldg(cq + 0), __ldg(cq + 1), __ldg(cq + 2), __ldg(cq + 3), __ldg(cq + 4));
+}
+__device__ __forceinline__ EdgeEval loadCoverShared(const TriCover *c) {
+    const int4 *cq = reinterpret_cast<const int4 *>(c);
+    return unpackCover(cq[0], cq[1], cq[2], cq[3], cq[4]);
 }
 __device__ __forceinline__ unsigned long long packFrag(float z, uint32_t key, int idx) {
     const uint32_t b = __float_as_uint(z);
@@ -388,61 +467,78 @@ __device__ __forceinline__ unsigned long long packFrag(float z, uint32_t key, in
     return ((unsigned long long)(~asc) << 32) | (unsigned long long)((key << 13) | uint32_t(idx));
 }
 
-template <bool FAST> __global__ void __launch_bounds__(128, 8) tileKernel(RasterParams P) {
+#ifndef MV_TILE_BLOCKS
+#define MV_TILE_BLOCKS 5
+#endif
+constexpr int kTileBlocksPerSM = MV_TILE_BLOCKS;  // persistent blocks of 4 warps per SM (bounds the register budget)
+template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) tileKernel(RasterParams P) {
     __shared__ unsigned long long s_frag[4][128];
+    __shared__ __align__(16) TriCover s_stage[4][32];  // this chunk's triangle records, one per lane (the large path reads them back)
     const int lane = threadIdx.x & 31;
     unsigned long long *frag = s_frag[threadIdx.x >> 5];
+    TriCover *stage = s_stage[threadIdx.x >> 5];
     const int tilesX = P.W / 32, nTiles = tilesX * (P.H / 4);
     const int totalTiles = min(P.chunkViews, P.N - P.viewBase) * nTiles;
+    int gw = 0;
+    if (lane == 0) gw = atomicAdd(P.tileCounter, 1);
+    gw = __shfl_sync(0xffffffffu, gw, 0);
     for (;;) {
-        int gw = 0;
-        if (lane == 0) gw = atomicAdd(P.tileCounter, 1);
-        gw = __shfl_sync(0xffffffffu, gw, 0);
         if (gw >= totalTiles) return;
-        // view-minor order: consecutive work items belong to different views, so a heavy view's tiles are spread over the
-        // whole queue instead of forming the tail
-        const int chunkN = totalTiles / nTiles;
-        int tile, vslot;
-        if (P.tune & 2) { tile = gw / chunkN; vslot = gw - tile * chunkN; }
-        else { vslot = gw / nTiles; tile = gw - vslot * nTiles; }
+        // claim the next work item now; the atomic's round trip overlaps this tile's work
+        int gwNext = 0;
+        if (lane == 0) gwNext = atomicAdd(P.tileCounter, 1);
+        const int vslot = gw / nTiles, tile = gw - vslot * nTiles;
         const int view = P.viewBase + vslot;
         const TriCover *cover = P.cover + size_t(vslot) * P.triCap;
         const TriShade *shade = P.shade + size_t(vslot) * P.triCap;
-        const short4 *bbox = P.bbox + size_t(vslot) * P.triCap;
-        const int nTris = min(__ldg(P.triCounts + view), P.triCap);
+        int32_t *binCount = P.binCounts + size_t(vslot) * nTiles + tile;
+        const uint16_t *bin = P.binList + (size_t(vslot) * nTiles + tile) * P.binCap;
+        const int4 *wide = P.wideList + size_t(vslot) * kWideCap;
+        const int nWide = min(__ldg(P.wideCounts + view), kWideCap);
+        const int nBin = min(*binCount, P.binCap);
+        const int total = nWide + nBin;
 
         const int ty = tile / tilesX;
         const int tx0 = (tile - ty * tilesX) * 32, ty0 = ty * 4;
         const int px = tx0 + (lane & 7) * 4, py = ty0 + (lane >> 3);
         const int sx32 = px * 256 + 128, sy32 = py * 256 + 128;
         unsigned long long best[4] = {0ull, 0ull, 0ull, 0ull};
+        const long long tp0 = P.tileProf ? clock64() : 0;
+        int nOv = 0, nSm = 0, nBg = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) frag[lane * 4 + k] = 0ull;
         __syncwarp();
+        if (lane == 0 && nBin) *binCount = 0;  // leave the bin empty for the next geometry pass
 
-        for (int base = 0; base < nTris; base += 32) {
-            const int tmine = base + lane;
-            bool ov = false, small = false;
+        for (int base = 0; base < total; base += 32) {
+            const int j = base + lane;
+            // which triangle is mine, and does its box touch this tile (bin entries always do; wide entries are checked)
+            int tmine = -1;
+            if (j < nWide) {
+                const int4 w = __ldg(wide + j);
+                const int x0 = w.x & 0xffff, x1 = int(unsigned(w.x) >> 16), y0 = w.y & 0xffff, y1 = int(unsigned(w.y) >> 16);
+                if (x0 <= tx0 + 31 && x1 >= tx0 && y0 <= ty0 + 3 && y1 >= ty0) tmine = w.z;
+            } else if (j < total) {
+                tmine = int(bin[j - nWide]);
+            }
+            const bool ov = tmine >= 0;
+            bool small = false;
             int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
-            if (tmine < nTris) {
-                const short4 b = __ldg(bbox + tmine);
-                ov = b.x <= tx0 + 31 && b.y >= tx0 && b.z <= ty0 + 3 && b.w >= ty0;
-                bx0 = max(int(b.x), tx0); bx1 = min(int(b.y), tx0 + 31); by0 = max(int(b.z), ty0); by1 = min(int(b.w), ty0 + 3);
-                small = ov && (bx1 - bx0 + 1) * (by1 - by0 + 1) <= kSmallArea;
+            EdgeEval e;
+            e.small = 1;
+            if (ov) {
+                const int4 *cq = reinterpret_cast<const int4 *>(cover + tmine);
+                const int4 q0 = __ldg(cq + 0), q1 = __ldg(cq + 1), q2 = __ldg(cq + 2), q3 = __ldg(cq + 3), q4 = __ldg(cq + 4);
+                int4 *sq = reinterpret_cast<int4 *>(stage + lane);
+                sq[0] = q0; sq[1] = q1; sq[2] = q2; sq[3] = q3; sq[4] = q4;
+                e = unpackCover(q0, q1, q2, q3, q4);
+                bx0 = max(int(unsigned(q4.z) & 0xffffu), tx0); bx1 = min(int(unsigned(q4.z) >> 16), tx0 + 31);
+                by0 = max(int(unsigned(q4.w) & 0xffffu), ty0); by1 = min(int(unsigned(q4.w) >> 16), ty0 + 3);
+                small = (bx1 - bx0 + 1) * (by1 - by0 + 1) <= kSmallArea;
             }
-            {   // adaptive: when many mid-sized triangles share this chunk, one lane each beats ~100 warp instructions each
-                const int area = (ov && !small) ? (bx1 - bx0 + 1) * (by1 - by0 + 1) : 0;
-                const unsigned big = __ballot_sync(0xffffffffu, area > 0);
-                if (big && (P.tune & 1)) {
-                    int maxArea = area;
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) maxArea = max(maxArea, __shfl_xor_sync(0xffffffffu, maxArea, off));
-                    if (__popc(big) * 8 > maxArea) small = ov;
-                }
-            }
+            if (P.tileProf) { nOv += __popc(__ballot_sync(0xffffffffu, ov)); nSm += __popc(__ballot_sync(0xffffffffu, small)); nBg += __popc(__ballot_sync(0xffffffffu, ov && !small)); }
             // ---- small triangles: one lane each
             if (small) {
-                const EdgeEval e = loadCover(cover + tmine);
                 for (int y = by0; y <= by1; ++y) {
                     const int sy = y * 256 + 128, sx0 = bx0 * 256 + 128;
                     if (e.small) {
@@ -469,40 +565,43 @@ template <bool FAST> __global__ void __launch_bounds__(128, 8) tileKernel(Raster
                     }
                 }
             }
-            // ---- large triangles: whole warp, lane = 4 pixels
+            // ---- large triangles: whole warp, lane = 4 pixels; the record comes back from shared memory
             unsigned bits = __ballot_sync(0xffffffffu, ov && !small);
+            __syncwarp();
             while (bits) {
                 const int bsel = __ffs(bits) - 1;
                 bits &= bits - 1;
-                const int ti = base + bsel;
-                const short4 tb = __ldg(bbox + ti);
-                if (px + 3 < tb.x || px > tb.y || py < tb.z || py > tb.w) continue;
-                const EdgeEval e = loadCover(cover + ti);
-                if (e.small) {
-                    int F0 = int(e.C0) + e.A0 * sx32 + e.B0 * sy32, F1 = int(e.C1) + e.A1 * sx32 + e.B1 * sy32, F2 = int(e.C2) + e.A2 * sx32 + e.B2 * sy32;
+                const int ti = __shfl_sync(0xffffffffu, tmine, bsel);
+                const TriCover *sc = stage + bsel;
+                const int x0 = int(sc->bx & 0xffffu), x1 = int(sc->bx >> 16), y0 = int(sc->by & 0xffffu), y1 = int(sc->by >> 16);
+                if (px + 3 < x0 || px > x1 || py < y0 || py > y1) continue;
+                const EdgeEval e2 = loadCoverShared(sc);
+                if (e2.small) {
+                    int F0 = int(e2.C0) + e2.A0 * sx32 + e2.B0 * sy32, F1 = int(e2.C1) + e2.A1 * sx32 + e2.B1 * sy32, F2 = int(e2.C2) + e2.A2 * sx32 + e2.B2 * sy32;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if ((F0 | F1 | F2) >= 0) {
-                            const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
-                            const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
-                            if (z <= 1.0f) { const unsigned long long f = packFrag(z, e.key, ti); best[k] = f > best[k] ? f : best[k]; }
+                            const float l0 = float(F0 + e2.u0) * e2.invArea, l1 = float(F1 + e2.u1) * e2.invArea, l2 = float(F2 + e2.u2) * e2.invArea;
+                            const float z = (l0 * e2.z0 + l1 * e2.z1) + l2 * e2.z2;
+                            if (z <= 1.0f) { const unsigned long long f = packFrag(z, e2.key, ti); best[k] = f > best[k] ? f : best[k]; }
                         }
-                        F0 += e.A0 * 256; F1 += e.A1 * 256; F2 += e.A2 * 256;
+                        F0 += e2.A0 * 256; F1 += e2.A1 * 256; F2 += e2.A2 * 256;
                     }
                 } else {
-                    long long F0 = e.C0 + (long long)e.A0 * sx32 + (long long)e.B0 * sy32, F1 = e.C1 + (long long)e.A1 * sx32 + (long long)e.B1 * sy32,
-                              F2 = e.C2 + (long long)e.A2 * sx32 + (long long)e.B2 * sy32;
+                    long long F0 = e2.C0 + (long long)e2.A0 * sx32 + (long long)e2.B0 * sy32, F1 = e2.C1 + (long long)e2.A1 * sx32 + (long long)e2.B1 * sy32,
+                              F2 = e2.C2 + (long long)e2.A2 * sx32 + (long long)e2.B2 * sy32;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if ((F0 | F1 | F2) >= 0) {
-                            const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
-                            const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
-                            if (z <= 1.0f) { const unsigned long long f = packFrag(z, e.key, ti); best[k] = f > best[k] ? f : best[k]; }
+                            const float l0 = float(F0 + e2.u0) * e2.invArea, l1 = float(F1 + e2.u1) * e2.invArea, l2 = float(F2 + e2.u2) * e2.invArea;
+                            const float z = (l0 * e2.z0 + l1 * e2.z1) + l2 * e2.z2;
+                            if (z <= 1.0f) { const unsigned long long f = packFrag(z, e2.key, ti); best[k] = f > best[k] ? f : best[k]; }
                         }
-                        F0 += (long long)e.A0 * 256; F1 += (long long)e.A1 * 256; F2 += (long long)e.A2 * 256;
+                        F0 += (long long)e2.A0 * 256; F1 += (long long)e2.A1 * 256; F2 += (long long)e2.A2 * 256;
                     }
                 }
             }
+            __syncwarp();  // the stage is rewritten by the next chunk
         }
         __syncwarp();
         // ---- merge both paths, recompute the winner's barycentrics, shade, store
@@ -515,6 +614,7 @@ template <bool FAST> __global__ void __launch_bounds__(128, 8) tileKernel(Raster
             const unsigned long long f = fs > best[k] ? fs : best[k];
             if (f == 0ull) { o[k] = 0xff000000u; wv[k] = 0.0f; continue; }
             const int ti = int(uint32_t(f) & 8191u);
+            const ShadeRec rec = loadShade(shade + ti);  // both records are in flight together
             const EdgeEval e = loadCover(cover + ti);
             const int sx = sx32 + k * 256;
             float l0, l1, l2;
@@ -527,13 +627,18 @@ template <bool FAST> __global__ void __launch_bounds__(128, 8) tileKernel(Raster
                 l1 = float(e.C1 + (long long)e.A1 * sx + (long long)e.B1 * sy32 + e.u1) * e.invArea;
                 l2 = float(e.C2 + (long long)e.A2 * sx + (long long)e.B2 * sy32 + e.u2) * e.invArea;
             }
-            o[k] = shadePixel<FAST>(shade + ti, l0, l1, l2, wv[k]);
+            o[k] = shadePixel<FAST>(rec, l0, l1, l2, wv[k]);
         }
         out.x = o[0]; out.y = o[1]; out.z = o[2]; out.w = o[3];
         uint8_t *obsView = P.obs + size_t(view) * P.W * P.H * 4;
         *reinterpret_cast<uint4 *>(obsView + (size_t(py) * P.W + px) * 4) = out;
         if (P.depth) *reinterpret_cast<float4 *>(P.depth + size_t(view) * P.W * P.H + size_t(py) * P.W + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
         __syncwarp();
+        if (P.tileProf && lane == 0) {
+            uint32_t *tp = P.tileProf + (size_t(view) * nTiles + tile) * 4;
+            tp[0] = uint32_t(clock64() - tp0); tp[1] = uint32_t(nOv); tp[2] = uint32_t(nSm); tp[3] = uint32_t(nBg);
+        }
+        gw = __shfl_sync(0xffffffffu, gwNext, 0);
     }
 }
 

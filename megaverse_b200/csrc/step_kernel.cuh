@@ -49,13 +49,18 @@ struct StepParams {
     int32_t *instCounts;         // [E][8]
     float *views;                // [E*A][16]
     int32_t *triCounts;          // [E*A] rasteriser triangle counters, zeroed here for the geometry kernel that follows
+    int32_t *wideCounts;         // [E*A] likewise (wide-triangle lists)
     const int32_t *actions;      // [E*A]
     const float *rtable;         // [E*A][MV_R_COUNT]
     float *rewards;              // [E*A]
     uint8_t *dones;              // [E]
     float *trueObjectives;       // [E*A]
+    float *hostRewards, *hostTrueObjectives;  // optional pinned host mirrors written directly by the kernel (or nullptr)
+    uint8_t *hostDones;
     int E, A, gridCells, gridWords;
     int forceReset;              // mv_reset(): re-initialise every env from its live level slot, no physics
+    uint32_t *ready;             // [E] completion stamps polled by the geometry kernel (programmatic dependent launch)
+    uint32_t readyStamp;
     int maxObj;                  // upper bound of n_obj over the live and staged levels (sizes the staging copy)
     uint32_t *prof;              // optional [E][16] per-phase cycle stamps (mv_debug_step_profile); nullptr in production
     MvConsts k;
@@ -810,6 +815,8 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
+    // let the geometry kernel's blocks start right away: they synchronise per env on P.ready, not on this grid's completion
+    asm volatile("griddepcontrol.launch_dependents;");
     if (env >= P.E) return;
     WarpShared &S = reinterpret_cast<WarpShared *>(smemRaw)[warpInBlock];
     const int A = P.A;
@@ -1199,15 +1206,20 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     }
 
     // ---- outputs of the finished step; VectorEnv::step captures trueObjective BEFORE reset and the rewards AFTER it (zeroed)
-    if (!P.forceReset) {
-        for (int i = lane; i < A; i += 32) {
-            if (doneFlag) P.trueObjectives[size_t(env) * A + i] = L->scenario == MV_SCENARIO_TOWER ? float(S.env.highest_tower) : float(S.env.solved);
-            P.rewards[size_t(env) * A + i] = doneFlag ? 0.0f : S.lastReward[i];
-        }
-        if (lane == 0) P.dones[env] = doneFlag ? 1 : 0;
-    } else {
-        for (int i = lane; i < A; i += 32) P.rewards[size_t(env) * A + i] = 0.0f;
-        if (lane == 0) P.dones[env] = 0;
+    // Host mirrors (pinned, mapped) are written by the kernel itself when given: no copy operations between the kernels
+    // of successive steps.
+    for (int i = lane; i < A; i += 32) {
+        const size_t idx = size_t(env) * A + i;
+        float to = P.trueObjectives[idx];
+        if (!P.forceReset && doneFlag) { to = L->scenario == MV_SCENARIO_TOWER ? float(S.env.highest_tower) : float(S.env.solved); P.trueObjectives[idx] = to; }
+        const float r = (P.forceReset || doneFlag) ? 0.0f : S.lastReward[i];
+        P.rewards[idx] = r;
+        if (P.hostRewards) { P.hostRewards[idx] = r; P.hostTrueObjectives[idx] = to; }
+    }
+    if (lane == 0) {
+        const uint8_t dn = (!P.forceReset && doneFlag) ? 1 : 0;
+        P.dones[env] = dn;
+        if (P.hostDones) P.hostDones[env] = dn;
     }
 
     if (resetNow) {
@@ -1242,7 +1254,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     MV_PROBE(6);  // outputs, flip/reset, object write-back
 
     writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
-    for (int i = lane; i < A; i += 32) P.triCounts[size_t(env) * A + i] = 0;
+    for (int i = lane; i < A; i += 32) { P.triCounts[size_t(env) * A + i] = 0; P.wideCounts[size_t(env) * A + i] = 0; }
     MV_PROBE(7);  // instance list + views
 
     // ---- commit env + agents
@@ -1255,6 +1267,12 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
     }
     MV_PROBE(8);  // commit
+    // publish: everything this warp wrote (state, instance list, views, zeroed triangle counters) before the stamp
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.ready + env), "r"(P.readyStamp) : "memory");
+    }
 #undef MV_PROBE
 }
 

@@ -14,6 +14,7 @@ for e in range(E):
 g.reset()
 rng = np.random.default_rng(1)
 names = ["stage", "action", "candlist", "kcc", "xform", "scenario", "out/reset", "instances", "commit"]
+g.set_option("overlap", int(os.environ.get("MV_OVERLAP", "1")))
 g.step_profile(True, False)
 acc = []
 for t in range(300):
