@@ -194,9 +194,8 @@ struct mv_engine {
                 return;
             }
             {
-                int boxes = out.level.n_terrain + out.level.n_obj + 2 * A;
-                for (int i = 0; i < out.level.n_static; ++i) boxes += (out.level.statics[i].flags & MV_OPAQUE) ? 1 : 0;
-                const int items = boxes * 6 + A * 128 + 2 * out.level.n_reward * 12;  // capsule 128 triangles, cone 12
+                const int32_t *mc = out.level.mesh_counts;  // work items of the geometry kernel: 6 faces per box, one per mesh triangle
+                const int items = mc[0] * 6 + mc[1] * MV_CAPSULE_TRIS + mc[2] * MV_SPHERE_TRIS + mc[3] * MV_CONE_TRIS + mc[4] * MV_CYLINDER_TRIS;
                 int cur = maxItemsSeen.load();
                 while (items > cur && !maxItemsSeen.compare_exchange_weak(cur, items)) {}
                 int curO = maxObjSeen.load();
@@ -224,7 +223,7 @@ struct mv_engine {
         for (int id : todo) {
             MV_CUDA(cudaMemcpyAsync(&d_levels.p[id], &h_levels.p[id], sizeof(MvLevel), cudaMemcpyHostToDevice, stream));
             const size_t nw = size_t(levelWords[size_t(id)]);  // only the words this level's grid uses
-            for (int plane = 0; plane < (scenario == MV_SCENARIO_TOWER ? 1 : 3); ++plane)
+            for (int plane = 0; plane < ((scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE) ? 1 : 3); ++plane)
                 MV_CUDA(cudaMemcpyAsync(d_solid.p + (size_t(id) * 3 + plane) * gridWords, h_solid.p + (size_t(id) * 3 + plane) * gridWords, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, stream));
         }
         return MV_OK;
@@ -280,7 +279,7 @@ struct mv_engine {
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
         const int nTiles = (W / 32) * (H / 4);
-        const int maxItems = MV_MAX_INSTANCES * 6 + A * 128 + 2 * MV_MAX_REWARD * 12;  // blocks past a view's real item count exit at once
+        const int maxItems = MV_MAX_INSTANCES * 6 + (A + MV_MAX_OBJECTS + MV_MAX_DECO) * 128 + 2 * MV_MAX_REWARD * 12;  // blocks past a view's real item count exit at once
         const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
         for (int base = 0; base < N; base += chunkViews) {
             const int cv = std::min(chunkViews, N - base);
@@ -775,12 +774,12 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
     const MvLevel &L = h->h_levels.p[size_t(env) * 2 + h->hostSlot[size_t(env)]];
     std::vector<int32_t> o;
-    o.push_back(L.n_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
+    o.push_back(L.n_grid_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
     static const uint32_t pal[22] = {0xffdd3c, 0x3bb372, 0x50c878, 0x2eb5d0, 0xadd8e6, 0x3a7fa6, 0x2c3e50, 0xffb400, 0xb3b3b3, 0x555555, 0x222222,
                                      0xffffff, 0xff0000, 0xffa770, 0xd468ee, 0xffe6e6, 0xffffe6, 0xccffcc, 0xe6ecff, 0xd9d9d9, 0xf2e6ff, 0xffebcc};
-    for (int i = 0; i < L.n_static; ++i) {
+    for (int i = 0; i < L.n_grid_static; ++i) {
         const MvBox &b = L.statics[i];
         // invert centre/half back to inclusive voxel bounds: min = c - h, max = c + h - 1
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
@@ -791,7 +790,7 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
         o.push_back(L.terrain[i].type);
         for (int a = 0; a < 6; ++a) o.push_back(L.terrain[i].bb[a]);
     }
-    for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
+    for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_init[i].voxel[a]);
     for (int i = 0; i < h->A; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
     if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);  // numPlatforms
@@ -870,7 +869,7 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
                 if ((sol[idx >> 5] >> (idx & 31)) & 1u) {
                     flags |= 1;
                     const float cx = x + L.grid_org[0] + 0.5f, cy = y + L.grid_org[1] + 0.5f, cz = z + L.grid_org[2] + 0.5f;
-                    for (int i = 0; i < L.n_static; ++i) {
+                    for (int i = 0; i < L.n_grid_static; ++i) {
                         const MvBox &b = L.statics[i];
                         if (fabsf(cx - b.c[0]) < b.h[0] && fabsf(cy - b.c[1]) < b.h[1] && fabsf(cz - b.c[2]) < b.h[2]) { flags |= (b.flags & MV_OPAQUE); break; }
                     }
@@ -992,10 +991,10 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     } catch (const std::exception &) { return MV_ERR_CAPACITY; }
     const MvLevel &L = lo.level;
     std::vector<int32_t> o;
-    o.push_back(L.n_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
+    o.push_back(L.n_grid_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
-    for (int i = 0; i < L.n_static; ++i) {
+    for (int i = 0; i < L.n_grid_static; ++i) {
         const MvBox &b = L.statics[i];
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
@@ -1005,7 +1004,7 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
         o.push_back(L.terrain[i].type);
         for (int a = 0; a < 6; ++a) o.push_back(L.terrain[i].bb[a]);
     }
-    for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_voxel[i][a]);
+    for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_init[i].voxel[a]);
     for (int i = 0; i < num_agents; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
     if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);

@@ -47,6 +47,9 @@ int randRange(int low, int high, Rng &rng) { return std::uniform_int_distributio
 bool randomBool(Rng &rng) { return bool(randRange(0, 2, rng)); }
 float frand(Rng &rng) { return std::uniform_real_distribution<float>{0, 1}(rng); }
 uint32_t randomLayoutColor(Rng &rng) { return kLayoutColors[randRange(0, 14, rng)]; }
+const uint32_t kObjectColors[14] = {C_YELLOW, C_GREEN, C_LIGHT_GREEN, C_BLUE, C_LIGHT_BLUE, C_DARK_BLUE, C_ORANGE, C_GREY, C_DARK_GREY, C_WHITE, C_RED,
+                                    C_LIGHT_ORANGE, C_VIOLET, C_LIGHT_PINK};
+uint32_t randomObjectColor(Rng &rng) { return kObjectColors[randRange(0, 14, rng)]; }  // const.hpp:96-119
 
 // ---- sparse voxel map with the reference's hash (voxel_grid.hpp:39-49): iteration order must match -------------------
 struct I3 { int x, y, z; };
@@ -55,6 +58,15 @@ inline I3 voxUnkey(uint32_t k) { return {int(k >> 20) - 512, int((k >> 10) & 102
 struct KeyHash { size_t operator()(uint32_t k) const noexcept { return size_t(k); } };
 struct Vox { uint8_t type = 0, terrain = 0; uint32_t color = C_WHITE; };
 using VoxMap = std::unordered_map<uint32_t, Vox, KeyHash>;
+
+// ObjectStackingComponent::addDrawablesAndCollisions (component_object_stacking.hpp:170-198): a 0.39 box, MOVABLE_BOX colour,
+// collision scale 1.15 / offset (0,-0.05,0) = collision class 0
+void setStackingBox(MvObjInit &o, const I3 &v) {
+    o.voxel[0] = int16_t(v.x); o.voxel[1] = int16_t(v.y); o.voxel[2] = int16_t(v.z);
+    o.color = int16_t(paletteIndex(C_LIGHT_BLUE));
+    o.scale[0] = o.scale[1] = o.scale[2] = 0.39f;
+    o.meta = 0;
+}
 
 struct IBox { int mn[3], mx[3]; };  // max exclusive for platform boxes, inclusive for merged boxes (as in the reference)
 
@@ -150,6 +162,7 @@ int scenarioFromName(const std::string &name) {
     const std::string n = lower(name);
     if (n == "towerbuilding") return MV_SCENARIO_TOWER;
     if (n == "collect") return MV_SCENARIO_COLLECT;
+    if (n == "rearrange") return MV_SCENARIO_REARRANGE;
     if (n == "obstacleseasy" || n == "obstaclesmedium" || n == "obstacleshard" || n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava" || n == "test")
         return MV_SCENARIO_OBSTACLES;
     return -1;
@@ -189,6 +202,8 @@ std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::strin
         const bool oneType = n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava";
         return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f}, {"obstaclesAgentCarriedObjectToExit", oneType ? 1.0f : 0.0f}};
     }
+    if (scenario == MV_SCENARIO_REARRANGE)  // scenario_rearrange.hpp:91-97
+        return {{"rearrangeOneMoreObjectCorrectPosition", 1.0f}, {"rearrangeAllObjectsCorrectPosition", 10.0f}};
     return {};
 }
 
@@ -211,6 +226,10 @@ int rewardSlot(int scenario, const std::string &key) {
         if (key == "obstaclesExtraReward") return MV_R_OBST_EXTRA;
         if (key == "obstaclesAgentCarriedObjectToExit") return MV_R_OBST_CARRIED_TO_EXIT;
     }
+    if (scenario == MV_SCENARIO_REARRANGE) {
+        if (key == "rearrangeOneMoreObjectCorrectPosition") return MV_R_REARRANGE_ONE_MORE;
+        if (key == "rearrangeAllObjectsCorrectPosition") return MV_R_REARRANGE_ALL;
+    }
     return -1;
 }
 
@@ -218,7 +237,8 @@ int gridCapacity(int scenario) {
     // TowerBuilding rooms are at most 29 x (6+18) x 24; Obstacles chains of up to 7 platforms (+ transitions, start, exit)
     // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
     // Collect: <= 41 x 41 landscape, heights <= 18, 16 cells of margin (objects can be put down beyond the edge), y from -30
-    const int cells = scenario == MV_SCENARIO_TOWER ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
+    // Rearrange: 19 x (6+18) x 14 room
+    const int cells = (scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE) ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
     return ((cells + 127) / 128) * 128;
 }
 
@@ -227,6 +247,7 @@ LevelGenerator::LevelGenerator(const std::string &scenarioName, int numAgents, c
 
 void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     std::memset(&out.level, 0, sizeof(MvLevel));
+    out.drawSeq.clear();
     // Env::reset: reseed the env stream from itself
     const auto sd = randRange(0, 1 << 30, rng_);
     rng_.seed((unsigned long)sd);
@@ -237,13 +258,50 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
         case MV_SCENARIO_TOWER: generateTower(out); break;
         case MV_SCENARIO_OBSTACLES: generateObstacles(out); break;
         case MV_SCENARIO_COLLECT: generateCollect(out); break;
+        case MV_SCENARIO_REARRANGE: generateRearrange(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
     MvLevel &L = out.level;
-    L.n_opaque = 0;
-    for (int i = 0; i < L.n_static; ++i)
-        if (L.statics[i].flags & MV_OPAQUE) L.statics[i].flags |= (L.n_opaque++) << 8;
+    if (scenario_ != MV_SCENARIO_REARRANGE) L.n_grid_static = L.n_static;
+    assignSlots(out);
     if (L.grid_dim[0] * L.grid_dim[1] * L.grid_dim[2] > gridCells) throw std::runtime_error("level exceeds the dense grid capacity");
+}
+
+// Instance slots in the reference's draw order: mesh type major (meshIndices is a std::map<DrawableType,int>), insertion
+// order minor (v4r_env_renderer.cpp:267-279).
+void LevelGenerator::assignSlots(LevelOut &out) {
+    MvLevel &L = out.level;
+    const int A = numAgents_;
+    std::vector<DrawRef> seq = out.drawSeq;
+    if (seq.empty()) {
+        for (int i = 0; i < L.n_static; ++i)
+            if (L.statics[i].flags & MV_OPAQUE) seq.push_back({DrawRef::STATIC, i});
+        for (int i = 0; i < L.n_terrain; ++i) seq.push_back({DrawRef::TERRAIN, i});
+        for (int i = 0; i < L.n_obj; ++i) seq.push_back({DrawRef::OBJECT, i});
+        seq.push_back({DrawRef::EYES, 0}); seq.push_back({DrawRef::BARS, 0}); seq.push_back({DrawRef::BODIES, 0}); seq.push_back({DrawRef::REWARDS, 0});
+        L.n_static_pre = L.n_static;
+    }
+    L.n_opaque = 0;
+    int slot = 0, terrainSeen = 0;
+    for (int mesh = 0; mesh < 5; ++mesh) {
+        const int first = slot;
+        for (const DrawRef &d : seq) {
+            switch (d.kind) {
+                case DrawRef::STATIC: if (mesh == 0) { L.statics[d.index].flags = (L.statics[d.index].flags & 255) | (slot++ << 8); ++L.n_opaque; } break;
+                case DrawRef::TERRAIN:  // slabs are consecutive in every scenario
+                    if (mesh == 0) { if (terrainSeen++ == 0) L.slot_terrain = slot; ++slot; }
+                    break;
+                case DrawRef::OBJECT: if (MV_OBJ_MESH(L.obj_init[d.index].meta) == mesh) L.obj_init[d.index].meta = (L.obj_init[d.index].meta & 255) | (slot++ << 8); break;
+                case DrawRef::DECO: if (L.deco[d.index].mesh == mesh) L.deco[d.index].slot = slot++; break;
+                case DrawRef::EYES: if (mesh == 0) { L.slot_eyes = slot; slot += A; } break;
+                case DrawRef::BARS: if (mesh == 0) { L.slot_bars = slot; slot += A; } break;
+                case DrawRef::BODIES: if (mesh == 1) { L.slot_body = slot; slot += A; } break;
+                case DrawRef::REWARDS: if (mesh == 3) { L.slot_reward = slot; slot += 2 * L.n_reward; } break;
+            }
+        }
+        L.mesh_counts[mesh] = slot - first;
+    }
+    if (slot > MV_MAX_INSTANCES) throw std::runtime_error("too many drawables");
 }
 
 void LevelGenerator::generateTower(LevelOut &out) {
@@ -331,12 +389,195 @@ void LevelGenerator::generateTower(LevelOut &out) {
     L.n_movable = int(objs.size());
     L.episode_len = params_.at("episodeLengthSec") + 4.0f * float(objs.size());  // scenario_tower_building.cpp:263-266
     for (int i = 0; i < L.n_obj; ++i) {
-        L.obj_voxel[i][0] = int16_t(objs[i].x); L.obj_voxel[i][1] = int16_t(objs[i].y); L.obj_voxel[i][2] = int16_t(objs[i].z);
-        L.obj_voxel[i][3] = int16_t(paletteIndex(C_LIGHT_BLUE));
+        setStackingBox(L.obj_init[i], objs[i]);
     }
     for (int a = 0; a < 3; ++a) { L.bz_min[a] = bz.mn[a]; L.bz_max[a] = bz.mx[a]; }
 
     // dense grid: the room's bounding box, with head-room above the walls for stacked objects
+    L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
+    L.grid_dim[0] = length; L.grid_dim[1] = height + 18; L.grid_dim[2] = width;
+    fillPlanes(out, &grid);
+}
+
+// RearrangeScenario (scenario_rearrange.cpp:46-300): a 19 x 14 walled room with a target arrangement on the left pedestal
+// and the same items, partly displaced, on the right one.
+void LevelGenerator::generateRearrange(LevelOut &out) {
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    const int leftC[3] = {5, 2, 5}, rightC[3] = {13, 2, 5};
+    // RearrangePlatform::init, EmptyPlatform::generate (no draws), addPlatform(..., randomBool)
+    const int height = randRange(4, 7, rng), length = 19, width = 14;
+    const bool drawWalls = randomBool(rng);
+    VoxMap grid{100};
+    fillBox(grid, {{0, 0, 0}, {length, 1, width}}, MV_SOLID | MV_OPAQUE, C_DARK_GREY);
+    const uint8_t wallType = uint8_t(MV_SOLID | (drawWalls ? MV_OPAQUE : 0));
+    fillBox(grid, {{0, 0, 0}, {1, height, width}}, wallType, C_DARK_GREY);
+    fillBox(grid, {{length - 1, 0, 0}, {length, height, width}}, wallType, C_DARK_GREY);
+    fillBox(grid, {{0, 0, 0}, {length, height, 1}}, wallType, C_DARK_GREY);
+    fillBox(grid, {{0, 0, width - 1}, {length, height, width}}, wallType, C_DARK_GREY);
+
+    // generateArrangement (:70-126)
+    struct Item { int mesh; uint32_t color; I3 off; };
+    static const int shapes[4] = {4, 1, 0, 2};  // Cylinder, Capsule, Box, Sphere as mesh codes (scenario_rearrange.hpp:33-35)
+    auto randomItem = [&](I3 off) { Item it; it.mesh = shapes[randRange(0, 4, rng)]; it.color = randomObjectColor(rng); it.off = off; return it; };
+    std::vector<Item> items;
+    {
+        const int arrangementSize = randRange(2, 8, rng);
+        std::vector<Item> q;  // FIFO
+        size_t qHead = 0;
+        std::vector<I3> used;
+        auto isUsed = [&](const I3 &c) { for (auto &u : used) if (u.x == c.x && u.y == c.y && u.z == c.z) return true; return false; };
+        const Item first = randomItem({0, 0, 0});
+        q.push_back(first); items.push_back(first); used.push_back({0, 0, 0});
+        std::vector<I3> directions{{-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+        while (qHead < q.size()) {
+            const Item curr = q[qHead++];
+            int maxBranches = randRange(1, int(directions.size()) + 1, rng);
+            maxBranches = randRange(1, maxBranches + 1, rng);
+            int numBranches = 0;
+            std::shuffle(directions.begin(), directions.end(), rng);
+            for (auto dir : directions) {
+                const I3 no{curr.off.x + dir.x, curr.off.y + dir.y, curr.off.z + dir.z};
+                const I3 below{no.x, no.y - 1, no.z};
+                if (no.y >= 2 || std::abs(no.x) >= 2 || std::abs(no.z) >= 2) continue;
+                if (isUsed(no)) continue;
+                if (!(no.y == 0 || isUsed(below))) continue;
+                const Item ni = randomItem(no);
+                q.push_back(ni); items.push_back(ni); used.push_back(no);
+                ++numBranches;
+                if (numBranches >= maxBranches) break;
+                if (int(items.size()) >= arrangementSize) break;
+            }
+            if (int(items.size()) >= arrangementSize) break;
+        }
+    }
+
+    // DefaultScenario::spawnAgents with RearrangeScenario::agentStartingPositions (:179-200)
+    std::vector<I3> agentPos(size_t(A), I3{0, 0, 0});
+    for (int i = 0; i < A; ++i)
+        for (int attempt = 0; attempt < 20; ++attempt) {
+            const int ax = randRange(2, length - 1, rng);
+            const int az = randRange(2, width - 1, rng);
+            if (std::fabs(float(ax - leftC[0])) < 2 && std::fabs(float(az - leftC[2])) < 2) continue;
+            if (std::fabs(float(ax - rightC[0])) < 2 && std::fabs(float(az - rightC[2])) < 2) continue;
+            agentPos[size_t(i)] = {ax, 2, az};
+            break;
+        }
+    for (int i = 0; i < A; ++i) {
+        const float yaw = frand(rng) * 3.14159265358979323846f * 2;
+        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        const float sx = float(agentPos[size_t(i)].x) + 0.5f, sy = float(agentPos[size_t(i)].y) + 0.0f, sz = float(agentPos[size_t(i)].z) + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        L.init_pos[i][0] = float(agentPos[size_t(i)].x); L.init_pos[i][1] = float(agentPos[size_t(i)].y); L.init_pos[i][2] = float(agentPos[size_t(i)].z);
+    }
+
+    // addEpisodeDrawables (:265-300): boxes of the voxel grid first
+    int ns = 0;
+    for (const auto &g : mergeVoxels(grid)) {
+        if (g.type == 0) continue;
+        for (const auto &b : g.boxes) {
+            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
+            MvBox &sb = L.statics[ns];
+            for (int a = 0; a < 3; ++a) {
+                sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
+                sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;
+            }
+            sb.flags = g.type;
+            sb.color = paletteIndex(g.color);
+            if (g.type & MV_OPAQUE) out.drawSeq.push_back({DrawRef::STATIC, ns});
+            ++ns;
+        }
+    }
+    L.n_grid_static = ns;
+    // pedestal footprints become solid voxels (placement logic only, no box): y = 1, 7 x 7 around both centres
+    for (int dx = -3; dx <= 3; ++dx)
+        for (int dz = -3; dz <= 3; ++dz) {
+            Vox v; v.type = MV_SOLID;
+            grid[voxKey(leftC[0] + dx, 1, leftC[2] + dz)] = v;
+            grid[voxKey(rightC[0] + dx, 1, rightC[2] + dz)] = v;
+        }
+
+    // arrangementDrawables (:202-263): scale = scales[shape] * 0.45, collision scale (1,0.5,1) cylinder / (1,2,1) capsule
+    const float objSize = 0.45f;
+    auto shapeScale = [&](int mesh, float sc[3]) {
+        const float b[3] = {mesh == 1 ? 0.8f : (mesh == 4 ? 0.9f : 1.0f), mesh == 1 ? 0.5f : (mesh == 4 ? 2.0f : 1.0f), mesh == 1 ? 0.8f : (mesh == 4 ? 0.9f : 1.0f)};
+        for (int a = 0; a < 3; ++a) sc[a] = b[a] * objSize;
+    };
+    auto colScaleY = [](int mesh) { return mesh == 4 ? 0.5f : (mesh == 1 ? 2.0f : 1.0f); };
+    L.n_deco = 0;
+    for (const Item &it : items) {  // the target, not interactive: static colliders + drawables
+        const I3 pos{it.off.x + leftC[0], it.off.y + leftC[1], it.off.z + leftC[2]};
+        const float t[3] = {float(pos.x) + 0.5f, float(pos.y) + 0.5f, float(pos.z) + 0.5f};
+        float sc[3];
+        shapeScale(it.mesh, sc);
+        if (ns >= MV_MAX_STATIC || L.n_deco >= MV_MAX_DECO) throw std::runtime_error("too many arrangement items");
+        MvBox &sb = L.statics[ns++];
+        const float cs[3] = {1.0f, colScaleY(it.mesh), 1.0f};
+        for (int a = 0; a < 3; ++a) { sb.c[a] = t[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * cs[a]; }
+        sb.flags = MV_SOLID; sb.color = 0;
+        MvDeco &d = L.deco[L.n_deco];
+        std::memset(d.model, 0, sizeof d.model);
+        d.model[0] = sc[0]; d.model[5] = sc[1]; d.model[10] = sc[2]; d.model[12] = t[0]; d.model[13] = t[1]; d.model[14] = t[2]; d.model[15] = 1.0f;
+        d.mesh = it.mesh; d.color = paletteIndex(it.color); d.slot = 0; d.pad = 0;
+        out.drawSeq.push_back({DrawRef::DECO, L.n_deco});
+        ++L.n_deco;
+    }
+    L.n_static_pre = ns;
+    {   // the working copy: the first numUnmovedItems stay in place, the rest go to random free floor cells
+        std::vector<I3> occupied;
+        for (const Item &it : items) occupied.push_back(it.off);
+        auto isOcc = [&](const I3 &c) { for (auto &u : occupied) if (u.x == c.x && u.y == c.y && u.z == c.z) return true; return false; };
+        const int numUnmoved = randRange(0, int(items.size()), rng);
+        int placed = 0;
+        L.n_obj = 0;
+        for (const Item &it : items) {
+            I3 off = it.off;
+            if (placed >= numUnmoved) {
+                while (isOcc(off)) { const int rx = randRange(-2, 3, rng); const int rz = randRange(-2, 3, rng); off = {rx, 0, rz}; }
+                occupied.push_back(off);
+            }
+            MvObjInit &o = L.obj_init[L.n_obj];
+            o.voxel[0] = int16_t(off.x + rightC[0]); o.voxel[1] = int16_t(off.y + rightC[1]); o.voxel[2] = int16_t(off.z + rightC[2]);
+            o.color = int16_t(paletteIndex(it.color));
+            shapeScale(it.mesh, o.scale);
+            o.meta = it.mesh | ((it.mesh == 4 ? 2 : (it.mesh == 1 ? 3 : 1)) << 3);
+            out.drawSeq.push_back({DrawRef::OBJECT, L.n_obj});
+            ++L.n_obj;
+            ++placed;
+        }
+    }
+    // floor slab between the pedestals and the two pedestals (addStaticCollidingBox, layout_utils.cpp:70-84)
+    auto addBox = [&](float sx, float sy, float sz, float tx, float ty, float tz, uint32_t color) {
+        if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
+        MvBox &sb = L.statics[ns];
+        const float sc[3] = {sx, sy, sz}, t[3] = {tx, ty, tz};
+        for (int a = 0; a < 3; ++a) { sb.c[a] = t[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.0f; }
+        sb.flags = MV_SOLID | MV_OPAQUE; sb.color = paletteIndex(color);
+        out.drawSeq.push_back({DrawRef::STATIC, ns});
+        ++ns;
+    };
+    addBox(8.35f, 0.5f, 5.65f, 9.5f + 0.0f, 0.0f + 1.0f, 7.0f + 0.0f, C_DARK_GREY);
+    const float lc[3] = {float(leftC[0]), float(leftC[1]), float(leftC[2])}, rc[3] = {float(rightC[0]), float(rightC[1]), float(rightC[2])};
+    addBox(3.0f, 0.5f, 3.0f, lc[0] + 0.5f, lc[1] + -0.5f, lc[2] + 0.5f, C_WHITE);
+    addBox(1.5f, 0.5f, 1.5f, lc[0] + 0.5f, lc[1] + -0.45f, lc[2] + 0.5f, C_DARK_GREY);
+    addBox(3.0f, 0.5f, 3.0f, lc[0] + 1.0f, lc[1] + -0.66f, lc[2] + 1.0f, C_WHITE);
+    addBox(3.0f, 0.5f, 3.0f, lc[0] + 1.5f, lc[1] + -0.82f, lc[2] + 1.5f, C_WHITE);
+    addBox(3.0f, 0.5f, 3.0f, rc[0] + 0.5f, rc[1] + -0.5f, rc[2] + 0.5f, C_BLUE);
+    addBox(1.5f, 0.5f, 1.5f, rc[0] + 0.5f, rc[1] + -0.45f, rc[2] + 0.5f, C_DARK_GREY);
+    addBox(3.0f, 0.5f, 3.0f, rc[0] + 0.0f, rc[1] + -0.66f, rc[2] + 1.0f, C_BLUE);
+    addBox(3.0f, 0.5f, 3.0f, rc[0] + -0.5f, rc[1] + -0.82f, rc[2] + 1.5f, C_BLUE);
+    L.n_static = ns;
+    out.drawSeq.push_back({DrawRef::EYES, 0}); out.drawSeq.push_back({DrawRef::BARS, 0}); out.drawSeq.push_back({DrawRef::BODIES, 0});
+
+    L.n_terrain = 0; L.n_reward = 0; L.n_movable = 0;
+    L.episode_len = params_.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
+    L.n_arr = int(items.size());
+    for (int i = 0; i < L.n_arr; ++i) {
+        L.arr[i][0] = int16_t(items[size_t(i)].mesh); L.arr[i][1] = int16_t(paletteIndex(items[size_t(i)].color));
+        L.arr[i][2] = int16_t(items[size_t(i)].off.x); L.arr[i][3] = int16_t(items[size_t(i)].off.y); L.arr[i][4] = int16_t(items[size_t(i)].off.z); L.arr[i][5] = 0;
+    }
+    for (int a = 0; a < 3; ++a) L.work_center[a] = rightC[a];
     L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
     L.grid_dim[0] = length; L.grid_dim[1] = height + 18; L.grid_dim[2] = width;
     fillPlanes(out, &grid);
@@ -496,8 +737,7 @@ void LevelGenerator::generateCollect(LevelOut &out) {
     if (int(objs.size()) > MV_MAX_OBJECTS - 1) throw std::runtime_error("too many movable objects");
     L.n_obj = int(objs.size());
     for (int i = 0; i < L.n_obj; ++i) {
-        L.obj_voxel[i][0] = int16_t(objs[size_t(i)].x); L.obj_voxel[i][1] = int16_t(objs[size_t(i)].y); L.obj_voxel[i][2] = int16_t(objs[size_t(i)].z);
-        L.obj_voxel[i][3] = int16_t(paletteIndex(C_LIGHT_BLUE));
+        setStackingBox(L.obj_init[i], objs[size_t(i)]);
     }
     if (int(rewards.size()) > MV_MAX_REWARD) throw std::runtime_error("too many reward objects");
     L.n_reward = int(rewards.size());
@@ -921,8 +1161,7 @@ void LevelGenerator::generateObstacles(LevelOut &out) {
     L.n_obj = int(objs.size());
     L.n_movable = int(objs.size());
     for (int i = 0; i < L.n_obj; ++i) {
-        L.obj_voxel[i][0] = int16_t(objs[size_t(i)].x); L.obj_voxel[i][1] = int16_t(objs[size_t(i)].y); L.obj_voxel[i][2] = int16_t(objs[size_t(i)].z);
-        L.obj_voxel[i][3] = int16_t(paletteIndex(C_LIGHT_BLUE));
+        setStackingBox(L.obj_init[i], objs[size_t(i)]);
     }
     if (int(rewards.size()) > MV_MAX_REWARD) throw std::runtime_error("too many reward objects");
     L.n_reward = int(rewards.size());

@@ -16,8 +16,12 @@ namespace mv {
 
 using FloatParams = std::map<std::string, float>;
 
+// one entry of a level's draw sequence (insertion order of the reference's drawables); slots are assigned per mesh type
+struct DrawRef { enum Kind { STATIC, TERRAIN, OBJECT, DECO, EYES, BARS, BODIES, REWARDS } kind; int index; };
+
 struct LevelOut {
     MvLevel level;
+    std::vector<DrawRef> drawSeq;  // empty: the default order (opaque statics, terrain, objects, eyes, bars, bodies, rewards)
     std::vector<uint32_t> solid;  // grid_dim product bits, x-major: idx = (x*dimY + y)*dimZ + z
     std::vector<uint32_t> exitBits, lavaBits;  // terrain planes, same indexing
 };
@@ -34,6 +38,8 @@ private:
     void generateTower(LevelOut &out);
     void generateObstacles(LevelOut &out);
     void generateCollect(LevelOut &out);
+    void generateRearrange(LevelOut &out);
+    void assignSlots(LevelOut &out);
     void fillPlanes(LevelOut &out, const void *voxMap);
     int scenario_;
     std::string name_;

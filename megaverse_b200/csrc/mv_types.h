@@ -28,6 +28,10 @@
 #define MV_SCENARIO_TOWER 0
 #define MV_SCENARIO_OBSTACLES 1
 #define MV_SCENARIO_COLLECT 2
+#define MV_SCENARIO_REARRANGE 3
+
+#define MV_MAX_DECO 32      // static drawables that are not axis-aligned layout boxes (other meshes, rotated boxes)
+#define MV_MAX_ARRANGEMENT 8
 
 // voxel / box flags (voxel_state.hpp:10-15)
 #define MV_SOLID 1
@@ -60,6 +64,8 @@
 #define MV_R_COLLECT_BAD 2
 #define MV_R_COLLECT_ALL 3
 #define MV_R_COLLECT_ABYSS 4
+#define MV_R_REARRANGE_ONE_MORE 1
+#define MV_R_REARRANGE_ALL 2
 #define MV_R_COUNT 8
 
 // fault bits (per env, sticky): the engine never exit()s, it reports
@@ -75,6 +81,18 @@ struct MvBox {       // static layout box: drawable (OPAQUE) and/or collider (SO
     float h[3];      // half extents = (max-min+1)/2 * voxelSize          (layout_utils.cpp:24-28)
     int32_t flags;   // MV_SOLID | MV_OPAQUE | (instance slot among the opaque boxes << 8)
     int32_t color;   // palette index
+};
+
+struct MvObjInit {   // a movable object at episode start
+    int16_t voxel[3];
+    int16_t color;   // palette index
+    float scale[3];  // local scale (0.39 for the stacking boxes, component_object_stacking.hpp:172)
+    int32_t meta;    // MvObject::meta
+};
+
+struct MvDeco {      // static drawable with an arbitrary model matrix
+    float model[16];
+    int32_t mesh, color, slot, pad;
 };
 
 struct MvTerrain {
@@ -96,10 +114,21 @@ struct MvLevel {
     int32_t n_reward;              // Obstacles / Collect: reward diamonds
     int32_t n_positive;            // Collect: numPositiveRewards
     int32_t n_opaque;              // number of drawable static boxes (their instance slot is flags >> 8)
-    int32_t pad0[1];               // statics[] must start 16-byte aligned
+    int32_t n_static_pre;          // statics[0 .. n_static_pre) precede the movable objects in collider order, the rest follow them
+    // instance-list layout, assigned by the host so that the list is in the reference's draw order (mesh type major,
+    // insertion order minor): first slot of the terrain slabs, agents' eyes / HUD bars / bodies, reward cones; totals per mesh
+    int32_t slot_terrain, slot_eyes, slot_bars, slot_body, slot_reward;
+    int32_t mesh_counts[5];        // box, capsule, sphere, cone, cylinder instances
+    int32_t n_deco;
+    int32_t n_arr;                 // Rearrange: target arrangement items
+    int16_t arr[MV_MAX_ARRANGEMENT][6];  // mesh, palette colour, offset x y z from the centre
+    int32_t work_center[3];        // Rearrange: rightCenter
+    int32_t n_grid_static;         // statics[0 .. n_grid_static) are the merged boxes of the voxel grid (the rest are free-standing boxes)
+    int32_t pad0[4];               // statics[] must start 16-byte aligned
     MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
     MvTerrain terrain[MV_MAX_TERRAIN];
-    int16_t obj_voxel[MV_MAX_OBJECTS][4];  // x,y,z,color
+    MvObjInit obj_init[MV_MAX_OBJECTS];
+    MvDeco deco[MV_MAX_DECO];
     float spawn_pos[MV_MAX_AGENTS][4];     // ghost origin at spawn (agent.cpp:45)
     float spawn_basis[MV_MAX_AGENTS][12];  // ghost basis rows (btMatrix3x3(btQuaternion(Y, yaw)))
     float init_pos[MV_MAX_AGENTS][4];      // FallDetection agentInitialPositions
@@ -131,8 +160,12 @@ struct MvObject {
     int32_t parent;  // -1 scene, else agent index (child of its pickupSpot)
     int32_t enabled; // collider responds (CF_NO_CONTACT_RESPONSE cleared)
     int32_t color;
-    int32_t pad;
+    int32_t meta;    // bits 0..2 mesh, bits 3..4 collision class (0: scale 1.15 offset (0,-0.05,0); 1: scale 1; 2: scale (1,0.5,1);
+                     // 3: scale (1,2,1)), bits 8.. instance slot
 };
+#define MV_OBJ_MESH(meta) ((meta) & 7)
+#define MV_OBJ_COLCLASS(meta) (((meta) >> 3) & 3)
+#define MV_OBJ_SLOT(meta) ((meta) >> 8)
 
 struct MvEnvState {
     float episode_sec;
@@ -144,7 +177,7 @@ struct MvEnvState {
     int32_t faults;
     // std::unordered_set<VoxelCoords> objectsInBuildingZone, emulated in libstdc++ iteration order (bzset.h)
     int32_t solved;          // Obstacles: all agents reached the exit
-    uint32_t reached_exit;   // Obstacles: bit per agent
+    uint32_t reached_exit;   // Obstacles: bit per agent; Rearrange: maxMatchingObjects
     uint32_t reward_alive[3];  // bit per reward object still in place
     int32_t positive_collected;  // Collect
     int32_t bz_count, bz_nb, bz_next_resize;
@@ -162,7 +195,7 @@ struct MvInstance {
     int32_t color;    // palette index
     int32_t pad[2];
 };
-#define MV_MAX_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 2 * MV_MAX_REWARD)
+#define MV_MAX_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 2 * MV_MAX_REWARD + MV_MAX_DECO)
 
 struct MvConsts {        // host-computed constants (so host libm decides their bits once, identically for oracle and device)
     float look_left[9];  // btMatrix3x3(btQuaternion(Y, +3.5*dt)) rows

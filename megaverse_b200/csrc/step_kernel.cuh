@@ -609,12 +609,31 @@ __device__ float towerReward(const MvEnvState &e) {
     return r;
 }
 
-// RigidBody::syncPose for an object resting in the scene (identity parent): centre = t + offset, half = |s| * 1.15
+// RigidBody::syncPose for an object resting in the scene (identity parent): centre = t + collisionOffset,
+// half = scaling * collisionScale (physics.hpp:69-74); the class selects the pair the scenario set on the body
 __device__ __forceinline__ void syncPoseScene(MvObject &o) {
-    o.col_c[0] = o.t[0] + 0.0f; o.col_c[1] = o.t[1] + -0.05f; o.col_c[2] = o.t[2] + 0.0f;
-    o.col_h[0] = sqrtf(o.s[0] * o.s[0] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.15f;
-    o.col_h[1] = sqrtf(0.0f * 0.0f + o.s[1] * o.s[1] + 0.0f * 0.0f) * 1.15f;
-    o.col_h[2] = sqrtf(0.0f * 0.0f + 0.0f * 0.0f + o.s[2] * o.s[2]) * 1.15f;
+    const int cls = MV_OBJ_COLCLASS(o.meta);
+    const float offY = cls == 0 ? -0.05f : 0.0f;
+    const float sx = cls == 0 ? 1.15f : 1.0f, sy = cls == 0 ? 1.15f : (cls == 2 ? 0.5f : (cls == 3 ? 2.0f : 1.0f)), sz = sx;
+    o.col_c[0] = o.t[0] + 0.0f; o.col_c[1] = o.t[1] + offY; o.col_c[2] = o.t[2] + 0.0f;
+    o.col_h[0] = sqrtf(o.s[0] * o.s[0] + 0.0f * 0.0f + 0.0f * 0.0f) * sx;
+    o.col_h[1] = sqrtf(0.0f * 0.0f + o.s[1] * o.s[1] + 0.0f * 0.0f) * sy;
+    o.col_h[2] = sqrtf(0.0f * 0.0f + 0.0f * 0.0f + o.s[2] * o.s[2]) * sz;
+}
+
+// RearrangeScenario::countMatchingObjects (scenario_rearrange.cpp:134-149): resting objects whose voxel offset from the work
+// centre equals a target item of the same shape and colour
+__device__ int rearrangeCountMatches(const WarpShared &S, const MvLevel &L) {
+    int matches = 0;
+    for (int oi = 0; oi < L.n_obj; ++oi) {
+        const MvObject &ob = S.objects[oi];
+        if (ob.parent >= 0) continue;  // pickedUp
+        const int x = int(lroundf(floorf(ob.t[0]))), y = int(lroundf(floorf(ob.t[1]))), z = int(lroundf(floorf(ob.t[2])));
+        const int ox = x - L.work_center[0], oy = y - L.work_center[1], oz = z - L.work_center[2];
+        for (int q = 0; q < L.n_arr; ++q)
+            if (L.arr[q][0] == MV_OBJ_MESH(ob.meta) && L.arr[q][1] == ob.color && L.arr[q][2] == ox && L.arr[q][3] == oy && L.arr[q][4] == oz) { ++matches; break; }
+    }
+    return matches;
 }
 
 // ---------------------------------------------------------------- episode (re)initialisation from a level slot
@@ -627,10 +646,11 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
     }
     for (int i = lane; i < L.n_obj; i += 32) {
         MvObject &o = S.objects[i];
-        const int x = L.obj_voxel[i][0], y = L.obj_voxel[i][1], z = L.obj_voxel[i][2];
+        const MvObjInit &oi = L.obj_init[i];
+        const int x = oi.voxel[0], y = oi.voxel[1], z = oi.voxel[2];
         o.t[0] = float(x) + 0.5f; o.t[1] = float(y) + 0.5f; o.t[2] = float(z) + 0.5f;
-        o.s[0] = 0.39f; o.s[1] = 0.39f; o.s[2] = 0.39f;
-        o.parent = -1; o.enabled = 1; o.color = L.obj_voxel[i][3]; o.pad = 0;
+        o.s[0] = oi.scale[0]; o.s[1] = oi.scale[1]; o.s[2] = oi.scale[2];
+        o.parent = -1; o.enabled = 1; o.color = oi.color; o.meta = oi.meta;
         syncPoseScene(o);
         const int gi = gridIndex(L, x, y, z);
         if (gi >= 0) objGrid[gi] = uint8_t(i);
@@ -658,11 +678,12 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
         mvBzClear(e);
         if (L.scenario == MV_SCENARIO_TOWER) {
             for (int i = 0; i < L.n_obj; ++i) {
-                const int x = L.obj_voxel[i][0], y = L.obj_voxel[i][1], z = L.obj_voxel[i][2];
+                const int x = L.obj_init[i].voxel[0], y = L.obj_init[i].voxel[1], z = L.obj_init[i].voxel[2];
                 if (inBuildingZone(L, x, z)) mvBzInsert(e, x, y, z);
             }
             e.bz_reward = towerReward(e);
         } else e.bz_reward = 0.0f;
+        if (L.scenario == MV_SCENARIO_REARRANGE) e.reached_exit = uint32_t(rearrangeCountMatches(S, L));  // maxMatchingObjects at episode start
     }
     __syncwarp();
 }
@@ -714,17 +735,16 @@ __device__ __forceinline__ M4 tsMatrix(V3 t, V3 sc) {
 }
 
 __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
-    // static part: opaque layout boxes in order (their slot is precomputed by the host), then terrain slabs
-    const int nOpaque = L.n_opaque;
+    // static part (every slot is precomputed by the host in draw order): opaque layout boxes, terrain slabs, decorations
     if (writeStatic) {
         for (int i = lane; i < L.n_static; i += 32) {
             const MvBox &b = L.statics[i];
             if (!(b.flags & MV_OPAQUE)) continue;
             putInstance(inst[b.flags >> 8], tsMatrix(v3(b.c[0], b.c[1], b.c[2]), v3(b.h[0], b.h[1], b.h[2])), 0, b.color);
         }
-        for (int i = lane; i < L.n_terrain; i += 32) putInstance(inst[nOpaque + i], loadM4(L.terrain[i].model), 0, L.terrain[i].color);
+        for (int i = lane; i < L.n_terrain; i += 32) putInstance(inst[L.slot_terrain + i], loadM4(L.terrain[i].model), 0, L.terrain[i].color);
+        for (int i = lane; i < L.n_deco; i += 32) putInstance(inst[L.deco[i].slot], loadM4(L.deco[i].model), L.deco[i].mesh, L.deco[i].color);
     }
-    const int base = nOpaque + L.n_terrain;
     const int no = L.n_obj;
     // movable objects: everything at reset, afterwards only what can have moved -- carried objects (they follow their
     // agent's camera) and the objects picked up / put down this step
@@ -738,7 +758,7 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
             const MvAgent &a = S.agents[o.parent];
             m = mul4(loadM4(a.object_t), mul4(loadM4(a.cam_local), mul4(pickupLocal(), m)));
         }
-        putInstance(inst[base + i], m, 0, o.color);
+        putInstance(inst[MV_OBJ_SLOT(o.meta)], m, MV_OBJ_MESH(o.meta), o.color);
     }
     // per agent: view matrix, eyes, HUD bar, body.  Every chain keeps the scene graph's right-to-left association;
     // products are formed cooperatively (sixteen lanes per matrix, two matrices per round):
@@ -766,7 +786,7 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
             __syncwarp();
             {  // r2
                 const float v = half == 0 ? mul4Elem(objT, T[0], e) : mul4Elem(T[6], T[1], e);
-                if (half == 0) inst[base + no + i].model[e] = v; else T[2][e] = v;
+                if (half == 0) inst[L.slot_eyes + i].model[e] = v; else T[2][e] = v;
             }
             __syncwarp();
             {  // r3
@@ -776,15 +796,15 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
             __syncwarp();
             {  // r4
                 if (half == 0) views[i * 16 + e] = inv4Elem(T[3], e);  // Camera::cameraMatrix: inverse of the absolute transform
-                else inst[base + no + A + i].model[e] = mul4Elem(objT, T[4], e);
+                else inst[L.slot_bars + i].model[e] = mul4Elem(objT, T[4], e);
             }
             if (half == 0) T[0][e] = bodyE;
             __syncwarp();
-            if (half == 0) inst[base + no + 2 * A + i].model[e] = mul4Elem(objT, T[0], e);  // r5
+            if (half == 0) inst[L.slot_body + i].model[e] = mul4Elem(objT, T[0], e);  // r5
             if (lane >= 16 && lane < 28) {  // mesh / colour / padding words of the three instances
                 const int which = (lane - 16) >> 2, w = (lane - 16) & 3;
                 const int agentColors[7] = {0, 1, 3, 7, 14, 10, 12};  // const.hpp:85 as palette indices
-                MvInstance &d = inst[base + no + which * A + i];
+                MvInstance &d = inst[(which == 0 ? L.slot_eyes : (which == 1 ? L.slot_bars : L.slot_body)) + i];
                 const int mesh = which == 2 ? 1 : 0, color = which == 0 ? 6 : (which == 1 ? 3 : agentColors[i % 7]);  // AGENT_EYES = DARK_NAVY, bar BLUE
                 if (w == 0) d.mesh = mesh; else if (w == 1) d.color = color; else d.pad[w - 2] = 0;
             }
@@ -801,13 +821,14 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
             const float far = L.scenario == MV_SCENARIO_COLLECT ? 500.0f : 1000.0f;
             root = mul4(translation4(v3(far, far, far)), root);
         }
-        putInstance(inst[base + no + 3 * A + 2 * i], root, 3, L.reward_voxel[i][3]);
-        putInstance(inst[base + no + 3 * A + 2 * i + 1], mul4(root, loadM4(L.cone_bottom_local)), 3, L.reward_voxel[i][3]);
+        putInstance(inst[L.slot_reward + 2 * i], root, 3, L.reward_voxel[i][3]);
+        putInstance(inst[L.slot_reward + 2 * i + 1], mul4(root, loadM4(L.cone_bottom_local)), 3, L.reward_voxel[i][3]);
     }
     if (lane == 0) {
-        counts[0] = base + no + 2 * A; counts[1] = base + no + 3 * A + 2 * nr;
-        counts[2] = A; counts[3] = 0; counts[4] = 2 * nr; counts[5] = 0; counts[6] = 0; counts[7] = 0;  // capsules, spheres, cones, cylinders
+        counts[0] = L.mesh_counts[0]; counts[1] = L.mesh_counts[0] + L.mesh_counts[1] + L.mesh_counts[2] + L.mesh_counts[3] + L.mesh_counts[4];
+        counts[2] = L.mesh_counts[1]; counts[3] = L.mesh_counts[2]; counts[4] = L.mesh_counts[3]; counts[5] = L.mesh_counts[4]; counts[6] = 0; counts[7] = 0;
     }
+    (void)no;
 }
 
 // ---------------------------------------------------------------- the kernel
@@ -934,17 +955,19 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
             const V3 envLo = v3(k.pos.x - 3.0f, k.pos.y - 6.0f, k.pos.z - 3.0f), envHi = v3(k.pos.x + 3.0f, k.pos.y + 3.0f, k.pos.z + 3.0f);
             {
                 int nc = 0;
-                const int n = ns + no + A;
+                const int n = ns + no + A, nsPre = L->n_static_pre;
                 for (int base = 0; base < n; base += 32) {
                     const int ci = base + lane;
                     bool keep = false;
                     int kind = 0, agentIdx = 0;
                     V3 c = v3(0, 0, 0), h = v3(0, 0, 0);
-                    if (ci < ns) {
-                        const MvBox &sb = L->statics[ci];  // global memory (L2 resident): scanned once per agent per step
+                    // collider order (= the reference's creation order, which decides ties): the first nsPre static boxes,
+                    // the movable objects, the remaining static boxes, the agents
+                    if (ci < nsPre || (ci >= nsPre + no && ci < ns + no)) {
+                        const MvBox &sb = L->statics[ci < nsPre ? ci : ci - no];  // global memory (L2 resident): scanned once per agent per step
                         if (sb.flags & MV_SOLID) { keep = true; c = v3(sb.c[0], sb.c[1], sb.c[2]); h = v3(sb.h[0], sb.h[1], sb.h[2]); }
-                    } else if (ci < ns + no) {
-                        const MvObject &ob = S.objects[ci - ns];
+                    } else if (ci < nsPre + no) {
+                        const MvObject &ob = S.objects[ci - nsPre];
                         if (ob.enabled) { keep = true; c = v3(ob.col_c[0], ob.col_c[1], ob.col_c[2]); h = v3(ob.col_h[0], ob.col_h[1], ob.col_h[2]); }
                     } else if (ci < n && ci - ns - no != i) {
                         agentIdx = ci - ns - no;
@@ -1007,6 +1030,17 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 for (int j = 0; j < A; ++j) S.lastReward[j] += rt[j * MV_R_COUNT + slotR] * rt[j * MV_R_COUNT + MV_R_TEAM_SPIRIT] * mult / A;
             };
             const float carryingScale = 0.78f, carryingScaleInverse = 1.0f / carryingScale;
+            // RearrangeScenario::checkDone / countMatchingObjects (scenario_rearrange.cpp:134-177)
+            auto rearrangeCheckDone = [&](int agentIdx) {
+                const int matches = rearrangeCountMatches(S, *L);
+                if (matches > int(e.reached_exit)) { rewardTeam(MV_R_REARRANGE_ONE_MORE, agentIdx, 1); e.reached_exit = uint32_t(matches); }
+                if (matches >= L->n_arr && !e.solved) {
+                    e.solved = 1;
+                    rewardTeam(MV_R_REARRANGE_ALL, agentIdx, 1);
+                    const float t = L->episode_len - 0.3f;  // doneWithTimer (scenario.hpp:114-117)
+                    e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
+                }
+            };
             for (int i = 0; i < A; ++i) {
                 if (!(P.actions[size_t(env) * A + i] & MV_A_INTERACT)) continue;
                 MvAgent &a = S.agents[i];
@@ -1032,7 +1066,11 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     auto objAt = [&](int g) { return g >= 0 ? int(objGrid[g]) : int(MV_NO_OBJECT); };
                     const bool empty = !solidAt(gi) && objAt(gi) == MV_NO_OBJECT;
                     // canPlaceObject: TowerBuilding only inside the building zone, default true elsewhere
-                    if (empty && !collidesWithAgent && (L->scenario != MV_SCENARIO_TOWER || inBuildingZone(*L, vx, vz))) {
+                    bool canPlace = true;
+                    if (L->scenario == MV_SCENARIO_TOWER) canPlace = inBuildingZone(*L, vx, vz);
+                    else if (L->scenario == MV_SCENARIO_REARRANGE)  // scenario_rearrange.cpp:128-132
+                        canPlace = abs(vx - L->work_center[0]) <= 2 && abs(vz - L->work_center[2]) <= 2;
+                    if (empty && !collidesWithAgent && canPlace) {
                         while (true) {
                             const int by = vy - 1;
                             if (by < -30) break;
@@ -1058,7 +1096,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                             rewardTeam(MV_R_TOWER_BUILDING, i, delta);
                             const int hgt = vy - L->bz_min[1] + 1;
                             e.highest_tower = e.highest_tower > hgt ? e.highest_tower : hgt;
-                        }
+                        } else if (L->scenario == MV_SCENARIO_REARRANGE) rearrangeCheckDone(i);  // placedObject
                     }
                 } else {
                     const V3 pickup = translationOf(pickAbs);
@@ -1083,7 +1121,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                             if (L->scenario == MV_SCENARIO_TOWER) {  // pickedObject (scenario_tower_building.cpp:216-225)
                                 if (inBuildingZone(*L, vx, vz)) mvBzErase(e, vx, vy, vz);
                                 if (!a.picked_up) { rewardAgent(MV_R_TOWER_PICKED_UP, i, 1); a.picked_up = 1; }
-                            }
+                            } else if (L->scenario == MV_SCENARIO_REARRANGE) rearrangeCheckDone(i);  // pickedObject
                             break;
                         } else vy += 1;
                         ++pickupHeight;
@@ -1108,7 +1146,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 a.hvel[0] = a.hvel[1] = a.hvel[2] = 0.0f;
                 a.vvel = 0;
             };
-            for (int i = 0; i < A; ++i)  // FallDetectionComponent::step
+            for (int i = 0; i < A && L->scenario != MV_SCENARIO_REARRANGE; ++i)  // FallDetectionComponent::step (Rearrange has none)
                 if (S.agents[i].object_t[13] < -20) {
                     resetAgent(i);
                     if (L->scenario == MV_SCENARIO_COLLECT) rewardAgent(MV_R_COLLECT_BAD, i, 1);  // agentFell (scenario_collect.cpp:214-218)

@@ -197,6 +197,7 @@ int orc_get_state(void *p, int envIdx, float *out, int cap) {
         uint32_t reached = 0, alive[3] = {0, 0, 0};
         env.agentReachedExit.resize(size_t(env.numAgents), false);
         for (int i = 0; i < env.numAgents; ++i) reached |= env.agentReachedExit[size_t(i)] ? (1u << i) : 0u;
+        if (env.scenario == Env::S_REARRANGE) reached = uint32_t(env.maxMatchingObjects);
         for (size_t r = 0; r < env.rewardSpawnPositions.size() && r < 96; ++r) {
             const Voxel *v = env.vg.grid.get(env.rewardSpawnPositions[r]);
             if (v && v->rewardObject == int(r)) alive[r >> 5] |= 1u << (r & 31);
@@ -206,6 +207,22 @@ int orc_get_state(void *p, int envIdx, float *out, int cap) {
     }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(float));
+    return int(o.size());
+}
+
+// Rearrange: [0] = items n, then per item 5 ints (shape, palette colour, offset3); then objects m and per object 2 ints
+// (shape, palette colour); then the work centre (3 ints) -- lets a test script a solving policy
+int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(envIdx)];
+    std::vector<int32_t> o;
+    o.push_back(int(env.arrangement.size()));
+    for (auto &it : env.arrangement)
+        for (int x : {it.shape, paletteIndex(it.color), int(it.offset.x), int(it.offset.y), int(it.offset.z)}) o.push_back(x);
+    o.push_back(int(env.arrangementObjects.size()));
+    for (int obj : env.arrangementObjects) { o.push_back(env.objects[size_t(obj)].mesh); o.push_back(env.objects[size_t(obj)].color); }
+    for (int x : {int(env.rightCenter.x), int(env.rightCenter.y), int(env.rightCenter.z)}) o.push_back(x);
+    if (int(o.size()) > cap) return -int(o.size());
+    std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
     return int(o.size());
 }
 

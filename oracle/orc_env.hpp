@@ -12,6 +12,7 @@
 #pragma once
 #include <cfloat>
 #include <cstdio>
+#include <queue>
 #include <stdexcept>
 
 #include "orc_level.hpp"
@@ -29,6 +30,15 @@ struct Instance {  // one drawable: mesh type, palette colour, model matrix (abs
     int mesh;
     int color;  // palette index
     Mat4 model;
+};
+
+// DrawablesMap (env.hpp:57-67,72): mesh type -> drawables in insertion order.  An entry names the scene-graph object whose
+// absolute transformation is the model matrix at draw time.
+struct DrawEntry {
+    enum Kind { D_STATIC, D_OBJECT, D_EYES, D_BAR, D_BODY, D_REWARD_ROOT, D_REWARD_BOTTOM } kind;
+    int index;
+    int color;
+    Mat4 model;  // D_STATIC
 };
 
 struct Agent {
@@ -91,6 +101,9 @@ struct MovableObject {
     Vec3 collisionScale{1.15f, 1.15f, 1.15f}, collisionOffset{0, -0.05f, 0};
     int collider = -1;
     int color = 0;
+    int mesh = MESH_BOX;
+    ColorRgb arrangementColor = WHITE;
+    bool pickedUp = false;  // ArrangementObject (scenario_rearrange.hpp:60-71)
 };
 
 struct StaticBox { BoundingBox bb; uint8_t type; ColorRgb color; };
@@ -100,8 +113,10 @@ using RewardShaping = std::map<std::string, float>;
 
 class Env {
 public:
-    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2 };
+    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3 };
     enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
+    struct RewardObject { Mat4 root, bottomLocal; int color; };
+    struct ArrangementItem { int shape = MESH_SPHERE; ColorRgb color = WHITE; VoxelCoords offset{0, 0, 0}; };  // scenario_rearrange.hpp:20-53
 
     Env(const std::string &scenarioName, int numAgents, const FloatParams &custom) : numAgents(numAgents) {
         std::string n;
@@ -112,6 +127,7 @@ public:
         floatParams["useUIRewardIndicators"] = 0.0f;
         if (n == "towerbuilding") scenario = S_TOWER;
         else if (n == "collect") scenario = S_COLLECT;
+        else if (n == "rearrange") scenario = S_REARRANGE;
         else if (n.rfind("obstacles", 0) == 0 || n == "test") {
             // ObstaclesScenario::initializeDefaultParameters + the registered variants (scenario_obstacles.hpp:48-270, init.hpp:33-56)
             scenario = S_OBSTACLES;
@@ -151,6 +167,8 @@ public:
         if (scenario == S_OBSTACLES)  // scenario_obstacles.hpp:37-45,201-206
             return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f},
                     {"obstaclesAgentCarriedObjectToExit", onePlatformType ? 1.0f : 0.0f}};
+        if (scenario == S_REARRANGE)  // scenario_rearrange.hpp:91-97
+            return {{"rearrangeOneMoreObjectCorrectPosition", 1.0f}, {"rearrangeAllObjectsCorrectPosition", 10.0f}};
         // scenario_tower_building.hpp:44-52
         return {{"teamSpirit", 0.1f}, {"towerPickedUpObject", 0.1f}, {"towerVisitedBuildingZoneWithObject", 0.1f}, {"towerBuildingReward", 1.0f}};
     }
@@ -163,15 +181,193 @@ public:
         std::fill(currAction.begin(), currAction.end(), 0);
         std::fill(lastReward.begin(), lastReward.end(), 0.0f);
         std::fill(totalReward.begin(), totalReward.end(), 0.0f);
-        agents.clear(); colliders.clear(); objects.clear(); staticBoxes.clear(); terrainSlabs.clear(); rewardObjects.clear();
+        agents.clear(); colliders.clear(); objects.clear(); staticBoxes.clear(); terrainSlabs.clear(); rewardObjects.clear(); drawables.clear();
 
         auto sd = randRange(0, 1 << 30, rng);
         rng.seed((unsigned long)sd);
 
-        if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else collectReset();
+        if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else if (scenario == S_COLLECT) collectReset(); else rearrangeReset();
         spawnAgents();
-        if (scenario == S_TOWER) towerAddEpisodeDrawables(); else if (scenario == S_OBSTACLES) obstaclesAddEpisodeDrawables(); else collectAddEpisodeDrawables();
+        if (scenario == S_TOWER) towerAddEpisodeDrawables(); else if (scenario == S_OBSTACLES) obstaclesAddEpisodeDrawables();
+        else if (scenario == S_COLLECT) collectAddEpisodeDrawables(); else rearrangeAddEpisodeDrawables();
         addAgentsAndUI();
+    }
+
+    // ---------------------------------------------------------------- Rearrange (scenario_rearrange.cpp:46-300)
+    static ArrangementItem randomArrangementItem(Rng &rng, const VoxelCoords &offset) {  // scenario_rearrange.hpp:31-46
+        static const std::vector<int> shapes{MESH_CYLINDER, MESH_CAPSULE, MESH_BOX, MESH_SPHERE};
+        ArrangementItem item;
+        item.shape = randomSample(shapes, rng);
+        item.color = randomObjectColor(rng);
+        item.offset = offset;
+        return item;
+    }
+    void rearrangeReset() {
+        solved = false;
+        vg.reset();
+        carryingObject.assign(size_t(numAgents), -1);
+        levelRoot = std::make_unique<Node>();
+        rearrangePlatform = std::make_unique<RearrangePlatform>(levelRoot.get(), rng, WALLS_ALL, floatParams);
+        rearrangePlatform->init(), rearrangePlatform->generate();
+        vg.addPlatform(*rearrangePlatform, DARK_GREY, DARK_GREY, randomBool(rng));
+        arrangement.clear();
+        arrangementObjects.clear();
+        generateArrangement();
+        // DefaultScenario::spawnAgents asks the scenario for the positions first (scenario_default.hpp:80-97)
+        agentSpawnPositions.assign(size_t(numAgents), Vec3{0, 0, 0});
+        for (int i = 0; i < numAgents; ++i)
+            for (int attempt = 0; attempt < 20; ++attempt) {  // :179-200
+                int agentX = randRange(2, rearrangePlatform->length - 1, rng);
+                int agentZ = randRange(2, rearrangePlatform->width - 1, rng);
+                if (std::fabs(agentX - leftCenter.x) < 2 && std::fabs(agentZ - leftCenter.z) < 2) continue;
+                if (std::fabs(agentX - rightCenter.x) < 2 && std::fabs(agentZ - rightCenter.z) < 2) continue;
+                agentSpawnPositions[size_t(i)] = Vec3{float(agentX), 2, float(agentZ)};
+                break;
+            }
+        agentInitialPositions = agentSpawnPositions;
+        objectSpawnPositions.clear(); rewardSpawnPositions.clear();
+    }
+    void generateArrangement() {  // :70-126
+        const int arrangementSize = randRange(2, 8, rng);
+        std::queue<ArrangementItem> q;
+        std::unordered_set<VoxelCoords, VoxelHash> used;
+        const auto firstItem = randomArrangementItem(rng, {0, 0, 0});
+        q.push(firstItem);
+        arrangement.emplace_back(firstItem);
+        used.insert({0, 0, 0});
+        std::vector<VoxelCoords> directions{{-1, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1}};
+        while (!q.empty()) {
+            const auto currItem = q.front();
+            q.pop();
+            int maxBranches = randRange(1, int(directions.size()) + 1, rng);
+            maxBranches = randRange(1, maxBranches + 1, rng);
+            int numBranches = 0;
+            std::shuffle(directions.begin(), directions.end(), rng);
+            for (auto dir : directions) {
+                const VoxelCoords newOffset(currItem.offset.x + dir.x, currItem.offset.y + dir.y, currItem.offset.z + dir.z);
+                const VoxelCoords below(newOffset.x, newOffset.y - 1, newOffset.z);
+                if (newOffset.y >= 2 || std::abs(newOffset.x) >= 2 || std::abs(newOffset.z) >= 2) continue;
+                if (used.count(newOffset)) continue;
+                if (!(newOffset.y == 0 || used.count(below))) continue;
+                const auto newItem = randomArrangementItem(rng, newOffset);
+                q.push(newItem);
+                arrangement.emplace_back(newItem);
+                used.insert(newOffset);
+                ++numBranches;
+                if (numBranches >= maxBranches) break;
+                if (int(arrangement.size()) >= arrangementSize) break;
+            }
+            if (int(arrangement.size()) >= arrangementSize) break;
+        }
+    }
+    bool arrangementContains(int shape, ColorRgb color, const VoxelCoords &offset) const {  // scenario_rearrange.hpp:77-84
+        for (const auto &item : arrangement)
+            if (item.shape == shape && item.color == color && item.offset == offset) return true;
+        return false;
+    }
+    int countMatchingObjects() const {  // :134-149
+        int matching = 0;
+        for (int obj : arrangementObjects) {
+            if (objects[size_t(obj)].pickedUp) continue;
+            const VoxelCoords voxelCoords = vg.grid.getCoords(translationOf(objectAbs(obj)));
+            const VoxelCoords offset(voxelCoords.x - rightCenter.x, voxelCoords.y - rightCenter.y, voxelCoords.z - rightCenter.z);
+            if (arrangementContains(objects[size_t(obj)].mesh, objects[size_t(obj)].arrangementColor, offset)) ++matching;
+        }
+        return matching;
+    }
+    void rearrangeCheckDone(int agentIdx) {  // :163-177
+        const auto matches = countMatchingObjects();
+        if (matches > maxMatchingObjects) {
+            rewardTeam("rearrangeOneMoreObjectCorrectPosition", agentIdx, 1);
+            maxMatchingObjects = matches;
+        }
+        if (matches >= int(arrangement.size()) && !solved) {
+            solved = true;
+            rewardTeam("rearrangeAllObjectsCorrectPosition", agentIdx, 1);
+            doneWithTimer();
+        }
+    }
+    void arrangementDrawables(VoxelCoords center, bool interactive) {  // :202-263
+        auto shapeScale = [](int shape) {
+            if (shape == MESH_CAPSULE) return Vec3{0.8f, 0.5f, 0.8f};
+            if (shape == MESH_CYLINDER) return Vec3{0.9f, 2, 0.9f};
+            return Vec3{1, 1, 1};
+        };
+        const auto objSize = 0.45f;
+        std::unordered_set<VoxelCoords, VoxelHash> occupied;
+        for (const auto &item : arrangement) occupied.insert(item.offset);
+        int numUnmovedItems = int(arrangement.size());
+        if (interactive) numUnmovedItems = randRange(0, int(arrangement.size()), rng);
+        int placedItems = 0;
+        for (const auto &item : arrangement) {
+            VoxelCoords pos(item.offset.x + center.x, item.offset.y + center.y, item.offset.z + center.z);
+            if (interactive && placedItems >= numUnmovedItems) {
+                VoxelCoords newOffset = item.offset;
+                while (occupied.count(newOffset)) {
+                    const int rx = randRange(-2, 3, rng);  // braced initialiser: left to right
+                    const int rz = randRange(-2, 3, rng);
+                    newOffset = VoxelCoords(rx, 0, rz);
+                }
+                pos = VoxelCoords(newOffset.x + center.x, newOffset.y + center.y, newOffset.z + center.z);
+                occupied.insert(newOffset);
+            }
+            const Vec3 translation{float(pos.x) + 0.5f, float(pos.y) + 0.5f, float(pos.z) + 0.5f};
+            MovableObject o;
+            o.local = mul(mat4Translation(translation), mul(mat4Scaling(shapeScale(item.shape) * objSize), mat4Identity()));
+            o.collisionScale = item.shape == MESH_CYLINDER ? Vec3{1, 0.5f, 1} : (item.shape == MESH_CAPSULE ? Vec3{1, 2, 1} : Vec3{1, 1, 1});
+            o.collisionOffset = Vec3{0, 0, 0};
+            o.color = paletteIndex(item.color);
+            o.arrangementColor = item.color;
+            o.mesh = item.shape;
+            o.collider = int(colliders.size());
+            colliders.push_back(Collider{});
+            if (interactive) {
+                objects.push_back(o);
+                const int idx = int(objects.size()) - 1;
+                syncPose(idx);
+                drawables[item.shape].push_back({DrawEntry::D_OBJECT, idx, o.color, mat4Identity()});
+                Voxel voxelState;
+                voxelState.physicsObject = idx;
+                vg.grid.set(pos, voxelState);
+                arrangementObjects.emplace_back(idx);
+                objectSpawnPositions.push_back(pos);  // (introspection only: Rearrange's episode length does not use it)
+            } else {  // never picked up: a static collider + drawable
+                Collider &c = colliders.back();
+                c.kind = 0;
+                c.c = translationOf(o.local) + o.collisionOffset;
+                c.h = scalingOf(o.local) * o.collisionScale;
+                drawables[item.shape].push_back({DrawEntry::D_STATIC, 0, o.color, o.local});
+            }
+            ++placedItems;
+        }
+    }
+    void rearrangeAddEpisodeDrawables() {  // :265-300
+        addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
+        for (int dx = -3; dx <= 3; ++dx)
+            for (int dz = -3; dz <= 3; ++dz) {
+                Voxel voxelState;
+                voxelState.voxelType = VOXEL_SOLID;
+                vg.grid.set(VoxelCoords(leftCenter.x + dx, 1, leftCenter.z + dz), voxelState);
+                vg.grid.set(VoxelCoords(rightCenter.x + dx, 1, rightCenter.z + dz), voxelState);
+            }
+        arrangementDrawables(leftCenter, false);
+        arrangementDrawables(rightCenter, true);
+        maxMatchingObjects = countMatchingObjects();
+        const Vec3 platformCenter{9.5f, 0, 7};
+        const Vec3 lc{float(leftCenter.x), float(leftCenter.y), float(leftCenter.z)}, rc{float(rightCenter.x), float(rightCenter.y), float(rightCenter.z)};
+        addStaticCollidingBox({8.35f, 0.5f, 5.65f}, platformCenter + Vec3{0.0f, 1, 0.0f}, DARK_GREY);
+        addStaticCollidingBox({3, 0.5f, 3}, lc + Vec3{0.5f, -0.5f, 0.5f}, LAYOUT_DEFAULT);
+        addStaticCollidingBox({1.5f, 0.5f, 1.5f}, lc + Vec3{0.5f, -0.45f, 0.5f}, DARK_GREY);
+        addStaticCollidingBox({3, 0.5f, 3}, lc + Vec3{1.0f, -0.66f, 1.0f}, LAYOUT_DEFAULT);
+        addStaticCollidingBox({3, 0.5f, 3}, lc + Vec3{1.5f, -0.82f, 1.5f}, LAYOUT_DEFAULT);
+        addStaticCollidingBox({3, 0.5f, 3}, rc + Vec3{0.5f, -0.5f, 0.5f}, BLUE);
+        addStaticCollidingBox({1.5f, 0.5f, 1.5f}, rc + Vec3{0.5f, -0.45f, 0.5f}, DARK_GREY);
+        addStaticCollidingBox({3, 0.5f, 3}, rc + Vec3{0, -0.66f, 1.0f}, BLUE);
+        addStaticCollidingBox({3, 0.5f, 3}, rc + Vec3{-0.5f, -0.82f, 1.5f}, BLUE);
+    }
+    void rearrangeStep() {  // ObjectStackingComponent::step (component_object_stacking.hpp:45-56)
+        for (int i = 0; i < numAgents; ++i)
+            if (currAction[i] & A_Interact) onInteractAction(i);
     }
 
     // ---------------------------------------------------------------- Collect (scenario_collect.cpp:20-218)
@@ -252,6 +448,7 @@ public:
             ro.bottomLocal = mul(mat4Translation({0.0f, -1.0f, 0.0f}), mul(mat4Identity(), mat4RotationX(180.0f * 3.14159265358979323846f / 180.0f)));
             ro.root = mul(mat4Translation(translation), mul(mat4Scaling({0.17f, 0.45f, 0.17f}), mat4Identity()));
             voxel.rewardObject = int(rewardObjects.size());
+            addRewardDrawables(ro);
             rewardObjects.push_back(ro);
             vg.grid.set(pos, voxel);
         }
@@ -384,7 +581,7 @@ public:
         addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
         for (auto &platform : platforms)
             for (auto &[terrainType, boxes] : platform->terrainBoxes)
-                for (auto &bb : boxes) terrainSlabs.push_back({terrainType, bb.boundingBox()});
+                for (auto &bb : boxes) addTerrain(terrainType, bb.boundingBox());
         addObjects(objectSpawnPositions);
         for (const auto &pos : rewardSpawnPositions) {
             // addDiamond (layout_utils.cpp:114-126): two cones, the lower one rotated 180 deg about X and shifted -1 in y
@@ -396,6 +593,7 @@ public:
             ro.color = paletteIndex(GREEN);
             if (!vg.grid.hasVoxel(pos)) vg.grid.set(pos, Voxel{});
             vg.grid.get(pos)->rewardObject = int(rewardObjects.size());
+            addRewardDrawables(ro);
             rewardObjects.push_back(ro);
         }
     }
@@ -526,7 +724,7 @@ public:
     void towerAddEpisodeDrawables() {
         addDrawablesAndCollisionObjectsFromVoxelGrid(1.0f);
         for (auto &[terrainType, boxes] : platform->terrainBoxes)
-            for (auto &bb : boxes) terrainSlabs.push_back({terrainType, bb.boundingBox()});
+            for (auto &bb : boxes) addTerrain(terrainType, bb.boundingBox());
         const auto objectPositions = objectSpawnPositions;
         for (const auto &pos : objectPositions)
             if (isInBuildingZone(pos)) objectsInBuildingZone.insert(pos);
@@ -540,6 +738,9 @@ public:
             if (info.type == VOXEL_EMPTY) continue;
             for (auto &box : boxes) {
                 staticBoxes.push_back({box, info.type, info.color});
+                if (info.type & VOXEL_OPAQUE)
+                    drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(info.color),
+                                                   mul(mat4Translation(staticBoxTranslation(box, voxelSize)), mul(mat4Scaling(staticBoxScale(box, voxelSize)), mat4Identity()))});
                 if (info.type & VOXEL_SOLID) {
                     Collider c;
                     c.kind = 0;
@@ -557,6 +758,33 @@ public:
         return Vec3{float(b.min.x + b.max.x) / 2 + 0.5f, float(b.min.y + b.max.y) / 2 + 0.5f, float(b.min.z + b.max.z) / 2 + 0.5f} * vs;
     }
 
+    void addTerrain(int terrain, const BoundingBox &bb) {  // layout_utils.cpp:53-68
+        terrainSlabs.push_back({terrain, bb});
+        const Vec3 scale = Vec3{float(bb.max.x - bb.min.x), 1.0f, float(bb.max.z - bb.min.z)} * 1.0f;
+        if (scale.x > 0) {
+            const Vec3 pos{bb.min.x * 1.0f + scale.x / 2, bb.min.y * 1.0f, bb.min.z * 1.0f + scale.z / 2};
+            Mat4 m = mul(mat4Scaling({0.5f, 0.025f, 0.5f}), mat4Identity());
+            m = mul(mat4Scaling(scale), m);
+            m = mul(mat4Translation({0.0f, 0.025f, 0.0f}), m);
+            m = mul(mat4Translation(pos), m);
+            drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(terrainColor(terrain)), m});
+        }
+    }
+    void addRewardDrawables(const RewardObject &ro) {  // addDiamond: root, then its bottom half (layout_utils.cpp:122-123)
+        const int idx = int(rewardObjects.size());
+        drawables[MESH_CONE].push_back({DrawEntry::D_REWARD_ROOT, idx, ro.color, mat4Identity()});
+        drawables[MESH_CONE].push_back({DrawEntry::D_REWARD_BOTTOM, idx, ro.color, mat4Identity()});
+    }
+    void addStaticCollidingBox(Vec3 scale, Vec3 translation, ColorRgb color) {  // layout_utils.cpp:70-84
+        const Mat4 m = mul(mat4Translation(translation), mul(mat4Scaling(scale), mat4Identity()));
+        drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(color), m});
+        Collider c;
+        c.kind = 0;
+        c.c = translationOf(m) + Vec3{0, 0, 0};
+        c.h = scalingOf(m) * Vec3{1, 1, 1};
+        colliders.push_back(c);
+    }
+
     void addObjects(const std::vector<VoxelCoords> &positions) {  // component_object_stacking.hpp:170-198
         const float objSize = 0.39f;
         for (const auto &pos : positions) {
@@ -567,6 +795,7 @@ public:
             o.collider = int(colliders.size());
             colliders.push_back(Collider{});
             objects.push_back(o);
+            drawables[MESH_BOX].push_back({DrawEntry::D_OBJECT, int(objects.size()) - 1, o.color, mat4Identity()});
             syncPose(int(objects.size()) - 1);
             if (!vg.grid.hasVoxel(pos)) vg.grid.set(pos, Voxel{});
             vg.grid.get(pos)->physicsObject = int(objects.size()) - 1;
@@ -595,6 +824,9 @@ public:
             a.barAnchorLocal = mul(mat4Translation({0, -0.131f, 0}), mat4Identity());
             a.barLocal = mul(mat4Identity(), mat4Scaling({0.24f, float(0.0015), float(0.001)}));
         }
+        for (int i = 0; i < numAgents; ++i) drawables[MESH_BOX].push_back({DrawEntry::D_EYES, i, paletteIndex(AGENT_EYES), mat4Identity()});
+        for (int i = 0; i < numAgents; ++i) drawables[MESH_BOX].push_back({DrawEntry::D_BAR, i, paletteIndex(BLUE), mat4Identity()});
+        for (int i = 0; i < numAgents; ++i) drawables[MESH_CAPSULE].push_back({DrawEntry::D_BODY, i, agents[i].color, mat4Identity()});
         agentColliderBase = int(colliders.size());
         for (int i = 0; i < numAgents; ++i) {
             Collider c;
@@ -632,7 +864,7 @@ public:
         }
         for (auto &a : agents) a.updateTransform();
 
-        if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else collectStep();
+        if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else if (scenario == S_COLLECT) collectStep(); else rearrangeStep();
 
         currEpisodeSec += lastFrameDurationSec;
         updateUI();
@@ -643,6 +875,7 @@ public:
     }
 
     float episodeLengthSec() const {
+        if (scenario == S_REARRANGE) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
         if (scenario == S_COLLECT) return floatParams.at("episodeLengthSec") + 2.0f * rewardSpawnPositions.size();  // scenario_collect.hpp:52-56
         if (scenario == S_OBSTACLES)  // scenario_obstacles.cpp:262-266
             return std::max(floatParams.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objectSpawnPositions.size()) * 1);
@@ -733,7 +966,10 @@ public:
             }
             const bool empty = !voxelPtr || (voxelPtr->empty() && voxelPtr->physicsObject < 0);
             // canPlaceObject: TowerBuilding only inside the building zone (scenario_tower_building.cpp:201-204), else the default (true)
-            if (empty && !collidesWithAgent && (scenario != S_TOWER || isInBuildingZone(voxel))) {
+            bool canPlace = true;
+            if (scenario == S_TOWER) canPlace = isInBuildingZone(voxel);
+            else if (scenario == S_REARRANGE) canPlace = std::abs(voxel.x - rightCenter.x) <= 2 && std::abs(voxel.z - rightCenter.z) <= 2;  // scenario_rearrange.cpp:128-132
+            if (empty && !collidesWithAgent && canPlace) {
                 while (true) {
                     VoxelCoords below{voxel.x, voxel.y - 1, voxel.z};
                     if (below.y < -30) break;
@@ -753,6 +989,7 @@ public:
                 colliders[o.collider].enabled = !colliders[o.collider].enabled;  // toggleCollision
                 carryingObject[agentIdx] = -1;
                 if (scenario == S_TOWER) placedObject(agentIdx, voxel);
+                else if (scenario == S_REARRANGE) { objects[obj].pickedUp = false; rearrangeCheckDone(agentIdx); }  // :151-155
             }
         } else {
             const Vec3 pickup = translationOf(agent.pickupAbs());
@@ -774,6 +1011,7 @@ public:
                     carryingObject[agentIdx] = obj;
                     voxelPtr->physicsObject = -1;
                     if (scenario == S_TOWER) pickedObject(agentIdx, voxel);
+                    else if (scenario == S_REARRANGE) { objects[obj].pickedUp = true; rearrangeCheckDone(agentIdx); }  // :157-161
                     break;
                 } else {
                     voxel = voxelAbove;
@@ -803,36 +1041,28 @@ public:
     // SceneGraph::Object::setClean(objects) (right-to-left composition up the parent chain, v4r_env_renderer.cpp:319-335).
     std::vector<Instance> instances() const {
         std::vector<Instance> out;
-        for (auto &sb : staticBoxes)
-            if (sb.type & VOXEL_OPAQUE)
-                out.push_back({MESH_BOX, paletteIndex(sb.color), mul(mat4Translation(staticBoxTranslation(sb.bb, 1.0f)), mul(mat4Scaling(staticBoxScale(sb.bb, 1.0f)), mat4Identity()))});
-        for (auto &ts : terrainSlabs) {  // layout_utils.cpp:53-68
-            const Vec3 scale = Vec3{float(ts.bb.max.x - ts.bb.min.x), 1.0f, float(ts.bb.max.z - ts.bb.min.z)} * 1.0f;
-            if (scale.x > 0) {
-                const Vec3 pos{ts.bb.min.x * 1.0f + scale.x / 2, ts.bb.min.y * 1.0f, ts.bb.min.z * 1.0f + scale.z / 2};
-                Mat4 m = mul(mat4Scaling({0.5f, 0.025f, 0.5f}), mat4Identity());
-                m = mul(mat4Scaling(scale), m);
-                m = mul(mat4Translation({0.0f, 0.025f, 0.0f}), m);
-                m = mul(mat4Translation(pos), m);
-                out.push_back({MESH_BOX, paletteIndex(terrainColor(ts.terrain)), m});
+        for (auto &[mesh, list] : drawables)
+            for (auto &d : list) {
+                Mat4 m = d.model;
+                switch (d.kind) {
+                    case DrawEntry::D_STATIC: break;
+                    case DrawEntry::D_OBJECT: {
+                        const MovableObject &o = objects[size_t(d.index)];
+                        m = o.local;
+                        if (o.parentAgent >= 0) {
+                            const Agent &a = agents[size_t(o.parentAgent)];
+                            m = mul(a.objectT, mul(a.cameraLocal, mul(a.pickupLocal, o.local)));
+                        }
+                        break;
+                    }
+                    case DrawEntry::D_EYES: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, mul(a.cameraLocal, a.eyesLocal)); break; }
+                    case DrawEntry::D_BAR: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, mul(a.cameraLocal, mul(a.uiLocal, mul(a.barAnchorLocal, a.barLocal)))); break; }
+                    case DrawEntry::D_BODY: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, a.bodyLocal); break; }
+                    case DrawEntry::D_REWARD_ROOT: m = rewardObjects[size_t(d.index)].root; break;
+                    case DrawEntry::D_REWARD_BOTTOM: m = mul(rewardObjects[size_t(d.index)].root, rewardObjects[size_t(d.index)].bottomLocal); break;
+                }
+                out.push_back({mesh, d.color, m});
             }
-        }
-        for (int i = 0; i < int(objects.size()); ++i) {
-            const MovableObject &o = objects[i];
-            Mat4 m = o.local;
-            if (o.parentAgent >= 0) {
-                const Agent &a = agents[o.parentAgent];
-                m = mul(a.objectT, mul(a.cameraLocal, mul(a.pickupLocal, o.local)));
-            }
-            out.push_back({MESH_BOX, o.color, m});
-        }
-        for (auto &a : agents) out.push_back({MESH_BOX, paletteIndex(AGENT_EYES), mul(a.objectT, mul(a.cameraLocal, a.eyesLocal))});
-        for (auto &a : agents) out.push_back({MESH_BOX, paletteIndex(BLUE), mul(a.objectT, mul(a.cameraLocal, mul(a.uiLocal, mul(a.barAnchorLocal, a.barLocal))))});
-        for (auto &a : agents) out.push_back({MESH_CAPSULE, a.color, mul(a.objectT, a.bodyLocal)});
-        for (auto &ro : rewardObjects) {  // DrawableType::Cone, insertion order: root then its bottom half (layout_utils.cpp:122-123)
-            out.push_back({MESH_CONE, ro.color, ro.root});
-            out.push_back({MESH_CONE, ro.color, mul(ro.root, ro.bottomLocal)});
-        }
         return out;
     }
     Mat4 viewMatrix(int agentIdx) const { return inverted(agents[agentIdx].cameraAbs()); }  // Camera::cameraMatrix
@@ -857,6 +1087,13 @@ public:
     std::vector<MovableObject> objects;
     std::vector<StaticBox> staticBoxes;
     std::vector<TerrainSlab> terrainSlabs;
+    std::map<int, std::vector<DrawEntry>> drawables;
+    // Rearrange
+    std::unique_ptr<RearrangePlatform> rearrangePlatform;
+    std::vector<ArrangementItem> arrangement;
+    std::vector<int> arrangementObjects;
+    int maxMatchingObjects = 0;
+    const VoxelCoords leftCenter{5, 2, 5}, rightCenter{13, 2, 5};
 
     VoxelGridComponent vg;
     std::vector<int> carryingObject;
@@ -874,7 +1111,6 @@ public:
     std::vector<bool> agentReachedExit;
     bool solved = false;
     int numPlatforms = 0;
-    struct RewardObject { Mat4 root, bottomLocal; int color; };
     int numPositiveRewards = 0, positiveRewardsCollected = 0;  // Collect
     std::vector<RewardObject> rewardObjects;
 

@@ -279,6 +279,13 @@ public:
 
 template <typename T> T triangularNumber(T n) { return n * (n + 1) / 2; }  // util/math_utils.hpp
 
+class RearrangePlatform : public EmptyPlatform {  // scenario_rearrange.cpp:11-34
+public:
+    RearrangePlatform(Node *parent, Rng &rng, int walls, const FloatParams &params) : EmptyPlatform(parent, rng, walls, params) {}
+    void init() override { height = randRange(4, 7, rng); length = 19; width = 14; }
+    void generate() override { EmptyPlatform::generate(); }
+};
+
 class WallPlatform : public EmptyPlatform {  // platforms.hpp:332-373
 public:
     WallPlatform(Node *parent, Rng &rng, int walls, const FloatParams &params, int w = -1) : EmptyPlatform(parent, rng, walls, params, w) {}

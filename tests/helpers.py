@@ -45,3 +45,57 @@ def purposeful_actions(rng, n, step):
             m |= (1 << 9) if rng.random() < 0.6 else (1 << 10)
         out[i] = m
     return out
+
+
+def rearrange_controller(o, e, A):
+    """one action mask per agent of env e: fetch a misplaced object, carry it to its target cell on the work pedestal"""
+    st = o.state(e); arr = o.arrangement(e)
+    n = arr[0]; items = arr[1:1+5*n].reshape(n,5); m = arr[1+5*n]; objs = arr[2+5*n:2+5*n+2*m].reshape(m,2); wc = arr[2+5*n+2*m:]
+    nobj = int(st[5]); base = 8 + 26*A
+    O = st[base:base+9*nobj].reshape(nobj,9)
+    out = np.zeros(A, dtype=np.int32)
+    # which target offsets are already satisfied / free
+    vox = np.floor(O[:, :3]).astype(int) - wc
+    for a in range(A):
+        ag = st[8+26*a: 8+26*(a+1)]
+        pos = ag[0:3]; b = ag[3:12]; fwd = np.array([b[6], -b[8]]); fwd /= (np.linalg.norm(fwd)+1e-9)
+        carrying = int(ag[22])
+        if a > 0:  # the other agents wander
+            out[a] = 1 << 3 if (int(st[2]) // 7 + a) % 3 else 1 << 5
+            continue
+        if carrying < 0:
+            # choose an object that is not at a matching offset
+            cand = None
+            for i in range(nobj):
+                ok = any((items[q,0]==objs[i,0] and items[q,1]==objs[i,1] and (items[q,2:5]==vox[i]).all()) for q in range(n))
+                if not ok and O[i,6] < 0:
+                    cand = i; break
+            if cand is None:
+                continue
+            tgt = O[cand, [0,2]]; want_dist = 1.0
+        else:
+            i = carrying
+            # free target offset of the same shape+colour
+            tgt = None
+            for q in range(n):
+                if items[q,0]==objs[i,0] and items[q,1]==objs[i,1]:
+                    taken = any((vox[j]==items[q,2:5]).all() and O[j,6] < 0 for j in range(nobj))
+                    if not taken and items[q,3]==0:
+                        tgt = (items[q,2:5]+wc)[[0,2]] + 0.5; break
+            if tgt is None:
+                continue
+            want_dist = 1.0
+        d = tgt - pos[[0,2]]; dist = np.linalg.norm(d)
+        ang = np.arctan2(fwd[0]*d[1]-fwd[1]*d[0], fwd[0]*d[0]+fwd[1]*d[1])
+        mask = 0
+        if abs(ang) > 0.12:
+            mask |= (1<<6) if ang > 0 else (1<<5)
+        elif dist > want_dist + 0.15:
+            mask |= 1<<3
+        elif dist < want_dist - 0.25:
+            mask |= 1<<4
+        else:
+            mask |= 1<<8
+        out[a] = mask
+    return out
+

@@ -106,6 +106,9 @@ class Oracle:
     def state(self, env):
         return self._dump("orc_get_state", env, np.float32)
 
+    def arrangement(self, env):
+        return self._dump("orc_get_arrangement", env, np.int32)
+
     def voxels(self, env):
         return self._dump("orc_get_voxels", env, np.int32).reshape(-1, 4)
 

@@ -315,3 +315,71 @@ def test_async_device_loop_matches_oracle(built):
     _assert_same_state(o, g, E, "sync step after async")
     assert _assert_same_frame(o, g, "sync step after async") == 1.0
     o.close(); g.close()
+
+
+@pytest.mark.parametrize("A", [1, 3])
+def test_rearrange_reset_parity(built, A):
+    """Rearrange: target arrangement (static colliders + sphere / capsule / cylinder / box drawables), its interactive copy,
+    pedestals; draw order = the reference's insertion order per mesh type"""
+    E = 8
+    o, g = _pair("Rearrange", E, A, 5)
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.voxels(e), g.voxels(e)), "voxels %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("policy", ["purposeful", "heads"])
+def test_rearrange_trajectory_parity(built, policy):
+    """pick up / put down arrangement objects (placement only on the work pedestal), matching-count rewards, solved + timer"""
+    E, A, steps = 12, 2, 900
+    o, g = _pair("Rearrange", E, A, 31)
+    rng = np.random.default_rng(12)
+    total, interactions = 0.0, 0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t) if policy == "purposeful" else helpers.random_head_actions(rng, E * A)
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        total += float(np.abs(ro).sum())
+        if t % 60 == 0 or t == steps - 1 or o.dones().any():
+            _assert_same_state(o, g, E, "step %d" % t)
+            for e in range(0, E, 5):
+                assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "step %d instances %d" % (t, e)
+                assert np.array_equal(o.voxels(e), g.voxels(e)), "step %d voxels %d" % (t, e)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+def test_rearrange_solved_by_script(built):
+    """a scripted agent (driven from the oracle's state) fetches misplaced objects and puts them on their target cells:
+    exercises canPlaceObject, the matching count, rearrangeOneMoreObjectCorrectPosition / rearrangeAllObjectsCorrectPosition
+    with the team-spirit split, doneWithTimer and the true objective -- identical on both sides"""
+    E, A, steps = 8, 2, 420
+    o, g = _pair("Rearrange", E, A, 3)
+    total, solved = 0.0, 0
+    for t in range(steps):
+        acts = np.concatenate([helpers.rearrange_controller(o, e, A) for e in range(E)])
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        total += float(np.abs(ro).sum())
+        if o.dones().any():
+            solved += int((o.true_objectives().reshape(E, A)[:, 0] * o.dones()).sum())
+        if float(np.abs(ro).sum()) > 0 or o.dones().any() or t % 50 == 0:
+            _assert_same_state(o, g, E, "step %d" % t)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+    assert total >= 5.0 and solved >= 1, (total, solved)
+    assert g.faults() == 0
+    o.close(); g.close()
