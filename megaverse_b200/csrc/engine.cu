@@ -500,7 +500,12 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
         std::vector<std::pair<std::string, float>> ordered(m.begin(), m.end());
         e->shaping.assign(size_t(e->N), ordered);
     }
-    for (int i = 0; i < e->E; ++i) e->gens.emplace_back(e->scenarioName, e->A, e->params);
+    try {
+        for (int i = 0; i < e->E; ++i) e->gens.emplace_back(e->scenarioName, e->A, e->params);
+    } catch (const std::exception &ex) {  // e.g. Sokoban without a Boxoban dataset (the reference exit()s here, scenario_sokoban.cpp:76-78)
+        e->setError(ex.what());
+        return fail(MV_ERR_ARG);
+    }
     e->levelWords.assign(size_t(e->E) * 2, 0);
     e->pool.reset(new WorkerPool(e->threads));
     e->gridCells = mv::gridCapacity(sc);
@@ -782,8 +787,9 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     for (int i = 0; i < L.n_grid_static; ++i) {
         const MvBox &b = L.statics[i];
         // invert centre/half back to inclusive voxel bounds: min = c - h, max = c + h - 1
-        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
-        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
+        const float vs = L.scenario == MV_SCENARIO_SOKOBAN ? 2.0f : 1.0f;  // voxel size of the scenario's grid
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] - b.h[a]) / vs)));
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] + b.h[a]) / vs)) - 1);
         o.push_back(b.flags & 255); o.push_back(int(pal[b.color]));
     }
     for (int i = 0; i < L.n_terrain; ++i) {
@@ -868,7 +874,8 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
                 int flags = 0;
                 if ((sol[idx >> 5] >> (idx & 31)) & 1u) {
                     flags |= 1;
-                    const float cx = x + L.grid_org[0] + 0.5f, cy = y + L.grid_org[1] + 0.5f, cz = z + L.grid_org[2] + 0.5f;
+                    const float vs = L.scenario == MV_SCENARIO_SOKOBAN ? 2.0f : 1.0f;
+                    const float cx = (x + L.grid_org[0] + 0.5f) * vs, cy = (y + L.grid_org[1] + 0.5f) * vs, cz = (z + L.grid_org[2] + 0.5f) * vs;
                     for (int i = 0; i < L.n_grid_static; ++i) {
                         const MvBox &b = L.statics[i];
                         if (fabsf(cx - b.c[0]) < b.h[0] && fabsf(cy - b.c[1]) < b.h[1] && fabsf(cz - b.c[2]) < b.h[2]) { flags |= (b.flags & MV_OPAQUE); break; }
@@ -996,8 +1003,9 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
     for (int i = 0; i < L.n_grid_static; ++i) {
         const MvBox &b = L.statics[i];
-        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] - b.h[a])));
-        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf(b.c[a] + b.h[a])) - 1);
+        const float vs = L.scenario == MV_SCENARIO_SOKOBAN ? 2.0f : 1.0f;  // voxel size of the scenario's grid
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] - b.h[a]) / vs)));
+        for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] + b.h[a]) / vs)) - 1);
         o.push_back(b.flags & 255); o.push_back(int(kPaletteRgb[b.color]));
     }
     for (int i = 0; i < L.n_terrain; ++i) {

@@ -12,6 +12,10 @@
 #include "levelgen.hpp"
 
 #include <algorithm>
+#include <array>
+#include <cstdio>
+#include <fstream>
+#include <iterator>
 #include <cstring>
 #include <set>
 #include <stdexcept>
@@ -163,6 +167,7 @@ int scenarioFromName(const std::string &name) {
     if (n == "towerbuilding") return MV_SCENARIO_TOWER;
     if (n == "collect") return MV_SCENARIO_COLLECT;
     if (n == "rearrange") return MV_SCENARIO_REARRANGE;
+    if (n == "sokoban") return MV_SCENARIO_SOKOBAN;
     if (n == "obstacleseasy" || n == "obstaclesmedium" || n == "obstacleshard" || n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava" || n == "test")
         return MV_SCENARIO_OBSTACLES;
     return -1;
@@ -172,6 +177,7 @@ int scenarioFromName(const std::string &name) {
 FloatParams defaultFloatParams(const std::string &name) {
     const std::string n = lower(name);
     FloatParams fp{{"episodeLengthSec", 60.0f}, {"verticalLookLimitRad", 0.2f}, {"useUIRewardIndicators", 0.0f}};
+    if (scenarioFromName(n) == MV_SCENARIO_SOKOBAN) fp["episodeLengthSec"] = 80.0f;  // scenario_sokoban.hpp:50-54
     if (scenarioFromName(n) == MV_SCENARIO_OBSTACLES) {
         fp["obstaclesMinNumPlatforms"] = 1; fp["obstaclesMaxNumPlatforms"] = 2; fp["obstaclesMinGap"] = 1; fp["obstaclesMaxGap"] = 2;
         fp["obstaclesMinLava"] = 1; fp["obstaclesMaxLava"] = 4; fp["obstaclesMinHeight"] = 1; fp["obstaclesMaxHeight"] = 3;
@@ -204,6 +210,8 @@ std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::strin
     }
     if (scenario == MV_SCENARIO_REARRANGE)  // scenario_rearrange.hpp:91-97
         return {{"rearrangeOneMoreObjectCorrectPosition", 1.0f}, {"rearrangeAllObjectsCorrectPosition", 10.0f}};
+    if (scenario == MV_SCENARIO_SOKOBAN)  // scenario_sokoban.hpp:41-48
+        return {{"sokobanBoxOnTarget", 1.0f}, {"sokobanBoxLeavesTarget", -1.0f}, {"sokobanAllBoxesOnTarget", 10.0f}};
     return {};
 }
 
@@ -226,6 +234,11 @@ int rewardSlot(int scenario, const std::string &key) {
         if (key == "obstaclesExtraReward") return MV_R_OBST_EXTRA;
         if (key == "obstaclesAgentCarriedObjectToExit") return MV_R_OBST_CARRIED_TO_EXIT;
     }
+    if (scenario == MV_SCENARIO_SOKOBAN) {
+        if (key == "sokobanBoxOnTarget") return MV_R_SOKOBAN_ON_TARGET;
+        if (key == "sokobanBoxLeavesTarget") return MV_R_SOKOBAN_LEAVES_TARGET;
+        if (key == "sokobanAllBoxesOnTarget") return MV_R_SOKOBAN_ALL;
+    }
     if (scenario == MV_SCENARIO_REARRANGE) {
         if (key == "rearrangeOneMoreObjectCorrectPosition") return MV_R_REARRANGE_ONE_MORE;
         if (key == "rearrangeAllObjectsCorrectPosition") return MV_R_REARRANGE_ALL;
@@ -238,12 +251,33 @@ int gridCapacity(int scenario) {
     // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
     // Collect: <= 41 x 41 landscape, heights <= 18, 16 cells of margin (objects can be put down beyond the edge), y from -30
     // Rearrange: 19 x (6+18) x 14 room
-    const int cells = (scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE) ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
+    // Sokoban: Boxoban rooms are 10 x 10 cells (voxel size 2), y in [-2, 6)
+    const int cells = (scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE || scenario == MV_SCENARIO_SOKOBAN) ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
     return ((cells + 127) / 128) * 128;
 }
 
 LevelGenerator::LevelGenerator(const std::string &scenarioName, int numAgents, const FloatParams &params)
-    : scenario_(scenarioFromName(scenarioName)), name_(lower(scenarioName)), numAgents_(numAgents), params_(params) {}
+    : scenario_(scenarioFromName(scenarioName)), name_(lower(scenarioName)), numAgents_(numAgents), params_(params) {
+    if (scenario_ == MV_SCENARIO_SOKOBAN) {  // SokobanScenario constructor (scenario_sokoban.cpp:39-81)
+        const char *envvar = std::getenv("BOXOBAN_LEVELS");
+        std::string dir = (envvar && std::strlen(envvar)) ? envvar : "~/datasets/boxoban";
+        const auto tilde = dir.find('~');
+        if (tilde != std::string::npos) {
+            const char *home = std::getenv("HOME");
+            if (!home || !std::strlen(home)) throw std::runtime_error("could not query HOME to resolve ~ in the path to the Boxoban levels");
+            dir.replace(tilde, 1, home);
+        }
+        const std::string dirWithLevels = dir + "/unfiltered/train";  // levelSet / levelSplit (scenario_sokoban.hpp:59)
+        for (int levelFileIdx = 0; levelFileIdx <= 999; ++levelFileIdx) {
+            char name[16];
+            std::snprintf(name, sizeof name, "%03d.txt", levelFileIdx);
+            const std::string path = dirWithLevels + "/" + name;
+            if (std::ifstream(path).good()) sokobanFiles_.push_back(path);
+        }
+        if (sokobanFiles_.empty())
+            throw std::runtime_error("could not find any Boxoban levels: set BOXOBAN_LEVELS or unpack the boxoban folder (unfiltered/medium/hard) into ~/datasets");
+    }
+}
 
 void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     std::memset(&out.level, 0, sizeof(MvLevel));
@@ -259,10 +293,15 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
         case MV_SCENARIO_OBSTACLES: generateObstacles(out); break;
         case MV_SCENARIO_COLLECT: generateCollect(out); break;
         case MV_SCENARIO_REARRANGE: generateRearrange(out); break;
+        case MV_SCENARIO_SOKOBAN: generateSokoban(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
     MvLevel &L = out.level;
     if (scenario_ != MV_SCENARIO_REARRANGE) L.n_grid_static = L.n_static;
+    if (scenario_ == MV_SCENARIO_SOKOBAN) {  // objects sit where the generator put them
+    } else
+        for (int i = 0; i < L.n_obj; ++i)
+            for (int a = 0; a < 3; ++a) L.obj_init[i].pos[a] = float(L.obj_init[i].voxel[a]) + 0.5f;
     assignSlots(out);
     if (L.grid_dim[0] * L.grid_dim[1] * L.grid_dim[2] > gridCells) throw std::runtime_error("level exceeds the dense grid capacity");
 }
@@ -580,6 +619,129 @@ void LevelGenerator::generateRearrange(LevelOut &out) {
     for (int a = 0; a < 3; ++a) L.work_center[a] = rightC[a];
     L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
     L.grid_dim[0] = length; L.grid_dim[1] = height + 18; L.grid_dim[2] = width;
+    fillPlanes(out, &grid);
+}
+
+// SokobanScenario (scenario_sokoban.cpp:83-295): Boxoban rooms on a voxel grid of size 2; boxes are pushed, not carried.
+void LevelGenerator::generateSokoban(LevelOut &out) {
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    const float voxelSize = 2;
+    if (sokobanLevels_.empty()) {  // reloadLevels (:83-105)
+        const std::string &path = sokobanFiles_[size_t(randRange(0, int(sokobanFiles_.size()), rng))];
+        std::ifstream f{path, std::ios::in | std::ios::binary};
+        const std::string content((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        if (content.empty()) throw std::runtime_error("could not read the level file " + path);
+        std::vector<std::string> lines;  // splitString on "\n" (strtok_r: empty lines vanish)
+        for (size_t pos = 0; pos < content.size();) {
+            const size_t e = content.find('\n', pos);
+            const std::string tok = content.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+            if (!tok.empty()) lines.push_back(tok);
+            if (e == std::string::npos) break;
+            pos = e + 1;
+        }
+        std::vector<std::string> level;
+        for (int i = 0; i < int(lines.size()); ++i) {
+            if (lines[size_t(i)].find(';') == 0) {
+                if (i > 0) sokobanLevels_.push_back(std::move(level));  // (the file's last level is never taken, as upstream)
+                level.clear();
+            } else level.push_back(lines[size_t(i)]);
+        }
+        std::shuffle(sokobanLevels_.begin(), sokobanLevels_.end(), rng);
+    }
+    if (sokobanLevels_.empty()) throw std::runtime_error("Boxoban file without levels");
+    const std::vector<std::string> rows = sokobanLevels_.back();
+    sokobanLevels_.pop_back();
+
+    // createLayout (:118-166)
+    static const uint32_t floorColors[5] = {C_WHITE, C_VL_YELLOW, C_VL_BLUE, C_VL_ORANGE, C_DARK_GREY};
+    const uint32_t floorColor = floorColors[randRange(0, 5, rng)];
+    VoxMap grid{100};
+    const int length = int(rows.size());
+    int width = 0;
+    std::vector<std::array<float, 3>> agentPos;
+    std::vector<I3> boxes;
+    for (int x = 0; x < length; ++x) {
+        const std::string &row = rows[size_t(x)];
+        width = std::max(width, int(row.size()));
+        for (int z = 0; z < int(row.size()); ++z) {
+            Vox fl; fl.type = MV_SOLID | MV_OPAQUE; fl.color = floorColor;
+            grid[voxKey(x, 0, z)] = fl;
+            const char ch = row[size_t(z)];
+            if (ch == '#') {
+                for (int y = 1; y <= 2; ++y) { Vox w; w.type = MV_SOLID; grid[voxKey(x, y, z)] = w; }
+                grid[voxKey(x, 1, z)].terrain = 1;  // SOKO_WALL
+            }
+            if (ch == '@' || ch == '+')
+                for (int i = 0; i < A; ++i) {
+                    const float ax = float(x) + float(i % 2) * 0.5f, az = float(z) + float(i % 4 > 1) * 0.5f;
+                    agentPos.push_back({ax * voxelSize, float(voxelSize + 0.3 * float(i) * voxelSize), az * voxelSize});
+                }
+            if (ch == '.' || ch == '+') { Vox gvx; gvx.type = 0; gvx.terrain = 2; grid[voxKey(x, 1, z)] = gvx; }  // SOKO_GOAL
+            if (ch == '$' || ch == '*') boxes.push_back({x, 1, z});
+        }
+    }
+    agentPos.resize(size_t(A), std::array<float, 3>{0, 0, 0});
+    for (int i = 0; i < A; ++i) {  // DefaultScenario::spawnAgents
+        const float yaw = frand(rng) * 3.14159265358979323846f * 2;
+        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        const float sx = agentPos[size_t(i)][0] + 0.5f, sy = agentPos[size_t(i)][1] + 0.0f, sz = agentPos[size_t(i)][2] + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        for (int a = 0; a < 3; ++a) L.init_pos[i][a] = agentPos[size_t(i)][size_t(a)];
+    }
+
+    // addEpisodeDrawables (:229-295): merged boxes (voxel size 2), terrain markers, pushable boxes
+    int ns = 0;
+    for (const auto &g : mergeVoxels(grid)) {
+        if (g.type == 0) continue;
+        for (const auto &b : g.boxes) {
+            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
+            MvBox &sb = L.statics[ns];
+            for (int a = 0; a < 3; ++a) {
+                sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * voxelSize;
+                sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * voxelSize;
+            }
+            sb.flags = g.type;
+            sb.color = paletteIndex(g.color);
+            if (g.type & MV_OPAQUE) out.drawSeq.push_back({DrawRef::STATIC, ns});
+            ++ns;
+        }
+    }
+    L.n_static = ns; L.n_static_pre = ns; L.n_grid_static = ns;
+    L.n_deco = 0;
+    for (int x = 0; x < length; ++x)
+        for (int z = 0; z < width; ++z) {
+            const auto it = grid.find(voxKey(x, 1, z));
+            if (it == grid.end() || it->second.terrain == 0) continue;
+            if (L.n_deco >= MV_MAX_DECO) throw std::runtime_error("too many terrain markers");
+            const float h = it->second.terrain == 1 ? 0.35f : 0.025f;
+            const float pos[3] = {voxelSize * float(x) + voxelSize / 2, voxelSize, voxelSize * float(z) + voxelSize / 2};
+            mvh::M4 m = mvh::mul(mvh::scaling(1.0f, h, 1.0f), mvh::identity());
+            m = mvh::mul(mvh::translation(0.0f, h, 0.0f), m);
+            m = mvh::mul(mvh::translation(pos[0], pos[1], pos[2]), m);
+            MvDeco &d = L.deco[L.n_deco];
+            std::memcpy(d.model, &m.c[0][0], 64);
+            d.mesh = 0; d.color = paletteIndex(it->second.terrain == 1 ? C_LIGHT_ORANGE : C_LIGHT_GREEN); d.slot = 0; d.pad = 0;
+            out.drawSeq.push_back({DrawRef::DECO, L.n_deco});
+            ++L.n_deco;
+        }
+    if (int(boxes.size()) > MV_MAX_OBJECTS - 1) throw std::runtime_error("too many boxes");
+    L.n_obj = int(boxes.size());
+    for (int i = 0; i < L.n_obj; ++i) {
+        MvObjInit &o = L.obj_init[i];
+        o.voxel[0] = int16_t(boxes[size_t(i)].x); o.voxel[1] = int16_t(boxes[size_t(i)].y); o.voxel[2] = int16_t(boxes[size_t(i)].z);
+        o.color = int16_t(paletteIndex(C_DARK_BLUE));
+        const float sc[3] = {voxelSize / 2, 0.45f, voxelSize / 2}, tr[3] = {float(boxes[size_t(i)].x) + 0.5f, float(boxes[size_t(i)].y) + 0.2f, float(boxes[size_t(i)].z) + 0.5f};
+        for (int a = 0; a < 3; ++a) { o.scale[a] = sc[a] * 0.8f; o.pos[a] = tr[a] * voxelSize; }
+        o.meta = 0 | (4 << 3);  // box mesh, collision scale (1.15,3,1.15) offset (0,0.6,0)
+        out.drawSeq.push_back({DrawRef::OBJECT, i});
+    }
+    out.drawSeq.push_back({DrawRef::EYES, 0}); out.drawSeq.push_back({DrawRef::BARS, 0}); out.drawSeq.push_back({DrawRef::BODIES, 0});
+    L.n_terrain = 0; L.n_reward = 0; L.n_movable = 0;
+    L.episode_len = params_.at("episodeLengthSec");
+    L.grid_org[0] = -2; L.grid_org[1] = -2; L.grid_org[2] = -2;
+    L.grid_dim[0] = length + 4; L.grid_dim[1] = 8; L.grid_dim[2] = width + 4;
     fillPlanes(out, &grid);
 }
 

@@ -39,6 +39,7 @@ private:
     void generateObstacles(LevelOut &out);
     void generateCollect(LevelOut &out);
     void generateRearrange(LevelOut &out);
+    void generateSokoban(LevelOut &out);
     void assignSlots(LevelOut &out);
     void fillPlanes(LevelOut &out, const void *voxMap);
     int scenario_;
@@ -46,6 +47,9 @@ private:
     int numAgents_;
     FloatParams params_;
     std::mt19937 rng_{std::random_device{}()};
+    // Sokoban: Boxoban level files found at construction, and the shuffled levels not played yet (scenario_sokoban.cpp:39-116)
+    std::vector<std::string> sokobanFiles_;
+    std::vector<std::vector<std::string>> sokobanLevels_;
 };
 
 int scenarioFromName(const std::string &name);  // -1 if unknown

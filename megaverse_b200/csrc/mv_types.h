@@ -29,8 +29,9 @@
 #define MV_SCENARIO_OBSTACLES 1
 #define MV_SCENARIO_COLLECT 2
 #define MV_SCENARIO_REARRANGE 3
+#define MV_SCENARIO_SOKOBAN 4
 
-#define MV_MAX_DECO 32      // static drawables that are not axis-aligned layout boxes (other meshes, rotated boxes)
+#define MV_MAX_DECO 128     // static drawables that are not axis-aligned layout boxes (other meshes, rotated boxes)
 #define MV_MAX_ARRANGEMENT 8
 
 // voxel / box flags (voxel_state.hpp:10-15)
@@ -66,6 +67,9 @@
 #define MV_R_COLLECT_ABYSS 4
 #define MV_R_REARRANGE_ONE_MORE 1
 #define MV_R_REARRANGE_ALL 2
+#define MV_R_SOKOBAN_ON_TARGET 1
+#define MV_R_SOKOBAN_LEAVES_TARGET 2
+#define MV_R_SOKOBAN_ALL 3
 #define MV_R_COUNT 8
 
 // fault bits (per env, sticky): the engine never exit()s, it reports
@@ -88,6 +92,7 @@ struct MvObjInit {   // a movable object at episode start
     int16_t color;   // palette index
     float scale[3];  // local scale (0.39 for the stacking boxes, component_object_stacking.hpp:172)
     int32_t meta;    // MvObject::meta
+    float pos[3];    // local translation (voxel + 0.5 for objects that sit in the middle of their voxel)
 };
 
 struct MvDeco {      // static drawable with an arbitrary model matrix
@@ -160,11 +165,11 @@ struct MvObject {
     int32_t parent;  // -1 scene, else agent index (child of its pickupSpot)
     int32_t enabled; // collider responds (CF_NO_CONTACT_RESPONSE cleared)
     int32_t color;
-    int32_t meta;    // bits 0..2 mesh, bits 3..4 collision class (0: scale 1.15 offset (0,-0.05,0); 1: scale 1; 2: scale (1,0.5,1);
-                     // 3: scale (1,2,1)), bits 8.. instance slot
+    int32_t meta;    // bits 0..2 mesh, bits 3..5 collision class (0: scale 1.15 offset (0,-0.05,0); 1: scale 1; 2: scale (1,0.5,1);
+                     // 3: scale (1,2,1); 4: scale (1.15,3,1.15) offset (0,0.6,0)), bits 8.. instance slot
 };
 #define MV_OBJ_MESH(meta) ((meta) & 7)
-#define MV_OBJ_COLCLASS(meta) (((meta) >> 3) & 3)
+#define MV_OBJ_COLCLASS(meta) (((meta) >> 3) & 7)
 #define MV_OBJ_SLOT(meta) ((meta) >> 8)
 
 struct MvEnvState {
@@ -179,7 +184,7 @@ struct MvEnvState {
     int32_t solved;          // Obstacles: all agents reached the exit
     uint32_t reached_exit;   // Obstacles: bit per agent; Rearrange: maxMatchingObjects
     uint32_t reward_alive[3];  // bit per reward object still in place
-    int32_t positive_collected;  // Collect
+    int32_t positive_collected;  // Collect; Sokoban: numBoxesOnGoal
     int32_t bz_count, bz_nb, bz_next_resize;
     int16_t bz_items[MV_MAX_OBJECTS][4];
     int32_t pad[2];

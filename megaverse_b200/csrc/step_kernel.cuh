@@ -613,8 +613,8 @@ __device__ float towerReward(const MvEnvState &e) {
 // half = scaling * collisionScale (physics.hpp:69-74); the class selects the pair the scenario set on the body
 __device__ __forceinline__ void syncPoseScene(MvObject &o) {
     const int cls = MV_OBJ_COLCLASS(o.meta);
-    const float offY = cls == 0 ? -0.05f : 0.0f;
-    const float sx = cls == 0 ? 1.15f : 1.0f, sy = cls == 0 ? 1.15f : (cls == 2 ? 0.5f : (cls == 3 ? 2.0f : 1.0f)), sz = sx;
+    const float offY = cls == 0 ? -0.05f : (cls == 4 ? 0.6f : 0.0f);
+    const float sx = (cls == 0 || cls == 4) ? 1.15f : 1.0f, sy = cls == 0 ? 1.15f : (cls == 2 ? 0.5f : (cls == 3 ? 2.0f : (cls == 4 ? 3.0f : 1.0f))), sz = sx;
     o.col_c[0] = o.t[0] + 0.0f; o.col_c[1] = o.t[1] + offY; o.col_c[2] = o.t[2] + 0.0f;
     o.col_h[0] = sqrtf(o.s[0] * o.s[0] + 0.0f * 0.0f + 0.0f * 0.0f) * sx;
     o.col_h[1] = sqrtf(0.0f * 0.0f + o.s[1] * o.s[1] + 0.0f * 0.0f) * sy;
@@ -648,7 +648,7 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
         MvObject &o = S.objects[i];
         const MvObjInit &oi = L.obj_init[i];
         const int x = oi.voxel[0], y = oi.voxel[1], z = oi.voxel[2];
-        o.t[0] = float(x) + 0.5f; o.t[1] = float(y) + 0.5f; o.t[2] = float(z) + 0.5f;
+        o.t[0] = oi.pos[0]; o.t[1] = oi.pos[1]; o.t[2] = oi.pos[2];
         o.s[0] = oi.scale[0]; o.s[1] = oi.scale[1]; o.s[2] = oi.scale[2];
         o.parent = -1; o.enabled = 1; o.color = oi.color; o.meta = oi.meta;
         syncPoseScene(o);
@@ -1041,7 +1041,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
                 }
             };
-            for (int i = 0; i < A; ++i) {
+            for (int i = 0; i < A && L->scenario != MV_SCENARIO_SOKOBAN; ++i) {  // ObjectStackingComponent (Sokoban has none)
                 if (!(P.actions[size_t(env) * A + i] & MV_A_INTERACT)) continue;
                 MvAgent &a = S.agents[i];
                 const M4 objT = loadM4(a.object_t), cam = loadM4(a.cam_local);
@@ -1146,12 +1146,62 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 a.hvel[0] = a.hvel[1] = a.hvel[2] = 0.0f;
                 a.vvel = 0;
             };
-            for (int i = 0; i < A && L->scenario != MV_SCENARIO_REARRANGE; ++i)  // FallDetectionComponent::step (Rearrange has none)
+            for (int i = 0; i < A && L->scenario != MV_SCENARIO_REARRANGE && L->scenario != MV_SCENARIO_SOKOBAN; ++i)  // FallDetectionComponent::step (Rearrange, Sokoban: none)
                 if (S.agents[i].object_t[13] < -20) {
                     resetAgent(i);
                     if (L->scenario == MV_SCENARIO_COLLECT) rewardAgent(MV_R_COLLECT_BAD, i, 1);  // agentFell (scenario_collect.cpp:214-218)
                 }
-            if (L->scenario == MV_SCENARIO_TOWER) {
+            if (L->scenario == MV_SCENARIO_SOKOBAN) {
+                // SokobanScenario::step (scenario_sokoban.cpp:168-222): push the box in front of the agent one cell further.  The grid
+                // has voxelSize 2; terrain plane 1 = SOKO_WALL, plane 2 = SOKO_GOAL
+                auto vox2 = [&](V3 p, int &x, int &y, int &z) { toVoxel(v3(p.x / 2.0f, p.y / 2.0f, p.z / 2.0f), x, y, z); };
+                for (int i = 0; i < A; ++i) {
+                    if (!(P.actions[size_t(env) * A + i] & MV_A_INTERACT)) continue;
+                    const MvAgent &a = S.agents[i];
+                    const M4 pickAbs = mul4(mul4(loadM4(a.object_t), loadM4(a.cam_local)), pickupLocal());
+                    int bx, by, bz;
+                    vox2(translationOf(pickAbs), bx, by, bz);
+                    const int gb = gridIndex(*L, bx, by, bz);
+                    if (gb < 0 || objGrid[gb] == MV_NO_OBJECT) continue;
+                    int ax, ay, az;
+                    vox2(v3(a.object_t[12], a.object_t[13], a.object_t[14]), ax, ay, az);
+                    if (abs(ax - bx) + abs(ay - by) + abs(az - bz) != 1) continue;
+                    const int dx = bx - ax, dy = by - ay, dz = bz - az;
+                    const int tx = bx + dx, ty = by + dy, tz = bz + dz;
+                    bool occupied = false;
+                    for (int j = 0; j < A; ++j) {
+                        int cx, cy, cz;
+                        vox2(v3(S.agents[j].object_t[12], S.agents[j].object_t[13], S.agents[j].object_t[14]), cx, cy, cz);
+                        if (cx == tx && cy == ty && cz == tz) { occupied = true; break; }
+                    }
+                    if (occupied) continue;
+                    const int gt = gridIndex(*L, tx, ty, tz);
+                    if (gt < 0) { e.faults |= MV_FAULT_GRID_RANGE; continue; }
+                    if (planeBit(1, gt) || objGrid[gt] != MV_NO_OBJECT) continue;  // wall, or another box
+                    const int oi = objGrid[gb];
+                    MvObject &o = S.objects[oi];
+                    objGrid[gt] = uint8_t(oi); objGrid[gb] = MV_NO_OBJECT;
+                    // parent()->translate(delta * voxelSize): T(v) * (T(t) * S(s)) -- translation column = v*1 + t summed as the product does
+                    const M4 moved = mul4(translation4(v3(float(dx) * 2.0f, float(dy) * 2.0f, float(dz) * 2.0f)), tsMatrix(v3(o.t[0], o.t[1], o.t[2]), v3(o.s[0], o.s[1], o.s[2])));
+                    o.t[0] = moved.c[12]; o.t[1] = moved.c[13]; o.t[2] = moved.c[14];
+                    syncPoseScene(o);
+                    S.objDirty[S.nDirty++] = oi;
+                    const bool fromGoal = planeBit(2, gb), toGoal = planeBit(2, gt);
+                    if (!fromGoal && toGoal) {
+                        e.positive_collected += 1;
+                        rewardTeam(MV_R_SOKOBAN_ON_TARGET, i, 1);
+                        if (e.positive_collected == no && !e.solved) {
+                            e.solved = 1;
+                            rewardTeam(MV_R_SOKOBAN_ALL, i, 1);
+                            const float t = L->episode_len - 0.3f;  // doneWithTimer()
+                            e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
+                        }
+                    } else if (fromGoal && !toGoal) {
+                        e.positive_collected -= 1;
+                        rewardTeam(MV_R_SOKOBAN_LEAVES_TARGET, i, 1);
+                    }
+                }
+            } else if (L->scenario == MV_SCENARIO_TOWER) {
                 // shaping: carrying an object inside the building zone (scenario_tower_building.cpp:184-198)
                 for (int i = 0; i < A; ++i) {
                     MvAgent &a = S.agents[i];

@@ -12,6 +12,8 @@
 #pragma once
 #include <cfloat>
 #include <cstdio>
+#include <cstring>
+#include <fstream>
 #include <queue>
 #include <stdexcept>
 
@@ -113,7 +115,9 @@ using RewardShaping = std::map<std::string, float>;
 
 class Env {
 public:
-    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3 };
+    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3, S_SOKOBAN = 4 };
+    enum SokobanTerrain { SOKO_EMPTY = 0, SOKO_WALL = 1, SOKO_GOAL = 2 };
+    struct SokobanLevel { std::vector<std::string> rows; };
     enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
     struct RewardObject { Mat4 root, bottomLocal; int color; };
     struct ArrangementItem { int shape = MESH_SPHERE; ColorRgb color = WHITE; VoxelCoords offset{0, 0, 0}; };  // scenario_rearrange.hpp:20-53
@@ -128,6 +132,27 @@ public:
         if (n == "towerbuilding") scenario = S_TOWER;
         else if (n == "collect") scenario = S_COLLECT;
         else if (n == "rearrange") scenario = S_REARRANGE;
+        else if (n == "sokoban") {  // scenario_sokoban.cpp:39-81, scenario_sokoban.hpp:50-54
+            scenario = S_SOKOBAN;
+            floatParams["episodeLengthSec"] = 80.0f;
+            vg = VoxelGridComponent(100, 0, 0, 0, 2);
+            const char *envvar = std::getenv("BOXOBAN_LEVELS");
+            std::string dir = (envvar && std::strlen(envvar)) ? envvar : "~/datasets/boxoban";
+            const auto tilde = dir.find('~');
+            if (tilde != std::string::npos) {
+                const char *home = std::getenv("HOME");
+                if (!home || !std::strlen(home)) throw std::runtime_error("oracle: HOME not set");
+                dir.replace(tilde, 1, home);
+            }
+            const std::string dirWithLevels = dir + "/unfiltered/train";
+            for (int levelFileIdx = 0; levelFileIdx <= 999; ++levelFileIdx) {
+                char name[16];
+                std::snprintf(name, sizeof name, "%03d.txt", levelFileIdx);
+                const std::string path = dirWithLevels + "/" + name;
+                if (std::ifstream(path).good()) allSokobanLevelFiles.emplace_back(path);
+            }
+            if (allSokobanLevelFiles.empty()) throw std::runtime_error("oracle: no Boxoban levels (set BOXOBAN_LEVELS)");
+        }
         else if (n.rfind("obstacles", 0) == 0 || n == "test") {
             // ObstaclesScenario::initializeDefaultParameters + the registered variants (scenario_obstacles.hpp:48-270, init.hpp:33-56)
             scenario = S_OBSTACLES;
@@ -167,6 +192,8 @@ public:
         if (scenario == S_OBSTACLES)  // scenario_obstacles.hpp:37-45,201-206
             return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f},
                     {"obstaclesAgentCarriedObjectToExit", onePlatformType ? 1.0f : 0.0f}};
+        if (scenario == S_SOKOBAN)  // scenario_sokoban.hpp:41-48
+            return {{"sokobanBoxOnTarget", 1.0f}, {"sokobanBoxLeavesTarget", -1.0f}, {"sokobanAllBoxesOnTarget", 10.0f}};
         if (scenario == S_REARRANGE)  // scenario_rearrange.hpp:91-97
             return {{"rearrangeOneMoreObjectCorrectPosition", 1.0f}, {"rearrangeAllObjectsCorrectPosition", 10.0f}};
         // scenario_tower_building.hpp:44-52
@@ -186,11 +213,161 @@ public:
         auto sd = randRange(0, 1 << 30, rng);
         rng.seed((unsigned long)sd);
 
-        if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else if (scenario == S_COLLECT) collectReset(); else rearrangeReset();
+        if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else if (scenario == S_COLLECT) collectReset();
+        else if (scenario == S_REARRANGE) rearrangeReset(); else sokobanReset();
         spawnAgents();
         if (scenario == S_TOWER) towerAddEpisodeDrawables(); else if (scenario == S_OBSTACLES) obstaclesAddEpisodeDrawables();
-        else if (scenario == S_COLLECT) collectAddEpisodeDrawables(); else rearrangeAddEpisodeDrawables();
+        else if (scenario == S_COLLECT) collectAddEpisodeDrawables(); else if (scenario == S_REARRANGE) rearrangeAddEpisodeDrawables(); else sokobanAddEpisodeDrawables();
         addAgentsAndUI();
+    }
+
+    // ---------------------------------------------------------------- Sokoban (scenario_sokoban.cpp:83-295)
+    void sokobanReloadLevels() {
+        const auto levelFilePath = randomSample(allSokobanLevelFiles, rng);
+        std::ifstream f{levelFilePath, std::ios::in | std::ios::binary};
+        std::string content((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+        if (content.empty()) throw std::runtime_error("oracle: could not read " + levelFilePath);
+        std::vector<std::string> lines;  // splitString(content, "\n"): strtok_r, i.e. empty lines vanish
+        {
+            size_t pos = 0;
+            while (pos < content.size()) {
+                const size_t e = content.find('\n', pos);
+                const std::string tok = content.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+                if (!tok.empty()) lines.push_back(tok);
+                if (e == std::string::npos) break;
+                pos = e + 1;
+            }
+        }
+        SokobanLevel level;
+        for (int i = 0; i < int(lines.size()); ++i) {
+            if (lines[size_t(i)].find(';') == 0) {
+                if (i > 0) sokobanLevels.emplace_back(std::move(level));
+                level = SokobanLevel{};
+            } else level.rows.emplace_back(lines[size_t(i)]);
+        }
+        std::shuffle(sokobanLevels.begin(), sokobanLevels.end(), rng);
+    }
+    void sokobanReset() {
+        vg.reset();
+        solved = false;
+        carryingObject.assign(size_t(numAgents), -1);
+        sokobanAgentPositions.clear(), boxesCoords.clear();
+        sokoLength = sokoWidth = 0;
+        numBoxes = numBoxesOnGoal = 0;
+        if (sokobanLevels.empty()) sokobanReloadLevels();
+        currLevel = sokobanLevels.back();
+        sokobanLevels.pop_back();
+        // createLayout (:118-166)
+        constexpr int wallHeight = 2;
+        const float voxelSize = 2;
+        auto &g = vg.grid;
+        static const std::vector<ColorRgb> floorColors = {LAYOUT_DEFAULT, VERY_LIGHT_YELLOW, VERY_LIGHT_BLUE, VERY_LIGHT_ORANGE, DARK_GREY};
+        auto floorColor = randomSample(floorColors, rng);
+        sokoLength = int(currLevel.rows.size());
+        for (int x = 0; x < sokoLength; ++x) {
+            const auto &row = currLevel.rows[size_t(x)];
+            sokoWidth = std::max(sokoWidth, int(row.size()));
+            for (int z = 0; z < int(row.size()); ++z) {
+                g.set({x, 0, z}, VoxelGridComponent::makeVoxel(VOXEL_SOLID | VOXEL_OPAQUE, TERRAIN_NONE, floorColor));
+                if (row[size_t(z)] == '#') {
+                    for (int y = 1; y <= wallHeight; ++y) g.set({x, y, z}, VoxelGridComponent::makeVoxel(VOXEL_SOLID));
+                    g.get(VoxelCoords{x, 1, z})->terrain = SOKO_WALL;
+                }
+                if (row[size_t(z)] == '@' || row[size_t(z)] == '+') {
+                    for (int agentIdx = 0; agentIdx < numAgents; ++agentIdx) {
+                        const float agentX = float(x) + float(agentIdx % 2) * 0.5f;
+                        const float agentZ = float(z) + float(agentIdx % 4 > 1) * 0.5f;
+                        sokobanAgentPositions.emplace_back(Vec3{agentX * voxelSize, float(voxelSize + 0.3 * float(agentIdx) * voxelSize), agentZ * voxelSize});
+                    }
+                }
+                if (row[size_t(z)] == '.' || row[size_t(z)] == '+') g.set({x, 1, z}, VoxelGridComponent::makeVoxel(VOXEL_EMPTY, SOKO_GOAL));
+                if (row[size_t(z)] == '$' || row[size_t(z)] == '*') { boxesCoords.emplace_back(x, 1, z); ++numBoxes; }
+            }
+        }
+        agentSpawnPositions = sokobanAgentPositions;
+        agentSpawnPositions.resize(size_t(numAgents), Vec3{0, 0, 0});  // a level without a player cell would index past the end upstream
+        agentInitialPositions = agentSpawnPositions;
+        objectSpawnPositions = boxesCoords; rewardSpawnPositions.clear();
+    }
+    void sokobanAddEpisodeDrawables() {  // :229-295
+        const float voxelSize = 2;
+        addDrawablesAndCollisionObjectsFromVoxelGrid(vg.grid.getVoxelSize());
+        auto &g = vg.grid;
+        for (int x = 0; x < sokoLength; ++x)
+            for (int z = 0; z < sokoWidth; ++z) {
+                if (!g.hasVoxel({x, 1, z})) continue;
+                auto v = g.get({x, 1, z});
+                if (v->terrain == SOKO_EMPTY) continue;
+                const Vec3 pos{voxelSize * float(x) + voxelSize / 2, voxelSize, voxelSize * float(z) + voxelSize / 2};
+                const float h = v->terrain == SOKO_WALL ? 0.35f : 0.025f;
+                Mat4 m = mul(mat4Scaling({1, h, 1}), mat4Identity());
+                m = mul(mat4Translation({0.0f, h, 0.0f}), m);
+                m = mul(mat4Translation(pos), m);
+                drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(v->terrain == SOKO_WALL ? LIGHT_ORANGE : LIGHT_GREEN), m});
+            }
+        for (auto box : boxesCoords) {
+            const Vec3 scale = Vec3{voxelSize / 2, 0.45f, voxelSize / 2} * 0.8f;
+            const Vec3 translation = Vec3{float(box.x) + 0.5f, float(box.y) + 0.2f, float(box.z) + 0.5f} * voxelSize;
+            MovableObject o;
+            o.local = mul(mat4Translation(translation), mul(mat4Scaling(scale), mat4Identity()));
+            o.collisionScale = Vec3{1.15f, 3, 1.15f};
+            o.collisionOffset = Vec3{0, 0.6f, 0};
+            o.color = paletteIndex(DARK_BLUE);
+            o.collider = int(colliders.size());
+            colliders.push_back(Collider{});
+            objects.push_back(o);
+            const int idx = int(objects.size()) - 1;
+            drawables[MESH_BOX].push_back({DrawEntry::D_OBJECT, idx, o.color, mat4Identity()});
+            syncPose(idx);
+            if (!g.hasVoxel(box)) g.set(box, VoxelGridComponent::makeVoxel(VOXEL_EMPTY));
+            g.get(box)->physicsObject = idx;
+        }
+    }
+    void sokobanStep() {  // :168-222
+        const float voxelSize = 2;
+        for (int i = 0; i < numAgents; ++i) {
+            const auto a = currAction[size_t(i)];
+            Agent &agent = agents[size_t(i)];
+            if (!(a & A_Interact)) continue;
+            const Vec3 t = translationOf(agent.pickupAbs());
+            auto voxel = vg.grid.getWithVector(t);
+            if (voxel && voxel->physicsObject >= 0) {
+                const auto boxPos = vg.grid.getCoords(t);
+                const auto agentPos = vg.grid.getCoords(translationOf(agent.objectT));
+                const int dist = std::abs(agentPos.x - boxPos.x) + std::abs(agentPos.y - boxPos.y) + std::abs(agentPos.z - boxPos.z);
+                if (dist == 1) {
+                    const VoxelCoords deltaPos(boxPos.x - agentPos.x, boxPos.y - agentPos.y, boxPos.z - agentPos.z);
+                    const VoxelCoords desiredPos(boxPos.x + deltaPos.x, boxPos.y + deltaPos.y, boxPos.z + deltaPos.z);
+                    bool occupied = false;
+                    for (int j = 0; j < numAgents; ++j)
+                        if (vg.grid.getCoords(translationOf(agents[size_t(j)].objectT)) == desiredPos) { occupied = true; break; }
+                    if (!occupied) {
+                        if (!vg.grid.hasVoxel(desiredPos)) vg.grid.set(desiredPos, VoxelGridComponent::makeVoxel(VOXEL_EMPTY));
+                        voxel = vg.grid.get(boxPos);  // (the insertion above may rehash the map)
+                        auto desiredPosVoxel = vg.grid.get(desiredPos);
+                        if (desiredPosVoxel->terrain != SOKO_WALL && desiredPosVoxel->physicsObject < 0) {
+                            const int obj = voxel->physicsObject;
+                            desiredPosVoxel->physicsObject = obj;
+                            objects[size_t(obj)].local = mul(mat4Translation(Vec3{float(deltaPos.x), float(deltaPos.y), float(deltaPos.z)} * voxelSize), objects[size_t(obj)].local);
+                            syncPose(obj);
+                            voxel->physicsObject = -1;
+                            if (voxel->terrain != SOKO_GOAL && desiredPosVoxel->terrain == SOKO_GOAL) {
+                                ++numBoxesOnGoal;
+                                rewardTeam("sokobanBoxOnTarget", i, 1);
+                                if (numBoxesOnGoal == numBoxes && !solved) {
+                                    solved = true;
+                                    rewardTeam("sokobanAllBoxesOnTarget", i, 1);
+                                    doneWithTimer();
+                                }
+                            } else if (voxel->terrain == SOKO_GOAL && desiredPosVoxel->terrain != SOKO_GOAL) {
+                                --numBoxesOnGoal;
+                                rewardTeam("sokobanBoxLeavesTarget", i, 1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
     }
 
     // ---------------------------------------------------------------- Rearrange (scenario_rearrange.cpp:46-300)
@@ -864,7 +1041,8 @@ public:
         }
         for (auto &a : agents) a.updateTransform();
 
-        if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else if (scenario == S_COLLECT) collectStep(); else rearrangeStep();
+        if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else if (scenario == S_COLLECT) collectStep();
+        else if (scenario == S_REARRANGE) rearrangeStep(); else sokobanStep();
 
         currEpisodeSec += lastFrameDurationSec;
         updateUI();
@@ -875,7 +1053,7 @@ public:
     }
 
     float episodeLengthSec() const {
-        if (scenario == S_REARRANGE) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
+        if (scenario == S_REARRANGE || scenario == S_SOKOBAN) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
         if (scenario == S_COLLECT) return floatParams.at("episodeLengthSec") + 2.0f * rewardSpawnPositions.size();  // scenario_collect.hpp:52-56
         if (scenario == S_OBSTACLES)  // scenario_obstacles.cpp:262-266
             return std::max(floatParams.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objectSpawnPositions.size()) * 1);
@@ -1088,6 +1266,13 @@ public:
     std::vector<StaticBox> staticBoxes;
     std::vector<TerrainSlab> terrainSlabs;
     std::map<int, std::vector<DrawEntry>> drawables;
+    // Sokoban
+    std::vector<std::string> allSokobanLevelFiles;
+    std::vector<SokobanLevel> sokobanLevels;
+    SokobanLevel currLevel;
+    int sokoLength = 0, sokoWidth = 0, numBoxes = 0, numBoxesOnGoal = 0;
+    std::vector<Vec3> sokobanAgentPositions;
+    std::vector<VoxelCoords> boxesCoords;
     // Rearrange
     std::unique_ptr<RearrangePlatform> rearrangePlatform;
     std::vector<ArrangementItem> arrangement;

@@ -383,3 +383,45 @@ def test_rearrange_solved_by_script(built):
     assert total >= 5.0 and solved >= 1, (total, solved)
     assert g.faults() == 0
     o.close(); g.close()
+
+
+@pytest.mark.parametrize("A", [1, 4])
+def test_sokoban_reset_parity(built, A):
+    """Sokoban (synthetic Boxoban-format rooms): voxel size 2, invisible wall colliders + low wall / goal markers, pushable boxes"""
+    E = 8
+    o, g = _pair("Sokoban", E, A, 9)
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.voxels(e), g.voxels(e)), "voxels %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+def test_sokoban_trajectory_parity(built):
+    """boxes pushed around (and occasionally onto / off goals: +1 / -1 team rewards), episode turnover at 80 s with the next
+    room taken from the env's shuffled level list"""
+    E, A, steps = 48, 2, 1260
+    o, g = _pair("Sokoban", E, A, 5)
+    rng = np.random.default_rng(3)
+    events, ndone = 0, 0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t)
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        events += int(np.abs(ro).sum() > 0); ndone += int(o.dones().sum())
+        if t % 100 == 0 or t == steps - 1 or o.dones().any() or np.abs(ro).sum() > 0:
+            _assert_same_state(o, g, E, "step %d" % t)
+            for e in range(0, E, 7):
+                assert np.array_equal(o.voxels(e), g.voxels(e)), "step %d voxels %d" % (t, e)
+                assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "step %d instances %d" % (t, e)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+    assert events >= 1 and ndone == E
+    assert g.faults() == 0
+    o.close(); g.close()
