@@ -148,6 +148,9 @@ struct mv_engine {
     DevBuf<int32_t> d_tileCounter;
     DevBuf<mvr::TriCover> d_cover;
     DevBuf<mvr::TriShade> d_shade;
+    DevBuf<MvDeco> d_deco;
+    PinBuf<MvDeco> h_deco;
+    int decoCap = 1, instCap = MV_BASE_INSTANCES + 1;
     DevBuf<int32_t> d_binCounts, d_wideCounts;
     DevBuf<uint16_t> d_binList;
     DevBuf<int4> d_wideList;
@@ -202,6 +205,7 @@ struct mv_engine {
                 while (out.level.n_obj > curO && !maxObjSeen.compare_exchange_weak(curO, out.level.n_obj)) {}
             }
             std::memcpy(&h_levels.p[size_t(e) * 2 + s], &out.level, sizeof(MvLevel));
+            if (!out.deco.empty()) std::memcpy(&h_deco.p[(size_t(e) * 2 + s) * size_t(decoCap)], out.deco.data(), sizeof(MvDeco) * out.deco.size());
             uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * 3 * gridWords;  // planes: solid, exit, lava
             const size_t nw = std::min(out.solid.size(), size_t(gridWords));
             std::memcpy(dst, out.solid.data(), sizeof(uint32_t) * nw);
@@ -222,6 +226,8 @@ struct mv_engine {
         }
         for (int id : todo) {
             MV_CUDA(cudaMemcpyAsync(&d_levels.p[id], &h_levels.p[id], sizeof(MvLevel), cudaMemcpyHostToDevice, stream));
+            if (h_levels.p[id].n_deco > 0)
+                MV_CUDA(cudaMemcpyAsync(&d_deco.p[size_t(id) * size_t(decoCap)], &h_deco.p[size_t(id) * size_t(decoCap)], sizeof(MvDeco) * size_t(h_levels.p[id].n_deco), cudaMemcpyHostToDevice, stream));
             const size_t nw = size_t(levelWords[size_t(id)]);  // only the words this level's grid uses
             for (int plane = 0; plane < ((scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE) ? 1 : 3); ++plane)
                 MV_CUDA(cudaMemcpyAsync(d_solid.p + (size_t(id) * 3 + plane) * gridWords, h_solid.p + (size_t(id) * 3 + plane) * gridWords, sizeof(uint32_t) * nw, cudaMemcpyHostToDevice, stream));
@@ -247,6 +253,7 @@ struct mv_engine {
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
         sp.triCounts = d_triCounts.p; sp.wideCounts = d_wideCounts.p;
         sp.prof = d_prof.p;
+        sp.deco = d_deco.p; sp.decoCap = decoCap; sp.instStride = instCap;
         sp.ready = d_ready.p; sp.readyStamp = ++readyStamp;
         sp.maxObj = std::min(int(MV_MAX_OBJECTS), maxObjSeen.load());
         sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
@@ -269,7 +276,7 @@ struct mv_engine {
     // L2 resident instead of growing with N
     int launchRaster() {
         mvr::RasterParams rp;
-        rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = MV_MAX_INSTANCES;
+        rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = instCap;
         // pinned allocations are mapped into the device address space (UVA), so the kernel can store through the host pointer
         rp.obs = rasterToHost ? h_obs.p : d_obs.p; rp.depth = wantDepth ? (rasterToHost ? h_depth.p : d_depth.p) : nullptr; rp.faults = d_faults.p;
         rp.cover = d_cover.p; rp.shade = d_shade.p; rp.triCounts = d_triCounts.p;
@@ -279,7 +286,7 @@ struct mv_engine {
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
         const int nTiles = (W / 32) * (H / 4);
-        const int maxItems = MV_MAX_INSTANCES * 6 + (A + MV_MAX_OBJECTS + MV_MAX_DECO) * 128 + 2 * MV_MAX_REWARD * 12;  // blocks past a view's real item count exit at once
+        const int maxItems = instCap * 6 + (A + MV_MAX_OBJECTS + decoCap) * 128 + 3 * MV_MAX_REWARD * 80;  // blocks past a view's real item count exit at once
         const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
         for (int base = 0; base < N; base += chunkViews) {
             const int cv = std::min(chunkViews, N - base);
@@ -422,7 +429,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
+        d_deco.free(); h_deco.free(); d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -509,6 +516,8 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     e->levelWords.assign(size_t(e->E) * 2, 0);
     e->pool.reset(new WorkerPool(e->threads));
     e->gridCells = mv::gridCapacity(sc);
+    e->decoCap = mv::decoCapacity(sc);
+    e->instCap = MV_BASE_INSTANCES + e->decoCap;
     e->gridWords = e->gridCells / 32;
     fillConsts(e->consts, w, h);
 
@@ -518,15 +527,16 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
     ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
-         ck(e->d_inst.alloc(E * MV_MAX_INSTANCES), "instances") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
+         ck(e->d_inst.alloc(E * size_t(e->instCap)), "instances") && ck(e->d_deco.alloc(E * 2 * size_t(e->decoCap)), "deco") && ck(e->h_deco.alloc(E * 2 * size_t(e->decoCap)), "h_deco") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
          ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_wideCounts.alloc(N), "wideCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     // rasteriser scratch: Collect's Perlin landscapes merge into up to ~500 boxes (+ up to 86 reward diamonds)
-    e->triCap = sc == MV_SCENARIO_COLLECT ? 4096 : (sc == MV_SCENARIO_OBSTACLES ? 2048 : 1024);
-    e->chunkViews = int(std::min<size_t>(N, sc == MV_SCENARIO_COLLECT ? 256 : 512));
+    const bool hexSc = sc == MV_SCENARIO_HEX_EXPLORE || sc == MV_SCENARIO_HEX_MEMORY;  // hundreds of wall / edging / landmark boxes
+    e->triCap = hexSc ? 8192 : (sc == MV_SCENARIO_COLLECT ? 4096 : (sc == MV_SCENARIO_OBSTACLES ? 2048 : 1024));
+    e->chunkViews = int(std::min<size_t>(N, hexSc ? 128 : (sc == MV_SCENARIO_COLLECT ? 256 : 512)));
     if (ok && e->allocTriScratch() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
@@ -775,6 +785,22 @@ int mv_close(mv_handle h) {
 }
 
 // ------------------------------------------------------------------------------------------------ introspection (tests)
+// reward-object voxels; for the hexagonal mazes the free-standing colliders instead (bit patterns of centre, half extents, orientation)
+static void dumpLevelExtras(const MvLevel &L, std::vector<int32_t> &o) {
+    const bool hex = L.scenario == MV_SCENARIO_HEX_EXPLORE || L.scenario == MV_SCENARIO_HEX_MEMORY;
+    o.push_back(hex ? 0 : L.n_reward);
+    for (int i = 0; i < L.n_reward && !hex; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
+    if (!hex) return;
+    o.push_back(L.n_static);
+    for (int i = 0; i < L.n_static; ++i) {
+        const MvBox &b = L.statics[i];
+        const float rot[2] = {(b.flags & MV_ROTATED) ? L.static_rot[i][0] : 1.0f, (b.flags & MV_ROTATED) ? L.static_rot[i][1] : 0.0f};
+        int32_t w[8];
+        std::memcpy(w, b.c, 12); std::memcpy(w + 3, b.h, 12); std::memcpy(w + 6, rot, 8);
+        for (int k = 0; k < 8; ++k) o.push_back(w[k]);
+    }
+}
+
 int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
     const MvLevel &L = h->h_levels.p[size_t(env) * 2 + h->hostSlot[size_t(env)]];
@@ -800,8 +826,7 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     for (int i = 0; i < h->A; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
     if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);  // numPlatforms
-        o.push_back(L.n_reward);
-        for (int i = 0; i < L.n_reward; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
+        dumpLevelExtras(L, o);
     }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
@@ -898,7 +923,7 @@ int mv_debug_get_instances(mv_handle h, int env, float *out, int cap) {
     cudaStreamSynchronize(h->stream);
     if (cudaMemcpy(cnt, h->d_instCounts.p + size_t(env) * 8, 32, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     std::vector<MvInstance> inst(static_cast<size_t>(cnt[1] > 0 ? cnt[1] : 1));
-    if (cudaMemcpy(inst.data(), h->d_inst.p + size_t(env) * MV_MAX_INSTANCES, sizeof(MvInstance) * inst.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (cudaMemcpy(inst.data(), h->d_inst.p + size_t(env) * size_t(h->instCap), sizeof(MvInstance) * inst.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     if (cnt[1] * 18 > cap) return -cnt[1] * 18;
     for (int i = 0; i < cnt[1]; ++i) {
         out[i * 18] = float(inst[size_t(i)].mesh); out[i * 18 + 1] = float(inst[size_t(i)].color);
@@ -1015,9 +1040,8 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     for (int i = 0; i < L.n_obj; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.obj_init[i].voxel[a]);
     for (int i = 0; i < num_agents; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
     if (L.scenario != MV_SCENARIO_TOWER) {
-        o.push_back(L.n_movable);
-        o.push_back(L.n_reward);
-        for (int i = 0; i < L.n_reward; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
+        o.push_back(L.n_movable);  // numPlatforms
+        dumpLevelExtras(L, o);
     }
     // spawn yaw basis bits, so the float side of spawnAgents is pinned too
     for (int i = 0; i < num_agents; ++i) for (int k = 0; k < 9; ++k) { int32_t u; std::memcpy(&u, &L.spawn_basis[i][k], 4); o.push_back(u); }

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <fstream>
 #include <iterator>
+#include <memory>
 #include <cstring>
 #include <set>
 #include <stdexcept>
@@ -168,6 +169,8 @@ int scenarioFromName(const std::string &name) {
     if (n == "collect") return MV_SCENARIO_COLLECT;
     if (n == "rearrange") return MV_SCENARIO_REARRANGE;
     if (n == "sokoban") return MV_SCENARIO_SOKOBAN;
+    if (n == "hexexplore") return MV_SCENARIO_HEX_EXPLORE;
+    if (n == "hexmemory") return MV_SCENARIO_HEX_MEMORY;
     if (n == "obstacleseasy" || n == "obstaclesmedium" || n == "obstacleshard" || n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava" || n == "test")
         return MV_SCENARIO_OBSTACLES;
     return -1;
@@ -210,6 +213,8 @@ std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::strin
     }
     if (scenario == MV_SCENARIO_REARRANGE)  // scenario_rearrange.hpp:91-97
         return {{"rearrangeOneMoreObjectCorrectPosition", 1.0f}, {"rearrangeAllObjectsCorrectPosition", 10.0f}};
+    if (scenario == MV_SCENARIO_HEX_EXPLORE) return {{"exploreSolved", 5.0f}};  // scenario_hex_explore.hpp:27-30
+    if (scenario == MV_SCENARIO_HEX_MEMORY) return {{"memoryCollectGood", 1.0f}, {"memoryCollectBad", -1.0f}};  // scenario_hex_memory.hpp:43-49
     if (scenario == MV_SCENARIO_SOKOBAN)  // scenario_sokoban.hpp:41-48
         return {{"sokobanBoxOnTarget", 1.0f}, {"sokobanBoxLeavesTarget", -1.0f}, {"sokobanAllBoxesOnTarget", 10.0f}};
     return {};
@@ -234,6 +239,11 @@ int rewardSlot(int scenario, const std::string &key) {
         if (key == "obstaclesExtraReward") return MV_R_OBST_EXTRA;
         if (key == "obstaclesAgentCarriedObjectToExit") return MV_R_OBST_CARRIED_TO_EXIT;
     }
+    if (scenario == MV_SCENARIO_HEX_EXPLORE && key == "exploreSolved") return MV_R_EXPLORE_SOLVED;
+    if (scenario == MV_SCENARIO_HEX_MEMORY) {
+        if (key == "memoryCollectGood") return MV_R_MEMORY_GOOD;
+        if (key == "memoryCollectBad") return MV_R_MEMORY_BAD;
+    }
     if (scenario == MV_SCENARIO_SOKOBAN) {
         if (key == "sokobanBoxOnTarget") return MV_R_SOKOBAN_ON_TARGET;
         if (key == "sokobanBoxLeavesTarget") return MV_R_SOKOBAN_LEAVES_TARGET;
@@ -246,11 +256,22 @@ int rewardSlot(int scenario, const std::string &key) {
     return -1;
 }
 
+int decoCapacity(int scenario) {
+    switch (scenario) {
+        case MV_SCENARIO_REARRANGE: return MV_MAX_ARRANGEMENT;
+        case MV_SCENARIO_SOKOBAN: return 128;       // wall / goal markers of a 10 x 10 room
+        case MV_SCENARIO_HEX_EXPLORE: case MV_SCENARIO_HEX_MEMORY: return MV_MAX_DECO;  // <= 294 walls x (wall + edging + <= 4 landmarks)
+        default: return 1;
+    }
+}
+
 int gridCapacity(int scenario) {
     // TowerBuilding rooms are at most 29 x (6+18) x 24; Obstacles chains of up to 7 platforms (+ transitions, start, exit)
     // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
     // Collect: <= 41 x 41 landscape, heights <= 18, 16 cells of margin (objects can be put down beyond the edge), y from -30
     // Rearrange: 19 x (6+18) x 14 room
+    if (scenario == MV_SCENARIO_HEX_EXPLORE) return 128;  // no voxel grid
+    if (scenario == MV_SCENARIO_HEX_MEMORY) return 64 * 4 * 64;  // one layer of cells over a maze of radius <= 7 * 3.5 * sqrt(3)
     // Sokoban: Boxoban rooms are 10 x 10 cells (voxel size 2), y in [-2, 6)
     const int cells = (scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE || scenario == MV_SCENARIO_SOKOBAN) ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
     return ((cells + 127) / 128) * 128;
@@ -282,9 +303,11 @@ LevelGenerator::LevelGenerator(const std::string &scenarioName, int numAgents, c
 void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     std::memset(&out.level, 0, sizeof(MvLevel));
     out.drawSeq.clear();
+    out.deco.clear();
     // Env::reset: reseed the env stream from itself
     const auto sd = randRange(0, 1 << 30, rng_);
     rng_.seed((unsigned long)sd);
+    episodeSeed_ = unsigned(sd);
     out.level.serial = serial;
     out.level.scenario = scenario_;
     out.level.look_limit = params_.at("verticalLookLimitRad");
@@ -294,11 +317,16 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
         case MV_SCENARIO_COLLECT: generateCollect(out); break;
         case MV_SCENARIO_REARRANGE: generateRearrange(out); break;
         case MV_SCENARIO_SOKOBAN: generateSokoban(out); break;
+        case MV_SCENARIO_HEX_EXPLORE: generateHexExplore(out); break;
+        case MV_SCENARIO_HEX_MEMORY: generateHexMemory(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
     MvLevel &L = out.level;
-    if (scenario_ != MV_SCENARIO_REARRANGE) L.n_grid_static = L.n_static;
-    if (scenario_ == MV_SCENARIO_SOKOBAN) {  // objects sit where the generator put them
+    L.n_deco = int(out.deco.size());
+    if (L.n_deco > decoCapacity(scenario_)) throw std::runtime_error("too many decorations");
+    if (scenario_ == MV_SCENARIO_HEX_EXPLORE || scenario_ == MV_SCENARIO_HEX_MEMORY) L.n_grid_static = 0;  // no voxel grid boxes at all
+    else if (scenario_ != MV_SCENARIO_REARRANGE) L.n_grid_static = L.n_static;
+    if (scenario_ == MV_SCENARIO_SOKOBAN || scenario_ == MV_SCENARIO_HEX_EXPLORE || scenario_ == MV_SCENARIO_HEX_MEMORY) {  // objects sit where the generator put them
     } else
         for (int i = 0; i < L.n_obj; ++i)
             for (int a = 0; a < 3; ++a) L.obj_init[i].pos[a] = float(L.obj_init[i].voxel[a]) + 0.5f;
@@ -331,7 +359,7 @@ void LevelGenerator::assignSlots(LevelOut &out) {
                     if (mesh == 0) { if (terrainSeen++ == 0) L.slot_terrain = slot; ++slot; }
                     break;
                 case DrawRef::OBJECT: if (MV_OBJ_MESH(L.obj_init[d.index].meta) == mesh) L.obj_init[d.index].meta = (L.obj_init[d.index].meta & 255) | (slot++ << 8); break;
-                case DrawRef::DECO: if (L.deco[d.index].mesh == mesh) L.deco[d.index].slot = slot++; break;
+                case DrawRef::DECO: if (out.deco[size_t(d.index)].mesh == mesh) out.deco[size_t(d.index)].slot = slot++; break;
                 case DrawRef::EYES: if (mesh == 0) { L.slot_eyes = slot; slot += A; } break;
                 case DrawRef::BARS: if (mesh == 0) { L.slot_bars = slot; slot += A; } break;
                 case DrawRef::BODIES: if (mesh == 1) { L.slot_body = slot; slot += A; } break;
@@ -550,12 +578,13 @@ void LevelGenerator::generateRearrange(LevelOut &out) {
         const float t[3] = {float(pos.x) + 0.5f, float(pos.y) + 0.5f, float(pos.z) + 0.5f};
         float sc[3];
         shapeScale(it.mesh, sc);
-        if (ns >= MV_MAX_STATIC || L.n_deco >= MV_MAX_DECO) throw std::runtime_error("too many arrangement items");
+        if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many arrangement items");
         MvBox &sb = L.statics[ns++];
         const float cs[3] = {1.0f, colScaleY(it.mesh), 1.0f};
         for (int a = 0; a < 3; ++a) { sb.c[a] = t[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * cs[a]; }
         sb.flags = MV_SOLID; sb.color = 0;
-        MvDeco &d = L.deco[L.n_deco];
+        out.deco.emplace_back();
+        MvDeco &d = out.deco.back();
         std::memset(d.model, 0, sizeof d.model);
         d.model[0] = sc[0]; d.model[5] = sc[1]; d.model[10] = sc[2]; d.model[12] = t[0]; d.model[13] = t[1]; d.model[14] = t[2]; d.model[15] = 1.0f;
         d.mesh = it.mesh; d.color = paletteIndex(it.color); d.slot = 0; d.pad = 0;
@@ -714,13 +743,14 @@ void LevelGenerator::generateSokoban(LevelOut &out) {
         for (int z = 0; z < width; ++z) {
             const auto it = grid.find(voxKey(x, 1, z));
             if (it == grid.end() || it->second.terrain == 0) continue;
-            if (L.n_deco >= MV_MAX_DECO) throw std::runtime_error("too many terrain markers");
+
             const float h = it->second.terrain == 1 ? 0.35f : 0.025f;
             const float pos[3] = {voxelSize * float(x) + voxelSize / 2, voxelSize, voxelSize * float(z) + voxelSize / 2};
             mvh::M4 m = mvh::mul(mvh::scaling(1.0f, h, 1.0f), mvh::identity());
             m = mvh::mul(mvh::translation(0.0f, h, 0.0f), m);
             m = mvh::mul(mvh::translation(pos[0], pos[1], pos[2]), m);
-            MvDeco &d = L.deco[L.n_deco];
+            out.deco.emplace_back();
+            MvDeco &d = out.deco.back();
             std::memcpy(d.model, &m.c[0][0], 64);
             d.mesh = 0; d.color = paletteIndex(it->second.terrain == 1 ? C_LIGHT_ORANGE : C_LIGHT_GREEN); d.slot = 0; d.pad = 0;
             out.drawSeq.push_back({DrawRef::DECO, L.n_deco});
@@ -744,6 +774,236 @@ void LevelGenerator::generateSokoban(LevelOut &out) {
     L.grid_dim[0] = length + 4; L.grid_dim[1] = 8; L.grid_dim[2] = width + 4;
     fillPlanes(out, &grid);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Hexagonal mazes (src/libs/mazes: honeycombmaze.cpp, maze.cpp, kruskal.cpp; component_hexagonal_maze.cpp).  Cells are
+// indexed row by row over axial coordinates (u, v); each cell keeps its remaining borders as (neighbour or -1, segment).
+// A uniformly shuffled edge list + union-find carves a spanning tree (Kruskal).  Upstream seeds that shuffle from
+// std::random_device, i.e. its mazes are not reproducible; here the seed is derived from the episode seed WITHOUT
+// consuming the env's stream, so all other draws of the episode stay where the reference has them.
+namespace {
+
+struct HexMaze {
+    struct Border { int cell; double seg[4]; };
+    int n = 0, cells = 0;
+    std::vector<std::vector<Border>> borders;
+    std::vector<std::array<double, 2>> centers;
+
+    int rowBegin(int u) const { return u < 0 ? -n - u + 1 : -n + 1; }
+    int rowEnd(int u) const { return u < 0 ? n - 1 : n - 1 - u; }
+    bool inside(int u, int v) const { return u > -n && u < n && v >= rowBegin(u) && v <= rowEnd(u); }
+    int index(int u, int v) const { return u <= 0 ? ((3 * n + u) * (n + u - 1)) / 2 + v : (3 * n * (n - 1) + (4 * n - u - 1) * u) / 2 + v; }
+
+    HexMaze(int size, unsigned seed) : n(size), cells(3 * size * (size - 1) + 1) {
+        borders.resize(size_t(cells));
+        centers.resize(size_t(cells));
+        static const int step[6][2] = {{-1, 0}, {-1, 1}, {0, 1}, {1, 0}, {1, -1}, {0, -1}};
+        const double hx = std::sqrt(3) / 2, hy = 1.5, wx = std::sqrt(3), wy = 0;
+        for (int u = -n + 1; u < n; ++u)
+            for (int v = rowBegin(u); v <= rowEnd(u); ++v) {
+                const int me = index(u, v);
+                const double cx = hx * u + wx * v, cy = hy * u + wy * v;
+                centers[size_t(me)] = {cx, cy};
+                for (int k = 0; k < 6; ++k) {
+                    const int uu = u + step[k][0], vv = v + step[k][1];
+                    const bool in = inside(uu, vv);
+                    const int other = in ? index(uu, vv) : -1;
+                    if (in && other > me) continue;  // the pair is recorded once, by its higher cell
+                    const double a0 = (k - 2.5) * M_PI / 3, a1 = a0 + M_PI / 3;
+                    Border b{other, {cx + std::cos(a0), cy + std::sin(a0), cx + std::cos(a1), cy + std::sin(a1)}};
+                    borders[size_t(me)].push_back(b);
+                    if (in) { b.cell = me; borders[size_t(other)].push_back(b); }
+                }
+            }
+        // spanning tree: every tree edge loses its border on both sides
+        std::vector<std::pair<int, int>> edges;
+        for (int i = 0; i < cells; ++i)
+            for (const Border &b : borders[size_t(i)])
+                if (b.cell > i) edges.push_back({i, b.cell});
+        std::mt19937 gen(seed);
+        std::shuffle(edges.begin(), edges.end(), gen);
+        std::vector<int> root(static_cast<size_t>(cells), 0);
+        for (int i = 0; i < cells; ++i) root[size_t(i)] = i;
+        auto find = [&](int x) { while (root[size_t(x)] != x) { root[size_t(x)] = root[size_t(root[size_t(x)])]; x = root[size_t(x)]; } return x; };
+        auto drop = [&](int a, int b) {
+            auto &l = borders[size_t(a)];
+            for (size_t i = 0; i < l.size(); ++i)
+                if (l[i].cell == b) { l.erase(l.begin() + long(i)); return; }
+        };
+        for (const auto &e : edges) {
+            const int a = find(e.first), b = find(e.second);
+            if (a == b) continue;
+            root[size_t(a)] = b;
+            drop(e.first, e.second);
+            drop(e.second, e.first);
+        }
+    }
+};
+
+const uint32_t kAllColors[22] = {C_YELLOW, C_GREEN, C_LIGHT_GREEN, C_BLUE, C_LIGHT_BLUE, C_DARK_BLUE, C_DARK_NAVY, C_ORANGE, C_GREY, C_DARK_GREY,
+                                 C_VERY_DARK_GREY, C_WHITE, C_RED, C_LIGHT_ORANGE, C_VIOLET, C_LIGHT_PINK, C_VL_YELLOW, C_VL_GREEN, C_VL_BLUE,
+                                 C_VL_GREY, C_VL_VIOLET, C_VL_ORANGE};
+uint32_t sampleRandomColor(Rng &rng) { return kAllColors[randRange(0, 22, rng)]; }  // const.hpp:90-94
+
+struct HexMazeComponent {  // HexagonalMazeComponent::reset (component_hexagonal_maze.cpp:19-46)
+    std::unique_ptr<HexMaze> maze;
+    int size = 0;
+    float scale = 3.5f, wallHeight = 1, omitProb = 0, landmarkProb = 0;
+    uint32_t bottomEdging = C_WHITE, topEdging = C_WHITE;
+    double xMin = 0, xMax = 0, yMin = 0, yMax = 0;
+    void reset(Rng &rng, unsigned episodeSeed, int minSize, int maxSize, float omitMin, float omitMax) {
+        size = randRange(minSize, maxSize, rng);
+        maze = std::make_unique<HexMaze>(size, episodeSeed ^ 0x6d617a65u);
+        const double xlim = std::sqrt(3) * (size - 0.5), ylim = 1.5 * size - 0.5;
+        xMin = -xlim; yMin = -ylim; xMax = xlim; yMax = ylim;
+        scale = 3.5f;
+        wallHeight = frand(rng) * 0.55f + 0.85f;
+        omitProb = frand(rng) * (omitMax - omitMin) + omitMin;
+        landmarkProb = frand(rng) * 0.15f + 0.15f;
+        bottomEdging = sampleRandomColor(rng);
+        topEdging = sampleRandomColor(rng);
+        xMin *= scale; xMax *= scale; yMin *= scale; yMax *= scale;
+    }
+};
+
+void pushDeco(LevelOut &out, const mvh::M4 &m, int mesh, uint32_t color) {
+    out.deco.emplace_back();
+    MvDeco &d = out.deco.back();
+    std::memcpy(d.model, &m.c[0][0], 64);
+    d.mesh = mesh; d.color = paletteIndex(color); d.slot = 0; d.pad = 0;
+    out.drawSeq.push_back({DrawRef::DECO, int(out.deco.size()) - 1});
+}
+
+// HexagonalMazeComponent::addDrawablesAndCollisions (component_hexagonal_maze.cpp:48-128): floor slab, then per remaining
+// border a wall (rotated box collider + drawable), optional landmark boxes on it, and its bottom edging
+void hexMazeBuild(const HexMazeComponent &hm, Rng &rng, LevelOut &out, int &ns) {
+    using namespace mvh;
+    MvLevel &L = out.level;
+    auto colLen = [](const M4 &m, int col) { return std::sqrt(m.c[col][0] * m.c[col][0] + m.c[col][1] * m.c[col][1] + m.c[col][2] * m.c[col][2]); };
+    {   // addStaticCollidingBox (layout_utils.cpp:70-84)
+        const float sc[3] = {float(hm.xMax - hm.xMin), 0.0001f, float(hm.yMax - hm.yMin)};
+        const float tr[3] = {float(hm.xMax + hm.xMin) / 2, 0.0f, float(hm.yMax + hm.yMin) / 2};
+        const uint32_t color = randomLayoutColor(rng);
+        MvBox &sb = L.statics[ns];
+        for (int a = 0; a < 3; ++a) { sb.c[a] = tr[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.0f; }
+        sb.flags = MV_SOLID | MV_OPAQUE; sb.color = paletteIndex(color);
+        out.drawSeq.push_back({DrawRef::STATIC, ns});
+        ++ns;
+    }
+    std::set<std::pair<int, int>> done;
+    const auto &all = hm.maze->borders;
+    for (int cell = 0; cell < int(all.size()); ++cell)
+        for (const HexMaze::Border &b : all[size_t(cell)]) {
+            std::pair<int, int> key{std::min(cell, b.cell), std::max(cell, b.cell)};
+            if (b.cell != -1) {
+                if (done.count(key)) continue;
+                if (frand(rng) < hm.omitProb) continue;
+            }
+            done.insert(key);
+            double x1 = b.seg[0], z1 = b.seg[1], x2 = b.seg[2], z2 = b.seg[3];
+            x1 *= hm.scale; z1 *= hm.scale; x2 *= hm.scale; z2 *= hm.scale;
+            const float length = 0.5f * std::sqrt(float((x1 - x2) * (x1 - x2) + (z1 - z2) * (z1 - z2)));
+            const float wt[3] = {float(x1 + x2) / 2, hm.wallHeight, float(z1 + z2) / 2};
+            const double dX = x1 - x2, dZ = z1 - z2;
+            float rotY = float(M_PI_2);
+            if (std::fabs(dX) > 1e-5f) rotY = -atanf(float(dZ / dX));
+            const M4 wall = mul(translation(wt[0], wt[1], wt[2]), mul(rotationY(rotY), mul(scaling(length, hm.wallHeight, 0.15f), identity())));
+            if (frand(rng) < hm.landmarkProb) {
+                const float lw = 0.15f, lh = lw * length / hm.wallHeight;
+                const int count = randRange(2, 5, rng);
+                for (int li = 0; li < count; ++li) {
+                    const float lz = frand(rng) * 1.2f + 1.5f;
+                    const M4 local = mul(translation(float(li % 2 == 1) * lw * 2, float(li > 1) * lh * 2 - 0.2f, 0.0f), mul(identity(), scaling(lw, lh, lz)));
+                    const uint32_t color = sampleRandomColor(rng);
+                    pushDeco(out, mul(wall, local), 0, color);
+                }
+            }
+            pushDeco(out, wall, 0, C_DARK_BLUE);
+            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many maze walls");
+            {   // collider: centre = translation, half extents = column lengths, orientation = the normalised first column
+                MvBox &sb = L.statics[ns];
+                sb.c[0] = wall.c[3][0] + 0.0f; sb.c[1] = wall.c[3][1] + 0.0f; sb.c[2] = wall.c[3][2] + 0.0f;
+                for (int a = 0; a < 3; ++a) sb.h[a] = colLen(wall, a) * 1.0f;
+                sb.flags = MV_SOLID | MV_ROTATED; sb.color = 0;
+                L.static_rot[ns][0] = wall.c[0][0] / sb.h[0];
+                L.static_rot[ns][1] = wall.c[0][2] / sb.h[0];
+                ++ns;
+            }
+            const float es[3] = {length * 1.02f, hm.wallHeight * 0.12f, 0.2f};
+            pushDeco(out, mul(translation(wt[0], es[1], wt[2]), mul(rotationY(rotY), mul(scaling(es[0], es[1], es[2]), identity()))), 0, hm.bottomEdging);
+        }
+}
+
+mvh::M4 coneBottomLocal() {  // addDiamond's lower half: rotateXLocal(180 deg) then translate(0,-1,0) (layout_utils.cpp:117-119)
+    using namespace mvh;
+    const float ang = 180.0f * 3.14159265358979323846f / 180.0f;
+    M4 rx = identity();
+    const float s = crsin(ang), c = crcos(ang);
+    rx.c[1][1] = c; rx.c[1][2] = s; rx.c[2][1] = -s; rx.c[2][2] = c;
+    return mul(translation(0.0f, -1.0f, 0.0f), mul(identity(), rx));
+}
+
+}  // namespace
+
+// HexExploreScenario (scenario_hex_explore.cpp:22-108): find the diamond hidden in the maze
+void LevelGenerator::generateHexExplore(LevelOut &out) {
+    using namespace mvh;
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    HexMazeComponent hm;
+    hm.reset(rng, episodeSeed_, 2, 8, 0.1f, 0.4f);
+    const auto &centers = hm.maze->centers;
+    const int rewardCell = randRange(0, int(centers.size()), rng);
+    const float rc[3] = {float(centers[size_t(rewardCell)][0]) * hm.scale, 0.0f, float(centers[size_t(rewardCell)][1]) * hm.scale};
+    // agentStartingPositions (:63-99): the first shuffled cell farther from the diamond than size * scale, agents on a unit circle
+    std::vector<int> order(centers.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = int(i);
+    std::shuffle(order.begin(), order.end(), rng);
+    std::vector<std::array<float, 3>> spawn;
+    float farthest = 0;
+    for (int cell : order) {
+        const float sp[3] = {float(centers[size_t(cell)][0]) * hm.scale, float(0.1), float(centers[size_t(cell)][1]) * hm.scale};
+        const float dx = rc[0] - sp[0], dy = rc[1] - sp[1], dz = rc[2] - sp[2];
+        const float distance = std::sqrt(dx * dx + dy * dy + dz * dz);
+        const float rotation = float(2 * M_PI / A);
+        if (distance > farthest) {
+            spawn.clear();
+            for (int i = 0; i < A; ++i) spawn.push_back({sp[0] + sinf(float(i) * rotation), sp[1] + 0.0f, sp[2] + cosf(float(i) * rotation)});
+            farthest = distance;
+        }
+        if (distance > float(hm.size) * hm.scale) break;
+    }
+    if (spawn.empty()) spawn.assign(size_t(A), std::array<float, 3>{0, 1, 0});
+    for (int i = 0; i < A; ++i) {  // DefaultScenario::spawnAgents
+        const float yaw = frand(rng) * 3.14159265358979323846f * 2;
+        yawBasis(yaw, L.spawn_basis[i]);
+        const float sx = spawn[size_t(i)][0] + 0.5f, sy = spawn[size_t(i)][1] + 0.0f, sz = spawn[size_t(i)][2] + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        for (int a = 0; a < 3; ++a) L.init_pos[i][a] = spawn[size_t(i)][size_t(a)];
+    }
+    int ns = 0;
+    hexMazeBuild(hm, rng, out, ns);
+    L.n_static = ns; L.n_static_pre = ns; L.n_grid_static = 0;
+    // the diamond (addDiamond, layout_utils.cpp:114-126)
+    const float sc = 1.9f;
+    const M4 root = mul(translation(rc[0] + 0.0f, rc[1] + 1.2f, rc[2] + 0.0f), mul(scaling(0.17f * sc, 0.35f * sc, 0.17f * sc), identity()));
+    const M4 bottom = coneBottomLocal();
+    std::memcpy(L.cone_bottom_local, &bottom.c[0][0], 64);
+    L.n_reward = 1; L.n_positive = 0;
+    std::memcpy(L.reward_root[0], &root.c[0][0], 64);
+    L.reward_voxel[0][0] = L.reward_voxel[0][1] = L.reward_voxel[0][2] = 0; L.reward_voxel[0][3] = int16_t(paletteIndex(C_VIOLET));
+    L.goal[0] = rc[0]; L.goal[1] = rc[1]; L.goal[2] = rc[2];
+    out.drawSeq.push_back({DrawRef::EYES, 0}); out.drawSeq.push_back({DrawRef::BARS, 0}); out.drawSeq.push_back({DrawRef::BODIES, 0});
+    out.drawSeq.push_back({DrawRef::REWARDS, 0});
+    L.n_terrain = 0; L.n_obj = 0; L.n_movable = 0;
+    L.episode_len = params_.at("episodeLengthSec");
+    L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
+    L.grid_dim[0] = 1; L.grid_dim[1] = 1; L.grid_dim[2] = 1;
+    out.solid.assign(1, 0u); out.exitBits.assign(1, 0u); out.lavaBits.assign(1, 0u);
+}
+
+void LevelGenerator::generateHexMemory(LevelOut &) { throw std::runtime_error("HexMemory: not implemented yet"); }
 
 // three bit planes over the dense grid: solid, exit terrain, lava terrain
 void LevelGenerator::fillPlanes(LevelOut &out, const void *gridPtr) {

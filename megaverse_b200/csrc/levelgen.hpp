@@ -21,6 +21,7 @@ struct DrawRef { enum Kind { STATIC, TERRAIN, OBJECT, DECO, EYES, BARS, BODIES, 
 
 struct LevelOut {
     MvLevel level;
+    std::vector<MvDeco> deco;      // level.n_deco static drawables with arbitrary model matrices
     std::vector<DrawRef> drawSeq;  // empty: the default order (opaque statics, terrain, objects, eyes, bars, bodies, rewards)
     std::vector<uint32_t> solid;  // grid_dim product bits, x-major: idx = (x*dimY + y)*dimZ + z
     std::vector<uint32_t> exitBits, lavaBits;  // terrain planes, same indexing
@@ -40,6 +41,9 @@ private:
     void generateCollect(LevelOut &out);
     void generateRearrange(LevelOut &out);
     void generateSokoban(LevelOut &out);
+    void generateHexExplore(LevelOut &out);
+    void generateHexMemory(LevelOut &out);
+    unsigned episodeSeed_ = 0;     // the value the env reseeded itself with at this reset
     void assignSlots(LevelOut &out);
     void fillPlanes(LevelOut &out, const void *voxMap);
     int scenario_;
@@ -56,7 +60,8 @@ int scenarioFromName(const std::string &name);  // -1 if unknown
 FloatParams defaultFloatParams(const std::string &scenarioName);
 // default reward shaping of the (registered) scenario name
 std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::string &scenarioName);
-int gridCapacity(int scenario);  // dense voxel grid capacity in cells
+int gridCapacity(int scenario);
+int decoCapacity(int scenario);  // most decorations a level of the scenario can hold  // dense voxel grid capacity in cells
 int rewardSlot(int scenario, const std::string &key);  // -1 if unknown
 
 }  // namespace mv

@@ -30,13 +30,16 @@
 #define MV_SCENARIO_COLLECT 2
 #define MV_SCENARIO_REARRANGE 3
 #define MV_SCENARIO_SOKOBAN 4
+#define MV_SCENARIO_HEX_EXPLORE 5
+#define MV_SCENARIO_HEX_MEMORY 6
 
-#define MV_MAX_DECO 128     // static drawables that are not axis-aligned layout boxes (other meshes, rotated boxes)
+#define MV_MAX_DECO 1536    // static drawables that are not axis-aligned layout boxes (other meshes, rotated boxes); stored beside MvLevel
 #define MV_MAX_ARRANGEMENT 8
 
 // voxel / box flags (voxel_state.hpp:10-15)
 #define MV_SOLID 1
 #define MV_OPAQUE 2
+#define MV_ROTATED 4   // static collider rotated about Y: MvLevel::static_rot holds its local x axis (ax, az)
 
 // action bits (env.hpp:22-42)
 #define MV_A_LEFT (1 << 1)
@@ -70,6 +73,9 @@
 #define MV_R_SOKOBAN_ON_TARGET 1
 #define MV_R_SOKOBAN_LEAVES_TARGET 2
 #define MV_R_SOKOBAN_ALL 3
+#define MV_R_EXPLORE_SOLVED 1
+#define MV_R_MEMORY_GOOD 1
+#define MV_R_MEMORY_BAD 2
 #define MV_R_COUNT 8
 
 // fault bits (per env, sticky): the engine never exit()s, it reports
@@ -128,12 +134,13 @@ struct MvLevel {
     int32_t n_arr;                 // Rearrange: target arrangement items
     int16_t arr[MV_MAX_ARRANGEMENT][6];  // mesh, palette colour, offset x y z from the centre
     int32_t work_center[3];        // Rearrange: rightCenter
+    float goal[3];                 // HexExplore: rewardObjectCoords
     int32_t n_grid_static;         // statics[0 .. n_grid_static) are the merged boxes of the voxel grid (the rest are free-standing boxes)
-    int32_t pad0[4];               // statics[] must start 16-byte aligned
+    int32_t pad0[1];               // statics[] must start 16-byte aligned
     MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
     MvTerrain terrain[MV_MAX_TERRAIN];
+    float static_rot[MV_MAX_STATIC][2];    // MV_ROTATED boxes: local x axis in world space (ax, 0, az)
     MvObjInit obj_init[MV_MAX_OBJECTS];
-    MvDeco deco[MV_MAX_DECO];
     float spawn_pos[MV_MAX_AGENTS][4];     // ghost origin at spawn (agent.cpp:45)
     float spawn_basis[MV_MAX_AGENTS][12];  // ghost basis rows (btMatrix3x3(btQuaternion(Y, yaw)))
     float init_pos[MV_MAX_AGENTS][4];      // FallDetection agentInitialPositions
@@ -200,7 +207,8 @@ struct MvInstance {
     int32_t color;    // palette index
     int32_t pad[2];
 };
-#define MV_MAX_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 2 * MV_MAX_REWARD + MV_MAX_DECO)
+#define MV_BASE_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 3 * MV_MAX_REWARD)
+#define MV_MAX_INSTANCES (MV_BASE_INSTANCES + MV_MAX_DECO)  // the engine allocates MV_BASE_INSTANCES + the scenario's decoration capacity per env
 
 struct MvConsts {        // host-computed constants (so host libm decides their bits once, identically for oracle and device)
     float look_left[9];  // btMatrix3x3(btQuaternion(Y, +3.5*dt)) rows

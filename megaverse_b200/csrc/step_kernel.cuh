@@ -45,7 +45,9 @@ struct StepParams {
     MvEnvState *envs;            // [E]
     MvAgent *agents;             // [E*A]
     MvObject *objects;           // [E][MV_MAX_OBJECTS]
-    MvInstance *instances;       // [E][MV_MAX_INSTANCES]
+    MvInstance *instances;       // [E][instStride]
+    const MvDeco *deco;          // [E][2][decoCap] decorations of the two level slots
+    int decoCap, instStride;
     int32_t *instCounts;         // [E][8]
     float *views;                // [E*A][16]
     int32_t *triCounts;          // [E*A] rasteriser triangle counters, zeroed here for the geometry kernel that follows
@@ -79,7 +81,7 @@ struct WarpShared {  // one per warp
     // this agent's collision candidates for the current step, ascending collider index: boxes are copied here (static
     // layout boxes straight from the level in global memory, movable objects from the staged records), agents are looked
     // up live because they move within the step
-    struct Cand { float c[3]; float h[3]; int32_t kind; int32_t agent; } cand[MV_MAX_CAND];
+    struct Cand { float c[3]; float h[3]; int32_t kind; int32_t agent; float ax, az; } cand[MV_MAX_CAND];  // kind 2: box rotated about Y
     alignas(16) float mtx[8][16];                // cooperative 4x4 products: one element per lane (writeInstances)
     alignas(8) unsigned long long sweepKey[32];  // warpSweep: per live candidate, min over features of (t bits << 32 | feature)
     uint8_t sweepList[32];                       // warpSweep: lanes of the candidates that passed the swept-bounds cull
@@ -263,8 +265,27 @@ struct ColliderView {
     __device__ __forceinline__ void fetch(int j, int &kind, V3 &c, V3 &h) const {
         const WarpShared::Cand &cd = S->cand[j];
         kind = cd.kind;
-        if (kind == 0) { c = v3(cd.c[0], cd.c[1], cd.c[2]); h = v3(cd.h[0], cd.h[1], cd.h[2]); }
+        if (kind != 1) { c = v3(cd.c[0], cd.c[1], cd.c[2]); h = v3(cd.h[0], cd.h[1], cd.h[2]); }
         else { const MvAgent &a = S->agents[cd.agent]; c = v3(a.pos[0], a.pos[1], a.pos[2]); h = v3(0, 0, 0); }
+    }
+    // boxes rotated about Y (kind 2): world <-> box frame; the local x axis in world space is (ax, 0, az)
+    __device__ __forceinline__ V3 toLocal(int j, int kind, V3 p) const {
+        if (kind != 2) return p;
+        const float ax = S->cand[j].ax, az = S->cand[j].az;
+        return v3(p.x * ax + p.z * az, p.y, p.x * -az + p.z * ax);
+    }
+    __device__ __forceinline__ V3 toWorld(int j, int kind, V3 n) const {
+        if (kind != 2) return n;
+        const float ax = S->cand[j].ax, az = S->cand[j].az;
+        return v3(n.x * ax + n.z * -az, n.y, n.x * az + n.z * ax);
+    }
+    __device__ __forceinline__ V3 boundsExt(int j, int kind, V3 h) const {  // broadphase half extents grown by the capsule
+        if (kind == 1) return v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
+        if (kind == 2) {
+            const float ax = S->cand[j].ax, az = S->cand[j].az;
+            return v3((fabsf(ax) * h.x + fabsf(az) * h.z) + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), (fabsf(az) * h.x + fabsf(ax) * h.z) + kCapsuleRadius);
+        }
+        return v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius);
     }
 };
 
@@ -291,8 +312,7 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
         int kind = 0; V3 c = v3(0, 0, 0), h = v3(0, 0, 0);
         if (j < cv.nc) {
             cv.fetch(j, kind, c, h);
-            const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
-                                     : v3(2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius);
+            const V3 ext = cv.boundsExt(j, kind, h);
             live = !(hx < c.x - ext.x || lx > c.x + ext.x || hy < c.y - ext.y || ly > c.y + ext.y || hz < c.z - ext.z || lz > c.z + ext.z);
         }
         if (!__ballot_sync(FULL, live)) continue;
@@ -301,12 +321,12 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
         bool needFeatures = live;
         if (live) {
             unsigned long long key0 = ~0ull;
-            if (kind == 0) {
+            if (kind != 1) {
                 V3 n0;
-                const float d0 = pointBoxDistance(from - c, v3(h.x, h.y + kCapsuleHalfHeight, h.z), n0);
+                const float d0 = pointBoxDistance(cv.toLocal(j, kind, from - c), v3(h.x, h.y + kCapsuleHalfHeight, h.z), n0);
                 if (d0 - rhoBox <= 0.0f) {
                     needFeatures = false;
-                    if (dot(d, n0) < -kSimdEpsilon) key0 = 0ull;  // t = 0, feature 0
+                    if (dot(cv.toLocal(j, kind, d), n0) < -kSimdEpsilon) key0 = 0ull;  // t = 0, feature 0
                 }
             }
             S.sweepKey[lane] = key0;
@@ -325,7 +345,7 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
             int k2; V3 c2, h2;
             cv.fetch(base + src, k2, c2, h2);
             float t; V3 nn; bool hit = false;
-            if (k2 == 0) hit = rayRoundedBoxFeatureOutside(from - c2, d, v3(h2.x, h2.y + kCapsuleHalfHeight, h2.z), rhoBox, f, t, nn);
+            if (k2 != 1) hit = rayRoundedBoxFeatureOutside(cv.toLocal(base + src, k2, from - c2), cv.toLocal(base + src, k2, d), v3(h2.x, h2.y + kCapsuleHalfHeight, h2.z), rhoBox, f, t, nn);
             else if (f == 0) hit = rayCapsule(from - c2, d, 2.0f * kCapsuleHalfHeight, rhoCap, t, nn);
             if (hit) atomicMin(&S.sweepKey[src], (static_cast<unsigned long long>(__float_as_uint(t + 0.0f)) << 32) | unsigned(f));
         }
@@ -334,8 +354,10 @@ __device__ SweepHit warpSweep(const ColliderView &cv, int self, V3 from, V3 to, 
             const unsigned long long key = S.sweepKey[lane];
             if (key != ~0ull) {
                 float t; V3 nn;
-                if (kind == 0) rayRoundedBoxFeature(from - c, d, v3(h.x, h.y + kCapsuleHalfHeight, h.z), rhoBox, int(key & 31u), t, nn);
-                else rayCapsule(from - c, d, 2.0f * kCapsuleHalfHeight, rhoCap, t, nn);
+                if (kind != 1) {
+                    rayRoundedBoxFeature(cv.toLocal(j, kind, from - c), cv.toLocal(j, kind, d), v3(h.x, h.y + kCapsuleHalfHeight, h.z), rhoBox, int(key & 31u), t, nn);
+                    nn = cv.toWorld(j, kind, nn);
+                } else rayCapsule(from - c, d, 2.0f * kCapsuleHalfHeight, rhoCap, t, nn);
                 if (t < bt && !(dot(filterDir, nn) < minSlopeDot)) { bt = t; bi = j; bn = nn; }
             }
         }
@@ -366,7 +388,7 @@ __device__ bool warpRecover(const ColliderView &cv, int self, V3 p, V3 &delta, i
             cv.fetch(j, kind, c, h);
             V3 nn;
             float dist;
-            if (kind == 0) dist = pointBoxDistance(p - c, v3(h.x, h.y + kCapsuleHalfHeight, h.z), nn) - kCapsuleRadius;
+            if (kind != 1) { dist = pointBoxDistance(cv.toLocal(j, kind, p - c), v3(h.x, h.y + kCapsuleHalfHeight, h.z), nn) - kCapsuleRadius; nn = cv.toWorld(j, kind, nn); }
             else dist = pointSegDistance(p - c, 2.0f * kCapsuleHalfHeight, nn) - 2.0f * kCapsuleRadius;
             if (dist < -kMaxPenetrationDepth) { pen = true; dl = nn * (-dist); }
         }
@@ -734,7 +756,7 @@ __device__ __forceinline__ M4 tsMatrix(V3 t, V3 sc) {
     return m;
 }
 
-__device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
+__device__ void writeInstances(const WarpShared &S, const MvLevel &L, const MvDeco *deco, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
     // static part (every slot is precomputed by the host in draw order): opaque layout boxes, terrain slabs, decorations
     if (writeStatic) {
         for (int i = lane; i < L.n_static; i += 32) {
@@ -743,7 +765,7 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, MvInstance
             putInstance(inst[b.flags >> 8], tsMatrix(v3(b.c[0], b.c[1], b.c[2]), v3(b.h[0], b.h[1], b.h[2])), 0, b.color);
         }
         for (int i = lane; i < L.n_terrain; i += 32) putInstance(inst[L.slot_terrain + i], loadM4(L.terrain[i].model), 0, L.terrain[i].color);
-        for (int i = lane; i < L.n_deco; i += 32) putInstance(inst[L.deco[i].slot], loadM4(L.deco[i].model), L.deco[i].mesh, L.deco[i].color);
+        for (int i = lane; i < L.n_deco; i += 32) putInstance(inst[deco[i].slot], loadM4(deco[i].model), deco[i].mesh, deco[i].color);
     }
     const int no = L.n_obj;
     // movable objects: everything at reset, afterwards only what can have moved -- carried objects (they follow their
@@ -960,12 +982,17 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     const int ci = base + lane;
                     bool keep = false;
                     int kind = 0, agentIdx = 0;
+                    float rax = 1.0f, raz = 0.0f;
                     V3 c = v3(0, 0, 0), h = v3(0, 0, 0);
                     // collider order (= the reference's creation order, which decides ties): the first nsPre static boxes,
                     // the movable objects, the remaining static boxes, the agents
                     if (ci < nsPre || (ci >= nsPre + no && ci < ns + no)) {
-                        const MvBox &sb = L->statics[ci < nsPre ? ci : ci - no];  // global memory (L2 resident): scanned once per agent per step
-                        if (sb.flags & MV_SOLID) { keep = true; c = v3(sb.c[0], sb.c[1], sb.c[2]); h = v3(sb.h[0], sb.h[1], sb.h[2]); }
+                        const int si = ci < nsPre ? ci : ci - no;
+                        const MvBox &sb = L->statics[si];  // global memory (L2 resident): scanned once per agent per step
+                        if (sb.flags & MV_SOLID) {
+                            keep = true; c = v3(sb.c[0], sb.c[1], sb.c[2]); h = v3(sb.h[0], sb.h[1], sb.h[2]);
+                            if (sb.flags & MV_ROTATED) { kind = 2; rax = L->static_rot[si][0]; raz = L->static_rot[si][1]; }
+                        }
                     } else if (ci < nsPre + no) {
                         const MvObject &ob = S.objects[ci - nsPre];
                         if (ob.enabled) { keep = true; c = v3(ob.col_c[0], ob.col_c[1], ob.col_c[2]); h = v3(ob.col_h[0], ob.col_h[1], ob.col_h[2]); }
@@ -976,8 +1003,9 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     }
                     if (keep) {
                         // agents may move up to an envelope of their own within this step: give capsules the same slack
-                        const V3 ext = kind == 0 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
-                                                 : v3(2.0f * kCapsuleRadius + 3.0f, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius) + 6.0f, 2.0f * kCapsuleRadius + 3.0f);
+                        V3 ext = kind != 1 ? v3(h.x + kCapsuleRadius, h.y + (kCapsuleHalfHeight + kCapsuleRadius), h.z + kCapsuleRadius)
+                                           : v3(2.0f * kCapsuleRadius + 3.0f, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius) + 6.0f, 2.0f * kCapsuleRadius + 3.0f);
+                        if (kind == 2) { ext.x = (fabsf(rax) * h.x + fabsf(raz) * h.z) + kCapsuleRadius; ext.z = (fabsf(raz) * h.x + fabsf(rax) * h.z) + kCapsuleRadius; }
                         keep = !(envHi.x < c.x - ext.x || envLo.x > c.x + ext.x || envHi.y < c.y - ext.y || envLo.y > c.y + ext.y ||
                                  envHi.z < c.z - ext.z || envLo.z > c.z + ext.z);
                     }
@@ -985,7 +1013,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     const int slotC = nc + __popc(m & ((1u << lane) - 1u));
                     if (keep && slotC < MV_MAX_CAND) {
                         WarpShared::Cand &cd = S.cand[slotC];
-                        cd.c[0] = c.x; cd.c[1] = c.y; cd.c[2] = c.z; cd.h[0] = h.x; cd.h[1] = h.y; cd.h[2] = h.z; cd.kind = kind; cd.agent = agentIdx;
+                        cd.c[0] = c.x; cd.c[1] = c.y; cd.c[2] = c.z; cd.h[0] = h.x; cd.h[1] = h.y; cd.h[2] = h.z; cd.kind = kind; cd.agent = agentIdx; cd.ax = rax; cd.az = raz;
                     }
                     nc += __popc(m);
                 }
@@ -1041,7 +1069,8 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
                 }
             };
-            for (int i = 0; i < A && L->scenario != MV_SCENARIO_SOKOBAN; ++i) {  // ObjectStackingComponent (Sokoban has none)
+            const bool hasStacking = L->scenario != MV_SCENARIO_SOKOBAN && L->scenario != MV_SCENARIO_HEX_EXPLORE && L->scenario != MV_SCENARIO_HEX_MEMORY;
+            for (int i = 0; i < A && hasStacking; ++i) {  // ObjectStackingComponent (Sokoban and the hex mazes have none)
                 if (!(P.actions[size_t(env) * A + i] & MV_A_INTERACT)) continue;
                 MvAgent &a = S.agents[i];
                 const M4 objT = loadM4(a.object_t), cam = loadM4(a.cam_local);
@@ -1146,12 +1175,29 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                 a.hvel[0] = a.hvel[1] = a.hvel[2] = 0.0f;
                 a.vvel = 0;
             };
-            for (int i = 0; i < A && L->scenario != MV_SCENARIO_REARRANGE && L->scenario != MV_SCENARIO_SOKOBAN; ++i)  // FallDetectionComponent::step (Rearrange, Sokoban: none)
+            const bool hasFallDetection = L->scenario == MV_SCENARIO_TOWER || L->scenario == MV_SCENARIO_OBSTACLES || L->scenario == MV_SCENARIO_COLLECT;
+            for (int i = 0; i < A && hasFallDetection; ++i)  // FallDetectionComponent::step
                 if (S.agents[i].object_t[13] < -20) {
                     resetAgent(i);
                     if (L->scenario == MV_SCENARIO_COLLECT) rewardAgent(MV_R_COLLECT_BAD, i, 1);  // agentFell (scenario_collect.cpp:214-218)
                 }
-            if (L->scenario == MV_SCENARIO_SOKOBAN) {
+            if (L->scenario == MV_SCENARIO_HEX_EXPLORE) {
+                // HexExploreScenario::step (scenario_hex_explore.cpp:42-58): first agent within 1.2 of the diamond's floor point
+                for (int i = 0; i < A; ++i) {
+                    const MvAgent &a = S.agents[i];
+                    const V3 dlt = v3(a.object_t[12] - L->goal[0], a.object_t[13] - L->goal[1], a.object_t[14] - L->goal[2]);
+                    const float distance = sqrtf(dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z);
+                    if (double(distance) < 1.2 && !e.solved) {
+                        e.solved = 1;
+                        const float t = L->episode_len - 0.3f;  // doneWithTimer()
+                        e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
+                        rewardTeam(MV_R_EXPLORE_SOLVED, i, 1);
+                        e.reward_alive[0] &= ~1u;  // rewardObject->translate({1e3, 1e3, 1e3})
+                        S.rewardDirty[0] |= 1u;
+                        break;
+                    }
+                }
+            } else if (L->scenario == MV_SCENARIO_SOKOBAN) {
                 // SokobanScenario::step (scenario_sokoban.cpp:168-222): push the box in front of the agent one cell further.  The grid
                 // has voxelSize 2; terrain plane 1 = SOKO_WALL, plane 2 = SOKO_GOAL
                 auto vox2 = [&](V3 p, int &x, int &y, int &z) { toVoxel(v3(p.x / 2.0f, p.y / 2.0f, p.z / 2.0f), x, y, z); };
@@ -1341,7 +1387,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     __syncwarp();
     MV_PROBE(6);  // outputs, flip/reset, object write-back
 
-    writeInstances(S, *L, P.instances + size_t(env) * MV_MAX_INSTANCES, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
+    writeInstances(S, *L, P.deco + (size_t(env) * 2 + slot) * P.decoCap, P.instances + size_t(env) * P.instStride, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
     for (int i = lane; i < A; i += 32) { P.triCounts[size_t(env) * A + i] = 0; P.wideCounts[size_t(env) * A + i] = 0; }
     MV_PROBE(7);  // instance list + views
 

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "orc_raster.hpp"
+#include "orc_maze.hpp"
 
 using namespace orc;
 
@@ -161,6 +162,16 @@ int orc_get_level(void *p, int envIdx, int32_t *out, int cap) {
         o.push_back(int(env.rewardSpawnPositions.size()));
         for (auto &c : env.rewardSpawnPositions)
             for (int x : {c.x, c.y, c.z}) o.push_back(x);
+        if (env.scenario == Env::S_HEX_EXPLORE || env.scenario == Env::S_HEX_MEMORY) {  // free-standing colliders (bit patterns)
+            o.push_back(env.agentColliderBase);
+            for (int i = 0; i < env.agentColliderBase; ++i) {
+                const Collider &c = env.colliders[size_t(i)];
+                const float f[8] = {c.c.x, c.c.y, c.c.z, c.h.x, c.h.y, c.h.z, c.rotated ? c.ax : 1.0f, c.rotated ? c.az : 0.0f};
+                int32_t w[8];
+                std::memcpy(w, f, 32);
+                for (int k = 0; k < 8; ++k) o.push_back(w[k]);
+            }
+        }
     }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
@@ -198,6 +209,7 @@ int orc_get_state(void *p, int envIdx, float *out, int cap) {
         env.agentReachedExit.resize(size_t(env.numAgents), false);
         for (int i = 0; i < env.numAgents; ++i) reached |= env.agentReachedExit[size_t(i)] ? (1u << i) : 0u;
         if (env.scenario == Env::S_REARRANGE) reached = uint32_t(env.maxMatchingObjects);
+        if (env.scenario == Env::S_HEX_EXPLORE) alive[0] = env.exploreRewardAlive ? 1u : 0u;
         for (size_t r = 0; r < env.rewardSpawnPositions.size() && r < 96; ++r) {
             const Voxel *v = env.vg.grid.get(env.rewardSpawnPositions[r]);
             if (v && v->rewardObject == int(r)) alive[r >> 5] |= 1u << (r & 31);
@@ -223,6 +235,25 @@ int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
     for (int x : {int(env.rightCenter.x), int(env.rightCenter.y), int(env.rightCenter.z)}) o.push_back(x);
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
+    return int(o.size());
+}
+
+// the honeycomb maze restatement, same layout as ref_honeycomb_maze (oracle/ref_shim/ref_shim.cpp)
+int orc_honeycomb_maze(int size, unsigned seed, double *out, int cap) {
+    HoneyCombMaze maze(size);
+    std::mt19937 gen(seed);
+    maze.initialiseGraph();
+    maze.generate(gen);
+    std::vector<double> o;
+    o.push_back(double(maze.adjacency.size()));
+    for (size_t c = 0; c < maze.adjacency.size(); ++c) {
+        o.push_back(maze.cellCenters[c].first); o.push_back(maze.cellCenters[c].second); o.push_back(double(maze.adjacency[c].size()));
+        for (auto &e : maze.adjacency[c])
+            for (double v : {double(e.cell), e.border[0], e.border[1], e.border[2], e.border[3]}) o.push_back(v);
+    }
+    for (double v : maze.coordinateBounds()) o.push_back(v);
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
     return int(o.size());
 }
 

@@ -15,9 +15,11 @@
 #include <cstring>
 #include <fstream>
 #include <queue>
+#include <set>
 #include <stdexcept>
 
 #include "orc_level.hpp"
+#include "orc_maze.hpp"
 #include "orc_physics.hpp"
 
 namespace orc {
@@ -115,7 +117,7 @@ using RewardShaping = std::map<std::string, float>;
 
 class Env {
 public:
-    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3, S_SOKOBAN = 4 };
+    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3, S_SOKOBAN = 4, S_HEX_EXPLORE = 5, S_HEX_MEMORY = 6 };
     enum SokobanTerrain { SOKO_EMPTY = 0, SOKO_WALL = 1, SOKO_GOAL = 2 };
     struct SokobanLevel { std::vector<std::string> rows; };
     enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
@@ -132,6 +134,8 @@ public:
         if (n == "towerbuilding") scenario = S_TOWER;
         else if (n == "collect") scenario = S_COLLECT;
         else if (n == "rearrange") scenario = S_REARRANGE;
+        else if (n == "hexexplore") scenario = S_HEX_EXPLORE;
+        else if (n == "hexmemory") scenario = S_HEX_MEMORY;
         else if (n == "sokoban") {  // scenario_sokoban.cpp:39-81, scenario_sokoban.hpp:50-54
             scenario = S_SOKOBAN;
             floatParams["episodeLengthSec"] = 80.0f;
@@ -192,6 +196,8 @@ public:
         if (scenario == S_OBSTACLES)  // scenario_obstacles.hpp:37-45,201-206
             return {{"obstaclesAgentAtExit", 1.0f}, {"obstaclesAllAgentsAtExit", 5.0f}, {"obstaclesExtraReward", 0.5f},
                     {"obstaclesAgentCarriedObjectToExit", onePlatformType ? 1.0f : 0.0f}};
+        if (scenario == S_HEX_EXPLORE) return {{"exploreSolved", 5.0f}};  // scenario_hex_explore.hpp:27-30
+        if (scenario == S_HEX_MEMORY) return {{"memoryCollectGood", 1.0f}, {"memoryCollectBad", -1.0f}};  // scenario_hex_memory.hpp:43-49
         if (scenario == S_SOKOBAN)  // scenario_sokoban.hpp:41-48
             return {{"sokobanBoxOnTarget", 1.0f}, {"sokobanBoxLeavesTarget", -1.0f}, {"sokobanAllBoxesOnTarget", 10.0f}};
         if (scenario == S_REARRANGE)  // scenario_rearrange.hpp:91-97
@@ -212,14 +218,165 @@ public:
 
         auto sd = randRange(0, 1 << 30, rng);
         rng.seed((unsigned long)sd);
+        episodeSeed = unsigned(sd);
 
         if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else if (scenario == S_COLLECT) collectReset();
-        else if (scenario == S_REARRANGE) rearrangeReset(); else sokobanReset();
+        else if (scenario == S_REARRANGE) rearrangeReset(); else if (scenario == S_SOKOBAN) sokobanReset(); else if (scenario == S_HEX_EXPLORE) hexExploreReset();
+        else hexMemoryReset();
+        if (scenario == S_HEX_MEMORY) hexMemorySpawnAgents(); else
         spawnAgents();
         if (scenario == S_TOWER) towerAddEpisodeDrawables(); else if (scenario == S_OBSTACLES) obstaclesAddEpisodeDrawables();
-        else if (scenario == S_COLLECT) collectAddEpisodeDrawables(); else if (scenario == S_REARRANGE) rearrangeAddEpisodeDrawables(); else sokobanAddEpisodeDrawables();
+        else if (scenario == S_COLLECT) collectAddEpisodeDrawables(); else if (scenario == S_REARRANGE) rearrangeAddEpisodeDrawables();
+        else if (scenario == S_SOKOBAN) sokobanAddEpisodeDrawables(); else if (scenario == S_HEX_EXPLORE) hexExploreAddEpisodeDrawables(); else hexMemoryAddEpisodeDrawables();
         addAgentsAndUI();
     }
+
+    // ---------------------------------------------------------------- hexagonal maze component (component_hexagonal_maze.cpp:19-128)
+    void hexMazeReset(int minSize, int maxSize, float omitMin, float omitMax) {
+        hexMazeSize = randRange(minSize, maxSize, rng);
+        hexMaze = std::make_unique<HoneyCombMaze>(hexMazeSize);
+        hexMaze->initialiseGraph();
+        std::mt19937 generator(episodeSeed ^ 0x6d617a65u);  // upstream: std::random_device (see orc_maze.hpp)
+        hexMaze->generate(generator);
+        const auto b = hexMaze->coordinateBounds();
+        hexXMin = b[0], hexYMin = b[1], hexXMax = b[2], hexYMax = b[3];
+        hexMazeScale = 3.5f;
+        hexWallHeight = frand(rng) * 0.55f + 0.85f;
+        hexOmitWallsProbability = frand(rng) * (omitMax - omitMin) + omitMin;
+        hexWallLandmarkProbability = frand(rng) * 0.15f + 0.15f;
+        hexBottomEdgingColor = sampleRandomColor(rng);
+        hexTopEdgingColor = sampleRandomColor(rng);
+        hexXMin *= hexMazeScale, hexXMax *= hexMazeScale, hexYMin *= hexMazeScale, hexYMax *= hexMazeScale;
+    }
+    void hexMazeAddDrawablesAndCollisions() {
+        const Vec3 scale{float(hexXMax - hexXMin), 0.0001f, float(hexYMax - hexYMin)};
+        const Vec3 translation{float(hexXMax + hexXMin) / 2, 0.0f, float(hexYMax + hexYMin) / 2};
+        addStaticCollidingBox(scale, translation, randomLayoutColor(rng));
+        std::set<std::pair<int, int>> existingWalls;
+        const auto &adjList = hexMaze->adjacency;
+        for (int cellIdx = 0; cellIdx < int(adjList.size()); ++cellIdx) {
+            for (const auto &entry : adjList[size_t(cellIdx)]) {
+                const int adjCellIdx = entry.cell;
+                auto cellPair = std::make_pair(cellIdx, adjCellIdx);
+                if (cellPair.first > cellPair.second) std::swap(cellPair.first, cellPair.second);
+                if (adjCellIdx != -1) {
+                    if (existingWalls.count(cellPair)) continue;
+                    if (frand(rng) < hexOmitWallsProbability) continue;
+                }
+                existingWalls.insert(cellPair);
+                double x1 = entry.border[0], z1 = entry.border[1], x2 = entry.border[2], z2 = entry.border[3];
+                x1 *= hexMazeScale, z1 *= hexMazeScale, x2 *= hexMazeScale, z2 *= hexMazeScale;
+                const auto length = 0.5f * sqrtf(float((x1 - x2) * (x1 - x2) + (z1 - z2) * (z1 - z2)));
+                const Vec3 wallScale{length, hexWallHeight, 0.15f};
+                const Vec3 wallTranslation{float(x1 + x2) / 2, hexWallHeight, float(z1 + z2) / 2};
+                const auto deltaX = x1 - x2;
+                const auto deltaZ = z1 - z2;
+                float rotationY = float(M_PI_2);
+                if (std::fabs(deltaX) > 1e-5f) {
+                    const auto tanAlpha = deltaZ / deltaX;
+                    rotationY = -atanf(float(tanAlpha));
+                }
+                // the wall object gets its transformation after its landmark children are created; absolute matrices are what count
+                const Mat4 wallLocal = mul(mat4Translation(wallTranslation), mul(mat4RotationY(rotationY), mul(mat4Scaling(wallScale), mat4Identity())));
+                if (frand(rng) < hexWallLandmarkProbability) {
+                    const auto landmarkWidth = 0.15f, landmarkHeight = landmarkWidth * length / hexWallHeight;
+                    int numLandmarks = randRange(2, 5, rng);
+                    for (int li = 0; li < numLandmarks; ++li) {
+                        const Vec3 landmarkScale{landmarkWidth, landmarkHeight, frand(rng) * 1.2f + 1.5f};
+                        const Vec3 landmarkTranslation{float(li % 2 == 1) * landmarkWidth * 2, float(li > 1) * landmarkHeight * 2 - 0.2f, 0};
+                        const Mat4 landmarkLocal = mul(mat4Translation(landmarkTranslation), mul(mat4Identity(), mat4Scaling(landmarkScale)));  // scaleLocal, translate
+                        const int color = paletteIndex(sampleRandomColor(rng));
+                        drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, color, mul(wallLocal, landmarkLocal)});
+                    }
+                }
+                drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(DARK_BLUE), wallLocal});
+                {   // RigidBody child with identity local: world transform = rotation part + translation, local scaling = column lengths
+                    Collider c;
+                    c.kind = 0;
+                    c.c = translationOf(wallLocal) + Vec3{0, 0, 0};
+                    c.h = scalingOf(wallLocal) * Vec3{1, 1, 1};
+                    c.rotated = true;
+                    const float lx = c.h.x;  // |first column|
+                    c.ax = wallLocal.c[0][0] / lx; c.az = wallLocal.c[0][2] / lx;
+                    colliders.push_back(c);
+                }
+                {
+                    const Vec3 edgingScale{length * 1.02f, hexWallHeight * 0.12f, 0.2f};
+                    const Vec3 bottomEdgingTranslation{wallTranslation.x, edgingScale.y, wallTranslation.z};
+                    const Mat4 m = mul(mat4Translation(bottomEdgingTranslation), mul(mat4RotationY(rotationY), mul(mat4Scaling(edgingScale), mat4Identity())));
+                    drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(hexBottomEdgingColor), m});
+                }
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- HexExplore (scenario_hex_explore.cpp:22-108)
+    void hexExploreReset() {
+        solved = false;
+        vg.reset();
+        carryingObject.assign(size_t(numAgents), -1);
+        objectSpawnPositions.clear(); rewardSpawnPositions.clear();
+        hexMazeReset(2, 8, 0.1f, 0.4f);
+        const auto &centers = hexMaze->cellCenters;
+        const auto randomCellIdx = randRange(0, int(hexMaze->adjacency.size()), rng);
+        const auto cellCenter = centers[size_t(randomCellIdx)];
+        rewardObjectCoords = Vec3{float(cellCenter.first) * hexMazeScale, 0, float(cellCenter.second) * hexMazeScale};
+        // agentStartingPositions (:63-99), asked for by DefaultScenario::spawnAgents before its own draws
+        agentSpawnPositions.clear();
+        std::vector<int> cellIndices(hexMaze->adjacency.size(), 0);
+        std::iota(cellIndices.begin(), cellIndices.end(), 0);
+        std::shuffle(cellIndices.begin(), cellIndices.end(), rng);
+        float furtherstDistance = 0;
+        for (auto cellIdx : cellIndices) {
+            const auto cc = centers[size_t(cellIdx)];
+            const Vec3 spawnPos{float(cc.first) * hexMazeScale, float(0.1), float(cc.second) * hexMazeScale};
+            const auto distance = length(rewardObjectCoords - spawnPos);
+            const auto rotation = float(2 * M_PI / numAgents);
+            if (distance > furtherstDistance) {
+                agentSpawnPositions.clear();
+                for (int i = 0; i < numAgents; ++i) {
+                    const Vec3 delta{sinf(float(i) * rotation), 0, cosf(float(i) * rotation)};
+                    agentSpawnPositions.emplace_back(spawnPos + delta);
+                }
+                furtherstDistance = distance;
+            }
+            if (distance > float(hexMazeSize) * hexMazeScale) break;
+        }
+        if (agentSpawnPositions.empty()) agentSpawnPositions.assign(size_t(numAgents), Vec3{0, 1, 0});
+        agentInitialPositions = agentSpawnPositions;
+    }
+    void hexExploreAddEpisodeDrawables() {
+        hexMazeAddDrawablesAndCollisions();
+        const auto scale = 1.9f;
+        RewardObject ro;
+        ro.bottomLocal = mul(mat4Translation({0.0f, -1.0f, 0.0f}), mul(mat4Identity(), mat4RotationX(180.0f * 3.14159265358979323846f / 180.0f)));
+        ro.root = mul(mat4Translation(rewardObjectCoords + Vec3{0, 1.2f, 0}), mul(mat4Scaling({0.17f * scale, 0.35f * scale, 0.17f * scale}), mat4Identity()));
+        ro.color = paletteIndex(VIOLET);
+        addRewardDrawables(ro);
+        rewardObjects.push_back(ro);
+        exploreRewardAlive = true;
+    }
+    void hexExploreStep() {
+        for (int i = 0; i < numAgents; ++i) {
+            const Vec3 t = translationOf(agents[size_t(i)].objectT);
+            const auto threshold = 1.2;
+            const auto distance = length(t - rewardObjectCoords);
+            if (distance < threshold && !solved) {
+                solved = true;
+                doneWithTimer();
+                rewardTeam("exploreSolved", i, 1);
+                rewardObjects[0].root = mul(mat4Translation({1e3f, 1e3f, 1e3f}), rewardObjects[0].root);
+                exploreRewardAlive = false;
+                break;
+            }
+        }
+    }
+
+    // ---------------------------------------------------------------- HexMemory: see below (scenario_hex_memory.cpp)
+    void hexMemoryReset() { throw std::runtime_error("oracle: HexMemory not restated yet"); }
+    void hexMemorySpawnAgents() {}
+    void hexMemoryAddEpisodeDrawables() {}
+    void hexMemoryStep() {}
 
     // ---------------------------------------------------------------- Sokoban (scenario_sokoban.cpp:83-295)
     void sokobanReloadLevels() {
@@ -1042,7 +1199,8 @@ public:
         for (auto &a : agents) a.updateTransform();
 
         if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else if (scenario == S_COLLECT) collectStep();
-        else if (scenario == S_REARRANGE) rearrangeStep(); else sokobanStep();
+        else if (scenario == S_REARRANGE) rearrangeStep(); else if (scenario == S_SOKOBAN) sokobanStep(); else if (scenario == S_HEX_EXPLORE) hexExploreStep();
+        else hexMemoryStep();
 
         currEpisodeSec += lastFrameDurationSec;
         updateUI();
@@ -1053,7 +1211,8 @@ public:
     }
 
     float episodeLengthSec() const {
-        if (scenario == S_REARRANGE || scenario == S_SOKOBAN) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
+        if (scenario == S_HEX_MEMORY) return floatParams.at("episodeLengthSec") + 3.0f * goodObjects.size();  // scenario_hex_memory.hpp:51-55
+        if (scenario == S_REARRANGE || scenario == S_SOKOBAN || scenario == S_HEX_EXPLORE) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
         if (scenario == S_COLLECT) return floatParams.at("episodeLengthSec") + 2.0f * rewardSpawnPositions.size();  // scenario_collect.hpp:52-56
         if (scenario == S_OBSTACLES)  // scenario_obstacles.cpp:262-266
             return std::max(floatParams.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objectSpawnPositions.size()) * 1);
@@ -1266,6 +1425,16 @@ public:
     std::vector<StaticBox> staticBoxes;
     std::vector<TerrainSlab> terrainSlabs;
     std::map<int, std::vector<DrawEntry>> drawables;
+    // hexagonal mazes
+    unsigned episodeSeed = 0;
+    std::unique_ptr<HoneyCombMaze> hexMaze;
+    int hexMazeSize = 0;
+    float hexMazeScale = 1.0f, hexWallHeight = 1.0f, hexOmitWallsProbability = 0.0f, hexWallLandmarkProbability = 0.0f;
+    ColorRgb hexBottomEdgingColor = WHITE, hexTopEdgingColor = WHITE;
+    double hexXMin = 0, hexXMax = 0, hexYMin = 0, hexYMax = 0;
+    Vec3 rewardObjectCoords{0, 0, 0};
+    bool exploreRewardAlive = false;
+    std::vector<Vec3> goodObjects, badObjects;
     // Sokoban
     std::vector<std::string> allSokobanLevelFiles;
     std::vector<SokobanLevel> sokobanLevels;

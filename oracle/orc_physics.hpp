@@ -34,6 +34,12 @@ struct Collider {
     Vec3 c;        // centre
     Vec3 h;        // box half extents (kind 0)
     bool enabled = true;  // !CF_NO_CONTACT_RESPONSE
+    // boxes rotated about Y (the hexagonal mazes' walls): the box's local x axis in world space is (ax, 0, az), its local z
+    // axis (-az, 0, ax).  The agent capsule is upright, hence symmetric about Y: queries run in the box's frame.
+    bool rotated = false;
+    float ax = 1.0f, az = 0.0f;
+    Vec3 toLocal(Vec3 p) const { return rotated ? Vec3{p.x * ax + p.z * az, p.y, p.x * -az + p.z * ax} : p; }
+    Vec3 toWorld(Vec3 n) const { return rotated ? Vec3{n.x * ax + n.z * -az, n.y, n.x * az + n.z * ax} : n; }
 };
 
 struct SweepHit {
@@ -191,8 +197,12 @@ inline SweepHit convexSweep(const std::vector<Collider> &cols, int self, Vec3 fr
         if (i == self || !c.enabled) continue;
         {   // broadphase, the role btRayAabb plays in btGhostObject::convexSweepTest: skip colliders whose bounds grown by
             // the capsule extents (full radius: 0.04 more than the narrow phase needs) miss the sweep segment's box
-            const Vec3 ext = c.kind == 0 ? Vec3{c.h.x + kCapsuleRadius, c.h.y + (kCapsuleHalfHeight + kCapsuleRadius), c.h.z + kCapsuleRadius}
-                                         : Vec3{2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius};
+            Vec3 ext = c.kind == 0 ? Vec3{c.h.x + kCapsuleRadius, c.h.y + (kCapsuleHalfHeight + kCapsuleRadius), c.h.z + kCapsuleRadius}
+                                   : Vec3{2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius};
+            if (c.kind == 0 && c.rotated) {  // bounds of the rotated box
+                ext.x = (fabsf(c.ax) * c.h.x + fabsf(c.az) * c.h.z) + kCapsuleRadius;
+                ext.z = (fabsf(c.az) * c.h.x + fabsf(c.ax) * c.h.z) + kCapsuleRadius;
+            }
             bool miss = false;
             for (int ax = 0; ax < 3; ++ax) {
                 const float lo = from[ax] < to[ax] ? from[ax] : to[ax], hi = from[ax] < to[ax] ? to[ax] : from[ax];
@@ -203,9 +213,10 @@ inline SweepHit convexSweep(const std::vector<Collider> &cols, int self, Vec3 fr
         float t;
         Vec3 n;
         bool hit;
-        if (c.kind == 0)
-            hit = rayRoundedBox(from - c.c, d, Vec3{c.h.x, c.h.y + kCapsuleHalfHeight, c.h.z}, kCapsuleRadius - kAllowedCcdPenetration, t, n);
-        else
+        if (c.kind == 0) {
+            hit = rayRoundedBox(c.toLocal(from - c.c), c.toLocal(d), Vec3{c.h.x, c.h.y + kCapsuleHalfHeight, c.h.z}, kCapsuleRadius - kAllowedCcdPenetration, t, n);
+            if (hit) n = c.toWorld(n);
+        } else
             hit = rayCapsule(from - c.c, d, 2.0f * kCapsuleHalfHeight, 2.0f * kCapsuleRadius - kAllowedCcdPenetration, t, n);
         if (!hit) continue;
         if (!(t < res.fraction)) continue;             // btCollisionWorld: castResult.m_fraction < m_closestHitFraction
@@ -220,7 +231,11 @@ inline SweepHit convexSweep(const std::vector<Collider> &cols, int self, Vec3 fr
 
 // signed capsule-vs-collider distance (negative = penetration depth) and outward normal
 inline float capsuleDistance(const Collider &c, Vec3 p, Vec3 &n) {
-    if (c.kind == 0) return pointBoxDistance(p - c.c, Vec3{c.h.x, c.h.y + kCapsuleHalfHeight, c.h.z}, n) - kCapsuleRadius;
+    if (c.kind == 0) {
+        const float d = pointBoxDistance(c.toLocal(p - c.c), Vec3{c.h.x, c.h.y + kCapsuleHalfHeight, c.h.z}, n) - kCapsuleRadius;
+        n = c.toWorld(n);
+        return d;
+    }
     return pointSegDistance(p - c.c, 2.0f * kCapsuleHalfHeight, n) - 2.0f * kCapsuleRadius;
 }
 

@@ -1,8 +1,14 @@
 // ORACLE tooling (test infrastructure): C entry points into pieces of the REAL reference compiled in place from
 // /root/reference by oracle/Makefile (`make ref` -> oracle/_ref/libmvref.so): vendored Magnum math / primitives and the
 // reference's own util headers (voxel hash, RNG helpers).  Used by tests/test_ref_shim.py to pin the restatement in
-// oracle/orc_math.hpp and oracle/orc_level.hpp.  Nothing here is copied: the reference sources are #included where they lie.
+// oracle/orc_math.hpp, oracle/orc_level.hpp and oracle/orc_maze.hpp.  Nothing here is copied: the reference sources are
+// included / compiled where they lie.
+#include <algorithm>
 #include <cstring>
+#include <vector>
+
+#include <mazes/honeycombmaze.h>  // src/libs/mazes
+#include <mazes/kruskal.h>
 #include <random>
 
 #include <Magnum/Magnum.h>
@@ -55,6 +61,32 @@ int ref_voxel_grid_order(const int *xyz, int n, int *out_xyz) {
     const auto copy = grid.getHashMap();
     for (auto &kv : copy) { out_xyz[k * 3] = kv.first.x(); out_xyz[k * 3 + 1] = kv.first.y(); out_xyz[k * 3 + 2] = kv.first.z(); ++k; }
     return k;
+}
+
+// the reference's honeycomb maze (src/libs/mazes) with the Kruskal generator seeded explicitly (upstream: random_device).
+// out: [vertices, then per cell: centre x, centre y, number of adjacency entries, then per entry: neighbour, x1, y1, x2, y2],
+// followed by the four coordinate bounds
+int ref_honeycomb_maze(int size, unsigned seed, double *out, int cap) {
+    struct SeededKruskal : Kruskal { explicit SeededKruskal(unsigned s) { generator = std::mt19937(s); } };
+    HoneyCombMaze maze(size);
+    SeededKruskal algorithm(seed);
+    maze.InitialiseGraph();
+    maze.GenerateMaze(&algorithm);
+    std::vector<double> o;
+    auto &adj = maze.getAdjacencyList();
+    o.push_back(double(adj.size()));
+    for (size_t c = 0; c < adj.size(); ++c) {
+        o.push_back(maze.getCellCenters()[c].first); o.push_back(maze.getCellCenters()[c].second); o.push_back(double(adj[c].size()));
+        for (auto &e : adj[c]) {
+            const auto [x1, y1, x2, y2] = dynamic_cast<LineBorder *>(e.second.get())->getBorderCoords();
+            for (double v : {double(e.first), x1, y1, x2, y2}) o.push_back(v);
+        }
+    }
+    const auto [xmin, ymin, xmax, ymax] = maze.GetCoordinateBounds();
+    for (double v : {xmin, ymin, xmax, ymax}) o.push_back(v);
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
 }
 
 }  // extern "C"

@@ -425,3 +425,45 @@ def test_sokoban_trajectory_parity(built):
     assert events >= 1 and ndone == E
     assert g.faults() == 0
     o.close(); g.close()
+
+
+@pytest.mark.parametrize("A", [1, 3])
+def test_hex_explore_reset_parity(built, A):
+    """HexExplore: honeycomb maze (Kruskal), walls as boxes rotated about Y (colliders + drawables), landmark and edging boxes,
+    the diamond; hundreds of instances per view"""
+    E = 6
+    o, g = _pair("HexExplore", E, A, 17)
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("policy", ["purposeful", "bits"])
+def test_hex_explore_trajectory_parity(built, policy):
+    """agents sliding along rotated walls (capsule vs oriented box sweeps / recoveries), finding the diamond: exploreSolved,
+    timer, the diamond moved away"""
+    E, A, steps = 24, 2, 930
+    o, g = _pair("HexExplore", E, A, 23)
+    rng = np.random.default_rng(4)
+    total, ndone = 0.0, 0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t) if policy == "purposeful" else helpers.random_bit_actions(rng, E * A)
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        total += float(np.abs(ro).sum()); ndone += int(o.dones().sum())
+        if t % 40 == 0 or t == steps - 1 or o.dones().any() or np.abs(ro).sum() > 0:
+            _assert_same_state(o, g, E, "step %d" % t)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+    if policy == "purposeful":
+        assert total > 0.0
+    assert ndone >= E
+    assert g.faults() == 0
+    o.close(); g.close()

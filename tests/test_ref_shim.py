@@ -124,3 +124,21 @@ def test_voxel_hash_rng_and_hash_map_order(libs):
         ka = R.ref_voxel_grid_order(xyz.ctypes.data, len(pts), oa.ctypes.data)
         kb = O.orc_voxel_grid_order(xyz.ctypes.data, len(pts), ob.ctypes.data)
         assert ka == kb and np.array_equal(oa[:ka], ob[:kb])
+
+
+@pytest.mark.parametrize("size", [2, 3, 5, 7])
+def test_honeycomb_maze_matches_reference_library(libs, size):
+    """the honeycomb maze + Kruskal restatement (oracle/orc_maze.hpp) against the reference's own maze library compiled from
+    /root/reference, both seeded explicitly: same adjacency lists in the same order, same border segments and centres (bits)"""
+    ref, L = libs
+    if not hasattr(ref, "ref_honeycomb_maze"):
+        pytest.skip("oracle/_ref/libmvref.so predates the maze shim")
+    for fn in (ref.ref_honeycomb_maze, L.orc_honeycomb_maze):
+        fn.argtypes = [C.c_int, C.c_uint, C.c_void_p, C.c_int]
+        fn.restype = C.c_int
+    for seed in (1, 42, 12345):
+        a = np.zeros(1 << 16, dtype=np.float64); b = np.zeros(1 << 16, dtype=np.float64)
+        na = ref.ref_honeycomb_maze(size, seed, a.ctypes.data, a.size)
+        nb = L.orc_honeycomb_maze(size, seed, b.ctypes.data, b.size)
+        assert na == nb and na > 0
+        assert np.array_equal(a[:na].view(np.uint64), b[:nb].view(np.uint64))
