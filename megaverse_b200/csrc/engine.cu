@@ -873,7 +873,7 @@ int mv_debug_get_state(mv_handle h, int env, float *out, int cap) {
         for (float x : {t[0], t[1], t[2], b.s[0], b.s[1], b.s[2], float(b.parent), b.enabled ? 1.f : 0.f, 0.f}) o.push_back(x);
     }
     if (L.scenario != MV_SCENARIO_TOWER) {
-        o.push_back(float(es.solved)); o.push_back(float(es.reached_exit));
+        o.push_back(float(es.solved)); o.push_back(float(L.scenario == MV_SCENARIO_HEX_MEMORY ? uint32_t(es.positive_collected) : es.reached_exit));
         for (int w = 0; w < 3; ++w) o.push_back(float(es.reward_alive[w] & 0xffffffu)), o.push_back(float(es.reward_alive[w] >> 24));
     }
     if (int(o.size()) > cap) return -int(o.size());

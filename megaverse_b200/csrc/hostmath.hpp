@@ -26,6 +26,22 @@ inline M4 mul(const M4 &a, const M4 &b) {
 }
 inline M4 translation(float x, float y, float z) { M4 m = identity(); m.c[3][0] = x; m.c[3][1] = y; m.c[3][2] = z; return m; }
 inline M4 scaling(float x, float y, float z) { M4 m = identity(); m.c[0][0] = x; m.c[1][1] = y; m.c[2][2] = z; return m; }
+// Magnum Matrix::inverted(): adjugate / determinant, same operation order as dev_math.cuh's inverted4 and the oracle's
+inline float det3skip(const M4 &m, int skipCol, int skipRow) {
+#define MVH_E(ci, ri) m.c[(ci) + ((ci) >= skipCol)][(ri) + ((ri) >= skipRow)]
+    return MVH_E(0, 0) * ((MVH_E(1, 1) * MVH_E(2, 2)) - (MVH_E(2, 1) * MVH_E(1, 2))) - MVH_E(0, 1) * (MVH_E(1, 0) * MVH_E(2, 2) - MVH_E(2, 0) * MVH_E(1, 2)) +
+           MVH_E(0, 2) * (MVH_E(1, 0) * MVH_E(2, 1) - MVH_E(2, 0) * MVH_E(1, 1));
+#undef MVH_E
+}
+inline float cofactor4(const M4 &m, int col, int row) { return (((row + col) & 1) ? -1 : 1) * det3skip(m, col, row); }
+inline M4 inverted(const M4 &m) {
+    float d = 0.0f;
+    for (int col = 0; col < 4; ++col) d += m.c[col][0] * cofactor4(m, col, 0);
+    M4 o;
+    for (int col = 0; col < 4; ++col)
+        for (int row = 0; row < 4; ++row) o.c[col][row] = cofactor4(m, row, col) / d;
+    return o;
+}
 inline M4 rotationY(float a) {
     const float s = crsin(a), c = crcos(a);
     M4 m = identity();

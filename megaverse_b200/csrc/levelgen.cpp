@@ -363,7 +363,15 @@ void LevelGenerator::assignSlots(LevelOut &out) {
                 case DrawRef::EYES: if (mesh == 0) { L.slot_eyes = slot; slot += A; } break;
                 case DrawRef::BARS: if (mesh == 0) { L.slot_bars = slot; slot += A; } break;
                 case DrawRef::BODIES: if (mesh == 1) { L.slot_body = slot; slot += A; } break;
-                case DrawRef::REWARDS: if (mesh == 3) { L.slot_reward = slot; slot += 2 * L.n_reward; } break;
+                case DrawRef::REWARDS:  // every reward object is a diamond: two cones
+                    if (mesh == 3) {
+                        L.slot_reward = slot;
+                        for (int r = 0; r < L.n_reward; ++r) { L.reward_slot[r] = int16_t(slot); L.reward_mesh[r] = 3; L.reward_cnt[r] = 2; slot += 2; }
+                    }
+                    break;
+                case DrawRef::REWARD_ONE:
+                    if (L.reward_mesh[d.index] == mesh) { L.reward_slot[d.index] = int16_t(slot); slot += L.reward_cnt[d.index]; }
+                    break;
             }
         }
         L.mesh_counts[mesh] = slot - first;
@@ -1003,7 +1011,118 @@ void LevelGenerator::generateHexExplore(LevelOut &out) {
     out.solid.assign(1, 0u); out.exitBits.assign(1, 0u); out.lavaBits.assign(1, 0u);
 }
 
-void LevelGenerator::generateHexMemory(LevelOut &) { throw std::runtime_error("HexMemory: not implemented yet"); }
+// HexMemoryScenario (scenario_hex_memory.cpp:19-217): a landmark object in the central cell shows which objects to collect
+void LevelGenerator::generateHexMemory(LevelOut &out) {
+    using namespace mvh;
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    HexMazeComponent hm;
+    hm.reset(rng, episodeSeed_, 2, 8, 0.1f, 0.95f);
+    const auto &centers = hm.maze->centers;
+    const int numCells = int(centers.size());
+    float minDist = 1e9f;
+    int centerCell = 0;
+    for (int c = 0; c < numCells; ++c) {
+        const double d = std::sqrt(centers[size_t(c)][0] * centers[size_t(c)][0] + centers[size_t(c)][1] * centers[size_t(c)][1]);
+        if (d < minDist) { centerCell = c; minDist = float(d); }
+    }
+    const float landmark[3] = {float(centers[size_t(centerCell)][0] * hm.scale), 1.0f, float(centers[size_t(centerCell)][1] * hm.scale)};
+    std::vector<std::array<float, 3>> coords;
+    for (int c = 0; c < numCells; ++c) {
+        if (c == centerCell) continue;
+        // Vector3(frand - 0.5f, 0, frand - 0.5f): GCC evaluates call arguments right to left, z is drawn first
+        const float oz = frand(rng) - 0.5f;
+        const float ox = frand(rng) - 0.5f;
+        const float cx = float(centers[size_t(c)][0]) + ox, cy = 0.5f + 0.0f, cz = float(centers[size_t(c)][1]) + oz;
+        coords.push_back({cx * hm.scale, cy, cz * hm.scale});
+    }
+    std::shuffle(coords.begin(), coords.end(), rng);
+    const float fraction = frand(rng) * 0.25f + 0.2f;
+    const long nGood = std::lround(ceilf(fraction * coords.size())), nBadWanted = nGood;
+    const long nBad = long(coords.size()) >= nGood + nBadWanted ? nBadWanted : 0;
+    // agents: evenly spaced on a circle of radius 1.5 around the origin, heading = their angle, no draws (:121-153)
+    const float rot = float(2 * M_PI / A);
+    for (int i = 0; i < A; ++i) {
+        const float p[3] = {sinf(rot * float(i)) * 1.5f, float(0.3) * 1.5f, cosf(rot * float(i)) * 1.5f};
+        yawBasis(rot * i, L.spawn_basis[i]);
+        const float sx = p[0] + 0.5f, sy = p[1] + 0.0f, sz = p[2] + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        for (int a = 0; a < 3; ++a) L.init_pos[i][a] = p[a];
+    }
+    // addEpisodeDrawables (:156-217)
+    enum { PILLAR, DIAMOND, SPHERE };
+    uint32_t goodColor = randomObjectColor(rng), badColor = goodColor;
+    int goodShape = randRange(0, 3, rng), badShape = goodShape;
+    while (badColor == goodColor && badShape == goodShape) { badColor = randomObjectColor(rng); badShape = randRange(0, 3, rng); }
+    int ns = 0;
+    hexMazeBuild(hm, rng, out, ns);
+    L.n_static = ns; L.n_static_pre = ns; L.n_grid_static = 0;
+    const M4 bottom = coneBottomLocal();
+    std::memcpy(L.cone_bottom_local, &bottom.c[0][0], 64);
+    auto shapeScale = [](int shape, float sc[3]) {
+        if (shape == SPHERE) { sc[0] = sc[1] = sc[2] = 0.75f; }
+        else if (shape == PILLAR) { sc[0] = 0.5f; sc[1] = 2.0f; sc[2] = 0.5f; }
+        else { sc[0] = 0.17f * float(2.2); sc[1] = 0.45f * float(2.2); sc[2] = 0.17f * float(2.2); }
+    };
+    auto shapeShift = [](int shape, float sh[3]) {
+        sh[0] = 0.5f; sh[2] = 0.5f;
+        sh[1] = shape == SPHERE ? 0.1f : (shape == PILLAR ? 0.05f : 0.6f);
+    };
+    // one object: root = T(loc) * S(scale); diamonds add the shared lower-cone local, pillars two caps re-parented keeping their pose
+    auto build = [&](int shape, const float loc[3], const float sc[3], M4 &root, M4 child[2], int &mesh, int &cnt) {
+        root = mul(translation(loc[0], loc[1], loc[2]), mul(scaling(sc[0], sc[1], sc[2]), identity()));
+        if (shape == SPHERE) { mesh = 2; cnt = 1; }
+        else if (shape == DIAMOND) { mesh = 3; cnt = 2; child[0] = bottom; }
+        else {
+            mesh = 4; cnt = 3;
+            const float capScale[3] = {sc[0] * 1.2f, 0.15f, sc[2] * 1.2f}, capT[3] = {0.0f * sc[0], 0.47f * sc[1], 0.0f * sc[2]};
+            const M4 inv = inverted(root);
+            for (int k = 0; k < 2; ++k) {
+                const float sgn = k == 0 ? 1.0f : -1.0f;
+                const float t[3] = {k == 0 ? loc[0] + capT[0] : loc[0] - capT[0], k == 0 ? loc[1] + capT[1] : loc[1] - capT[1], k == 0 ? loc[2] + capT[2] : loc[2] - capT[2]};
+                (void)sgn;
+                child[k] = mul(inv, mul(translation(t[0], t[1], t[2]), mul(scaling(capScale[0], capScale[1], capScale[2]), identity())));
+            }
+        }
+    };
+    {   // the landmark: static
+        float sc[3], sh[3];
+        shapeScale(goodShape, sc); shapeShift(goodShape, sh);
+        const float loc[3] = {landmark[0] + sh[0], landmark[1] + sh[1], landmark[2] + sh[2]};
+        M4 root, child[2]; int mesh, cnt;
+        build(goodShape, loc, sc, root, child, mesh, cnt);
+        pushDeco(out, root, mesh, goodColor);
+        for (int k = 1; k < cnt; ++k) pushDeco(out, mul(root, child[k - 1]), mesh, goodColor);
+    }
+    const float objScale = float(0.6);
+    if (nGood + nBad > MV_MAX_REWARD) throw std::runtime_error("too many collectable objects");
+    L.n_reward = int(nGood + nBad); L.n_positive = int(nGood);
+    for (int r = 0; r < L.n_reward; ++r) {
+        const bool good = r < nGood;
+        const int shape = good ? goodShape : badShape;
+        const auto &c = coords[size_t(r)];
+        float sc[3], sh[3];
+        shapeScale(shape, sc); shapeShift(shape, sh);
+        const float loc[3] = {c[0] + sh[0] * objScale, c[1] + sh[1] * objScale, c[2] + sh[2] * objScale};
+        const float scs[3] = {sc[0] * objScale, sc[1] * objScale, sc[2] * objScale};
+        M4 root, child[2]; int mesh, cnt;
+        build(shape, loc, scs, root, child, mesh, cnt);
+        std::memcpy(L.reward_root[r], &root.c[0][0], 64);
+        if (mesh == 4) { std::memcpy(L.reward_child[r][0], &child[0].c[0][0], 64); std::memcpy(L.reward_child[r][1], &child[1].c[0][0], 64); }
+        L.reward_mesh[r] = int8_t(mesh); L.reward_cnt[r] = int8_t(cnt);
+        if (good) L.reward_good[r >> 5] |= 1u << (r & 31);
+        L.reward_voxel[r][0] = int16_t(std::lround(std::floor(c[0]))); L.reward_voxel[r][1] = int16_t(std::lround(std::floor(c[1]))); L.reward_voxel[r][2] = int16_t(std::lround(std::floor(c[2])));
+        L.reward_voxel[r][3] = int16_t(paletteIndex(good ? goodColor : badColor));
+        out.drawSeq.push_back({DrawRef::REWARD_ONE, r});
+    }
+    out.drawSeq.push_back({DrawRef::EYES, 0}); out.drawSeq.push_back({DrawRef::BARS, 0}); out.drawSeq.push_back({DrawRef::BODIES, 0});
+    L.n_terrain = 0; L.n_obj = 0; L.n_movable = 0;
+    L.episode_len = params_.at("episodeLengthSec") + 3.0f * float(nGood);  // scenario_hex_memory.hpp:51-55
+    L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
+    L.grid_dim[0] = 1; L.grid_dim[1] = 1; L.grid_dim[2] = 1;
+    out.solid.assign(1, 0u); out.exitBits.assign(1, 0u); out.lavaBits.assign(1, 0u);
+}
 
 // three bit planes over the dense grid: solid, exit terrain, lava terrain
 void LevelGenerator::fillPlanes(LevelOut &out, const void *gridPtr) {

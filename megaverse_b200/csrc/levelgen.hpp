@@ -17,7 +17,7 @@ namespace mv {
 using FloatParams = std::map<std::string, float>;
 
 // one entry of a level's draw sequence (insertion order of the reference's drawables); slots are assigned per mesh type
-struct DrawRef { enum Kind { STATIC, TERRAIN, OBJECT, DECO, EYES, BARS, BODIES, REWARDS } kind; int index; };
+struct DrawRef { enum Kind { STATIC, TERRAIN, OBJECT, DECO, EYES, BARS, BODIES, REWARDS, REWARD_ONE } kind; int index; };  // REWARDS: all, as cone pairs
 
 struct LevelOut {
     MvLevel level;

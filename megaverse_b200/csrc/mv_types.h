@@ -21,7 +21,7 @@
 #define MV_MAX_STATIC 768
 #define MV_MAX_TERRAIN 16
 #define MV_MAX_OBJECTS 128
-#define MV_MAX_REWARD 96
+#define MV_MAX_REWARD 128
 #define MV_MAX_CAND 96      // per-agent collision candidates per step
 #define MV_NO_OBJECT 0xFF
 
@@ -147,6 +147,12 @@ struct MvLevel {
     int16_t reward_voxel[MV_MAX_REWARD][4];  // reward objects: voxel + palette colour (Collect: GREEN = +1, RED = -1)
     float reward_root[MV_MAX_REWARD][16];    // addDiamond root model matrix (layout_utils.cpp:114-126)
     float cone_bottom_local[16];             // the lower cone's local transform (rotateXLocal(180 deg), translate(0,-1,0))
+    // per reward object: first instance slot, mesh, number of instances (1 sphere, 2 cones, 3 cylinders = pillar with two caps),
+    // goodness (HexMemory); pillars keep their caps' local transforms (setParentKeepTransformation, layout_utils.cpp:100-112)
+    int16_t reward_slot[MV_MAX_REWARD];
+    int8_t reward_mesh[MV_MAX_REWARD], reward_cnt[MV_MAX_REWARD];
+    uint32_t reward_good[4];
+    float reward_child[MV_MAX_REWARD][2][16];
 };
 
 struct MvAgent {
@@ -190,7 +196,7 @@ struct MvEnvState {
     // std::unordered_set<VoxelCoords> objectsInBuildingZone, emulated in libstdc++ iteration order (bzset.h)
     int32_t solved;          // Obstacles: all agents reached the exit
     uint32_t reached_exit;   // Obstacles: bit per agent; Rearrange: maxMatchingObjects
-    uint32_t reward_alive[3];  // bit per reward object still in place
+    uint32_t reward_alive[4];  // bit per reward object still in place
     int32_t positive_collected;  // Collect; Sokoban: numBoxesOnGoal
     int32_t bz_count, bz_nb, bz_next_resize;
     int16_t bz_items[MV_MAX_OBJECTS][4];

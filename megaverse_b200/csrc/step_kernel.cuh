@@ -77,7 +77,8 @@ struct WarpShared {  // one per warp
     int objDirty[MV_MAX_AGENTS * 2];
     int nDirty;
     int doneFlag;
-    uint32_t rewardDirty[3];  // reward objects collected this step (their instances need rewriting)
+    uint32_t rewardDirty[4];  // reward objects collected this step (their instances need rewriting)
+    uint32_t memoryNear;      // HexMemory: bit per agent that has a collectable within reach
     // this agent's collision candidates for the current step, ascending collider index: boxes are copied here (static
     // layout boxes straight from the level in global memory, movable objects from the staged records), agents are looked
     // up live because they move within the step
@@ -696,7 +697,7 @@ __device__ void resetEnv(WarpShared &S, const MvLevel &L, uint8_t *objGrid, int 
         MvEnvState &e = S.env;
         e.episode_sec = 0.0f; e.num_frames = 0; e.highest_tower = 0;
         e.solved = 0; e.reached_exit = 0u; e.positive_collected = 0;
-        for (int w = 0; w < 3; ++w) { const int nb = L.n_reward - 32 * w; e.reward_alive[w] = nb >= 32 ? 0xffffffffu : (nb > 0 ? ((1u << nb) - 1u) : 0u); }
+        for (int w = 0; w < 4; ++w) { const int nb = L.n_reward - 32 * w; e.reward_alive[w] = nb >= 32 ? 0xffffffffu : (nb > 0 ? ((1u << nb) - 1u) : 0u); }
         mvBzClear(e);
         if (L.scenario == MV_SCENARIO_TOWER) {
             for (int i = 0; i < L.n_obj; ++i) {
@@ -839,12 +840,14 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, const MvDe
         const bool alive = (S.env.reward_alive[i >> 5] >> (i & 31)) & 1u;
         if (!writeStatic && !((S.rewardDirty[i >> 5] >> (i & 31)) & 1u)) continue;
         M4 root = loadM4(L.reward_root[i]);
-        if (!alive) {  // collected: Obstacles moves it by 1000, Collect by 500 (scenario_obstacles.cpp:224, scenario_collect.cpp:157)
-            const float far = L.scenario == MV_SCENARIO_COLLECT ? 500.0f : 1000.0f;
+        if (!alive) {  // collected: moved away by 1000 (Obstacles :224, HexExplore :54), 500 (Collect :157) or 100 (HexMemory :108)
+            const float far = L.scenario == MV_SCENARIO_COLLECT ? 500.0f : (L.scenario == MV_SCENARIO_HEX_MEMORY ? 100.0f : 1000.0f);
             root = mul4(translation4(v3(far, far, far)), root);
         }
-        putInstance(inst[L.slot_reward + 2 * i], root, 3, L.reward_voxel[i][3]);
-        putInstance(inst[L.slot_reward + 2 * i + 1], mul4(root, loadM4(L.cone_bottom_local)), 3, L.reward_voxel[i][3]);
+        const int slot0 = L.reward_slot[i], mesh = L.reward_mesh[i], cnt = L.reward_cnt[i];
+        putInstance(inst[slot0], root, mesh, L.reward_voxel[i][3]);
+        for (int k = 1; k < cnt; ++k)
+            putInstance(inst[slot0 + k], mul4(root, mesh == 3 ? loadM4(L.cone_bottom_local) : loadM4(L.reward_child[i][k - 1])), mesh, L.reward_voxel[i][3]);
     }
     if (lane == 0) {
         counts[0] = L.mesh_counts[0]; counts[1] = L.mesh_counts[0] + L.mesh_counts[1] + L.mesh_counts[2] + L.mesh_counts[3] + L.mesh_counts[4];
@@ -886,7 +889,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         const uint32_t *asrc = reinterpret_cast<const uint32_t *>(&P.agents[size_t(env) * A]);
         uint32_t *adst = reinterpret_cast<uint32_t *>(&S.agents[0]);
         for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
-        if (lane == 0) { S.nDirty = 0; S.rewardDirty[0] = S.rewardDirty[1] = S.rewardDirty[2] = 0u; }
+        if (lane == 0) { S.nDirty = 0; S.rewardDirty[0] = S.rewardDirty[1] = S.rewardDirty[2] = S.rewardDirty[3] = 0u; S.memoryNear = 0u; }
         for (int i = lane; i < MV_MAX_AGENTS; i += 32) S.lastReward[i] = 0.0f;
     }
     __syncwarp();
@@ -1048,6 +1051,20 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         __syncwarp();
 
         MV_PROBE(4);  // updateTransform
+        if (L->scenario == MV_SCENARIO_HEX_MEMORY) {
+            // lanes look for collectables within the collect radius of some agent; the ordered (rare) bookkeeping stays on lane 0
+            for (int i = 0; i < A; ++i) {
+                const MvAgent &a = S.agents[i];
+                bool near = false;
+                for (int r = lane; r < L->n_reward; r += 32) {
+                    if (!((S.env.reward_alive[r >> 5] >> (r & 31)) & 1u)) continue;
+                    const V3 dlt = v3(L->reward_root[r][12] - a.object_t[12], L->reward_root[r][13] - a.object_t[13], L->reward_root[r][14] - a.object_t[14]);
+                    if (sqrtf(dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z) < 1.0f) near = true;
+                }
+                if (__ballot_sync(FULL, near) && lane == 0) S.memoryNear |= 1u << i;
+            }
+            __syncwarp();
+        }
         // ---- scenario step: interact, fall detection, shaping rewards -- scalar work, lane 0
         if (lane == 0) {
             MvEnvState &e = S.env;
@@ -1181,7 +1198,36 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     resetAgent(i);
                     if (L->scenario == MV_SCENARIO_COLLECT) rewardAgent(MV_R_COLLECT_BAD, i, 1);  // agentFell (scenario_collect.cpp:214-218)
                 }
-            if (L->scenario == MV_SCENARIO_HEX_EXPLORE) {
+            if (L->scenario == MV_SCENARIO_HEX_MEMORY) {
+                // HexMemoryScenario::step (scenario_hex_memory.cpp:79-119); positive_collected = goodObjectsCollected, n_positive = #good
+                if (e.positive_collected >= L->n_positive && !e.solved) {
+                    e.solved = 1;
+                    const float t = L->episode_len - 0.3f;  // doneWithTimer()
+                    e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
+                }
+                for (int i = 0; i < A; ++i) {
+                    if (!((S.memoryNear >> i) & 1u)) continue;
+                    const MvAgent &a = S.agents[i];
+                    const V3 t = v3(a.object_t[12], a.object_t[13], a.object_t[14]);
+                    int ax, ay, az;
+                    toVoxel(t, ax, ay, az);
+                    for (int dx = -1; dx <= 1; ++dx)
+                        for (int dz = -1; dz <= 1; ++dz)
+                            for (int r = 0; r < L->n_reward; ++r) {  // the voxel's object list, insertion order
+                                if (!((e.reward_alive[r >> 5] >> (r & 31)) & 1u)) continue;
+                                if (L->reward_voxel[r][0] != ax + dx || L->reward_voxel[r][1] != ay || L->reward_voxel[r][2] != az + dz) continue;
+                                const V3 dlt = v3(L->reward_root[r][12] - t.x, L->reward_root[r][13] - t.y, L->reward_root[r][14] - t.z);
+                                const float distance = sqrtf(dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z);
+                                if (distance < 1.0f) {
+                                    const bool good = (L->reward_good[r >> 5] >> (r & 31)) & 1u;
+                                    rewardTeam(good ? MV_R_MEMORY_GOOD : MV_R_MEMORY_BAD, i, 1);
+                                    e.positive_collected += good ? 1 : 0;
+                                    e.reward_alive[r >> 5] &= ~(1u << (r & 31));
+                                    S.rewardDirty[r >> 5] |= 1u << (r & 31);
+                                }
+                            }
+                }
+            } else if (L->scenario == MV_SCENARIO_HEX_EXPLORE) {
                 // HexExploreScenario::step (scenario_hex_explore.cpp:42-58): first agent within 1.2 of the diamond's floor point
                 for (int i = 0; i < A; ++i) {
                     const MvAgent &a = S.agents[i];

@@ -210,6 +210,11 @@ int orc_get_state(void *p, int envIdx, float *out, int cap) {
         for (int i = 0; i < env.numAgents; ++i) reached |= env.agentReachedExit[size_t(i)] ? (1u << i) : 0u;
         if (env.scenario == Env::S_REARRANGE) reached = uint32_t(env.maxMatchingObjects);
         if (env.scenario == Env::S_HEX_EXPLORE) alive[0] = env.exploreRewardAlive ? 1u : 0u;
+        if (env.scenario == Env::S_HEX_MEMORY) {
+            reached = uint32_t(env.goodObjectsCollected);
+            for (size_t r = 0; r < env.memoryObjects.size() && r < 96; ++r)
+                if (env.memoryObjects[r].alive) alive[r >> 5] |= 1u << (r & 31);
+        }
         for (size_t r = 0; r < env.rewardSpawnPositions.size() && r < 96; ++r) {
             const Voxel *v = env.vg.grid.get(env.rewardSpawnPositions[r]);
             if (v && v->rewardObject == int(r)) alive[r >> 5] |= 1u << (r & 31);

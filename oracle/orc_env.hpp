@@ -39,7 +39,7 @@ struct Instance {  // one drawable: mesh type, palette colour, model matrix (abs
 // DrawablesMap (env.hpp:57-67,72): mesh type -> drawables in insertion order.  An entry names the scene-graph object whose
 // absolute transformation is the model matrix at draw time.
 struct DrawEntry {
-    enum Kind { D_STATIC, D_OBJECT, D_EYES, D_BAR, D_BODY, D_REWARD_ROOT, D_REWARD_BOTTOM } kind;
+    enum Kind { D_STATIC, D_OBJECT, D_EYES, D_BAR, D_BODY, D_REWARD_ROOT, D_REWARD_BOTTOM, D_MEMORY } kind;  // D_MEMORY: index = object * 4 + child
     int index;
     int color;
     Mat4 model;  // D_STATIC
@@ -122,6 +122,7 @@ public:
     struct SokobanLevel { std::vector<std::string> rows; };
     enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
     struct RewardObject { Mat4 root, bottomLocal; int color; };
+    struct MemoryObject { Mat4 root; Mat4 childLocal[2]; int numChildren = 0; bool good = false, alive = true; VoxelCoords voxel{0, 0, 0}; };  // CollectableObject
     struct ArrangementItem { int shape = MESH_SPHERE; ColorRgb color = WHITE; VoxelCoords offset{0, 0, 0}; };  // scenario_rearrange.hpp:20-53
 
     Env(const std::string &scenarioName, int numAgents, const FloatParams &custom) : numAgents(numAgents) {
@@ -372,11 +373,156 @@ public:
         }
     }
 
-    // ---------------------------------------------------------------- HexMemory: see below (scenario_hex_memory.cpp)
-    void hexMemoryReset() { throw std::runtime_error("oracle: HexMemory not restated yet"); }
-    void hexMemorySpawnAgents() {}
-    void hexMemoryAddEpisodeDrawables() {}
-    void hexMemoryStep() {}
+    // ---------------------------------------------------------------- HexMemory (scenario_hex_memory.cpp:19-217)
+    enum MemoryShape { SHAPE_PILLAR, SHAPE_DIAMOND, SHAPE_SPHERE };
+    void hexMemoryReset() {
+        solved = false;
+        vg.reset();
+        carryingObject.assign(size_t(numAgents), -1);
+        objectSpawnPositions.clear(); rewardSpawnPositions.clear();
+        goodObjects.clear(), badObjects.clear();
+        goodObjectsCollected = 0;
+        memoryObjects.clear();
+        hexMazeReset(2, 8, 0.1f, 0.95f);
+        const auto &centers = hexMaze->cellCenters;
+        const int numCells = int(hexMaze->adjacency.size());
+        float minDistanceToCenter = 1e9f;
+        int centerCellIdx = 0;
+        for (int cellIdx = 0; cellIdx < numCells; ++cellIdx) {
+            const auto cellCenter = centers[size_t(cellIdx)];
+            const auto distanceToCenter = std::sqrt(cellCenter.first * cellCenter.first + cellCenter.second * cellCenter.second);
+            if (distanceToCenter < minDistanceToCenter) { centerCellIdx = cellIdx; minDistanceToCenter = float(distanceToCenter); }
+        }
+        const auto mazeCenter = centers[size_t(centerCellIdx)];
+        landmarkLocation = Vec3{float(mazeCenter.first * hexMazeScale), 1.0f, float(mazeCenter.second * hexMazeScale)};
+        std::vector<Vec3> objectCoordinates;
+        for (int cellIdx = 0; cellIdx < numCells; ++cellIdx) {
+            if (cellIdx == centerCellIdx) continue;
+            const auto cellCenter = centers[size_t(cellIdx)];
+            Vec3 coord{float(cellCenter.first), 0.5f, float(cellCenter.second)};
+            // Vector3(frand - 0.5f, 0, frand - 0.5f): GCC evaluates call arguments right to left, z's draw comes first
+            const float oz = frand(rng) - 0.5f;
+            const float ox = frand(rng) - 0.5f;
+            coord += Vec3{ox, 0, oz};
+            objectCoordinates.emplace_back(Vec3{coord.x * hexMazeScale, coord.y, coord.z * hexMazeScale});
+        }
+        std::shuffle(objectCoordinates.begin(), objectCoordinates.end(), rng);
+        const float cellWithObjectsFraction = frand(rng) * 0.25f + 0.2f;
+        const long numCellsWithGoodObjects = std::lround(ceilf(cellWithObjectsFraction * objectCoordinates.size()));
+        const long numCellsWithBadObjects = std::lround(ceilf(cellWithObjectsFraction * objectCoordinates.size()));
+        goodObjects = std::vector<Vec3>(objectCoordinates.begin(), objectCoordinates.begin() + numCellsWithGoodObjects);
+        if (int(objectCoordinates.size()) >= numCellsWithGoodObjects + numCellsWithBadObjects)
+            badObjects = std::vector<Vec3>(objectCoordinates.begin() + numCellsWithGoodObjects, objectCoordinates.begin() + numCellsWithGoodObjects + numCellsWithBadObjects);
+        // agentStartingPositions (:121-130)
+        const auto rotationBetweenAgents = float(2 * M_PI / numAgents);
+        agentSpawnPositions.assign(size_t(numAgents), Vec3{0, 0, 0});
+        for (int i = 0; i < numAgents; ++i)
+            agentSpawnPositions[size_t(i)] = Vec3{sinf(rotationBetweenAgents * float(i)), float(0.3), cosf(rotationBetweenAgents * float(i))} * 1.5f;
+        agentInitialPositions = agentSpawnPositions;
+    }
+    void hexMemorySpawnAgents() {  // :132-153: evenly spaced headings, no draws
+        const float lookLimit = floatParams["verticalLookLimitRad"];
+        const auto rotationBetweenAgents = float(2 * M_PI / numAgents);
+        agents.resize(size_t(numAgents));
+        for (int i = 0; i < numAgents; ++i) {
+            const auto randomRotation = rotationBetweenAgents * i;
+            agents[size_t(i)].init(agentSpawnPositions[size_t(i)] + Vec3{0.5f, 0.0f, 0.5f}, randomRotation, lookLimit);
+            agents[size_t(i)].updateTransform();
+        }
+    }
+    // addSphere / addDiamond / addPillar (layout_utils.cpp:86-126); returns the index of the created memory object or -1 for the landmark
+    void addMemoryShape(int shape, ColorRgb color, Vec3 loc, Vec3 scale, bool collectable, bool good) {
+        MemoryObject mo;
+        mo.good = good; mo.alive = true;
+        mo.root = mul(mat4Translation(loc), mul(mat4Scaling(scale), mat4Identity()));
+        const int idx = collectable ? int(memoryObjects.size()) : -1;
+        const int pc = paletteIndex(color);
+        auto pushDraw = [&](int mesh, int child, const Mat4 &model) {
+            if (collectable) drawables[mesh].push_back({DrawEntry::D_MEMORY, idx * 4 + child, pc, mat4Identity()});
+            else drawables[mesh].push_back({DrawEntry::D_STATIC, 0, pc, model});
+        };
+        if (shape == SHAPE_SPHERE) {
+            mo.numChildren = 0;
+            pushDraw(MESH_SPHERE, 0, mo.root);
+        } else if (shape == SHAPE_DIAMOND) {
+            mo.numChildren = 1;
+            mo.childLocal[0] = mul(mat4Translation({0.0f, -1.0f, 0.0f}), mul(mat4Identity(), mat4RotationX(180.0f * 3.14159265358979323846f / 180.0f)));
+            pushDraw(MESH_CONE, 0, mo.root);
+            pushDraw(MESH_CONE, 1, mul(mo.root, mo.childLocal[0]));
+        } else {
+            mo.numChildren = 2;
+            const Vec3 capScale{scale.x * 1.2f, 0.15f, scale.z * 1.2f};
+            const Vec3 capTranslation = Vec3{0, 0.47f, 0} * scale;
+            pushDraw(MESH_CYLINDER, 0, mo.root);
+            const Mat4 rootInv = inverted(mo.root);
+            for (int k = 0; k < 2; ++k) {  // addCylinder(...)->setParentKeepTransformation(rootObject): local = parentAbs^-1 * abs
+                const Vec3 t = k == 0 ? loc + capTranslation : loc - capTranslation;
+                const Mat4 capAbs = mul(mat4Translation(t), mul(mat4Scaling(capScale), mat4Identity()));
+                mo.childLocal[k] = mul(rootInv, capAbs);
+                pushDraw(MESH_CYLINDER, k + 1, mul(mo.root, mo.childLocal[k]));
+            }
+        }
+        if (collectable) memoryObjects.push_back(mo);
+    }
+    void hexMemoryAddEpisodeDrawables() {  // :156-217
+        static const std::vector<int> shapes = {SHAPE_PILLAR, SHAPE_DIAMOND, SHAPE_SPHERE};
+        auto goodObjectColor = randomObjectColor(rng), badObjectColor = goodObjectColor;
+        auto goodShape = randomSample(shapes, rng), badShape = goodShape;
+        while (badObjectColor == goodObjectColor && badShape == goodShape) {
+            badObjectColor = randomObjectColor(rng);
+            badShape = randomSample(shapes, rng);
+        }
+        hexMazeAddDrawablesAndCollisions();
+        auto shapeScale = [](int shape) {
+            if (shape == SHAPE_SPHERE) return Vec3{0.75f, 0.75f, 0.75f};
+            if (shape == SHAPE_PILLAR) return Vec3{0.5f, 2, 0.5f};
+            return Vec3{0.17f, 0.45f, 0.17f} * float(2.2);
+        };
+        auto shapeShift = [](int shape) {
+            if (shape == SHAPE_SPHERE) return Vec3{0.5f, 0.1f, 0.5f};
+            if (shape == SHAPE_PILLAR) return Vec3{0.5f, 0.05f, 0.5f};
+            return Vec3{0.5f, 0.6f, 0.5f};
+        };
+        addMemoryShape(goodShape, goodObjectColor, landmarkLocation + shapeShift(goodShape), shapeScale(goodShape), false, true);
+        const float objScale = float(0.6);
+        bool isGood = true;
+        for (const auto *objects : {&goodObjects, &badObjects}) {
+            for (const auto &coord : *objects) {
+                const auto shape = isGood ? goodShape : badShape;
+                const auto color = isGood ? goodObjectColor : badObjectColor;
+                addMemoryShape(shape, color, coord + shapeShift(shape) * objScale, shapeScale(shape) * objScale, true, isGood);
+                memoryObjects.back().voxel = vg.grid.getCoords(coord);
+            }
+            isGood = !isGood;
+        }
+    }
+    void hexMemoryStep() {  // :79-119
+        constexpr auto collectRadius = 1.0f;
+        if (goodObjectsCollected >= int(goodObjects.size()) && !solved) {
+            solved = true;
+            doneWithTimer();
+        }
+        for (int i = 0; i < numAgents; ++i) {
+            const Vec3 t = translationOf(agents[size_t(i)].objectT);
+            const auto agentCoords = vg.grid.getCoords(t);
+            for (int dx = -1; dx <= 1; ++dx)
+                for (int dz = -1; dz <= 1; ++dz) {
+                    const VoxelCoords coords(agentCoords.x + dx, agentCoords.y, agentCoords.z + dz);
+                    // voxel->objects: the collectables whose cell is this voxel, in insertion order
+                    for (auto &mo : memoryObjects) {
+                        if (!mo.alive || !(mo.voxel == coords)) continue;
+                        const Vec3 pillarPos = translationOf(mo.root);
+                        const auto distance = length(pillarPos - t);
+                        if (distance < collectRadius) {
+                            rewardTeam(mo.good ? "memoryCollectGood" : "memoryCollectBad", i, 1);
+                            goodObjectsCollected += mo.good;
+                            mo.root = mul(mat4Translation({100, 100, 100}), mo.root);
+                            mo.alive = false;
+                        }
+                    }
+                }
+        }
+    }
 
     // ---------------------------------------------------------------- Sokoban (scenario_sokoban.cpp:83-295)
     void sokobanReloadLevels() {
@@ -1397,6 +1543,12 @@ public:
                     case DrawEntry::D_BODY: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, a.bodyLocal); break; }
                     case DrawEntry::D_REWARD_ROOT: m = rewardObjects[size_t(d.index)].root; break;
                     case DrawEntry::D_REWARD_BOTTOM: m = mul(rewardObjects[size_t(d.index)].root, rewardObjects[size_t(d.index)].bottomLocal); break;
+                    case DrawEntry::D_MEMORY: {
+                        const MemoryObject &mo = memoryObjects[size_t(d.index / 4)];
+                        const int child = d.index % 4;
+                        m = child == 0 ? mo.root : mul(mo.root, mo.childLocal[child - 1]);
+                        break;
+                    }
                 }
                 out.push_back({mesh, d.color, m});
             }
@@ -1435,6 +1587,9 @@ public:
     Vec3 rewardObjectCoords{0, 0, 0};
     bool exploreRewardAlive = false;
     std::vector<Vec3> goodObjects, badObjects;
+    std::vector<MemoryObject> memoryObjects;
+    Vec3 landmarkLocation{0, 0, 0};
+    int goodObjectsCollected = 0;
     // Sokoban
     std::vector<std::string> allSokobanLevelFiles;
     std::vector<SokobanLevel> sokobanLevels;

@@ -108,7 +108,7 @@ def test_unordered_set_order_emulation(built):
 
 
 @pytest.mark.parametrize("scenario,num_agents", [("TowerBuilding", 1), ("TowerBuilding", 4), ("ObstaclesHard", 1), ("ObstaclesEasy", 2), ("ObstaclesMedium", 3),
-                                                 ("ObstaclesWalls", 1), ("ObstaclesSteps", 2), ("ObstaclesLava", 1), ("Collect", 1), ("Collect", 4), ("Rearrange", 1), ("Rearrange", 3), ("Sokoban", 1), ("Sokoban", 4), ("HexExplore", 1), ("HexExplore", 3)])
+                                                 ("ObstaclesWalls", 1), ("ObstaclesSteps", 2), ("ObstaclesLava", 1), ("Collect", 1), ("Collect", 4), ("Rearrange", 1), ("Rearrange", 3), ("Sokoban", 1), ("Sokoban", 4), ("HexExplore", 1), ("HexExplore", 3), ("HexMemory", 1), ("HexMemory", 4)])
 def test_level_generation_matches_oracle(built, scenario, num_agents):
     """the product's flat host level generator against the oracle's reference-style one: same RNG draws, same merged
     boxes in the same order, same objects, spawn cells and spawn yaw bits -- over consecutive episodes of one stream"""

@@ -467,3 +467,45 @@ def test_hex_explore_trajectory_parity(built, policy):
     assert ndone >= E
     assert g.faults() == 0
     o.close(); g.close()
+
+
+@pytest.mark.parametrize("A", [1, 4])
+def test_hex_memory_reset_parity(built, A):
+    """HexMemory: landmark object in the central cell, good / bad collectables (pillars = cylinder + two re-parented caps,
+    diamonds = two cones, spheres), agents on a circle with evenly spaced headings"""
+    E = 6
+    o, g = _pair("HexMemory", E, A, 29)
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("policy", ["purposeful", "bits"])
+def test_hex_memory_trajectory_parity(built, policy):
+    """collecting good (+1) and bad (-1) objects within the collect radius, all-good-collected -> solved + timer, objects moved
+    away; episode length grows with the number of good objects"""
+    E, A, steps = 16, 2, 1000
+    o, g = _pair("HexMemory", E, A, 41)
+    rng = np.random.default_rng(6)
+    total, ndone = 0.0, 0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t) if policy == "purposeful" else helpers.random_bit_actions(rng, E * A)
+        o.step(acts)
+        g.step(acts)
+        ro, rg = o.rewards(), np.array(g.rewards())
+        assert np.array_equal(ro.view(np.uint32), rg.view(np.uint32)), "step %d rewards %s vs %s" % (t, ro, rg)
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d dones" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        total += float(np.abs(ro).sum()); ndone += int(o.dones().sum())
+        if t % 50 == 0 or t == steps - 1 or o.dones().any() or np.abs(ro).sum() > 0:
+            _assert_same_state(o, g, E, "step %d" % t)
+            for e in range(0, E, 5):
+                assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "step %d instances %d" % (t, e)
+            assert _assert_same_frame(o, g, "step %d" % t) > 0.999
+    assert total > 0.0
+    assert g.faults() == 0
+    o.close(); g.close()
