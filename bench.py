@@ -29,6 +29,9 @@ sys.path.insert(0, ROOT)
 SCENARIO, ENVS_PER_GPU, AGENTS, W, H = "TowerBuilding", 256, 1, 128, 72
 OBS_BYTES = W * H * 4
 METRIC, UNIT = "agent obs/sec (whole box)", "obs/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of geomKernel + tileKernel per launch at 256 envs (profiles/r1c_summary.txt: 7.95 + 6.21
+# + 2.83 MB); the 9.4 MB of observations themselves stay in the 126 MB L2 until the consumer reads them
+NCU_DRAM_BYTES_PER_STEP = 16990000
 
 
 def measured_peaks():
@@ -130,7 +133,7 @@ def main():
         # the reference's own CPU path cannot be built here; the port (oracle) stands in.  Rank 0 only.
         if rank != 0:
             return
-        k = min(K, 400)
+        k = min(K, 4000)  # ~15 s at 256 envs on a 128-thread host: each "step" is one pass over the same 256-env batch
         v, dt = run_cpu(k, min(Wm, 10), cores, E)
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": k, "warmup": min(Wm, 10),
                 "ms_per_step": dt / k * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -152,8 +155,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     eng = capi.Engine(SCENARIO, E, AGENTS, W, H, num_threads=min(8, max(1, cores // max(world, 1))), device=local_rank)
-    for e in range(E):
-        eng.seed_env(e, 42 + rank * E + e)  # megaverse_test_app.cpp:250-254
+    from megaverse_b200 import sharding
+
+    begin, end = sharding.shard_range(E * world, world, rank)  # weak scaling: E envs on every rank
+    for e, seed in enumerate(sharding.env_seeds(begin, end)):
+        eng.seed_env(e, seed)  # global env i is seeded 42 + i (megaverse_test_app.cpp:250-254)
     eng.reset()
     stream = torch.cuda.ExternalStream(eng.stream(), device=local_rank)
     acts_host = action_stream(K + Wm, N, 1 + rank)
@@ -174,10 +180,7 @@ def main():
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            tt = torch.tensor([ms], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms = float(tt.item())
+        _, ms, _ = sharding.aggregate_throughput(1, ms, dist if world > 1 else None)  # max over ranks of the device time
         return ms
 
     step_bytes = N * 4
@@ -222,7 +225,7 @@ def main():
         stp.append(s_ms); ras.append(r_ms)
     ras_ms, stp_ms = float(np.mean(ras[10:])), float(np.mean(stp[10:]))
     achieved = N * OBS_BYTES / (ras_ms / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "mvr::geomKernel + mvr::tileKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": "mvr::geomKernel + mvr::tileKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_STEP if E == ENVS_PER_GPU else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": N * OBS_BYTES, "kernel_ms": ras_ms, "step_kernel_ms": stp_ms,
                 "note": "obs-write bytes / rasteriser duration; the kernel is FP32-issue bound (per-pixel Phong shading), see DESIGN.md"}
     faults = eng.faults()
@@ -230,8 +233,11 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
-        ksample = 60
+        ksample = 300  # then scaled to ~15 s of CPU work
         v, dt = run_cpu(ksample, 3, cores, E)
+        if dt < 12.0:
+            ksample = int(min(20000, ksample * 15.0 / max(dt, 1e-3)))
+            v, dt = run_cpu(ksample, 3, cores, E)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d envs x %d steps of the same workload on all %d host threads (%.1f s)" % (E, ksample, cores, dt)}
 
