@@ -83,6 +83,10 @@ int mv_step_device(mv_handle h, const int32_t *d_masks);
  * stream order).  mv_sync waits for everything enqueued and publishes the last step's rewards/dones/true objectives to the
  * host pointers.  Episode bookkeeping lags the device by two steps on this path, so it needs episodes of >= 4 steps
  * (always true with the scenarios' own parameters); a violation raises MV_FAULT_LEVEL_NOT_READY in mv_faults. */
+/* MegaverseGym::drawHires + getHiresObservation (megaverse.cpp:154-177,199-203): renders every agent view once more at w x h
+ * (multiples of 32 x 4, e.g. the reference's 768 x 432) from the state of the last step; *out = uint8[N][h][w][4], engine-owned,
+ * valid until the next mv_draw_hires / mv_close */
+int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out);
 int mv_sync(mv_handle h);
 /* after mv_step_device steps: waits, then copies the device obs (and depth, when enabled) into the host buffers that
  * mv_obs_host / mv_depth_host return */

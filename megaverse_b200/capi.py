@@ -58,7 +58,7 @@ def lib():
 EXPORTS = [
     "mv_create", "mv_last_error", "mv_seed", "mv_seed_env", "mv_reset", "mv_set_actions", "mv_encode_action", "mv_step", "mv_obs_host", "mv_depth_host",
     "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device",
-    "mv_sync", "mv_fetch_obs", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
+    "mv_sync", "mv_fetch_obs", "mv_draw_hires", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
     "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_tile_profile", "mv_debug_bzset", "mv_debug_generate_level",
 ]
@@ -112,6 +112,14 @@ class Engine:
 
     def sync(self):
         self._ck(lib().mv_sync(self._h))
+
+    def draw_hires(self, w, h):
+        """uint8[N,h,w,4] view of the engine's hi-res frame (valid until the next draw_hires)"""
+        p = C.c_void_p()
+        lib().mv_draw_hires.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        self._ck(lib().mv_draw_hires(self._h, int(w), int(h), C.byref(p)))
+        n = self.N * h * w * 4
+        return np.frombuffer((C.c_char * n).from_address(p.value), dtype=np.uint8).reshape(self.N, h, w, 4)
 
     def fetch_obs(self):
         self._ck(lib().mv_fetch_obs(self._h))

@@ -101,6 +101,9 @@ template <typename T> struct PinBuf {
 
 }  // namespace
 
+struct MvConsts;
+static void fillConstsFor(MvConsts &k, int W, int H);
+
 struct mv_engine {
     std::string error;
     void setError(const std::string &e) { error = e; }
@@ -148,6 +151,14 @@ struct mv_engine {
     DevBuf<int32_t> d_tileCounter;
     DevBuf<mvr::TriCover> d_cover;
     DevBuf<mvr::TriShade> d_shade;
+    // hi-res pass (draw_hires): its own scratch, allocated on first use
+    struct Hires {
+        int W = 0, H = 0, chunk = 0, binCap = 0;
+        DevBuf<uint8_t> d_obs; PinBuf<uint8_t> h_obs;
+        DevBuf<mvr::TriCover> cover; DevBuf<mvr::TriShade> shade;
+        DevBuf<int32_t> binCounts; DevBuf<uint16_t> binList; DevBuf<int4> wideList;
+        void free() { d_obs.free(); h_obs.free(); cover.free(); shade.free(); binCounts.free(); binList.free(); wideList.free(); W = H = 0; }
+    } hires;
     DevBuf<MvDeco> d_deco;
     PinBuf<MvDeco> h_deco;
     int decoCap = 1, instCap = MV_BASE_INSTANCES + 1;
@@ -315,6 +326,60 @@ struct mv_engine {
         }
         return MV_OK;
     }
+    // draw_hires (megaverse.cpp:154-177): every agent view once more, at (w, h), from the instance lists and camera matrices of
+    // the last step -- the same two kernels, their own scratch.  Result in hires.h_obs, uint8[N][h][w][4].
+    int drawHires(int w, int hgt) {
+        if (!didReset) { setError("mv_draw_hires before mv_reset"); return MV_ERR_STATE; }
+        if (w < 32 || hgt < 4 || (w % 32) || (hgt % 4) || w > 4096 || hgt > 4096) { setError("hi-res size must be a multiple of 32 x 4"); return MV_ERR_ARG; }
+        int rc = drain();
+        if (rc) return rc;
+        const int nTiles = (w / 32) * (hgt / 4);
+        if (hires.W != w || hires.H != hgt) {
+            hires.free();
+            hires.binCap = std::max(256, std::min(1024, triCap / 4));
+            const size_t perView = size_t(triCap) * (sizeof(mvr::TriCover) + sizeof(mvr::TriShade)) + size_t(nTiles) * (size_t(hires.binCap) * 2 + 4);
+            hires.chunk = int(std::max<size_t>(1, std::min<size_t>(size_t(N), (size_t(192) << 20) / perView)));
+            const size_t px = size_t(N) * w * hgt * 4, tiles = size_t(hires.chunk) * nTiles;
+            if (hires.d_obs.alloc(px) != cudaSuccess || hires.h_obs.alloc(px) != cudaSuccess || hires.cover.alloc(size_t(hires.chunk) * triCap) != cudaSuccess ||
+                hires.shade.alloc(size_t(hires.chunk) * triCap) != cudaSuccess || hires.binCounts.alloc(tiles) != cudaSuccess ||
+                hires.binList.alloc(tiles * size_t(hires.binCap)) != cudaSuccess || hires.wideList.alloc(size_t(hires.chunk) * mvr::kWideCap) != cudaSuccess ||
+                cudaMemset(hires.binCounts.p, 0, sizeof(int32_t) * tiles) != cudaSuccess) {
+                hires.free();
+                setError("hi-res buffers: allocation failed");
+                return MV_ERR_CUDA;
+            }
+            hires.W = w; hires.H = hgt;
+        }
+        MvConsts k;
+        fillConstsFor(k, w, hgt);
+        mvr::RasterParams rp;
+        rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = instCap;
+        rp.obs = hires.d_obs.p; rp.depth = nullptr; rp.faults = d_faults.p;
+        rp.cover = hires.cover.p; rp.shade = hires.shade.p; rp.triCounts = d_triCounts.p;
+        rp.binCounts = hires.binCounts.p; rp.binList = hires.binList.p; rp.wideCounts = d_wideCounts.p; rp.wideList = hires.wideList.p; rp.binCap = hires.binCap;
+        rp.tileProf = nullptr; rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.ready = nullptr; rp.readyStamp = 0;
+        rp.N = N; rp.A = A; rp.W = w; rp.H = hgt; rp.triCap = triCap;
+        rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
+        const int maxItems = instCap * 6 + (A + MV_MAX_OBJECTS + decoCap) * 128 + 3 * MV_MAX_REWARD * 80;
+        const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
+        // the per-view triangle / wide-list counters are shared with the training-resolution pass: clear them first
+        MV_CUDA(cudaMemsetAsync(d_triCounts.p, 0, sizeof(int32_t) * size_t(N), stream));
+        MV_CUDA(cudaMemsetAsync(d_wideCounts.p, 0, sizeof(int32_t) * size_t(N), stream));
+        for (int base = 0; base < N; base += hires.chunk) {
+            const int cv = std::min(hires.chunk, N - base);
+            rp.viewBase = base; rp.chunkViews = cv;
+            mvr::geomKernel<<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+            MV_CUDA(cudaGetLastError());
+            const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * mvr::kTileBlocksPerSM);
+            if (fastShading) mvr::tileKernel<true><<<tileBlocks, 128, 0, stream>>>(rp);
+            else mvr::tileKernel<false><<<tileBlocks, 128, 0, stream>>>(rp);
+            MV_CUDA(cudaGetLastError());
+            launches += 2;
+        }
+        MV_CUDA(cudaMemcpyAsync(hires.h_obs.p, hires.d_obs.p, size_t(N) * w * hgt * 4, cudaMemcpyDeviceToHost, stream));
+        MV_CUDA(cudaStreamSynchronize(stream));
+        return MV_OK;
+    }
     int allocTriScratch() {
         d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free();
         const size_t cnt = size_t(chunkViews) * size_t(triCap);
@@ -429,7 +494,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        d_deco.free(); h_deco.free(); d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
+        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -468,6 +533,10 @@ void fillConsts(MvConsts &k, int W, int H) {
     k.p22 = farZ / (nearZ - farZ);
     k.p32 = farZ * nearZ / (nearZ - farZ);
 }
+
+}  // namespace
+static void fillConstsFor(MvConsts &k, int W, int H) { fillConsts(k, W, H); }
+namespace {
 
 int setKernelAttrs(mv_engine *h) {
     cudaError_t err = cudaFuncSetAttribute(mvk::stepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(mvk::WarpShared) * 4));
@@ -688,6 +757,15 @@ int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable) {
     }
     if (out && h->d_tileProf.p && cudaMemcpy(out, h->d_tileProf.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     if (!enable) h->d_tileProf.free();
+    return MV_OK;
+}
+
+int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    const int rc = h->drawHires(w, hgt);
+    if (rc) return rc;
+    if (out) *out = h->hires.h_obs.p;
     return MV_OK;
 }
 

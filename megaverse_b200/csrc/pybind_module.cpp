@@ -138,11 +138,21 @@ public:
         check(mv_true_objectives(h__, &t));
         return t[size_t(envIdx) * numAgentsPerEnv_ + agentIdx];
     }
-    // hi-res / overview rendering is a "next" row: accepted, but draws at the training resolution
+    // hi-res rendering (megaverse.cpp:148-177,199-203): the same rasteriser at renderW x renderH; the overview camera / viewer is
+    // out of scope (a reference build without WITH_GUI does nothing there either)
     void setRenderResolution(int hiresW, int hiresH) { renderW_ = hiresW; renderH_ = hiresH; }
-    void drawHires() {}
+    void drawHires() {
+        alive();
+        py::gil_scoped_release nogil;
+        check(mv_draw_hires(h__, renderW_, renderH_, &hires_));
+    }
     void drawOverview() {}
-    py::array_t<uint8_t> getHiresObservation(int envIdx, int agentIdx) { return getObservation(envIdx, agentIdx); }
+    py::array_t<uint8_t> getHiresObservation(int envIdx, int agentIdx) {
+        alive();
+        if (!hires_) throw std::runtime_error("get_hires_observation before draw_hires");
+        const size_t view = size_t(envIdx) * numAgentsPerEnv_ + agentIdx;
+        return py::array_t<uint8_t>({renderH_, renderW_, 4}, hires_ + view * size_t(renderW_) * renderH_ * 4, py::none{});  // does not own memory
+    }
 
     std::map<std::string, float> getRewardShaping(int envIdx, int agentIdx) {
         alive();
@@ -173,6 +183,7 @@ private:
     mv_handle h__ = nullptr;
     int numEnvs_, numAgentsPerEnv_, w_, h_;
     int renderW_ = 768, renderH_ = 432;
+    const uint8_t *hires_ = nullptr;
     std::vector<int32_t> masks_;
 };
 

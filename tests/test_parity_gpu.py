@@ -509,3 +509,27 @@ def test_hex_memory_trajectory_parity(built, policy):
     assert total > 0.0
     assert g.faults() == 0
     o.close(); g.close()
+
+
+def test_hires_render_matches_oracle(built):
+    """draw_hires (megaverse.cpp:154-177): the same state rendered at 768x432 equals an oracle that renders at 768x432"""
+    import orc
+    from megaverse_b200 import capi
+
+    E, A = 3, 2
+    o = orc.Oracle("ObstaclesHard", E, A, 768, 432)
+    g = capi.Engine("ObstaclesHard", E, A, 128, 72, num_threads=2)
+    g.set_option("fast_shading", 0)
+    o.seed(11); g.seed(11); o.reset(); g.reset()
+    rng = np.random.default_rng(2)
+    for t in range(40):
+        acts = helpers.purposeful_actions(rng, E * A, t)
+        o.step(acts); g.step(acts)
+    hi = np.array(g.draw_hires(768, 432))
+    assert hi.shape == (E * A, 432, 768, 4)
+    assert np.array_equal(hi, o.obs()), "hi-res frame differs: %d pixels" % int((hi != o.obs()).any(axis=-1).sum())
+    lo = np.array(g.obs())  # the training-resolution pass is undisturbed
+    g.step(np.zeros(E * A, dtype=np.int32)); o.step(np.zeros(E * A, dtype=np.int32))
+    assert np.array(g.obs()).shape == lo.shape and g.faults() == 0
+    _assert_same_state(o, g, E, "after hires")
+    o.close(); g.close()
