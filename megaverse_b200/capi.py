@@ -121,6 +121,19 @@ class Engine:
         n = self.N * h * w * 4
         return np.frombuffer((C.c_char * n).from_address(p.value), dtype=np.uint8).reshape(self.N, h, w, 4)
 
+    def device_array(self, what="obs"):
+        """zero-copy handle on an engine-owned device tensor for any consumer of the CUDA array interface
+        (`torch.as_tensor(eng.device_array("obs"), device="cuda")`, CuPy, Numba): "obs" uint8[N,h,w,4], "depth" float32[N,h,w],
+        "rewards" float32[N], "dones" uint8[E].  Valid in the engine stream's order (mv_stream) until mv_close."""
+        shapes = {"obs": ((self.N, self.h, self.w, 4), "|u1"), "depth": ((self.N, self.h, self.w), "<f4"), "rewards": ((self.N,), "<f4"), "dones": ((self.E,), "|u1")}
+        shape, typestr = shapes[what]
+        ptr, stream = self.device_ptr(what), self.stream()
+
+        class _DeviceArray:
+            __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None, "stream": stream or 1}
+
+        return _DeviceArray()
+
     def fetch_obs(self):
         self._ck(lib().mv_fetch_obs(self._h))
 

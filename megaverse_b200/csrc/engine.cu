@@ -604,7 +604,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     // rasteriser scratch: Collect's Perlin landscapes merge into up to ~500 boxes (+ up to 86 reward diamonds)
     const bool hexSc = sc == MV_SCENARIO_HEX_EXPLORE || sc == MV_SCENARIO_HEX_MEMORY;  // hundreds of wall / edging / landmark boxes
-    e->triCap = hexSc ? 8192 : (sc == MV_SCENARIO_COLLECT ? 4096 : (sc == MV_SCENARIO_OBSTACLES ? 2048 : 1024));
+    e->triCap = hexSc ? 8192 : (sc == MV_SCENARIO_COLLECT ? 4096 : ((sc == MV_SCENARIO_OBSTACLES || e->A > 1) ? 2048 : 1024));  // other agents' capsules: 128 triangles each
     e->chunkViews = int(std::min<size_t>(N, hexSc ? 128 : (sc == MV_SCENARIO_COLLECT ? 256 : 512)));
     if (ok && e->allocTriScratch() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&

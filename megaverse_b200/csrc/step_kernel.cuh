@@ -598,7 +598,8 @@ __device__ bool updateTransform(MvAgent &a, M4 &out) {
         else { const float s = 1.0f / sqrtf(s2); axis = v3(t[0] * s, t[1] * s, t[2] * s); }
     }
     const V3 na = mgNormalized(axis);
-    const float rotation = 2.0f * cracos(t[3]);
+    const float wq = t[3] < -1.0f ? -1.0f : (t[3] > 1.0f ? 1.0f : t[3]);  // btAcos clamps (btScalar.h)
+    const float rotation = 2.0f * cracos(wq);
     if (isnan(position.x) || isnan(position.y) || isnan(position.z) || isnan(rotation)) return false;
     if (isnan(na.x) || isnan(na.y) || isnan(na.z)) return false;
     position = position + v3(0, 0.05f, 0.0f);

@@ -113,7 +113,8 @@ inline Quat quatFromMat3(const Mat3 &m) {
     return {t[0], t[1], t[2], t[3]};
 }
 // btQuaternion::getAngle: 2*acos(w);  getAxis: s2 = 1-w*w; if (s2 < 10*eps) (1,0,0) else xyz/sqrt(s2)
-inline float quatAngle(const Quat &q) { return 2.0f * cracos(q.w); }
+// (btAcos clamps its argument to [-1, 1], btScalar.h: a w that rounds above 1 gives angle 0, not NaN)
+inline float quatAngle(const Quat &q) { float w = q.w; if (w < -1.0f) w = -1.0f; if (w > 1.0f) w = 1.0f; return 2.0f * cracos(w); }
 inline Vec3 quatAxis(const Quat &q) {
     float s2 = 1.0f - q.w * q.w;
     if (s2 < 10.0f * 1.1920929e-07f) return {1, 0, 0};

@@ -533,3 +533,23 @@ def test_hires_render_matches_oracle(built):
     assert np.array(g.obs()).shape == lo.shape and g.faults() == 0
     _assert_same_state(o, g, E, "after hires")
     o.close(); g.close()
+
+
+def test_device_tensor_interface(built):
+    """the obs tensor through the CUDA array interface (what a GPU learner consumes): zero-copy, equals the
+    host copy of the same step"""
+    import torch
+    from megaverse_b200 import capi
+
+    g = capi.Engine("Collect", 4, 2, 128, 72, num_threads=2)
+    g.seed(3); g.reset()
+    g.step(np.full(8, 1 << 3, dtype=np.int32))
+    t = torch.as_tensor(g.device_array("obs"), device="cuda")
+    assert t.shape == (8, 72, 128, 4) and t.dtype == torch.uint8 and t.data_ptr() == g.device_ptr("obs")
+    g.set_option("zero_copy", 0)  # make the kernel write HBM and copy down, so both copies exist
+    g.step(np.full(8, 1 << 3, dtype=np.int32))
+    torch.cuda.synchronize()
+    assert np.array_equal(t.cpu().numpy(), np.array(g.obs()))
+    r = torch.as_tensor(g.device_array("rewards"), device="cuda")
+    assert np.array_equal(r.cpu().numpy(), np.array(g.rewards()))
+    g.close()
