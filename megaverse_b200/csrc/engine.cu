@@ -151,6 +151,12 @@ struct mv_engine {
     DevBuf<int32_t> d_tileCounter;
     DevBuf<mvr::TriCover> d_cover;
     DevBuf<mvr::TriShade> d_shade;
+    // host delivery pipeline (mv_step with host buffers, zero_copy off): views are rasterised in slices and each slice goes
+    // down on a second stream (copy engine) while the next one is rasterised
+    cudaStream_t copyStream = nullptr;
+    std::vector<cudaEvent_t> sliceDone;
+    bool pipelineHost = false;   // this launch: slice + copy on the second stream
+    int hostSlices = 1;          // measured on B200: slicing loses (each slice pays the latency-bound kernels' tail); zero-copy is the default
     // hi-res pass (draw_hires): its own scratch, allocated on first use
     struct Hires {
         int W = 0, H = 0, chunk = 0, binCap = 0;
@@ -299,8 +305,11 @@ struct mv_engine {
         const int nTiles = (W / 32) * (H / 4);
         const int maxItems = instCap * 6 + (A + MV_MAX_OBJECTS + decoCap) * 128 + 3 * MV_MAX_REWARD * 80;  // blocks past a view's real item count exit at once
         const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
-        for (int base = 0; base < N; base += chunkViews) {
-            const int cv = std::min(chunkViews, N - base);
+        int sliceViews = chunkViews;
+        if (pipelineHost) sliceViews = std::max(1, std::min(chunkViews, (N + hostSlices - 1) / hostSlices));
+        int sliceIdx = 0;
+        for (int base = 0; base < N; base += sliceViews, ++sliceIdx) {
+            const int cv = std::min(sliceViews, N - base);
             rp.viewBase = base; rp.chunkViews = cv;
             if (overlap && base == 0) {
                 // programmatic dependent launch: the grid may start before the step kernel has drained; its blocks wait
@@ -323,6 +332,14 @@ struct mv_engine {
             else mvr::tileKernel<false><<<tileBlocks, 128, 0, stream>>>(rp);
             MV_CUDA(cudaGetLastError());
             launches += 2;
+            if (pipelineHost) {
+                while (int(sliceDone.size()) <= sliceIdx) { cudaEvent_t e2; MV_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); sliceDone.push_back(e2); }
+                MV_CUDA(cudaEventRecord(sliceDone[size_t(sliceIdx)], stream));
+                MV_CUDA(cudaStreamWaitEvent(copyStream, sliceDone[size_t(sliceIdx)], 0));
+                const size_t px = size_t(W) * H;
+                MV_CUDA(cudaMemcpyAsync(h_obs.p + size_t(base) * px * 4, d_obs.p + size_t(base) * px * 4, size_t(cv) * px * 4, cudaMemcpyDeviceToHost, copyStream));
+                if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, d_depth.p + size_t(base) * px, sizeof(float) * size_t(cv) * px, cudaMemcpyDeviceToHost, copyStream));
+            }
         }
         return MV_OK;
     }
@@ -417,11 +434,12 @@ struct mv_engine {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        if (copyObs && !rasterToHost) {
+        if (copyObs && !rasterToHost && !pipelineHost) {
             MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
         MV_CUDA(cudaStreamSynchronize(stream));
+        if (pipelineHost) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         return MV_OK;
     }
@@ -462,7 +480,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        rasterToHost = false;
+        rasterToHost = false; pipelineHost = false;
         rc = launchStep(dActions, false, &slotP);  // rewards / dones / true objectives land in the ring slot straight from the kernel
         if (rc) return rc;
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
@@ -482,6 +500,7 @@ struct mv_engine {
             rtableDirty = false;
         }
         rasterToHost = copyObs && zeroCopy;
+        pipelineHost = copyObs && !zeroCopy && hostSlices > 1 && copyStream != nullptr;
         rc = launchStep(dActions, false);
         if (rc) return rc;
         rc = finishStep(copyObs);
@@ -499,6 +518,9 @@ struct mv_engine {
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &p : ring) { if (p.ev) { cudaEventDestroy(p.ev); p.ev = nullptr; } p.rewards.free(); p.trueObj.free(); p.dones.free(); }
+        for (auto &e2 : sliceDone) if (e2) cudaEventDestroy(e2);
+        sliceDone.clear();
+        if (copyStream) { cudaStreamDestroy(copyStream); copyStream = nullptr; }
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 };
@@ -592,7 +614,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
 
     auto ck = [&](cudaError_t err, const char *what) { if (err != cudaSuccess) { e->setError(std::string(what) + ": " + cudaGetErrorString(err)); return false; } return true; };
     const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
-    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream");
+    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream") && ck(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking), "copy stream");
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
     ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
@@ -648,6 +670,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
+    if (k == "host_slices") { if (value < 1 || value > 64) return MV_ERR_ARG; h->hostSlices = value; return MV_OK; }
     if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
     if (k == "overlap") { cudaStreamSynchronize(h->stream); h->overlap = value != 0; return MV_OK; }
     h->setError("unknown option " + k);
@@ -707,6 +730,7 @@ int mv_reset(mv_handle h) {
         h->rtableDirty = false;
     }
     h->rasterToHost = h->obsToHost && h->zeroCopy;
+    h->pipelineHost = false;
     rc = h->launchStep(h->d_actions.p, true);
     if (rc) return rc;
     rc = h->finishStep(h->obsToHost);
