@@ -82,6 +82,10 @@ __device__ __forceinline__ ClipVert lerpVert(const ClipVert &a, const ClipVert &
 }
 __device__ __forceinline__ int32_t snapSub(float v) { return int32_t(floorf(v * 256.0f + 0.5f)); }
 
+#ifndef MV_TILE_RUN
+#define MV_TILE_RUN 2
+#endif
+constexpr int kTileRun = MV_TILE_RUN;  // consecutive tiles per queue claim of the tile kernel
 constexpr int kWideTiles = 8;   // more tiles than this: the triangle goes to the view's wide list
 constexpr int kWideCap = 512;
 
@@ -479,14 +483,22 @@ template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) ti
     TriCover *stage = s_stage[threadIdx.x >> 5];
     const int tilesX = P.W / 32, nTiles = tilesX * (P.H / 4);
     const int totalTiles = min(P.chunkViews, P.N - P.viewBase) * nTiles;
+    // Work queue: one global counter claimed in short runs of consecutive tiles (fewer same-address atomics, and neighbouring
+    // tiles share their triangle records in L1); near the end of the queue single tiles keep the tail balanced.  The next
+    // claim is issued while the run's last tile is processed, so its round trip is hidden.
+    const int numWarps = int(gridDim.x) * 4;
+    auto runLength = [&](int at) { return at + 8 * numWarps < totalTiles ? kTileRun : 1; };
+    int run = runLength(0);
     int gw = 0;
-    if (lane == 0) gw = atomicAdd(P.tileCounter, 1);
+    if (lane == 0) gw = atomicAdd(P.tileCounter, run);
     gw = __shfl_sync(0xffffffffu, gw, 0);
+    int gwEnd = gw + run;
     for (;;) {
         if (gw >= totalTiles) return;
-        // claim the next work item now; the atomic's round trip overlaps this tile's work
-        int gwNext = 0;
-        if (lane == 0) gwNext = atomicAdd(P.tileCounter, 1);
+        const bool lastOfRun = gw + 1 >= gwEnd;
+        const int nextRun = runLength(gw);
+        int gwNext = gw + 1;
+        if (lastOfRun && lane == 0) gwNext = atomicAdd(P.tileCounter, nextRun);
         const int vslot = gw / nTiles, tile = gw - vslot * nTiles;
         const int view = P.viewBase + vslot;
         const TriCover *cover = P.cover + size_t(vslot) * P.triCap;
@@ -638,7 +650,8 @@ template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) ti
             uint32_t *tp = P.tileProf + (size_t(view) * nTiles + tile) * 4;
             tp[0] = uint32_t(clock64() - tp0); tp[1] = uint32_t(nOv); tp[2] = uint32_t(nSm); tp[3] = uint32_t(nBg);
         }
-        gw = __shfl_sync(0xffffffffu, gwNext, 0);
+        if (lastOfRun) { gw = __shfl_sync(0xffffffffu, gwNext, 0); gwEnd = gw + nextRun; }
+        else gw = gwNext;
     }
 }
 

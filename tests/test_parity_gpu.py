@@ -553,3 +553,23 @@ def test_device_tensor_interface(built):
     r = torch.as_tensor(g.device_array("rewards"), device="cuda")
     assert np.array_equal(r.cpu().numpy(), np.array(g.rewards()))
     g.close()
+
+
+@pytest.mark.parametrize("scenario,A,w,h", [("Collect", 8, 64, 64), ("Rearrange", 8, 160, 96), ("HexMemory", 8, 64, 64), ("Sokoban", 8, 128, 72)])
+def test_many_agents_other_resolutions(built, scenario, A, w, h):
+    """eight agents per env (the engine's maximum) and non-default render sizes: agent-agent capsule contacts, eight views per env"""
+    E, steps = 3, 160
+    o, g = _pair(scenario, E, A, 13, w=w, h=h)
+    rng = np.random.default_rng(9)
+    _assert_same_state(o, g, E, "reset")
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t)
+        o.step(acts)
+        g.step(acts)
+        assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), "step %d" % t
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d" % t
+    _assert_same_state(o, g, E, "end")
+    assert _assert_same_frame(o, g, "end") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
