@@ -37,5 +37,40 @@ def main():
     print("rewards earned:", float(np.abs(np.array(rewards)).sum()))
 
 
+SCENARIOS = ["ObstaclesHard", "ObstaclesLava", "Collect", "Sokoban", "Rearrange", "HexExplore", "HexMemory"]
+
+
+def scenario_run(name, E=3, A=2, seed=77, steps=200):
+    """level dumps at reset, then a fixed action stream: rewards, dones and the final states"""
+    o = orc.Oracle(name, E, A, render=False)
+    o.seed(seed)
+    o.reset()
+    levels = [o.level(e) for e in range(E)]
+    rng = np.random.default_rng(11)
+    rewards, dones = [], []
+    for t in range(steps):
+        o.step(helpers.purposeful_actions(rng, E * A, t))
+        rewards.append(o.rewards().copy()); dones.append(o.dones().copy())
+    states = [o.state(e) for e in range(E)]
+    o.close()
+    return levels, np.array(rewards), np.array(dones), states
+
+
+def main_scenarios():
+    os.environ.setdefault("BOXOBAN_LEVELS", os.path.join(HERE, "boxoban"))
+    out = {}
+    for name in SCENARIOS:
+        levels, rewards, dones, states = scenario_run(name)
+        for e, lv in enumerate(levels):
+            out["%s_level%d" % (name, e)] = lv
+        out[name + "_rewards"] = rewards
+        out[name + "_dones"] = dones
+        for e, st in enumerate(states):
+            out["%s_state%d" % (name, e)] = st
+    np.savez_compressed(os.path.join(HERE, "scenarios_golden.npz"), **out)
+    print("scenarios:", {n: float(np.abs(out[n + "_rewards"]).sum()) for n in SCENARIOS})
+
+
 if __name__ == "__main__":
     main()
+    main_scenarios()

@@ -2,6 +2,7 @@
 the libstdc++ hash-set order emulation, and the C ABI's exported symbols.  No compute call needs a GPU here."""
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -181,6 +182,26 @@ def test_oracle_golden_trajectory(built):
     assert np.array_equal(o.state(0).view(np.uint32), g["final_state0"].view(np.uint32))
     assert np.array_equal(o.obs()[0], g["last_frame"])
     o.close()
+
+
+def test_oracle_golden_scenarios(built):
+    """every other scenario against tests/golden/scenarios_golden.npz: level dumps at reset, then rewards / dones over a fixed
+    action stream and the final states (bit patterns)"""
+    import helpers
+    import orc
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "scenarios_golden.npz"))
+    for name in make_golden.SCENARIOS:
+        levels, rewards, dones, states = make_golden.scenario_run(name)
+        for e, lv in enumerate(levels):
+            assert np.array_equal(lv, g["%s_level%d" % (name, e)]), "%s level %d" % (name, e)
+        assert np.array_equal(rewards.view(np.uint32), g[name + "_rewards"].view(np.uint32)), name
+        assert np.array_equal(dones, g[name + "_dones"]), name
+        for e, st in enumerate(states):
+            assert np.array_equal(st.view(np.uint32), g["%s_state%d" % (name, e)].view(np.uint32)), "%s state %d" % (name, e)
 
 
 def test_mesh_tables_match_reference_magnum(built):
