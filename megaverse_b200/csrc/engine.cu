@@ -8,6 +8,8 @@
 // serially on the caller thread between the two, vector_env.cpp:94-105): every env always has its NEXT level pre-staged
 // in HBM (no RNG draw happens during an episode, so the next level only depends on the env's RNG state after the
 // previous generation), and the step kernel flips to it by itself when the episode ends.
+#include <cuda.h>
+#include <dlfcn.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -156,6 +158,14 @@ struct mv_engine {
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> sliceDone;
     bool pipelineHost = false;   // this launch: slice + copy on the second stream
+    // progressive download: ONE raster launch, the tile kernel counts finished tiles per slice of views and the copy stream waits
+    // on those counters (cuStreamWaitValue32, cyclic >= on cumulative targets) before each slice's cudaMemcpyAsync
+    typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+    WaitValue32Fn waitValue32 = nullptr;
+    DevBuf<uint32_t> d_sliceDone;
+    uint32_t sliceTarget[32] = {};
+    int progSlices = 8;
+    bool progressive = false, progressiveNow = false;  // measured on B200: no faster than one copy; zero-copy is the default delivery
     int hostSlices = 1;          // measured on B200: slicing loses (each slice pays the latency-bound kernels' tail); zero-copy is the default
     // hi-res pass (draw_hires): its own scratch, allocated on first use
     struct Hires {
@@ -299,6 +309,8 @@ struct mv_engine {
         rp.cover = d_cover.p; rp.shade = d_shade.p; rp.triCounts = d_triCounts.p;
         rp.binCounts = d_binCounts.p; rp.binList = d_binList.p; rp.wideCounts = d_wideCounts.p; rp.wideList = d_wideList.p; rp.binCap = binCap;
         rp.tileProf = d_tileProf.p;
+        const int progViews = std::max(1, (N + progSlices - 1) / progSlices);
+        rp.sliceDone = progressiveNow ? d_sliceDone.p : nullptr; rp.sliceViews = progViews;
         rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0;
         rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
         rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
@@ -341,6 +353,22 @@ struct mv_engine {
                 if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, d_depth.p + size_t(base) * px, sizeof(float) * size_t(cv) * px, cudaMemcpyDeviceToHost, copyStream));
             }
         }
+        if (progressiveNow) {
+            const size_t px = size_t(W) * H;
+            for (int sl = 0, base = 0; base < N; ++sl, base += progViews) {
+                const int cv = std::min(progViews, N - base);
+                sliceTarget[sl] += uint32_t(cv) * uint32_t(nTiles);
+                const CUresult wr = waitValue32(copyStream, CUdeviceptr(reinterpret_cast<uintptr_t>(d_sliceDone.p + sl)), sliceTarget[sl], CU_STREAM_WAIT_VALUE_GEQ);
+                if (wr != CUDA_SUCCESS) {
+                    int memops = -1;
+                    cudaDeviceGetAttribute(&memops, cudaDevAttrMemSyncDomainCount, device);
+                    setError("cuStreamWaitValue32 failed with CUresult " + std::to_string(int(wr)));
+                    return MV_ERR_CUDA;
+                }
+                MV_CUDA(cudaMemcpyAsync(h_obs.p + size_t(base) * px * 4, d_obs.p + size_t(base) * px * 4, size_t(cv) * px * 4, cudaMemcpyDeviceToHost, copyStream));
+                if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, d_depth.p + size_t(base) * px, sizeof(float) * size_t(cv) * px, cudaMemcpyDeviceToHost, copyStream));
+            }
+        }
         return MV_OK;
     }
     // draw_hires (megaverse.cpp:154-177): every agent view once more, at (w, h), from the instance lists and camera matrices of
@@ -374,7 +402,7 @@ struct mv_engine {
         rp.obs = hires.d_obs.p; rp.depth = nullptr; rp.faults = d_faults.p;
         rp.cover = hires.cover.p; rp.shade = hires.shade.p; rp.triCounts = d_triCounts.p;
         rp.binCounts = hires.binCounts.p; rp.binList = hires.binList.p; rp.wideCounts = d_wideCounts.p; rp.wideList = hires.wideList.p; rp.binCap = hires.binCap;
-        rp.tileProf = nullptr; rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.ready = nullptr; rp.readyStamp = 0;
+        rp.tileProf = nullptr; rp.sliceDone = nullptr; rp.sliceViews = 1; rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.ready = nullptr; rp.readyStamp = 0;
         rp.N = N; rp.A = A; rp.W = w; rp.H = hgt; rp.triCap = triCap;
         rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
         const int maxItems = instCap * 6 + (A + MV_MAX_OBJECTS + decoCap) * 128 + 3 * MV_MAX_REWARD * 80;
@@ -434,12 +462,12 @@ struct mv_engine {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        if (copyObs && !rasterToHost && !pipelineHost) {
+        if (copyObs && !rasterToHost && !pipelineHost && !progressiveNow) {
             MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
         MV_CUDA(cudaStreamSynchronize(stream));
-        if (pipelineHost) MV_CUDA(cudaStreamSynchronize(copyStream));
+        if (pipelineHost || progressiveNow) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         return MV_OK;
     }
@@ -480,7 +508,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        rasterToHost = false; pipelineHost = false;
+        rasterToHost = false; pipelineHost = false; progressiveNow = false;
         rc = launchStep(dActions, false, &slotP);  // rewards / dones / true objectives land in the ring slot straight from the kernel
         if (rc) return rc;
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
@@ -501,6 +529,7 @@ struct mv_engine {
         }
         rasterToHost = copyObs && zeroCopy;
         pipelineHost = copyObs && !zeroCopy && hostSlices > 1 && copyStream != nullptr;
+        progressiveNow = copyObs && !zeroCopy && !pipelineHost && progressive && waitValue32 != nullptr && N >= 2 * progSlices;
         rc = launchStep(dActions, false);
         if (rc) return rc;
         rc = finishStep(copyObs);
@@ -513,7 +542,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
+        d_sliceDone.free(); hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -616,12 +645,17 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
     bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream") && ck(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking), "copy stream");
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
+    {   // stream memory operations come from the driver API: resolved at run time from the already loaded libcuda (no link-time
+        // dependency, the library must also load on machines without a driver); _v2 is the CUDA 12 ABI, v1 is disabled here
+        if (void *drv = dlopen("libcuda.so.1", RTLD_LAZY | RTLD_LOCAL))
+            e->waitValue32 = reinterpret_cast<mv_engine::WaitValue32Fn>(dlsym(drv, "cuStreamWaitValue32_v2"));
+    }
     ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
          ck(e->d_inst.alloc(E * size_t(e->instCap)), "instances") && ck(e->d_deco.alloc(E * 2 * size_t(e->decoCap)), "deco") && ck(e->h_deco.alloc(E * 2 * size_t(e->decoCap)), "h_deco") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
-         ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_wideCounts.alloc(N), "wideCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter") && ck(e->d_ready.alloc(E), "ready") &&
+         ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_wideCounts.alloc(N), "wideCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter") && ck(e->d_sliceDone.alloc(32), "sliceDone") && ck(cudaMemset(e->d_sliceDone.p, 0, 128), "sliceDone") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     // rasteriser scratch: Collect's Perlin landscapes merge into up to ~500 boxes (+ up to 86 reward diamonds)
@@ -670,6 +704,8 @@ int mv_set_option(mv_handle h, const char *key, int value) {
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
+    if (k == "progressive") { h->progressive = value != 0; return MV_OK; }
+    if (k == "progressive_slices") { if (value < 1 || value > 32) return MV_ERR_ARG; cudaDeviceSynchronize(); h->progSlices = value; cudaMemset(h->d_sliceDone.p, 0, 128); std::memset(h->sliceTarget, 0, sizeof h->sliceTarget); return MV_OK; }
     if (k == "host_slices") { if (value < 1 || value > 64) return MV_ERR_ARG; h->hostSlices = value; return MV_OK; }
     if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
     if (k == "overlap") { cudaStreamSynchronize(h->stream); h->overlap = value != 0; return MV_OK; }
@@ -730,7 +766,7 @@ int mv_reset(mv_handle h) {
         h->rtableDirty = false;
     }
     h->rasterToHost = h->obsToHost && h->zeroCopy;
-    h->pipelineHost = false;
+    h->pipelineHost = false; h->progressiveNow = false;
     rc = h->launchStep(h->d_actions.p, true);
     if (rc) return rc;
     rc = h->finishStep(h->obsToHost);
@@ -1088,6 +1124,7 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
         cudaMemset(dBinCounts, 0, sizeof(int32_t) * tilesV);
         mvr::RasterParams rp;
         rp.binCounts = dBinCounts; rp.binList = dBinList; rp.wideCounts = dWideCount; rp.wideList = dWideList; rp.binCap = binCap; rp.tileProf = nullptr;
+        rp.sliceDone = nullptr; rp.sliceViews = 1;
         rp.ready = nullptr; rp.readyStamp = 0;
         rp.instances = dInst; rp.instCounts = dCnt; rp.views = dView; rp.instStride = int(inst.size()); rp.obs = dObs; rp.depth = depth ? dDepth : nullptr;
         rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.viewBase = 0; rp.chunkViews = 1;

@@ -63,6 +63,8 @@ struct RasterParams {
     int32_t *tileCounter;        // dynamic tile queue of the persistent tile warps (reset by geomKernel)
     const uint32_t *ready;       // [E] step-kernel completion stamps (nullptr: plain stream order)
     uint32_t readyStamp;         // value ready[env] holds once this step's state, instances and views of env are written
+    uint32_t *sliceDone;         // optional [slices] cumulative count of finished tiles per slice of sliceViews views: lets a copy
+    int sliceViews;              //   stream (cuStreamWaitValue32) download finished slices while later views are still rasterised
     uint32_t *tileProf;          // optional [views][tiles][4] {cycles, triangles overlapping, small-path lanes, big-path triangles} (debug)
     int fastShading;             // 1: approximate rsqrt / fused multiply-add in the fragment stage (+-1 LSB), 0: bit-exact
     int viewBase, chunkViews;
@@ -646,6 +648,11 @@ template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) ti
         *reinterpret_cast<uint4 *>(obsView + (size_t(py) * P.W + px) * 4) = out;
         if (P.depth) *reinterpret_cast<float4 *>(P.depth + size_t(view) * P.W * P.H + size_t(py) * P.W + px) = make_float4(wv[0], wv[1], wv[2], wv[3]);
         __syncwarp();
+        if (P.sliceDone) {  // publish this tile's pixels, then count it
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(P.sliceDone + view / P.sliceViews, 1u);
+        }
         if (P.tileProf && lane == 0) {
             uint32_t *tp = P.tileProf + (size_t(view) * nTiles + tile) * 4;
             tp[0] = uint32_t(clock64() - tp0); tp[1] = uint32_t(nOv); tp[2] = uint32_t(nSm); tp[3] = uint32_t(nBg);

@@ -13,8 +13,11 @@ for e in range(E):
 g.reset()
 rng = np.random.default_rng(1)
 acts = (1 << rng.integers(0, 11, size=(600, E))).astype(np.int32)
-for name, opts in [("zero_copy", {"zero_copy": 1}), ("slices=1 (one big copy)", {"zero_copy": 0, "host_slices": 1}), ("slices=2", {"zero_copy": 0, "host_slices": 2}),
-                   ("slices=4", {"zero_copy": 0, "host_slices": 4}), ("slices=8", {"zero_copy": 0, "host_slices": 8})]:
+for name, opts in [("zero_copy", {"zero_copy": 1}), ("one big copy", {"zero_copy": 0, "progressive": 0, "host_slices": 1}),
+                   ("progressive, 4 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 4}),
+                   ("progressive, 8 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 8}),
+                   ("progressive, 16 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 16}),
+                   ("progressive, 32 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 32})]:
     for k, v in opts.items():
         g.set_option(k, v)
     for t in range(50):
@@ -23,5 +26,5 @@ for name, opts in [("zero_copy", {"zero_copy": 1}), ("slices=1 (one big copy)", 
     for t in range(50, 550):
         g.step(acts[t])
     dt = (time.perf_counter() - t0) / 500
-    print("%-26s %.1f us/step = %.2fM obs/s" % (name, dt * 1e6, E / dt / 1e6))
+    print("%-26s %.1f us/step = %.2fM obs/s (faults %d)" % (name, dt * 1e6, E / dt / 1e6, g.faults()))
 g.close()
