@@ -518,12 +518,14 @@ template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) ti
         const int sx32 = px * 256 + 128, sy32 = py * 256 + 128;
         unsigned long long best[4] = {0ull, 0ull, 0ull, 0ull};
         const long long tp0 = P.tileProf ? clock64() : 0;
+        long long tpA = 0, tpB = 0;
         int nOv = 0, nSm = 0, nBg = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) frag[lane * 4 + k] = 0ull;
         __syncwarp();
         if (lane == 0 && nBin) *binCount = 0;  // leave the bin empty for the next geometry pass
 
+        if (P.tileProf) tpA = clock64() + (total < 0 ? 1 : 0);  // (after the counts have arrived: total is consumed)
         for (int base = 0; base < total; base += 32) {
             const int j = base + lane;
             // which triangle is mine, and does its box touch this tile (bin entries always do; wide entries are checked)
@@ -618,6 +620,7 @@ template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) ti
             __syncwarp();  // the stage is rewritten by the next chunk
         }
         __syncwarp();
+        if (P.tileProf) tpB = clock64();
         // ---- merge both paths, recompute the winner's barycentrics, shade, store
         uint4 out;
         float wv[4];
@@ -655,7 +658,7 @@ template <bool FAST> __global__ void __launch_bounds__(128, kTileBlocksPerSM) ti
         }
         if (P.tileProf && lane == 0) {
             uint32_t *tp = P.tileProf + (size_t(view) * nTiles + tile) * 4;
-            tp[0] = uint32_t(clock64() - tp0); tp[1] = uint32_t(nOv); tp[2] = uint32_t(nSm); tp[3] = uint32_t(nBg);
+            tp[0] = uint32_t(clock64() - tp0); tp[1] = uint32_t(nOv) | (uint32_t(tpA - tp0) << 12); tp[2] = uint32_t(nSm) | (uint32_t(tpB - tpA) << 12); tp[3] = uint32_t(nBg);
         }
         if (lastOfRun) { gw = __shfl_sync(0xffffffffu, gwNext, 0); gwEnd = gw + nextRun; }
         else gw = gwNext;

@@ -19,7 +19,10 @@ for t in range(200):
 g.tile_profile(True, False)
 g.step((1 << rng.integers(0, 11, size=E * A)).astype(np.int32))
 p = g.tile_profile(True, True).astype(np.int64)
-cyc, nov, nsm, nbg = p[..., 0].ravel(), p[..., 1].ravel(), p[..., 2].ravel(), p[..., 3].ravel()
+cyc, nov, nsm, nbg = p[..., 0].ravel(), (p[..., 1] & 0xfff).ravel(), (p[..., 2] & 0xfff).ravel(), p[..., 3].ravel()
+tA, tB = (p[..., 1] >> 12).ravel(), (p[..., 2] >> 12).ravel()
+print("phases (cycles, mean / p50): set-up %.0f / %.0f; lists + coverage + depth %.0f / %.0f; resolve+shade+store %.0f / %.0f" % (
+    tA.mean(), np.median(tA), tB.mean(), np.median(tB), (cyc - tA - tB).mean(), np.median(cyc - tA - tB)))
 print("%s E=%d A=%d kernel ms %s" % (scenario, E, A, g.last_kernel_ms()))
 print("tiles %d; cycles/tile mean %.0f p50 %.0f p90 %.0f p99 %.0f max %d; sum %.1f Mcycles" % (cyc.size, cyc.mean(), np.median(cyc), np.percentile(cyc, 90), np.percentile(cyc, 99), cyc.max(), cyc.sum() / 1e6))
 print("overlapping tris/tile mean %.1f p90 %.0f max %d; small mean %.1f; big mean %.1f max %d" % (nov.mean(), np.percentile(nov, 90), nov.max(), nsm.mean(), nbg.mean(), nbg.max()))
