@@ -236,7 +236,10 @@ __device__ __forceinline__ ClipVert makeVert(const M4 &mv, const float nm[9], V3
 
 // ---------------------------------------------------------------------------------------------------- geometry kernel
 // grid = (ceil(maxItems / blockDim.x), chunkViews); blockIdx.y selects the view
-__global__ void __launch_bounds__(128) geomKernel(RasterParams P) {
+#ifndef MV_GEOM_BLOCKS
+#define MV_GEOM_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P) {
     const int vslot = blockIdx.y;
     const int view = P.viewBase + vslot;
     if (view >= P.N) return;
