@@ -133,6 +133,8 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
 /* per-tile cost of the tile kernel: out = uint32[N][tiles][4] {cycles, overlapping triangles, lane-per-triangle count, warp-per-triangle count} */
 int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable);
+/* host-only: colour tables of the generators + the rasteriser's palette (tests pin them against the reference's env/const.hpp) */
+int mv_debug_color_tables(uint32_t *out, int cap);
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);
 
 #ifdef __cplusplus

@@ -820,6 +820,19 @@ int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable) {
     return MV_OK;
 }
 
+// host-only: the colour tables of the level generators followed by the rasteriser's palette (float bit patterns), in the layout of
+// the oracle's / reference shim's *_color_tables
+int mv_debug_color_tables(uint32_t *out, int cap) {
+    std::vector<uint32_t> o = mv::colorTables();
+    for (int i = 0; i < 22; ++i)
+        for (float f : {float((kPaletteRgb[i] >> 16) & 255) / 255.0f, float((kPaletteRgb[i] >> 8) & 255) / 255.0f, float(kPaletteRgb[i] & 255) / 255.0f}) {
+            uint32_t u; std::memcpy(&u, &f, 4); o.push_back(u);
+        }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
+
 int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }

@@ -256,6 +256,16 @@ int rewardSlot(int scenario, const std::string &key) {
     return -1;
 }
 
+std::vector<uint32_t> colorTables() {
+    static const uint32_t agent[7] = {C_YELLOW, C_GREEN, C_BLUE, C_ORANGE, C_VIOLET, C_VERY_DARK_GREY, C_RED};  // const.hpp:85, the step kernel's agentColors
+    std::vector<uint32_t> o{22u, 7u, 14u, 14u};
+    o.insert(o.end(), kPalette, kPalette + 22);
+    o.insert(o.end(), agent, agent + 7);
+    o.insert(o.end(), kObjectColors, kObjectColors + 14);
+    o.insert(o.end(), kLayoutColors, kLayoutColors + 14);
+    return o;
+}
+
 int decoCapacity(int scenario) {
     switch (scenario) {
         case MV_SCENARIO_REARRANGE: return MV_MAX_ARRANGEMENT;

@@ -60,6 +60,8 @@ int scenarioFromName(const std::string &name);  // -1 if unknown
 FloatParams defaultFloatParams(const std::string &scenarioName);
 // default reward shaping of the (registered) scenario name
 std::vector<std::pair<std::string, float>> defaultRewardShaping(const std::string &scenarioName);
+// colour tables as the generators use them: [n all, n agent, n object, n layout], then the 0xRRGGBB values in that order (test pin)
+std::vector<uint32_t> colorTables();
 int gridCapacity(int scenario);
 int decoCapacity(int scenario);  // most decorations a level of the scenario can hold  // dense voxel grid capacity in cells
 int rewardSlot(int scenario, const std::string &key);  // -1 if unknown

@@ -243,6 +243,26 @@ int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
     return int(o.size());
 }
 
+// colour tables of the restatement, same layout as ref_color_tables (oracle/ref_shim/ref_shim.cpp)
+int orc_color_tables(unsigned *out, int cap) {
+    std::vector<unsigned> o{unsigned(numColors), unsigned(numAgentColors), unsigned(numObjectColors), unsigned(numLayoutColors)};
+    for (int i = 0; i < numColors; ++i) o.push_back(unsigned(allColors[i]));
+    for (int i = 0; i < numAgentColors; ++i) o.push_back(unsigned(agentColors[i]));
+    for (int i = 0; i < numObjectColors; ++i) o.push_back(unsigned(objectColors[i]));
+    for (int i = 0; i < numLayoutColors; ++i) o.push_back(unsigned(layoutColors[i]));
+    for (int i = 0; i < numColors; ++i) {
+        const unsigned c = unsigned(allColors[i]);
+        for (float f : {float((c >> 16) & 255) / 255.0f, float((c >> 8) & 255) / 255.0f, float(c & 255) / 255.0f}) { unsigned u; std::memcpy(&u, &f, 4); o.push_back(u); }
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
+// the Perlin restatement (orc_level.hpp), same call as ref_perlin
+void orc_perlin(unsigned seed, int n, const double *xy, int octaves, double *out) {
+    const PerlinNoise perlin(seed);
+    for (int i = 0; i < n; ++i) out[i] = perlin.accumulatedOctaveNoise2D_0_1(xy[2 * i], xy[2 * i + 1], octaves);
+}
 // the honeycomb maze restatement, same layout as ref_honeycomb_maze (oracle/ref_shim/ref_shim.cpp)
 int orc_honeycomb_maze(int size, unsigned seed, double *out, int cap) {
     HoneyCombMaze maze(size);

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <vector>
 
+#include <env/const.hpp>           // src/libs/env/include/env/const.hpp: ColorRgb, colour tables, rgb()
+#include <util/perlin_noise.hpp>   // src/libs/util/include/util/perlin_noise.hpp (siv::PerlinNoise as vendored by the reference)
 #include <mazes/honeycombmaze.h>  // src/libs/mazes
 #include <mazes/kruskal.h>
 #include <random>
@@ -63,6 +65,28 @@ int ref_voxel_grid_order(const int *xyz, int n, int *out_xyz) {
     return k;
 }
 
+// the reference's colour tables (env/const.hpp:25-143): [n all, n agent, n object, n layout] then the 0xRRGGBB values in that order,
+// then rgb(allColors[i]) as 3 floats each (bit patterns), i.e. what the renderer multiplies with
+int ref_color_tables(unsigned *out, int cap) {
+    using namespace Megaverse;
+    std::vector<unsigned> o{unsigned(numColors), unsigned(numAgentColors), unsigned(numObjectColors), unsigned(numLayoutColors)};
+    for (int i = 0; i < numColors; ++i) o.push_back(unsigned(allColors[i]));
+    for (int i = 0; i < numAgentColors; ++i) o.push_back(unsigned(agentColors[i]));
+    for (int i = 0; i < numObjectColors; ++i) o.push_back(unsigned(objectColors[i]));
+    for (int i = 0; i < numLayoutColors; ++i) o.push_back(unsigned(layoutColors[i]));
+    for (int i = 0; i < numColors; ++i) {
+        const Magnum::Color3 c = rgb(allColors[i]);
+        for (float f : {c.r(), c.g(), c.b()}) { unsigned u; std::memcpy(&u, &f, 4); o.push_back(u); }
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
+// the reference's Perlin noise (scenario_collect.cpp:57-75 uses accumulatedOctaveNoise2D_0_1 on a PerlinNoise(seed))
+void ref_perlin(unsigned seed, int n, const double *xy, int octaves, double *out) {
+    const siv::PerlinNoise perlin(seed);
+    for (int i = 0; i < n; ++i) out[i] = perlin.accumulatedOctaveNoise2D_0_1(xy[2 * i], xy[2 * i + 1], octaves);
+}
 // the reference's honeycomb maze (src/libs/mazes) with the Kruskal generator seeded explicitly (upstream: random_device).
 // out: [vertices, then per cell: centre x, centre y, number of adjacency entries, then per entry: neighbour, x1, y1, x2, y2],
 // followed by the four coordinate bounds

@@ -142,3 +142,50 @@ def test_honeycomb_maze_matches_reference_library(libs, size):
         nb = L.orc_honeycomb_maze(size, seed, b.ctypes.data, b.size)
         assert na == nb and na > 0
         assert np.array_equal(a[:na].view(np.uint64), b[:nb].view(np.uint64))
+
+
+def test_perlin_noise_matches_reference_header(libs):
+    """Collect's landscape noise: the restated PerlinNoise against the reference's own header, bit for bit, over the argument range the
+    scenario uses (x / fx, z / fz with frequencies 0.1 .. 9.9, 1 .. 9 octaves, seeds below 1e9)"""
+    ref, L = libs
+    if not hasattr(ref, "ref_perlin"):
+        pytest.skip("oracle/_ref/libmvref.so predates the perlin shim")
+    rng = np.random.default_rng(5)
+    for fn in (ref.ref_perlin, L.orc_perlin):
+        fn.argtypes = [C.c_uint, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        fn.restype = None
+    for seed in (0, 1, 123456789, 999999999):
+        for octaves in (1, 3, 9):
+            xy = np.ascontiguousarray(rng.uniform(0, 42, size=(500, 2)) / rng.uniform(0.4, 420, size=(500, 1)))
+            a = np.zeros(500); b = np.zeros(500)
+            ref.ref_perlin(seed, 500, xy.ctypes.data, octaves, a.ctypes.data)
+            L.orc_perlin(seed, 500, xy.ctypes.data, octaves, b.ctypes.data)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (seed, octaves)
+
+
+def test_color_tables_match_reference(libs):
+    """env/const.hpp's colour tables (all / agent / object / layout colours) and rgb(): the oracle's and the product's copies
+    against the reference header, incl. the float palette the rasteriser multiplies with (bit patterns)"""
+    from megaverse_b200 import capi
+
+    ref, L = libs
+    if not hasattr(ref, "ref_color_tables"):
+        pytest.skip("oracle/_ref/libmvref.so predates the colour shim")
+    P = capi.lib()
+    outs = []
+    for fn in (ref.ref_color_tables, L.orc_color_tables, P.mv_debug_color_tables):
+        fn.argtypes = [C.c_void_p, C.c_int]
+        fn.restype = C.c_int
+        buf = np.zeros(512, dtype=np.uint32)
+        n = fn(buf.ctypes.data, buf.size)
+        assert n > 0
+        outs.append(buf[:n].copy())
+    assert np.array_equal(outs[0], outs[1]), "oracle colour tables differ from the reference's"
+    assert np.array_equal(outs[0], outs[2]), "product colour tables differ from the reference's"
+    # the step kernel's agent colours are palette indices into allColors
+    import re
+    src = open(os.path.join(ROOT, "megaverse_b200", "csrc", "step_kernel.cuh")).read()
+    idx = [int(x) for x in re.search(r"agentColors\[7\] = \{([0-9, ]+)\}", src).group(1).split(",")]
+    n_all = int(outs[0][0])
+    all_colors, agent_colors = outs[0][4:4 + n_all], outs[0][4 + n_all:4 + n_all + 7]
+    assert [int(all_colors[i]) for i in idx] == [int(c) for c in agent_colors]
