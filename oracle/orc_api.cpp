@@ -243,6 +243,20 @@ int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
     return int(o.size());
 }
 
+// the scene-graph conventions the restatement uses (see ref_scenegraph_case in oracle/ref_shim/ref_shim.cpp for the scenario code it mirrors)
+void orc_scenegraph_case(const float *ps, float angle, const float *pt, const float *cs, const float *ct, const float *fs, const float *ft,
+                         const float *rs, const float *rt, float *out48) {
+    const Mat4 parentLocal = mul(mat4Translation({pt[0], pt[1], pt[2]}), mul(mat4RotationY(angle), mul(mat4Scaling({ps[0], ps[1], ps[2]}), mat4Identity())));
+    const Mat4 childLocal = mul(mat4Translation({ct[0], ct[1], ct[2]}), mul(mat4Identity(), mat4Scaling({cs[0], cs[1], cs[2]})));
+    const Mat4 childAbs = mul(parentLocal, childLocal);
+    std::memcpy(out48, &childAbs.c[0][0], 64);
+    std::memcpy(out48 + 16, &childAbs.c[0][0], 64);
+    const Mat4 root = mul(mat4Translation({rt[0], rt[1], rt[2]}), mul(mat4Scaling({rs[0], rs[1], rs[2]}), mat4Identity()));
+    const Mat4 freeAbs = mul(mat4Translation({ft[0], ft[1], ft[2]}), mul(mat4Scaling({fs[0], fs[1], fs[2]}), mat4Identity()));
+    const Mat4 local = mul(inverted(root), freeAbs);  // setParentKeepTransformation
+    const Mat4 abs = mul(root, local);
+    std::memcpy(out48 + 32, &abs.c[0][0], 64);
+}
 // colour tables of the restatement, same layout as ref_color_tables (oracle/ref_shim/ref_shim.cpp)
 int orc_color_tables(unsigned *out, int cap) {
     std::vector<unsigned> o{unsigned(numColors), unsigned(numAgentColors), unsigned(numObjectColors), unsigned(numLayoutColors)};

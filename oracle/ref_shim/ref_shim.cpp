@@ -18,6 +18,9 @@
 #include <Magnum/Math/Vector3.h>
 #include <Magnum/Primitives/Cube.h>
 #include <Magnum/Trade/MeshData.h>
+#include <Magnum/SceneGraph/MatrixTransformation3D.h>
+#include <Magnum/SceneGraph/Object.h>
+#include <Magnum/SceneGraph/Scene.h>
 
 #include <util/util.hpp>        // src/libs/util/include/util/util.hpp: Rng, randRange, frand
 #include <util/voxel_grid.hpp>  // src/libs/util/include/util/voxel_grid.hpp: VoxelCoords hash, toVoxel, VoxelGrid
@@ -65,6 +68,33 @@ int ref_voxel_grid_order(const int *xyz, int n, int *out_xyz) {
     return k;
 }
 
+// Magnum SceneGraph, the way the reference's scenarios use it (Object3D = Object<MatrixTransformation3D>, util/magnum.hpp):
+//   parent:  scale(ps).rotateY(angle).translate(pt)                 (component_hexagonal_maze.cpp:117)
+//   child of parent:  scaleLocal(cs).translate(ct)                   (:110)
+//   free object:  scale(fs).translate(ft), then setParentKeepTransformation(parent-like root = scale(rs).translate(rt))  (layout_utils.cpp:100-112)
+// out: 3 x 16 floats: child's absoluteTransformationMatrix(), the same after SceneGraph::Object::setClean (the renderer's path,
+// v4r_env_renderer.cpp:319-335), and the re-parented object's absoluteTransformationMatrix()
+void ref_scenegraph_case(const float *ps, float angle, const float *pt, const float *cs, const float *ct, const float *fs, const float *ft,
+                         const float *rs, const float *rt, float *out48) {
+    using Object3D = SceneGraph::Object<SceneGraph::MatrixTransformation3D>;
+    using Scene3D = SceneGraph::Scene<SceneGraph::MatrixTransformation3D>;
+    Scene3D scene;
+    auto &parent = scene.addChild<Object3D>();
+    auto &child = parent.addChild<Object3D>();
+    child.scaleLocal({cs[0], cs[1], cs[2]}).translate({ct[0], ct[1], ct[2]});
+    parent.scale({ps[0], ps[1], ps[2]}).rotateY(Rad(angle)).translate({pt[0], pt[1], pt[2]});
+    store(child.absoluteTransformationMatrix(), out48);
+    scene.setClean();
+    std::vector<std::reference_wrapper<Object3D>> objs{child};
+    Object3D::setClean(objs);
+    store(child.absoluteTransformationMatrix(), out48 + 16);
+    auto &root = scene.addChild<Object3D>();
+    root.scale({rs[0], rs[1], rs[2]}).translate({rt[0], rt[1], rt[2]});
+    auto &free = scene.addChild<Object3D>();
+    free.scale({fs[0], fs[1], fs[2]}).translate({ft[0], ft[1], ft[2]});
+    free.setParentKeepTransformation(&root);
+    store(free.absoluteTransformationMatrix(), out48 + 32);
+}
 // the reference's colour tables (env/const.hpp:25-143): [n all, n agent, n object, n layout] then the 0xRRGGBB values in that order,
 // then rgb(allColors[i]) as 3 floats each (bit patterns), i.e. what the renderer multiplies with
 int ref_color_tables(unsigned *out, int cap) {

@@ -189,3 +189,33 @@ def test_color_tables_match_reference(libs):
     n_all = int(outs[0][0])
     all_colors, agent_colors = outs[0][4:4 + n_all], outs[0][4 + n_all:4 + n_all + 7]
     assert [int(all_colors[i]) for i in idx] == [int(c) for c in agent_colors]
+
+
+def test_scene_graph_conventions_match_magnum(libs):
+    """what the restatement assumes about Magnum's SceneGraph, against the real one: scale / rotateY / translate prepend, scaleLocal
+    appends, a child's absolute matrix = parent * local (also through Object::setClean, the renderer's path), and
+    setParentKeepTransformation = inverse(parent abs) * abs.  Bit-exact without rotation; with a rotation the sin/cos values differ
+    by at most 1 ulp (the transcendentals note in DESIGN.md), so that case is compared with a tolerance."""
+    ref, L = libs
+    if not hasattr(ref, "ref_scenegraph_case"):
+        pytest.skip("oracle/_ref/libmvref.so predates the scene-graph shim")
+    fp = C.c_void_p
+    for fn in (ref.ref_scenegraph_case, L.orc_scenegraph_case):
+        fn.argtypes = [fp, C.c_float, fp, fp, fp, fp, fp, fp, fp, fp]
+        fn.restype = None
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        v = [_f(rng.uniform(0.1, 3.0, 3)) for _ in range(8)]
+        v[1] = _f(rng.uniform(-20, 20, 3)); v[3] = _f(rng.uniform(-1, 1, 3)); v[5] = _f(rng.uniform(-20, 20, 3)); v[7] = _f(rng.uniform(-20, 20, 3))
+        ps, pt, cs, ct, fs, ft, rs, rt = v
+        for angle, exact in ((0.0, True), (float(rng.uniform(-3.1, 3.1)), False)):
+            a = np.zeros(48, dtype=np.float32); b = np.zeros(48, dtype=np.float32)
+            args = lambda out: (ps.ctypes.data, C.c_float(angle), pt.ctypes.data, cs.ctypes.data, ct.ctypes.data, fs.ctypes.data, ft.ctypes.data,
+                                rs.ctypes.data, rt.ctypes.data, out.ctypes.data)
+            ref.ref_scenegraph_case(*args(a)); L.orc_scenegraph_case(*args(b))
+            assert np.array_equal(a[:16].view(np.uint32), a[16:32].view(np.uint32)), "setClean changes the absolute matrix"
+            if exact:
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), trial
+            else:
+                assert np.allclose(a, b, rtol=2e-6, atol=2e-6), trial
+                assert np.array_equal(a[32:].view(np.uint32), b[32:].view(np.uint32)), trial  # the re-parented object has no rotation
