@@ -243,6 +243,106 @@ int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
     return int(o.size());
 }
 
+// the restated layout pipeline, same case and layout as ref_voxel_layout_case (oracle/ref_shim/ref_shim.cpp)
+int orc_voxel_layout_case(int type, unsigned seed, int rotate, int drawWalls, const float *params9, int32_t *out, int cap) {
+    FloatParams fp{{"obstaclesMinGap", params9[0]}, {"obstaclesMaxGap", params9[1]}, {"obstaclesMinLava", params9[2]}, {"obstaclesMaxLava", params9[3]},
+                   {"obstaclesMinHeight", params9[4]}, {"obstaclesMaxHeight", params9[5]}, {"verticalLookLimitRad", params9[6]}, {"episodeLengthSec", params9[7]},
+                   {"obstaclesNumAllowedMaxDifficulty", params9[8]}};
+    Rng rng(seed);
+    auto levelRoot = std::make_unique<Node>();
+    StartPlatform start(levelRoot.get(), rng, fp);
+    start.init(); start.generate();
+    std::unique_ptr<Platform> p;
+    const int walls = 4 | 8, w = rotate ? -1 : start.width;
+    switch (type) {
+        case 1: p = std::make_unique<WallPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        case 2: p = std::make_unique<LavaPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        case 3: p = std::make_unique<StepPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        case 4: p = std::make_unique<GapPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        default: p = std::make_unique<ExitPlatform>(start.nextPlatformAnchor, rng, fp, w); break;
+    }
+    p->init();
+    if (rotate == 1) p->rotateCCW(start.width); else if (rotate == 2) p->rotateCW(start.width);
+    p->generate();
+    VoxelGridComponent vg(100, 0, 0, 0, 1);
+    vg.addPlatform(start, LAYOUT_DEFAULT, DARK_GREY, bool(drawWalls));
+    vg.addPlatform(*p, VERY_LIGHT_BLUE, GREY, bool(drawWalls));
+    const auto byType = vg.toBoundingBoxes();
+#define BX(v) (v).x
+#define BY(v) (v).y
+#define BZ(v) (v).z
+
+    std::vector<int32_t> o;
+    o.push_back(int(byType.size()));
+    for (auto &kv : byType) {
+        o.push_back(int(kv.first.type)); o.push_back(int(kv.first.color)); o.push_back(int(kv.second.size()));
+        for (auto &b : kv.second) for (int v : {BX(b.min), BY(b.min), BZ(b.min), BX(b.max), BY(b.max), BZ(b.max)}) o.push_back(v);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+
+#undef BX
+#undef BY
+#undef BZ
+}
+// the restated platforms (orc_level.hpp), same case and layout as ref_platform_case (oracle/ref_shim/ref_shim.cpp)
+int orc_platform_case(int type, unsigned seed, int walls, int w, int l, int rotate, int prevWidth, const float *params9, int nObjects, int nAgents, int32_t *out, int cap) {
+    FloatParams fp{{"obstaclesMinGap", params9[0]}, {"obstaclesMaxGap", params9[1]}, {"obstaclesMinLava", params9[2]}, {"obstaclesMaxLava", params9[3]},
+                   {"obstaclesMinHeight", params9[4]}, {"obstaclesMaxHeight", params9[5]}, {"verticalLookLimitRad", params9[6]}, {"episodeLengthSec", params9[7]},
+                   {"obstaclesNumAllowedMaxDifficulty", params9[8]}};
+    Rng rng(seed);
+    auto sceneRoot = std::make_unique<Node>();
+    auto anchorOwner = std::make_unique<Node>();
+    Node *anchor = anchorOwner.get();
+    anchor->parent = sceneRoot.get();
+    anchor->local = mul(mat4Translation({3, 1, 2}), anchor->local);
+    std::unique_ptr<Platform> p;
+    switch (type) {
+        case 0: p = std::make_unique<EmptyPlatform>(anchor, rng, walls, fp, w); break;
+        case 1: p = std::make_unique<WallPlatform>(anchor, rng, walls, fp, w); break;
+        case 2: p = std::make_unique<LavaPlatform>(anchor, rng, walls, fp, w); break;
+        case 3: p = std::make_unique<StepPlatform>(anchor, rng, walls, fp, w); break;
+        case 4: p = std::make_unique<GapPlatform>(anchor, rng, walls, fp, w); break;
+        case 5: p = std::make_unique<StartPlatform>(anchor, rng, fp, w); break;
+        case 6: p = std::make_unique<ExitPlatform>(anchor, rng, fp, w); break;
+        default: p = std::make_unique<TransitionPlatform>(anchor, rng, walls, fp, l, w); break;
+    }
+    p->init();
+    if (rotate == 1) p->rotateCCW(prevWidth); else if (rotate == 2) p->rotateCW(prevWidth);
+    p->generate();
+#define BX(v) (v).x
+#define BY(v) (v).y
+#define BZ(v) (v).z
+
+    std::vector<int32_t> o;
+    auto pushBox = [&](const BoundingBox &b) { for (int v : {BX(b.min), BY(b.min), BZ(b.min), BX(b.max), BY(b.max), BZ(b.max)}) o.push_back(v); };
+    for (int v : {p->length, p->height, p->width, int(p->isMaxDifficulty()), p->requiresMovableBoxesToTraverse()}) o.push_back(v);
+    o.push_back(int(p->layoutBoxes.size()));
+    for (auto &b : p->layoutBoxes) pushBox(b.boundingBox());
+    o.push_back(int(p->wallBoxes.size()));
+    for (auto &b : p->wallBoxes) pushBox(b.boundingBox());
+    o.push_back(int(p->terrainBoxes.size()));
+    for (auto &kv : p->terrainBoxes) { o.push_back(int(kv.first)); o.push_back(int(kv.second.size())); for (auto &b : kv.second) pushBox(b.boundingBox()); }
+    pushBox(p->platformBoundingBox());
+
+    const auto objs = p->generateObjectPositions(nObjects);
+    o.push_back(int(objs.size()));
+    for (auto &c : objs) for (int v : {int(c.x), int(c.y), int(c.z)}) o.push_back(v);
+    const auto spawns = p->agentSpawnPoints(nAgents);
+    o.push_back(int(spawns.size()));
+    for (auto &c : spawns) for (float f : {c.x, c.y, c.z}) { int32_t u; std::memcpy(&u, &f, 4); o.push_back(u); }
+    if (p->nextPlatformAnchor) {
+        const Vec3 t = translationOf(p->nextPlatformAnchor->absolute());
+        for (float f : {t.x, t.y, t.z}) { int32_t u; std::memcpy(&u, &f, 4); o.push_back(u); }
+    }
+#undef BX
+#undef BY
+#undef BZ
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
 // the scene-graph conventions the restatement uses (see ref_scenegraph_case in oracle/ref_shim/ref_shim.cpp for the scenario code it mirrors)
 void orc_scenegraph_case(const float *ps, float angle, const float *pt, const float *cs, const float *ct, const float *fs, const float *ft,
                          const float *rs, const float *rt, float *out48) {

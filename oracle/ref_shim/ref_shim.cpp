@@ -8,6 +8,8 @@
 #include <vector>
 
 #include <env/const.hpp>           // src/libs/env/include/env/const.hpp: ColorRgb, colour tables, rgb()
+#include <scenarios/platforms.hpp>  // src/libs/scenarios/include/scenarios/platforms.hpp (with ref_shim/inc/env/env.hpp standing in for env.hpp)
+#include <scenarios/component_voxel_grid.hpp>  // VoxelGridComponent::addPlatform + the greedy voxel -> box merge (with the stand-ins in ref_shim/inc)
 #include <util/perlin_noise.hpp>   // src/libs/util/include/util/perlin_noise.hpp (siv::PerlinNoise as vendored by the reference)
 #include <mazes/honeycombmaze.h>  // src/libs/mazes
 #include <mazes/kruskal.h>
@@ -94,6 +96,114 @@ void ref_scenegraph_case(const float *ps, float angle, const float *pt, const fl
     free.scale({fs[0], fs[1], fs[2]}).translate({ft[0], ft[1], ft[2]});
     free.setParentKeepTransformation(&root);
     store(free.absoluteTransformationMatrix(), out48 + 32);
+}
+// the reference's obstacle-course platforms (platforms.hpp:137-559): one platform of the given type under an anchor object at (3,1,2),
+// init -> optional rotateCCW / rotateCW -> generate, then everything a scenario reads from it.  params9: obstaclesMin/MaxGap,
+// Min/MaxLava, Min/MaxHeight, verticalLookLimitRad, episodeLengthSec, obstaclesNumAllowedMaxDifficulty
+int ref_platform_case(int type, unsigned seed, int walls, int w, int l, int rotate, int prevWidth, const float *params9, int nObjects, int nAgents, int32_t *out, int cap) {
+    using namespace Megaverse;
+    using Scene3D = SceneGraph::Scene<SceneGraph::MatrixTransformation3D>;
+    FloatParams fp{{"obstaclesMinGap", params9[0]}, {"obstaclesMaxGap", params9[1]}, {"obstaclesMinLava", params9[2]}, {"obstaclesMaxLava", params9[3]},
+                   {"obstaclesMinHeight", params9[4]}, {"obstaclesMaxHeight", params9[5]}, {"verticalLookLimitRad", params9[6]}, {"episodeLengthSec", params9[7]},
+                   {"obstaclesNumAllowedMaxDifficulty", params9[8]}};
+    Rng rng(seed);
+    Scene3D scene;
+    auto &anchor = scene.addChild<Object3D>();
+    anchor.translate({3, 1, 2});
+    std::unique_ptr<Platform> p;
+    switch (type) {
+        case 0: p = std::make_unique<EmptyPlatform>(&anchor, rng, walls, fp, w); break;
+        case 1: p = std::make_unique<WallPlatform>(&anchor, rng, walls, fp, w); break;
+        case 2: p = std::make_unique<LavaPlatform>(&anchor, rng, walls, fp, w); break;
+        case 3: p = std::make_unique<StepPlatform>(&anchor, rng, walls, fp, w); break;
+        case 4: p = std::make_unique<GapPlatform>(&anchor, rng, walls, fp, w); break;
+        case 5: p = std::make_unique<StartPlatform>(&anchor, rng, fp, w); break;
+        case 6: p = std::make_unique<ExitPlatform>(&anchor, rng, fp, w); break;
+        default: p = std::make_unique<TransitionPlatform>(&anchor, rng, walls, fp, l, w); break;
+    }
+    p->init();
+    if (rotate == 1) p->rotateCCW(prevWidth); else if (rotate == 2) p->rotateCW(prevWidth);
+    p->generate();
+#define BX(v) (v).x()
+#define BY(v) (v).y()
+#define BZ(v) (v).z()
+
+    std::vector<int32_t> o;
+    auto pushBox = [&](const BoundingBox &b) { for (int v : {BX(b.min), BY(b.min), BZ(b.min), BX(b.max), BY(b.max), BZ(b.max)}) o.push_back(v); };
+    for (int v : {p->length, p->height, p->width, int(p->isMaxDifficulty()), p->requiresMovableBoxesToTraverse()}) o.push_back(v);
+    o.push_back(int(p->layoutBoxes.size()));
+    for (auto &b : p->layoutBoxes) pushBox(b.boundingBox());
+    o.push_back(int(p->wallBoxes.size()));
+    for (auto &b : p->wallBoxes) pushBox(b.boundingBox());
+    o.push_back(int(p->terrainBoxes.size()));
+    for (auto &kv : p->terrainBoxes) { o.push_back(int(kv.first)); o.push_back(int(kv.second.size())); for (auto &b : kv.second) pushBox(b.boundingBox()); }
+    pushBox(p->platformBoundingBox());
+
+    const auto objs = p->generateObjectPositions(nObjects);
+    o.push_back(int(objs.size()));
+    for (auto &c : objs) for (int v : {c.x(), c.y(), c.z()}) o.push_back(v);
+    const auto spawns = p->agentSpawnPoints(nAgents);
+    o.push_back(int(spawns.size()));
+    for (auto &c : spawns) for (float f : {c.x(), c.y(), c.z()}) { int32_t u; std::memcpy(&u, &f, 4); o.push_back(u); }
+    if (p->nextPlatformAnchor) {
+        const Vector3 t = p->nextPlatformAnchor->absoluteTransformation().translation();
+        for (float f : {t.x(), t.y(), t.z()}) { int32_t u; std::memcpy(&u, &f, 4); o.push_back(u); }
+    }
+#undef BX
+#undef BY
+#undef BZ
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
+// the reference's layout pipeline for two chained platforms: Start, then one of the obstacle types hung on its anchor (turned or
+// not), both added to a VoxelGridComponent (component_voxel_grid.hpp:73-106) and merged into boxes by toBoundingBoxes (:108-187).
+// out: number of (type, colour) groups, then per group type, colour, count and the boxes (inclusive min/max), in std::map order
+int ref_voxel_layout_case(int type, unsigned seed, int rotate, int drawWalls, const float *params9, int32_t *out, int cap) {
+    using namespace Megaverse;
+    using Scene3D = SceneGraph::Scene<SceneGraph::MatrixTransformation3D>;
+    FloatParams fp{{"obstaclesMinGap", params9[0]}, {"obstaclesMaxGap", params9[1]}, {"obstaclesMinLava", params9[2]}, {"obstaclesMaxLava", params9[3]},
+                   {"obstaclesMinHeight", params9[4]}, {"obstaclesMaxHeight", params9[5]}, {"verticalLookLimitRad", params9[6]}, {"episodeLengthSec", params9[7]},
+                   {"obstaclesNumAllowedMaxDifficulty", params9[8]}};
+    Rng rng(seed);
+    Scene3D scene;
+    auto &levelRoot = scene.addChild<Object3D>();
+    StartPlatform start(&levelRoot, rng, fp);
+    start.init(); start.generate();
+    std::unique_ptr<Platform> p;
+    const int walls = 4 | 8, w = rotate ? -1 : start.width;
+    switch (type) {
+        case 1: p = std::make_unique<WallPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        case 2: p = std::make_unique<LavaPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        case 3: p = std::make_unique<StepPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        case 4: p = std::make_unique<GapPlatform>(start.nextPlatformAnchor, rng, walls, fp, w); break;
+        default: p = std::make_unique<ExitPlatform>(start.nextPlatformAnchor, rng, fp, w); break;
+    }
+    p->init();
+    if (rotate == 1) p->rotateCCW(start.width); else if (rotate == 2) p->rotateCW(start.width);
+    p->generate();
+    Scenario scenario;
+    VoxelGridComponent<VoxelState> vg{scenario, 100, 0, 0, 0, 1};
+    vg.addPlatform(start, ColorRgb::LAYOUT_DEFAULT, ColorRgb::DARK_GREY, bool(drawWalls));
+    vg.addPlatform(*p, ColorRgb::VERY_LIGHT_BLUE, ColorRgb::GREY, bool(drawWalls));
+    const auto byType = vg.toBoundingBoxes();
+#define BX(v) (v).x()
+#define BY(v) (v).y()
+#define BZ(v) (v).z()
+
+    std::vector<int32_t> o;
+    o.push_back(int(byType.size()));
+    for (auto &kv : byType) {
+        o.push_back(int(kv.first.type)); o.push_back(int(kv.first.color)); o.push_back(int(kv.second.size()));
+        for (auto &b : kv.second) for (int v : {BX(b.min), BY(b.min), BZ(b.min), BX(b.max), BY(b.max), BZ(b.max)}) o.push_back(v);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+
+#undef BX
+#undef BY
+#undef BZ
 }
 // the reference's colour tables (env/const.hpp:25-143): [n all, n agent, n object, n layout] then the 0xRRGGBB values in that order,
 // then rgb(allColors[i]) as 3 floats each (bit patterns), i.e. what the renderer multiplies with

@@ -219,3 +219,60 @@ def test_scene_graph_conventions_match_magnum(libs):
             else:
                 assert np.allclose(a, b, rtol=2e-6, atol=2e-6), trial
                 assert np.array_equal(a[32:].view(np.uint32), b[32:].view(np.uint32)), trial  # the re-parented object has no rotation
+
+
+def test_platforms_match_reference_header(libs):
+    """the obstacle-course platforms (Empty / Wall / Lava / Step / Gap / Start / Exit / Transition) of the oracle against the
+    reference's own scenarios/platforms.hpp compiled in place: same RNG draws in init() / generate(), same layout, wall and terrain
+    boxes after the scene-graph transforms (incl. the 90-degree turns), same object cells, spawn points, difficulty flags and anchors"""
+    ref, L = libs
+    if not hasattr(ref, "ref_platform_case"):
+        pytest.skip("oracle/_ref/libmvref.so predates the platform shim")
+    for fn in (ref.ref_platform_case, L.orc_platform_case):
+        fn.argtypes = [C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        fn.restype = C.c_int
+    param_sets = [_f([1, 2, 1, 4, 1, 3, 0.2, 60, 1]), _f([2, 3, 3, 10, 2, 4, 0.2, 60, 1]), _f([1, 3, 2, 10, 1, 3, 0.2, 60, 1])]
+    checked = 0
+    for ptype in range(8):
+        for seed in range(1, 26):
+            for width in (-1, 5, 8):
+                if ptype == 7 and width == -1:
+                    continue
+                for rotate, prev_w in ((0, 0), (1, 6), (2, 7)):
+                    params = param_sets[seed % 3]
+                    walls = [4 | 8, 15, 1 | 4 | 8][seed % 3]
+                    a = np.zeros(4096, dtype=np.int32); b = np.zeros(4096, dtype=np.int32)
+                    args = (ptype, seed, walls, width, 3 + seed % 4, rotate, prev_w, params.ctypes.data, 1 + seed % 5, 1 + seed % 4)
+                    na = ref.ref_platform_case(*args, a.ctypes.data, a.size)
+                    nb = L.orc_platform_case(*args, b.ctypes.data, b.size)
+                    assert na == nb and na > 0, (ptype, seed, width, rotate)
+                    assert np.array_equal(a[:na], b[:nb]), "platform type %d seed %d width %d rotate %d: first diff at %s" % (
+                        ptype, seed, width, rotate, np.nonzero(a[:na] != b[:nb])[0][:5])
+                    checked += 1
+    assert checked > 1500
+
+
+def test_voxel_layout_pipeline_matches_reference(libs):
+    """platforms -> VoxelGridComponent::addPlatform -> toBoundingBoxes (the greedy voxel merge that produces every static box the
+    scenarios draw and collide with): the restatement against the reference's own component_voxel_grid.hpp + platforms.hpp, for a
+    start platform followed by each obstacle type, straight and turned both ways, with visible and invisible walls.  Group order
+    (std::map<BBoxInfo>), box order (hash-map iteration) and extents must be identical."""
+    ref, L = libs
+    if not hasattr(ref, "ref_voxel_layout_case"):
+        pytest.skip("oracle/_ref/libmvref.so predates the layout shim")
+    for fn in (ref.ref_voxel_layout_case, L.orc_voxel_layout_case):
+        fn.argtypes = [C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        fn.restype = C.c_int
+    param_sets = [_f([1, 2, 1, 4, 1, 3, 0.2, 60, 1]), _f([2, 3, 3, 10, 2, 4, 0.2, 60, 1])]
+    checked = 0
+    for ptype in (1, 2, 3, 4, 6):
+        for seed in range(1, 41):
+            for rotate in (0, 1, 2):
+                a = np.zeros(1 << 14, dtype=np.int32); b = np.zeros(1 << 14, dtype=np.int32)
+                args = (ptype, seed, rotate, seed % 2, param_sets[seed % 2].ctypes.data)
+                na = ref.ref_voxel_layout_case(*args, a.ctypes.data, a.size)
+                nb = L.orc_voxel_layout_case(*args, b.ctypes.data, b.size)
+                assert na == nb and na > 4, (ptype, seed, rotate)
+                assert np.array_equal(a[:na], b[:nb]), "type %d seed %d rotate %d: first diff at %s" % (ptype, seed, rotate, np.nonzero(a[:na] != b[:nb])[0][:5])
+                checked += 1
+    assert checked == 600
