@@ -243,6 +243,43 @@ int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
     return int(o.size());
 }
 
+// the restated pick-up / put-down logic (Env::onInteractAction), same scripted scene and layout as ref_stacking_case
+int orc_stacking_case(const int *solid, int nSolid, const int *objVoxels, int nObj, int nAgents, const float *script, int nEvents, int32_t *out, int cap) {
+    Env env("ObstaclesEasy", nAgents, {});  // a scenario whose stacking callbacks are the defaults (canPlaceObject: true)
+    env.vg.reset();
+    env.agents.assign(size_t(nAgents), Agent{});
+    for (auto &a : env.agents) a.pickupLocal = mul(mat4Translation({0.0f, -0.44f, -1.0f}), mat4Identity());
+    env.carryingObject.assign(size_t(nAgents), -1);
+    for (int i = 0; i < nSolid; ++i) env.vg.grid.set(VoxelCoords(solid[i * 3], solid[i * 3 + 1], solid[i * 3 + 2]), VoxelGridComponent::makeVoxel(VOXEL_SOLID | VOXEL_OPAQUE));
+    std::vector<VoxelCoords> positions;
+    for (int i = 0; i < nObj; ++i) positions.emplace_back(objVoxels[i * 3], objVoxels[i * 3 + 1], objVoxels[i * 3 + 2]);
+    env.addObjects(positions);
+    std::vector<int32_t> o;
+    auto bits = [](float f) { int32_t u; std::memcpy(&u, &f, 4); return u; };
+    for (int ev = 0; ev < nEvents; ++ev) {
+        const float *e = script + size_t(ev) * 33;
+        const int ai = int(e[0]);
+        std::memcpy(&env.agents[size_t(ai)].objectT.c[0][0], e + 1, 64);
+        std::memcpy(&env.agents[size_t(ai)].cameraLocal.c[0][0], e + 17, 64);
+        env.onInteractAction(ai);
+        for (int k = 0; k < nObj; ++k) {
+            const MovableObject &ob = env.objects[size_t(k)];
+            const Vec3 t = translationOf(env.objectAbs(k)), sc = scalingOf(ob.local);
+            for (float f : {t.x, t.y, t.z, sc.x, sc.y, sc.z}) o.push_back(bits(f));
+            o.push_back(ob.parentAgent); o.push_back(env.colliders[size_t(ob.collider)].enabled ? 1 : 0);
+        }
+        for (int a = 0; a < nAgents; ++a) o.push_back(env.carryingObject[size_t(a)]);
+        std::vector<std::array<int32_t, 4>> occ;
+        for (auto &kv : env.vg.grid.getHashMap())
+            if (kv.second.physicsObject >= 0) occ.push_back({kv.first.x, kv.first.y, kv.first.z, kv.second.physicsObject});
+        std::sort(occ.begin(), occ.end());
+        o.push_back(int(occ.size()));
+        for (auto &r : occ) for (int v : r) o.push_back(v);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
 // the restated layout pipeline, same case and layout as ref_voxel_layout_case (oracle/ref_shim/ref_shim.cpp)
 int orc_voxel_layout_case(int type, unsigned seed, int rotate, int drawWalls, const float *params9, int32_t *out, int cap) {
     FloatParams fp{{"obstaclesMinGap", params9[0]}, {"obstaclesMaxGap", params9[1]}, {"obstaclesMinLava", params9[2]}, {"obstaclesMaxLava", params9[3]},

@@ -4,11 +4,13 @@
 // oracle/orc_math.hpp, oracle/orc_level.hpp and oracle/orc_maze.hpp.  Nothing here is copied: the reference sources are
 // included / compiled where they lie.
 #include <algorithm>
+#include <array>
 #include <cstring>
 #include <vector>
 
 #include <env/const.hpp>           // src/libs/env/include/env/const.hpp: ColorRgb, colour tables, rgb()
 #include <scenarios/platforms.hpp>  // src/libs/scenarios/include/scenarios/platforms.hpp (with ref_shim/inc/env/env.hpp standing in for env.hpp)
+#include <scenarios/component_object_stacking.hpp>  // the pick-up / put-down logic (with the stand-ins in ref_shim/inc)
 #include <scenarios/component_voxel_grid.hpp>  // VoxelGridComponent::addPlatform + the greedy voxel -> box merge (with the stand-ins in ref_shim/inc)
 #include <util/perlin_noise.hpp>   // src/libs/util/include/util/perlin_noise.hpp (siv::PerlinNoise as vendored by the reference)
 #include <mazes/honeycombmaze.h>  // src/libs/mazes
@@ -204,6 +206,77 @@ int ref_voxel_layout_case(int type, unsigned seed, int rotate, int drawWalls, co
 #undef BX
 #undef BY
 #undef BZ
+}
+// the reference's ObjectStackingComponent::onInteractAction (component_object_stacking.hpp:58-168) on a scripted scene:
+//   solid voxels, movable 0.39 boxes sitting in voxels, agents whose object / camera matrices the script sets before every interact.
+// script: per event 1 + 16 + 16 floats (agent index, agent matrix, camera-local matrix).  out per event: per object 3 translation bits
+// (absolute), 3 local scaling bits, parent (-1 scene, else agent), collides; then carrying[agent] per agent; then the voxels holding
+// an object as sorted (x, y, z, object) rows, preceded by their count.
+int ref_stacking_case(const int *solid, int nSolid, const int *objVoxels, int nObj, int nAgents, const float *script, int nEvents, int32_t *out, int cap) {
+    using namespace Megaverse;
+    struct TestAgent : AbstractAgent {
+        explicit TestAgent(Object3D *parent) : AbstractAgent{parent} {
+            cameraObject = &addChild<Object3D>();
+            pickupSpot = &cameraObject->addChild<Object3D>();
+            pickupSpot->translate({0.0f, -0.44f, -1.0f});  // agent.cpp:40
+        }
+        Object3D *interactLocation() override { return pickupSpot; }
+        Object3D *cameraObject, *pickupSpot;
+    };
+    struct NoCallbacks : ObjectStackingCallbacks {} callbacks;
+    Env env;
+    env.numAgents = nAgents;
+    Env::EnvState st;
+    st.scene = std::make_unique<Scene3D>();
+    st.physics = std::make_unique<Env::Physics>();
+    VoxelGrid<VoxelWithPhysicsObjects> grid(100, {0, 0, 0}, 1);
+    for (int i = 0; i < nSolid; ++i) grid.set({solid[i * 3], solid[i * 3 + 1], solid[i * 3 + 2]}, makeVoxel<VoxelWithPhysicsObjects>(VOXEL_SOLID | VOXEL_OPAQUE));
+    std::vector<RigidBody *> objects;
+    btBoxShape shape(btVector3{1, 1, 1});
+    for (int i = 0; i < nObj; ++i) {  // what addDrawablesAndCollisions does per object (:170-198), minus Bullet and the drawable
+        const VoxelCoords pos{objVoxels[i * 3], objVoxels[i * 3 + 1], objVoxels[i * 3 + 2]};
+        auto &object = st.scene->addChild<RigidBody>(st.scene.get(), 0.0f, &shape, st.physics->bWorld);
+        object.scale({0.39f, 0.39f, 0.39f}).translate({float(pos.x()) + 0.5f, float(pos.y()) + 0.5f, float(pos.z()) + 0.5f});
+        if (!grid.hasVoxel(pos)) grid.set(pos, VoxelWithPhysicsObjects{});
+        grid.get(pos)->physicsObject = &object;
+        objects.push_back(&object);
+    }
+    std::vector<TestAgent *> agents;
+    for (int i = 0; i < nAgents; ++i) { agents.push_back(&st.scene->addChild<TestAgent>(st.scene.get())); st.agents.push_back(agents.back()); }
+    Scenario scenario;
+    ObjectStackingComponent<VoxelWithPhysicsObjects> stacking{scenario, nAgents, grid, callbacks};
+    stacking.reset(env, st);
+    std::vector<int32_t> o;
+    auto bits = [](float f) { int32_t u; std::memcpy(&u, &f, 4); return u; };
+    for (int ev = 0; ev < nEvents; ++ev) {
+        const float *e = script + size_t(ev) * 33;
+        const int ai = int(e[0]);
+        agents[size_t(ai)]->setTransformation(Matrix4::from(e + 1));
+        agents[size_t(ai)]->cameraObject->setTransformation(Matrix4::from(e + 17));
+        stacking.onInteractAction(ai, st);
+        for (auto *obj : objects) {
+            const Vector3 t = obj->absoluteTransformation().translation(), sc = obj->transformation().scaling();
+            for (float f : {t.x(), t.y(), t.z(), sc.x(), sc.y(), sc.z()}) o.push_back(bits(f));
+            int parent = -1;
+            for (int a = 0; a < nAgents; ++a) if (obj->parent() == agents[size_t(a)]->pickupSpot) parent = a;
+            o.push_back(parent); o.push_back(obj->colliding() ? 1 : 0);
+        }
+        for (int a = 0; a < nAgents; ++a) {
+            int carried = -1;
+            for (int k = 0; k < nObj; ++k) if (stacking.agentCarryingObject(a) == objects[size_t(k)]) carried = k;
+            o.push_back(carried);
+        }
+        std::vector<std::array<int32_t, 4>> occ;
+        for (auto &kv : grid.getHashMap())
+            if (kv.second.physicsObject)
+                for (int k = 0; k < nObj; ++k) if (kv.second.physicsObject == objects[size_t(k)]) occ.push_back({kv.first.x(), kv.first.y(), kv.first.z(), k});
+        std::sort(occ.begin(), occ.end());
+        o.push_back(int(occ.size()));
+        for (auto &r : occ) for (int v : r) o.push_back(v);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
 }
 // the reference's colour tables (env/const.hpp:25-143): [n all, n agent, n object, n layout] then the 0xRRGGBB values in that order,
 // then rgb(allColors[i]) as 3 floats each (bit patterns), i.e. what the renderer multiplies with

@@ -276,3 +276,69 @@ def test_voxel_layout_pipeline_matches_reference(libs):
                 assert np.array_equal(a[:na], b[:nb]), "type %d seed %d rotate %d: first diff at %s" % (ptype, seed, rotate, np.nonzero(a[:na] != b[:nb])[0][:5])
                 checked += 1
     assert checked == 600
+
+
+def test_object_stacking_matches_reference_header(libs):
+    """ObjectStackingComponent::onInteractAction (pick up from the voxel in front / the one above it unless something sits on top,
+    carry as a child of the pickup spot at 0.78 scale, put down into the voxel of the carried object's position, let it sink to the
+    first solid / occupied voxel, refuse occupied voxels and voxels holding another agent): the oracle's Env::onInteractAction
+    against the reference's own component_object_stacking.hpp driven on real Magnum scene-graph objects.  Random scripts of agent
+    poses; object poses, parents, collision flags, carrying state and voxel occupancy must agree bit for bit after every event."""
+    ref, L = libs
+    if not hasattr(ref, "ref_stacking_case"):
+        pytest.skip("oracle/_ref/libmvref.so predates the stacking shim")
+    vp = C.c_void_p
+    for fn in (ref.ref_stacking_case, L.orc_stacking_case):
+        fn.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp, C.c_int]
+        fn.restype = C.c_int
+
+    def rot_y(a):
+        c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+        m = np.eye(4, dtype=np.float32); m[0, 0] = c; m[0, 2] = -s; m[2, 0] = s; m[2, 2] = c  # column-major rows = columns
+        return m
+
+    def rot_x(a):
+        c, s = np.float32(np.cos(a)), np.float32(np.sin(a))
+        m = np.eye(4, dtype=np.float32); m[1, 1] = c; m[1, 2] = s; m[2, 1] = -s; m[2, 2] = c
+        return m
+
+    def trans(t):
+        m = np.eye(4, dtype=np.float32); m[3, :3] = t
+        return m
+
+    rng = np.random.default_rng(17)
+    total_picks = 0
+    for trial in range(60):
+        solid = np.array([[x, 0, z] for x in range(8) for z in range(8)] + [[4, 1, 4], [4, 2, 4], [1, 1, 6]], dtype=np.int32)
+        cells = [(2, 1, 2), (2, 2, 2), (5, 1, 3), (6, 1, 6), (3, 1, 5), (5, 1, 5)]
+        objs = np.array(cells[: 3 + trial % 4], dtype=np.int32)
+        A = 1 + trial % 3
+        events = []
+        for ev in range(40):
+            ai = int(rng.integers(0, A))
+            if rng.random() < 0.6:  # stand next to an object / target cell and face it
+                tx, ty, tz = cells[int(rng.integers(0, len(cells)))]
+                yaw = float(rng.uniform(-np.pi, np.pi))
+                fwd = np.array([-np.sin(yaw), 0.0, -np.cos(yaw)])  # the pickup spot is 1 m along the agent's -z
+                pos = np.array([tx + 0.5, 1.0 + 1.8 + rng.uniform(-0.1, 0.6), tz + 0.5]) - fwd * rng.uniform(0.7, 1.3)
+            else:
+                yaw = float(rng.uniform(-np.pi, np.pi))
+                pos = np.array([rng.uniform(0.5, 7.5), 1.0 + 1.8 + rng.uniform(-0.2, 1.5), rng.uniform(0.5, 7.5)])
+            agent_m = rot_y(yaw) @ trans(pos.astype(np.float32))          # row-vector convention of the flattened column-major matrix
+            cam_m = rot_x(float(rng.uniform(-0.2, 0.2))) @ trans(np.float32([0, 0.41, 0]))
+            events.append(np.concatenate([[np.float32(ai)], agent_m.ravel(), cam_m.ravel()]))
+        script = np.ascontiguousarray(np.array(events, dtype=np.float32))
+        a = np.zeros(1 << 16, dtype=np.int32); b = np.zeros(1 << 16, dtype=np.int32)
+        args = (solid.ctypes.data, len(solid), objs.ctypes.data, len(objs), A, script.ctypes.data, len(events))
+        na = ref.ref_stacking_case(*args, a.ctypes.data, a.size)
+        nb = L.orc_stacking_case(*args, b.ctypes.data, b.size)
+        assert na == nb and na > 0, trial
+        assert np.array_equal(a[:na], b[:nb]), "trial %d: first diff at %s" % (trial, np.nonzero(a[:na] != b[:nb])[0][:5])
+        pos_ = 0
+        for _ in range(len(events)):  # rows: objects * 8, carrying per agent, count, count * 4
+            carried = a[pos_ + len(objs) * 8: pos_ + len(objs) * 8 + A]
+            total_picks += int((carried >= 0).any())
+            cnt = int(a[pos_ + len(objs) * 8 + A])
+            pos_ += len(objs) * 8 + A + 1 + 4 * cnt
+        assert pos_ == na
+    assert total_picks > 100  # the scripts really pick things up
