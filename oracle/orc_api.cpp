@@ -243,6 +243,51 @@ int orc_get_arrangement(void *p, int envIdx, int32_t *out, int cap) {
     return int(o.size());
 }
 
+// the restated layout helpers, same sequence and layout as ref_layout_utils_case (oracle/ref_shim/ref_shim.cpp)
+int orc_layout_utils_case(unsigned seed, int32_t *out, int cap) {
+    Env env("ObstaclesEasy", 1, {});
+    Rng rng(seed);
+    auto fr = [&](float lo, float hi) { return lo + (hi - lo) * frand(rng); };
+    Boxes boxes;
+    for (int i = 0; i < 5; ++i) {
+        const int x = randRange(-5, 20, rng), y = randRange(0, 4, rng), z = randRange(-5, 20, rng);
+        const int x1 = x + randRange(0, 9, rng), y1 = y + randRange(0, 3, rng), z1 = z + randRange(0, 9, rng);
+        boxes.push_back(BoundingBox{VoxelCoords(x, y, z), VoxelCoords(x1, y1, z1)});
+    }
+    env.addBoundingBoxes(boxes, VOXEL_SOLID | VOXEL_OPAQUE, GREY, 1.0f);
+    env.addBoundingBoxes(boxes, VOXEL_SOLID, DARK_GREY, 2.0f);
+    env.addBoundingBoxes(boxes, VOXEL_OPAQUE, ORANGE, 1.0f);
+    for (int i = 0; i < 4; ++i) {
+        const int x = randRange(0, 20, rng), z = randRange(0, 20, rng);
+        const int y = randRange(1, 3, rng), x1 = x + randRange(0, 6, rng), z1 = z + randRange(1, 6, rng);
+        env.addTerrain(i % 2 ? TERRAIN_LAVA : TERRAIN_EXIT, BoundingBox{VoxelCoords(x, y, z), VoxelCoords(x1, 2, z1)});
+    }
+    for (int i = 0; i < 4; ++i) {
+        const float sx = fr(0.1f, 9), sy = fr(0.0001f, 2), sz = fr(0.1f, 9);
+        const float tx = fr(-20, 20), ty = fr(-1, 3), tz = fr(-20, 20);
+        env.addStaticCollidingBox({sx, sy, sz}, {tx, ty, tz}, BLUE);
+    }
+    for (int i = 0; i < 3; ++i) {
+        { const float x = fr(-20, 20), y = fr(0, 3), z = fr(-20, 20); const float k = fr(0.5f, 2.5f); env.addMemoryShape(Env::SHAPE_DIAMOND, GREEN, {x, y, z}, Vec3{0.17f, 0.45f, 0.17f} * k, false, true); }
+        { const float x = fr(-20, 20), y = fr(0, 3), z = fr(-20, 20); const float k = fr(0.5f, 1.5f); env.addMemoryShape(Env::SHAPE_PILLAR, VIOLET, {x, y, z}, Vec3{0.5f, 2, 0.5f} * k, false, true); }
+        { const float x = fr(-20, 20), y = fr(0, 3), z = fr(-20, 20); const float k = fr(0.5f, 1.5f); env.addMemoryShape(Env::SHAPE_SPHERE, RED, {x, y, z}, Vec3{0.75f, 0.75f, 0.75f} * k, false, true); }
+    }
+    std::vector<int32_t> o;
+    auto bits = [](float f) { int32_t u; std::memcpy(&u, &f, 4); return u; };
+    for (int t = 0; t < 5; ++t) o.push_back(int(env.drawables[t].size()));
+    for (int t = 0; t < 5; ++t)
+        for (auto &d : env.drawables[t]) {
+            for (int i = 0; i < 16; ++i) o.push_back(bits((&d.model.c[0][0])[i]));
+            const unsigned c = unsigned(allColors[d.color]);
+            for (float f : {float((c >> 16) & 255) / 255.0f, float((c >> 8) & 255) / 255.0f, float(c & 255) / 255.0f}) o.push_back(bits(f));
+        }
+    o.push_back(int(env.colliders.size()));
+    for (auto &c : env.colliders)
+        for (float f : {c.c.x, c.c.y, c.c.z, c.h.x, c.h.y, c.h.z}) o.push_back(bits(f));
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
 // the restated pick-up / put-down logic (Env::onInteractAction), same scripted scene and layout as ref_stacking_case
 int orc_stacking_case(const int *solid, int nSolid, const int *objVoxels, int nObj, int nAgents, const float *script, int nEvents, int32_t *out, int cap) {
     Env env("ObstaclesEasy", nAgents, {});  // a scenario whose stacking callbacks are the defaults (canPlaceObject: true)

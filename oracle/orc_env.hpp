@@ -1212,22 +1212,23 @@ public:
         addObjects(objectPositions);
     }
 
-    void addDrawablesAndCollisionObjectsFromVoxelGrid(float voxelSize) {
+    void addDrawablesAndCollisionObjectsFromVoxelGrid(float voxelSize) {  // layout_utils.hpp:12-18
         auto byType = vg.toBoundingBoxes();
-        for (auto &[info, boxes] : byType) {
-            if (info.type == VOXEL_EMPTY) continue;
-            for (auto &box : boxes) {
-                staticBoxes.push_back({box, info.type, info.color});
-                if (info.type & VOXEL_OPAQUE)
-                    drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(info.color),
-                                                   mul(mat4Translation(staticBoxTranslation(box, voxelSize)), mul(mat4Scaling(staticBoxScale(box, voxelSize)), mat4Identity()))});
-                if (info.type & VOXEL_SOLID) {
-                    Collider c;
-                    c.kind = 0;
-                    c.h = staticBoxScale(box, voxelSize);
-                    c.c = staticBoxTranslation(box, voxelSize);
-                    colliders.push_back(c);
-                }
+        for (auto &[info, boxes] : byType) addBoundingBoxes(boxes, info.type, info.color, voxelSize);
+    }
+    void addBoundingBoxes(const Boxes &boxes, int voxelType, ColorRgb color, float voxelSize) {  // layout_utils.cpp:17-50
+        if (voxelType == VOXEL_EMPTY) return;
+        for (auto &box : boxes) {
+            staticBoxes.push_back({box, uint8_t(voxelType), color});
+            if (voxelType & VOXEL_OPAQUE)
+                drawables[MESH_BOX].push_back({DrawEntry::D_STATIC, 0, paletteIndex(color),
+                                               mul(mat4Translation(staticBoxTranslation(box, voxelSize)), mul(mat4Scaling(staticBoxScale(box, voxelSize)), mat4Identity()))});
+            if (voxelType & VOXEL_SOLID) {
+                Collider c;
+                c.kind = 0;
+                c.h = staticBoxScale(box, voxelSize);
+                c.c = staticBoxTranslation(box, voxelSize);
+                colliders.push_back(c);
             }
         }
     }

@@ -29,15 +29,27 @@ enum class Action { Idle = 0, Interact = 1 << 8 };  // env.hpp:22-42 (only the b
 inline Action operator&(Action a, Action b) { return Action(int(a) & int(b)); }
 inline bool operator!(Action a) { return int(a) == 0; }
 
-enum class DrawableType { Box = 0 };  // env.hpp:57-67 (name only)
-using DrawablesMap = std::map<DrawableType, std::vector<std::pair<Object3D *, Magnum::Color3>>>;
+enum class DrawableType { First = 0, Box = 0, Capsule = 1, Sphere = 2, Cone = 3, Cylinder = 4, NumTypes };  // env.hpp:57-67
+struct SceneObjectInfo {  // env.hpp:70-80
+    SceneObjectInfo(Object3D *objectPtr, const Magnum::Color3 &color) : objectPtr{objectPtr}, color{color} {}
+    Object3D *objectPtr;
+    Magnum::Color3 color;
+};
+using DrawablesMap = std::map<DrawableType, std::vector<SceneObjectInfo>>;
 
 class RigidBody : public Object3D {  // physics.hpp:19-102 without Bullet
 public:
     RigidBody(Object3D *parent, Magnum::Float, btCollisionShape *, btDynamicsWorld &) : Object3D{parent} {}
-    void setCollisionScale(const Magnum::Vector3 &) {}
-    void setCollisionOffset(const Magnum::Vector3 &) {}
-    void syncPose() { ++syncs; }
+    void setCollisionScale(const Magnum::Vector3 &s) { collisionScale = s; }
+    void setCollisionOffset(const Magnum::Vector3 &o) { collisionOffset = o; }
+    // physics.hpp:69-74: world transform = (rotation, translation + offset), local scaling = scaling * collisionScale -- kept as numbers
+    void syncPose() {
+        const auto &m = absoluteTransformationMatrix();
+        colliderOrigin = m.translation() + collisionOffset;
+        colliderScaling = m.scaling() * collisionScale;
+        ++syncs;
+    }
+    Magnum::Vector3 collisionScale{1, 1, 1}, collisionOffset{0, 0, 0}, colliderOrigin{0, 0, 0}, colliderScaling{0, 0, 0};
     void toggleCollision() { collides = !collides; }
     bool colliding() const { return collides; }
     bool collides = true;

@@ -5,11 +5,13 @@
 // included / compiled where they lie.
 #include <algorithm>
 #include <array>
+#include <functional>
 #include <cstring>
 #include <vector>
 
 #include <env/const.hpp>           // src/libs/env/include/env/const.hpp: ColorRgb, colour tables, rgb()
 #include <scenarios/platforms.hpp>  // src/libs/scenarios/include/scenarios/platforms.hpp (with ref_shim/inc/env/env.hpp standing in for env.hpp)
+#include <scenarios/layout_utils.hpp>  // src/libs/scenarios/src/layout_utils.cpp is compiled into this library as is
 #include <scenarios/component_object_stacking.hpp>  // the pick-up / put-down logic (with the stand-ins in ref_shim/inc)
 #include <scenarios/component_voxel_grid.hpp>  // VoxelGridComponent::addPlatform + the greedy voxel -> box merge (with the stand-ins in ref_shim/inc)
 #include <util/perlin_noise.hpp>   // src/libs/util/include/util/perlin_noise.hpp (siv::PerlinNoise as vendored by the reference)
@@ -274,6 +276,64 @@ int ref_stacking_case(const int *solid, int nSolid, const int *objVoxels, int nO
         o.push_back(int(occ.size()));
         for (auto &r : occ) for (int v : r) o.push_back(v);
     }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
+// the reference's layout_utils.cpp (compiled in place): what each helper adds to the drawables map and to the collision world.
+// out: per drawable type 0..4 its count, then per drawable 16 matrix bits (absoluteTransformationMatrix) + colour 0xRRGGBB-as-floats
+// (3 bits); then the number of rigid bodies and per body 6 bits (collider origin, collider scaling)
+int ref_layout_utils_case(unsigned seed, int32_t *out, int cap) {
+    using namespace Megaverse;
+    Rng rng(seed);
+    Env::EnvState st;
+    st.scene = std::make_unique<Scene3D>();
+    st.physics = std::make_unique<Env::Physics>();
+    DrawablesMap drawables;
+    auto fr = [&](float lo, float hi) { return lo + (hi - lo) * frand(rng); };
+    Boxes boxes;
+    for (int i = 0; i < 5; ++i) {
+        const int x = randRange(-5, 20, rng), y = randRange(0, 4, rng), z = randRange(-5, 20, rng);
+        const int x1 = x + randRange(0, 9, rng), y1 = y + randRange(0, 3, rng), z1 = z + randRange(0, 9, rng);  // (named: argument order is unspecified)
+        boxes.emplace_back(x, y, z, x1, y1, z1);
+    }
+    addBoundingBoxes(drawables, st, boxes, VOXEL_SOLID | VOXEL_OPAQUE, ColorRgb::GREY, 1.0f);
+    addBoundingBoxes(drawables, st, boxes, VOXEL_SOLID, ColorRgb::DARK_GREY, 2.0f);   // invisible colliders, voxel size 2 (Sokoban)
+    addBoundingBoxes(drawables, st, boxes, VOXEL_OPAQUE, ColorRgb::ORANGE, 1.0f);     // drawn, no collider
+    for (int i = 0; i < 4; ++i) {
+        const int x = randRange(0, 20, rng), z = randRange(0, 20, rng);
+        const int y = randRange(1, 3, rng), x1 = x + randRange(0, 6, rng), z1 = z + randRange(1, 6, rng);
+        addTerrain(drawables, st, i % 2 ? TERRAIN_LAVA : TERRAIN_EXIT, BoundingBox{x, y, z, x1, 2, z1}, 1.0f);
+    }
+    for (int i = 0; i < 4; ++i) {
+        const float sx = fr(0.1f, 9), sy = fr(0.0001f, 2), sz = fr(0.1f, 9);
+        const float tx = fr(-20, 20), ty = fr(-1, 3), tz = fr(-20, 20);
+        addStaticCollidingBox(drawables, st, {sx, sy, sz}, {tx, ty, tz}, ColorRgb::BLUE);
+    }
+    for (int i = 0; i < 3; ++i) {
+        { const float x = fr(-20, 20), y = fr(0, 3), z = fr(-20, 20); const float k = fr(0.5f, 2.5f); addDiamond(drawables, *st.scene, {x, y, z}, Magnum::Vector3{0.17f, 0.45f, 0.17f} * k, ColorRgb::GREEN); }
+        { const float x = fr(-20, 20), y = fr(0, 3), z = fr(-20, 20); const float k = fr(0.5f, 1.5f); addPillar(drawables, *st.scene, {x, y, z}, Magnum::Vector3{0.5f, 2, 0.5f} * k, ColorRgb::VIOLET); }
+        { const float x = fr(-20, 20), y = fr(0, 3), z = fr(-20, 20); const float k = fr(0.5f, 1.5f); addSphere(drawables, *st.scene, {x, y, z}, Magnum::Vector3{0.75f, 0.75f, 0.75f} * k, ColorRgb::RED); }
+    }
+    std::vector<int32_t> o;
+    auto bits = [](float f) { int32_t u; std::memcpy(&u, &f, 4); return u; };
+    for (int t = 0; t < 5; ++t) o.push_back(int(drawables[DrawableType(t)].size()));
+    for (int t = 0; t < 5; ++t)
+        for (auto &d : drawables[DrawableType(t)]) {
+            const Matrix4 m = d.objectPtr->absoluteTransformationMatrix();
+            for (int i = 0; i < 16; ++i) o.push_back(bits(m.data()[i]));
+            for (float f : {d.color.r(), d.color.g(), d.color.b()}) o.push_back(bits(f));
+        }
+    std::vector<RigidBody *> bodies;
+    std::function<void(Object3D &)> walk = [&](Object3D &n) {
+        if (auto *rb = dynamic_cast<RigidBody *>(&n)) bodies.push_back(rb);
+        for (Object3D &c : n.children()) walk(c);
+    };
+    // creation order: children lists are in insertion order
+    for (Object3D &c : st.scene->children()) walk(c);
+    o.push_back(int(bodies.size()));
+    for (auto *rb : bodies)
+        for (float f : {rb->colliderOrigin.x(), rb->colliderOrigin.y(), rb->colliderOrigin.z(), rb->colliderScaling.x(), rb->colliderScaling.y(), rb->colliderScaling.z()}) o.push_back(bits(f));
     if (int(o.size()) > cap) return -int(o.size());
     std::copy(o.begin(), o.end(), out);
     return int(o.size());

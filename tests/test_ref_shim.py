@@ -342,3 +342,22 @@ def test_object_stacking_matches_reference_header(libs):
             pos_ += len(objs) * 8 + A + 1 + 4 * cnt
         assert pos_ == na
     assert total_picks > 100  # the scripts really pick things up
+
+
+def test_layout_utils_match_reference(libs):
+    """the drawables and colliders that layout_utils.cpp creates -- addBoundingBoxes (voxel sizes 1 and 2, drawn / solid / both),
+    addTerrain, addStaticCollidingBox, addDiamond, addPillar (caps re-parented keeping their transformation), addSphere -- from the
+    reference's own source file compiled in place, against the oracle: model matrices (absoluteTransformationMatrix), colours and the
+    collider origin / scaling RigidBody::syncPose would hand to Bullet, bit for bit, in creation order per mesh type"""
+    ref, L = libs
+    if not hasattr(ref, "ref_layout_utils_case"):
+        pytest.skip("oracle/_ref/libmvref.so predates the layout-utils shim")
+    for fn in (ref.ref_layout_utils_case, L.orc_layout_utils_case):
+        fn.argtypes = [C.c_uint, C.c_void_p, C.c_int]
+        fn.restype = C.c_int
+    for seed in range(1, 201):
+        a = np.zeros(1 << 14, dtype=np.int32); b = np.zeros(1 << 14, dtype=np.int32)
+        na = ref.ref_layout_utils_case(seed, a.ctypes.data, a.size)
+        nb = L.orc_layout_utils_case(seed, b.ctypes.data, b.size)
+        assert na == nb and na > 100, seed
+        assert np.array_equal(a[:na], b[:nb]), "seed %d: first diff at %s (counts %s vs %s)" % (seed, np.nonzero(a[:na] != b[:nb])[0][:5], a[:5], b[:5])
