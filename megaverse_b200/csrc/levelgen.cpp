@@ -943,8 +943,9 @@ void hexMazeBuild(const HexMazeComponent &hm, Rng &rng, LevelOut &out, int &ns) 
                 sb.c[0] = wall.c[3][0] + 0.0f; sb.c[1] = wall.c[3][1] + 0.0f; sb.c[2] = wall.c[3][2] + 0.0f;
                 for (int a = 0; a < 3; ++a) sb.h[a] = colLen(wall, a) * 1.0f;
                 sb.flags = MV_SOLID | MV_ROTATED; sb.color = 0;
-                L.static_rot[ns][0] = wall.c[0][0] / sb.h[0];
-                L.static_rot[ns][1] = wall.c[0][2] / sb.h[0];
+                const float lenInv = 1.0f / sb.h[0];  // what Bullet is handed: Matrix4::rotation() = column * (1 / length)
+                L.static_rot[ns][0] = wall.c[0][0] * lenInv;
+                L.static_rot[ns][1] = wall.c[0][2] * lenInv;
                 ++ns;
             }
             const float es[3] = {length * 1.02f, hm.wallHeight * 0.12f, 0.2f};

@@ -780,51 +780,45 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, const MvDe
         M4 m = tsMatrix(v3(o.t[0], o.t[1], o.t[2]), v3(o.s[0], o.s[1], o.s[2]));
         if (o.parent >= 0) {
             const MvAgent &a = S.agents[o.parent];
-            m = mul4(loadM4(a.object_t), mul4(loadM4(a.cam_local), mul4(pickupLocal(), m)));
+            m = mul4(mul4(mul4(loadM4(a.object_t), loadM4(a.cam_local)), pickupLocal()), m);  // left to right, as absoluteTransformation()
         }
         putInstance(inst[MV_OBJ_SLOT(o.meta)], m, MV_OBJ_MESH(o.meta), o.color);
     }
-    // per agent: view matrix, eyes, HUD bar, body.  Every chain keeps the scene graph's right-to-left association;
-    // products are formed cooperatively (sixteen lanes per matrix, two matrices per round):
-    //   r1  T0 = cam * eyes            T1 = anchor * bar
-    //   r2  eyes instance = objT * T0  T2 = ui * T1
-    //   r3  T3 = objT * cam            T4 = cam * T2
-    //   r4  view = inverse(T3)         bar instance = objT * T4
-    //   r5  body instance = objT * body
+    // per agent: view matrix, eyes, HUD bar, body.  Every chain is associated the way Magnum's absoluteTransformation()
+    // recursion does it (SceneGraph/Object.hpp:114-117): from the root, left to right -- ((objT * cam) * ui) * anchor) * bar.
+    // Products are formed cooperatively (sixteen lanes per matrix, two matrices per round):
+    //   r1  T3 = objT * cam              body instance = objT * body
+    //   r2  eyes instance = T3 * eyes    T1 = T3 * ui
+    //   r3  view = inverse(T3)           T2 = T1 * anchor
+    //   r4                               bar instance = T2 * bar
     {
         float (*T)[16] = const_cast<float (*)[16]>(S.mtx);
         const int half = lane >> 4, e = lane & 15;
         const float eyesE = tsElem(0.0f, 0.0f, -0.19f, 0.25f, 0.12f, 0.2f, e), uiE = tsElem(0, 0, -0.2f, 1, 1, 1, e);
         const float anchorE = tsElem(0, -0.131f, 0, 1, 1, 1, e), bodyE = tsElem(0, 0.09f, 0, 0.35f, 0.36f, 0.35f, e);
-        // constant locals: slots 5 (eyes), 6 (ui / body after r2), 7 (anchor)
-        if (half == 0) { T[5][e] = eyesE; T[6][e] = uiE; } else { T[7][e] = anchorE; }
+        // constant locals: slots 5 (eyes), 6 (ui), 7 (anchor), 0 (body)
+        if (half == 0) { T[5][e] = eyesE; T[6][e] = uiE; } else { T[7][e] = anchorE; T[0][e] = bodyE; }
         for (int i = 0; i < A; ++i) {
             const MvAgent &a = S.agents[i];
             const float *objT = a.object_t, *cam = a.cam_local;
             if (half == 1) T[4][e] = tsElem(0, 0, 0, a.bar_scale[0], a.bar_scale[1], a.bar_scale[2], e);  // scaling4(bar)
             __syncwarp();
             {  // r1
-                const float v = half == 0 ? mul4Elem(cam, T[5], e) : mul4Elem(T[7], T[4], e);
-                T[half][e] = v;
+                if (half == 0) T[3][e] = mul4Elem(objT, cam, e);
+                else inst[L.slot_body + i].model[e] = mul4Elem(objT, T[0], e);
             }
             __syncwarp();
             {  // r2
-                const float v = half == 0 ? mul4Elem(objT, T[0], e) : mul4Elem(T[6], T[1], e);
-                if (half == 0) inst[L.slot_eyes + i].model[e] = v; else T[2][e] = v;
+                const float v = half == 0 ? mul4Elem(T[3], T[5], e) : mul4Elem(T[3], T[6], e);
+                if (half == 0) inst[L.slot_eyes + i].model[e] = v; else T[1][e] = v;
             }
             __syncwarp();
             {  // r3
-                const float v = half == 0 ? mul4Elem(objT, cam, e) : mul4Elem(cam, T[2], e);
-                T[3 + half][e] = v;
-            }
-            __syncwarp();
-            {  // r4
                 if (half == 0) views[i * 16 + e] = inv4Elem(T[3], e);  // Camera::cameraMatrix: inverse of the absolute transform
-                else inst[L.slot_bars + i].model[e] = mul4Elem(objT, T[4], e);
+                else T[2][e] = mul4Elem(T[1], T[7], e);
             }
-            if (half == 0) T[0][e] = bodyE;
             __syncwarp();
-            if (half == 0) inst[L.slot_body + i].model[e] = mul4Elem(objT, T[0], e);  // r5
+            if (half == 1) inst[L.slot_bars + i].model[e] = mul4Elem(T[2], T[4], e);  // r4
             if (lane >= 16 && lane < 28) {  // mesh / colour / padding words of the three instances
                 const int which = (lane - 16) >> 2, w = (lane - 16) & 3;
                 const int agentColors[7] = {0, 1, 3, 7, 14, 10, 12};  // const.hpp:85 as palette indices

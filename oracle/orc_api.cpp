@@ -580,4 +580,75 @@ void orc_rng_probe(double *out3) {
 }
 int orc_max_threads() { return int(std::thread::hardware_concurrency()); }
 
+
+// ---- scenario pin (tests/test_ref_shim.py): one env driven tick by tick beside the reference's real scenario sources
+// (oracle/ref_shim/scen_shim.cpp).  Layouts match ref_scen_*.
+static uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+void orc_scen_reset(void *p, int e) { static_cast<OrcVec *>(p)->envs[size_t(e)]->reset(); }
+void orc_scen_step(void *p, int e, const int *actions) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
+    for (int i = 0; i < env.numAgents; ++i) env.setAction(i, actions[i]);
+    env.step();
+}
+// test hook: put an agent somewhere else (btKinematicCharacterController::warp, as FallDetectionComponent does) so that scripted
+// trajectories reach the objects, boxes and rewards quickly; the reference-side puppets follow through orc_scen_poses
+void orc_scen_warp(void *p, int e, int agent, float x, float y, float z, float yaw) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
+    env.agents[size_t(agent)].kcc.warp({x, y, z});
+    env.agents[size_t(agent)].kcc.basis = mat3FromQuat(quatAxisAngle({0, 1, 0}, yaw));  // as DefaultKinematicAgent's constructor turns it
+    env.colliders[size_t(env.agentColliderBase + agent)].c = env.agents[size_t(agent)].kcc.pos;
+}
+void orc_scen_spawns(void *p, int e, uint32_t *out) {  // per agent: DefaultKinematicAgent's startingPosition xyz, rotationRad
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
+    for (int i = 0; i < env.numAgents; ++i) {
+        const Agent &a = env.agents[size_t(i)];
+        out[4 * i] = fbits(a.spawnPos.x), out[4 * i + 1] = fbits(a.spawnPos.y), out[4 * i + 2] = fbits(a.spawnPos.z), out[4 * i + 3] = fbits(a.spawnRot);
+    }
+}
+void orc_scen_poses(void *p, int e, float *out) {  // per agent: objectT[16] cameraLocal[16] onGround (column-major, as Magnum stores)
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
+    for (int i = 0; i < env.numAgents; ++i) {
+        const Agent &a = env.agents[size_t(i)];
+        std::memcpy(out + i * 33, &a.objectT, 64);
+        std::memcpy(out + i * 33 + 16, &a.cameraLocal, 64);
+        out[i * 33 + 32] = a.kcc.onGround() ? 1.0f : 0.0f;
+    }
+}
+void orc_scen_teleports(void *p, int e, uint32_t *out) {  // per agent: (count, last target xyz)
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
+    for (int i = 0; i < env.numAgents; ++i) out[4 * i] = 0, out[4 * i + 1] = out[4 * i + 2] = out[4 * i + 3] = fbits(0.0f);
+    for (auto &[i, t] : env.teleportLog) { ++out[4 * i]; out[4 * i + 1] = fbits(t.x), out[4 * i + 2] = fbits(t.y), out[4 * i + 3] = fbits(t.z); }
+}
+int orc_scenario_dump(void *p, int e, uint32_t *out, int cap) {
+    Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
+    std::vector<uint32_t> o;
+    o.push_back(fbits(env.episodeLengthSec()));
+    o.push_back(env.done ? 1u : 0u);
+    o.push_back(fbits(env.currEpisodeSec));
+    o.push_back(uint32_t(env.numAgents));
+    for (int i = 0; i < env.numAgents; ++i) {
+        o.push_back(fbits(env.lastReward[size_t(i)]));
+        o.push_back(fbits(env.totalReward[size_t(i)]));
+        o.push_back(fbits(env.trueObjective(i)));
+    }
+    const auto inst = env.instances();
+    o.push_back(uint32_t(inst.size()));
+    for (auto &in : inst) {
+        o.push_back(uint32_t(in.mesh));
+        o.push_back(uint32_t(allColors[in.color]));
+        const float *m = reinterpret_cast<const float *>(&in.model);
+        for (int k = 0; k < 16; ++k) o.push_back(fbits(m[k]));
+    }
+    o.push_back(uint32_t(env.agentColliderBase));
+    for (int c = 0; c < env.agentColliderBase; ++c) {
+        const Collider &col = env.colliders[size_t(c)];
+        o.push_back(fbits(col.c.x)), o.push_back(fbits(col.c.y)), o.push_back(fbits(col.c.z));
+        o.push_back(fbits(col.h.x)), o.push_back(fbits(col.h.y)), o.push_back(fbits(col.h.z));
+        o.push_back(fbits(col.rotated ? col.ax : 1.0f)), o.push_back(fbits(col.rotated ? col.az : 0.0f));
+        o.push_back(col.enabled ? 1u : 0u);
+    }
+    if (int(o.size()) > cap) return -int(o.size());
+    std::copy(o.begin(), o.end(), out);
+    return int(o.size());
+}
 }  // extern "C"

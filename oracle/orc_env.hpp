@@ -54,11 +54,14 @@ struct Agent {
     Mat4 pickupLocal = mat4Identity();  // pickupSpot, child of cameraObject
     Mat4 bodyLocal, eyesLocal, uiLocal, barAnchorLocal, barLocal;
     int color = 0;
+    Vec3 spawnPos{0, 0, 0};  // constructor arguments, kept for the scenario pin (tests/test_ref_shim.py)
+    float spawnRot = 0.0f;
 
     static constexpr float rotateRadians = 3.5f, rotateXRadians = 1.5f, agentHeight = 1.75f;
 
     void init(Vec3 startingPosition, float rotationRad, float lookLimit) {  // agent.cpp:26-67
         *this = Agent{};
+        spawnPos = startingPosition, spawnRot = rotationRad;
         verticalLookLimitRad = lookLimit;
         cameraLocal = mul(mat4Translation({0, 0.41f, 0}), cameraLocal);
         pickupLocal = mul(mat4Translation({0.0f, -0.44f, -1.0f}), pickupLocal);
@@ -297,8 +300,8 @@ public:
                     c.c = translationOf(wallLocal) + Vec3{0, 0, 0};
                     c.h = scalingOf(wallLocal) * Vec3{1, 1, 1};
                     c.rotated = true;
-                    const float lx = c.h.x;  // |first column|
-                    c.ax = wallLocal.c[0][0] / lx; c.az = wallLocal.c[0][2] / lx;
+                    const float lxInv = 1.0f / c.h.x;  // Matrix4::rotation(): column * lengthInverted() (Math/Vector.h:547,561)
+                    c.ax = wallLocal.c[0][0] * lxInv; c.az = wallLocal.c[0][2] * lxInv;
                     colliders.push_back(c);
                 }
                 {
@@ -1322,6 +1325,7 @@ public:
 
     void step() {
         std::fill(lastReward.begin(), lastReward.end(), 0.0f);
+        teleportLog.clear();
         const float dt = lastFrameDurationSec;
         for (int i = 0; i < numAgents; ++i) {
             const int a = currAction[i];
@@ -1511,6 +1515,7 @@ public:
         auto v = vg.grid.getWithVector(p);
         while (v && !v->empty() && p.y < 1000) { p.y += 1; v = vg.grid.getWithVector(p); }
         const float halfVoxel = vg.grid.getVoxelSize() / 2;
+        teleportLog.push_back({i, {p.x + halfVoxel, p.y + halfVoxel, p.z + halfVoxel}});
         agents[i].kcc.warp({p.x + halfVoxel, p.y + halfVoxel, p.z + halfVoxel});
         colliders[agentColliderBase + i].c = agents[i].kcc.pos;
     }
@@ -1521,8 +1526,10 @@ public:
 
     // ---------------------------------------------------------------- render interface
     // Instances in V4R draw order: mesh type major (meshIndices is a std::map<DrawableType,int>), insertion order minor
-    // (v4r_env_renderer.cpp:267-279). Model matrices are the drawables' absoluteTransformationMatrix() as computed by
-    // SceneGraph::Object::setClean(objects) (right-to-left composition up the parent chain, v4r_env_renderer.cpp:319-335).
+    // (v4r_env_renderer.cpp:267-279). Model matrices are the drawables' absoluteTransformationMatrix() (v4r_env_renderer.cpp:52-55),
+    // which Magnum recomputes on every call as compose(parent.absoluteTransformation(), transformation()) (SceneGraph/Object.hpp:114-117):
+    // the chain is multiplied LEFT to RIGHT from the root, ((agent * camera) * ui) * ...  -- pinned by tests/test_ref_shim.py against
+    // the reference's own scene graph and scenario sources.
     std::vector<Instance> instances() const {
         std::vector<Instance> out;
         for (auto &[mesh, list] : drawables)
@@ -1535,12 +1542,12 @@ public:
                         m = o.local;
                         if (o.parentAgent >= 0) {
                             const Agent &a = agents[size_t(o.parentAgent)];
-                            m = mul(a.objectT, mul(a.cameraLocal, mul(a.pickupLocal, o.local)));
+                            m = mul(a.pickupAbs(), o.local);
                         }
                         break;
                     }
-                    case DrawEntry::D_EYES: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, mul(a.cameraLocal, a.eyesLocal)); break; }
-                    case DrawEntry::D_BAR: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, mul(a.cameraLocal, mul(a.uiLocal, mul(a.barAnchorLocal, a.barLocal)))); break; }
+                    case DrawEntry::D_EYES: { const Agent &a = agents[size_t(d.index)]; m = mul(a.cameraAbs(), a.eyesLocal); break; }
+                    case DrawEntry::D_BAR: { const Agent &a = agents[size_t(d.index)]; m = mul(mul(mul(a.cameraAbs(), a.uiLocal), a.barAnchorLocal), a.barLocal); break; }
                     case DrawEntry::D_BODY: { const Agent &a = agents[size_t(d.index)]; m = mul(a.objectT, a.bodyLocal); break; }
                     case DrawEntry::D_REWARD_ROOT: m = rewardObjects[size_t(d.index)].root; break;
                     case DrawEntry::D_REWARD_BOTTOM: m = mul(rewardObjects[size_t(d.index)].root, rewardObjects[size_t(d.index)].bottomLocal); break;
@@ -1572,6 +1579,7 @@ public:
     std::vector<float> lastReward, totalReward;
 
     std::vector<Agent> agents;
+    std::vector<std::pair<int, Vec3>> teleportLog;  // (agent, target) of this tick's AbstractAgent::teleport calls
     std::vector<Collider> colliders;
     int agentColliderBase = 0;
     std::vector<MovableObject> objects;

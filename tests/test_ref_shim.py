@@ -361,3 +361,189 @@ def test_layout_utils_match_reference(libs):
         nb = L.orc_layout_utils_case(seed, b.ctypes.data, b.size)
         assert na == nb and na > 100, seed
         assert np.array_equal(a[:na], b[:nb]), "seed %d: first diff at %s (counts %s vs %s)" % (seed, np.nonzero(a[:na] != b[:nb])[0][:5], a[:5], b[:5])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's REAL scenario sources, driven tick by tick beside the oracle (oracle/_ref/libmvscen.so: scenario_*.cpp,
+# component_*.hpp/.cpp, layout_utils.cpp, env/scenario.hpp and scenario_default.hpp compiled in place against Bullet-free
+# stand-ins, oracle/ref_shim/scen_shim.cpp).  The agents on the reference side are posed puppets that receive the oracle's
+# agent transforms every tick, so what is compared -- bit for bit -- is everything a scenario decides: the level it builds at
+# reset (every drawable's mesh, colour and absolute matrix in draw order, every collider handed to Bullet, the agents' spawn
+# arguments, the episode length), and per tick the rewards, timers, done flag, true objectives, teleports and the moved
+# drawables / toggled colliders.
+SCEN = os.path.join(ROOT, "oracle", "_ref", "libmvscen.so")
+MAZE_SEED_XOR = 0x6D617A65  # the oracle seeds the maze's Kruskal generator from the episode seed (upstream: std::random_device)
+
+
+@pytest.fixture(scope="module")
+def scen_libs(built):
+    import orc
+
+    if not os.path.exists(SCEN):
+        if os.path.isdir("/root/reference/src/libs/scenarios"):
+            import subprocess
+
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "scen"])
+        else:
+            pytest.skip("oracle/_ref/libmvscen.so not built and /root/reference absent")
+    R, O = C.CDLL(SCEN), orc.lib()
+    R.ref_scen_create.restype = C.c_void_p
+    R.ref_scen_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    R.ref_scen_destroy.argtypes = [C.c_void_p]
+    R.ref_scen_seed.argtypes = [C.c_void_p, C.c_int]
+    R.ref_scen_reset_begin.argtypes = [C.c_void_p, C.c_uint, C.c_void_p]
+    R.ref_scen_reset_end.argtypes = [C.c_void_p, C.c_void_p]
+    R.ref_scen_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.ref_scen_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    O.orc_scen_reset.argtypes = [C.c_void_p, C.c_int]
+    O.orc_scen_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    O.orc_scen_spawns.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    O.orc_scen_warp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    O.orc_scen_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    O.orc_scen_teleports.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    O.orc_scenario_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return R, O
+
+
+_SCEN_CAP = 1 << 20
+
+
+def _scen_dump(fn, *args):
+    buf = np.zeros(_SCEN_CAP, np.uint32)
+    n = fn(*args, buf.ctypes.data, _SCEN_CAP)
+    assert n > 0
+    d = buf[:n]
+    A = int(d[3])
+    out = {"length": d[0], "done": int(d[1]), "sec": d[2], "agents": d[4:4 + 3 * A].copy()}
+    i = 4 + 3 * A
+    n_inst = int(d[i]); i += 1
+    out["inst"] = d[i:i + 18 * n_inst].reshape(n_inst, 18).copy(); i += 18 * n_inst
+    n_col = int(d[i]); i += 1
+    out["col"] = d[i:i + 9 * n_col].reshape(n_col, 9).copy(); i += 9 * n_col
+    assert i == n
+    return out
+
+
+def _scen_same(r, o, where):
+    assert r["length"] == o["length"], f"{where}: episode length"
+    assert r["done"] == o["done"], f"{where}: done"
+    assert r["sec"] == o["sec"], f"{where}: episode clock {r['sec']:#x} vs {o['sec']:#x}"
+    assert np.array_equal(r["agents"], o["agents"]), f"{where}: rewards / objectives {r['agents'].view(np.float32)} vs {o['agents'].view(np.float32)}"
+    assert r["col"].shape == o["col"].shape, f"{where}: collider count"
+    if len(r["col"]):
+        # an axis-aligned box reaches Bullet with Matrix4::rotation() of its scene-graph matrix, whose diagonal is s * (1 / s): that
+        # is 1 or 1 - 1ulp.  The oracle treats such boxes as exactly axis aligned; rotated ones (maze walls) must agree bit for bit.
+        aligned = (o["col"][:, 6] == np.float32(1).view(np.uint32)) & (o["col"][:, 7] == 0)
+        rx = r["col"][:, 6:8].copy().view(np.float32)
+        assert np.all(np.abs(rx[aligned] - np.float32([1, 0])) <= 6e-8), f"{where}: an axis-aligned collider is not"
+        r = dict(r); r["col"] = r["col"].copy(); r["col"][aligned, 6:8] = o["col"][aligned, 6:8]
+    for k in ("inst", "col"):
+        assert r[k].shape == o[k].shape, f"{where}: {k} count {r[k].shape[0]} vs {o[k].shape[0]}"
+        if not np.array_equal(r[k], o[k]):
+            bad = np.nonzero((r[k] != o[k]).any(axis=1))[0]
+            raise AssertionError(f"{where}: {k} rows {bad[:8]} of {len(r[k])} differ, first ref {r[k][bad[0]]} oracle {o[k][bad[0]]}")
+
+
+def _cosim(R, O, scenario, A, seed, max_ticks, episodes=2, params=None, warp_every=0):
+    import helpers
+    import orc
+
+    params = params or {}
+    keys = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+    vals = (C.c_float * max(1, len(params)))(*[float(v) for v in params.values()])
+    o = orc.Oracle(scenario, 1, A, params=params, render=False)
+    rh = R.ref_scen_create(scenario.encode(), A, keys, vals, len(params))
+    assert rh
+    stats = {"ticks": 0, "reward_events": 0, "dones": 0, "teleports": 0}
+    try:
+        o.seed_env(0, seed)
+        R.ref_scen_seed(rh, seed)
+        rng = np.random.default_rng(seed)
+        poses = np.zeros(33 * A, np.float32)
+        for ep in range(episodes):
+            O.orc_scen_reset(o.h_, 0)
+            sp_r, sp_o = np.zeros(4 * A, np.uint32), np.zeros(4 * A, np.uint32)
+            R.ref_scen_reset_begin(rh, MAZE_SEED_XOR, sp_r.ctypes.data)
+            O.orc_scen_spawns(o.h_, 0, sp_o.ctypes.data)
+            assert np.array_equal(sp_r, sp_o), f"{scenario} ep {ep}: spawn arguments {sp_r.view(np.float32)} vs {sp_o.view(np.float32)}"
+            O.orc_scen_poses(o.h_, 0, poses.ctypes.data)
+            R.ref_scen_reset_end(rh, poses.ctypes.data)
+            _scen_same(_scen_dump(R.ref_scen_dump, rh), _scen_dump(O.orc_scenario_dump, o.h_, 0), f"{scenario} A={A} seed={seed} ep={ep} reset")
+            last = None
+            for t in range(max_ticks):
+                if warp_every and last is not None and t % warp_every == warp_every - 1:
+                    # drop agents beside random drawables (objects, boxes, rewards, walls ...) so that the scripted walk interacts
+                    # with the level far more often than it would on foot
+                    world = last["inst"][last["inst"][:, 14].view(np.float32) < 400]
+                    special = world[(world[:, 0] != 0) | (world[:, 1] == 0x3A7FA6)]  # rewards, objects, pillars; Sokoban's boxes
+                    for a in range(A):
+                        if rng.random() < 0.7:
+                            pool = special if len(special) and rng.random() < 0.6 else world
+                            m = pool[rng.integers(len(pool)), 2:].view(np.float32)
+                            if scenario == "Sokoban":  # the cell next to a box, facing one of the four directions
+                                k = int(rng.integers(4))
+                                dx, dz = [(1.5, 0), (-1.5, 0), (0, 1.5), (0, -1.5)][k]
+                                yaw = float(rng.integers(4)) * np.pi / 2
+                                O.orc_scen_warp(o.h_, 0, a, float(m[12] + dx), float(m[13] + 1.4), float(m[14] + dz), yaw)
+                            else:
+                                O.orc_scen_warp(o.h_, 0, a, float(m[12] + rng.uniform(-0.8, 0.8)), float(m[13] + 1.2), float(m[14] + rng.uniform(-0.8, 0.8)),
+                                                float(rng.uniform(0, 2 * np.pi)))
+                if scenario == "Rearrange" and ep == 0 and not warp_every:
+                    acts = helpers.rearrange_controller(o, 0, A)
+                else:
+                    acts = np.asarray(helpers.purposeful_actions(rng, A, t), np.int32)
+                acts = np.ascontiguousarray(acts, np.int32)
+                if scenario == "Sokoban" and warp_every:
+                    acts |= 1 << 8  # keep pushing
+                O.orc_scen_step(o.h_, 0, acts.ctypes.data)
+                O.orc_scen_poses(o.h_, 0, poses.ctypes.data)
+                tp_r, tp_o = np.zeros(4 * A, np.uint32), np.zeros(4 * A, np.uint32)
+                R.ref_scen_step(rh, acts.ctypes.data, poses.ctypes.data, tp_r.ctypes.data)
+                O.orc_scen_teleports(o.h_, 0, tp_o.ctypes.data)
+                assert np.array_equal(tp_r, tp_o), f"{scenario} ep {ep} t {t}: teleports {tp_r} vs {tp_o}"
+                r, d = _scen_dump(R.ref_scen_dump, rh), _scen_dump(O.orc_scenario_dump, o.h_, 0)
+                _scen_same(r, d, f"{scenario} A={A} seed={seed} ep={ep} t={t}")
+                stats["ticks"] += 1
+                stats["reward_events"] += int((r["agents"].view(np.float32)[0::3] != 0).sum())
+                stats["teleports"] += int(tp_r[0::4].sum())
+                last = r
+                if r["done"]:
+                    stats["dones"] += 1
+                    break
+    finally:
+        o.close()
+        R.ref_scen_destroy(rh)
+    return stats
+
+
+@pytest.mark.parametrize("scenario,A,seed,ticks", [
+    ("TowerBuilding", 1, 3, 1400), ("TowerBuilding", 4, 17, 500),
+    ("ObstaclesEasy", 2, 5, 600), ("ObstaclesMedium", 1, 9, 600), ("ObstaclesHard", 3, 13, 600),
+    ("ObstaclesWalls", 2, 21, 300), ("ObstaclesSteps", 2, 22, 300), ("ObstaclesLava", 2, 23, 300),
+    ("Collect", 1, 4, 1200), ("Collect", 4, 8, 500),
+    ("Sokoban", 1, 6, 700), ("Sokoban", 2, 12, 400),
+    ("Rearrange", 1, 10, 900), ("Rearrange", 3, 11, 400),
+    ("HexExplore", 1, 14, 700), ("HexExplore", 4, 15, 300),
+    ("HexMemory", 1, 16, 900), ("HexMemory", 2, 18, 400),
+])
+def test_real_scenario_sources_match_the_oracle_tick_by_tick(scen_libs, scenario, A, seed, ticks):
+    R, O = scen_libs
+    stats = _cosim(R, O, scenario, A, seed, ticks)
+    assert stats["ticks"] > 0
+
+
+@pytest.mark.parametrize("scenario,A,seed,ticks,warp", [
+    ("TowerBuilding", 1, 3, 1400, 25), ("TowerBuilding", 4, 17, 500, 25),
+    ("ObstaclesEasy", 2, 5, 600, 25), ("ObstaclesHard", 3, 13, 600, 25),
+    ("Collect", 4, 8, 500, 25),
+    ("Sokoban", 2, 9, 700, 12), ("Sokoban", 1, 4, 700, 12),
+    ("Rearrange", 2, 10, 600, 25),
+    ("HexExplore", 1, 14, 700, 25),
+    ("HexMemory", 1, 16, 900, 25), ("HexMemory", 2, 18, 400, 25),
+])
+def test_real_scenario_sources_match_the_oracle_with_agents_dropped_next_to_things(scen_libs, scenario, A, seed, ticks, warp):
+    """same comparison on 40-second episodes (the timer runs out inside the window) with agents put beside random objects, boxes and
+    rewards every `warp` ticks: pick-ups, placements, pushes, collections and both ways of finishing an episode all occur"""
+    R, O = scen_libs
+    stats = _cosim(R, O, scenario, A, seed, ticks, warp_every=warp, params={"episodeLengthSec": 40.0})
+    assert stats["reward_events"] + stats["dones"] > 0, stats
