@@ -742,8 +742,8 @@ __device__ __forceinline__ float tsElem(float tx, float ty, float tz, float sx, 
 }
 
 // ---------------------------------------------------------------- render inputs (K3): instance list + view matrices
-// Model matrices are the drawables' absoluteTransformationMatrix() as SceneGraph::Object::setClean(objects) composes
-// them: right to left up the parent chain (v4r_env_renderer.cpp:319-335).
+// Model matrices are the drawables' absoluteTransformationMatrix() (v4r_env_renderer.cpp:52-55), which Magnum evaluates as
+// compose(parent.absoluteTransformation(), transformation()) -- left to right from the scene root (SceneGraph/Object.hpp:114-117).
 __device__ __forceinline__ void putInstance(MvInstance &d, const M4 &m, int mesh, int color) {
     storeM4(d.model, m);
     d.mesh = mesh; d.color = color; d.pad[0] = 0; d.pad[1] = 0;
