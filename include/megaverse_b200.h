@@ -50,6 +50,14 @@ int32_t mv_encode_action(const int32_t *heads6);
 /* MegaverseGym::step -> VectorEnv::step (vector_env.cpp:89-108): physics + scenario logic, reset of finished envs, render.
  * Synchronous: on return observations / rewards / dones are in host memory. */
 int mv_step(mv_handle h);
+/* mv_step in two halves, for a double-buffered consumer (two engines of half the envs each, the arrangement Sample Factory's
+ * sampler uses with two env groups per worker: while the policy looks at group A, group B steps).  mv_step_begin uploads the
+ * action masks and enqueues the kernels and the device->host copies, then returns; mv_step_end waits for them and does the
+ * episode bookkeeping -- on return the host buffers are valid exactly as after mv_step.  With option "zero_copy" 0 the
+ * observation tensor travels by the copy engine, which overlaps with the other engine's kernels.  Any other call that needs a
+ * finished step (mv_reset, mv_step_device, mv_fetch_obs) ends an outstanding begin first; a second begin is MV_ERR_STATE. */
+int mv_step_begin(mv_handle h);
+int mv_step_end(mv_handle h);
 
 /* MegaverseGym::getObservation (megaverse.cpp:139-143): uint8[N][h][w][4] RGBA, view index env*A+agent, host memory */
 int mv_obs_host(mv_handle h, const uint8_t **out);

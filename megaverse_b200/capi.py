@@ -29,7 +29,7 @@ def lib():
         L.mv_create.argtypes = [C.c_char_p, ci, ci, ci, ci, ci, ci, C.POINTER(C.c_char_p), C.POINTER(cf), ci, C.POINTER(vp)]
         L.mv_last_error.argtypes = [vp]
         L.mv_last_error.restype = C.c_char_p
-        for name in ("mv_reset", "mv_step", "mv_close", "mv_sync", "mv_fetch_obs"):
+        for name in ("mv_reset", "mv_step", "mv_step_begin", "mv_step_end", "mv_close", "mv_sync", "mv_fetch_obs"):
             getattr(L, name).argtypes = [vp]
         L.mv_seed.argtypes = [vp, ci]
         L.mv_seed_env.argtypes = [vp, ci, ci]
@@ -56,7 +56,7 @@ def lib():
 
 
 EXPORTS = [
-    "mv_create", "mv_last_error", "mv_seed", "mv_seed_env", "mv_reset", "mv_set_actions", "mv_encode_action", "mv_step", "mv_obs_host", "mv_depth_host",
+    "mv_create", "mv_last_error", "mv_seed", "mv_seed_env", "mv_reset", "mv_set_actions", "mv_encode_action", "mv_step", "mv_step_begin", "mv_step_end", "mv_obs_host", "mv_depth_host",
     "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device",
     "mv_sync", "mv_fetch_obs", "mv_draw_hires", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
@@ -106,6 +106,17 @@ class Engine:
         assert m.size == self.N
         self._ck(lib().mv_set_actions(self._h, m.ctypes.data))
         self._ck(lib().mv_step(self._h))
+
+    def step_begin(self, masks):
+        """first half of step(): upload the masks, enqueue kernels and device->host copies, return at once"""
+        m = np.ascontiguousarray(masks, dtype=np.int32)
+        assert m.size == self.N
+        self._ck(lib().mv_set_actions(self._h, m.ctypes.data))
+        self._ck(lib().mv_step_begin(self._h))
+
+    def step_end(self):
+        """second half: wait; obs() / rewards() / dones() are then valid as after step()"""
+        self._ck(lib().mv_step_end(self._h))
 
     def step_device(self, d_masks_ptr=None):
         self._ck(lib().mv_step_device(self._h, C.c_void_p(d_masks_ptr) if d_masks_ptr else None))

@@ -122,6 +122,7 @@ struct mv_engine {
     int triCap = 1024, chunkViews = 0;
     std::atomic<int> maxItemsSeen{0}, maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
+    bool hostStepPending = false;  // between mv_step_begin and mv_step_end
     bool zeroCopy = true;  // host-facing steps: the tile kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
     bool rasterToHost = false;
     int numSMs = 148;
@@ -458,7 +459,7 @@ struct mv_engine {
         else { cudaEventElapsedTime(&lastMs[0], ev[0], ev[1]); cudaEventElapsedTime(&lastMs[1], ev[1], ev[2]); }
     }
 
-    int finishStep(bool copyObs) {
+    int finishStep(bool copyObs, bool wait = true) {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
@@ -466,6 +467,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
+        if (!wait) return MV_OK;
         MV_CUDA(cudaStreamSynchronize(stream));
         if (pipelineHost || progressiveNow) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
@@ -494,6 +496,7 @@ struct mv_engine {
     // because an env cannot finish twice within four steps (doneWithTimer leaves 0.3 s = 4.5 steps, scenario.hpp:114-117)
     int stepAsync(const int32_t *dActions) {
         if (!didReset) { setError("mv_step_device before mv_reset"); return MV_ERR_STATE; }
+        if (hostStepPending) { const int rcp = stepEnd(); if (rcp) return rcp; }
         Pending &slotP = ring[asyncSteps % 3];
         // levels generated since the previous call go up first (done at step k-3 -> retired at call k-1 -> uploaded ahead
         // of kernel k; that env cannot flip again before step k+1), then step k-2 is retired and its regeneration jobs
@@ -517,8 +520,9 @@ struct mv_engine {
         return MV_OK;
     }
 
-    int stepCommon(const int32_t *dActions, bool copyObs) {
+    int stepCommon(const int32_t *dActions, bool copyObs, bool split = false) {
         if (!didReset) { setError("mv_step before mv_reset"); return MV_ERR_STATE; }
+        if (hostStepPending) { setError("mv_step_begin is outstanding: call mv_step_end first"); return MV_ERR_STATE; }
         int rc = drain();
         if (rc) return rc;
         rc = flushUploads();
@@ -532,8 +536,20 @@ struct mv_engine {
         progressiveNow = copyObs && !zeroCopy && !pipelineHost && progressive && waitValue32 != nullptr && N >= 2 * progSlices;
         rc = launchStep(dActions, false);
         if (rc) return rc;
-        rc = finishStep(copyObs);
+        rc = finishStep(copyObs, !split);
         if (rc) return rc;
+        if (split) { hostStepPending = true; return MV_OK; }
+        afterFlip(h_dones.p);
+        return MV_OK;
+    }
+    // second half of a split host-facing step (mv_step_begin / mv_step_end): wait for the copies enqueued by stepCommon(split)
+    int stepEnd() {
+        if (!hostStepPending) { setError("mv_step_end without mv_step_begin"); return MV_ERR_STATE; }
+        MV_CUDA(cudaStreamSynchronize(stream));
+        if (pipelineHost || progressiveNow) MV_CUDA(cudaStreamSynchronize(copyStream));
+        readKernelTimes();
+        hostStepPending = false;
+        std::memset(h_actions.p, 0, sizeof(int32_t) * N);  // env.cpp:140-142: actions are cleared after every step
         afterFlip(h_dones.p);
         return MV_OK;
     }
@@ -749,6 +765,7 @@ int mv_reset(mv_handle h) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     ensureMirrors(h);
+    if (h->hostStepPending) { const int rcp = h->stepEnd(); if (rcp) return rcp; }
     if (h->didReset) { const int rcd = h->drain(); if (rcd) return rcd; }
     if (!h->didReset) {
         // initial device state: slot 1 / episode -1 so that the forced flip lands on (slot 0, episode 0)
@@ -800,6 +817,19 @@ int mv_step(mv_handle h) {
     return rc;
 }
 
+int mv_step_begin(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    if (cudaMemcpyAsync(h->d_actions.p, h->h_actions.p, sizeof(int32_t) * h->N, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("actions upload failed"); return MV_ERR_CUDA; }
+    return h->stepCommon(h->d_actions.p, h->obsToHost, true);
+}
+
+int mv_step_end(mv_handle h) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    return h->stepEnd();
+}
+
 int mv_step_device(mv_handle h, const int32_t *d_masks) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
@@ -845,6 +875,7 @@ int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
 int mv_fetch_obs(mv_handle h) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    if (h->hostStepPending) { const int rcp = h->stepEnd(); if (rcp) return rcp; }
     const int rc = h->drain();
     if (rc) return rc;
     const size_t px = size_t(h->N) * h->W * h->H;

@@ -65,4 +65,46 @@ inline void yawBasis(float angle, float rows[9]) {
     rows[6] = xz - wy; rows[7] = yz + wx; rows[8] = 1.0f - (xx + yy);
 }
 
+// btMatrix3x3::setRotation(q) / getRotation(q) (scalar paths) on row-major 3x3s
+inline void rowsFromQuat(const float q[4], float rows[9]) {
+    const float dd = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const float k = 2.0f / dd;
+    const float xs = q[0] * k, ys = q[1] * k, zs = q[2] * k;
+    const float wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    const float xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    const float yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    rows[0] = 1.0f - (yy + zz); rows[1] = xy - wz; rows[2] = xz + wy;
+    rows[3] = xy + wz; rows[4] = 1.0f - (xx + zz); rows[5] = yz - wx;
+    rows[6] = xz - wy; rows[7] = yz + wx; rows[8] = 1.0f - (xx + yy);
+}
+inline void quatFromRows(const float m[9], float q[4]) {
+    const float trace = m[0] + m[4] + m[8];
+    if (trace > 0.0f) {
+        float s = sqrtf(trace + 1.0f);
+        q[3] = s * 0.5f;
+        s = 0.5f / s;
+        q[0] = (m[7] - m[5]) * s;
+        q[1] = (m[2] - m[6]) * s;
+        q[2] = (m[3] - m[1]) * s;
+    } else {
+        const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        float s = sqrtf(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0f);
+        q[i] = s * 0.5f;
+        s = 0.5f / s;
+        q[3] = (m[k * 3 + j] - m[j * 3 + k]) * s;
+        q[j] = (m[j * 3 + i] + m[i * 3 + j]) * s;
+        q[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+    }
+}
+// the ghost basis a freshly spawned agent ends up with: btQuaternion(Y, angle) -> matrix (agent.cpp:42-44), then the character
+// controller's constructor (setUp -> setGravity -> setUpVector, kinematic_character_controller.cpp:148,646-651,727-749) reads the
+// rotation back as a quaternion, multiplies by the identity correction and stores the matrix again -- not always a no-op in float
+inline void spawnBasis(float angle, float rows[9]) {
+    float first[9], q[4];
+    yawBasis(angle, first);
+    quatFromRows(first, q);
+    rowsFromQuat(q, rows);
+}
+
 }  // namespace mvh

@@ -445,7 +445,7 @@ void LevelGenerator::generateTower(LevelOut &out) {
     // DefaultScenario::spawnAgents
     for (int i = 0; i < A; ++i) {
         const float yaw = frand(rng) * 3.14159265358979323846f * 2;
-        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        mvh::spawnBasis(yaw, L.spawn_basis[i]);
         const float sx = float(agentSpawn[i].x) + 0.5f, sy = float(agentSpawn[i].y) + 0.0f, sz = float(agentSpawn[i].z) + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         L.init_pos[i][0] = float(agentSpawn[i].x); L.init_pos[i][1] = float(agentSpawn[i].y); L.init_pos[i][2] = float(agentSpawn[i].z);
@@ -551,7 +551,7 @@ void LevelGenerator::generateRearrange(LevelOut &out) {
         }
     for (int i = 0; i < A; ++i) {
         const float yaw = frand(rng) * 3.14159265358979323846f * 2;
-        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        mvh::spawnBasis(yaw, L.spawn_basis[i]);
         const float sx = float(agentPos[size_t(i)].x) + 0.5f, sy = float(agentPos[size_t(i)].y) + 0.0f, sz = float(agentPos[size_t(i)].z) + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         L.init_pos[i][0] = float(agentPos[size_t(i)].x); L.init_pos[i][1] = float(agentPos[size_t(i)].y); L.init_pos[i][2] = float(agentPos[size_t(i)].z);
@@ -732,7 +732,7 @@ void LevelGenerator::generateSokoban(LevelOut &out) {
     agentPos.resize(size_t(A), std::array<float, 3>{0, 0, 0});
     for (int i = 0; i < A; ++i) {  // DefaultScenario::spawnAgents
         const float yaw = frand(rng) * 3.14159265358979323846f * 2;
-        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        mvh::spawnBasis(yaw, L.spawn_basis[i]);
         const float sx = agentPos[size_t(i)][0] + 0.5f, sy = agentPos[size_t(i)][1] + 0.0f, sz = agentPos[size_t(i)][2] + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         for (int a = 0; a < 3; ++a) L.init_pos[i][a] = agentPos[size_t(i)][size_t(a)];
@@ -996,7 +996,7 @@ void LevelGenerator::generateHexExplore(LevelOut &out) {
     if (spawn.empty()) spawn.assign(size_t(A), std::array<float, 3>{0, 1, 0});
     for (int i = 0; i < A; ++i) {  // DefaultScenario::spawnAgents
         const float yaw = frand(rng) * 3.14159265358979323846f * 2;
-        yawBasis(yaw, L.spawn_basis[i]);
+        spawnBasis(yaw, L.spawn_basis[i]);
         const float sx = spawn[size_t(i)][0] + 0.5f, sy = spawn[size_t(i)][1] + 0.0f, sz = spawn[size_t(i)][2] + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         for (int a = 0; a < 3; ++a) L.init_pos[i][a] = spawn[size_t(i)][size_t(a)];
@@ -1056,7 +1056,7 @@ void LevelGenerator::generateHexMemory(LevelOut &out) {
     const float rot = float(2 * M_PI / A);
     for (int i = 0; i < A; ++i) {
         const float p[3] = {sinf(rot * float(i)) * 1.5f, float(0.3) * 1.5f, cosf(rot * float(i)) * 1.5f};
-        yawBasis(rot * i, L.spawn_basis[i]);
+        spawnBasis(rot * i, L.spawn_basis[i]);
         const float sx = p[0] + 0.5f, sy = p[1] + 0.0f, sz = p[2] + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         for (int a = 0; a < 3; ++a) L.init_pos[i][a] = p[a];
@@ -1264,7 +1264,7 @@ void LevelGenerator::generateCollect(LevelOut &out) {
     // DefaultScenario::spawnAgents
     for (int i = 0; i < A; ++i) {
         const float yaw = frand(rng) * 3.14159265358979323846f * 2;
-        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        mvh::spawnBasis(yaw, L.spawn_basis[i]);
         const float sx = float(agentSpawn[size_t(i)].x) + 0.5f, sy = float(agentSpawn[size_t(i)].y) + 0.0f, sz = float(agentSpawn[size_t(i)].z) + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         L.init_pos[i][0] = float(agentSpawn[size_t(i)].x); L.init_pos[i][1] = float(agentSpawn[size_t(i)].y); L.init_pos[i][2] = float(agentSpawn[size_t(i)].z);
@@ -1674,7 +1674,7 @@ void LevelGenerator::generateObstacles(LevelOut &out) {
     // DefaultScenario::spawnAgents
     for (int i = 0; i < A; ++i) {
         const float yaw = frand(rng) * 3.14159265358979323846f * 2;
-        mvh::yawBasis(yaw, L.spawn_basis[i]);
+        mvh::spawnBasis(yaw, L.spawn_basis[i]);
         const float sx = float(agentSpawn[size_t(i)].x) + 0.5f, sy = float(agentSpawn[size_t(i)].y) + 0.0f, sz = float(agentSpawn[size_t(i)].z) + 0.5f;
         L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
         L.init_pos[i][0] = float(agentSpawn[size_t(i)].x); L.init_pos[i][1] = float(agentSpawn[size_t(i)].y); L.init_pos[i][2] = float(agentSpawn[size_t(i)].z);

@@ -66,6 +66,10 @@ struct Agent {
         cameraLocal = mul(mat4Translation({0, 0.41f, 0}), cameraLocal);
         pickupLocal = mul(mat4Translation({0.0f, -0.44f, -1.0f}), pickupLocal);
         kcc.basis = mat3FromQuat(quatAxisAngle({0, 1, 0}, rotationRad));
+        // KinematicCharacterController's constructor then runs setUp(up) -> setGravity -> setUpVector (kinematic_character_controller.cpp:
+        // 148,646-651,727-749): with the up axis unchanged the correcting rotation is the identity quaternion, but the ghost's basis
+        // still goes matrix -> quaternion -> matrix once (xform.getRotation(), xform.setRotation(orn)), which is not always a no-op in float
+        kcc.basis = mat3FromQuat(quatFromMat3(kcc.basis));
         kcc.pos = {startingPosition.x, startingPosition.y + agentHeight, startingPosition.z};
     }
     void updateTransform() {  // agent.cpp:73-98

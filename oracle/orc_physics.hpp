@@ -188,6 +188,32 @@ inline bool rayCapsule(Vec3 o, Vec3 d, float L, float R, float &tOut, Vec3 &nOut
     return true;
 }
 
+// broadphase, the role btRayAabb plays in btGhostObject::convexSweepTest: skip colliders whose bounds grown by the capsule
+// extents (full radius: 0.04 more than the narrow phase needs) miss the sweep segment's box
+inline bool sweepBroadphaseMiss(const Collider &c, Vec3 from, Vec3 to) {
+    Vec3 ext = c.kind == 0 ? Vec3{c.h.x + kCapsuleRadius, c.h.y + (kCapsuleHalfHeight + kCapsuleRadius), c.h.z + kCapsuleRadius}
+                           : Vec3{2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius};
+    if (c.kind == 0 && c.rotated) {  // bounds of the rotated box
+        ext.x = (fabsf(c.ax) * c.h.x + fabsf(c.az) * c.h.z) + kCapsuleRadius;
+        ext.z = (fabsf(c.az) * c.h.x + fabsf(c.ax) * c.h.z) + kCapsuleRadius;
+    }
+    bool miss = false;
+    for (int ax = 0; ax < 3; ++ax) {
+        const float lo = from[ax] < to[ax] ? from[ax] : to[ax], hi = from[ax] < to[ax] ? to[ax] : from[ax];
+        if (hi < c.c[ax] - ext[ax] || lo > c.c[ax] + ext[ax]) miss = true;
+    }
+    return miss;
+}
+// narrow phase of one sweep: the agent capsule from `from` along d against one collider (see the header comment)
+inline bool sweepNarrow(const Collider &c, Vec3 from, Vec3 d, float &t, Vec3 &n) {
+    if (c.kind == 0) {
+        const bool hit = rayRoundedBox(c.toLocal(from - c.c), c.toLocal(d), Vec3{c.h.x, c.h.y + kCapsuleHalfHeight, c.h.z}, kCapsuleRadius - kAllowedCcdPenetration, t, n);
+        if (hit) n = c.toWorld(n);
+        return hit;
+    }
+    return rayCapsule(from - c.c, d, 2.0f * kCapsuleHalfHeight, 2.0f * kCapsuleRadius - kAllowedCcdPenetration, t, n);
+}
+
 // KinematicClosestNotMeConvexResultCallback (kinematic_character_controller.cpp:53-96) over all colliders.
 inline SweepHit convexSweep(const std::vector<Collider> &cols, int self, Vec3 from, Vec3 to, Vec3 filterDir, float minSlopeDot) {
     SweepHit res;
@@ -195,30 +221,10 @@ inline SweepHit convexSweep(const std::vector<Collider> &cols, int self, Vec3 fr
     for (int i = 0; i < int(cols.size()); ++i) {
         const Collider &c = cols[i];
         if (i == self || !c.enabled) continue;
-        {   // broadphase, the role btRayAabb plays in btGhostObject::convexSweepTest: skip colliders whose bounds grown by
-            // the capsule extents (full radius: 0.04 more than the narrow phase needs) miss the sweep segment's box
-            Vec3 ext = c.kind == 0 ? Vec3{c.h.x + kCapsuleRadius, c.h.y + (kCapsuleHalfHeight + kCapsuleRadius), c.h.z + kCapsuleRadius}
-                                   : Vec3{2.0f * kCapsuleRadius, 2.0f * (kCapsuleHalfHeight + kCapsuleRadius), 2.0f * kCapsuleRadius};
-            if (c.kind == 0 && c.rotated) {  // bounds of the rotated box
-                ext.x = (fabsf(c.ax) * c.h.x + fabsf(c.az) * c.h.z) + kCapsuleRadius;
-                ext.z = (fabsf(c.az) * c.h.x + fabsf(c.ax) * c.h.z) + kCapsuleRadius;
-            }
-            bool miss = false;
-            for (int ax = 0; ax < 3; ++ax) {
-                const float lo = from[ax] < to[ax] ? from[ax] : to[ax], hi = from[ax] < to[ax] ? to[ax] : from[ax];
-                if (hi < c.c[ax] - ext[ax] || lo > c.c[ax] + ext[ax]) miss = true;
-            }
-            if (miss) continue;
-        }
+        if (sweepBroadphaseMiss(c, from, to)) continue;
         float t;
         Vec3 n;
-        bool hit;
-        if (c.kind == 0) {
-            hit = rayRoundedBox(c.toLocal(from - c.c), c.toLocal(d), Vec3{c.h.x, c.h.y + kCapsuleHalfHeight, c.h.z}, kCapsuleRadius - kAllowedCcdPenetration, t, n);
-            if (hit) n = c.toWorld(n);
-        } else
-            hit = rayCapsule(from - c.c, d, 2.0f * kCapsuleHalfHeight, 2.0f * kCapsuleRadius - kAllowedCcdPenetration, t, n);
-        if (!hit) continue;
+        if (!sweepNarrow(c, from, d, t, n)) continue;
         if (!(t < res.fraction)) continue;             // btCollisionWorld: castResult.m_fraction < m_closestHitFraction
         if (dot(filterDir, n) < minSlopeDot) continue;  // slope filter
         res.hit = true;

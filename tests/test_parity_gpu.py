@@ -317,6 +317,59 @@ def test_async_device_loop_matches_oracle(built):
     o.close(); g.close()
 
 
+@pytest.mark.parametrize("zero_copy", [1, 0])
+def test_split_host_step_matches_oracle(built, zero_copy):
+    """mv_step_begin / mv_step_end (the double-buffered consumer's call pair): two engines holding the two halves of the env range
+    step alternately -- begin on one while the other's result is read -- and every delivered frame / reward / done equals the
+    oracle's, across episode turnovers; the protocol errors are MV_ERR_STATE"""
+    import orc
+    from megaverse_b200 import capi
+
+    E, A, steps = 16, 2, 150
+    params = {"episodeLengthSec": -33.0}
+    half = E // 2
+    gs = []
+    for k in range(2):
+        e = capi.Engine("TowerBuilding", half, A, 128, 72, num_threads=2, params=params)
+        e.set_option("fast_shading", 0)
+        e.set_option("zero_copy", zero_copy)
+        gs.append(e)
+    o = orc.Oracle("TowerBuilding", E, A, params=params)
+    for e in range(E):  # Env::seed per env, the same value on both sides
+        o.seed_env(e, 1000 + e)
+        gs[e // half].seed_env(e % half, 1000 + e)
+    o.reset()
+    for e in gs:
+        e.reset()
+    rng = np.random.default_rng(9)
+    with pytest.raises(capi.MegaverseError):
+        gs[0].step_end()  # nothing outstanding
+    ndone = 0
+    acts = helpers.purposeful_actions(rng, E * A, 0)
+    for k in range(2):
+        gs[k].step_begin(acts[k * half * A:(k + 1) * half * A])
+    with pytest.raises(capi.MegaverseError):
+        gs[0].step_begin(acts[:half * A])  # already begun
+    for t in range(steps):
+        o.step(acts)
+        ndone += int(o.dones().sum())
+        nxt = helpers.purposeful_actions(rng, E * A, t + 1)
+        for k in range(2):
+            gs[k].step_end()
+            sl = slice(k * half * A, (k + 1) * half * A)
+            assert np.array_equal(o.rewards()[sl].view(np.uint32), np.array(gs[k].rewards()).view(np.uint32)), "step %d group %d" % (t, k)
+            assert np.array_equal(o.dones()[k * half:(k + 1) * half], np.array(gs[k].dones())), "step %d group %d" % (t, k)
+            assert np.array_equal(o.obs()[sl], np.array(gs[k].obs())), "frames, step %d group %d" % (t, k)
+            if t + 1 < steps:
+                gs[k].step_begin(nxt[sl])
+        acts = nxt
+    assert ndone >= 2
+    for e in gs:
+        assert e.faults() == 0
+        e.close()
+    o.close()
+
+
 @pytest.mark.parametrize("A", [1, 3])
 def test_rearrange_reset_parity(built, A):
     """Rearrange: target arrangement (static colliders + sphere / capsule / cylinder / box drawables), its interactive copy,

@@ -547,3 +547,112 @@ def test_real_scenario_sources_match_the_oracle_with_agents_dropped_next_to_thin
     R, O = scen_libs
     stats = _cosim(R, O, scenario, A, seed, ticks, warp_every=warp, params={"episodeLengthSec": 40.0})
     assert stats["reward_events"] + stats["dones"] > 0, stats
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's WHOLE env library running on its own (oracle/_ref/libmvenv.so): env.cpp, agent.cpp, the character controller,
+# RigidBody / MotionState and every scenario source, compiled unmodified against a stand-in for the absent Bullet
+# (oracle/ref_shim/mini_bullet: LinearMath and the world's containers restated, narrow phase = the oracle's analytic definitions).
+# No puppets here: the reference's own kinematics drive its agents; the oracle has to follow bit for bit, tick after tick.
+ENVLIB = os.path.join(ROOT, "oracle", "_ref", "libmvenv.so")
+
+
+@pytest.fixture(scope="module")
+def env_libs(built):
+    import orc
+
+    if not os.path.exists(ENVLIB):
+        if os.path.isdir("/root/reference/src/libs/env"):
+            import subprocess
+
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "envlib"])
+        else:
+            pytest.skip("oracle/_ref/libmvenv.so not built and /root/reference absent")
+    R, O = C.CDLL(ENVLIB), orc.lib()
+    R.ref_env_create.restype = C.c_void_p
+    R.ref_env_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    R.ref_env_destroy.argtypes = [C.c_void_p]
+    R.ref_env_seed.argtypes = [C.c_void_p, C.c_int]
+    R.ref_env_reset.argtypes = [C.c_void_p, C.c_uint]
+    R.ref_env_step.argtypes = [C.c_void_p, C.c_void_p]
+    R.ref_env_warp.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    R.ref_env_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    O.orc_scen_reset.argtypes = [C.c_void_p, C.c_int]
+    O.orc_scen_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    O.orc_scen_warp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
+    O.orc_scenario_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    return R, O
+
+
+def _full_run(R, O, scenario, A, seed, max_ticks, episodes=2, params=None, warp_every=0):
+    import helpers
+    import orc
+
+    params = params or {}
+    keys = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+    vals = (C.c_float * max(1, len(params)))(*[float(v) for v in params.values()])
+    o = orc.Oracle(scenario, 1, A, params=params, render=False)
+    rh = R.ref_env_create(scenario.encode(), A, keys, vals, len(params))
+    assert rh
+    stats = {"ticks": 0, "reward_events": 0, "dones": 0}
+    try:
+        o.seed_env(0, seed)
+        R.ref_env_seed(rh, seed)
+        rng = np.random.default_rng(seed)
+        for ep in range(episodes):
+            O.orc_scen_reset(o.h_, 0)
+            R.ref_env_reset(rh, MAZE_SEED_XOR)
+            last = _scen_dump(R.ref_env_dump, rh)
+            _scen_same(last, _scen_dump(O.orc_scenario_dump, o.h_, 0), f"{scenario} A={A} seed={seed} ep={ep} reset")
+            for t in range(max_ticks):
+                if warp_every and t % warp_every == warp_every - 1:
+                    world = last["inst"][last["inst"][:, 14].view(np.float32) < 400]
+                    special = world[(world[:, 0] != 0) | (world[:, 1] == 0x3A7FA6)]
+                    for a in range(A):
+                        if rng.random() < 0.7:
+                            pool = special if len(special) and rng.random() < 0.6 else world
+                            m = pool[rng.integers(len(pool)), 2:].view(np.float32)
+                            if scenario == "Sokoban":
+                                dx, dz = [(1.5, 0), (-1.5, 0), (0, 1.5), (0, -1.5)][int(rng.integers(4))]
+                                pos = (float(m[12] + dx), float(m[13] + 1.4), float(m[14] + dz), float(rng.integers(4)) * np.pi / 2)
+                            else:
+                                pos = (float(m[12] + rng.uniform(-0.8, 0.8)), float(m[13] + 1.2), float(m[14] + rng.uniform(-0.8, 0.8)), float(rng.uniform(0, 2 * np.pi)))
+                            O.orc_scen_warp(o.h_, 0, a, *pos)
+                            R.ref_env_warp(rh, a, *pos)
+                if scenario == "Rearrange" and ep == 0 and not warp_every:
+                    acts = helpers.rearrange_controller(o, 0, A)
+                else:
+                    acts = np.asarray(helpers.purposeful_actions(rng, A, t), np.int32)
+                acts = np.ascontiguousarray(acts, np.int32)
+                if scenario == "Sokoban" and warp_every:
+                    acts |= 1 << 8
+                O.orc_scen_step(o.h_, 0, acts.ctypes.data)
+                R.ref_env_step(rh, acts.ctypes.data)
+                last = _scen_dump(R.ref_env_dump, rh)
+                _scen_same(last, _scen_dump(O.orc_scenario_dump, o.h_, 0), f"{scenario} A={A} seed={seed} ep={ep} t={t}")
+                stats["ticks"] += 1
+                stats["reward_events"] += int((last["agents"].view(np.float32)[0::3] != 0).sum())
+                if last["done"]:
+                    stats["dones"] += 1
+                    break
+    finally:
+        o.close()
+        R.ref_env_destroy(rh)
+    return stats
+
+
+@pytest.mark.parametrize("scenario,A,seed,ticks,warp,params", [
+    ("TowerBuilding", 1, 3, 1400, 0, None), ("TowerBuilding", 4, 17, 600, 0, None), ("TowerBuilding", 2, 31, 700, 25, {"episodeLengthSec": 40.0}),
+    ("ObstaclesEasy", 2, 5, 600, 0, None), ("ObstaclesMedium", 1, 9, 800, 0, None), ("ObstaclesHard", 3, 13, 600, 0, None),
+    ("ObstaclesHard", 2, 14, 700, 25, {"episodeLengthSec": 40.0}),
+    ("ObstaclesWalls", 2, 21, 300, 0, None), ("ObstaclesSteps", 2, 22, 300, 0, None), ("ObstaclesLava", 2, 23, 500, 0, None),
+    ("Collect", 1, 4, 1200, 0, None), ("Collect", 4, 8, 600, 25, {"episodeLengthSec": 40.0}),
+    ("Sokoban", 1, 6, 700, 0, None), ("Sokoban", 2, 9, 700, 12, {"episodeLengthSec": 40.0}),
+    ("Rearrange", 1, 10, 900, 0, None), ("Rearrange", 2, 10, 600, 25, {"episodeLengthSec": 40.0}),
+    ("HexExplore", 1, 14, 700, 0, None), ("HexExplore", 2, 19, 700, 25, {"episodeLengthSec": 40.0}),
+    ("HexMemory", 1, 16, 900, 0, None), ("HexMemory", 2, 18, 500, 25, {"episodeLengthSec": 40.0}),
+])
+def test_reference_env_library_on_stand_in_bullet_matches_the_oracle(env_libs, scenario, A, seed, ticks, warp, params):
+    R, O = env_libs
+    stats = _full_run(R, O, scenario, A, seed, ticks, params=params, warp_every=warp)
+    assert stats["ticks"] > 0
