@@ -1,0 +1,119 @@
+"""Generates tests/golden/ref_env_golden.npz from the REFERENCE's own env library (oracle/_ref/libmvenv.so: env.cpp, agent.cpp, the
+character controller and every scenario source of /root/reference compiled in place on the Bullet stand-in of
+oracle/ref_shim/mini_bullet -- see oracle/ref_shim/env_shim.cpp for what is real and what is stand-in).  Needs /root/reference (to
+build that library), so it runs in the build container only; the fixture travels.
+
+For every case: E independent reference envs (Env::seed(1000 + i)), driven like VectorEnv::step drives them (vector_env.cpp:30-108:
+step, read rewards / done / true objective, reset the finished ones), T ticks of scripted actions.  Stored per tick and env: the
+action masks, rewards, done flags, true objectives, the number of drawables and a CRC-32 of the whole drawable list after the tick
+([mesh type, 24-bit colour, 16 matrix bit patterns] per drawable, draw order).  tests replay the actions on the oracle (CPU suite) and
+on the device engine (GPU suite) and compare all of it bit for bit.
+
+    python tests/golden/make_ref_golden.py
+"""
+import ctypes as C
+import os
+import sys
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(HERE))
+os.environ.setdefault("BOXOBAN_LEVELS", os.path.join(HERE, "boxoban"))
+import helpers  # noqa: E402
+
+MAZE_SEED_XOR = 0x6D617A65
+CASES = [  # scenario, agents, envs, ticks, params
+    ("TowerBuilding", 2, 4, 240, {"episodeLengthSec": -33.0}),
+    ("ObstaclesHard", 1, 4, 240, {}),
+    ("Collect", 2, 4, 240, {"episodeLengthSec": -2.0}),
+    ("Sokoban", 1, 3, 200, {"episodeLengthSec": 8.0}),
+    ("Rearrange", 2, 3, 200, {"episodeLengthSec": 8.0}),
+    ("HexExplore", 1, 2, 160, {"episodeLengthSec": 6.0}),
+    ("HexMemory", 2, 2, 160, {"episodeLengthSec": 4.0}),
+]
+
+
+def load():
+    lib = os.path.join(ROOT, "oracle", "_ref", "libmvenv.so")
+    if not os.path.exists(lib):
+        import subprocess
+
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "envlib"])
+    R = C.CDLL(lib)
+    R.ref_env_create.restype = C.c_void_p
+    R.ref_env_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    R.ref_env_destroy.argtypes = [C.c_void_p]
+    R.ref_env_seed.argtypes = [C.c_void_p, C.c_int]
+    R.ref_env_reset.argtypes = [C.c_void_p, C.c_uint]
+    R.ref_env_step.argtypes = [C.c_void_p, C.c_void_p]
+    R.ref_env_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    return R
+
+
+def dump(R, h, buf):
+    n = R.ref_env_dump(h, buf.ctypes.data, len(buf))
+    assert n > 0
+    d = buf[:n]
+    A = int(d[3])
+    i = 4 + 3 * A
+    n_inst = int(d[i])
+    inst = d[i + 1:i + 1 + 18 * n_inst]
+    return {"done": int(d[1]), "agents": d[4:4 + 3 * A].view(np.float32).reshape(A, 3).copy(), "n_inst": n_inst, "crc": zlib.crc32(inst.tobytes())}
+
+
+def main():
+    R = load()
+    buf = np.zeros(1 << 20, np.uint32)
+    out = {}
+    for scenario, A, E, T, params in CASES:
+        keys = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
+        vals = (C.c_float * max(1, len(params)))(*[float(v) for v in params.values()])
+        envs = []
+        for e in range(E):
+            h = R.ref_env_create(scenario.encode(), A, keys, vals, len(params))
+            R.ref_env_seed(h, 1000 + e)
+            R.ref_env_reset(h, MAZE_SEED_XOR)
+            envs.append(h)
+        rng = np.random.default_rng(77)
+        acts = np.zeros((T, E, A), np.int32)
+        rew = np.zeros((T, E, A), np.float32)
+        tobj = np.zeros((T, E, A), np.float32)
+        done = np.zeros((T, E), np.uint8)
+        ninst = np.zeros((T + 1, E), np.int32)
+        crc = np.zeros((T + 1, E), np.uint32)
+        for e, h in enumerate(envs):
+            d = dump(R, h, buf)
+            ninst[0, e], crc[0, e] = d["n_inst"], d["crc"]
+        for t in range(T):
+            a = np.asarray(helpers.purposeful_actions(rng, E * A, t), np.int32).reshape(E, A)
+            acts[t] = a
+            for e, h in enumerate(envs):
+                row = np.ascontiguousarray(a[e])
+                R.ref_env_step(h, row.ctypes.data)
+                d = dump(R, h, buf)
+                rew[t, e] = d["agents"][:, 0]
+                done[t, e] = d["done"]
+                if d["done"]:  # VectorEnv::step: true objectives are read on the last frame, then the env is reset
+                    tobj[t, e] = d["agents"][:, 2]
+                    R.ref_env_reset(h, MAZE_SEED_XOR)
+                    d = dump(R, h, buf)
+                ninst[t + 1, e], crc[t + 1, e] = d["n_inst"], d["crc"]
+        for h in envs:
+            R.ref_env_destroy(h)
+        key = scenario
+        out[key + "/meta"] = np.array([A, E, T], np.int32)
+        out[key + "/param_keys"] = np.array(list(params.keys()), dtype="U32")
+        out[key + "/param_vals"] = np.array(list(params.values()), np.float32)
+        out[key + "/actions"], out[key + "/rewards"], out[key + "/true_objectives"] = acts, rew, tobj
+        out[key + "/dones"], out[key + "/n_inst"], out[key + "/crc"] = done, ninst, crc
+        print(scenario, "episodes finished:", int(done.sum()), "reward events:", int((rew != 0).sum()), "drawables:", ninst.min(), "..", ninst.max())
+    path = os.path.join(HERE, "ref_env_golden.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()
