@@ -15,6 +15,8 @@
 
 #include <mazes/spanningtreealgorithm.h>
 
+#include <Magnum/SceneGraph/Camera.h>
+
 #include <env/env.hpp>
 #include <env/scenario.hpp>
 #include <scenarios/scenario_collect.hpp>
@@ -114,6 +116,15 @@ void ref_env_warp(void *p, int agent, float x, float y, float z, float yaw) {
     btTransform t = ghost.getWorldTransform();
     t.setRotation(btQuaternion(btVector3(0, 1, 0), yaw));
     ghost.setWorldTransform(t);
+}
+
+// what the renderer reads per agent (v4r_env_renderer.cpp:303-314): Camera3D::cameraMatrix(), 16 floats column-major
+void ref_env_views(void *p, float *out) {
+    auto &h = *static_cast<Handle *>(p);
+    for (int i = 0; i < h.env.getNumAgents(); ++i) {
+        const auto m = h.env.getAgents()[size_t(i)]->getCamera()->cameraMatrix();
+        std::memcpy(out + 16 * i, m.data(), 64);
+    }
 }
 
 // Same layout as orc_scenario_dump (oracle/orc_api.cpp).  Floats as bit patterns.

@@ -577,6 +577,7 @@ def env_libs(built):
     R.ref_env_step.argtypes = [C.c_void_p, C.c_void_p]
     R.ref_env_warp.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
     R.ref_env_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_env_views.argtypes = [C.c_void_p, C.c_void_p]
     O.orc_scen_reset.argtypes = [C.c_void_p, C.c_int]
     O.orc_scen_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     O.orc_scen_warp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float]
@@ -630,6 +631,10 @@ def _full_run(R, O, scenario, A, seed, max_ticks, episodes=2, params=None, warp_
                 R.ref_env_step(rh, acts.ctypes.data)
                 last = _scen_dump(R.ref_env_dump, rh)
                 _scen_same(last, _scen_dump(O.orc_scenario_dump, o.h_, 0), f"{scenario} A={A} seed={seed} ep={ep} t={t}")
+                views = np.zeros((A, 16), np.float32)
+                R.ref_env_views(rh, views.ctypes.data)  # Camera3D::cameraMatrix(): what the renderer takes as the view matrix
+                for a in range(A):
+                    assert np.array_equal(views[a].view(np.uint32), o.view(0, a).view(np.uint32)), f"{scenario} ep={ep} t={t}: view matrix of agent {a}"
                 stats["ticks"] += 1
                 stats["reward_events"] += int((last["agents"].view(np.float32)[0::3] != 0).sum())
                 if last["done"]:
