@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <string>
 #include <vector>
@@ -18,7 +19,9 @@
 #include <Magnum/SceneGraph/Camera.h>
 
 #include <env/env.hpp>
+#include <env/env_renderer.hpp>
 #include <env/scenario.hpp>
+#include <env/vector_env.hpp>
 #include <scenarios/scenario_collect.hpp>
 #include <scenarios/scenario_hex_explore.hpp>
 #include <scenarios/scenario_hex_memory.hpp>
@@ -38,7 +41,12 @@ void sincosf(float x, float *s, float *c) noexcept { *s = float(std::sin(double(
 }
 
 static unsigned g_mazeSeed = 0;
-SpanningtreeAlgorithm::SpanningtreeAlgorithm() { generator = std::mt19937(g_mazeSeed); }
+static std::deque<unsigned> g_mazeSeedQueue;  // VectorEnv runs: one entry per env about to be reset, in reset order
+SpanningtreeAlgorithm::SpanningtreeAlgorithm() {
+    unsigned seed = g_mazeSeed;
+    if (!g_mazeSeedQueue.empty()) { seed = g_mazeSeedQueue.front(); g_mazeSeedQueue.pop_front(); }
+    generator = std::mt19937(seed);
+}
 
 using namespace Megaverse;
 
@@ -128,13 +136,11 @@ void ref_env_views(void *p, float *out) {
 }
 
 // Same layout as orc_scenario_dump (oracle/orc_api.cpp).  Floats as bit patterns.
-int ref_env_dump(void *p, uint32_t *out, int cap) {
-    auto &h = *static_cast<Handle *>(p);
-    auto &env = h.env;
+static int dumpEnv(Env &env, uint32_t *out, int cap) {
     std::vector<uint32_t> o;
     o.push_back(bits(env.episodeLengthSec()));
     o.push_back(env.isDone() ? 1u : 0u);
-    o.push_back(bits(h.state().currEpisodeSec));
+    o.push_back(bits((env.*get(EnvStateTag())).currEpisodeSec));
     o.push_back(uint32_t(env.getNumAgents()));
     for (int i = 0; i < env.getNumAgents(); ++i) {
         o.push_back(bits(env.getLastReward(i)));
@@ -169,5 +175,71 @@ int ref_env_dump(void *p, uint32_t *out, int cap) {
     std::copy(o.begin(), o.end(), out);
     return int(o.size());
 }
+int ref_env_dump(void *p, uint32_t *out, int cap) { return dumpEnv(static_cast<Handle *>(p)->env, out, cap); }
+
+// ---- the reference's VectorEnv (vector_env.cpp, compiled as is) over several envs, read the way MegaverseGym reads it
+// (megaverse.cpp:118-143): step(), then getLastReward per agent (zeroed by the reset of a finished env), done, trueObjectives
+namespace {
+unsigned predictedMazeSeed(Env &env, unsigned mazeSeedXor) {
+    Rng copy = env.getRng();
+    return unsigned(randRange(0, 1 << 30, copy)) ^ mazeSeedXor;
+}
+struct NullRenderer : EnvRenderer {
+    unsigned mazeSeedXor = 0;
+    void reset(Env &, int) override {}
+    // runs right after each env's step (vector_env.cpp:49-52): a finished env is about to be reset by VectorEnv::step's loop
+    void preDraw(Env &env, int) override { if (env.isDone()) g_mazeSeedQueue.push_back(predictedMazeSeed(env, mazeSeedXor)); }
+    void draw(Envs &) override {}
+    const uint8_t *getObservation(int, int) const override { return nullptr; }
+    Overview *getOverview() override { return nullptr; }
+};
+struct VecHandle {
+    Envs envs;
+    NullRenderer renderer;
+    std::unique_ptr<VectorEnv> vec;
+};
+}  // namespace
+
+void *ref_vec_create(const char *name, int numEnvs, int numAgents, const char **keys, const float *vals, int nparams, unsigned mazeSeedXor) {
+    registerScenarios();
+    FloatParams fp;
+    for (int i = 0; i < nparams; ++i) fp[keys[i]] = vals[i];
+    auto v = std::make_unique<VecHandle>();
+    for (int i = 0; i < numEnvs; ++i) v->envs.emplace_back(std::make_unique<Env>(name, numAgents, fp));
+    v->renderer.mazeSeedXor = mazeSeedXor;
+    v->vec = std::make_unique<VectorEnv>(v->envs, v->renderer, 1);
+    return v.release();
+}
+void ref_vec_destroy(void *p) {
+    auto *v = static_cast<VecHandle *>(p);
+    v->vec->close();
+    delete v;
+}
+void ref_vec_seed_env(void *p, int env, int seedValue) { static_cast<VecHandle *>(p)->envs[size_t(env)]->seed(seedValue); }
+void ref_vec_reset(void *p) {
+    auto *v = static_cast<VecHandle *>(p);
+    g_mazeSeedQueue.clear();
+    for (auto &e : v->envs) g_mazeSeedQueue.push_back(predictedMazeSeed(*e, v->renderer.mazeSeedXor));  // VectorEnv::reset resets in index order
+    v->vec->reset();
+    g_mazeSeedQueue.clear();  // (scenarios without a maze never consume their entries)
+}
+// masks[env * A + agent]; out: rewards[N], dones[E], trueObjectives[N] (valid where done)
+void ref_vec_step(void *p, const int *masks, float *rewards, uint8_t *dones, float *trueObjectives) {
+    auto *v = static_cast<VecHandle *>(p);
+    const int E = int(v->envs.size()), A = v->envs[0]->getNumAgents();
+    for (int e = 0; e < E; ++e)
+        for (int a = 0; a < A; ++a) v->envs[size_t(e)]->setAction(a, Action(masks[e * A + a]));
+    g_mazeSeedQueue.clear();
+    v->vec->step();
+    g_mazeSeedQueue.clear();
+    for (int e = 0; e < E; ++e) {
+        dones[e] = v->vec->done[size_t(e)] ? 1 : 0;
+        for (int a = 0; a < A; ++a) {
+            rewards[e * A + a] = v->envs[size_t(e)]->getLastReward(a);
+            trueObjectives[e * A + a] = v->vec->trueObjectives[size_t(e)][size_t(a)];
+        }
+    }
+}
+int ref_vec_dump(void *p, int env, uint32_t *out, int cap) { return dumpEnv(*static_cast<VecHandle *>(p)->envs[size_t(env)], out, cap); }
 
 }  // extern "C"

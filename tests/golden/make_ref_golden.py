@@ -3,8 +3,8 @@ character controller and every scenario source of /root/reference compiled in pl
 oracle/ref_shim/mini_bullet -- see oracle/ref_shim/env_shim.cpp for what is real and what is stand-in).  Needs /root/reference (to
 build that library), so it runs in the build container only; the fixture travels.
 
-For every case: E independent reference envs (Env::seed(1000 + i)), driven like VectorEnv::step drives them (vector_env.cpp:30-108:
-step, read rewards / done / true objective, reset the finished ones), T ticks of scripted actions.  Stored per tick and env: the
+For every case: E reference envs (Env::seed(1000 + i)) inside the reference's own VectorEnv (vector_env.cpp, compiled as is, null
+renderer), read the way MegaverseGym reads it (megaverse.cpp:118-143), T ticks of scripted actions.  Stored per tick and env: the
 action masks, rewards, done flags, true objectives, the number of drawables and a CRC-32 of the whole drawable list after the tick
 ([mesh type, 24-bit colour, 16 matrix bit patterns] per drawable, draw order).  tests replay the actions on the oracle (CPU suite) and
 on the device engine (GPU suite) and compare all of it bit for bit.
@@ -38,30 +38,28 @@ CASES = [  # scenario, agents, envs, ticks, params
 
 def load():
     lib = os.path.join(ROOT, "oracle", "_ref", "libmvenv.so")
-    if not os.path.exists(lib):
-        import subprocess
+    import subprocess
 
-        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "envlib"])
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "envlib"])
     R = C.CDLL(lib)
-    R.ref_env_create.restype = C.c_void_p
-    R.ref_env_create.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
-    R.ref_env_destroy.argtypes = [C.c_void_p]
-    R.ref_env_seed.argtypes = [C.c_void_p, C.c_int]
-    R.ref_env_reset.argtypes = [C.c_void_p, C.c_uint]
-    R.ref_env_step.argtypes = [C.c_void_p, C.c_void_p]
-    R.ref_env_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    R.ref_vec_create.restype = C.c_void_p
+    R.ref_vec_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int, C.c_uint]
+    R.ref_vec_destroy.argtypes = [C.c_void_p]
+    R.ref_vec_seed_env.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    R.ref_vec_reset.argtypes = [C.c_void_p]
+    R.ref_vec_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    R.ref_vec_dump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     return R
 
 
-def dump(R, h, buf):
-    n = R.ref_env_dump(h, buf.ctypes.data, len(buf))
+def drawables(R, v, e, buf):
+    n = R.ref_vec_dump(v, e, buf.ctypes.data, len(buf))
     assert n > 0
     d = buf[:n]
     A = int(d[3])
     i = 4 + 3 * A
     n_inst = int(d[i])
-    inst = d[i + 1:i + 1 + 18 * n_inst]
-    return {"done": int(d[1]), "agents": d[4:4 + 3 * A].view(np.float32).reshape(A, 3).copy(), "n_inst": n_inst, "crc": zlib.crc32(inst.tobytes())}
+    return n_inst, zlib.crc32(d[i + 1:i + 1 + 18 * n_inst].tobytes())
 
 
 def main():
@@ -71,12 +69,11 @@ def main():
     for scenario, A, E, T, params in CASES:
         keys = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
         vals = (C.c_float * max(1, len(params)))(*[float(v) for v in params.values()])
-        envs = []
+        # the reference's VectorEnv over E envs (vector_env.cpp compiled as is), seeded per env like megaverse_test_app.cpp:250-254
+        v = R.ref_vec_create(scenario.encode(), E, A, keys, vals, len(params), MAZE_SEED_XOR)
         for e in range(E):
-            h = R.ref_env_create(scenario.encode(), A, keys, vals, len(params))
-            R.ref_env_seed(h, 1000 + e)
-            R.ref_env_reset(h, MAZE_SEED_XOR)
-            envs.append(h)
+            R.ref_vec_seed_env(v, e, 1000 + e)
+        R.ref_vec_reset(v)
         rng = np.random.default_rng(77)
         acts = np.zeros((T, E, A), np.int32)
         rew = np.zeros((T, E, A), np.float32)
@@ -84,25 +81,20 @@ def main():
         done = np.zeros((T, E), np.uint8)
         ninst = np.zeros((T + 1, E), np.int32)
         crc = np.zeros((T + 1, E), np.uint32)
-        for e, h in enumerate(envs):
-            d = dump(R, h, buf)
-            ninst[0, e], crc[0, e] = d["n_inst"], d["crc"]
+        for e in range(E):
+            ninst[0, e], crc[0, e] = drawables(R, v, e, buf)
         for t in range(T):
-            a = np.asarray(helpers.purposeful_actions(rng, E * A, t), np.int32).reshape(E, A)
+            a = np.ascontiguousarray(np.asarray(helpers.purposeful_actions(rng, E * A, t), np.int32).reshape(E, A))
             acts[t] = a
-            for e, h in enumerate(envs):
-                row = np.ascontiguousarray(a[e])
-                R.ref_env_step(h, row.ctypes.data)
-                d = dump(R, h, buf)
-                rew[t, e] = d["agents"][:, 0]
-                done[t, e] = d["done"]
-                if d["done"]:  # VectorEnv::step: true objectives are read on the last frame, then the env is reset
-                    tobj[t, e] = d["agents"][:, 2]
-                    R.ref_env_reset(h, MAZE_SEED_XOR)
-                    d = dump(R, h, buf)
-                ninst[t + 1, e], crc[t + 1, e] = d["n_inst"], d["crc"]
-        for h in envs:
-            R.ref_env_destroy(h)
+            r, d, o = np.zeros(E * A, np.float32), np.zeros(E, np.uint8), np.zeros(E * A, np.float32)
+            # VectorEnv::step, then what MegaverseGym hands out (megaverse.cpp:118-143): last rewards (a finished env was reset inside
+            # step(), which zeroes them), done flags, the true objectives VectorEnv kept from the episode's last frame
+            R.ref_vec_step(v, a.ctypes.data, r.ctypes.data, d.ctypes.data, o.ctypes.data)
+            rew[t], done[t] = r.reshape(E, A), d
+            tobj[t][d != 0] = o.reshape(E, A)[d != 0]
+            for e in range(E):
+                ninst[t + 1, e], crc[t + 1, e] = drawables(R, v, e, buf)
+        R.ref_vec_destroy(v)
         key = scenario
         out[key + "/meta"] = np.array([A, E, T], np.int32)
         out[key + "/param_keys"] = np.array(list(params.keys()), dtype="U32")
