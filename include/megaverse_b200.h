@@ -143,6 +143,8 @@ int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
 int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable);
 /* host-only: colour tables of the generators + the rasteriser's palette (tests pin them against the reference's env/const.hpp) */
 int mv_debug_color_tables(uint32_t *out, int cap);
+/* host-only: default reward shaping ("R key=hexbits") and default float parameters ("P key=hexbits") of a scenario, one per line */
+int mv_debug_defaults(const char *scenario, char *out, int cap);
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);
 
 #ifdef __cplusplus

@@ -863,6 +863,26 @@ int mv_debug_color_tables(uint32_t *out, int cap) {
     return int(o.size());
 }
 
+// host-only: a scenario's default reward shaping (as mv_create builds it) and default float parameters, as text
+// "R key=bits\n" / "P key=bits\n" lines in key order, float values as 8 hex digits
+int mv_debug_defaults(const char *scenario, char *out, int cap) {
+    if (!scenario || mv::scenarioFromName(scenario) < 0) return MV_ERR_ARG;
+    std::map<std::string, float> m{{"teamSpirit", 0.0f}};
+    for (auto &kv : mv::defaultRewardShaping(scenario)) m[kv.first] = kv.second;
+    std::string text;
+    char line[160];
+    auto put = [&](char tag, const std::string &k, float v) {
+        uint32_t u; std::memcpy(&u, &v, 4);
+        std::snprintf(line, sizeof(line), "%c %s=%08x\n", tag, k.c_str(), u);
+        text += line;
+    };
+    for (auto &kv : m) put('R', kv.first, kv.second);
+    for (auto &kv : mv::defaultFloatParams(scenario)) put('P', kv.first, kv.second);
+    if (int(text.size()) + 1 > cap) return -int(text.size()) - 1;
+    std::memcpy(out, text.c_str(), text.size() + 1);
+    return int(text.size());
+}
+
 int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }

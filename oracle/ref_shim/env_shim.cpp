@@ -7,6 +7,7 @@
 //
 // One substitution, as in scen_shim.cpp: the maze library's SpanningtreeAlgorithm constructor takes its seed from the test.
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <deque>
@@ -124,6 +125,22 @@ void ref_env_warp(void *p, int agent, float x, float y, float z, float yaw) {
     btTransform t = ghost.getWorldTransform();
     t.setRotation(btQuaternion(btVector3(0, 1, 0), yaw));
     ghost.setWorldTransform(t);
+}
+
+// a scenario's reward shaping and float parameters right after construction, same text layout as mv_debug_defaults
+int ref_env_defaults(void *p, char *out, int cap) {
+    auto &h = *static_cast<Handle *>(p);
+    std::string text;
+    char line[160];
+    auto put = [&](char tag, const std::string &k, float v) {
+        std::snprintf(line, sizeof(line), "%c %s=%08x\n", tag, k.c_str(), bits(v));
+        text += line;
+    };
+    for (auto &kv : h.env.getScenario().getRewardShaping(0)) put('R', kv.first, kv.second);
+    for (auto &kv : h.env.getScenario().getFloatParams()) put('P', kv.first, kv.second);
+    if (int(text.size()) + 1 > cap) return -int(text.size()) - 1;
+    std::memcpy(out, text.c_str(), text.size() + 1);
+    return int(text.size());
 }
 
 // what the renderer reads per agent (v4r_env_renderer.cpp:303-314): Camera3D::cameraMatrix(), 16 floats column-major

@@ -661,3 +661,31 @@ def test_reference_env_library_on_stand_in_bullet_matches_the_oracle(env_libs, s
     R, O = env_libs
     stats = _full_run(R, O, scenario, A, seed, ticks, params=params, warp_every=warp)
     assert stats["ticks"] > 0
+
+
+@pytest.mark.parametrize("scenario", ["TowerBuilding", "ObstaclesEasy", "ObstaclesMedium", "ObstaclesHard", "ObstaclesWalls", "ObstaclesSteps", "ObstaclesLava",
+                                      "Collect", "Sokoban", "Rearrange", "HexExplore", "HexMemory"])
+def test_default_reward_shaping_and_parameters_match_the_reference_scenarios(env_libs, scenario):
+    """Scenario::init() of the real scenario classes (reward shaping incl. teamSpirit, float parameters) against the tables the product
+    builds its engine from (host-only accessor, no GPU needed)"""
+    from megaverse_b200 import capi
+
+    R, _ = env_libs
+    R.ref_env_defaults.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    rh = R.ref_env_create(scenario.encode(), 2, None, None, 0)
+    buf = C.create_string_buffer(8192)
+    assert R.ref_env_defaults(rh, buf, 8192) > 0
+    R.ref_env_destroy(rh)
+    ref = buf.value.decode()
+    L = capi.lib()
+    L.mv_debug_defaults.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    buf2 = C.create_string_buffer(8192)
+    assert L.mv_debug_defaults(scenario.encode(), buf2, 8192) > 0
+    ours = buf2.value.decode()
+    ref_r = sorted(l for l in ref.splitlines() if l.startswith("R "))
+    our_r = sorted(l for l in ours.splitlines() if l.startswith("R "))
+    assert ref_r == our_r, "reward shaping:\nreference %s\nproduct   %s" % (ref_r, our_r)
+    # float parameters: every parameter the reference scenario defines must exist with the same default
+    ref_p = dict(l[2:].split("=") for l in ref.splitlines() if l.startswith("P "))
+    our_p = dict(l[2:].split("=") for l in ours.splitlines() if l.startswith("P "))
+    assert ref_p == {k: our_p.get(k) for k in ref_p}, "parameters:\nreference %s\nproduct   %s" % (ref_p, our_p)
