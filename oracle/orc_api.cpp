@@ -651,4 +651,20 @@ int orc_scenario_dump(void *p, int e, uint32_t *out, int cap) {
     std::copy(o.begin(), o.end(), out);
     return int(o.size());
 }
+
+// ---- fragment / vertex stage pieces for the shader pin (tests/test_ref_shim.py, oracle/ref_shim/shade_shim.cpp)
+void orc_shade(int n, const float *P3, const float *N3, const float *diffuse3, float *out3, uint8_t *outUnorm3) {
+    for (int i = 0; i < n; ++i) {
+        float Lo[3];
+        shadeFragment(P3 + 3 * i, N3 + 3 * i, diffuse3 + 3 * i, Lo);
+        for (int c = 0; c < 3; ++c) { out3[3 * i + c] = Lo[c]; outUnorm3[3 * i + c] = toUnorm8(Lo[c]); }
+    }
+}
+void orc_normal_matrix(const float *mv16, float *out9) {  // column-major 3x3, as uber.vert's normal_mat
+    Mat4 mv;
+    std::memcpy(&mv.c[0][0], mv16, 64);
+    float nm[3][3];
+    normalMatrix(mv, nm);
+    std::memcpy(out9, nm, 36);
+}
 }  // extern "C"

@@ -125,6 +125,38 @@ inline uint8_t toUnorm8(float c) {
     return uint8_t(floorf(c * 255.0f + 0.5f));
 }
 
+// The lit fragment stage, uber.frag:112-141 (non-V4R_BLINN_PHONG branch) with the one light the environment sets up: camera-space
+// position (0,4,2), colour 0.66 (v4r_env_renderer.cpp:220), specular (1,1,1), shininess 300 (:204-213).  P = interpolated camera-space
+// position, N = interpolated (unnormalised) normal, diffuse = material colour.  Pinned against the shader text itself compiled with
+// glm (oracle/ref_shim/shade_shim.cpp) by tests/test_ref_shim.py.
+inline void shadeFragment(const float P[3], const float N[3], const float diffuse[3], float Lo[3]) {
+    const float cd[3] = {-P[0], -P[1], -P[2]};
+    const float ld[3] = {0.0f + cd[0], 4.0f + cd[1], 2.0f + cd[2]};
+    const float ldi = 1.0f / sqrtf((ld[0] * ld[0] + ld[1] * ld[1]) + ld[2] * ld[2]);
+    const float nl[3] = {ld[0] * ldi, ld[1] * ldi, ld[2] * ldi};
+    const float nni = 1.0f / sqrtf((N[0] * N[0] + N[1] * N[1]) + N[2] * N[2]);
+    const float nn[3] = {N[0] * nni, N[1] * nni, N[2] * nni};
+    const float ndl = (nn[0] * nl[0] + nn[1] * nl[1]) + nn[2] * nl[2];
+    const float intensity = ndl > 0.0f ? ndl : 0.0f;
+    float spec = 0.0f;
+    if (intensity > 0.001f) {
+        // reflect(I, N) = I - 2*dot(N, I)*N with I = -nl
+        const float dni = -ndl;
+        const float refl[3] = {-nl[0] - (2.0f * dni) * nn[0], -nl[1] - (2.0f * dni) * nn[1], -nl[2] - (2.0f * dni) * nn[2]};
+        const float cdi = 1.0f / sqrtf((cd[0] * cd[0] + cd[1] * cd[1]) + cd[2] * cd[2]);
+        const float vdr = ((cd[0] * cdi) * refl[0] + (cd[1] * cdi) * refl[1]) + (cd[2] * cdi) * refl[2];
+        const float base = vdr > 0.0f ? vdr : 0.0f;
+        spec = pow300(base);
+        spec = spec < 0.0f ? 0.0f : (spec > 1.0f ? 1.0f : spec);
+    }
+    for (int c = 0; c < 3; ++c) {
+        float l = 0.33f * diffuse[c];
+        l = l + ((0.73f * diffuse[c]) * 0.66f) * intensity;
+        l = l + 1.0f * spec;
+        Lo[c] = l;
+    }
+}
+
 // Renders one view.  rgba: H*W*4 bytes; depth (optional): H*W floats = view-space w of the visible fragment, 0 where
 // nothing was drawn (V4R's own depth output: uber.vert:103-105, uber.frag:180-182, cleared to 0).
 inline void renderView(const Mat4 &view, const std::vector<Instance> &instances, int W, int H, uint8_t *rgba, float *depth) {
@@ -220,32 +252,9 @@ inline void renderView(const Mat4 &view, const std::vector<Instance> &instances,
             if (depth) depth[pi] = r;  // interpolated gl_Position.w == 1 / (sum lambda_i / w_i)
             const uint32_t rgb = uint32_t(allColors[t.color]);
             const float diffuse[3] = {float((rgb >> 16) & 255) / 255.0f, float((rgb >> 8) & 255) / 255.0f, float(rgb & 255) / 255.0f};
-            // uber.frag:112-141
-            const float cd[3] = {-P[0], -P[1], -P[2]};
-            const float ld[3] = {0.0f + cd[0], 4.0f + cd[1], 2.0f + cd[2]};
-            const float ldi = 1.0f / sqrtf((ld[0] * ld[0] + ld[1] * ld[1]) + ld[2] * ld[2]);
-            const float nl[3] = {ld[0] * ldi, ld[1] * ldi, ld[2] * ldi};
-            const float nni = 1.0f / sqrtf((N[0] * N[0] + N[1] * N[1]) + N[2] * N[2]);
-            const float nn[3] = {N[0] * nni, N[1] * nni, N[2] * nni};
-            const float ndl = (nn[0] * nl[0] + nn[1] * nl[1]) + nn[2] * nl[2];
-            const float intensity = ndl > 0.0f ? ndl : 0.0f;
-            float spec = 0.0f;
-            if (intensity > 0.001f) {
-                // reflect(I, N) = I - 2*dot(N, I)*N with I = -nl
-                const float dni = -ndl;
-                const float refl[3] = {-nl[0] - (2.0f * dni) * nn[0], -nl[1] - (2.0f * dni) * nn[1], -nl[2] - (2.0f * dni) * nn[2]};
-                const float cdi = 1.0f / sqrtf((cd[0] * cd[0] + cd[1] * cd[1]) + cd[2] * cd[2]);
-                const float vdr = ((cd[0] * cdi) * refl[0] + (cd[1] * cdi) * refl[1]) + (cd[2] * cdi) * refl[2];
-                const float base = vdr > 0.0f ? vdr : 0.0f;
-                spec = pow300(base);
-                spec = spec < 0.0f ? 0.0f : (spec > 1.0f ? 1.0f : spec);
-            }
-            for (int c = 0; c < 3; ++c) {
-                float Lo = 0.33f * diffuse[c];
-                Lo = Lo + ((0.73f * diffuse[c]) * 0.66f) * intensity;
-                Lo = Lo + 1.0f * spec;
-                o[c] = toUnorm8(Lo);
-            }
+            float Lo[3];
+            shadeFragment(P, N, diffuse, Lo);
+            for (int c = 0; c < 3; ++c) o[c] = toUnorm8(Lo[c]);
             o[3] = 255;
         }
 }

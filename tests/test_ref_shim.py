@@ -689,3 +689,74 @@ def test_default_reward_shaping_and_parameters_match_the_reference_scenarios(env
     ref_p = dict(l[2:].split("=") for l in ref.splitlines() if l.startswith("P "))
     our_p = dict(l[2:].split("=") for l in ours.splitlines() if l.startswith("P "))
     assert ref_p == {k: our_p.get(k) for k in ref_p}, "parameters:\nreference %s\nproduct   %s" % (ref_p, our_p)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The renderer's shading, from the shader's own text: oracle/_ref/libmvshade.so compiles `compute_color()` cut out of V4R's uber.frag
+# (at build time, see oracle/Makefile) with the glm vendored next to it, and the vertex stage's normal matrix with the same glm calls.
+SHADE = os.path.join(ROOT, "oracle", "_ref", "libmvshade.so")
+
+
+@pytest.fixture(scope="module")
+def shade_libs(built):
+    import orc
+
+    if not os.path.exists(SHADE):
+        if os.path.isdir("/root/reference/src/3rdparty/v4r"):
+            import subprocess
+
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "shade"])
+        else:
+            pytest.skip("oracle/_ref/libmvshade.so not built and /root/reference absent")
+    return C.CDLL(SHADE), orc.lib()
+
+
+def test_fragment_stage_matches_the_shader_text(shade_libs):
+    """uber.frag:112-141 evaluated by glm on the CPU vs the oracle's restatement: camera-space positions all over the frustum, normals of
+    any length and direction (incl. facing away and grazing), every palette colour.  The oracle computes pow(x, 300) by repeated squaring
+    and GLSL leaves pow's precision to the implementation, so the colours agree to a few float ulps of the sum, and the bytes written to
+    the R8G8B8A8_UNORM attachment to +-1 -- the bar BASELINE.json sets for RGB."""
+    R, O = shade_libs
+    rng = np.random.default_rng(3)
+    n = 200000
+    P = np.stack([rng.uniform(-40, 40, n), rng.uniform(-25, 25, n), -np.exp(rng.uniform(np.log(0.02), np.log(110), n))], 1).astype(np.float32)
+    N = (rng.normal(size=(n, 3)) * np.exp(rng.uniform(-3, 3, (n, 1)))).astype(np.float32)
+    # a share of highlights: normals close to the half-way direction between light and eye
+    k = n // 4
+    cd = -P[:k].astype(np.float64)
+    ld = np.array([0.0, 4.0, 2.0]) + cd
+    h = ld / np.linalg.norm(ld, axis=1, keepdims=True) + cd / np.linalg.norm(cd, axis=1, keepdims=True)
+    N[:k] = (h / np.linalg.norm(h, axis=1, keepdims=True) + rng.normal(scale=0.02, size=(k, 3))).astype(np.float32)
+    pal = np.array([[(c >> 16) & 255, (c >> 8) & 255, c & 255] for c in
+                    [0xffdd3c, 0x3bb372, 0x50c878, 0x2eb5d0, 0xadd8e6, 0x3a7fa6, 0x2c3e50, 0xffb400, 0xb3b3b3, 0x555555, 0x222222, 0xffffff, 0xff0000, 0xffa770,
+                     0xd468ee, 0xffe6e6, 0xffffe6, 0xccffcc, 0xe6ecff, 0xd9d9d9, 0xf2e6ff, 0xffebcc]], np.float32) / np.float32(255.0)
+    D = np.ascontiguousarray(pal[rng.integers(len(pal), size=n)])
+    P, N = np.ascontiguousarray(P), np.ascontiguousarray(N)
+    ref, ours, ours8 = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros((n, 3), np.uint8)
+    R.ref_shade(n, C.c_void_p(P.ctypes.data), C.c_void_p(N.ctypes.data), C.c_void_p(D.ctypes.data), C.c_void_p(ref.ctypes.data))
+    O.orc_shade(n, C.c_void_p(P.ctypes.data), C.c_void_p(N.ctypes.data), C.c_void_p(D.ctypes.data), C.c_void_p(ours.ctypes.data), C.c_void_p(ours8.ctypes.data))
+    assert np.isfinite(ref).all() and np.isfinite(ours).all()
+    lit = (ref[:, 0] > 0.33 * D[:, 0] + 1e-6).mean()
+    shiny = ((ref - (0.33 * D + 0.73 * D * 0.66)).max(axis=1) > 0.01).mean()  # fragments with a visible specular term
+    assert lit > 0.3 and shiny > 0.02, (lit, shiny)
+    assert np.abs(ref - ours).max() < 2e-4, "colour difference %g" % np.abs(ref - ours).max()
+    ref8 = np.floor(np.clip(ref, 0, 1) * np.float32(255.0) + np.float32(0.5)).astype(np.int16)  # UNORM8 conversion of the attachment
+    d8 = np.abs(ref8 - ours8.astype(np.int16))
+    assert d8.max() <= 1, "byte difference %d" % d8.max()
+    assert (d8 == 0).mean() > 0.999, "share of identical bytes %.5f" % (d8 == 0).mean()
+
+
+def test_normal_matrix_matches_the_vertex_stage(shade_libs):
+    """uber.vert:86: transpose(inverse(mat3(mv))) by glm vs the oracle's normalMatrix (cofactors / determinant), on model-view matrices
+    of the kind the scene graph produces (rotation * non-uniform scale)"""
+    R, O = shade_libs
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for _ in range(3000):
+        mv = _rand_affine(rng)
+        a, b = np.zeros(9, np.float32), np.zeros(9, np.float32)
+        R.ref_normal_matrix(C.c_void_p(mv.ctypes.data), C.c_void_p(a.ctypes.data))
+        O.orc_normal_matrix(C.c_void_p(mv.ctypes.data), C.c_void_p(b.ctypes.data))
+        scale = np.abs(a).max()
+        worst = max(worst, float(np.abs(a - b).max() / scale))
+    assert worst < 2e-6, worst  # same formula, different association of the 3x3 cofactor products: a few ulps
