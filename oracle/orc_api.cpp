@@ -667,4 +667,31 @@ void orc_normal_matrix(const float *mv16, float *out9) {  // column-major 3x3, a
     normalMatrix(mv, nm);
     std::memcpy(out9, nm, 36);
 }
+
+// ---- the analytic narrow phase on its own (tests/test_cpu.py: the sweep against its definition through the distance function)
+// collider8: kind, cx, cy, cz, hx, hy, hz, yaw (kind 0 = box turned by yaw about Y, 1 = another agent's capsule)
+static Collider colliderFrom(const float *c8) {
+    Collider c;
+    c.kind = int(c8[0]);
+    c.c = {c8[1], c8[2], c8[3]};
+    c.h = {c8[4], c8[5], c8[6]};
+    if (c.kind == 0 && c8[7] != 0.0f) { c.rotated = true; c.ax = crcos(c8[7]); c.az = -crsin(c8[7]); }
+    return c;
+}
+int orc_sweep_case(const float *collider8, const float *from3, const float *to3, float *t, float *n3) {
+    const Collider c = colliderFrom(collider8);
+    const Vec3 f{from3[0], from3[1], from3[2]}, to{to3[0], to3[1], to3[2]};
+    Vec3 n{0, 0, 0};
+    float tt = 1.0f;
+    const bool hit = !sweepBroadphaseMiss(c, f, to) && sweepNarrow(c, f, to - f, tt, n);
+    *t = tt; n3[0] = n.x, n3[1] = n.y, n3[2] = n.z;
+    return hit ? 1 : 0;
+}
+float orc_capsule_distance(const float *collider8, const float *p3, float *n3) {
+    const Collider c = colliderFrom(collider8);
+    Vec3 n{0, 0, 0};
+    const float d = capsuleDistance(c, {p3[0], p3[1], p3[2]}, n);
+    n3[0] = n.x, n3[1] = n.y, n3[2] = n.z;
+    return d;
+}
 }  // extern "C"

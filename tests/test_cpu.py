@@ -230,3 +230,66 @@ def test_mesh_tables_match_reference_magnum(built):
         v, _ = orc.mesh(t)
         nrm = np.linalg.norm(v[:, 3:].view(np.float32), axis=1)
         assert np.allclose(nrm, 1.0, atol=1e-5)
+
+
+def test_analytic_sweep_agrees_with_its_definition(built):
+    """The narrow phase that stands in for Bullet's convex sweep (oracle/orc_physics.hpp header) is DEFINED as: the first t in [0,1] at
+    which the agent capsule penetrates the collider by allowedCcdPenetration (0.04); an already deeper start reports t = 0 only when
+    moving into the surface.  Checked here against the independent signed-distance function (the one recoverFromPenetration uses) by
+    dense sampling along random sweeps -- boxes axis-aligned and turned about Y, and other agents' capsules."""
+    import ctypes as C
+
+    import orc
+
+    O = orc.lib()
+    O.orc_sweep_case.argtypes = [C.c_void_p] * 5
+    O.orc_capsule_distance.argtypes = [C.c_void_p] * 3
+    O.orc_capsule_distance.restype = C.c_float
+    rng = np.random.default_rng(12)
+    n3 = np.zeros(3, np.float32)
+
+    def dist(col, p):
+        p = np.ascontiguousarray(p, np.float32)
+        return float(O.orc_capsule_distance(col.ctypes.data, p.ctypes.data, n3.ctypes.data))
+
+    hits = misses = starts_inside = 0
+    for case in range(4000):
+        kind = 0 if rng.random() < 0.8 else 1
+        col = np.zeros(8, np.float32)
+        col[0] = kind
+        col[1:4] = rng.uniform(-2, 2, 3)
+        col[4:7] = rng.uniform(0.05, 3.0, 3)
+        col[7] = 0.0 if rng.random() < 0.5 else rng.uniform(-3.1, 3.1)
+        a = rng.normal(size=3); a /= np.linalg.norm(a)
+        reach = float(np.linalg.norm(col[4:7])) + 1.5
+        f = (col[1:4] + a * rng.uniform(0.2, 1.3) * reach).astype(np.float32)
+        to = (col[1:4] + rng.normal(size=3) * 0.6 * reach).astype(np.float32) if rng.random() < 0.7 else (f + rng.normal(size=3).astype(np.float32) * 0.3)
+        f, to = np.ascontiguousarray(f, np.float32), np.ascontiguousarray(to, np.float32)
+        t = np.zeros(1, np.float32)
+        hit = O.orc_sweep_case(col.ctypes.data, f.ctypes.data, to.ctypes.data, t.ctypes.data, n3.ctypes.data)
+        n_hit = n3.copy()
+        d = (to - f).astype(np.float64)
+        length = float(np.linalg.norm(d))
+        tol = 2e-4 + 1e-5 * reach
+        d0 = dist(col, f)
+        ts = np.linspace(0.0, 1.0, 129)
+        ds = np.array([dist(col, f + d * s) for s in ts])
+        if hit:
+            hits += 1
+            th = float(t[0])
+            assert 0.0 <= th <= 1.0
+            assert abs(float(np.linalg.norm(n_hit)) - 1.0) < 1e-4, "hit normal is not unit length"
+            if th == 0.0:  # started at or beyond the tolerance: must be moving into the surface
+                starts_inside += 1
+                assert d0 <= -0.04 + tol, (case, d0)
+                assert float(np.dot(n_hit, d)) <= 1e-6 * max(length, 1.0), (case, "t = 0 while moving away")
+            else:
+                dh = dist(col, f + d * th)
+                assert abs(dh + 0.04) < tol, (case, "distance at the hit", dh)
+                assert (ds[ts < th - 1e-3] > -0.04 - tol).all(), (case, "deeper than the tolerance before the reported hit")
+        else:
+            misses += 1
+            # never crosses the tolerance surface from outside
+            crossing = (ds[:-1] > -0.04 + tol) & (ds[1:] < -0.04 - tol)
+            assert not crossing.any(), (case, "crossed the tolerance surface without a hit", float(ds.min()))
+    assert hits > 800 and misses > 800 and starts_inside > 5, (hits, misses, starts_inside)
