@@ -31,7 +31,7 @@ OBS_BYTES = W * H * 4
 METRIC, UNIT = "agent obs/sec (whole box)", "obs/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of geomKernel + tileKernel per launch at 256 envs (profiles/r1c_summary.txt: 7.95 + 6.21
 # + 2.83 MB); the 9.4 MB of observations themselves stay in the 126 MB L2 until the consumer reads them
-NCU_DRAM_BYTES_PER_STEP = 16990000
+NCU_DRAM_BYTES_PER_STEP = 16736000  # geomKernel (7.68 MB read + 6.26 MB written) + tileKernel (2.79 MB read) per launch pair, profiles/r1h_summary.txt
 
 
 def measured_peaks():
