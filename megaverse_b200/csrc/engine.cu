@@ -625,6 +625,15 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     if (sc < 0) { g_createError = std::string("unknown scenario ") + (scenario ? scenario : "(null)"); return MV_ERR_ARG; }
     if (w <= 0 || h <= 0 || w % 32 != 0 || h % 4 != 0 || (w / 32) * (h / 4) > 128) { g_createError = "render size must be a multiple of 32x4 with at most 128 tiles"; return MV_ERR_ARG; }
     if (num_envs <= 0 || num_agents <= 0 || num_agents > MV_MAX_AGENTS) { g_createError = "bad num_envs / num_agents_per_env"; return MV_ERR_ARG; }
+    for (int i = 0; i < nparams; ++i) {
+        if (!keys || !keys[i] || !vals) { g_createError = "null parameter key / value array"; return MV_ERR_ARG; }
+        // the interactive viewer's reward-indicator HUD (scenario_default.hpp:144-160, set by viewer_app.cpp:147 only) adds drawables this
+        // engine does not draw: refuse instead of rendering frames that differ from the reference's
+        if (std::string(keys[i]) == "useUIRewardIndicators" && vals[i] > 0.0f) {
+            g_createError = "useUIRewardIndicators > 0 (the viewer's reward-indicator HUD) is not supported";
+            return MV_ERR_ARG;
+        }
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_createError = "no CUDA device: megaverse_b200 has no CPU fallback"; return MV_ERR_CUDA; }
     if (device < 0 || device >= ndev) { g_createError = "bad CUDA device ordinal"; return MV_ERR_ARG; }

@@ -41,6 +41,24 @@ def test_no_cpu_fallback(built):
     assert ei.value.code == capi.MV_ERR_ARG
 
 
+def test_argument_errors_are_reported_not_fatal(built):
+    """argument validation happens before any CUDA call, so it is testable without a device: status code + mv_last_error instead of the
+    reference's TLOG(FATAL) -> exit(-1)"""
+    from megaverse_b200 import capi
+
+    for args, kwargs, needle in (
+        (("NoSuchScenario", 1, 1), {}, "unknown scenario"),
+        (("TowerBuilding", 0, 1), {}, "num_envs"),
+        (("TowerBuilding", 1, 99), {}, "num_envs"),
+        (("TowerBuilding", 1, 1, 100, 72), {}, "render size"),
+        (("TowerBuilding", 1, 1), {"params": {"useUIRewardIndicators": 1.0}}, "useUIRewardIndicators"),
+    ):
+        with pytest.raises(capi.MegaverseError) as ei:
+            capi.Engine(*args, **kwargs)
+        assert ei.value.code == capi.MV_ERR_ARG, (args, ei.value)
+        assert needle in str(ei.value), (args, ei.value)
+
+
 def test_product_does_not_link_or_import_the_oracle(built):
     from megaverse_b200 import capi
 
