@@ -311,3 +311,27 @@ def test_analytic_sweep_agrees_with_its_definition(built):
             crossing = (ds[:-1] > -0.04 + tol) & (ds[1:] < -0.04 - tol)
             assert not crossing.any(), (case, "crossed the tolerance surface without a hit", float(ds.min()))
     assert hits > 800 and misses > 800 and starts_inside > 5, (hits, misses, starts_inside)
+
+
+@pytest.mark.parametrize("scenario,num_agents,params", [
+    ("ObstaclesEasy", 2, {"obstaclesMinNumPlatforms": 3, "obstaclesMaxNumPlatforms": 5, "obstaclesMinGap": 2, "obstaclesMaxGap": 4, "obstaclesMinLava": 2, "obstaclesMaxLava": 6,
+                          "obstaclesMinHeight": 1, "obstaclesMaxHeight": 4, "obstaclesNumAllowedMaxDifficulty": 2}),
+    ("ObstaclesHard", 3, {"obstaclesMinNumPlatforms": 1, "obstaclesMaxNumPlatforms": 3, "episodeLengthSec": 20.0}),
+    ("TowerBuilding", 8, {"episodeLengthSec": 10.0, "verticalLookLimitRad": 0.9}),
+    ("Collect", 8, {"episodeLengthSec": 30.0}),
+])
+def test_level_generation_with_custom_parameters_matches_oracle(built, scenario, num_agents, params):
+    """the same comparison under non-default float parameters (the reference's FloatParams dict of MegaverseEnv(..., params=...))"""
+    import orc
+    from megaverse_b200 import capi
+
+    for seed in range(80, 95):
+        o = orc.Oracle(scenario, 1, num_agents, params=params, render=False)
+        o.seed_env(0, seed)
+        for episode in range(2):
+            o.reset()
+            want = o.level(0)
+            got = capi.generate_level(scenario, num_agents, seed, episode, params)
+            n = len(want)
+            assert np.array_equal(want, got[:n]), "%s seed %d episode %d: first diff at %s" % (scenario, seed, episode, np.nonzero(want != got[:n])[0][:5])
+        o.close()

@@ -656,6 +656,12 @@ def _full_run(R, O, scenario, A, seed, max_ticks, episodes=2, params=None, warp_
     ("Rearrange", 1, 10, 900, 0, None), ("Rearrange", 2, 10, 600, 25, {"episodeLengthSec": 40.0}),
     ("HexExplore", 1, 14, 700, 0, None), ("HexExplore", 2, 19, 700, 25, {"episodeLengthSec": 40.0}),
     ("HexMemory", 1, 16, 900, 0, None), ("HexMemory", 2, 18, 500, 25, {"episodeLengthSec": 40.0}),
+    # non-default parameters: a wide camera pitch range, a custom obstacle course, eight agents
+    ("TowerBuilding", 2, 41, 400, 0, {"verticalLookLimitRad": 0.9}),
+    ("ObstaclesEasy", 2, 42, 500, 25, {"obstaclesMinNumPlatforms": 3, "obstaclesMaxNumPlatforms": 5, "obstaclesMinGap": 2, "obstaclesMaxGap": 4, "obstaclesMinLava": 2,
+                                       "obstaclesMaxLava": 6, "obstaclesMinHeight": 1, "obstaclesMaxHeight": 4, "obstaclesNumAllowedMaxDifficulty": 2}),
+    ("Collect", 8, 43, 300, 25, {"episodeLengthSec": 30.0}),
+    ("TowerBuilding", 8, 44, 300, 25, None),
 ])
 def test_reference_env_library_on_stand_in_bullet_matches_the_oracle(env_libs, scenario, A, seed, ticks, warp, params):
     R, O = env_libs
