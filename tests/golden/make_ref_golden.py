@@ -25,14 +25,20 @@ os.environ.setdefault("BOXOBAN_LEVELS", os.path.join(HERE, "boxoban"))
 import helpers  # noqa: E402
 
 MAZE_SEED_XOR = 0x6D617A65
-CASES = [  # scenario, agents, envs, ticks, params
-    ("TowerBuilding", 2, 4, 240, {"episodeLengthSec": -33.0}),
-    ("ObstaclesHard", 1, 4, 240, {}),
-    ("Collect", 2, 4, 240, {"episodeLengthSec": -2.0}),
-    ("Sokoban", 1, 3, 200, {"episodeLengthSec": 8.0}),
-    ("Rearrange", 2, 3, 200, {"episodeLengthSec": 8.0}),
-    ("HexExplore", 1, 2, 160, {"episodeLengthSec": 6.0}),
-    ("HexMemory", 2, 2, 160, {"episodeLengthSec": 4.0}),
+CASES = [  # case name, scenario, agents, envs, ticks, params
+    ("TowerBuilding", "TowerBuilding", 2, 4, 240, {"episodeLengthSec": -33.0}),
+    ("ObstaclesHard", "ObstaclesHard", 1, 4, 240, {}),
+    ("Collect", "Collect", 2, 4, 240, {"episodeLengthSec": -2.0}),
+    ("Sokoban", "Sokoban", 1, 3, 200, {"episodeLengthSec": 8.0}),
+    ("Rearrange", "Rearrange", 2, 3, 200, {"episodeLengthSec": 8.0}),
+    ("HexExplore", "HexExplore", 1, 2, 160, {"episodeLengthSec": 6.0}),
+    ("HexMemory", "HexMemory", 2, 2, 160, {"episodeLengthSec": 4.0}),
+    ("TowerBuilding_8agents_widepitch", "TowerBuilding", 8, 2, 200, {"verticalLookLimitRad": 0.9}),
+    ("ObstaclesEasy_custom_course", "ObstaclesEasy", 2, 3, 240, {"obstaclesMinNumPlatforms": 3, "obstaclesMaxNumPlatforms": 5, "obstaclesMinGap": 2, "obstaclesMaxGap": 4,
+                                                                "obstaclesMinLava": 2, "obstaclesMaxLava": 6, "obstaclesMinHeight": 1, "obstaclesMaxHeight": 4,
+                                                                "obstaclesNumAllowedMaxDifficulty": 2}),
+    ("ObstaclesLava", "ObstaclesLava", 2, 3, 200, {}),
+    ("Collect_8agents_short", "Collect", 8, 2, 200, {"episodeLengthSec": -4.0}),
 ]
 
 
@@ -66,7 +72,7 @@ def main():
     R = load()
     buf = np.zeros(1 << 20, np.uint32)
     out = {}
-    for scenario, A, E, T, params in CASES:
+    for key, scenario, A, E, T, params in CASES:
         keys = (C.c_char_p * max(1, len(params)))(*[k.encode() for k in params])
         vals = (C.c_float * max(1, len(params)))(*[float(v) for v in params.values()])
         # the reference's VectorEnv over E envs (vector_env.cpp compiled as is), seeded per env like megaverse_test_app.cpp:250-254
@@ -95,13 +101,13 @@ def main():
             for e in range(E):
                 ninst[t + 1, e], crc[t + 1, e] = drawables(R, v, e, buf)
         R.ref_vec_destroy(v)
-        key = scenario
+        out[key + "/scenario"] = np.array(scenario)
         out[key + "/meta"] = np.array([A, E, T], np.int32)
         out[key + "/param_keys"] = np.array(list(params.keys()), dtype="U32")
         out[key + "/param_vals"] = np.array(list(params.values()), np.float32)
         out[key + "/actions"], out[key + "/rewards"], out[key + "/true_objectives"] = acts, rew, tobj
         out[key + "/dones"], out[key + "/n_inst"], out[key + "/crc"] = done, ninst, crc
-        print(scenario, "episodes finished:", int(done.sum()), "reward events:", int((rew != 0).sum()), "drawables:", ninst.min(), "..", ninst.max())
+        print(key, "episodes finished:", int(done.sum()), "reward events:", int((rew != 0).sum()), "drawables:", ninst.min(), "..", ninst.max())
     path = os.path.join(HERE, "ref_env_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -14,7 +14,8 @@ GOLDEN = os.path.join(HERE, "golden", "ref_env_golden.npz")
 # env/const.hpp's palette in the product's / oracle's index order (pinned against the reference by tests/test_ref_shim.py)
 PALETTE = [0xffdd3c, 0x3bb372, 0x50c878, 0x2eb5d0, 0xadd8e6, 0x3a7fa6, 0x2c3e50, 0xffb400, 0xb3b3b3, 0x555555, 0x222222,
            0xffffff, 0xff0000, 0xffa770, 0xd468ee, 0xffe6e6, 0xffffe6, 0xccffcc, 0xe6ecff, 0xd9d9d9, 0xf2e6ff, 0xffebcc]
-SCENARIOS = ["TowerBuilding", "ObstaclesHard", "Collect", "Sokoban", "Rearrange", "HexExplore", "HexMemory"]
+CASES = ["TowerBuilding", "ObstaclesHard", "Collect", "Sokoban", "Rearrange", "HexExplore", "HexMemory", "TowerBuilding_8agents_widepitch",
+         "ObstaclesEasy_custom_course", "ObstaclesLava", "Collect_8agents_short"]
 
 
 def _crc(inst18):
@@ -27,16 +28,17 @@ def _crc(inst18):
     return len(rows), zlib.crc32(rows.tobytes())
 
 
-def _replay(make, scenario):
+def _replay(make, case):
     g = np.load(GOLDEN)
-    A, E, T = (int(v) for v in g[scenario + "/meta"])
-    params = {str(k): float(v) for k, v in zip(g[scenario + "/param_keys"], g[scenario + "/param_vals"])}
+    scenario = str(g[case + "/scenario"])
+    A, E, T = (int(v) for v in g[case + "/meta"])
+    params = {str(k): float(v) for k, v in zip(g[case + "/param_keys"], g[case + "/param_vals"])}
     sim = make(scenario, E, A, params)
     for e in range(E):
         sim.seed_env(e, 1000 + e)
     sim.reset()
-    acts, rew, tobj, done = g[scenario + "/actions"], g[scenario + "/rewards"], g[scenario + "/true_objectives"], g[scenario + "/dones"]
-    ninst, crc = g[scenario + "/n_inst"], g[scenario + "/crc"]
+    acts, rew, tobj, done = g[case + "/actions"], g[case + "/rewards"], g[case + "/true_objectives"], g[case + "/dones"]
+    ninst, crc = g[case + "/n_inst"], g[case + "/crc"]
 
     def check_drawables(t):
         for e in range(E):
@@ -59,21 +61,21 @@ def _replay(make, scenario):
     return int(done.sum()), int((rew != 0).sum())
 
 
-@pytest.mark.parametrize("scenario", SCENARIOS)
-def test_oracle_replays_the_reference_env_library_golden(built, scenario):
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_replays_the_reference_env_library_golden(built, case):
     import orc
 
-    _replay(lambda s, E, A, p: orc.Oracle(s, E, A, params=p, render=False), scenario)
+    _replay(lambda s, E, A, p: orc.Oracle(s, E, A, params=p, render=False), case)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("scenario", SCENARIOS)
-def test_device_replays_the_reference_env_library_golden(built, scenario):
+@pytest.mark.parametrize("case", CASES)
+def test_device_replays_the_reference_env_library_golden(built, case):
     from megaverse_b200 import capi
 
     def make(s, E, A, p):
         g = capi.Engine(s, E, A, 128, 72, num_threads=2, params=p)
         return g
 
-    _replay(make, scenario)
+    _replay(make, case)
     # the same through the asynchronous device-resident path is covered against the oracle in test_parity_gpu.py
