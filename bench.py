@@ -266,7 +266,7 @@ def main():
     achieved = N * OBS_BYTES / (ras_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": "mvr::geomKernel + mvr::tileKernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_STEP if E == ENVS_PER_GPU else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": N * OBS_BYTES, "kernel_ms": ras_ms, "step_kernel_ms": stp_ms,
-                "note": "obs-write bytes / rasteriser duration; the kernel is FP32-issue bound (per-pixel Phong shading), see DESIGN.md"}
+                "note": "obs-write bytes / rasteriser duration; the kernels are latency / issue bound on short dependent chains (3.8 triangles per 32x4 tile), not HBM bound: DESIGN.md section 10"}
     faults = eng.faults()
     eng.close()
 
