@@ -127,6 +127,14 @@ void ref_env_warp(void *p, int agent, float x, float y, float z, float yaw) {
     ghost.setWorldTransform(t);
 }
 
+// Env::actionSpaceSizes (env.cpp:33), the table MegaverseGym::setActions (megaverse.cpp:100-116) walks
+int ref_action_space_sizes(int *out, int cap) {
+    const auto &v = Env::actionSpaceSizes;
+    if (int(v.size()) > cap) return -int(v.size());
+    std::copy(v.begin(), v.end(), out);
+    return int(v.size());
+}
+
 // a scenario's reward shaping and float parameters right after construction, same text layout as mv_debug_defaults
 int ref_env_defaults(void *p, char *out, int cap) {
     auto &h = *static_cast<Handle *>(p);

@@ -766,3 +766,30 @@ def test_normal_matrix_matches_the_vertex_stage(shade_libs):
         scale = np.abs(a).max()
         worst = max(worst, float(np.abs(a - b).max() / scale))
     assert worst < 2e-6, worst  # same formula, different association of the 3x3 cofactor products: a few ulps
+
+
+def test_action_encoding_follows_the_reference_action_space(env_libs):
+    """Env::actionSpaceSizes as compiled from env.cpp, and the Action bits Env::step tests (env.hpp:22-42, through the real enum): head h
+    with choice a > 0 sets bit 1 + sum_{j<h}(size_j - 1) + (a - 1), the rule of MegaverseGym::setActions (megaverse.cpp:100-116) --
+    the product's mv_encode_action must agree for every combination"""
+    import itertools
+
+    from megaverse_b200 import capi
+
+    R, _ = env_libs
+    sizes = (C.c_int * 16)()
+    n = R.ref_action_space_sizes(sizes, 16)
+    sizes = [sizes[i] for i in range(n)]
+    assert sizes == [3, 3, 3, 2, 2, 3]
+    L = capi.lib()
+    L.mv_encode_action.argtypes = [C.c_void_p]
+    L.mv_encode_action.restype = C.c_int32
+    for heads in itertools.product(*[range(s) for s in sizes]):
+        want, base = 0, 0
+        for h, a in enumerate(heads):
+            if a > 0:
+                want |= 1 << (base + a)
+            base += sizes[h] - 1
+        arr = np.array(heads, np.int32)
+        assert L.mv_encode_action(arr.ctypes.data) == want, heads
+    assert base == 10  # bits 1..10: Left, Right, Forward, Backward, LookLeft, LookRight, Jump, Interact, LookDown, LookUp
