@@ -9,6 +9,10 @@
 //   src/libs/scenarios/src/layout_utils.cpp:17-68 (addBoundingBoxes, addTerrain)
 //   src/libs/scenarios/src/scenario_tower_building.cpp:8-266 (+ scenario_tower_building.hpp:42-52)
 //   src/libs/env/src/vector_env.cpp:89-120 (done handling)   src/libs/bindings/megaverse.cpp:60-69,100-137
+//   + the other scenario sources (obstacles, collect, sokoban, rearrange, hex_explore, hex_memory, component_hexagonal_maze), cited inline.
+// PINNED: the reference's whole env library (env.cpp, agent.cpp, kinematic_character_controller.cpp, vector_env.cpp, every scenario
+// source) is compiled in place on a Bullet stand-in (oracle/ref_shim/env_shim.cpp, mini_bullet/) and this restatement follows it bit
+// for bit, tick by tick (tests/test_ref_shim.py, tests/test_ref_golden.py).  What that leaves unpinned is stated in orc_physics.hpp.
 #pragma once
 #include <cfloat>
 #include <cstdio>

@@ -6,8 +6,10 @@
 //   :509-517 (warp), :519-526 (preStep), :528-602 (playerStep), :625-644 (jump), :679-682 (onGround),
 //   :753-792 (setAcceleration); constants kinematic_character_controller.hpp:155-177, agent.cpp:52-59.
 //
+// PINNED: the state machine below against the reference's own kinematic_character_controller.cpp, compiled in place on the Bullet
+// stand-in of ref_shim/mini_bullet and run beside this file tick by tick (tests/test_ref_shim.py).
 // The collision arithmetic underneath (btGhostObject::convexSweepTest, contact manifolds) lives in
-// Bullet 2.89, which is NOT vendored under /root/reference and not installed: PARITY UNPINNED.
+// Bullet 2.89, which is NOT vendored under /root/reference and not installed: PARITY UNPINNED for that part.
 // It is replaced by an exact analytic definition with the same contract:
 //   * sweep(upright capsule, from->to) vs a box = first t in [0,1] at which the capsule PENETRATES the
 //     box by `allowedCcdPenetration` (Bullet world default 0.04) -- i.e. a ray against the box grown by the

@@ -7,7 +7,9 @@
 //   output layout              RGBA8 rows top-down, view index = env*A + agent (v4r_env_renderer.cpp:357-361)
 // The fixed-function part (clip, 8-bit sub-pixel snap, top-left rule, perspective-correct varyings) follows the
 // Vulkan specification's rasterisation rules; the reference's actual GPU is not observable here (PARITY UNPINNED
-// for pixels: the north star allows +-1 LSB per channel against real V4R frames).
+// for assembled frames: the north star allows +-1 LSB per channel against real V4R frames).  PINNED: shadeFragment against the
+// shader's own compute_color() text compiled with glm, normalMatrix against the vertex stage's glm expression, the view matrices
+// against Magnum's Camera feature, the model matrices against the reference's scene graph (tests/test_ref_shim.py).
 #pragma once
 #include <cstdint>
 #include <cstring>
