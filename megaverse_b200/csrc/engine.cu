@@ -123,6 +123,7 @@ struct mv_engine {
     std::atomic<int> maxItemsSeen{0}, maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
     bool hostStepPending = false;  // between mv_step_begin and mv_step_end
+    bool cullInstances = false;    // option "cull": instance-level frustum culling + block compaction in the geometry kernel
     bool zeroCopy = true;  // host-facing steps: the tile kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
     bool rasterToHost = false;
     int numSMs = 148;
@@ -334,10 +335,12 @@ struct mv_engine {
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = 1;
                 cfg.attrs = attr; cfg.numAttrs = 1;
-                MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::geomKernel, rp));
+                if (cullInstances) MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::geomKernel<true>, rp));
+                else MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::geomKernel<false>, rp));
             } else {
                 rp.ready = nullptr; rp.readyStamp = 0;
-                mvr::geomKernel<<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+                if (cullInstances) mvr::geomKernel<true><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+                else mvr::geomKernel<false><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
             }
             MV_CUDA(cudaGetLastError());
             const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * mvr::kTileBlocksPerSM);  // persistent blocks of 4 warps
@@ -414,7 +417,8 @@ struct mv_engine {
         for (int base = 0; base < N; base += hires.chunk) {
             const int cv = std::min(hires.chunk, N - base);
             rp.viewBase = base; rp.chunkViews = cv;
-            mvr::geomKernel<<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+            if (cullInstances) mvr::geomKernel<true><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
+            else mvr::geomKernel<false><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
             MV_CUDA(cudaGetLastError());
             const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * mvr::kTileBlocksPerSM);
             if (fastShading) mvr::tileKernel<true><<<tileBlocks, 128, 0, stream>>>(rp);
@@ -729,6 +733,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
+    if (k == "cull") { h->cullInstances = value != 0; return MV_OK; }
     if (k == "progressive") { h->progressive = value != 0; return MV_OK; }
     if (k == "progressive_slices") { if (value < 1 || value > 32) return MV_ERR_ARG; cudaDeviceSynchronize(); h->progSlices = value; cudaMemset(h->d_sliceDone.p, 0, 128); std::memset(h->sliceTarget, 0, sizeof h->sliceTarget); return MV_OK; }
     if (k == "host_slices") { if (value < 1 || value > 64) return MV_ERR_ARG; h->hostSlices = value; return MV_OK; }
@@ -1203,7 +1208,7 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
         rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.viewBase = 0; rp.chunkViews = 1;
         rp.N = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
         const int items = nBox * 6 + (n - nBox) * 128;  // upper bound
-        mvr::geomKernel<<<dim3(unsigned((items + 127) / 128 + 1), 1), 128>>>(rp);
+        mvr::geomKernel<false><<<dim3(unsigned((items + 127) / 128 + 1), 1), 128>>>(rp);
         mvr::tileKernel<false><<<((w / 32) * (h / 4) + 3) / 4, 128>>>(rp);
         ok = cudaDeviceSynchronize() == cudaSuccess;
         if (ok) {

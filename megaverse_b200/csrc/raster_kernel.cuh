@@ -239,12 +239,32 @@ __device__ __forceinline__ ClipVert makeVert(const M4 &mv, const float nm[9], V3
 #ifndef MV_GEOM_BLOCKS
 #define MV_GEOM_BLOCKS 4
 #endif
+// Conservative instance-level frustum test (option "cull", off by default): the bounding sphere of the instance's mesh in view space
+// against the near plane and the four side planes.  Unit meshes span |x|,|z| <= 1 and |y| <= 1 (capsule: 2), so a vertex lies within
+// bx*|col0| + by*|col1| + bz*|col2| of the instance origin.  An instance that fails contributes no fragment (clipAndSetup would have
+// clipped or scissored every one of its triangles), so frames do not change.
+__device__ __forceinline__ bool instanceMayBeVisible(const M4 &mv, float by, float p00, float p11) {
+    const float l0 = sqrtf(mv.c[0] * mv.c[0] + mv.c[1] * mv.c[1] + mv.c[2] * mv.c[2]);
+    const float l1 = sqrtf(mv.c[4] * mv.c[4] + mv.c[5] * mv.c[5] + mv.c[6] * mv.c[6]);
+    const float l2 = sqrtf(mv.c[8] * mv.c[8] + mv.c[9] * mv.c[9] + mv.c[10] * mv.c[10]);
+    const float r = (l0 + by * l1 + l2) * 1.001f + 1e-3f;
+    const float x = mv.c[12], y = mv.c[13], z = mv.c[14];
+    if (-z - 0.01f < -r) return false;  // wholly in front of the near plane (camera looks down -z)
+    // side planes x_clip = +-w_clip, y_clip = +-w_clip with x_clip = p00 * x, y_clip = p11 * y, w_clip = -z: inward unit normals
+    const float ix = rsqrtf(p00 * p00 + 1.0f), iy = rsqrtf(p11 * p11 + 1.0f);
+    const float ax = fabsf(p00), ay = fabsf(p11);
+    if ((-ax * x - z) * ix < -r || (ax * x - z) * ix < -r) return false;
+    if ((-ay * y - z) * iy < -r || (ay * y - z) * iy < -r) return false;
+    return true;
+}
+
+template <bool CULL>
 __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P) {
     const int vslot = blockIdx.y;
     const int view = P.viewBase + vslot;
     if (view >= P.N) return;
     const int env = view / P.A;
-    const int item = blockIdx.x * blockDim.x + threadIdx.x;
+    int item = blockIdx.x * blockDim.x + threadIdx.x;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.tileCounter = 0;  // for the tile kernel that follows in-stream
     // Launched with programmatic stream serialisation this grid starts while the step kernel is still running: each block
     // waits for its own env's completion stamp (release/acquire through L2) instead of for the whole step grid, so the
@@ -273,7 +293,9 @@ __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P
     const int nBoxInst = cnt[0];
     const int nBoxItems = nBoxInst * 6;
     const int capItems = cnt[2] * MV_CAPSULE_TRIS, sphItems = cnt[3] * MV_SPHERE_TRIS, coneItems = cnt[4] * MV_CONE_TRIS, cylItems = cnt[5] * MV_CYLINDER_TRIS;
-    if (item >= nBoxItems + capItems + sphItems + coneItems + cylItems) return;
+    if (!CULL) {
+        if (item >= nBoxItems + capItems + sphItems + coneItems + cylItems) return;
+    }
 
     SetupCtx cx;
     cx.cover = P.cover + size_t(vslot) * P.triCap;
@@ -295,6 +317,54 @@ __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P
     for (int i = 0; i < 4; ++i) {
         const float4 col = __ldcg(reinterpret_cast<const float4 *>(P.views + size_t(view) * 16) + i);
         viewM.c[i * 4 + 0] = col.x; viewM.c[i * 4 + 1] = col.y; viewM.c[i * 4 + 2] = col.z; viewM.c[i * 4 + 3] = col.w;
+    }
+
+    if (CULL) {
+        // block-level cull + compaction: the first thread of every instance inside this block's 128 items tests the instance, the
+        // survivors' items are packed to the front, and whole warps beyond them retire before any vertex work
+        __shared__ uint8_t s_vis[128];
+        __shared__ uint8_t s_items[128];
+        __shared__ int s_warpCount[4];
+        const int total = nBoxItems + capItems + sphItems + coneItems + cylItems;
+        if (int(blockIdx.x * blockDim.x) >= total) return;  // block-uniform
+        auto instanceOf = [&](int it, int &sub, float &by) {
+            by = 1.0f;
+            if (it < nBoxItems) { sub = it % 6; return it / 6; }
+            int rest = it - nBoxItems;
+            if (rest < capItems) { sub = rest % MV_CAPSULE_TRIS; by = 2.0f; return nBoxInst + rest / MV_CAPSULE_TRIS; }
+            if ((rest -= capItems) < sphItems) { sub = rest % MV_SPHERE_TRIS; return nBoxInst + cnt[2] + rest / MV_SPHERE_TRIS; }
+            if ((rest -= sphItems) < coneItems) { sub = rest % MV_CONE_TRIS; return nBoxInst + cnt[2] + cnt[3] + rest / MV_CONE_TRIS; }
+            rest -= coneItems;
+            sub = rest % MV_CYLINDER_TRIS;
+            return nBoxInst + cnt[2] + cnt[3] + cnt[4] + rest / MV_CYLINDER_TRIS;
+        };
+        const bool valid = item < total;
+        int sub0 = 0, sub = 0;
+        float by0 = 1.0f, by = 1.0f;
+        const int ii0 = instanceOf(int(blockIdx.x * blockDim.x), sub0, by0);
+        const int ii = valid ? instanceOf(item, sub, by) : ii0;
+        if (valid && (sub == 0 || threadIdx.x == 0)) {
+            M4 model;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
+                model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
+            }
+            s_vis[ii - ii0] = instanceMayBeVisible(mul4(viewM, model), by, P.p00, P.p11) ? 1 : 0;
+        }
+        __syncthreads();
+        const bool alive = valid && s_vis[ii - ii0] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, alive);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) s_warpCount[warp] = __popc(bal);
+        __syncthreads();
+        int base = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { if (w < warp) base += s_warpCount[w]; tot += s_warpCount[w]; }
+        if (alive) s_items[base + __popc(bal & ((1u << lane) - 1u))] = uint8_t(threadIdx.x);
+        __syncthreads();
+        if (int(threadIdx.x) >= tot) return;
+        item = int(blockIdx.x * blockDim.x) + int(s_items[threadIdx.x]);
     }
 
     if (item < nBoxItems) {
