@@ -265,6 +265,11 @@ __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P
     if (view >= P.N) return;
     const int env = view / P.A;
     int item = blockIdx.x * blockDim.x + threadIdx.x;
+    // CULL: per-block tables of the (at most 23) instances this block's 128 items belong to, filled by one thread per instance
+    __shared__ float s_mv[CULL ? 24 : 1][16];
+    __shared__ float s_nm[CULL ? 24 : 1][9];
+    __shared__ int s_color[CULL ? 24 : 1];
+    int cullFirst = 0;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *P.tileCounter = 0;  // for the tile kernel that follows in-stream
     // Launched with programmatic stream serialisation this grid starts while the step kernel is still running: each block
     // waits for its own env's completion stamp (release/acquire through L2) instead of for the whole step grid, so the
@@ -350,10 +355,35 @@ __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P
                 const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
                 model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
             }
-            s_vis[ii - ii0] = instanceMayBeVisible(mul4(viewM, model), by, P.p00, P.p11) ? 1 : 0;
+            const M4 mvL = mul4(viewM, model);
+            const bool vis = instanceMayBeVisible(mvL, by, P.p00, P.p11);
+            s_vis[ii - ii0] = vis ? 1 : 0;
+            if (vis) {  // the same products every item of this instance would otherwise repeat
+                float nmL[9];
+                normalMatrix(mvL, nmL);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) s_mv[ii - ii0][q] = mvL.c[q];
+#pragma unroll
+                for (int q = 0; q < 9; ++q) s_nm[ii - ii0][q] = nmL[q];
+                s_color[ii - ii0] = __ldcg(&inst[ii].color);
+            }
         }
         __syncthreads();
-        const bool alive = valid && s_vis[ii - ii0] != 0;
+        bool alive = valid && s_vis[ii - ii0] != 0;
+        if (alive && item < nBoxItems) {
+            // a box face whose plane clearly faces away from the eye (at the view-space origin) only yields triangles the
+            // rasteriser's winding test drops: outward normal n, face centre c = origin + n (unit cube), cull when n_view . c_view > 0
+            const float *m = s_mv[ii - ii0], *nmS = s_nm[ii - ii0];
+            const float *fn = c_boxVerts[sub * 4] + 3;
+            const float cxv = m[12] + (fn[0] * m[0] + fn[1] * m[4] + fn[2] * m[8]);
+            const float cyv = m[13] + (fn[0] * m[1] + fn[1] * m[5] + fn[2] * m[9]);
+            const float czv = m[14] + (fn[0] * m[2] + fn[1] * m[6] + fn[2] * m[10]);
+            const float nxv = nmS[0] * fn[0] + nmS[3] * fn[1] + nmS[6] * fn[2];
+            const float nyv = nmS[1] * fn[0] + nmS[4] * fn[1] + nmS[7] * fn[2];
+            const float nzv = nmS[2] * fn[0] + nmS[5] * fn[1] + nmS[8] * fn[2];
+            const float d = nxv * cxv + nyv * cyv + nzv * czv;
+            if (d > 1e-3f * sqrtf((nxv * nxv + nyv * nyv + nzv * nzv) * (cxv * cxv + cyv * cyv + czv * czv))) alive = false;
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, alive);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         if (lane == 0) s_warpCount[warp] = __popc(bal);
@@ -365,20 +395,31 @@ __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P
         __syncthreads();
         if (int(threadIdx.x) >= tot) return;
         item = int(blockIdx.x * blockDim.x) + int(s_items[threadIdx.x]);
+        cullFirst = ii0;
     }
 
     if (item < nBoxItems) {
         const int ii = item / 6, face = item % 6;
-        M4 model;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
-            model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
-        }
-        const int color = __ldcg(&inst[ii].color);
-        const M4 mv = mul4(viewM, model);
+        M4 mv;
         float nm[9];
-        normalMatrix(mv, nm);
+        int color;
+        if (CULL) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) mv.c[q] = s_mv[ii - cullFirst][q];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) nm[q] = s_nm[ii - cullFirst][q];
+            color = s_color[ii - cullFirst];
+        } else {
+            M4 model;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
+                model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
+            }
+            color = __ldcg(&inst[ii].color);
+            mv = mul4(viewM, model);
+            normalMatrix(mv, nm);
+        }
         ClipVert cvt[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -396,15 +437,23 @@ __global__ void __launch_bounds__(128, MV_GEOM_BLOCKS) geomKernel(RasterParams P
         else if ((rest -= capItems) < sphItems) { mesh = 2; ii += cnt[2] + rest / MV_SPHERE_TRIS; tri = rest % MV_SPHERE_TRIS; }
         else if ((rest -= sphItems) < coneItems) { mesh = 3; ii += cnt[2] + cnt[3] + rest / MV_CONE_TRIS; tri = rest % MV_CONE_TRIS; }
         else { rest -= coneItems; mesh = 4; ii += cnt[2] + cnt[3] + cnt[4] + rest / MV_CYLINDER_TRIS; tri = rest % MV_CYLINDER_TRIS; }
-        M4 model;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
-            model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
-        }
-        const M4 mv = mul4(viewM, model);
+        M4 mv;
         float nm[9];
-        normalMatrix(mv, nm);
+        if (CULL) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) mv.c[q] = s_mv[ii - cullFirst][q];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) nm[q] = s_nm[ii - cullFirst][q];
+        } else {
+            M4 model;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 col = __ldcg(reinterpret_cast<const float4 *>(inst[ii].model) + i);
+                model.c[i * 4 + 0] = col.x; model.c[i * 4 + 1] = col.y; model.c[i * 4 + 2] = col.z; model.c[i * 4 + 3] = col.w;
+            }
+            mv = mul4(viewM, model);
+            normalMatrix(mv, nm);
+        }
         ClipVert cvt[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
