@@ -335,3 +335,41 @@ def test_level_generation_with_custom_parameters_matches_oracle(built, scenario,
             n = len(want)
             assert np.array_equal(want, got[:n]), "%s seed %d episode %d: first diff at %s" % (scenario, seed, episode, np.nonzero(want != got[:n])[0][:5])
         o.close()
+
+
+def test_drop_in_surface_covers_the_reference_bindings(built):
+    """every name the reference's pybind module defines (src/libs/bindings/megaverse.cpp:267-292) exists on ours, and every public method /
+    attribute of the reference's Python MegaverseEnv (megaverse/megaverse_env.py) exists on our MegaverseEnv.  Parsed from the reference
+    sources, so it only runs where /root/reference is mounted."""
+    import ast
+    import importlib
+    import os
+    import re
+
+    bind = "/root/reference/src/libs/bindings/megaverse.cpp"
+    pyenv = "/root/reference/megaverse/megaverse_env.py"
+    if not (os.path.exists(bind) and os.path.exists(pyenv)):
+        pytest.skip("/root/reference absent")
+    names = re.findall(r'\.def\("([a-z_]+)"', open(bind).read())
+    assert len(names) >= 18
+    m = importlib.import_module("megaverse_b200.extension.megaverse")
+    for n in names:
+        assert hasattr(m, n) or hasattr(m.MegaverseGym, n), "binding %s is missing" % n
+    tree = ast.parse(open(pyenv).read())
+    cls = [c for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "MegaverseEnv"][0]
+    methods = [f.name for f in cls.body if isinstance(f, ast.FunctionDef) and not f.name.startswith("_")]
+    init = [f for f in cls.body if isinstance(f, ast.FunctionDef) and f.name == "__init__"][0]
+    ctor_args = [a.arg for a in init.args.args]
+    attrs = sorted({t.attr for n in ast.walk(init) if isinstance(n, ast.Assign) for t in n.targets
+                    if isinstance(t, ast.Attribute) and isinstance(t.value, ast.Name) and t.value.id == "self"})
+    import inspect
+
+    from megaverse_b200.megaverse_env import MegaverseEnv
+
+    for n in methods:
+        assert callable(getattr(MegaverseEnv, n, None)), "MegaverseEnv.%s is missing" % n
+    ours = list(inspect.signature(MegaverseEnv.__init__).parameters)
+    assert ours[:len(ctor_args)] == ctor_args, (ours, ctor_args)
+    src = inspect.getsource(MegaverseEnv)
+    for a in attrs:
+        assert re.search(r"self\.%s\b" % re.escape(a), src), "attribute %s is not set by our MegaverseEnv" % a
