@@ -111,6 +111,45 @@ def run_cpu(steps, warmup, threads, envs):
     return envs * AGENTS * steps / dt, dt
 
 
+def run_reference_env_library(envs, threads, seconds=4.0):
+    """simulation-only rate of the REFERENCE's own env library where its build travelled with the snapshot (oracle/_ref/pyref: the
+    reference's pybind module + env.cpp / agent.cpp / character controller / scenarios compiled in place on the Bullet stand-in, null
+    renderer -- DESIGN.md section 6).  No rendering: the reference renders on the GPU.  Returns None when the module is not there."""
+    try:
+        d = os.path.join(ROOT, "oracle", "_ref", "pyref")
+        if not os.path.isdir(d):
+            return None
+        sys.path.insert(0, d)
+        import megaverse as ref_ext
+
+        ref_ext.set_megaverse_log_level(2)
+        g = ref_ext.MegaverseGym(SCENARIO, W, H, envs, AGENTS, threads, True, {})
+        g.seed(42)
+        g.reset()
+        rng = np.random.default_rng(1)
+        heads = rng.integers(0, [3, 3, 3, 2, 2, 3], size=(64, envs * AGENTS, 6)).tolist()
+
+        def one(t):
+            row = heads[t % 64]
+            for e in range(envs):
+                for a in range(AGENTS):
+                    g.set_actions(e, a, row[e * AGENTS + a])
+            g.step()
+
+        for t in range(10):
+            one(t)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            one(n)
+            n += 1
+        dt = time.perf_counter() - t0
+        g.close()
+        return {"value": envs * AGENTS * n / dt, "unit": "agent steps/s (simulation only, no rendering)", "threads": threads, "steps": n,
+                "note": "reference env library compiled in place on the Bullet stand-in (analytic narrow phase), driven through its own pybind module"}
+    except Exception as ex:  # never let the context figure break the bench line
+        return {"unavailable": str(ex)[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,7 +362,8 @@ def main():
             ksample = int(min(20000, ksample * 15.0 / max(dt, 1e-3)))
             v, dt = run_cpu(ksample, 3, cores, E)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "%d envs x %d steps of the same workload on all %d host threads (%.1f s)" % (E, ksample, cores, dt)}
+                        "sample": "%d envs x %d steps of the same workload on all %d host threads (%.1f s)" % (E, ksample, cores, dt),
+                        "reference_env_library": run_reference_env_library(E, min(cores, 16))}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
