@@ -598,6 +598,7 @@ void orc_scen_warp(void *p, int e, int agent, float x, float y, float z, float y
     env.agents[size_t(agent)].kcc.basis = mat3FromQuat(quatAxisAngle({0, 1, 0}, yaw));  // as DefaultKinematicAgent's constructor turns it
     env.colliders[size_t(env.agentColliderBase + agent)].c = env.agents[size_t(agent)].kcc.pos;
 }
+int orc_scen_undefined_spawn(void *p, int e) { return static_cast<OrcVec *>(p)->envs[size_t(e)]->undefinedSpawn ? 1 : 0; }
 void orc_scen_spawns(void *p, int e, uint32_t *out) {  // per agent: DefaultKinematicAgent's startingPosition xyz, rotationRad
     Env &env = *static_cast<OrcVec *>(p)->envs[size_t(e)];
     for (int i = 0; i < env.numAgents; ++i) {

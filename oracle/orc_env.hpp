@@ -1045,6 +1045,11 @@ public:
         for (auto &p : platforms) vg.addPlatform(*p, layoutColor, wallColor, drawWalls);
 
         agentSpawnPositions = startPlatform->agentSpawnPoints(numAgents);
+        // ten random attempts per agent (platforms.hpp:221-244) can leave fewer spawn points than agents on a small start platform; the
+        // reference then indexes past the end of this vector in spawnAgents (scenario_default.hpp:83-91) -- undefined behaviour, whatever
+        // the heap holds.  The oracle makes it defined (the origin, what a zeroed heap gives) and remembers; the product refuses such
+        // configurations ("start platform too small for the agents"), and the parity tests stay away from them.
+        if (int(agentSpawnPositions.size()) < numAgents) { undefinedSpawn = true; agentSpawnPositions.resize(size_t(numAgents), Vec3{0, 0, 0}); }
         agentInitialPositions = agentSpawnPositions;
 
         std::vector<int> numBoxes(platforms.size());
@@ -1588,6 +1593,7 @@ public:
 
     std::vector<Agent> agents;
     std::vector<std::pair<int, Vec3>> teleportLog;  // (agent, target) of this tick's AbstractAgent::teleport calls
+    bool undefinedSpawn = false;                     // see obstaclesReset: the reference read past its spawn-point vector
     std::vector<Collider> colliders;
     int agentColliderBase = 0;
     std::vector<MovableObject> objects;
