@@ -10,7 +10,8 @@
 //   Magnum  Matrix4::rotationX                    src/3rdparty/magnum/src/Magnum/Math/Matrix4.h:991-999
 //   Bullet  btQuaternion(axis,angle), btMatrix3x3::setRotation/getRotation, btQuaternion::getAxis/getAngle
 //           -- Bullet 2.89 is NOT vendored in /root/reference; restated from the published upstream
-//           algorithm (parity unpinned).
+//           algorithm (parity unpinned for these few routines; the stand-in Bullet the reference's env library is
+//           compiled against for the pins forwards to them, see ref_shim/mini_bullet/mini_bullet.hpp and DESIGN.md section 6).
 #pragma once
 #include <cmath>
 #include <cstdint>

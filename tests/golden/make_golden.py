@@ -1,9 +1,9 @@
 """Generates tests/golden/tower_golden.npz from the ORACLE (oracle/liborc.so).
 
-The reference itself cannot run in the build container (Bullet 2.89, Vulkan and EGL are absent: SURVEY.md 8c) and its own
-tests hold no trajectory / reward / pixel golden vectors, so these goldens pin the ORACLE's behaviour over time (any change
-of the restatement's arithmetic shows up as a golden diff); the pieces of the reference that DO build here (Magnum math and
-primitives) are pinned separately by tests/test_ref_shim.py.
+These goldens pin the ORACLE's behaviour over time, frames included (any change of the restatement's arithmetic shows up as a golden
+diff).  The reference's own outputs are pinned elsewhere: tests/test_ref_shim.py runs the oracle beside the reference's env library
+compiled in place, and make_ref_golden.py / make_ref_python_golden.py write goldens FROM that build (no frames: the reference's
+renderers need Vulkan / OpenGL, which this image does not have).
 
     python tests/golden/make_golden.py
 """
