@@ -79,6 +79,9 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
  * mv_step delivers the observation tensor to host memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps
  * let the rasteriser store rows straight into the pinned host buffer instead of copying afterwards; the HBM copy returned
  * by mv_obs_device is then only refreshed by mv_step_device), "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
+ * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity -- about one Collect landscape in several
+ * thousand has more boxes than MV_MAX_STATIC -- makes mv_step / mv_reset fail with MV_ERR_CAPACITY by default, which keeps every env on
+ * the reference's level sequence; with 1 the env takes the next level of its stream instead and mv_levels_skipped counts it),
  * "cull" (0/1, default 0: per-instance frustum test, per-face back-face test and block compaction in the geometry kernel, per-instance
  * matrices shared through shared memory; the emitted triangles, hence the frames, are unchanged; +5..10 % throughput),
  * "progressive" (0/1, default 0; with zero_copy off: the tile kernel counts finished tiles per slice of views and a copy stream
@@ -147,6 +150,10 @@ int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable);
 int mv_debug_color_tables(uint32_t *out, int cap);
 /* host-only: default reward shaping ("R key=hexbits") and default float parameters ("P key=hexbits") of a scenario, one per line */
 int mv_debug_defaults(const char *scenario, char *out, int cap);
+/* host-only: number of levels among the first `episodes` of the env stream seeded env_seed that do not fit the engine's capacities */
+int mv_debug_count_unfit_levels(const char *scenario, int num_agents, int env_seed, int episodes, const char *const *keys, const float *vals, int nparams);
+/* levels replaced so far under option "skip_unfit_levels" (0 unless that option is set) */
+int mv_levels_skipped(mv_handle h);
 int mv_debug_bzset(const int32_t *ops, int nops, int32_t *out_xyz, int cap);
 
 #ifdef __cplusplus

@@ -123,6 +123,8 @@ struct mv_engine {
     std::atomic<int> maxItemsSeen{0}, maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
     bool hostStepPending = false;  // between mv_step_begin and mv_step_end
+    bool skipUnfitLevels = false;  // option "skip_unfit_levels": replace a level that exceeds a fixed capacity by the stream's next one
+    std::atomic<int> levelsSkipped{0};
     bool cullInstances = false;    // option "cull": instance-level frustum culling + block compaction in the geometry kernel
     bool zeroCopy = true;  // host-facing steps: the tile kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
     bool rasterToHost = false;
@@ -219,7 +221,12 @@ struct mv_engine {
         pool->submit([this, e, s, serial] {
             mv::LevelOut out;
             try {
-                gens[size_t(e)].generate(out, serial, gridCells);
+                if (skipUnfitLevels) {
+                    const int skipped = gens[size_t(e)].generateFitting(out, serial, gridCells);
+                    if (skipped) levelsSkipped.fetch_add(skipped);
+                } else {
+                    gens[size_t(e)].generate(out, serial, gridCells);
+                }
             } catch (const std::exception &ex) {
                 std::lock_guard<std::mutex> lk(genMutex);
                 genErrors.push_back(ex.what());
@@ -734,6 +741,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
     if (k == "cull") { h->cullInstances = value != 0; return MV_OK; }
+    if (k == "skip_unfit_levels") { h->skipUnfitLevels = value != 0; return MV_OK; }
     if (k == "progressive") { h->progressive = value != 0; return MV_OK; }
     if (k == "progressive_slices") { if (value < 1 || value > 32) return MV_ERR_ARG; cudaDeviceSynchronize(); h->progSlices = value; cudaMemset(h->d_sliceDone.p, 0, 128); std::memset(h->sliceTarget, 0, sizeof h->sliceTarget); return MV_OK; }
     if (k == "host_slices") { if (value < 1 || value > 64) return MV_ERR_ARG; h->hostSlices = value; return MV_OK; }
@@ -896,6 +904,23 @@ int mv_debug_defaults(const char *scenario, char *out, int cap) {
     std::memcpy(out, text.c_str(), text.size() + 1);
     return int(text.size());
 }
+
+// host-only: how many levels of the env stream (seed env_seed) up to and including `episode` generateFitting had to skip, or < 0
+int mv_debug_count_unfit_levels(const char *scenario, int num_agents, int env_seed, int episodes, const char *const *keys, const float *vals, int nparams) {
+    if (!scenario || mv::scenarioFromName(scenario) < 0 || num_agents < 1 || num_agents > MV_MAX_AGENTS) return MV_ERR_ARG;
+    try {
+        mv::FloatParams params = mv::defaultFloatParams(scenario);
+        for (int i = 0; i < nparams; ++i) params[keys[i]] = vals[i];
+        mv::LevelGenerator gen(scenario, num_agents, params);
+        gen.seed((unsigned long)env_seed);
+        mv::LevelOut lo;
+        int skipped = 0;
+        for (int ep = 0; ep < episodes; ++ep) skipped += gen.generateFitting(lo, ep, 1 << 30);
+        return skipped;
+    } catch (const std::exception &ex) { g_createError = ex.what(); return MV_ERR_CAPACITY; }
+}
+
+int mv_levels_skipped(mv_handle h) { return h ? h->levelsSkipped.load() : MV_ERR_ARG; }
 
 int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
     if (!h) return MV_ERR_ARG;
@@ -1237,7 +1262,7 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     mv::LevelOut lo;
     try {
         for (int ep = 0; ep <= episode; ++ep) gen.generate(lo, ep, 1 << 30);
-    } catch (const std::exception &) { return MV_ERR_CAPACITY; }
+    } catch (const std::exception &ex) { g_createError = ex.what(); return MV_ERR_CAPACITY; }  // mv_last_error(NULL) tells why
     const MvLevel &L = lo.level;
     std::vector<int32_t> o;
     o.push_back(L.n_grid_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);

@@ -310,6 +310,17 @@ LevelGenerator::LevelGenerator(const std::string &scenarioName, int numAgents, c
     }
 }
 
+int LevelGenerator::generateFitting(LevelOut &out, int serial, int gridCells, int attempts) {
+    for (int skipped = 0;; ++skipped) {
+        try {
+            generate(out, serial, gridCells);
+            return skipped;
+        } catch (const std::runtime_error &) {
+            if (skipped + 1 >= attempts) throw;
+        }
+    }
+}
+
 void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     std::memset(&out.level, 0, sizeof(MvLevel));
     out.drawSeq.clear();

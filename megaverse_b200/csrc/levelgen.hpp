@@ -34,6 +34,11 @@ public:
     // Generates the next episode's level.  gridCells = capacity of the dense grid (cells); throws std::runtime_error
     // if the level does not fit the engine's fixed capacities.
     void generate(LevelOut &out, int serial, int gridCells);
+    // Same, but a level that does not fit the engine's capacities (a few Collect landscapes in ten thousand decompose into more
+    // boxes than MV_MAX_STATIC) is replaced by the level the env's stream yields next instead of failing: up to `attempts` draws.
+    // Returns how many levels were skipped.  The env's level sequence then differs from the reference's from that episode on, which
+    // is why the engine only does this when asked to (option "skip_unfit_levels").
+    int generateFitting(LevelOut &out, int serial, int gridCells, int attempts = 8);
 
 private:
     void generateTower(LevelOut &out);

@@ -174,6 +174,7 @@ public:
     uintptr_t obsDevicePtr() { alive(); uint8_t *p; check(mv_obs_device(h__, &p)); return reinterpret_cast<uintptr_t>(p); }
     int faults() { alive(); int32_t f; check(mv_faults(h__, &f)); return f; }
     void setOption(const std::string &key, int value) { alive(); check(mv_set_option(h__, key.c_str(), value)); }
+    int levelsSkipped() { alive(); return mv_levels_skipped(h__); }
 
     void close() {
         if (h__) { mv_close(h__); h__ = nullptr; }
@@ -219,5 +220,6 @@ PYBIND11_MODULE(megaverse, m) {
         .def("get_true_objectives", &MegaverseGym::getTrueObjectives)
         .def("obs_device_ptr", &MegaverseGym::obsDevicePtr)
         .def("faults", &MegaverseGym::faults)
-        .def("set_option", &MegaverseGym::setOption);
+        .def("set_option", &MegaverseGym::setOption)
+        .def("levels_skipped", &MegaverseGym::levelsSkipped);
 }

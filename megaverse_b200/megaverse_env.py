@@ -27,6 +27,8 @@ def make_env_multitask(multitask_name, task_idx, num_envs, num_agents_per_env, n
 
 
 class MegaverseEnv(Env):
+    SKIP_UNFIT_LEVELS = True
+
     def __init__(self, scenario_name, num_envs, num_agents_per_env, num_simulation_threads, use_vulkan=False, params=None):
         scenario_name = scenario_name.casefold()
         self.scenario_name = scenario_name
@@ -49,6 +51,12 @@ class MegaverseEnv(Env):
                     raise Exception('Params of type %r not supported', type(v))
 
         self.env = MegaverseGym(self.scenario_name, self.img_w, self.img_h, num_envs, num_agents_per_env, num_simulation_threads, use_vulkan, float_params)
+        # The engine has fixed per-level capacities; about one Collect landscape in several hundred decomposes into more boxes than fit
+        # (the reference has no such limit).  The C ABI's default is to fail loudly so that every env stays on the reference's level
+        # sequence; a training run is better served by taking the next level of that env's stream instead -- counted, see
+        # `levels_skipped()`.  Set MegaverseEnv.SKIP_UNFIT_LEVELS = False before constructing for the strict behaviour.
+        if self.SKIP_UNFIT_LEVELS:
+            self.env.set_option("skip_unfit_levels", 1)
         self.default_shaping_scheme = self.env.get_reward_shaping(0, 0)
         self.action_space = self.generate_action_space(self.env.action_space_sizes())
         self.observation_space = Box(0, 255, (self.channels, self.img_h, self.img_w), dtype=np.uint8)
@@ -123,6 +131,10 @@ class MegaverseEnv(Env):
         env_idx = actor_idx // self.num_agents_per_env
         agent_idx = actor_idx % self.num_agents_per_env
         return self.env.set_reward_shaping(env_idx, agent_idx, reward_shaping)
+
+    def levels_skipped(self):
+        """(extension) levels replaced because they exceeded an engine capacity, see __init__"""
+        return self.env.levels_skipped()
 
     def close(self):
         if self.env:
