@@ -79,8 +79,7 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
  * mv_step delivers the observation tensor to host memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps
  * let the rasteriser store rows straight into the pinned host buffer instead of copying afterwards; the HBM copy returned
  * by mv_obs_device is then only refreshed by mv_step_device), "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
- * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity -- about one Collect landscape in several
- * thousand has more boxes than MV_MAX_STATIC -- makes mv_step / mv_reset fail with MV_ERR_CAPACITY by default, which keeps every env on
+ * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity -- roughly one Collect landscape in a thousand has more boxes than MV_MAX_STATIC -- makes mv_step / mv_reset fail with MV_ERR_CAPACITY by default, which keeps every env on
  * the reference's level sequence; with 1 the env takes the next level of its stream instead and mv_levels_skipped counts it),
  * "cull" (0/1, default 0: per-instance frustum test, per-face back-face test and block compaction in the geometry kernel, per-instance
  * matrices shared through shared memory; the emitted triangles, hence the frames, are unchanged; +5..10 % throughput),

@@ -51,7 +51,7 @@ class MegaverseEnv(Env):
                     raise Exception('Params of type %r not supported', type(v))
 
         self.env = MegaverseGym(self.scenario_name, self.img_w, self.img_h, num_envs, num_agents_per_env, num_simulation_threads, use_vulkan, float_params)
-        # The engine has fixed per-level capacities; about one Collect landscape in several hundred decomposes into more boxes than fit
+        # The engine has fixed per-level capacities; roughly one Collect landscape in a thousand decomposes into more boxes than fit
         # (the reference has no such limit).  The C ABI's default is to fail loudly so that every env stays on the reference's level
         # sequence; a training run is better served by taking the next level of that env's stream instead -- counted, see
         # `levels_skipped()`.  Set MegaverseEnv.SKIP_UNFIT_LEVELS = False before constructing for the strict behaviour.
