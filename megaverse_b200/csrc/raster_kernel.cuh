@@ -589,6 +589,10 @@ __device__ __forceinline__ EdgeEval loadCoverShared(const TriCover *c) {
     const int4 *cq = reinterpret_cast<const int4 *>(c);
     return unpackCover(cq[0], cq[1], cq[2], cq[3], cq[4]);
 }
+// the fragment's low word is (draw-order key << 13) | triangle-list index: key = instance * 128 + triangle-in-mesh + 1 has to stay below
+// 2^19 and the per-view triangle capacity below 2^13 -- the constraint to revisit when a capacity in mv_types.h is raised
+static_assert((MV_MAX_INSTANCES + 1) * 128 <= (1 << 19), "draw-order key does not fit beside the 13-bit triangle index");
+static_assert(MV_CAPSULE_TRIS <= 128 && MV_SPHERE_TRIS <= 128 && MV_CONE_TRIS <= 128 && MV_CYLINDER_TRIS <= 128, "triangle-in-mesh index needs 7 bits");
 __device__ __forceinline__ unsigned long long packFrag(float z, uint32_t key, int idx) {
     const uint32_t b = __float_as_uint(z);
     const uint32_t asc = b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);  // monotonic in z over all floats (tiny negative z can come out of the clipper)
