@@ -1,0 +1,118 @@
+"""GPU parity at the sizes BASELINE.json's configs are defined on.
+
+Every case runs the CUDA engine (through the C ABI) and the threaded oracle on the same seeds and the same action stream for
+>= 60 ticks with a forced early episode turnover, through BOTH the host-facing call (mv_step) and the asynchronous
+device-resident call (mv_step_device, the path bench.py times):
+
+  * rewards, done flags and true objectives bit-exact every tick (host-facing) / at every synchronisation point (async),
+  * the complete kinematic + scenario state of every env bit-exact at the end,
+  * all N frames (+ depth where the config has it) byte-exact in the exact fragment mode and within +-1 LSB per channel in
+    the production mode (fast_shading), depth bit-exact in both,
+  * no fault bit.
+
+Configs: [1] TowerBuilding 256x1, [2] ObstaclesHard 2048x1 RGB+depth, [3] Collect 1024x4, plus two sizes that straddle what
+used to be the rasteriser's view-chunk boundaries (HexExplore N > 128, Collect N just above 256).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+THREADS = max(1, min(128, os.cpu_count() or 1))
+
+# scenario, envs, agents, depth, params forcing an early turnover, ticks
+CASES = {
+    "tower_256x1": ("TowerBuilding", 256, 1, False, {"episodeLengthSec": -37.0}, 64),
+    # Obstacles episodes last max(episodeLengthSec, 35 s * platforms + objects) (scenario_obstacles.cpp:262-266): allowing levels without a
+    # middle platform (1 in 8) gives turnovers after 2.5 s while the other envs keep full-size ObstaclesHard levels
+    "obstacles_hard_2048x1_depth": ("ObstaclesHard", 2048, 1, True, {"episodeLengthSec": 2.5, "obstaclesMinNumPlatforms": 0}, 64),
+    "collect_1024x4": ("Collect", 1024, 4, False, {"episodeLengthSec": -2.0}, 64),
+    "hex_explore_72x2": ("HexExplore", 72, 2, False, {"episodeLengthSec": 2.5}, 60),
+    "collect_65x4": ("Collect", 65, 4, False, {"episodeLengthSec": -2.0}, 60),
+}
+
+
+def _make(name, fast):
+    import orc
+    from megaverse_b200 import capi
+
+    scenario, E, A, depth, params, ticks = CASES[name]
+    o = orc.Oracle(scenario, E, A, 128, 72, params=params, depth=depth, threads=THREADS, render=False)
+    g = capi.Engine(scenario, E, A, 128, 72, num_threads=min(16, THREADS), params=params, depth=depth)
+    g.set_option("fast_shading", 1 if fast else 0)
+    for e in range(E):
+        o.seed_env(e, 1000 + e)
+        g.seed_env(e, 1000 + e)
+    o.reset()
+    g.reset()
+    rng = np.random.default_rng(17)
+    acts = np.stack([helpers.purposeful_actions(rng, E * A, t) if t % 2 else helpers.random_bit_actions(rng, E * A) for t in range(ticks)]).astype(np.int32)
+    return o, g, acts, (scenario, E, A, depth, ticks)
+
+
+def _check_scalars(o, g, tag):
+    assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), tag + ": rewards"
+    assert np.array_equal(o.dones(), np.array(g.dones())), tag + ": dones"
+    assert np.array_equal(o.true_objectives().view(np.uint32), np.array(g.true_objectives()).view(np.uint32)), tag + ": true objectives"
+
+
+def _check_end(o, g, E, depth, fast, tag):
+    import orc
+
+    for e in range(E):
+        so, sg = o.state(e), g.state(e)
+        assert so.shape == sg.shape and np.array_equal(so.view(np.uint32), sg.view(np.uint32)), "%s: state of env %d" % (tag, e)
+    orc.lib().orc_render_now(o.h_)
+    a, b = o.obs(), np.array(g.obs())
+    diff = np.abs(a.astype(np.int16) - b.astype(np.int16))
+    if fast:
+        assert diff.max() <= 1, "%s: max RGB diff %d in %d pixels (views %s)" % (tag, diff.max(), int((diff > 1).sum()), np.unique(np.nonzero(diff > 1)[0])[:8])
+        assert float((diff == 0).mean()) > 0.999, tag
+    else:
+        assert diff.max() == 0, "%s: %d bytes differ (views %s)" % (tag, int((diff > 0).sum()), np.unique(np.nonzero(diff)[0])[:8])
+    if depth:
+        assert np.array_equal(o.depth().view(np.uint32), np.array(g.depth()).view(np.uint32)), tag + ": depth"
+    assert g.faults() == 0, "%s: fault bits %d" % (tag, g.faults())
+
+
+@pytest.mark.parametrize("fast", [0, 1])
+@pytest.mark.parametrize("name", list(CASES))
+def test_host_step_at_baseline_size(built, name, fast):
+    o, g, acts, (scenario, E, A, depth, ticks) = _make(name, fast)
+    ndone = 0
+    for t in range(ticks):
+        o.step(acts[t])
+        g.step(acts[t])
+        _check_scalars(o, g, "%s tick %d" % (name, t))
+        ndone += int(o.dones().sum())
+    assert ndone > 0, "the case is meant to cross an episode boundary"
+    _check_end(o, g, E, depth, fast, name)
+    o.close(); g.close()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_device_step_at_baseline_size(built, name):
+    """the asynchronous device-resident loop (what bench.py's `value` times), production shading"""
+    import torch
+
+    o, g, acts, (scenario, E, A, depth, ticks) = _make(name, 1)
+    dacts = torch.from_numpy(acts).cuda()
+    torch.cuda.synchronize()
+    ndone = 0
+    for t in range(ticks):
+        o.step(acts[t])
+        ndone += int(o.dones().sum())
+        g.step_device(dacts.data_ptr() + t * E * A * 4)
+        if t % 16 == 15:
+            g.sync()
+            _check_scalars(o, g, "%s async tick %d" % (name, t))
+    g.sync()
+    assert ndone > 0
+    _check_scalars(o, g, name + " async end")
+    g.fetch_obs()
+    _check_end(o, g, E, depth, 1, name + " async")
+    o.close(); g.close()
