@@ -75,19 +75,17 @@ int mv_true_objectives(mv_handle h, const float **out);
 int mv_get_reward_shaping(mv_handle h, int env, int agent, const char **keys, float *vals, int cap, int *n);
 int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *keys, const float *vals, int n);
 
-/* options: "depth" (0/1, before first reset), "tri_cap" (rasteriser triangle capacity), "obs_to_host" (0/1: whether
- * mv_step delivers the observation tensor to host memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps
- * let the rasteriser store rows straight into the pinned host buffer instead of copying afterwards; the HBM copy returned
- * by mv_obs_device is then only refreshed by mv_step_device), "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
- * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity -- roughly one Collect landscape in a thousand has more boxes than MV_MAX_STATIC -- makes mv_step / mv_reset fail with MV_ERR_CAPACITY by default, which keeps every env on
- * the reference's level sequence; with 1 the env takes the next level of its stream instead and mv_levels_skipped counts it),
- * "cull" (0/1, default 0: per-instance frustum test, per-face back-face test and block compaction in the geometry kernel, per-instance
- * matrices shared through shared memory; the emitted triangles, hence the frames, are unchanged; +5..10 % throughput),
- * "progressive" (0/1, default 0; with zero_copy off: the tile kernel counts finished tiles per slice of views and a copy stream
- * waits on those counters -- cuStreamWaitValue32 -- to download finished slices during the raster; "progressive_slices" 1..32),
- * "host_slices" (1..64, default 1; with zero_copy off: rasterise in that many slices and download each on a second stream --
- * measured slower than zero-copy on B200, kept for hosts without mapped pinned memory),
- * "overlap" (0/1, default 1: the geometry kernel is a programmatic dependent launch of the step kernel and synchronises per env;
+/* options: "depth" (0/1, before first reset), "obs_to_host" (0/1: whether mv_step delivers the observation tensor to host
+ * memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps let the rasteriser store rows straight into the pinned
+ * host buffer instead of copying afterwards; the HBM copy returned by mv_obs_device is then only refreshed by mv_step_device),
+ * "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
+ * "tri_cap" (32..1022, default 320: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
+ * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
+ * chosen from the number of views by default, results do not depend on it),
+ * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity makes mv_step / mv_reset fail with
+ * MV_ERR_CAPACITY by default, which keeps every env on the reference's level sequence; with 1 the env takes the next level of its
+ * stream instead and mv_levels_skipped counts it),
+ * "overlap" (0/1, default 1: the raster kernel is a programmatic dependent launch of the step kernel and synchronises per env;
  * 0 serialises the kernels so that mv_last_kernel_ms can time them separately) */
 int mv_set_option(mv_handle h, const char *key, int value);
 
@@ -143,8 +141,6 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 /* per-env cycle stamps of the step kernel's phases: out = uint32[E][16] (0 staged, 1 actions, 2 candidate list, 3 controllers,
  * 4 transforms, 5 scenario, 6 outputs/reset, 7 instance list, 8 commit, 12 candidate count); enable=1 arms it, 0 frees it */
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
-/* per-tile cost of the tile kernel: out = uint32[N][tiles][4] {cycles, overlapping triangles, lane-per-triangle count, warp-per-triangle count} */
-int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable);
 /* host-only: colour tables of the generators + the rasteriser's palette (tests pin them against the reference's env/const.hpp) */
 int mv_debug_color_tables(uint32_t *out, int cap);
 /* host-only: default reward shaping ("R key=hexbits") and default float parameters ("P key=hexbits") of a scenario, one per line */

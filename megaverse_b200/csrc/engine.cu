@@ -2,14 +2,13 @@
 // worker pool, and launches the two kernels of a step on one CUDA stream.
 //
 //   mv_step  =  [H2D actions] -> stepKernel (physics + scenario + in-kernel reset + instance lists)
-//                             -> rasterKernel (obs tensor) -> [D2H obs/rewards/dones] -> schedule next-level generation
+//                             -> viewKernel (geometry + raster + shading in shared memory -> obs tensor)
+//                             -> [D2H obs/rewards/dones] -> schedule next-level generation
 //
 // There is no host synchronisation between physics, episode reset and rendering (the reference resets finished envs
 // serially on the caller thread between the two, vector_env.cpp:94-105): every env always has its NEXT level pre-staged
 // in HBM (no RNG draw happens during an episode, so the next level only depends on the env's RNG state after the
 // previous generation), and the step kernel flips to it by itself when the episode ends.
-#include <cuda.h>
-#include <dlfcn.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -26,7 +25,7 @@
 #include "../../include/megaverse_b200.h"
 #include "hostmath.hpp"
 #include "levelgen.hpp"
-#include "raster_kernel.cuh"
+#include "raster_view.cuh"
 #include "step_kernel.cuh"
 
 namespace {
@@ -119,14 +118,13 @@ struct mv_engine {
     std::unique_ptr<WorkerPool> pool;
 
     int gridCells = 0, gridWords = 0;
-    int triCap = 1024, chunkViews = 0;
-    std::atomic<int> maxItemsSeen{0}, maxObjSeen{0};
+    int triCap = 320;              // triangle-list capacity of one raster CTA (shared memory); larger views are drawn in several batches
+    std::atomic<int> maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
     bool hostStepPending = false;  // between mv_step_begin and mv_step_end
     bool skipUnfitLevels = false;  // option "skip_unfit_levels": replace a level that exceeds a fixed capacity by the stream's next one
     std::atomic<int> levelsSkipped{0};
-    bool cullInstances = false;    // option "cull": instance-level frustum culling + block compaction in the geometry kernel
-    bool zeroCopy = true;  // host-facing steps: the tile kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
+    bool zeroCopy = true;  // host-facing steps: the raster kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
     bool rasterToHost = false;
     int numSMs = 148;
     MvConsts consts{};
@@ -153,39 +151,22 @@ struct mv_engine {
     DevBuf<uint8_t> d_obs;
     DevBuf<float> d_depth;
     DevBuf<int32_t> d_faults;
-    DevBuf<int32_t> d_triCounts;
-    DevBuf<int32_t> d_tileCounter;
-    DevBuf<mvr::TriCover> d_cover;
-    DevBuf<mvr::TriShade> d_shade;
-    // host delivery pipeline (mv_step with host buffers, zero_copy off): views are rasterised in slices and each slice goes
-    // down on a second stream (copy engine) while the next one is rasterised
-    cudaStream_t copyStream = nullptr;
-    std::vector<cudaEvent_t> sliceDone;
-    bool pipelineHost = false;   // this launch: slice + copy on the second stream
-    // progressive download: ONE raster launch, the tile kernel counts finished tiles per slice of views and the copy stream waits
-    // on those counters (cuStreamWaitValue32, cyclic >= on cumulative targets) before each slice's cudaMemcpyAsync
-    typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-    WaitValue32Fn waitValue32 = nullptr;
-    DevBuf<uint32_t> d_sliceDone;
-    uint32_t sliceTarget[32] = {};
-    int progSlices = 8;
-    bool progressive = false, progressiveNow = false;  // measured on B200: no faster than one copy; zero-copy is the default delivery
-    int hostSlices = 1;          // measured on B200: slicing loses (each slice pays the latency-bound kernels' tail); zero-copy is the default
-    // hi-res pass (draw_hires): its own scratch, allocated on first use
+    // rasteriser (raster_view.cuh): a persistent grid of CTAs pulling (view, band) items from a never-reset counter
+    DevBuf<uint32_t> d_workCounter;
+    uint32_t counterBase = 0;          // what the counter read before the next launch's first claim
+    DevBuf<unsigned long long> d_spill;  // [rasterGrid][spillStride]
+    int rasterGrid = 0, rasterCtasPerSM = 0, spillStride = 0, rasterBands = 1;
+    size_t rasterSmem = 0;
+    // hi-res pass (draw_hires): its own output buffers, allocated on first use
     struct Hires {
-        int W = 0, H = 0, chunk = 0, binCap = 0;
+        int W = 0, H = 0;
         DevBuf<uint8_t> d_obs; PinBuf<uint8_t> h_obs;
-        DevBuf<mvr::TriCover> cover; DevBuf<mvr::TriShade> shade;
-        DevBuf<int32_t> binCounts; DevBuf<uint16_t> binList; DevBuf<int4> wideList;
-        void free() { d_obs.free(); h_obs.free(); cover.free(); shade.free(); binCounts.free(); binList.free(); wideList.free(); W = H = 0; }
+        DevBuf<unsigned long long> spill;
+        void free() { d_obs.free(); h_obs.free(); spill.free(); W = H = 0; }
     } hires;
     DevBuf<MvDeco> d_deco;
     PinBuf<MvDeco> h_deco;
     int decoCap = 1, instCap = MV_BASE_INSTANCES + 1;
-    DevBuf<int32_t> d_binCounts, d_wideCounts;
-    DevBuf<uint16_t> d_binList;
-    DevBuf<int4> d_wideList;
-    int binCap = 512;
 
     PinBuf<MvLevel> h_levels;      // [E][2] staging mirror
     PinBuf<uint32_t> h_solid;      // [E][2][gridWords]
@@ -202,7 +183,6 @@ struct mv_engine {
     struct Pending { bool valid = false; cudaEvent_t ev = nullptr; PinBuf<float> rewards, trueObj; PinBuf<uint8_t> dones; };
     Pending ring[3];
     DevBuf<uint32_t> d_prof;  // mv_debug_step_profile only
-    DevBuf<uint32_t> d_tileProf;
     DevBuf<uint32_t> d_ready; // per-env step completion stamps (step kernel -> geometry kernel)
     uint32_t readyStamp = 0;
     bool overlap = true;      // geometry kernel launched as a programmatic dependent of the step kernel
@@ -233,10 +213,6 @@ struct mv_engine {
                 return;
             }
             {
-                const int32_t *mc = out.level.mesh_counts;  // work items of the geometry kernel: 6 faces per box, one per mesh triangle
-                const int items = mc[0] * 6 + mc[1] * MV_CAPSULE_TRIS + mc[2] * MV_SPHERE_TRIS + mc[3] * MV_CONE_TRIS + mc[4] * MV_CYLINDER_TRIS;
-                int cur = maxItemsSeen.load();
-                while (items > cur && !maxItemsSeen.compare_exchange_weak(cur, items)) {}
                 int curO = maxObjSeen.load();
                 while (out.level.n_obj > curO && !maxObjSeen.compare_exchange_weak(curO, out.level.n_obj)) {}
             }
@@ -287,7 +263,6 @@ struct mv_engine {
         sp.levels = d_levels.p; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
         sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
-        sp.triCounts = d_triCounts.p; sp.wideCounts = d_wideCounts.p;
         sp.prof = d_prof.p;
         sp.deco = d_deco.p; sp.decoCap = decoCap; sp.instStride = instCap;
         sp.ready = d_ready.p; sp.readyStamp = ++readyStamp;
@@ -308,98 +283,52 @@ struct mv_engine {
         if (timing) MV_CUDA(cudaEventRecord(ev[2], stream));
         return MV_OK;
     }
-    // geometry + tile kernels over view chunks; the triangle scratch of a chunk is reused by the next one, so it stays
-    // L2 resident instead of growing with N
-    int launchRaster() {
-        mvr::RasterParams rp;
-        rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = instCap;
-        // pinned allocations are mapped into the device address space (UVA), so the kernel can store through the host pointer
-        rp.obs = rasterToHost ? h_obs.p : d_obs.p; rp.depth = wantDepth ? (rasterToHost ? h_depth.p : d_depth.p) : nullptr; rp.faults = d_faults.p;
-        rp.cover = d_cover.p; rp.shade = d_shade.p; rp.triCounts = d_triCounts.p;
-        rp.binCounts = d_binCounts.p; rp.binList = d_binList.p; rp.wideCounts = d_wideCounts.p; rp.wideList = d_wideList.p; rp.binCap = binCap;
-        rp.tileProf = d_tileProf.p;
-        const int progViews = std::max(1, (N + progSlices - 1) / progSlices);
-        rp.sliceDone = progressiveNow ? d_sliceDone.p : nullptr; rp.sliceViews = progViews;
-        rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0;
-        rp.N = N; rp.A = A; rp.W = W; rp.H = H; rp.triCap = triCap;
-        rp.p00 = consts.p00; rp.p11 = consts.p11; rp.p22 = consts.p22; rp.p32 = consts.p32;
-        const int nTiles = (W / 32) * (H / 4);
-        const int maxItems = instCap * 6 + (A + MV_MAX_OBJECTS + decoCap) * 128 + 3 * MV_MAX_REWARD * 80;  // blocks past a view's real item count exit at once
-        const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
-        int sliceViews = chunkViews;
-        if (pipelineHost) sliceViews = std::max(1, std::min(chunkViews, (N + hostSlices - 1) / hostSlices));
-        int sliceIdx = 0;
-        for (int base = 0; base < N; base += sliceViews, ++sliceIdx) {
-            const int cv = std::min(sliceViews, N - base);
-            rp.viewBase = base; rp.chunkViews = cv;
-            if (overlap && base == 0) {
-                // programmatic dependent launch: the grid may start before the step kernel has drained; its blocks wait
-                // for their env's stamp
-                rp.ready = d_ready.p; rp.readyStamp = readyStamp;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(unsigned(itemBlocks), unsigned(cv)); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-                attr[0].val.programmaticStreamSerializationAllowed = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                if (cullInstances) MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::geomKernel<true>, rp));
-                else MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::geomKernel<false>, rp));
-            } else {
-                rp.ready = nullptr; rp.readyStamp = 0;
-                if (cullInstances) mvr::geomKernel<true><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
-                else mvr::geomKernel<false><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
-            }
-            MV_CUDA(cudaGetLastError());
-            const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * mvr::kTileBlocksPerSM);  // persistent blocks of 4 warps
-            if (fastShading) mvr::tileKernel<true><<<tileBlocks, 128, 0, stream>>>(rp);
-            else mvr::tileKernel<false><<<tileBlocks, 128, 0, stream>>>(rp);
-            MV_CUDA(cudaGetLastError());
-            launches += 2;
-            if (pipelineHost) {
-                while (int(sliceDone.size()) <= sliceIdx) { cudaEvent_t e2; MV_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); sliceDone.push_back(e2); }
-                MV_CUDA(cudaEventRecord(sliceDone[size_t(sliceIdx)], stream));
-                MV_CUDA(cudaStreamWaitEvent(copyStream, sliceDone[size_t(sliceIdx)], 0));
-                const size_t px = size_t(W) * H;
-                MV_CUDA(cudaMemcpyAsync(h_obs.p + size_t(base) * px * 4, d_obs.p + size_t(base) * px * 4, size_t(cv) * px * 4, cudaMemcpyDeviceToHost, copyStream));
-                if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, d_depth.p + size_t(base) * px, sizeof(float) * size_t(cv) * px, cudaMemcpyDeviceToHost, copyStream));
-            }
-        }
-        if (progressiveNow) {
-            const size_t px = size_t(W) * H;
-            for (int sl = 0, base = 0; base < N; ++sl, base += progViews) {
-                const int cv = std::min(progViews, N - base);
-                sliceTarget[sl] += uint32_t(cv) * uint32_t(nTiles);
-                const CUresult wr = waitValue32(copyStream, CUdeviceptr(reinterpret_cast<uintptr_t>(d_sliceDone.p + sl)), sliceTarget[sl], CU_STREAM_WAIT_VALUE_GEQ);
-                if (wr != CUDA_SUCCESS) {
-                    int memops = -1;
-                    cudaDeviceGetAttribute(&memops, cudaDevAttrMemSyncDomainCount, device);
-                    setError("cuStreamWaitValue32 failed with CUresult " + std::to_string(int(wr)));
-                    return MV_ERR_CUDA;
-                }
-                MV_CUDA(cudaMemcpyAsync(h_obs.p + size_t(base) * px * 4, d_obs.p + size_t(base) * px * 4, size_t(cv) * px * 4, cudaMemcpyDeviceToHost, copyStream));
-                if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, d_depth.p + size_t(base) * px, sizeof(float) * size_t(cv) * px, cudaMemcpyDeviceToHost, copyStream));
-            }
-        }
+    // One persistent launch over all (view, band) items.  Every CTA makes exactly one failing claim when the queue is empty, so the
+    // work counter advances by items + grid per launch and the host keeps the base instead of resetting the counter (no memset node
+    // between the step kernel and its programmatic dependent).
+    int launchView(mvr::ViewParams &vp, int grid, bool dependent) {
+        vp.workCounter = d_workCounter.p; vp.counterBase = counterBase;
+        counterBase += uint32_t(vp.N) * uint32_t(vp.bands) + uint32_t(grid);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(unsigned(grid)); cfg.blockDim = dim3(mvr::kThreads); cfg.dynamicSmemBytes = rasterSmem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = dependent ? 1 : 0;
+        if (fastShading) MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::viewKernel<true>, vp));
+        else MV_CUDA(cudaLaunchKernelEx(&cfg, mvr::viewKernel<false>, vp));
+        launches += 1;
         return MV_OK;
     }
+    int launchRaster() {
+        mvr::ViewParams vp = {};
+        vp.instances = d_inst.p; vp.instCounts = d_instCounts.p; vp.views = d_views.p; vp.instStride = instCap;
+        // pinned allocations are mapped into the device address space (UVA), so the kernel can store through the host pointer
+        vp.obs = rasterToHost ? h_obs.p : d_obs.p; vp.depth = wantDepth ? (rasterToHost ? h_depth.p : d_depth.p) : nullptr;
+        vp.spill = d_spill.p; vp.spillStride = spillStride; vp.consumed = nullptr;
+        vp.N = N; vp.A = A; vp.W = W; vp.H = H; vp.bands = rasterBands; vp.bandRows = ((H / 4 + rasterBands - 1) / rasterBands) * 4; vp.triCap = triCap;
+        vp.p00 = consts.p00; vp.p11 = consts.p11; vp.p22 = consts.p22; vp.p32 = consts.p32;
+        // programmatic dependent launch: the grid may start before the step kernel has drained; a CTA waits for its env's stamp
+        vp.ready = overlap ? d_ready.p : nullptr; vp.readyStamp = overlap ? readyStamp : 0;
+        return launchView(vp, std::min(rasterGrid, N * rasterBands), overlap);
+    }
     // draw_hires (megaverse.cpp:154-177): every agent view once more, at (w, h), from the instance lists and camera matrices of
-    // the last step -- the same two kernels, their own scratch.  Result in hires.h_obs, uint8[N][h][w][4].
+    // the last step -- the same kernel over row bands of the large frame.  Result in hires.h_obs, uint8[N][h][w][4].
     int drawHires(int w, int hgt) {
         if (!didReset) { setError("mv_draw_hires before mv_reset"); return MV_ERR_STATE; }
         if (w < 32 || hgt < 4 || (w % 32) || (hgt % 4) || w > 4096 || hgt > 4096) { setError("hi-res size must be a multiple of 32 x 4"); return MV_ERR_ARG; }
         int rc = drain();
         if (rc) return rc;
-        const int nTiles = (w / 32) * (hgt / 4);
+        // bands of about a hundred 32x4 tiles each
+        const int tilesX = w / 32, tileRows = hgt / 4;
+        const int rowsPerBand = std::max(1, 96 / tilesX) * 4;
+        const int bands = (hgt + rowsPerBand - 1) / rowsPerBand;
+        const int stride = w * rowsPerBand;
+        (void)tileRows;
         if (hires.W != w || hires.H != hgt) {
             hires.free();
-            hires.binCap = std::max(256, std::min(1024, triCap / 4));
-            const size_t perView = size_t(triCap) * (sizeof(mvr::TriCover) + sizeof(mvr::TriShade)) + size_t(nTiles) * (size_t(hires.binCap) * 2 + 4);
-            hires.chunk = int(std::max<size_t>(1, std::min<size_t>(size_t(N), (size_t(192) << 20) / perView)));
-            const size_t px = size_t(N) * w * hgt * 4, tiles = size_t(hires.chunk) * nTiles;
-            if (hires.d_obs.alloc(px) != cudaSuccess || hires.h_obs.alloc(px) != cudaSuccess || hires.cover.alloc(size_t(hires.chunk) * triCap) != cudaSuccess ||
-                hires.shade.alloc(size_t(hires.chunk) * triCap) != cudaSuccess || hires.binCounts.alloc(tiles) != cudaSuccess ||
-                hires.binList.alloc(tiles * size_t(hires.binCap)) != cudaSuccess || hires.wideList.alloc(size_t(hires.chunk) * mvr::kWideCap) != cudaSuccess ||
-                cudaMemset(hires.binCounts.p, 0, sizeof(int32_t) * tiles) != cudaSuccess) {
+            const size_t px = size_t(N) * w * hgt * 4;
+            if (hires.d_obs.alloc(px) != cudaSuccess || hires.h_obs.alloc(px) != cudaSuccess || hires.spill.alloc(size_t(rasterGrid) * size_t(stride)) != cudaSuccess) {
                 hires.free();
                 setError("hi-res buffers: allocation failed");
                 return MV_ERR_CUDA;
@@ -408,46 +337,39 @@ struct mv_engine {
         }
         MvConsts k;
         fillConstsFor(k, w, hgt);
-        mvr::RasterParams rp;
-        rp.instances = d_inst.p; rp.instCounts = d_instCounts.p; rp.views = d_views.p; rp.instStride = instCap;
-        rp.obs = hires.d_obs.p; rp.depth = nullptr; rp.faults = d_faults.p;
-        rp.cover = hires.cover.p; rp.shade = hires.shade.p; rp.triCounts = d_triCounts.p;
-        rp.binCounts = hires.binCounts.p; rp.binList = hires.binList.p; rp.wideCounts = d_wideCounts.p; rp.wideList = hires.wideList.p; rp.binCap = hires.binCap;
-        rp.tileProf = nullptr; rp.sliceDone = nullptr; rp.sliceViews = 1; rp.tileCounter = d_tileCounter.p; rp.fastShading = fastShading ? 1 : 0; rp.ready = nullptr; rp.readyStamp = 0;
-        rp.N = N; rp.A = A; rp.W = w; rp.H = hgt; rp.triCap = triCap;
-        rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
-        const int maxItems = instCap * 6 + (A + MV_MAX_OBJECTS + decoCap) * 128 + 3 * MV_MAX_REWARD * 80;
-        const int itemBlocks = std::min((maxItems + 127) / 128, (maxItemsSeen.load() + 127) / 128);
-        // the per-view triangle / wide-list counters are shared with the training-resolution pass: clear them first
-        MV_CUDA(cudaMemsetAsync(d_triCounts.p, 0, sizeof(int32_t) * size_t(N), stream));
-        MV_CUDA(cudaMemsetAsync(d_wideCounts.p, 0, sizeof(int32_t) * size_t(N), stream));
-        for (int base = 0; base < N; base += hires.chunk) {
-            const int cv = std::min(hires.chunk, N - base);
-            rp.viewBase = base; rp.chunkViews = cv;
-            if (cullInstances) mvr::geomKernel<true><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
-            else mvr::geomKernel<false><<<dim3(unsigned(itemBlocks), unsigned(cv)), 128, 0, stream>>>(rp);
-            MV_CUDA(cudaGetLastError());
-            const int tileBlocks = std::min((cv * nTiles + 3) / 4, numSMs * mvr::kTileBlocksPerSM);
-            if (fastShading) mvr::tileKernel<true><<<tileBlocks, 128, 0, stream>>>(rp);
-            else mvr::tileKernel<false><<<tileBlocks, 128, 0, stream>>>(rp);
-            MV_CUDA(cudaGetLastError());
-            launches += 2;
-        }
+        mvr::ViewParams vp = {};
+        vp.instances = d_inst.p; vp.instCounts = d_instCounts.p; vp.views = d_views.p; vp.instStride = instCap;
+        vp.obs = hires.d_obs.p; vp.depth = nullptr; vp.spill = hires.spill.p; vp.spillStride = stride; vp.consumed = nullptr;
+        vp.N = N; vp.A = A; vp.W = w; vp.H = hgt; vp.bands = bands; vp.bandRows = rowsPerBand; vp.triCap = triCap;
+        vp.p00 = k.p00; vp.p11 = k.p11; vp.p22 = k.p22; vp.p32 = k.p32;
+        vp.ready = nullptr; vp.readyStamp = 0;
+        rc = launchView(vp, std::min(rasterGrid, N * bands), false);
+        if (rc) return rc;
         MV_CUDA(cudaMemcpyAsync(hires.h_obs.p, hires.d_obs.p, size_t(N) * w * hgt * 4, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaStreamSynchronize(stream));
         return MV_OK;
     }
-    int allocTriScratch() {
-        d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free();
-        const size_t cnt = size_t(chunkViews) * size_t(triCap);
-        const size_t tiles = size_t(chunkViews) * size_t((W / 32) * (H / 4));
-        binCap = std::max(256, std::min(1024, triCap / 4));
-        if (d_cover.alloc(cnt) != cudaSuccess || d_shade.alloc(cnt) != cudaSuccess || d_binCounts.alloc(tiles) != cudaSuccess ||
-            d_binList.alloc(tiles * size_t(binCap)) != cudaSuccess || d_wideList.alloc(size_t(chunkViews) * mvr::kWideCap) != cudaSuccess ||
-            cudaMemset(d_binCounts.p, 0, sizeof(int32_t) * tiles) != cudaSuccess) {
-            setError("triangle scratch allocation failed");
-            return MV_ERR_CUDA;
+    // shared-memory carve-up, occupancy and the per-CTA spill slabs for the current triangle-list capacity / band count
+    int configureRaster() {
+        if (stream) cudaStreamSynchronize(stream);
+        rasterSmem = mvr::smemLayout(triCap).total;
+        int maxOptin = 0;
+        MV_CUDA(cudaDeviceGetAttribute(&maxOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        if (int(rasterSmem) > maxOptin) { setError("tri_cap needs more shared memory than an SM has"); return MV_ERR_ARG; }
+        for (int fast = 0; fast < 2; ++fast) {
+            const void *fn = fast ? reinterpret_cast<const void *>(mvr::viewKernel<true>) : reinterpret_cast<const void *>(mvr::viewKernel<false>);
+            MV_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, maxOptin));  // per function, not per engine: allow the device maximum
+            int perSM = 0;
+            MV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, fn, mvr::kThreads, rasterSmem));
+            if (perSM < 1) { setError("raster kernel does not fit on an SM with this tri_cap"); return MV_ERR_CUDA; }
+            rasterCtasPerSM = fast ? std::min(rasterCtasPerSM, perSM) : perSM;
         }
+        rasterGrid = numSMs * rasterCtasPerSM;
+        const int bandRows = ((H / 4 + rasterBands - 1) / rasterBands) * 4;
+        spillStride = W * bandRows;
+        d_spill.free();
+        if (d_spill.alloc(size_t(rasterGrid) * size_t(spillStride)) != cudaSuccess) { setError("raster spill slab allocation failed"); return MV_ERR_CUDA; }
+        hires.free();  // its spill slab is sized by the grid
         return MV_OK;
     }
 
@@ -474,13 +396,12 @@ struct mv_engine {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        if (copyObs && !rasterToHost && !pipelineHost && !progressiveNow) {
+        if (copyObs && !rasterToHost) {
             MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
         if (!wait) return MV_OK;
         MV_CUDA(cudaStreamSynchronize(stream));
-        if (pipelineHost || progressiveNow) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         return MV_OK;
     }
@@ -522,7 +443,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        rasterToHost = false; pipelineHost = false; progressiveNow = false;
+        rasterToHost = false;
         rc = launchStep(dActions, false, &slotP);  // rewards / dones / true objectives land in the ring slot straight from the kernel
         if (rc) return rc;
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
@@ -543,8 +464,6 @@ struct mv_engine {
             rtableDirty = false;
         }
         rasterToHost = copyObs && zeroCopy;
-        pipelineHost = copyObs && !zeroCopy && hostSlices > 1 && copyStream != nullptr;
-        progressiveNow = copyObs && !zeroCopy && !pipelineHost && progressive && waitValue32 != nullptr && N >= 2 * progSlices;
         rc = launchStep(dActions, false);
         if (rc) return rc;
         rc = finishStep(copyObs, !split);
@@ -557,7 +476,6 @@ struct mv_engine {
     int stepEnd() {
         if (!hostStepPending) { setError("mv_step_end without mv_step_begin"); return MV_ERR_STATE; }
         MV_CUDA(cudaStreamSynchronize(stream));
-        if (pipelineHost || progressiveNow) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         hostStepPending = false;
         std::memset(h_actions.p, 0, sizeof(int32_t) * N);  // env.cpp:140-142: actions are cleared after every step
@@ -569,14 +487,11 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        d_sliceDone.free(); hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_tileProf.free(); d_ready.free(); d_triCounts.free(); d_tileCounter.free(); d_cover.free(); d_shade.free(); d_binCounts.free(); d_binList.free(); d_wideList.free(); d_wideCounts.free();
+        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &p : ring) { if (p.ev) { cudaEventDestroy(p.ev); p.ev = nullptr; } p.rewards.free(); p.trueObj.free(); p.dones.free(); }
-        for (auto &e2 : sliceDone) if (e2) cudaEventDestroy(e2);
-        sliceDone.clear();
-        if (copyStream) { cudaStreamDestroy(copyStream); copyStream = nullptr; }
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 };
@@ -679,26 +594,21 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
 
     auto ck = [&](cudaError_t err, const char *what) { if (err != cudaSuccess) { e->setError(std::string(what) + ": " + cudaGetErrorString(err)); return false; } return true; };
     const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
-    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream") && ck(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking), "copy stream");
+    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream");
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
-    {   // stream memory operations come from the driver API: resolved at run time from the already loaded libcuda (no link-time
-        // dependency, the library must also load on machines without a driver); _v2 is the CUDA 12 ABI, v1 is disabled here
-        if (void *drv = dlopen("libcuda.so.1", RTLD_LAZY | RTLD_LOCAL))
-            e->waitValue32 = reinterpret_cast<mv_engine::WaitValue32Fn>(dlsym(drv, "cuStreamWaitValue32_v2"));
-    }
     ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
          ck(e->d_inst.alloc(E * size_t(e->instCap)), "instances") && ck(e->d_deco.alloc(E * 2 * size_t(e->decoCap)), "deco") && ck(e->h_deco.alloc(E * 2 * size_t(e->decoCap)), "h_deco") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
-         ck(e->d_triCounts.alloc(N), "triCounts") && ck(e->d_wideCounts.alloc(N), "wideCounts") && ck(e->d_tileCounter.alloc(4), "tileCounter") && ck(e->d_sliceDone.alloc(32), "sliceDone") && ck(cudaMemset(e->d_sliceDone.p, 0, 128), "sliceDone") && ck(e->d_ready.alloc(E), "ready") &&
+         ck(e->d_workCounter.alloc(4), "workCounter") && ck(cudaMemset(e->d_workCounter.p, 0, 16), "workCounter") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
-    // rasteriser scratch: Collect's Perlin landscapes merge into up to ~500 boxes (+ up to 86 reward diamonds)
-    const bool hexSc = sc == MV_SCENARIO_HEX_EXPLORE || sc == MV_SCENARIO_HEX_MEMORY;  // hundreds of wall / edging / landmark boxes
-    e->triCap = hexSc ? 8192 : (sc == MV_SCENARIO_COLLECT ? 4096 : ((sc == MV_SCENARIO_OBSTACLES || e->A > 1) ? 2048 : 1024));  // other agents' capsules: 128 triangles each
-    e->chunkViews = int(std::min<size_t>(N, hexSc ? 128 : (sc == MV_SCENARIO_COLLECT ? 256 : 512)));
-    if (ok && e->allocTriScratch() != MV_OK) return fail(MV_ERR_CUDA);
+    if (e->instCap > mvr::kMaxInstancesPerEnv) { e->setError("instance capacity exceeds the draw-order key range"); return fail(MV_ERR_CAPACITY); }
+    // few views: split every view into row bands so that the persistent grid (2 CTAs per SM) has something to balance
+    e->rasterBands = N <= 160 ? 3 : (N <= 320 ? 2 : 1);
+    while (e->rasterBands > 1 && (h / 4) % e->rasterBands) --e->rasterBands;
+    if (ok && e->configureRaster() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
          ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults");
@@ -711,7 +621,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     std::memset(e->h_obs.p, 0, N * px * 4);
     for (size_t v = 0; v < N; ++v) e->fillRtableRow(int(v));
     ok = ck(cudaMemset(e->d_trueObj.p, 0, sizeof(float) * N), "memset") && ck(cudaMemset(e->d_faults.p, 0, sizeof(int32_t) * E), "memset") &&
-         ck(cudaMemset(e->d_actions.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_triCounts.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_agents.p, 0, sizeof(MvAgent) * N), "memset") &&
+         ck(cudaMemset(e->d_actions.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_agents.p, 0, sizeof(MvAgent) * N), "memset") &&
          ck(cudaMemset(e->d_objects.p, 0, sizeof(MvObject) * E * MV_MAX_OBJECTS), "memset");
     if (!ok) return fail(MV_ERR_CUDA);
     if (uploadPalette(e) != MV_OK) return fail(MV_ERR_CUDA);
@@ -732,19 +642,22 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         }
         return MV_OK;
     }
-    if (k == "tri_cap") {
-        if (value < 64 || value > 8192) { h->setError("tri_cap out of range [64,8192]"); return MV_ERR_ARG; }
-        if (h->stream) cudaStreamSynchronize(h->stream);
+    if (k == "tri_cap") {  // triangles a raster CTA keeps in shared memory; views with more are drawn in several batches
+        if (value < 32 || value > mvr::kMaxTriCap) { h->setError("tri_cap out of range [32,1022]"); return MV_ERR_ARG; }
+        const int old = h->triCap;
         h->triCap = value;
-        return h->allocTriScratch();
+        const int rc = h->configureRaster();
+        if (rc) { h->triCap = old; h->configureRaster(); }
+        return rc;
+    }
+    if (k == "raster_bands") {  // row bands per view (each band is one work item of the persistent raster grid)
+        if (value < 1 || value > h->H / 4 || (h->H / 4) % value) { h->setError("raster_bands must divide the number of 4-pixel tile rows"); return MV_ERR_ARG; }
+        h->rasterBands = value;
+        return h->configureRaster();
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
-    if (k == "cull") { h->cullInstances = value != 0; return MV_OK; }
     if (k == "skip_unfit_levels") { h->skipUnfitLevels = value != 0; return MV_OK; }
-    if (k == "progressive") { h->progressive = value != 0; return MV_OK; }
-    if (k == "progressive_slices") { if (value < 1 || value > 32) return MV_ERR_ARG; cudaDeviceSynchronize(); h->progSlices = value; cudaMemset(h->d_sliceDone.p, 0, 128); std::memset(h->sliceTarget, 0, sizeof h->sliceTarget); return MV_OK; }
-    if (k == "host_slices") { if (value < 1 || value > 64) return MV_ERR_ARG; h->hostSlices = value; return MV_OK; }
     if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
     if (k == "overlap") { cudaStreamSynchronize(h->stream); h->overlap = value != 0; return MV_OK; }
     h->setError("unknown option " + k);
@@ -805,7 +718,6 @@ int mv_reset(mv_handle h) {
         h->rtableDirty = false;
     }
     h->rasterToHost = h->obsToHost && h->zeroCopy;
-    h->pipelineHost = false; h->progressiveNow = false;
     rc = h->launchStep(h->d_actions.p, true);
     if (rc) return rc;
     rc = h->finishStep(h->obsToHost);
@@ -856,20 +768,6 @@ int mv_step_device(mv_handle h, const int32_t *d_masks) {
     if (!h) return MV_ERR_ARG;
     if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     return h->stepAsync(d_masks ? d_masks : h->d_actions.p);
-}
-
-int mv_debug_tile_profile(mv_handle h, uint32_t *out, int enable) {
-    if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) return MV_ERR_CUDA;
-    cudaStreamSynchronize(h->stream);
-    const size_t n = size_t(h->N) * size_t((h->W / 32) * (h->H / 4)) * 4;
-    if (enable && !h->d_tileProf.p) {
-        if (h->d_tileProf.alloc(n) != cudaSuccess) { h->setError("tile profile buffer allocation failed"); return MV_ERR_CUDA; }
-        cudaMemset(h->d_tileProf.p, 0, sizeof(uint32_t) * n);
-    }
-    if (out && h->d_tileProf.p && cudaMemcpy(out, h->d_tileProf.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
-    if (!enable) h->d_tileProf.free();
-    return MV_OK;
 }
 
 // host-only: the colour tables of the level generators followed by the rasteriser's palette (float bit patterns), in the layout of
@@ -1196,11 +1094,6 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
     MvConsts k;
     fillConsts(k, w, h);
     if (uploadPalette(&tmp) != MV_OK) return MV_ERR_CUDA;
-    const int triCap = 8192;
-    MvInstance *dInst = nullptr; int32_t *dCnt = nullptr, *dFault = nullptr, *dTri = nullptr, *dTileCtr = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
-    mvr::TriCover *dCover = nullptr; mvr::TriShade *dShade = nullptr;
-    int32_t *dBinCounts = nullptr, *dWideCount = nullptr; uint16_t *dBinList = nullptr; int4 *dWideList = nullptr;
-    const int binCap = 2048, tilesV = (w / 32) * (h / 4);
     int32_t cnt[8] = {nBox, n, 0, 0, 0, 0, 0, 0};
     {   // instances must be sorted by mesh type (draw order)
         int last = 0;
@@ -1211,41 +1104,34 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
             if (m >= 1) cnt[1 + m] += 1;
         }
     }
-    bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 32) == cudaSuccess && cudaMalloc(&dFault, 4) == cudaSuccess &&
+    // a small triangle list on purpose: scenes of a few hundred triangles exercise the multi-batch path
+    const int triCap = 96;
+    const size_t smem = mvr::smemLayout(triCap).total;
+    MvInstance *dInst = nullptr; int32_t *dCnt = nullptr; float *dView = nullptr, *dDepth = nullptr; uint8_t *dObs = nullptr;
+    uint32_t *dCtr = nullptr; unsigned long long *dSpill = nullptr;
+    const int bands = (h / 4) % 2 == 0 ? 2 : 1, bandRows = (h / 4 / bands) * 4;
+    bool ok = cudaMalloc(&dInst, sizeof(MvInstance) * inst.size()) == cudaSuccess && cudaMalloc(&dCnt, 32) == cudaSuccess &&
               cudaMalloc(&dView, 64) == cudaSuccess && cudaMalloc(&dObs, size_t(w) * h * 4) == cudaSuccess && cudaMalloc(&dDepth, size_t(w) * h * 4) == cudaSuccess &&
-              cudaMalloc(&dTri, 4) == cudaSuccess && cudaMalloc(&dTileCtr, 4) == cudaSuccess && cudaMalloc(&dCover, sizeof(mvr::TriCover) * triCap) == cudaSuccess &&
-              cudaMalloc(&dShade, sizeof(mvr::TriShade) * triCap) == cudaSuccess && cudaMalloc(&dBinCounts, sizeof(int32_t) * tilesV) == cudaSuccess &&
-              cudaMalloc(&dWideCount, 4) == cudaSuccess && cudaMalloc(&dBinList, sizeof(uint16_t) * size_t(tilesV) * binCap) == cudaSuccess &&
-              cudaMalloc(&dWideList, sizeof(int4) * mvr::kWideCap) == cudaSuccess;
+              cudaMalloc(&dCtr, 16) == cudaSuccess && cudaMalloc(&dSpill, sizeof(unsigned long long) * size_t(bands) * size_t(w) * bandRows) == cudaSuccess &&
+              cudaFuncSetAttribute(mvr::viewKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) == cudaSuccess;
     if (ok) {
         cudaMemcpy(dInst, inst.data(), sizeof(MvInstance) * inst.size(), cudaMemcpyHostToDevice);
         cudaMemcpy(dCnt, cnt, 32, cudaMemcpyHostToDevice);
         cudaMemcpy(dView, view16, 64, cudaMemcpyHostToDevice);
-        cudaMemset(dFault, 0, 4);
-        cudaMemset(dTri, 0, 4);
-        cudaMemset(dWideCount, 0, 4);
-        cudaMemset(dBinCounts, 0, sizeof(int32_t) * tilesV);
-        mvr::RasterParams rp;
-        rp.binCounts = dBinCounts; rp.binList = dBinList; rp.wideCounts = dWideCount; rp.wideList = dWideList; rp.binCap = binCap; rp.tileProf = nullptr;
-        rp.sliceDone = nullptr; rp.sliceViews = 1;
-        rp.ready = nullptr; rp.readyStamp = 0;
-        rp.instances = dInst; rp.instCounts = dCnt; rp.views = dView; rp.instStride = int(inst.size()); rp.obs = dObs; rp.depth = depth ? dDepth : nullptr;
-        rp.faults = dFault; rp.cover = dCover; rp.shade = dShade; rp.triCounts = dTri; rp.tileCounter = dTileCtr; rp.fastShading = 0; rp.viewBase = 0; rp.chunkViews = 1;
-        rp.N = 1; rp.A = 1; rp.W = w; rp.H = h; rp.triCap = triCap; rp.p00 = k.p00; rp.p11 = k.p11; rp.p22 = k.p22; rp.p32 = k.p32;
-        const int items = nBox * 6 + (n - nBox) * 128;  // upper bound
-        mvr::geomKernel<false><<<dim3(unsigned((items + 127) / 128 + 1), 1), 128>>>(rp);
-        mvr::tileKernel<false><<<((w / 32) * (h / 4) + 3) / 4, 128>>>(rp);
+        cudaMemset(dCtr, 0, 16);
+        mvr::ViewParams vp = {};
+        vp.instances = dInst; vp.instCounts = dCnt; vp.views = dView; vp.instStride = int(inst.size()); vp.obs = dObs; vp.depth = depth ? dDepth : nullptr;
+        vp.workCounter = dCtr; vp.counterBase = 0; vp.ready = nullptr; vp.readyStamp = 0; vp.consumed = nullptr; vp.spill = dSpill; vp.spillStride = w * bandRows;
+        vp.N = 1; vp.A = 1; vp.W = w; vp.H = h; vp.bands = bands; vp.bandRows = bandRows; vp.triCap = triCap;
+        vp.p00 = k.p00; vp.p11 = k.p11; vp.p22 = k.p22; vp.p32 = k.p32;
+        mvr::viewKernel<false><<<bands, mvr::kThreads, smem>>>(vp);
         ok = cudaDeviceSynchronize() == cudaSuccess;
         if (ok) {
             cudaMemcpy(rgba, dObs, size_t(w) * h * 4, cudaMemcpyDeviceToHost);
             if (depth) cudaMemcpy(depth, dDepth, size_t(w) * h * 4, cudaMemcpyDeviceToHost);
-            int32_t f = 0;
-            cudaMemcpy(&f, dFault, 4, cudaMemcpyDeviceToHost);
-            if (f) ok = false;
         }
     }
-    cudaFree(dTri); cudaFree(dTileCtr); cudaFree(dCover); cudaFree(dShade); cudaFree(dBinCounts); cudaFree(dWideCount); cudaFree(dBinList); cudaFree(dWideList);
-    cudaFree(dInst); cudaFree(dCnt); cudaFree(dFault); cudaFree(dView); cudaFree(dObs); cudaFree(dDepth);
+    cudaFree(dCtr); cudaFree(dSpill); cudaFree(dInst); cudaFree(dCnt); cudaFree(dView); cudaFree(dObs); cudaFree(dDepth);
     return ok ? MV_OK : MV_ERR_CUDA;
 }
 

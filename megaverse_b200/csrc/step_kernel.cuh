@@ -50,8 +50,8 @@ struct StepParams {
     int decoCap, instStride;
     int32_t *instCounts;         // [E][8]
     float *views;                // [E*A][16]
-    int32_t *triCounts;          // [E*A] rasteriser triangle counters, zeroed here for the geometry kernel that follows
-    int32_t *wideCounts;         // [E*A] likewise (wide-triangle lists)
+
+
     const int32_t *actions;      // [E*A]
     const float *rtable;         // [E*A][MV_R_COUNT]
     float *rewards;              // [E*A]
@@ -1429,7 +1429,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     MV_PROBE(6);  // outputs, flip/reset, object write-back
 
     writeInstances(S, *L, P.deco + (size_t(env) * 2 + slot) * P.decoCap, P.instances + size_t(env) * P.instStride, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
-    for (int i = lane; i < A; i += 32) { P.triCounts[size_t(env) * A + i] = 0; P.wideCounts[size_t(env) * A + i] = 0; }
+
     MV_PROBE(7);  // instance list + views
 
     // ---- commit env + agents

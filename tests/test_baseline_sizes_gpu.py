@@ -36,11 +36,15 @@ CASES = {
 }
 
 
-def _make(name, fast):
+def _make(name, fast, min_episode_sec=None):
     import orc
     from megaverse_b200 import capi
 
     scenario, E, A, depth, params, ticks = CASES[name]
+    if min_episode_sec is not None and scenario == "Collect":
+        # Collect episodes last episodeLengthSec + 2 s per reward object (scenario_collect.hpp:52-56): -2.0 lets one-reward levels end on
+        # their first tick, every tick -- fine for the host-facing call, outside the asynchronous call's contract (>= 3 ticks per episode)
+        params = dict(params, episodeLengthSec=-2.0 + min_episode_sec)
     o = orc.Oracle(scenario, E, A, 128, 72, params=params, depth=depth, threads=THREADS, render=False)
     g = capi.Engine(scenario, E, A, 128, 72, num_threads=min(16, THREADS), params=params, depth=depth)
     g.set_option("fast_shading", 1 if fast else 0)
@@ -99,7 +103,7 @@ def test_device_step_at_baseline_size(built, name):
     """the asynchronous device-resident loop (what bench.py's `value` times), production shading"""
     import torch
 
-    o, g, acts, (scenario, E, A, depth, ticks) = _make(name, 1)
+    o, g, acts, (scenario, E, A, depth, ticks) = _make(name, 1, min_episode_sec=0.5)
     dacts = torch.from_numpy(acts).cuda()
     torch.cuda.synchronize()
     ndone = 0

@@ -629,18 +629,21 @@ def test_many_agents_other_resolutions(built, scenario, A, w, h):
 
 
 @pytest.mark.parametrize("scenario,A", [("TowerBuilding", 2), ("HexExplore", 2), ("HexMemory", 1), ("Collect", 4), ("ObstaclesHard", 1), ("Rearrange", 2)])
-def test_instance_culling_keeps_frames_identical(built, scenario, A):
-    """option "cull" (instance-level frustum test + block compaction in the geometry kernel) must not change a single byte: two engines on
-    the same seeds and actions, one with the option, frames and depth compared every step; the culled one also against the oracle at the end"""
+def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
+    """how the rasteriser splits its work must not change a single byte: a triangle list of 32 entries per CTA (every view is drawn in many
+    batches through the spill slab, repainting pixels that later batches win), the default list, and views cut into 1, 2 or 3 row bands --
+    engines on the same seeds and actions, frames and depth compared every step; each against the oracle at the end"""
     import orc
     from megaverse_b200 import capi
 
     E, steps = 6, 90
     gs = []
-    for cull in (0, 1):
+    for tri_cap, bands in ((32, 1), (0, 3), (200, 2), (0, 1)):
         g = capi.Engine(scenario, E, A, 128, 72, num_threads=2, depth=True)
         g.set_option("fast_shading", 0)
-        g.set_option("cull", cull)
+        if tri_cap:
+            g.set_option("tri_cap", tri_cap)
+        g.set_option("raster_bands", bands)
         g.seed(77)
         g.reset()
         gs.append(g)
@@ -648,16 +651,19 @@ def test_instance_culling_keeps_frames_identical(built, scenario, A):
     o.seed(77)
     o.reset()
     rng = np.random.default_rng(2)
-    assert np.array_equal(np.array(gs[0].obs()), np.array(gs[1].obs())), "first frame"
+    for g in gs[1:]:
+        assert np.array_equal(np.array(gs[0].obs()), np.array(g.obs())), "first frame"
     for t in range(steps):
         acts = helpers.purposeful_actions(rng, E * A, t)
         for g in gs:
             g.step(acts)
         o.step(acts)
-        assert np.array_equal(np.array(gs[0].obs()), np.array(gs[1].obs())), "frames differ at step %d" % t
-        assert np.array_equal(np.array(gs[0].depth()), np.array(gs[1].depth())), "depth differs at step %d" % t
-    assert np.array_equal(o.obs(), np.array(gs[1].obs())), "culled engine vs oracle"
-    for g in gs:
+        for i, g in enumerate(gs[1:]):
+            assert np.array_equal(np.array(gs[0].obs()), np.array(g.obs())), "frames of configuration %d differ at step %d" % (i + 1, t)
+            assert np.array_equal(np.array(gs[0].depth()), np.array(g.depth())), "depth of configuration %d differs at step %d" % (i + 1, t)
+    for i, g in enumerate(gs):
+        assert np.array_equal(o.obs(), np.array(g.obs())), "configuration %d vs oracle" % i
+        assert np.array_equal(o.depth().view(np.uint32), np.array(g.depth()).view(np.uint32)), "configuration %d vs oracle (depth)" % i
         assert g.faults() == 0
         g.close()
     o.close()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """End-to-end step time through host buffers (mv_set_actions + mv_step) under the delivery modes: zero-copy stores from the
-tile kernel vs sliced rasterisation + copy-engine downloads."""
+raster kernel vs one copy-engine download after it."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,11 +13,7 @@ for e in range(E):
 g.reset()
 rng = np.random.default_rng(1)
 acts = (1 << rng.integers(0, 11, size=(600, E))).astype(np.int32)
-for name, opts in [("zero_copy", {"zero_copy": 1}), ("one big copy", {"zero_copy": 0, "progressive": 0, "host_slices": 1}),
-                   ("progressive, 4 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 4}),
-                   ("progressive, 8 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 8}),
-                   ("progressive, 16 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 16}),
-                   ("progressive, 32 slices", {"zero_copy": 0, "progressive": 1, "progressive_slices": 32})]:
+for name, opts in [("zero_copy", {"zero_copy": 1}), ("one copy after the raster", {"zero_copy": 0})]:
     for k, v in opts.items():
         g.set_option(k, v)
     for t in range(50):
