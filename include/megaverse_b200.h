@@ -79,7 +79,7 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
  * memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps let the rasteriser store rows straight into the pinned
  * host buffer instead of copying afterwards; the HBM copy returned by mv_obs_device is then only refreshed by mv_step_device),
  * "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
- * "tri_cap" (32..1022, default 320: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
+ * "tri_cap" (32..1022, default 288: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
  * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
  * chosen from the number of views by default, results do not depend on it),
  * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity makes mv_step / mv_reset fail with
@@ -141,6 +141,8 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 /* per-env cycle stamps of the step kernel's phases: out = uint32[E][16] (0 staged, 1 actions, 2 candidate list, 3 controllers,
  * 4 transforms, 5 scenario, 6 outputs/reset, 7 instance list, 8 commit, 12 candidate count); enable=1 arms it, 0 frees it */
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
+/* rasteriser launch shape: out4 = {persistent grid size, CTAs per SM, dynamic shared memory per CTA in bytes, row bands per view} */
+int mv_debug_raster_config(mv_handle h, int32_t *out4);
 /* host-only: colour tables of the generators + the rasteriser's palette (tests pin them against the reference's env/const.hpp) */
 int mv_debug_color_tables(uint32_t *out, int cap);
 /* host-only: default reward shaping ("R key=hexbits") and default float parameters ("P key=hexbits") of a scenario, one per line */

@@ -118,7 +118,7 @@ struct mv_engine {
     std::unique_ptr<WorkerPool> pool;
 
     int gridCells = 0, gridWords = 0;
-    int triCap = 320;              // triangle-list capacity of one raster CTA (shared memory); larger views are drawn in several batches
+    int triCap = 288;              // triangle-list capacity of one raster CTA (shared memory); larger views are drawn in several batches
     std::atomic<int> maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
     bool hostStepPending = false;  // between mv_step_begin and mv_step_end
@@ -909,6 +909,11 @@ int mv_faults(mv_handle h, int32_t *out) {
     int32_t f = 0;
     for (int e = 0; e < h->E; ++e) f |= st[size_t(e)].faults | h->h_faults.p[e];
     *out = f;
+    return MV_OK;
+}
+int mv_debug_raster_config(mv_handle h, int32_t *out4) {  // {persistent grid, CTAs per SM, dynamic shared memory bytes, row bands per view}
+    if (!h || !out4) return MV_ERR_ARG;
+    out4[0] = h->rasterGrid; out4[1] = h->rasterCtasPerSM; out4[2] = int32_t(h->rasterSmem); out4[3] = h->rasterBands;
     return MV_OK;
 }
 int mv_kernel_launches(mv_handle h, int64_t *out) { if (!h || !out) return MV_ERR_ARG; *out = h->launches; return MV_OK; }

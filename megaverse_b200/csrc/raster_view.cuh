@@ -55,6 +55,7 @@ constexpr int kThreads = 256;     // per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kInstChunk = 128;   // instances per TMA chunk (one thread each in the instance pass)
 constexpr int kXfWords = 23;      // per instance: model-view (12: three rows of each column), normal matrix (9), colour, mesh | face mask << 8
+constexpr int kClipVerts = 6;     // a triangle clipped by two planes has at most 5 vertices
 constexpr int kSmallArea = 24;    // triangles covering at most this many pixels of a tile are evaluated by one lane
 // a fragment is (~depth bits << 32) | (draw-order key << kIdxBits) | index in the CTA's triangle list
 constexpr int kIdxBits = 10;
@@ -90,7 +91,7 @@ struct ViewParams {
     float p00, p11, p22, p32;
 };
 
-struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, meshV, meshI, misc, total; };
+struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, meshV, meshI, clip, slow, misc, total; };
 struct ViewMisc {
     float view[16];
     int32_t counts[8];
@@ -99,6 +100,7 @@ struct ViewMisc {
     int32_t tileCtr;
     uint32_t claim;
     int32_t wsum[kWarps];
+    int32_t nSlow[2];   // entries of the two slow-item lists (alternating per item sub-pass)
     alignas(8) unsigned long long bar[2];
 };
 __host__ __device__ inline SmemLayout smemLayout(int triCap) {
@@ -112,6 +114,8 @@ __host__ __device__ inline SmemLayout smemLayout(int triCap) {
     L.frag = o; o += uint32_t(kWarps) * 128u * 8u;
     L.meshV = o; o += uint32_t(kMeshVerts) * 6u * 4u;
     L.meshI = o; o += (uint32_t(kMeshIdx) + 15u) & ~15u;
+    L.clip = o; o += uint32_t(kWarps) * 4u * kClipVerts * 40u;  // per warp: polygon + scratch of two source triangles (ClipVert = 40 B)
+    L.slow = o; o += 2u * kThreads * 2u;                        // two lists of at most one entry per thread
     L.misc = o; o += (uint32_t(sizeof(ViewMisc)) + 15u) & ~15u;
     L.total = o;
     return L;
@@ -237,84 +241,62 @@ __device__ __forceinline__ void writeTri(const SetupCtx &cx, int slot, const Cli
     cx.shade[slot] = s;
 }
 
-// The rare path: an item with a vertex beyond the near or the far plane (the floor under the agent's feet, a wall it leans on).  Each of
-// its nSrc source triangles (v0 v1 v2 and, for a box face, v0 v2 v3) is clipped against z >= 0 and z <= w, projected and fanned; the fan
-// pieces of one source triangle share its key (coplanar and disjoint, they never tie on a pixel).  Out of line so that its polygon
-// arrays (local memory) stay off the common path.  Returns true when the list was full.
-__device__ __noinline__ bool clipSlow(const SetupCtx cx, const ClipVert v0, const ClipVert v1, const ClipVert v2, const ClipVert v3, int nSrc, int color,
-                                      uint32_t keyBase) {
-    const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
-    ClipVert poly[2][6];
-    ScreenVert scr[2][6];
-    TriBox box[2][4];
-    int cnt[2] = {0, 0};
-    unsigned vis = 0;  // bit t*4+k: fan piece k of source triangle t is visible
-    int total = 0;
-    for (int t = 0; t < nSrc; ++t) {
-        ClipVert tmp[6];
-        int n = 3;
-        poly[t][0] = v0; poly[t][1] = t == 0 ? v1 : v2; poly[t][2] = t == 0 ? v2 : v3;
-        for (int plane = 0; plane < 2 && n >= 3; ++plane) {
-            int m = 0;
-            for (int i = 0; i < n; ++i) {
-                const ClipVert &a = poly[t][i];
-                const ClipVert &b = poly[t][(i + 1) % n];
-                const float da = plane == 0 ? a.cz : a.cw - a.cz;
-                const float db = plane == 0 ? b.cz : b.cw - b.cz;
-                const bool ina = da >= 0.0f, inb = db >= 0.0f;
-                if (ina) tmp[m++] = a;
-                if (ina != inb) {  // always interpolate from the inside vertex so that shared edges clip identically
-                    if (ina) tmp[m++] = lerpVert(a, b, da / (da - db));
-                    else tmp[m++] = lerpVert(b, a, db / (db - da));
-                }
-            }
-            n = m;
-            for (int i = 0; i < n; ++i) poly[t][i] = tmp[i];
-        }
-        if (n < 3) continue;
-        cnt[t] = n;
-        for (int i = 0; i < n; ++i) scr[t][i] = projectVert(poly[t][i], hw, hh);
-        for (int k = 1; k + 1 < n; ++k)
-            if (triBox(cx, scr[t][0], scr[t][k], scr[t][k + 1], box[t][k - 1])) { vis |= 1u << (t * 4 + k - 1); ++total; }
-    }
-    if (!total) return false;
-    int slot = reserveTris(cx, total);
-    if (slot < 0) return true;
-    for (int t = 0; t < nSrc; ++t)
-        for (int k = 1; k + 1 < cnt[t]; ++k)
-            if (vis & (1u << (t * 4 + k - 1)))
-                writeTri(cx, slot++, poly[t][0], poly[t][k], poly[t][k + 1], scr[t][0], scr[t][k], scr[t][k + 1], box[t][k - 1], color, keyBase + uint32_t(t));
-    return false;
-}
-
 __device__ __forceinline__ bool insideNearFar(const ClipVert &v) { return v.cz >= 0.0f && (v.cw - v.cz) >= 0.0f; }
 
-// one box face: four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern); true when the list was full
-__device__ __forceinline__ bool setupFace(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, const ClipVert &v3, int color, uint32_t keyBase) {
-    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) return clipSlow(cx, v0, v1, v2, v3, 2, color, keyBase);
+enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appended (or invisible) / the list is full / crosses the near or far plane
+
+// one box face: four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern)
+__device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, const ClipVert &v3, int color,
+                                                 uint32_t keyBase) {
+    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) return kSetupClip;
     const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
     const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh), s3 = projectVert(v3, hw, hh);
     TriBox b0, b1;
     const bool vis0 = triBox(cx, s0, s1, s2, b0), vis1 = triBox(cx, s0, s2, s3, b1);
     const int n = (vis0 ? 1 : 0) + (vis1 ? 1 : 0);
-    if (!n) return false;
+    if (!n) return kSetupDone;
     int slot = reserveTris(cx, n);
-    if (slot < 0) return true;
+    if (slot < 0) return kSetupFull;
     if (vis0) writeTri(cx, slot++, v0, v1, v2, s0, s1, s2, b0, color, keyBase);
     if (vis1) writeTri(cx, slot, v0, v2, v3, s0, s2, s3, b1, color, keyBase + 1u);
-    return false;
+    return kSetupDone;
 }
 // one mesh triangle
-__device__ __forceinline__ bool setupTri(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, int color, uint32_t key) {
-    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) return clipSlow(cx, v0, v1, v2, v2, 1, color, key);
+__device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, int color, uint32_t key) {
+    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) return kSetupClip;
     const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
     const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh);
     TriBox b0;
-    if (!triBox(cx, s0, s1, s2, b0)) return false;
+    if (!triBox(cx, s0, s1, s2, b0)) return kSetupDone;
     const int slot = reserveTris(cx, 1);
-    if (slot < 0) return true;
+    if (slot < 0) return kSetupFull;
     writeTri(cx, slot, v0, v1, v2, s0, s1, s2, b0, color, key);
-    return false;
+    return kSetupDone;
+}
+
+// Sutherland-Hodgman of one triangle against z >= 0 and z <= w, polygon and scratch in SHARED memory (dynamic indexing: the
+// same loop over per-thread arrays lives in local memory and stalls a whole CTA behind one thread).  Returns the vertex count (0: gone).
+__device__ __forceinline__ int clipNearFar(ClipVert *poly, ClipVert *tmp) {
+    int n = 3;
+    for (int plane = 0; plane < 2; ++plane) {
+        int m = 0;
+        for (int i = 0; i < n; ++i) {
+            const ClipVert a = poly[i];
+            const ClipVert b = poly[i + 1 == n ? 0 : i + 1];
+            const float da = plane == 0 ? a.cz : a.cw - a.cz;
+            const float db = plane == 0 ? b.cz : b.cw - b.cz;
+            const bool ina = da >= 0.0f, inb = db >= 0.0f;
+            if (ina) tmp[m++] = a;
+            if (ina != inb) {  // always interpolate from the inside vertex so that shared edges clip identically
+                if (ina) tmp[m++] = lerpVert(a, b, da / (da - db));
+                else tmp[m++] = lerpVert(b, a, db / (db - da));
+            }
+        }
+        n = m;
+        for (int i = 0; i < n; ++i) poly[i] = tmp[i];
+        if (n < 3) return 0;
+    }
+    return n;
 }
 
 // uber.vert:53-110 for one vertex; mv = rows 0..2 of the model-view matrix's four columns, nm = inverse transpose of its 3x3
@@ -647,6 +629,8 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(V
     unsigned long long *fragAll = reinterpret_cast<unsigned long long *>(smem + L.frag);
     float *meshV = reinterpret_cast<float *>(smem + L.meshV);    // [kMeshVerts][6]
     uint8_t *meshI = smem + L.meshI;
+    uint16_t *slowAll = reinterpret_cast<uint16_t *>(smem + L.slow);  // [2][kThreads]: instance-in-chunk | item << 7 | done << 15
+    ClipVert *clipScratch = reinterpret_cast<ClipVert *>(smem + L.clip) + (threadIdx.x >> 5) * 4 * kClipVerts;
     ViewMisc &M = *reinterpret_cast<ViewMisc *>(smem + L.misc);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -707,6 +691,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(V
             M.nTris = 0;
             M.nValid = 0x7fffffff;
             M.tileCtr = 0;
+            M.nSlow[0] = 0; M.nSlow[1] = 0;
         }
         __syncthreads();
         if (tid < 16) M.view[tid] = __ldcg(P.views + size_t(view) * 16 + tid);
@@ -725,7 +710,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(V
 
         SetupCtx cx;
         cx.cover = cover; cx.shade = shade; cx.nTris = &M.nTris; cx.nValid = &M.nValid; cx.triCap = P.triCap; cx.W = P.W; cx.H = P.H; cx.rowLo = rowLo; cx.rowHi = rowHi;
-        int batch = 0;
+        int batch = 0, parity = 0;
 
         for (int c = 0; c < nChunks; ++c) {
             const int buf = c & 1;
@@ -805,13 +790,15 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(V
                 __syncthreads();
             }
             const int totalItems = off[kInstChunk];
-            // ---- item pass: one thread per visible box face / mesh triangle; items that do not fit the list wait for the next batch
-            for (int ibase = 0; ibase < totalItems; ibase += kThreads) {
+            // ---- item pass: one thread per visible box face / mesh triangle.  Items that do not fit the list wait for the next batch;
+            // items crossing the near / far plane go to a short list that the warps then clip co-operatively (see slowItem)
+            for (int ibase = 0; ibase < totalItems; ibase += kThreads, parity ^= 1) {
                 const int j = ibase + tid;
-                bool pending = j < totalItems;
+                uint16_t *slowList = slowAll + parity * kThreads;
+                if (tid == 0) M.nSlow[parity ^ 1] = 0;  // the other list: last read before the barrier that closed the previous sub-pass
+                bool pending = j < totalItems, pushed = false, again = false;
                 for (;;) {
                     if (pending) {
-                        bool overflow;
                         int lo = 0, hi = cCnt - 1;  // largest i with off[i] <= j (instances without items share their successor's offset)
                         while (lo < hi) {
                             const int mid = (lo + hi + 1) >> 1;
@@ -827,27 +814,102 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(V
                         const int meta = __float_as_int(xf[22 * kInstChunk + i]);
                         const int mesh = meta & 255;
                         const uint32_t ii = uint32_t(cBase + i);
+                        SetupResult res;
                         if (mesh == 0) {
                             const int face = __fns(unsigned(meta >> 8), 0, sub + 1);
                             ClipVert cvt[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) cvt[k] = makeVert(mv, nm, meshV + (face * 4 + k) * 6, P.p00, P.p11, P.p22, P.p32);
-                            const uint32_t keyBase = ii * 128u + uint32_t(face) * 2u + 1u;
-                            overflow = setupFace(cx, cvt[0], cvt[1], cvt[2], cvt[3], color, keyBase);
+                            res = setupFace(cx, cvt[0], cvt[1], cvt[2], cvt[3], color, ii * 128u + uint32_t(face) * 2u + 1u);
                         } else {
                             const int vBase = mesh == 1 ? kVCapsule : (mesh == 2 ? kVSphere : (mesh == 3 ? kVCone : kVCylinder));
                             const int iBase = mesh == 1 ? kICapsule : (mesh == 2 ? kISphere : (mesh == 3 ? kICone : kICylinder));
                             ClipVert cvt[3];
 #pragma unroll
                             for (int k = 0; k < 3; ++k) cvt[k] = makeVert(mv, nm, meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6, P.p00, P.p11, P.p22, P.p32);
-                            overflow = setupTri(cx, cvt[0], cvt[1], cvt[2], color, ii * 128u + uint32_t(sub) + 1u);
+                            res = setupTri(cx, cvt[0], cvt[1], cvt[2], color, ii * 128u + uint32_t(sub) + 1u);
                         }
-                        pending = overflow;
+                        pending = res == kSetupFull;
+                        if (res == kSetupClip) {
+                            int at;
+                            asm volatile("atom.shared.add.s32 %0, [%1], 1;" : "=r"(at) : "r"(smemAddrOf(&M.nSlow[parity])) : "memory");
+                            slowList[at] = uint16_t(i | (sub << 7));
+                            pushed = true;
+                        }
                     }
-                    if (!__syncthreads_or(pending ? 1 : 0)) break;
-                    // the list is full: draw what it holds, then retry the items that did not fit
+                    const bool any = __syncthreads_or((pending || pushed) ? 1 : 0) || again;
+                    pushed = false;
+                    if (!any) break;
+                    // ---- clipped items, one warp each
+                    bool slowFull = false;
+                    const int nSlow = M.nSlow[parity];
+                    for (int sidx = warp; sidx < nSlow; sidx += kWarps) {
+                        const int e = slowList[sidx];
+                        if (e & 0x8000) continue;  // done in an earlier round
+                        const int i = e & 127, sub = (e >> 7) & 127;
+                        float mv[12], nm[9];
+#pragma unroll
+                        for (int q = 0; q < 12; ++q) mv[q] = xf[q * kInstChunk + i];
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) nm[q] = xf[(12 + q) * kInstChunk + i];
+                        const int color = __float_as_int(xf[21 * kInstChunk + i]);
+                        const int meta = __float_as_int(xf[22 * kInstChunk + i]);
+                        const int mesh = meta & 255;
+                        const uint32_t ii = uint32_t(cBase + i);
+                        ClipVert *poly0 = clipScratch, *poly1 = clipScratch + kClipVerts, *tmp0 = clipScratch + 2 * kClipVerts, *tmp1 = clipScratch + 3 * kClipVerts;
+                        int nSrc;
+                        uint32_t keyBase;
+                        if (mesh == 0) {  // lanes 0..3: the face's vertices; source triangles (0,1,2) and (0,2,3)
+                            const int face = __fns(unsigned(meta >> 8), 0, sub + 1);
+                            nSrc = 2; keyBase = ii * 128u + uint32_t(face) * 2u + 1u;
+                            if (lane < 4) {
+                                const ClipVert v = makeVert(mv, nm, meshV + (face * 4 + lane) * 6, P.p00, P.p11, P.p22, P.p32);
+                                if (lane == 0) { poly0[0] = v; poly1[0] = v; }
+                                else if (lane == 1) poly0[1] = v;
+                                else if (lane == 2) { poly0[2] = v; poly1[1] = v; }
+                                else poly1[2] = v;
+                            }
+                        } else {
+                            const int vBase = mesh == 1 ? kVCapsule : (mesh == 2 ? kVSphere : (mesh == 3 ? kVCone : kVCylinder));
+                            const int iBase = mesh == 1 ? kICapsule : (mesh == 2 ? kISphere : (mesh == 3 ? kICone : kICylinder));
+                            nSrc = 1; keyBase = ii * 128u + uint32_t(sub) + 1u;
+                            if (lane < 3) poly0[lane] = makeVert(mv, nm, meshV + (vBase + int(meshI[iBase + sub * 3 + lane])) * 6, P.p00, P.p11, P.p22, P.p32);
+                        }
+                        __syncwarp();
+                        int nv = 0;
+                        if (lane < nSrc) nv = clipNearFar(lane ? poly1 : poly0, lane ? tmp1 : tmp0);  // one lane per source triangle
+                        __syncwarp();
+                        const int n0 = __shfl_sync(0xffffffffu, nv, 0), n1 = __shfl_sync(0xffffffffu, nv, 1);
+                        // fan pieces (0, k, k+1), at most three per source triangle: one lane each; the pieces of one source triangle share
+                        // its key (coplanar and disjoint, they never tie on a pixel)
+                        const int t = lane / 3, k = lane - t * 3 + 1;
+                        const ClipVert *pp = t ? poly1 : poly0;
+                        bool vis = false;
+                        TriBox tb;
+                        ScreenVert sa, sb, sc;
+                        if (lane < 6 && k + 1 < (t ? n1 : n0)) {
+                            const float hw = float(P.W) * 0.5f, hh = float(P.H) * 0.5f;
+                            sa = projectVert(pp[0], hw, hh); sb = projectVert(pp[k], hw, hh); sc = projectVert(pp[k + 1], hw, hh);
+                            vis = triBox(cx, sa, sb, sc, tb);
+                        }
+                        const unsigned vm = __ballot_sync(0xffffffffu, vis);
+                        bool done = true;
+                        if (vm) {
+                            int base = 0;
+                            if (lane == 0) base = reserveTris(cx, __popc(vm));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (base < 0) done = false;
+                            else if (vis) writeTri(cx, base + __popc(vm & ((1u << lane) - 1u)), pp[0], pp[k], pp[k + 1], sa, sb, sc, tb, color, keyBase + uint32_t(t));
+                        }
+                        if (done) { if (lane == 0) slowList[sidx] = uint16_t(e | 0x8000); }
+                        else slowFull = true;
+                        __syncwarp();  // the scratch polygons are rewritten by the warp's next entry
+                    }
+                    if (!__syncthreads_or((pending || slowFull) ? 1 : 0)) break;
+                    // the list is full: draw what it holds, then retry what did not fit
                     tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, false);
                     ++batch;
+                    again = true;
                     __syncthreads();
                     if (tid == 0) { M.nTris = 0; M.nValid = 0x7fffffff; M.tileCtr = 0; }
                     __syncthreads();

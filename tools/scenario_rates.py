@@ -32,5 +32,5 @@ for scenario, E, A, depth in CONFIGS:
         g.sync()
         ks.append(g.last_kernel_ms())
     ks = np.array(ks[5:]).mean(axis=0)
-    print("%-14s E=%-5d A=%d depth=%d: %.3f ms/step = %.2fM obs/s; step kernel %.3f ms, raster %.3f ms; faults %d" % (scenario, E, A, depth, dt * 1e3, E * A / dt / 1e6, ks[0], ks[1], g.faults()))
+    print("%-14s E=%-5d A=%d depth=%d: %.3f ms/step = %.2fM obs/s; step kernel %.3f ms, raster %.3f ms; faults %d" % (scenario, E, A, depth, dt * 1e3, E * A / dt / 1e6, ks[0], ks[1], g.faults()), g.raster_config())
     g.close()
