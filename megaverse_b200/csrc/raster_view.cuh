@@ -51,7 +51,13 @@ struct __align__(16) TriShade {  // what deferred shading reads for the winning 
 };
 static_assert(sizeof(TriCover) == 80 && sizeof(TriShade) == 96, "triangle record layout");
 
-constexpr int kThreads = 256;     // per CTA
+#ifndef MV_VIEW_THREADS
+#define MV_VIEW_THREADS 256
+#endif
+#ifndef MV_VIEW_MIN_CTAS
+#define MV_VIEW_MIN_CTAS 2
+#endif
+constexpr int kThreads = MV_VIEW_THREADS;     // per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kInstChunk = 128;   // instances per TMA chunk (one thread each in the instance pass)
 constexpr int kXfWords = 23;      // per instance: model-view (12: three rows of each column), normal matrix (9), colour, mesh | face mask << 8
@@ -150,7 +156,8 @@ __device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parit
     } while (!done);
 }
 
-struct ClipVert { float cx, cy, cz, cw, px, py, pz, nx, ny, nz; };
+struct ClipVert { float cx, cy, cz, cw, px, py, pz, nx, ny, nz; };  // clipNearFar indexes it as float[10]
+static_assert(sizeof(ClipVert) == 40, "ClipVert is ten floats");
 
 __device__ __forceinline__ ClipVert lerpVert(const ClipVert &a, const ClipVert &b, float t) {
     ClipVert o;
@@ -248,7 +255,12 @@ enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appende
 // one box face: four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern)
 __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, const ClipVert &v3, int color,
                                                  uint32_t keyBase) {
-    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) return kSetupClip;
+    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) {
+        // wholly behind the near plane or wholly beyond the far plane: clipping would leave nothing
+        if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f && v3.cz < 0.0f) return kSetupDone;
+        if ((v0.cw - v0.cz) < 0.0f && (v1.cw - v1.cz) < 0.0f && (v2.cw - v2.cz) < 0.0f && (v3.cw - v3.cz) < 0.0f) return kSetupDone;
+        return kSetupClip;
+    }
     const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
     const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh), s3 = projectVert(v3, hw, hh);
     TriBox b0, b1;
@@ -263,7 +275,11 @@ __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipV
 }
 // one mesh triangle
 __device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, int color, uint32_t key) {
-    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) return kSetupClip;
+    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) {
+        if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f) return kSetupDone;
+        if ((v0.cw - v0.cz) < 0.0f && (v1.cw - v1.cz) < 0.0f && (v2.cw - v2.cz) < 0.0f) return kSetupDone;
+        return kSetupClip;
+    }
     const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
     const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh);
     TriBox b0;
@@ -274,26 +290,35 @@ __device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVe
     return kSetupDone;
 }
 
-// Sutherland-Hodgman of one triangle against z >= 0 and z <= w, polygon and scratch in SHARED memory (dynamic indexing: the
-// same loop over per-thread arrays lives in local memory and stalls a whole CTA behind one thread).  Returns the vertex count (0: gone).
-__device__ __forceinline__ int clipNearFar(ClipVert *poly, ClipVert *tmp) {
+// Sutherland-Hodgman of one triangle against z >= 0 and z <= w by a group of 16 lanes: lane c < 10 owns component c of every vertex
+// (ClipVert is ten floats), the in/out decisions are the same for all lanes of the group (broadcast reads of the z and w components).
+// Polygon and scratch live in SHARED memory (ten floats per vertex, kClipVerts vertices each).  The input triangle is in bufA, so is
+// the result; returns the vertex count (0: nothing left).
+__device__ __forceinline__ int clipNearFar(float *bufA, float *bufB, int c, unsigned groupMask) {
+    float *src = bufA, *dst = bufB;
     int n = 3;
     for (int plane = 0; plane < 2; ++plane) {
         int m = 0;
         for (int i = 0; i < n; ++i) {
-            const ClipVert a = poly[i];
-            const ClipVert b = poly[i + 1 == n ? 0 : i + 1];
-            const float da = plane == 0 ? a.cz : a.cw - a.cz;
-            const float db = plane == 0 ? b.cz : b.cw - b.cz;
+            const int i1 = i + 1 == n ? 0 : i + 1;
+            const float az = src[i * 10 + 2], aw = src[i * 10 + 3], bz = src[i1 * 10 + 2], bw = src[i1 * 10 + 3];
+            const float da = plane == 0 ? az : aw - az;
+            const float db = plane == 0 ? bz : bw - bz;
             const bool ina = da >= 0.0f, inb = db >= 0.0f;
-            if (ina) tmp[m++] = a;
-            if (ina != inb) {  // always interpolate from the inside vertex so that shared edges clip identically
-                if (ina) tmp[m++] = lerpVert(a, b, da / (da - db));
-                else tmp[m++] = lerpVert(b, a, db / (db - da));
+            float a = 0.0f, b = 0.0f;
+            if (c < 10) { a = src[i * 10 + c]; b = src[i1 * 10 + c]; }
+            if (ina) { if (c < 10) dst[m * 10 + c] = a; ++m; }
+            if (ina != inb) {  // always interpolate from the inside vertex so that shared edges clip identically (lerpVert)
+                float val;
+                if (ina) { const float t = da / (da - db); val = a + t * (b - a); }
+                else { const float t = db / (db - da); val = b + t * (a - b); }
+                if (c < 10) dst[m * 10 + c] = val;
+                ++m;
             }
         }
+        __syncwarp(groupMask);
         n = m;
-        for (int i = 0; i < n; ++i) poly[i] = tmp[i];
+        float *sw = src; src = dst; dst = sw;
         if (n < 3) return 0;
     }
     return n;
@@ -618,7 +643,7 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
-template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(ViewParams P) {
+template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTAS) viewKernel(ViewParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const SmemLayout L = smemLayout(P.triCap);
     MvInstance *stage = reinterpret_cast<MvInstance *>(smem + L.stage);
@@ -876,10 +901,12 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, 2) viewKernel(V
                             if (lane < 3) poly0[lane] = makeVert(mv, nm, meshV + (vBase + int(meshI[iBase + sub * 3 + lane])) * 6, P.p00, P.p11, P.p22, P.p32);
                         }
                         __syncwarp();
-                        int nv = 0;
-                        if (lane < nSrc) nv = clipNearFar(lane ? poly1 : poly0, lane ? tmp1 : tmp0);  // one lane per source triangle
+                        int nv = 0;  // sixteen lanes per source triangle
+                        if ((lane >> 4) < nSrc)
+                            nv = clipNearFar(reinterpret_cast<float *>(lane >> 4 ? poly1 : poly0), reinterpret_cast<float *>(lane >> 4 ? tmp1 : tmp0), lane & 15,
+                                             0xffffu << (lane & 16));
                         __syncwarp();
-                        const int n0 = __shfl_sync(0xffffffffu, nv, 0), n1 = __shfl_sync(0xffffffffu, nv, 1);
+                        const int n0 = __shfl_sync(0xffffffffu, nv, 0), n1 = __shfl_sync(0xffffffffu, nv, 16);
                         // fan pieces (0, k, k+1), at most three per source triangle: one lane each; the pieces of one source triangle share
                         // its key (coplanar and disjoint, they never tie on a pixel)
                         const int t = lane / 3, k = lane - t * 3 + 1;

@@ -11,6 +11,8 @@ if len(sys.argv) > 1:
     CONFIGS = [(sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), len(sys.argv) > 4 and sys.argv[4] == "depth")]
 for scenario, E, A, depth in CONFIGS:
     g = capi.Engine(scenario, E, A, 128, 72, num_threads=16, depth=depth)
+    for k, v in [kv.split("=") for kv in os.environ.get("MV_OPTS", "").split(",") if kv]:
+        g.set_option(k, int(v))
     for e in range(E):
         g.seed_env(e, 42 + e)
     g.reset()
