@@ -76,8 +76,10 @@ int mv_get_reward_shaping(mv_handle h, int env, int agent, const char **keys, fl
 int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *keys, const float *vals, int n);
 
 /* options: "depth" (0/1, before first reset), "obs_to_host" (0/1: whether mv_step delivers the observation tensor to host
- * memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps let the rasteriser store rows straight into the pinned
- * host buffer instead of copying afterwards; the HBM copy returned by mv_obs_device is then only refreshed by mv_step_device),
+ * memory; 1 by default), "zero_copy" (-1/0/1, default -1 = by size: host-facing steps either let the rasteriser store rows straight into the
+ * pinned host buffer -- batches up to 24 MB of observations; the HBM tensor is then stale and mv_obs_device refuses it until the next
+ * mv_step_device -- or rasterise into HBM in "host_slices" launches (0 = by size, one per ~12 MB) whose downloads run on the copy
+ * engine while the next slice is drawn),
  * "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
  * "tri_cap" (32..1022, default 288: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
  * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
@@ -93,6 +95,11 @@ int mv_set_option(mv_handle h, const char *key, int value);
  * mv_step_device: like mv_step but takes the action masks from DEVICE memory (NULL = the engine's own buffer, see
  * mv_actions_device) and leaves the observation tensor on the device; rewards/dones still land on the host. */
 int mv_step_device(mv_handle h, const int32_t *d_masks);
+/* Redirect the HBM output of the rasteriser into caller-owned device memory: d_obs = uint8[N][h][w][4] (and d_depth = float[N][h][w]
+ * when option depth is on; NULL keeps the engine's own).  Lets several engines -- one per scenario of a multi-task batch, reference
+ * megaverse_env.py:27-39 -- write into slices of ONE contiguous tensor that a consumer or an NCCL gather reads without a staging copy.
+ * NULL, NULL restores the engine's own buffers.  Valid in the engine stream's order (mv_stream). */
+int mv_set_obs_buffer(mv_handle h, uint8_t *d_obs, float *d_depth);
 /* mv_step_device is ASYNCHRONOUS: it returns after enqueueing the step on the engine stream (device tensors are valid in
  * stream order).  mv_sync waits for everything enqueued and publishes the last step's rewards/dones/true objectives to the
  * host pointers.  Episode bookkeeping lags the device by two steps on this path, so it needs episodes of >= 4 steps
@@ -143,6 +150,9 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
 /* rasteriser launch shape: out4 = {persistent grid size, CTAs per SM, dynamic shared memory per CTA in bytes, row bands per view} */
 int mv_debug_raster_config(mv_handle h, int32_t *out4);
+/* rasteriser work counters since the last enable: out8 = {work items, instances read, instances with visible items, items (box faces /
+ * mesh triangles set up), items clipped at the near / far plane, triangles drawn, batches, -}; enable=1 arms / clears, 0 frees */
+int mv_debug_raster_stats(mv_handle h, unsigned long long *out8, int enable);
 /* host-only: colour tables of the generators + the rasteriser's palette (tests pin them against the reference's env/const.hpp) */
 int mv_debug_color_tables(uint32_t *out, int cap);
 /* host-only: default reward shaping ("R key=hexbits") and default float parameters ("P key=hexbits") of a scenario, one per line */

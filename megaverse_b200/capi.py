@@ -57,10 +57,10 @@ def lib():
 
 EXPORTS = [
     "mv_create", "mv_last_error", "mv_seed", "mv_seed_env", "mv_reset", "mv_set_actions", "mv_encode_action", "mv_step", "mv_step_begin", "mv_step_end", "mv_obs_host", "mv_depth_host",
-    "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device",
+    "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device", "mv_set_obs_buffer",
     "mv_sync", "mv_fetch_obs", "mv_draw_hires", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
-    "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_raster_config", "mv_debug_color_tables", "mv_debug_defaults", "mv_debug_count_unfit_levels", "mv_levels_skipped", "mv_debug_bzset", "mv_debug_generate_level",
+    "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_raster_config", "mv_debug_raster_stats", "mv_debug_color_tables", "mv_debug_defaults", "mv_debug_count_unfit_levels", "mv_levels_skipped", "mv_debug_bzset", "mv_debug_generate_level",
 ]
 
 
@@ -120,6 +120,11 @@ class Engine:
 
     def step_device(self, d_masks_ptr=None):
         self._ck(lib().mv_step_device(self._h, C.c_void_p(d_masks_ptr) if d_masks_ptr else None))
+
+    def set_obs_buffer(self, d_obs_ptr=None, d_depth_ptr=None):
+        """rasterise into caller-owned device memory (a slice of a larger tensor) instead of the engine's own obs buffer"""
+        lib().mv_set_obs_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._ck(lib().mv_set_obs_buffer(self._h, C.c_void_p(d_obs_ptr) if d_obs_ptr else None, C.c_void_p(d_depth_ptr) if d_depth_ptr else None))
 
     def sync(self):
         self._ck(lib().mv_sync(self._h))
@@ -213,6 +218,13 @@ class Engine:
         lib().mv_debug_raster_config.argtypes = [C.c_void_p, C.c_void_p]
         self._ck(lib().mv_debug_raster_config(self._h, out))
         return {"grid": out[0], "ctas_per_sm": out[1], "smem": out[2], "bands": out[3]}
+
+    def raster_stats(self, enable=True, read=True):
+        out = (C.c_ulonglong * 8)()
+        lib().mv_debug_raster_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        self._ck(lib().mv_debug_raster_stats(self._h, out if read else None, 1 if enable else 0))
+        names = ["work_items", "instances", "visible_instances", "items", "clipped_items", "triangles", "batches"]
+        return {n: int(out[i]) for i, n in enumerate(names)}
 
     def last_kernel_ms(self):
         out = (C.c_float * 2)()

@@ -124,8 +124,15 @@ struct mv_engine {
     bool hostStepPending = false;  // between mv_step_begin and mv_step_end
     bool skipUnfitLevels = false;  // option "skip_unfit_levels": replace a level that exceeds a fixed capacity by the stream's next one
     std::atomic<int> levelsSkipped{0};
-    bool zeroCopy = true;  // host-facing steps: the raster kernel stores the obs rows straight into pinned host memory (no D2H copy after it)
+    // host delivery of the obs tensor (host-facing steps).  zero copy: the raster kernel stores the rows straight into pinned host
+    // memory (best for small batches: no second pass).  Sliced: the views are rasterised in a few launches and each slice goes down on
+    // the copy engine (second stream) while the next one is rasterised (best when PCIe time exceeds raster time).  -1 = by size.
+    int zeroCopyOpt = -1, hostSlicesOpt = 0;
     bool rasterToHost = false;
+    bool deviceObsFresh = false;   // the HBM obs tensor holds the last step's frames (false after a zero-copy host-facing step)
+    int sliceCount = 1;            // this launch: > 1 = sliced download on copyStream
+    cudaStream_t copyStream = nullptr;
+    std::vector<cudaEvent_t> sliceEv;
     int numSMs = 148;
     MvConsts consts{};
 
@@ -150,11 +157,14 @@ struct mv_engine {
     DevBuf<float> d_trueObj;
     DevBuf<uint8_t> d_obs;
     DevBuf<float> d_depth;
+    uint8_t *obsOut = nullptr;     // where the rasteriser writes in HBM: d_obs, or the caller's tensor slice (mv_set_obs_buffer)
+    float *depthOut = nullptr;
     DevBuf<int32_t> d_faults;
     // rasteriser (raster_view.cuh): a persistent grid of CTAs pulling (view, band) items from a never-reset counter
     DevBuf<uint32_t> d_workCounter;
     uint32_t counterBase = 0;          // what the counter read before the next launch's first claim
     DevBuf<unsigned long long> d_spill;  // [rasterGrid][spillStride]
+    DevBuf<unsigned long long> d_rasterStats;  // mv_debug_raster_stats only
     int rasterGrid = 0, rasterCtasPerSM = 0, spillStride = 0, rasterBands = 1;
     size_t rasterSmem = 0;
     // hi-res pass (draw_hires): its own output buffers, allocated on first use
@@ -304,13 +314,40 @@ struct mv_engine {
         mvr::ViewParams vp = {};
         vp.instances = d_inst.p; vp.instCounts = d_instCounts.p; vp.views = d_views.p; vp.instStride = instCap;
         // pinned allocations are mapped into the device address space (UVA), so the kernel can store through the host pointer
-        vp.obs = rasterToHost ? h_obs.p : d_obs.p; vp.depth = wantDepth ? (rasterToHost ? h_depth.p : d_depth.p) : nullptr;
-        vp.spill = d_spill.p; vp.spillStride = spillStride; vp.consumed = nullptr;
-        vp.N = N; vp.A = A; vp.W = W; vp.H = H; vp.bands = rasterBands; vp.bandRows = ((H / 4 + rasterBands - 1) / rasterBands) * 4; vp.triCap = triCap;
+        vp.obs = rasterToHost ? h_obs.p : obsOut; vp.depth = wantDepth ? (rasterToHost ? h_depth.p : depthOut) : nullptr;
+        vp.spill = d_spill.p; vp.spillStride = spillStride; vp.consumed = nullptr; vp.stats = d_rasterStats.p;
+        vp.A = A; vp.W = W; vp.H = H; vp.bands = rasterBands; vp.bandRows = ((H / 4 + rasterBands - 1) / rasterBands) * 4; vp.triCap = triCap;
         vp.p00 = consts.p00; vp.p11 = consts.p11; vp.p22 = consts.p22; vp.p32 = consts.p32;
         // programmatic dependent launch: the grid may start before the step kernel has drained; a CTA waits for its env's stamp
         vp.ready = overlap ? d_ready.p : nullptr; vp.readyStamp = overlap ? readyStamp : 0;
-        return launchView(vp, std::min(rasterGrid, N * rasterBands), overlap);
+        deviceObsFresh = !rasterToHost;
+        if (sliceCount <= 1) {
+            vp.viewBase = 0; vp.N = N;
+            return launchView(vp, std::min(rasterGrid, N * rasterBands), overlap);
+        }
+        // sliced download: whole envs per slice; slice s is copied down by the copy engine while slice s+1 is rasterised
+        const size_t px = size_t(W) * H;
+        const int perSlice = ((E + sliceCount - 1) / sliceCount) * A;
+        for (int base = 0, si = 0; base < N; base += perSlice, ++si) {
+            const int cnt = std::min(perSlice, N - base);
+            vp.viewBase = base; vp.N = cnt;
+            const int rc = launchView(vp, std::min(rasterGrid, cnt * rasterBands), overlap && si == 0);
+            if (rc) return rc;
+            while (int(sliceEv.size()) <= si) { cudaEvent_t e2; MV_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); sliceEv.push_back(e2); }
+            MV_CUDA(cudaEventRecord(sliceEv[size_t(si)], stream));
+            MV_CUDA(cudaStreamWaitEvent(copyStream, sliceEv[size_t(si)], 0));
+            MV_CUDA(cudaMemcpyAsync(h_obs.p + size_t(base) * px * 4, obsOut + size_t(base) * px * 4, size_t(cnt) * px * 4, cudaMemcpyDeviceToHost, copyStream));
+            if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, depthOut + size_t(base) * px, sizeof(float) * size_t(cnt) * px, cudaMemcpyDeviceToHost, copyStream));
+        }
+        return MV_OK;
+    }
+    // how a host-facing step delivers its obs: returns the slice count (0 = zero-copy stores, 1 = one copy after the raster)
+    int hostDelivery() const {
+        const size_t bytes = size_t(N) * W * H * (wantDepth ? 8 : 4);
+        const bool zc = zeroCopyOpt < 0 ? bytes <= (size_t(24) << 20) : zeroCopyOpt != 0;
+        if (zc) return 0;
+        if (hostSlicesOpt > 0) return std::min(hostSlicesOpt, E);
+        return int(std::max<size_t>(1, std::min<size_t>({size_t(16), size_t(E), bytes / (size_t(12) << 20)})));
     }
     // draw_hires (megaverse.cpp:154-177): every agent view once more, at (w, h), from the instance lists and camera matrices of
     // the last step -- the same kernel over row bands of the large frame.  Result in hires.h_obs, uint8[N][h][w][4].
@@ -340,7 +377,7 @@ struct mv_engine {
         mvr::ViewParams vp = {};
         vp.instances = d_inst.p; vp.instCounts = d_instCounts.p; vp.views = d_views.p; vp.instStride = instCap;
         vp.obs = hires.d_obs.p; vp.depth = nullptr; vp.spill = hires.spill.p; vp.spillStride = stride; vp.consumed = nullptr;
-        vp.N = N; vp.A = A; vp.W = w; vp.H = hgt; vp.bands = bands; vp.bandRows = rowsPerBand; vp.triCap = triCap;
+        vp.viewBase = 0; vp.N = N; vp.A = A; vp.W = w; vp.H = hgt; vp.bands = bands; vp.bandRows = rowsPerBand; vp.triCap = triCap;
         vp.p00 = k.p00; vp.p11 = k.p11; vp.p22 = k.p22; vp.p32 = k.p32;
         vp.ready = nullptr; vp.readyStamp = 0;
         rc = launchView(vp, std::min(rasterGrid, N * bands), false);
@@ -396,12 +433,13 @@ struct mv_engine {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        if (copyObs && !rasterToHost) {
-            MV_CUDA(cudaMemcpyAsync(h_obs.p, d_obs.p, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
-            if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, d_depth.p, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
+        if (copyObs && !rasterToHost && sliceCount <= 1) {
+            MV_CUDA(cudaMemcpyAsync(h_obs.p, obsOut, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
+            if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, depthOut, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
         if (!wait) return MV_OK;
         MV_CUDA(cudaStreamSynchronize(stream));
+        if (sliceCount > 1) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         return MV_OK;
     }
@@ -443,7 +481,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        rasterToHost = false;
+        rasterToHost = false; sliceCount = 1;
         rc = launchStep(dActions, false, &slotP);  // rewards / dones / true objectives land in the ring slot straight from the kernel
         if (rc) return rc;
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
@@ -463,7 +501,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        rasterToHost = copyObs && zeroCopy;
+        { const int d = copyObs ? hostDelivery() : 1; rasterToHost = copyObs && d == 0; sliceCount = std::max(1, d); }
         rc = launchStep(dActions, false);
         if (rc) return rc;
         rc = finishStep(copyObs, !split);
@@ -476,6 +514,7 @@ struct mv_engine {
     int stepEnd() {
         if (!hostStepPending) { setError("mv_step_end without mv_step_begin"); return MV_ERR_STATE; }
         MV_CUDA(cudaStreamSynchronize(stream));
+        if (sliceCount > 1) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         hostStepPending = false;
         std::memset(h_actions.p, 0, sizeof(int32_t) * N);  // env.cpp:140-142: actions are cleared after every step
@@ -487,11 +526,14 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free();
+        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &p : ring) { if (p.ev) { cudaEventDestroy(p.ev); p.ev = nullptr; } p.rewards.free(); p.trueObj.free(); p.dones.free(); }
+        for (auto &e2 : sliceEv) if (e2) cudaEventDestroy(e2);
+        sliceEv.clear();
+        if (copyStream) { cudaStreamDestroy(copyStream); copyStream = nullptr; }
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
     }
 };
@@ -594,7 +636,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
 
     auto ck = [&](cudaError_t err, const char *what) { if (err != cudaSuccess) { e->setError(std::string(what) + ": " + cudaGetErrorString(err)); return false; } return true; };
     const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
-    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream");
+    bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream") && ck(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking), "copy stream");
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
     ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
@@ -624,6 +666,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(cudaMemset(e->d_actions.p, 0, sizeof(int32_t) * N), "memset") && ck(cudaMemset(e->d_agents.p, 0, sizeof(MvAgent) * N), "memset") &&
          ck(cudaMemset(e->d_objects.p, 0, sizeof(MvObject) * E * MV_MAX_OBJECTS), "memset");
     if (!ok) return fail(MV_ERR_CUDA);
+    e->obsOut = e->d_obs.p;
     if (uploadPalette(e) != MV_OK) return fail(MV_ERR_CUDA);
     if (setKernelAttrs(e) != MV_OK) return fail(MV_ERR_CUDA);
     *out = e;
@@ -639,6 +682,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         if (h->wantDepth && !h->d_depth.p) {
             const size_t cnt = size_t(h->N) * h->W * h->H;
             if (h->d_depth.alloc(cnt) != cudaSuccess || h->h_depth.alloc(cnt) != cudaSuccess) { h->setError("depth allocation failed"); return MV_ERR_CUDA; }
+            if (!h->depthOut) h->depthOut = h->d_depth.p;
         }
         return MV_OK;
     }
@@ -656,7 +700,8 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         return h->configureRaster();
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
-    if (k == "zero_copy") { h->zeroCopy = value != 0; return MV_OK; }
+    if (k == "zero_copy") { h->zeroCopyOpt = value < 0 ? -1 : (value != 0); return MV_OK; }
+    if (k == "host_slices") { if (value < 0 || value > 64) return MV_ERR_ARG; h->hostSlicesOpt = value; return MV_OK; }
     if (k == "skip_unfit_levels") { h->skipUnfitLevels = value != 0; return MV_OK; }
     if (k == "fast_shading") { h->fastShading = value != 0; return MV_OK; }
     if (k == "overlap") { cudaStreamSynchronize(h->stream); h->overlap = value != 0; return MV_OK; }
@@ -717,7 +762,7 @@ int mv_reset(mv_handle h) {
         if (cudaMemcpyAsync(h->d_rtable.p, h->h_rtable.p, sizeof(float) * h->N * MV_R_COUNT, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("rtable upload failed"); return MV_ERR_CUDA; }
         h->rtableDirty = false;
     }
-    h->rasterToHost = h->obsToHost && h->zeroCopy;
+    { const int d = h->obsToHost ? h->hostDelivery() : 1; h->rasterToHost = h->obsToHost && d == 0; h->sliceCount = std::max(1, d); }
     rc = h->launchStep(h->d_actions.p, true);
     if (rc) return rc;
     rc = h->finishStep(h->obsToHost);
@@ -835,9 +880,10 @@ int mv_fetch_obs(mv_handle h) {
     if (h->hostStepPending) { const int rcp = h->stepEnd(); if (rcp) return rcp; }
     const int rc = h->drain();
     if (rc) return rc;
+    if (!h->deviceObsFresh) return MV_OK;  // the last step stored its frames straight into the host buffer: that copy is the newer one
     const size_t px = size_t(h->N) * h->W * h->H;
-    if (cudaMemcpyAsync(h->h_obs.p, h->d_obs.p, px * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { h->setError("obs download failed"); return MV_ERR_CUDA; }
-    if (h->wantDepth && cudaMemcpyAsync(h->h_depth.p, h->d_depth.p, px * sizeof(float), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { h->setError("depth download failed"); return MV_ERR_CUDA; }
+    if (cudaMemcpyAsync(h->h_obs.p, h->obsOut, px * 4, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { h->setError("obs download failed"); return MV_ERR_CUDA; }
+    if (h->wantDepth && cudaMemcpyAsync(h->h_depth.p, h->depthOut, px * sizeof(float), cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) { h->setError("depth download failed"); return MV_ERR_CUDA; }
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->setError("stream sync failed"); return MV_ERR_CUDA; }
     return MV_OK;
 }
@@ -870,9 +916,27 @@ int mv_depth_host(mv_handle h, const float **out) { if (!h || !out || !h->wantDe
 int mv_rewards(mv_handle h, const float **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_rewards.p; return MV_OK; }
 int mv_dones(mv_handle h, const uint8_t **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_dones.p; return MV_OK; }
 int mv_true_objectives(mv_handle h, const float **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_trueObj.p; return MV_OK; }
+int mv_set_obs_buffer(mv_handle h, uint8_t *d_obs, float *d_depth) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->obsOut = d_obs ? d_obs : h->d_obs.p;
+    h->depthOut = d_depth ? d_depth : h->d_depth.p;
+    return MV_OK;
+}
 int mv_actions_device(mv_handle h, int32_t **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_actions.p; return MV_OK; }
-int mv_obs_device(mv_handle h, uint8_t **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_obs.p; return MV_OK; }
-int mv_depth_device(mv_handle h, float **p) { if (!h || !p || !h->wantDepth) return MV_ERR_ARG; *p = h->d_depth.p; return MV_OK; }
+int mv_obs_device(mv_handle h, uint8_t **p) {
+    if (!h || !p) return MV_ERR_ARG;
+    if (h->didReset && !h->deviceObsFresh) { h->setError("the last step delivered its frames to the host buffer only (zero-copy): the HBM tensor is stale; use mv_step_device or option zero_copy=0"); return MV_ERR_STATE; }
+    *p = h->obsOut;
+    return MV_OK;
+}
+int mv_depth_device(mv_handle h, float **p) {
+    if (!h || !p || !h->wantDepth) return MV_ERR_ARG;
+    if (h->didReset && !h->deviceObsFresh) { h->setError("the last step delivered its frames to the host buffer only (zero-copy): the HBM tensor is stale"); return MV_ERR_STATE; }
+    *p = h->depthOut;
+    return MV_OK;
+}
 int mv_rewards_device(mv_handle h, float **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_rewards.p; return MV_OK; }
 int mv_dones_device(mv_handle h, uint8_t **p) { if (!h || !p) return MV_ERR_ARG; *p = h->d_dones.p; return MV_OK; }
 int mv_stream(mv_handle h, void **s) { if (!h || !s) return MV_ERR_ARG; *s = h->stream; return MV_OK; }
@@ -909,6 +973,19 @@ int mv_faults(mv_handle h, int32_t *out) {
     int32_t f = 0;
     for (int e = 0; e < h->E; ++e) f |= st[size_t(e)].faults | h->h_faults.p[e];
     *out = f;
+    return MV_OK;
+}
+// totals since enable: {work items, instances read, instances with visible items, items, clipped items, triangles, batches, -}
+int mv_debug_raster_stats(mv_handle h, unsigned long long *out8, int enable) {
+    if (!h) return MV_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return MV_ERR_CUDA;
+    cudaStreamSynchronize(h->stream);
+    if (out8 && h->d_rasterStats.p && cudaMemcpy(out8, h->d_rasterStats.p, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (enable && !h->d_rasterStats.p) {
+        if (h->d_rasterStats.alloc(8) != cudaSuccess) { h->setError("raster stats allocation failed"); return MV_ERR_CUDA; }
+    }
+    if (enable) cudaMemset(h->d_rasterStats.p, 0, 64);
+    else h->d_rasterStats.free();
     return MV_OK;
 }
 int mv_debug_raster_config(mv_handle h, int32_t *out4) {  // {persistent grid, CTAs per SM, dynamic shared memory bytes, row bands per view}
@@ -1127,7 +1204,7 @@ int mv_debug_render_instances(const float *view16, const float *inst18, int n, i
         mvr::ViewParams vp = {};
         vp.instances = dInst; vp.instCounts = dCnt; vp.views = dView; vp.instStride = int(inst.size()); vp.obs = dObs; vp.depth = depth ? dDepth : nullptr;
         vp.workCounter = dCtr; vp.counterBase = 0; vp.ready = nullptr; vp.readyStamp = 0; vp.consumed = nullptr; vp.spill = dSpill; vp.spillStride = w * bandRows;
-        vp.N = 1; vp.A = 1; vp.W = w; vp.H = h; vp.bands = bands; vp.bandRows = bandRows; vp.triCap = triCap;
+        vp.viewBase = 0; vp.N = 1; vp.A = 1; vp.W = w; vp.H = h; vp.bands = bands; vp.bandRows = bandRows; vp.triCap = triCap;
         vp.p00 = k.p00; vp.p11 = k.p11; vp.p22 = k.p22; vp.p32 = k.p32;
         mvr::viewKernel<false><<<bands, mvr::kThreads, smem>>>(vp);
         ok = cudaDeviceSynchronize() == cudaSuccess;

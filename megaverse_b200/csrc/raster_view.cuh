@@ -89,9 +89,11 @@ struct ViewParams {
     const uint32_t *ready;       // [E] step-kernel completion stamps (nullptr: plain stream order)
     uint32_t readyStamp;         // value ready[env] holds once this step's state, instances and views of env are written
     uint32_t *consumed;          // optional [E]: += 1 when a work item of env has read the env's instance list and view (step/raster overlap)
+    unsigned long long *stats;   // optional [8]: work items, instances, visible instances, items, clipped items, triangles, batches, - (debug)
     unsigned long long *spill;   // [gridDim.x][spillStride] per-CTA fragment slab for views drawn in several batches
     int spillStride;             // >= W * bandRows
-    int N, A, W, H;
+    int viewBase, N;             // this launch draws views [viewBase, viewBase + N)
+    int A, W, H;
     int bands, bandRows;         // bandRows: multiple of 4; bands * bandRows >= H
     int triCap;                  // triangle list capacity of a CTA (shared memory), <= kMaxTriCap
     float p00, p11, p22, p32;
@@ -107,6 +109,7 @@ struct ViewMisc {
     uint32_t claim;
     int32_t wsum[kWarps];
     int32_t nSlow[2];   // entries of the two slow-item lists (alternating per item sub-pass)
+    uint32_t stat[8];   // debug counters of the current work item
     alignas(8) unsigned long long bar[2];
 };
 __host__ __device__ inline SmemLayout smemLayout(int triCap) {
@@ -693,7 +696,8 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         __syncthreads();
         const uint32_t claim = M.claim;
         if (claim >= total) break;
-        const int view = int(claim / uint32_t(bands)), band = int(claim - uint32_t(view) * uint32_t(bands));
+        const int vrel = int(claim / uint32_t(bands)), band = int(claim - uint32_t(vrel) * uint32_t(bands));
+        const int view = P.viewBase + vrel;
         const int env = view / P.A;
         const int rowLo = band * P.bandRows, rowHi = min(P.H, rowLo + P.bandRows) - 1;
         const int bandTiles = tilesX * ((rowHi - rowLo + 1) >> 2);
@@ -717,6 +721,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
             M.nValid = 0x7fffffff;
             M.tileCtr = 0;
             M.nSlow[0] = 0; M.nSlow[1] = 0;
+            for (int q = 0; q < 8; ++q) M.stat[q] = 0;
         }
         __syncthreads();
         if (tid < 16) M.view[tid] = __ldcg(P.views + size_t(view) * 16 + tid);
@@ -796,6 +801,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                     }
                 }
                 xf[22 * kInstChunk + tid] = __int_as_float(meta);
+                if (P.stats && items) atomicAdd(&M.stat[2], 1u);
             }
             // exclusive scan of the item counts over the chunk
             {
@@ -815,6 +821,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                 __syncthreads();
             }
             const int totalItems = off[kInstChunk];
+            if (P.stats && tid == 0) { M.stat[1] += uint32_t(cCnt); M.stat[3] += uint32_t(totalItems); }
             // ---- item pass: one thread per visible box face / mesh triangle.  Items that do not fit the list wait for the next batch;
             // items crossing the near / far plane go to a short list that the warps then clip co-operatively (see slowItem)
             for (int ibase = 0; ibase < totalItems; ibase += kThreads, parity ^= 1) {
@@ -868,6 +875,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                     // ---- clipped items, one warp each
                     bool slowFull = false;
                     const int nSlow = M.nSlow[parity];
+                    if (P.stats && tid == 0 && !again) M.stat[4] += uint32_t(nSlow);
                     for (int sidx = warp; sidx < nSlow; sidx += kWarps) {
                         const int e = slowList[sidx];
                         if (e & 0x8000) continue;  // done in an earlier round
@@ -935,6 +943,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                     if (!__syncthreads_or((pending || slowFull) ? 1 : 0)) break;
                     // the list is full: draw what it holds, then retry what did not fit
                     tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, false);
+                    if (P.stats && tid == 0) M.stat[5] += uint32_t(min(M.nTris, M.nValid));
                     ++batch;
                     again = true;
                     __syncthreads();
@@ -950,6 +959,13 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         }
         tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
+        if (P.stats && tid < 8) {
+            unsigned long long v = M.stat[tid];
+            if (tid == 0) v = 1;
+            if (tid == 5) v += (unsigned long long)min(M.nTris, M.nValid);
+            if (tid == 6) v = (unsigned long long)(batch + 1);
+            atomicAdd(P.stats + tid, v);
+        }
     }
 }
 

@@ -597,10 +597,16 @@ def test_device_tensor_interface(built):
     g = capi.Engine("Collect", 4, 2, 128, 72, num_threads=2)
     g.seed(3); g.reset()
     g.step(np.full(8, 1 << 3, dtype=np.int32))
-    t = torch.as_tensor(g.device_array("obs"), device="cuda")
-    assert t.shape == (8, 72, 128, 4) and t.dtype == torch.uint8 and t.data_ptr() == g.device_ptr("obs")
+    # a small batch is delivered by zero-copy stores into the host buffer: the HBM tensor is stale and the engine says so
+    with pytest.raises(capi.MegaverseError):
+        g.device_array("obs")
+    host = np.array(g.obs()).copy()
+    g.fetch_obs()  # must not overwrite the (newer) host copy with the stale HBM tensor
+    assert np.array_equal(host, np.array(g.obs()))
     g.set_option("zero_copy", 0)  # make the kernel write HBM and copy down, so both copies exist
     g.step(np.full(8, 1 << 3, dtype=np.int32))
+    t = torch.as_tensor(g.device_array("obs"), device="cuda")
+    assert t.shape == (8, 72, 128, 4) and t.dtype == torch.uint8 and t.data_ptr() == g.device_ptr("obs")
     torch.cuda.synchronize()
     assert np.array_equal(t.cpu().numpy(), np.array(g.obs()))
     r = torch.as_tensor(g.device_array("rewards"), device="cuda")

@@ -34,5 +34,11 @@ for scenario, E, A, depth in CONFIGS:
         g.sync()
         ks.append(g.last_kernel_ms())
     ks = np.array(ks[5:]).mean(axis=0)
+    g.raster_stats(True, False)
+    for t in range(10):
+        g.step_device(acts.data_ptr() + t * E * A * 4)
+    g.sync()
+    st = g.raster_stats(False, True)
+    print("   per work item:", {k: round(v / max(1, st["work_items"]), 1) for k, v in st.items() if k != "work_items"})
     print("%-14s E=%-5d A=%d depth=%d: %.3f ms/step = %.2fM obs/s; step kernel %.3f ms, raster %.3f ms; faults %d" % (scenario, E, A, depth, dt * 1e3, E * A / dt / 1e6, ks[0], ks[1], g.faults()), g.raster_config())
     g.close()
