@@ -84,9 +84,12 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
  * "tri_cap" (32..1022, default 288: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
  * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
  * chosen from the number of views by default, results do not depend on it),
- * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds a fixed capacity makes mv_step / mv_reset fail with
- * MV_ERR_CAPACITY by default, which keeps every env on the reference's level sequence; with 1 the env takes the next level of its
- * stream instead and mv_levels_skipped counts it),
+ * "static_cap" (before the first reset: initial size of the per-level static-box arrays, default 768; they grow whenever a
+ * generated level has more boxes -- the reference has no bound, component_voxel_grid.hpp:108-187),
+ * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds one of the remaining fixed capacities -- movable objects, reward
+ * objects, terrain slabs, the dense grid -- makes mv_step / mv_reset fail with MV_ERR_CAPACITY, and keeps failing: the env would
+ * otherwise leave the reference's level sequence; with 1 the env takes the next level of its stream instead and mv_levels_skipped
+ * counts it),
  * "overlap" (0/1, default 1: the raster kernel is a programmatic dependent launch of the step kernel and synchronises per env;
  * 0 serialises the kernels so that mv_last_kernel_ms can time them separately) */
 int mv_set_option(mv_handle h, const char *key, int value);

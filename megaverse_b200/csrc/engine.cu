@@ -142,6 +142,9 @@ struct mv_engine {
     int64_t launches = 0;
 
     DevBuf<MvLevel> d_levels;
+    DevBuf<MvBox> d_statics;       // [E][2][staticCap]
+    DevBuf<float> d_staticRot;     // [E][2][staticCap][2]
+    int staticCap = MV_INITIAL_STATIC_CAP;  // grows when a generated level has more static boxes (growStatics)
     DevBuf<uint32_t> d_solid;
     DevBuf<uint8_t> d_objGrid;
     DevBuf<MvEnvState> d_envs;
@@ -176,9 +179,14 @@ struct mv_engine {
     } hires;
     DevBuf<MvDeco> d_deco;
     PinBuf<MvDeco> h_deco;
-    int decoCap = 1, instCap = MV_BASE_INSTANCES + 1;
+    int decoCap = 1, instCap = MV_DYN_INSTANCES + MV_INITIAL_STATIC_CAP + 1;
 
     PinBuf<MvLevel> h_levels;      // [E][2] staging mirror
+    PinBuf<MvBox> h_statics;       // [E][2][staticCap]
+    PinBuf<float> h_staticRot;
+    // levels with more static boxes than the arrays hold: parked here by the workers until flushUploads has grown the arrays
+    std::vector<std::pair<int, mv::LevelOut>> oversize;
+    int wantStaticCap = 0;
     PinBuf<uint32_t> h_solid;      // [E][2][gridWords]
     PinBuf<int32_t> h_actions;
     PinBuf<float> h_rtable;
@@ -226,7 +234,24 @@ struct mv_engine {
                 int curO = maxObjSeen.load();
                 while (out.level.n_obj > curO && !maxObjSeen.compare_exchange_weak(curO, out.level.n_obj)) {}
             }
-            std::memcpy(&h_levels.p[size_t(e) * 2 + s], &out.level, sizeof(MvLevel));
+            if (int(out.statics.size()) > staticCap) {  // the arrays are grown on the caller's thread (flushUploads), then the level goes in
+                std::lock_guard<std::mutex> lk(genMutex);
+                wantStaticCap = std::max(wantStaticCap, int(out.statics.size()));
+                oversize.emplace_back(e * 2 + s, std::move(out));
+                return;
+            }
+            stageLevel(e * 2 + s, out);
+        });
+    }
+    // worker thread (or flushUploads for parked levels): copy a generated level into the pinned staging mirrors and queue its upload
+    void stageLevel(int id, const mv::LevelOut &out) {
+        {
+            std::memcpy(&h_levels.p[size_t(id)], &out.level, sizeof(MvLevel));
+            if (!out.statics.empty()) {
+                std::memcpy(h_statics.p + size_t(id) * size_t(staticCap), out.statics.data(), sizeof(MvBox) * out.statics.size());
+                std::memcpy(h_staticRot.p + size_t(id) * size_t(staticCap) * 2, out.staticRot.data(), sizeof(float) * out.staticRot.size());
+            }
+            const int e = id >> 1, s = id & 1;
             if (!out.deco.empty()) std::memcpy(&h_deco.p[(size_t(e) * 2 + s) * size_t(decoCap)], out.deco.data(), sizeof(MvDeco) * out.deco.size());
             uint32_t *dst = h_solid.p + (size_t(e) * 2 + s) * 3 * gridWords;  // planes: solid, exit, lava
             const size_t nw = std::min(out.solid.size(), size_t(gridWords));
@@ -236,18 +261,59 @@ struct mv_engine {
             levelWords[size_t(e) * 2 + s] = int(nw);
             std::lock_guard<std::mutex> lk(genMutex);
             pendingUpload.push_back(e * 2 + s);
-        });
+        }
+    }
+    // more static boxes per level: re-pitch every array that is laid out by staticCap (level statics, instance lists), device and host
+    int growStatics(int need) {
+        const int newCap = std::max(staticCap * 2, ((need + 255) / 256) * 256);
+        const int newInstCap = MV_DYN_INSTANCES + newCap + decoCap;
+        if (newInstCap > mvr::kMaxInstancesPerEnv) { setError("a level needs more drawables than the draw-order key can number"); return MV_ERR_CAPACITY; }
+        MV_CUDA(cudaStreamSynchronize(stream));
+        DevBuf<MvBox> nStat; DevBuf<float> nRot; DevBuf<MvInstance> nInst; PinBuf<MvBox> hStat; PinBuf<float> hRot;
+        const size_t rows = size_t(E) * 2;
+        if (nStat.alloc(rows * newCap) != cudaSuccess || nRot.alloc(rows * newCap * 2) != cudaSuccess || nInst.alloc(size_t(E) * newInstCap) != cudaSuccess ||
+            hStat.alloc(rows * newCap) != cudaSuccess || hRot.alloc(rows * newCap * 2) != cudaSuccess) {
+            nStat.free(); nRot.free(); nInst.free(); hStat.free(); hRot.free();
+            setError("growing the static-box arrays: allocation failed");
+            return MV_ERR_CUDA;
+        }
+        MV_CUDA(cudaMemcpy2D(nStat.p, sizeof(MvBox) * newCap, d_statics.p, sizeof(MvBox) * staticCap, sizeof(MvBox) * staticCap, rows, cudaMemcpyDeviceToDevice));
+        MV_CUDA(cudaMemcpy2D(nRot.p, sizeof(float) * 2 * newCap, d_staticRot.p, sizeof(float) * 2 * staticCap, sizeof(float) * 2 * staticCap, rows, cudaMemcpyDeviceToDevice));
+        MV_CUDA(cudaMemcpy2D(nInst.p, sizeof(MvInstance) * newInstCap, d_inst.p, sizeof(MvInstance) * instCap, sizeof(MvInstance) * instCap, size_t(E), cudaMemcpyDeviceToDevice));
+        for (size_t r = 0; r < rows; ++r) {
+            std::memcpy(hStat.p + r * newCap, h_statics.p + r * staticCap, sizeof(MvBox) * staticCap);
+            std::memcpy(hRot.p + r * newCap * 2, h_staticRot.p + r * staticCap * 2, sizeof(float) * 2 * staticCap);
+        }
+        d_statics.free(); d_staticRot.free(); d_inst.free(); h_statics.free(); h_staticRot.free();
+        d_statics = nStat; d_staticRot = nRot; d_inst = nInst; h_statics = hStat; h_staticRot = hRot;
+        staticCap = newCap; instCap = newInstCap;
+        return MV_OK;
     }
     int flushUploads() {
         pool->waitAll();
         std::vector<int> todo;
         {
             std::lock_guard<std::mutex> lk(genMutex);
-            if (!genErrors.empty()) { setError("level generation failed: " + genErrors.front()); genErrors.clear(); return MV_ERR_CAPACITY; }
+            // sticky: the env whose level could not be generated would otherwise flip to a stale level later; only mv_close recovers
+            if (!genErrors.empty()) { setError("level generation failed: " + genErrors.front()); return MV_ERR_CAPACITY; }
+        }
+        if (!oversize.empty()) {  // workers are idle (waitAll above): grow, then stage what they parked
+            const int rc = growStatics(wantStaticCap);
+            if (rc) return rc;
+            for (auto &po : oversize) stageLevel(po.first, po.second);
+            oversize.clear();
+            wantStaticCap = 0;
+        }
+        {
+            std::lock_guard<std::mutex> lk(genMutex);
             todo.swap(pendingUpload);
         }
         for (int id : todo) {
             MV_CUDA(cudaMemcpyAsync(&d_levels.p[id], &h_levels.p[id], sizeof(MvLevel), cudaMemcpyHostToDevice, stream));
+            if (const int nst = h_levels.p[id].n_static) {
+                MV_CUDA(cudaMemcpyAsync(d_statics.p + size_t(id) * size_t(staticCap), h_statics.p + size_t(id) * size_t(staticCap), sizeof(MvBox) * size_t(nst), cudaMemcpyHostToDevice, stream));
+                MV_CUDA(cudaMemcpyAsync(d_staticRot.p + size_t(id) * size_t(staticCap) * 2, h_staticRot.p + size_t(id) * size_t(staticCap) * 2, sizeof(float) * 2 * size_t(nst), cudaMemcpyHostToDevice, stream));
+            }
             if (h_levels.p[id].n_deco > 0)
                 MV_CUDA(cudaMemcpyAsync(&d_deco.p[size_t(id) * size_t(decoCap)], &h_deco.p[size_t(id) * size_t(decoCap)], sizeof(MvDeco) * size_t(h_levels.p[id].n_deco), cudaMemcpyHostToDevice, stream));
             const size_t nw = size_t(levelWords[size_t(id)]);  // only the words this level's grid uses
@@ -270,7 +336,7 @@ struct mv_engine {
         mvk::StepParams sp;
         sp.hostRewards = mirror ? mirror->rewards.p : nullptr; sp.hostTrueObjectives = mirror ? mirror->trueObj.p : nullptr;
         sp.hostDones = mirror ? mirror->dones.p : nullptr;
-        sp.levels = d_levels.p; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
+        sp.levels = d_levels.p; sp.statics = d_statics.p; sp.staticRot = d_staticRot.p; sp.staticCap = staticCap; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
         sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
         sp.prof = d_prof.p;
@@ -524,7 +590,7 @@ struct mv_engine {
 
     void freeAll() {
         if (pool) { pool->waitAll(); pool.reset(); }
-        d_levels.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
+        d_levels.free(); d_statics.free(); d_staticRot.free(); h_statics.free(); h_staticRot.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
         hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
@@ -630,7 +696,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     e->pool.reset(new WorkerPool(e->threads));
     e->gridCells = mv::gridCapacity(sc);
     e->decoCap = mv::decoCapacity(sc);
-    e->instCap = MV_BASE_INSTANCES + e->decoCap;
+    e->instCap = MV_DYN_INSTANCES + e->staticCap + e->decoCap;
     e->gridWords = e->gridCells / 32;
     fillConsts(e->consts, w, h);
 
@@ -638,7 +704,8 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     const size_t E = size_t(e->E), N = size_t(e->N), px = size_t(w) * h;
     bool ok = ck(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "stream") && ck(cudaStreamCreateWithFlags(&e->copyStream, cudaStreamNonBlocking), "copy stream");
     for (auto &evx : e->ev) ok = ok && ck(cudaEventCreate(&evx), "event");
-    ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
+    ok = ok && ck(e->d_levels.alloc(E * 2), "levels") && ck(e->d_statics.alloc(E * 2 * size_t(e->staticCap)), "statics") && ck(e->d_staticRot.alloc(E * 2 * size_t(e->staticCap) * 2), "staticRot") &&
+         ck(e->h_statics.alloc(E * 2 * size_t(e->staticCap)), "h_statics") && ck(e->h_staticRot.alloc(E * 2 * size_t(e->staticCap) * 2), "h_staticRot") && ck(e->d_solid.alloc(E * 2 * 3 * e->gridWords), "solid") && ck(e->d_objGrid.alloc(E * e->gridCells), "objGrid") &&
          ck(e->d_envs.alloc(E), "envs") && ck(e->d_agents.alloc(N), "agents") && ck(e->d_objects.alloc(E * MV_MAX_OBJECTS), "objects") &&
          ck(e->d_inst.alloc(E * size_t(e->instCap)), "instances") && ck(e->d_deco.alloc(E * 2 * size_t(e->decoCap)), "deco") && ck(e->h_deco.alloc(E * 2 * size_t(e->decoCap)), "h_deco") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
@@ -693,6 +760,20 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         const int rc = h->configureRaster();
         if (rc) { h->triCap = old; h->configureRaster(); }
         return rc;
+    }
+    if (k == "static_cap") {  // initial size of the per-level static-box arrays (they grow on demand; tests start small to exercise that)
+        if (h->didReset) { h->setError("option static_cap must be set before the first reset"); return MV_ERR_STATE; }
+        if (value < 1 || value > (1 << 20)) return MV_ERR_ARG;
+        const size_t rows = size_t(h->E) * 2;
+        h->d_statics.free(); h->d_staticRot.free(); h->h_statics.free(); h->h_staticRot.free(); h->d_inst.free();
+        h->staticCap = value;
+        h->instCap = MV_DYN_INSTANCES + h->staticCap + h->decoCap;
+        if (h->d_statics.alloc(rows * value) != cudaSuccess || h->d_staticRot.alloc(rows * value * 2) != cudaSuccess || h->h_statics.alloc(rows * value) != cudaSuccess ||
+            h->h_staticRot.alloc(rows * value * 2) != cudaSuccess || h->d_inst.alloc(size_t(h->E) * size_t(h->instCap)) != cudaSuccess) {
+            h->setError("static_cap: allocation failed");
+            return MV_ERR_CUDA;
+        }
+        return MV_OK;
     }
     if (k == "raster_bands") {  // row bands per view (each band is one work item of the persistent raster grid)
         if (value < 1 || value > h->H / 4 || (h->H / 4) % value) { h->setError("raster_bands must divide the number of 4-pixel tile rows"); return MV_ERR_ARG; }
@@ -1007,15 +1088,15 @@ int mv_close(mv_handle h) {
 
 // ------------------------------------------------------------------------------------------------ introspection (tests)
 // reward-object voxels; for the hexagonal mazes the free-standing colliders instead (bit patterns of centre, half extents, orientation)
-static void dumpLevelExtras(const MvLevel &L, std::vector<int32_t> &o) {
+static void dumpLevelExtras(const MvLevel &L, const MvBox *statics, const float *staticRot, std::vector<int32_t> &o) {
     const bool hex = L.scenario == MV_SCENARIO_HEX_EXPLORE || L.scenario == MV_SCENARIO_HEX_MEMORY;
     o.push_back(hex ? 0 : L.n_reward);
     for (int i = 0; i < L.n_reward && !hex; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
     if (!hex) return;
     o.push_back(L.n_static);
     for (int i = 0; i < L.n_static; ++i) {
-        const MvBox &b = L.statics[i];
-        const float rot[2] = {(b.flags & MV_ROTATED) ? L.static_rot[i][0] : 1.0f, (b.flags & MV_ROTATED) ? L.static_rot[i][1] : 0.0f};
+        const MvBox &b = statics[i];
+        const float rot[2] = {(b.flags & MV_ROTATED) ? staticRot[i * 2] : 1.0f, (b.flags & MV_ROTATED) ? staticRot[i * 2 + 1] : 0.0f};
         int32_t w[8];
         std::memcpy(w, b.c, 12); std::memcpy(w + 3, b.h, 12); std::memcpy(w + 6, rot, 8);
         for (int k = 0; k < 8; ++k) o.push_back(w[k]);
@@ -1024,7 +1105,10 @@ static void dumpLevelExtras(const MvLevel &L, std::vector<int32_t> &o) {
 
 int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     if (!h || env < 0 || env >= h->E || !h->didReset) return MV_ERR_ARG;
-    const MvLevel &L = h->h_levels.p[size_t(env) * 2 + h->hostSlot[size_t(env)]];
+    const size_t lid = size_t(env) * 2 + h->hostSlot[size_t(env)];
+    const MvLevel &L = h->h_levels.p[lid];
+    const MvBox *statics = h->h_statics.p + lid * size_t(h->staticCap);
+    const float *staticRot = h->h_staticRot.p + lid * size_t(h->staticCap) * 2;
     std::vector<int32_t> o;
     o.push_back(L.n_grid_static); o.push_back(L.n_terrain); o.push_back(L.n_obj);
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
@@ -1032,7 +1116,7 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     static const uint32_t pal[22] = {0xffdd3c, 0x3bb372, 0x50c878, 0x2eb5d0, 0xadd8e6, 0x3a7fa6, 0x2c3e50, 0xffb400, 0xb3b3b3, 0x555555, 0x222222,
                                      0xffffff, 0xff0000, 0xffa770, 0xd468ee, 0xffe6e6, 0xffffe6, 0xccffcc, 0xe6ecff, 0xd9d9d9, 0xf2e6ff, 0xffebcc};
     for (int i = 0; i < L.n_grid_static; ++i) {
-        const MvBox &b = L.statics[i];
+        const MvBox &b = statics[i];
         // invert centre/half back to inclusive voxel bounds: min = c - h, max = c + h - 1
         const float vs = L.scenario == MV_SCENARIO_SOKOBAN ? 2.0f : 1.0f;  // voxel size of the scenario's grid
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] - b.h[a]) / vs)));
@@ -1047,7 +1131,7 @@ int mv_debug_get_level(mv_handle h, int env, int32_t *out, int cap) {
     for (int i = 0; i < h->A; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
     if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);  // numPlatforms
-        dumpLevelExtras(L, o);
+        dumpLevelExtras(L, statics, staticRot, o);
     }
     if (int(o.size()) > cap) return -int(o.size());
     std::memcpy(out, o.data(), o.size() * sizeof(int32_t));
@@ -1066,7 +1150,8 @@ int mv_debug_get_state(mv_handle h, int env, float *out, int cap) {
     const MvLevel &L = h->h_levels.p[size_t(env) * 2 + es.slot];
     std::vector<float> o;
     int ncol = h->A + L.n_obj;
-    for (int i = 0; i < L.n_static; ++i) ncol += (L.statics[i].flags & MV_SOLID) ? 1 : 0;
+    const MvBox *statics = h->h_statics.p + (size_t(env) * 2 + es.slot) * size_t(h->staticCap);
+    for (int i = 0; i < L.n_static; ++i) ncol += (statics[i].flags & MV_SOLID) ? 1 : 0;
     const float len = L.episode_len;
     o.push_back(es.episode_sec); o.push_back(len); o.push_back(float(es.num_frames)); o.push_back(float(es.highest_tower));
     o.push_back(es.bz_reward); o.push_back(float(L.n_obj)); o.push_back(float(ncol)); o.push_back(0.f);
@@ -1109,6 +1194,7 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
     if (cudaMemcpy(&es, &h->d_envs.p[env], sizeof es, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     const MvLevel &L = h->h_levels.p[size_t(env) * 2 + es.slot];
     const uint32_t *sol = h->h_solid.p + (size_t(env) * 2 + es.slot) * 3 * h->gridWords;
+    const MvBox *statics = h->h_statics.p + (size_t(env) * 2 + es.slot) * size_t(h->staticCap);
     std::vector<uint8_t> og(size_t(h->gridCells));
     if (cudaMemcpy(og.data(), h->d_objGrid.p + size_t(env) * h->gridCells, og.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     // opacity is a property of the box a solid voxel belongs to
@@ -1123,7 +1209,7 @@ int mv_debug_get_voxels(mv_handle h, int env, int32_t *out, int cap) {
                     const float vs = L.scenario == MV_SCENARIO_SOKOBAN ? 2.0f : 1.0f;
                     const float cx = (x + L.grid_org[0] + 0.5f) * vs, cy = (y + L.grid_org[1] + 0.5f) * vs, cz = (z + L.grid_org[2] + 0.5f) * vs;
                     for (int i = 0; i < L.n_grid_static; ++i) {
-                        const MvBox &b = L.statics[i];
+                        const MvBox &b = statics[i];
                         if (fabsf(cx - b.c[0]) < b.h[0] && fabsf(cy - b.c[1]) < b.h[1] && fabsf(cz - b.c[2]) < b.h[2]) { flags |= (b.flags & MV_OPAQUE); break; }
                     }
                 }
@@ -1237,7 +1323,7 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_min[a]);
     for (int a = 0; a < 3; ++a) o.push_back(L.bz_max[a]);
     for (int i = 0; i < L.n_grid_static; ++i) {
-        const MvBox &b = L.statics[i];
+        const MvBox &b = lo.statics[size_t(i)];
         const float vs = L.scenario == MV_SCENARIO_SOKOBAN ? 2.0f : 1.0f;  // voxel size of the scenario's grid
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] - b.h[a]) / vs)));
         for (int a = 0; a < 3; ++a) o.push_back(int(lroundf((b.c[a] + b.h[a]) / vs)) - 1);
@@ -1251,7 +1337,7 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
     for (int i = 0; i < num_agents; ++i) for (int a = 0; a < 3; ++a) o.push_back(int(L.init_pos[i][a]));
     if (L.scenario != MV_SCENARIO_TOWER) {
         o.push_back(L.n_movable);  // numPlatforms
-        dumpLevelExtras(L, o);
+        dumpLevelExtras(L, lo.statics.data(), lo.staticRot.data(), o);
     }
     // spawn yaw basis bits, so the float side of spawnAgents is pinned too
     for (int i = 0; i < num_agents; ++i) for (int k = 0; k < 9; ++k) { int32_t u; std::memcpy(&u, &L.spawn_basis[i][k], 4); o.push_back(u); }

@@ -310,6 +310,12 @@ LevelGenerator::LevelGenerator(const std::string &scenarioName, int numAgents, c
     }
 }
 
+// the i-th static box of the level under construction (the arrays grow as needed: the reference has no bound on them)
+static MvBox &staticAt(LevelOut &out, int i) {
+    if (int(out.statics.size()) <= i) { out.statics.resize(size_t(i) + 1); out.staticRot.resize((size_t(i) + 1) * 2, 0.0f); }
+    return out.statics[size_t(i)];
+}
+
 int LevelGenerator::generateFitting(LevelOut &out, int serial, int gridCells, int attempts) {
     for (int skipped = 0;; ++skipped) {
         try {
@@ -325,6 +331,8 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
     std::memset(&out.level, 0, sizeof(MvLevel));
     out.drawSeq.clear();
     out.deco.clear();
+    out.statics.clear();
+    out.staticRot.clear();
     // Env::reset: reseed the env stream from itself
     const auto sd = randRange(0, 1 << 30, rng_);
     rng_.seed((unsigned long)sd);
@@ -363,7 +371,7 @@ void LevelGenerator::assignSlots(LevelOut &out) {
     std::vector<DrawRef> seq = out.drawSeq;
     if (seq.empty()) {
         for (int i = 0; i < L.n_static; ++i)
-            if (L.statics[i].flags & MV_OPAQUE) seq.push_back({DrawRef::STATIC, i});
+            if (staticAt(out, i).flags & MV_OPAQUE) seq.push_back({DrawRef::STATIC, i});
         for (int i = 0; i < L.n_terrain; ++i) seq.push_back({DrawRef::TERRAIN, i});
         for (int i = 0; i < L.n_obj; ++i) seq.push_back({DrawRef::OBJECT, i});
         seq.push_back({DrawRef::EYES, 0}); seq.push_back({DrawRef::BARS, 0}); seq.push_back({DrawRef::BODIES, 0}); seq.push_back({DrawRef::REWARDS, 0});
@@ -375,7 +383,7 @@ void LevelGenerator::assignSlots(LevelOut &out) {
         const int first = slot;
         for (const DrawRef &d : seq) {
             switch (d.kind) {
-                case DrawRef::STATIC: if (mesh == 0) { L.statics[d.index].flags = (L.statics[d.index].flags & 255) | (slot++ << 8); ++L.n_opaque; } break;
+                case DrawRef::STATIC: if (mesh == 0) { staticAt(out, d.index).flags = (staticAt(out, d.index).flags & 255) | (slot++ << 8); ++L.n_opaque; } break;
                 case DrawRef::TERRAIN:  // slabs are consecutive in every scenario
                     if (mesh == 0) { if (terrainSeen++ == 0) L.slot_terrain = slot; ++slot; }
                     break;
@@ -397,7 +405,7 @@ void LevelGenerator::assignSlots(LevelOut &out) {
         }
         L.mesh_counts[mesh] = slot - first;
     }
-    if (slot > MV_MAX_INSTANCES) throw std::runtime_error("too many drawables");
+    if (slot > MV_HARD_MAX_INSTANCES) throw std::runtime_error("too many drawables");
 }
 
 void LevelGenerator::generateTower(LevelOut &out) {
@@ -467,8 +475,7 @@ void LevelGenerator::generateTower(LevelOut &out) {
     for (const auto &g : mergeVoxels(grid)) {
         if (g.type == 0) continue;
         for (const auto &b : g.boxes) {
-            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
-            MvBox &sb = L.statics[ns++];
+            MvBox &sb = staticAt(out, ns++);
             for (int a = 0; a < 3; ++a) {
                 sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
                 sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;
@@ -573,8 +580,7 @@ void LevelGenerator::generateRearrange(LevelOut &out) {
     for (const auto &g : mergeVoxels(grid)) {
         if (g.type == 0) continue;
         for (const auto &b : g.boxes) {
-            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
-            MvBox &sb = L.statics[ns];
+            MvBox &sb = staticAt(out, ns);
             for (int a = 0; a < 3; ++a) {
                 sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
                 sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;
@@ -607,8 +613,7 @@ void LevelGenerator::generateRearrange(LevelOut &out) {
         const float t[3] = {float(pos.x) + 0.5f, float(pos.y) + 0.5f, float(pos.z) + 0.5f};
         float sc[3];
         shapeScale(it.mesh, sc);
-        if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many arrangement items");
-        MvBox &sb = L.statics[ns++];
+        MvBox &sb = staticAt(out, ns++);
         const float cs[3] = {1.0f, colScaleY(it.mesh), 1.0f};
         for (int a = 0; a < 3; ++a) { sb.c[a] = t[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * cs[a]; }
         sb.flags = MV_SOLID; sb.color = 0;
@@ -646,8 +651,7 @@ void LevelGenerator::generateRearrange(LevelOut &out) {
     }
     // floor slab between the pedestals and the two pedestals (addStaticCollidingBox, layout_utils.cpp:70-84)
     auto addBox = [&](float sx, float sy, float sz, float tx, float ty, float tz, uint32_t color) {
-        if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
-        MvBox &sb = L.statics[ns];
+        MvBox &sb = staticAt(out, ns);
         const float sc[3] = {sx, sy, sz}, t[3] = {tx, ty, tz};
         for (int a = 0; a < 3; ++a) { sb.c[a] = t[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.0f; }
         sb.flags = MV_SOLID | MV_OPAQUE; sb.color = paletteIndex(color);
@@ -754,8 +758,7 @@ void LevelGenerator::generateSokoban(LevelOut &out) {
     for (const auto &g : mergeVoxels(grid)) {
         if (g.type == 0) continue;
         for (const auto &b : g.boxes) {
-            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
-            MvBox &sb = L.statics[ns];
+            MvBox &sb = staticAt(out, ns);
             for (int a = 0; a < 3; ++a) {
                 sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * voxelSize;
                 sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * voxelSize;
@@ -913,7 +916,7 @@ void hexMazeBuild(const HexMazeComponent &hm, Rng &rng, LevelOut &out, int &ns) 
         const float sc[3] = {float(hm.xMax - hm.xMin), 0.0001f, float(hm.yMax - hm.yMin)};
         const float tr[3] = {float(hm.xMax + hm.xMin) / 2, 0.0f, float(hm.yMax + hm.yMin) / 2};
         const uint32_t color = randomLayoutColor(rng);
-        MvBox &sb = L.statics[ns];
+        MvBox &sb = staticAt(out, ns);
         for (int a = 0; a < 3; ++a) { sb.c[a] = tr[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.0f; }
         sb.flags = MV_SOLID | MV_OPAQUE; sb.color = paletteIndex(color);
         out.drawSeq.push_back({DrawRef::STATIC, ns});
@@ -948,15 +951,14 @@ void hexMazeBuild(const HexMazeComponent &hm, Rng &rng, LevelOut &out, int &ns) 
                 }
             }
             pushDeco(out, wall, 0, C_DARK_BLUE);
-            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many maze walls");
             {   // collider: centre = translation, half extents = column lengths, orientation = the normalised first column
-                MvBox &sb = L.statics[ns];
+                MvBox &sb = staticAt(out, ns);
                 sb.c[0] = wall.c[3][0] + 0.0f; sb.c[1] = wall.c[3][1] + 0.0f; sb.c[2] = wall.c[3][2] + 0.0f;
                 for (int a = 0; a < 3; ++a) sb.h[a] = colLen(wall, a) * 1.0f;
                 sb.flags = MV_SOLID | MV_ROTATED; sb.color = 0;
                 const float lenInv = 1.0f / sb.h[0];  // what Bullet is handed: Matrix4::rotation() = column * (1 / length)
-                L.static_rot[ns][0] = wall.c[0][0] * lenInv;
-                L.static_rot[ns][1] = wall.c[0][2] * lenInv;
+                out.staticRot[size_t(ns) * 2] = wall.c[0][0] * lenInv;
+                out.staticRot[size_t(ns) * 2 + 1] = wall.c[0][2] * lenInv;
                 ++ns;
             }
             const float es[3] = {length * 1.02f, hm.wallHeight * 0.12f, 0.2f};
@@ -1285,8 +1287,7 @@ void LevelGenerator::generateCollect(LevelOut &out) {
     for (const auto &g : mergeVoxels(grid)) {
         if (g.type == 0) continue;
         for (const auto &b : g.boxes) {
-            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
-            MvBox &sb = L.statics[ns++];
+            MvBox &sb = staticAt(out, ns++);
             for (int a = 0; a < 3; ++a) {
                 sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
                 sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;
@@ -1696,8 +1697,7 @@ void LevelGenerator::generateObstacles(LevelOut &out) {
     for (const auto &g : mergeVoxels(grid)) {
         if (g.type == 0) continue;
         for (const auto &b : g.boxes) {
-            if (ns >= MV_MAX_STATIC) throw std::runtime_error("too many static boxes");
-            MvBox &sb = L.statics[ns++];
+            MvBox &sb = staticAt(out, ns++);
             for (int a = 0; a < 3; ++a) {
                 sb.h[a] = (float(b.mx[a] - b.mn[a] + 1) / 2) * 1.0f;
                 sb.c[a] = (float(b.mn[a] + b.mx[a]) / 2 + 0.5f) * 1.0f;

@@ -21,6 +21,8 @@ struct DrawRef { enum Kind { STATIC, TERRAIN, OBJECT, DECO, EYES, BARS, BODIES, 
 
 struct LevelOut {
     MvLevel level;
+    std::vector<MvBox> statics;    // level.n_static layout boxes: collider order == draw order (std::map<BBoxInfo,Boxes> order); no bound
+    std::vector<float> staticRot;  // two floats per static box (MV_ROTATED ones: local x axis in world space)
     std::vector<MvDeco> deco;      // level.n_deco static drawables with arbitrary model matrices
     std::vector<DrawRef> drawSeq;  // empty: the default order (opaque statics, terrain, objects, eyes, bars, bodies, rewards)
     std::vector<uint32_t> solid;  // grid_dim product bits, x-major: idx = (x*dimY + y)*dimZ + z
@@ -32,10 +34,10 @@ public:
     LevelGenerator(const std::string &scenarioName, int numAgents, const FloatParams &params);
     void seed(unsigned long s) { rng_.seed(s); }
     // Generates the next episode's level.  gridCells = capacity of the dense grid (cells); throws std::runtime_error
-    // if the level does not fit the engine's fixed capacities.
+    // if the level does not fit one of the engine's fixed capacities (the number of static boxes is not one of them).
     void generate(LevelOut &out, int serial, int gridCells);
-    // Same, but a level that does not fit the engine's capacities (a few Collect landscapes in ten thousand decompose into more
-    // boxes than MV_MAX_STATIC) is replaced by the level the env's stream yields next instead of failing: up to `attempts` draws.
+    // Same, but a level that does not fit a fixed capacity is replaced by the level the env's stream yields next instead of failing: up
+    // to `attempts` draws.
     // Returns how many levels were skipped.  The env's level sequence then differs from the reference's from that episode on, which
     // is why the engine only does this when asked to (option "skip_unfit_levels").
     int generateFitting(LevelOut &out, int serial, int gridCells, int attempts = 8);

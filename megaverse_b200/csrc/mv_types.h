@@ -2,6 +2,8 @@
 //
 // HBM layout (one GPU, E envs, A agents per env, N = E*A views):
 //   levels   MvLevel[E][2]          double-buffered immutable level description (host-generated, H2D on reset only)
+//   statics  MvBox[E][2][staticCap] the levels' static layout boxes (collider order == draw order); staticCap grows on demand
+//   staticRot float[E][2][staticCap][2]  MV_ROTATED boxes: local x axis in world space (ax, az)
 //   solid    uint32[E][2][3][GW]    bit-packed voxel planes over the level's bounding grid: solid, exit terrain, lava terrain
 //   objGrid  uint8[E][GC]           dynamic voxel -> movable-object id map (0xFF = none)
 //   envs     MvEnvState[E]          per-env scalars + the building-zone set
@@ -18,7 +20,7 @@
 #include <stdint.h>
 
 #define MV_MAX_AGENTS 8
-#define MV_MAX_STATIC 768
+#define MV_INITIAL_STATIC_CAP 768   // static boxes per level the engine starts with; it grows when a generated level needs more
 #define MV_MAX_TERRAIN 16
 #define MV_MAX_OBJECTS 128
 #define MV_MAX_REWARD 128
@@ -136,10 +138,10 @@ struct MvLevel {
     int32_t work_center[3];        // Rearrange: rightCenter
     float goal[3];                 // HexExplore: rewardObjectCoords
     int32_t n_grid_static;         // statics[0 .. n_grid_static) are the merged boxes of the voxel grid (the rest are free-standing boxes)
-    int32_t pad0[1];               // statics[] must start 16-byte aligned
-    MvBox statics[MV_MAX_STATIC];          // collider order == draw order (std::map<BBoxInfo,Boxes> order)
+    int32_t pad0[1];
+    // the static boxes themselves live beside the level (StepParams::statics / staticRot): their number has no bound in the reference
+    // (component_voxel_grid.hpp:108-187), so the engine sizes that array at run time
     MvTerrain terrain[MV_MAX_TERRAIN];
-    float static_rot[MV_MAX_STATIC][2];    // MV_ROTATED boxes: local x axis in world space (ax, 0, az)
     MvObjInit obj_init[MV_MAX_OBJECTS];
     float spawn_pos[MV_MAX_AGENTS][4];     // ghost origin at spawn (agent.cpp:45)
     float spawn_basis[MV_MAX_AGENTS][12];  // ghost basis rows (btMatrix3x3(btQuaternion(Y, yaw)))
@@ -213,8 +215,10 @@ struct MvInstance {
     int32_t color;    // palette index
     int32_t pad[2];
 };
-#define MV_BASE_INSTANCES (MV_MAX_STATIC + MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 3 * MV_MAX_REWARD)
-#define MV_MAX_INSTANCES (MV_BASE_INSTANCES + MV_MAX_DECO)  // the engine allocates MV_BASE_INSTANCES + the scenario's decoration capacity per env
+// instance slots besides the static boxes and decorations: the engine allocates staticCap + MV_DYN_INSTANCES + the scenario's decoration
+// capacity per env; the rasteriser's draw-order key bounds the total at MV_HARD_MAX_INSTANCES
+#define MV_DYN_INSTANCES (MV_MAX_TERRAIN + MV_MAX_OBJECTS + 3 * MV_MAX_AGENTS + 3 * MV_MAX_REWARD)
+#define MV_HARD_MAX_INSTANCES 32767
 
 struct MvConsts {        // host-computed constants (so host libm decides their bits once, identically for oracle and device)
     float look_left[9];  // btMatrix3x3(btQuaternion(Y, +3.5*dt)) rows
@@ -227,7 +231,7 @@ struct MvConsts {        // host-computed constants (so host libm decides their 
 
 #ifdef __cplusplus
 static_assert(sizeof(MvBox) == 32 && sizeof(MvObject) == 64, "TMA bulk copies need 16-byte multiples");
-static_assert(offsetof(MvLevel, statics) % 16 == 0 && sizeof(MvLevel) % 16 == 0, "MvLevel alignment");
+static_assert(sizeof(MvLevel) % 16 == 0, "MvLevel alignment");
 static_assert(sizeof(MvInstance) == 80, "MvInstance layout");
 static_assert(sizeof(MvEnvState) % 4 == 0 && sizeof(MvAgent) % 4 == 0, "word copies");
 #endif

@@ -40,6 +40,9 @@ constexpr unsigned FULL = 0xffffffffu;
 
 struct StepParams {
     const MvLevel *levels;       // [E][2]
+    const MvBox *statics;        // [E][2][staticCap] static layout boxes of the two level slots (collider order == draw order)
+    const float *staticRot;      // [E][2][staticCap][2] MV_ROTATED boxes: local x axis in world space (ax, az)
+    int staticCap;
     const uint32_t *solid;       // [E][2][3][gridWords] planes: solid, exit terrain, lava terrain
     uint8_t *objGrid;            // [E][gridCells]
     MvEnvState *envs;            // [E]
@@ -758,11 +761,11 @@ __device__ __forceinline__ M4 tsMatrix(V3 t, V3 sc) {
     return m;
 }
 
-__device__ void writeInstances(const WarpShared &S, const MvLevel &L, const MvDeco *deco, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
+__device__ void writeInstances(const WarpShared &S, const MvLevel &L, const MvBox *statics, const MvDeco *deco, MvInstance *inst, int32_t *counts, float *views, int A, bool writeStatic, int lane) {
     // static part (every slot is precomputed by the host in draw order): opaque layout boxes, terrain slabs, decorations
     if (writeStatic) {
         for (int i = lane; i < L.n_static; i += 32) {
-            const MvBox &b = L.statics[i];
+            const MvBox &b = statics[i];
             if (!(b.flags & MV_OPAQUE)) continue;
             putInstance(inst[b.flags >> 8], tsMatrix(v3(b.c[0], b.c[1], b.c[2]), v3(b.h[0], b.h[1], b.h[2])), 0, b.color);
         }
@@ -890,6 +893,8 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     __syncwarp();
     int slot = S.env.slot;
     const MvLevel *L = &P.levels[size_t(env) * 2 + slot];
+    const MvBox *statics = P.statics + (size_t(env) * 2 + slot) * size_t(P.staticCap);
+    const float *staticRot = P.staticRot + (size_t(env) * 2 + slot) * size_t(P.staticCap) * 2;
     int ns = L->n_static, no = L->n_obj;
     if (!P.forceReset) mbarWait(&S.mbar, 0);
 
@@ -986,10 +991,10 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     // the movable objects, the remaining static boxes, the agents
                     if (ci < nsPre || (ci >= nsPre + no && ci < ns + no)) {
                         const int si = ci < nsPre ? ci : ci - no;
-                        const MvBox &sb = L->statics[si];  // global memory (L2 resident): scanned once per agent per step
+                        const MvBox &sb = statics[si];  // global memory (L2 resident): scanned once per agent per step
                         if (sb.flags & MV_SOLID) {
                             keep = true; c = v3(sb.c[0], sb.c[1], sb.c[2]); h = v3(sb.h[0], sb.h[1], sb.h[2]);
-                            if (sb.flags & MV_ROTATED) { kind = 2; rax = L->static_rot[si][0]; raz = L->static_rot[si][1]; }
+                            if (sb.flags & MV_ROTATED) { kind = 2; rax = staticRot[size_t(si) * 2]; raz = staticRot[size_t(si) * 2 + 1]; }
                         }
                     } else if (ci < nsPre + no) {
                         const MvObject &ob = S.objects[ci - nsPre];
@@ -1401,6 +1406,8 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         // flip to the pre-staged next level (episode end, or mv_reset forcing a new episode everywhere)
         slot ^= 1;
         L = &P.levels[size_t(env) * 2 + slot];
+        statics = P.statics + (size_t(env) * 2 + slot) * size_t(P.staticCap);
+        staticRot = P.staticRot + (size_t(env) * 2 + slot) * size_t(P.staticCap) * 2;
         if (lane == 0) {
             S.env.slot = slot;
             S.env.episode_idx += 1;
@@ -1428,7 +1435,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     __syncwarp();
     MV_PROBE(6);  // outputs, flip/reset, object write-back
 
-    writeInstances(S, *L, P.deco + (size_t(env) * 2 + slot) * P.decoCap, P.instances + size_t(env) * P.instStride, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
+    writeInstances(S, *L, statics, P.deco + (size_t(env) * 2 + slot) * P.decoCap, P.instances + size_t(env) * P.instStride, P.instCounts + size_t(env) * 8, P.views + size_t(env) * A * 16, A, resetNow, lane);
 
     MV_PROBE(7);  // instance list + views
 

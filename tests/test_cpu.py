@@ -375,24 +375,27 @@ def test_drop_in_surface_covers_the_reference_bindings(built):
         assert re.search(r"self\.%s\b" % re.escape(a), src), "attribute %s is not set by our MegaverseEnv" % a
 
 
-def test_unfit_levels_are_counted_and_can_be_skipped(built):
-    """a few Collect landscapes in a thousand decompose into more boxes than MV_MAX_STATIC: by default generation fails with a message
-    (the engine then fails mv_step / mv_reset loudly), LevelGenerator::generateFitting -- option "skip_unfit_levels" -- takes the
-    stream's next level instead; other scenarios never hit a capacity on these streams"""
+def test_levels_of_any_size_are_generated(built):
+    """the reference's voxel grid and box merge have no capacity (component_voxel_grid.hpp:108-187): neither has the product.  A Collect
+    landscape that decomposes into more static boxes than the engine's initial array (found by fuzzing; it used to be refused) is generated
+    like any other and equals the oracle's; no level of any scenario is ever skipped"""
     import ctypes as C
 
+    import orc
     from megaverse_b200 import capi
 
     L = capi.lib()
     L.mv_debug_count_unfit_levels.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-    L.mv_last_error.restype = C.c_char_p
-    # a stream whose first level does not fit (found by fuzzing): refused by default ...
-    with pytest.raises(capi.MegaverseError):
-        capi.generate_level("Collect", 2, 889027061, 0)
-    assert b"too many static boxes" in L.mv_last_error(None)
-    # ... skipped once when asked to, after which the stream goes on
-    assert L.mv_debug_count_unfit_levels(b"Collect", 2, 889027061, 3, None, None, 0) == 1
-    unfit = sum(L.mv_debug_count_unfit_levels(b"Collect", 2, seed, 10, None, None, 0) for seed in range(20000, 20100))
-    assert 0 <= unfit <= 8, unfit  # about 0.1-0.2 % of 1000 levels
+    seed = 889027061
+    o = orc.Oracle("Collect", 1, 2, render=False)
+    o.seed_env(0, seed)
+    o.reset()
+    want = o.level(0)
+    got = capi.generate_level("Collect", 2, seed, 0)
+    assert want[0] > 768, "the case is meant to exceed the initial static-box capacity (%d boxes)" % want[0]
+    assert np.array_equal(want, got[:len(want)])
+    o.close()
+    assert L.mv_debug_count_unfit_levels(b"Collect", 2, seed, 3, None, None, 0) == 0
+    assert sum(L.mv_debug_count_unfit_levels(b"Collect", 2, s, 10, None, None, 0) for s in range(20000, 20100)) == 0
     for scen in (b"TowerBuilding", b"ObstaclesHard", b"Rearrange", b"HexExplore", b"HexMemory"):
-        assert sum(L.mv_debug_count_unfit_levels(scen, 2, seed, 5, None, None, 0) for seed in range(20000, 20040)) == 0, scen
+        assert sum(L.mv_debug_count_unfit_levels(scen, 2, s, 5, None, None, 0) for s in range(20000, 20040)) == 0, scen

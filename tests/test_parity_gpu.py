@@ -673,3 +673,55 @@ def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
         assert g.faults() == 0
         g.close()
     o.close()
+
+
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_static_box_arrays_grow_on_demand(built, mode):
+    """the number of static boxes of a level has no bound (component_voxel_grid.hpp:108-187): the engine's per-level arrays and the instance
+    lists that depend on them are re-pitched whenever a generated level needs more.  Started from 16 boxes, every Collect landscape forces
+    growth -- at reset and again at episode turnovers, on the host-facing and on the asynchronous path -- and one env is seeded with a
+    landscape of more than 768 boxes (the former fixed capacity).  State, rewards, dones and frames equal the oracle's throughout."""
+    import torch
+
+    import orc
+    from megaverse_b200 import capi
+
+    E, A, steps = 6, 2, 75
+    params = {"episodeLengthSec": -1.0}
+    o = orc.Oracle("Collect", E, A, 128, 72, params=params)
+    g = capi.Engine("Collect", E, A, 128, 72, num_threads=3, params=params)
+    g.set_option("fast_shading", 0)
+    g.set_option("static_cap", 16)
+    for e in range(E):
+        seed = 889027061 if e == 1 else 300 + e
+        o.seed_env(e, seed); g.seed_env(e, seed)
+    o.reset(); g.reset()
+    assert o.level(1)[0] > 768
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    rng = np.random.default_rng(8)
+    acts = np.stack([helpers.purposeful_actions(rng, E * A, t) for t in range(steps)]).astype(np.int32)
+    dacts = torch.from_numpy(acts).cuda()
+    torch.cuda.synchronize()
+    ndone = 0
+    for t in range(steps):
+        o.step(acts[t])
+        ndone += int(o.dones().sum())
+        if mode == "host":
+            g.step(acts[t])
+            assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), "step %d" % t
+            assert np.array_equal(o.dones(), np.array(g.dones())), "step %d" % t
+            if o.dones().any():
+                assert _assert_same_frame(o, g, "step %d" % t) == 1.0
+        else:
+            g.step_device(dacts.data_ptr() + t * E * A * 4)
+    if mode == "device":
+        g.sync()
+        g.fetch_obs()
+    assert ndone >= 3
+    _assert_same_state(o, g, E, "end")
+    assert _assert_same_frame(o, g, "end") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
