@@ -125,6 +125,10 @@ int mv_stream(mv_handle h, void **stream);
 
 /* sticky per-env fault bits ORed over all envs (MV_FAULT_* in mv_types.h); 0 = healthy */
 int mv_faults(mv_handle h, int32_t *out);
+/* the same bits without a device round trip: the step kernel ORs every fault it raises into a pinned host word (sticky).  Valid for
+ * the steps whose results the host has (after mv_step / mv_step_end / mv_sync).  Non-zero means physics or level state left the
+ * envelope the engine guarantees (MV_FAULT_* in csrc/mv_types.h): the Python MegaverseEnv raises on it. */
+int mv_fault_word(mv_handle h, int32_t *out);
 /* number of kernels the engine launched since creation */
 int mv_kernel_launches(mv_handle h, int64_t *out);
 /* device time of the last step's kernels in milliseconds: [0] step kernel, [1] raster kernel (CUDA events) */

@@ -58,7 +58,7 @@ def lib():
 EXPORTS = [
     "mv_create", "mv_last_error", "mv_seed", "mv_seed_env", "mv_reset", "mv_set_actions", "mv_encode_action", "mv_step", "mv_step_begin", "mv_step_end", "mv_obs_host", "mv_depth_host",
     "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device", "mv_set_obs_buffer",
-    "mv_sync", "mv_fetch_obs", "mv_draw_hires", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_kernel_launches",
+    "mv_sync", "mv_fetch_obs", "mv_draw_hires", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_fault_word", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
     "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_raster_config", "mv_debug_raster_stats", "mv_debug_color_tables", "mv_debug_defaults", "mv_debug_count_unfit_levels", "mv_levels_skipped", "mv_debug_bzset", "mv_debug_generate_level",
 ]
@@ -200,6 +200,13 @@ class Engine:
     def faults(self):
         f = C.c_int32()
         self._ck(lib().mv_faults(self._h, C.byref(f)))
+        return f.value
+
+    def fault_word(self):
+        """the latched fault bits without a device round trip (mv_fault_word)"""
+        f = C.c_int32()
+        lib().mv_fault_word.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        self._ck(lib().mv_fault_word(self._h, C.byref(f)))
         return f.value
 
     def kernel_launches(self):

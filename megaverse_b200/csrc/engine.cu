@@ -30,6 +30,18 @@
 
 namespace {
 
+// every entry point runs on the engine's device and leaves the calling thread's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+        if (prev == dev) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 thread_local std::string g_createError;
 
 #define MV_CUDA(call)                                                                                             \
@@ -196,9 +208,12 @@ struct mv_engine {
     PinBuf<uint8_t> h_obs;
     PinBuf<float> h_depth;
     PinBuf<int32_t> h_faults;
+    PinBuf<int32_t> h_faultWord;   // OR of all fault bits raised so far, written by the step kernel (system-scope atomic)
 
     // mv_step_device pipeline: results of step k are consumed by the host while steps k+1, k+2 already run
-    struct Pending { bool valid = false; cudaEvent_t ev = nullptr; PinBuf<float> rewards, trueObj; PinBuf<uint8_t> dones; };
+    struct Pending { bool valid = false; uint64_t step = 0; cudaEvent_t ev = nullptr; PinBuf<float> rewards, trueObj; PinBuf<uint8_t> dones; };
+    std::vector<int64_t> lastAsyncDone;  // [E] asynchronous step index of the env's previous episode end
+    bool asyncContractBroken = false;
     Pending ring[3];
     DevBuf<uint32_t> d_prof;  // mv_debug_step_profile only
     DevBuf<uint32_t> d_ready; // per-env step completion stamps (step kernel -> geometry kernel)
@@ -336,6 +351,7 @@ struct mv_engine {
         mvk::StepParams sp;
         sp.hostRewards = mirror ? mirror->rewards.p : nullptr; sp.hostTrueObjectives = mirror ? mirror->trueObj.p : nullptr;
         sp.hostDones = mirror ? mirror->dones.p : nullptr;
+        sp.hostFaults = h_faultWord.p;
         sp.levels = d_levels.p; sp.statics = d_statics.p; sp.staticRot = d_staticRot.p; sp.staticCap = staticCap; sp.solid = d_solid.p; sp.objGrid = d_objGrid.p; sp.envs = d_envs.p; sp.agents = d_agents.p;
         sp.objects = d_objects.p; sp.instances = d_inst.p; sp.instCounts = d_instCounts.p; sp.views = d_views.p;
         sp.actions = dActions; sp.rtable = d_rtable.p; sp.rewards = d_rewards.p; sp.dones = d_dones.p; sp.trueObjectives = d_trueObj.p;
@@ -518,7 +534,16 @@ struct mv_engine {
         std::memcpy(h_dones.p, p.dones.p, E);
         std::memcpy(h_trueObj.p, p.trueObj.p, sizeof(float) * N);
         p.valid = false;
+        // the pre-staged next level of an env is delivered three calls after its episode ended: an env that finishes again sooner
+        // flipped to a stale level on the device (MV_FAULT_LEVEL_NOT_READY is latched there as well) -- refuse to go on
+        if (lastAsyncDone.empty()) lastAsyncDone.assign(size_t(E), -1000);
+        for (int e = 0; e < E; ++e)
+            if (h_dones.p[e]) {
+                if (int64_t(p.step) - lastAsyncDone[size_t(e)] < 3) asyncContractBroken = true;
+                lastAsyncDone[size_t(e)] = int64_t(p.step);
+            }
         afterFlip(h_dones.p);
+        if (asyncContractBroken) { setError("mv_step_device: an episode lasted fewer than 3 steps -- outside the asynchronous call's contract; use mv_step"); return MV_ERR_STATE; }
         return MV_OK;
     }
     int drain() {
@@ -533,6 +558,7 @@ struct mv_engine {
     int stepAsync(const int32_t *dActions) {
         if (!didReset) { setError("mv_step_device before mv_reset"); return MV_ERR_STATE; }
         if (hostStepPending) { const int rcp = stepEnd(); if (rcp) return rcp; }
+        if (asyncContractBroken) { setError("mv_step_device: an episode lasted fewer than 3 steps -- outside the asynchronous call's contract; use mv_step"); return MV_ERR_STATE; }
         Pending &slotP = ring[asyncSteps % 3];
         // levels generated since the previous call go up first (done at step k-3 -> retired at call k-1 -> uploaded ahead
         // of kernel k; that env cannot flip again before step k+1), then step k-2 is retired and its regeneration jobs
@@ -552,6 +578,7 @@ struct mv_engine {
         if (rc) return rc;
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
         slotP.valid = true;
+        slotP.step = asyncSteps;
         ++asyncSteps;
         return MV_OK;
     }
@@ -594,7 +621,7 @@ struct mv_engine {
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
         hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
-        h_faults.free();
+        h_faults.free(); h_faultWord.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &p : ring) { if (p.ev) { cudaEventDestroy(p.ev); p.ev = nullptr; } p.rewards.free(); p.trueObj.free(); p.dones.free(); }
         for (auto &e2 : sliceEv) if (e2) cudaEventDestroy(e2);
@@ -673,7 +700,8 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     if (device < 0 || device >= ndev) { g_createError = "bad CUDA device ordinal"; return MV_ERR_ARG; }
     auto *e = new mv_engine;
     auto fail = [&](int code) { g_createError = e->error; e->freeAll(); delete e; return code; };
-    if (cudaSetDevice(device) != cudaSuccess) { e->setError("cudaSetDevice failed"); return fail(MV_ERR_CUDA); }
+    DeviceGuard dg__(device);
+    if (!dg__.ok) { e->setError("cudaSetDevice failed"); return fail(MV_ERR_CUDA); }
     e->scenario = sc; e->W = w; e->H = h; e->E = num_envs; e->A = num_agents; e->N = num_envs * num_agents; e->device = device;
     e->threads = num_threads < 1 ? 1 : num_threads;
     e->scenarioName = scenario;
@@ -720,10 +748,11 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
     if (ok && e->configureRaster() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&
          ck(e->h_rtable.alloc(N * MV_R_COUNT), "h_rtable") && ck(e->h_rewards.alloc(N), "h_rewards") && ck(e->h_dones.alloc(E), "h_dones") &&
-         ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults");
+         ck(e->h_trueObj.alloc(N), "h_trueObj") && ck(e->h_obs.alloc(N * px * 4), "h_obs") && ck(e->h_faults.alloc(E), "h_faults") && ck(e->h_faultWord.alloc(1), "h_faultWord");
     for (auto &p : e->ring) ok = ok && ck(cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming), "event") && ck(p.rewards.alloc(N), "ring") && ck(p.trueObj.alloc(N), "ring") && ck(p.dones.alloc(E), "ring");
     if (!ok) return fail(MV_ERR_CUDA);
     std::memset(e->h_actions.p, 0, sizeof(int32_t) * N);
+    e->h_faultWord.p[0] = 0;
     std::memset(e->h_rewards.p, 0, sizeof(float) * N);
     std::memset(e->h_dones.p, 0, E);
     std::memset(e->h_trueObj.p, 0, sizeof(float) * N);
@@ -824,7 +853,8 @@ int mv_seed_env(mv_handle h, int env, int seed) {
 
 int mv_reset(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     ensureMirrors(h);
     if (h->hostStepPending) { const int rcp = h->stepEnd(); if (rcp) return rcp; }
     if (h->didReset) { const int rcd = h->drain(); if (rcd) return rcd; }
@@ -870,29 +900,36 @@ int mv_set_actions(mv_handle h, const int32_t *masks) {
 
 int mv_step(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    if (!h->didReset) { h->setError("mv_step before mv_reset"); return MV_ERR_STATE; }
+    if (h->hostStepPending) { h->setError("mv_step_begin is outstanding: call mv_step_end first"); return MV_ERR_STATE; }
     if (cudaMemcpyAsync(h->d_actions.p, h->h_actions.p, sizeof(int32_t) * h->N, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("actions upload failed"); return MV_ERR_CUDA; }
     const int rc = h->stepCommon(h->d_actions.p, h->obsToHost);
+    if (rc) cudaStreamSynchronize(h->stream);  // the upload may still be reading the pinned masks
     std::memset(h->h_actions.p, 0, sizeof(int32_t) * h->N);  // env.cpp:140-142: actions are cleared after every step
     return rc;
 }
 
 int mv_step_begin(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     if (cudaMemcpyAsync(h->d_actions.p, h->h_actions.p, sizeof(int32_t) * h->N, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("actions upload failed"); return MV_ERR_CUDA; }
     return h->stepCommon(h->d_actions.p, h->obsToHost, true);
 }
 
 int mv_step_end(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     return h->stepEnd();
 }
 
 int mv_step_device(mv_handle h, const int32_t *d_masks) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     return h->stepAsync(d_masks ? d_masks : h->d_actions.p);
 }
 
@@ -948,7 +985,8 @@ int mv_levels_skipped(mv_handle h) { return h ? h->levelsSkipped.load() : MV_ERR
 
 int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     const int rc = h->drawHires(w, hgt);
     if (rc) return rc;
     if (out) *out = h->hires.h_obs.p;
@@ -957,7 +995,8 @@ int mv_draw_hires(mv_handle h, int w, int hgt, const uint8_t **out) {
 
 int mv_fetch_obs(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     if (h->hostStepPending) { const int rcp = h->stepEnd(); if (rcp) return rcp; }
     const int rc = h->drain();
     if (rc) return rc;
@@ -971,7 +1010,8 @@ int mv_fetch_obs(mv_handle h) {
 
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) return MV_ERR_CUDA;
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) return MV_ERR_CUDA;
     cudaStreamSynchronize(h->stream);
     if (enable && !h->d_prof.p) {
         if (h->d_prof.alloc(size_t(h->E) * 16) != cudaSuccess) { h->setError("profile buffer allocation failed"); return MV_ERR_CUDA; }
@@ -984,7 +1024,8 @@ int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable) {
 
 int mv_sync(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     const int rc = h->drain();
     if (rc) return rc;
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) { h->setError("stream sync failed"); return MV_ERR_CUDA; }
@@ -999,7 +1040,8 @@ int mv_dones(mv_handle h, const uint8_t **out) { if (!h || !out) return MV_ERR_A
 int mv_true_objectives(mv_handle h, const float **out) { if (!h || !out) return MV_ERR_ARG; *out = h->h_trueObj.p; return MV_OK; }
 int mv_set_obs_buffer(mv_handle h, uint8_t *d_obs, float *d_depth) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->obsOut = d_obs ? d_obs : h->d_obs.p;
     h->depthOut = d_depth ? d_depth : h->d_depth.p;
@@ -1059,7 +1101,8 @@ int mv_faults(mv_handle h, int32_t *out) {
 // totals since enable: {work items, instances read, instances with visible items, items, clipped items, triangles, batches, -}
 int mv_debug_raster_stats(mv_handle h, unsigned long long *out8, int enable) {
     if (!h) return MV_ERR_ARG;
-    if (cudaSetDevice(h->device) != cudaSuccess) return MV_ERR_CUDA;
+    DeviceGuard dg__(h->device);
+    if (!dg__.ok) return MV_ERR_CUDA;
     cudaStreamSynchronize(h->stream);
     if (out8 && h->d_rasterStats.p && cudaMemcpy(out8, h->d_rasterStats.p, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     if (enable && !h->d_rasterStats.p) {
@@ -1074,12 +1117,17 @@ int mv_debug_raster_config(mv_handle h, int32_t *out4) {  // {persistent grid, C
     out4[0] = h->rasterGrid; out4[1] = h->rasterCtasPerSM; out4[2] = int32_t(h->rasterSmem); out4[3] = h->rasterBands;
     return MV_OK;
 }
+int mv_fault_word(mv_handle h, int32_t *out) {  // no device round trip: the step kernel ORs raised bits into pinned host memory
+    if (!h || !out) return MV_ERR_ARG;
+    *out = *const_cast<volatile int32_t *>(h->h_faultWord.p);
+    return MV_OK;
+}
 int mv_kernel_launches(mv_handle h, int64_t *out) { if (!h || !out) return MV_ERR_ARG; *out = h->launches; return MV_OK; }
 int mv_last_kernel_ms(mv_handle h, float *out2) { if (!h || !out2) return MV_ERR_ARG; out2[0] = h->lastMs[0]; out2[1] = h->lastMs[1]; return MV_OK; }
 
 int mv_close(mv_handle h) {
     if (!h) return MV_ERR_ARG;
-    cudaSetDevice(h->device);
+    DeviceGuard dg__(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->freeAll();
     delete h;

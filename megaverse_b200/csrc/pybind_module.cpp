@@ -12,6 +12,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -35,7 +37,11 @@ public:
         std::vector<const char *> keys;
         std::vector<float> vals;
         for (auto &kv : floatParams) { keys.push_back(kv.first.c_str()); vals.push_back(kv.second); }
-        const int rc = mv_create(scenario.c_str(), w, h, numEnvs, numAgentsPerEnv, numSimulationThreads, 0, keys.data(), vals.data(), int(keys.size()), &h__);
+        // the reference's constructor has no device argument (one process per GPU, CUDA_VISIBLE_DEVICES): MEGAVERSE_B200_DEVICE picks the
+        // ordinal for processes that see several GPUs
+        int device = 0;
+        if (const char *dv = std::getenv("MEGAVERSE_B200_DEVICE")) device = std::atoi(dv);
+        const int rc = mv_create(scenario.c_str(), w, h, numEnvs, numAgentsPerEnv, numSimulationThreads, device, keys.data(), vals.data(), int(keys.size()), &h__);
         if (rc != MV_OK) throw std::runtime_error(std::string("MegaverseGym: ") + mv_last_error(nullptr));
         masks_.assign(size_t(numEnvs) * numAgentsPerEnv, 0);
     }
@@ -136,6 +142,7 @@ public:
         alive();
         const float *t;
         check(mv_true_objectives(h__, &t));
+        if (envIdx < 0 || envIdx >= numEnvs_ || agentIdx < 0 || agentIdx >= numAgentsPerEnv_) throw std::out_of_range("true_objective: bad env/agent index");
         return t[size_t(envIdx) * numAgentsPerEnv_ + agentIdx];
     }
     // hi-res rendering (megaverse.cpp:148-177,199-203): the same rasteriser at renderW x renderH; the overview camera / viewer is
@@ -150,6 +157,7 @@ public:
     py::array_t<uint8_t> getHiresObservation(int envIdx, int agentIdx) {
         alive();
         if (!hires_) throw std::runtime_error("get_hires_observation before draw_hires");
+        if (envIdx < 0 || envIdx >= numEnvs_ || agentIdx < 0 || agentIdx >= numAgentsPerEnv_) throw std::out_of_range("get_hires_observation: bad env/agent index");
         const size_t view = size_t(envIdx) * numAgentsPerEnv_ + agentIdx;
         return py::array_t<uint8_t>({renderH_, renderW_, 4}, hires_ + view * size_t(renderW_) * renderH_ * 4, py::none{});  // does not own memory
     }
@@ -173,6 +181,7 @@ public:
     }
     uintptr_t obsDevicePtr() { alive(); uint8_t *p; check(mv_obs_device(h__, &p)); return reinterpret_cast<uintptr_t>(p); }
     int faults() { alive(); int32_t f; check(mv_faults(h__, &f)); return f; }
+    int faultWord() { alive(); int32_t f; check(mv_fault_word(h__, &f)); return f; }
     void setOption(const std::string &key, int value) { alive(); check(mv_set_option(h__, key.c_str(), value)); }
     int levelsSkipped() { alive(); return mv_levels_skipped(h__); }
 
@@ -220,6 +229,7 @@ PYBIND11_MODULE(megaverse, m) {
         .def("get_true_objectives", &MegaverseGym::getTrueObjectives)
         .def("obs_device_ptr", &MegaverseGym::obsDevicePtr)
         .def("faults", &MegaverseGym::faults)
+        .def("fault_word", &MegaverseGym::faultWord)
         .def("set_option", &MegaverseGym::setOption)
         .def("levels_skipped", &MegaverseGym::levelsSkipped);
 }

@@ -62,6 +62,7 @@ struct StepParams {
     float *trueObjectives;       // [E*A]
     float *hostRewards, *hostTrueObjectives;  // optional pinned host mirrors written directly by the kernel (or nullptr)
     uint8_t *hostDones;
+    int32_t *hostFaults;         // pinned host word: OR of every fault bit any env ever raised (read by the host without a device round trip)
     int E, A, gridCells, gridWords;
     int forceReset;              // mv_reset(): re-initialise every env from its live level slot, no physics
     uint32_t *ready;             // [E] completion stamps polled by the geometry kernel (programmatic dependent launch)
@@ -1448,6 +1449,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
         uint32_t *adst = reinterpret_cast<uint32_t *>(&P.agents[size_t(env) * A]);
         for (int i = lane; i < int(sizeof(MvAgent) / 4) * A; i += 32) adst[i] = asrc[i];
     }
+    if (lane == 0 && S.env.faults && P.hostFaults) atomicOr_system(P.hostFaults, S.env.faults);  // sticky, rare
     MV_PROBE(8);  // commit
     // publish: everything this warp wrote (state, instance list, views, zeroed triangle counters) before the stamp
     __syncwarp();

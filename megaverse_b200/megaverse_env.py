@@ -26,8 +26,20 @@ def make_env_multitask(multitask_name, task_idx, num_envs, num_agents_per_env, n
     return MegaverseEnv(scenario, num_envs, num_agents_per_env, num_simulation_threads, use_vulkan, params)
 
 
+FAULT_NAMES = {1: "LEVEL_NOT_READY", 2: "TRI_OVERFLOW", 4: "GRID_RANGE", 8: "NAN", 16: "ENVELOPE", 32: "CAND_OVERFLOW"}  # csrc/mv_types.h
+
+
+class MegaverseFault(RuntimeError):
+    """the engine left the envelope in which its results equal the reference's (a capacity of the collision or level code was exceeded,
+    a NaN position, a level that arrived late): frames, rewards and dones from here on are not trustworthy"""
+
+
 class MegaverseEnv(Env):
-    SKIP_UNFIT_LEVELS = True
+    # The number of static boxes of a level is unbounded, as in the reference; the remaining fixed capacities (movable objects, reward
+    # objects, terrain slabs) were never exceeded on hundreds of thousands of generated levels.  Should one be, the strict default makes
+    # step() / reset() fail instead of leaving the reference's level sequence; True takes the env's next level instead and counts it
+    # (`levels_skipped()`, also reported in the infos).
+    SKIP_UNFIT_LEVELS = False
 
     def __init__(self, scenario_name, num_envs, num_agents_per_env, num_simulation_threads, use_vulkan=False, params=None):
         scenario_name = scenario_name.casefold()
@@ -51,10 +63,6 @@ class MegaverseEnv(Env):
                     raise Exception('Params of type %r not supported', type(v))
 
         self.env = MegaverseGym(self.scenario_name, self.img_w, self.img_h, num_envs, num_agents_per_env, num_simulation_threads, use_vulkan, float_params)
-        # The engine has fixed per-level capacities; roughly one Collect landscape in a thousand decomposes into more boxes than fit
-        # (the reference has no such limit).  The C ABI's default is to fail loudly so that every env stays on the reference's level
-        # sequence; a training run is better served by taking the next level of that env's stream instead -- counted, see
-        # `levels_skipped()`.  Set MegaverseEnv.SKIP_UNFIT_LEVELS = False before constructing for the strict behaviour.
         if self.SKIP_UNFIT_LEVELS:
             self.env.set_option("skip_unfit_levels", 1)
         self.default_shaping_scheme = self.env.get_reward_shaping(0, 0)
@@ -77,13 +85,22 @@ class MegaverseEnv(Env):
         chw = np.transpose(obs[:, :, :, :3], (0, 3, 1, 2))
         return [chw[i] for i in range(self.num_agents)]
 
+    def check_faults(self):
+        """raise if the engine latched a fault bit (one pinned-memory read, no device round trip)"""
+        word = self.env.fault_word()
+        if word:
+            names = [n for b, n in FAULT_NAMES.items() if word & b]
+            raise MegaverseFault("megaverse_b200 engine fault bits 0x%x (%s)" % (word, ", ".join(names)))
+
     def reset(self):
         self.env.reset()
+        self.check_faults()
         return self.observations()
 
     def step(self, actions):
         self.env.set_actions_batch(np.asarray(actions, dtype=np.int32).reshape(self.num_agents, 6))
         self.env.step()
+        self.check_faults()
 
         env_dones = self.env.get_dones()
         dones, infos = [], []
@@ -95,6 +112,11 @@ class MegaverseEnv(Env):
             else:
                 infos.extend([{} for _ in range(self.num_agents_per_env)])
 
+        if self.SKIP_UNFIT_LEVELS:
+            skipped = self.env.levels_skipped()
+            if skipped:
+                for info in infos:
+                    info['levels_skipped'] = skipped
         rewards = self.env.get_last_rewards()
         obs = self.observations()
         return obs, rewards, dones, infos

@@ -725,3 +725,23 @@ def test_static_box_arrays_grow_on_demand(built, mode):
     assert _assert_same_frame(o, g, "end") == 1.0
     assert g.faults() == 0
     o.close(); g.close()
+
+
+def test_async_call_refuses_episodes_shorter_than_its_pipeline(built):
+    """mv_step_device delivers an env's next level three calls after its episode ended; an episode of fewer than three steps is outside that
+    contract and must be refused loudly (MV_ERR_STATE, fault bit latched), never answered with a stale level"""
+    import torch
+    from megaverse_b200 import capi
+
+    E = 8
+    g = capi.Engine("TowerBuilding", E, 1, 128, 72, num_threads=2, params={"episodeLengthSec": -400.0})  # every episode ends on its first step
+    g.seed(1); g.reset()
+    acts = torch.zeros((E,), dtype=torch.int32, device="cuda")
+    with pytest.raises(capi.MegaverseError) as ei:
+        for t in range(8):
+            g.step_device(acts.data_ptr())
+        g.sync()
+    assert ei.value.code == capi.MV_ERR_STATE
+    torch.cuda.synchronize()
+    assert g.fault_word() & 1  # MV_FAULT_LEVEL_NOT_READY
+    g.close()
