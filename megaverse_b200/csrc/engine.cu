@@ -1137,7 +1137,7 @@ int mv_close(mv_handle h) {
 // ------------------------------------------------------------------------------------------------ introspection (tests)
 // reward-object voxels; for the hexagonal mazes the free-standing colliders instead (bit patterns of centre, half extents, orientation)
 static void dumpLevelExtras(const MvLevel &L, const MvBox *statics, const float *staticRot, std::vector<int32_t> &o) {
-    const bool hex = L.scenario == MV_SCENARIO_HEX_EXPLORE || L.scenario == MV_SCENARIO_HEX_MEMORY;
+    const bool hex = L.scenario == MV_SCENARIO_HEX_EXPLORE || L.scenario == MV_SCENARIO_HEX_MEMORY || L.scenario == MV_SCENARIO_EMPTY;
     o.push_back(hex ? 0 : L.n_reward);
     for (int i = 0; i < L.n_reward && !hex; ++i) for (int a = 0; a < 3; ++a) o.push_back(L.reward_voxel[i][a]);
     if (!hex) return;

@@ -171,6 +171,7 @@ int scenarioFromName(const std::string &name) {
     if (n == "sokoban") return MV_SCENARIO_SOKOBAN;
     if (n == "hexexplore") return MV_SCENARIO_HEX_EXPLORE;
     if (n == "hexmemory") return MV_SCENARIO_HEX_MEMORY;
+    if (n == "empty") return MV_SCENARIO_EMPTY;
     if (n == "obstacleseasy" || n == "obstaclesmedium" || n == "obstacleshard" || n == "obstacleswalls" || n == "obstaclessteps" || n == "obstacleslava" || n == "test")
         return MV_SCENARIO_OBSTACLES;
     return -1;
@@ -280,7 +281,7 @@ int gridCapacity(int scenario) {
     // with the y range starting at -30 (objects dropped into gaps sink to y = -30, component_object_stacking.hpp:96-100)
     // Collect: <= 41 x 41 landscape, heights <= 18, 16 cells of margin (objects can be put down beyond the edge), y from -30
     // Rearrange: 19 x (6+18) x 14 room
-    if (scenario == MV_SCENARIO_HEX_EXPLORE) return 128;  // no voxel grid
+    if (scenario == MV_SCENARIO_HEX_EXPLORE || scenario == MV_SCENARIO_EMPTY) return 128;  // no voxel grid
     if (scenario == MV_SCENARIO_HEX_MEMORY) return 64 * 4 * 64;  // one layer of cells over a maze of radius <= 7 * 3.5 * sqrt(3)
     // Sokoban: Boxoban rooms are 10 x 10 cells (voxel size 2), y in [-2, 6)
     const int cells = (scenario == MV_SCENARIO_TOWER || scenario == MV_SCENARIO_REARRANGE || scenario == MV_SCENARIO_SOKOBAN) ? 30 * 25 * 25 : (scenario == MV_SCENARIO_COLLECT ? 74 * 62 * 74 : 512 * 1024);
@@ -348,12 +349,13 @@ void LevelGenerator::generate(LevelOut &out, int serial, int gridCells) {
         case MV_SCENARIO_SOKOBAN: generateSokoban(out); break;
         case MV_SCENARIO_HEX_EXPLORE: generateHexExplore(out); break;
         case MV_SCENARIO_HEX_MEMORY: generateHexMemory(out); break;
+        case MV_SCENARIO_EMPTY: generateEmpty(out); break;
         default: throw std::runtime_error("unsupported scenario");
     }
     MvLevel &L = out.level;
     L.n_deco = int(out.deco.size());
     if (L.n_deco > decoCapacity(scenario_)) throw std::runtime_error("too many decorations");
-    if (scenario_ == MV_SCENARIO_HEX_EXPLORE || scenario_ == MV_SCENARIO_HEX_MEMORY) L.n_grid_static = 0;  // no voxel grid boxes at all
+    if (scenario_ == MV_SCENARIO_HEX_EXPLORE || scenario_ == MV_SCENARIO_HEX_MEMORY || scenario_ == MV_SCENARIO_EMPTY) L.n_grid_static = 0;  // no voxel grid boxes at all
     else if (scenario_ != MV_SCENARIO_REARRANGE) L.n_grid_static = L.n_static;
     if (scenario_ == MV_SCENARIO_SOKOBAN || scenario_ == MV_SCENARIO_HEX_EXPLORE || scenario_ == MV_SCENARIO_HEX_MEMORY) {  // objects sit where the generator put them
     } else
@@ -1030,6 +1032,34 @@ void LevelGenerator::generateHexExplore(LevelOut &out) {
     out.drawSeq.push_back({DrawRef::REWARDS, 0});
     L.n_terrain = 0; L.n_obj = 0; L.n_movable = 0;
     L.episode_len = params_.at("episodeLengthSec");
+    L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
+    L.grid_dim[0] = 1; L.grid_dim[1] = 1; L.grid_dim[2] = 1;
+    out.solid.assign(1, 0u); out.exitBits.assign(1, 0u); out.lavaBits.assign(1, 0u);
+}
+
+// EmptyScenario (scenario_empty.cpp:15-30): every agent at (1,1,1), one static colliding box, no rules, no rewards
+void LevelGenerator::generateEmpty(LevelOut &out) {
+    MvLevel &L = out.level;
+    Rng &rng = rng_;
+    const int A = numAgents_;
+    for (int i = 0; i < A; ++i) {  // DefaultScenario::spawnAgents
+        const float yaw = frand(rng) * 3.14159265358979323846f * 2;
+        mvh::spawnBasis(yaw, L.spawn_basis[i]);
+        const float sx = 1.0f + 0.5f, sy = 1.0f + 0.0f, sz = 1.0f + 0.5f;
+        L.spawn_pos[i][0] = sx; L.spawn_pos[i][1] = sy + 1.75f; L.spawn_pos[i][2] = sz;
+        for (int a = 0; a < 3; ++a) L.init_pos[i][a] = 1.0f;
+    }
+    {   // addStaticCollidingBox(drawables, envState, {10, 1, 10}, {5, 0, 5}, ColorRgb::BLUE) (layout_utils.cpp:70-84)
+        const float sc[3] = {10.0f, 1.0f, 10.0f}, tr[3] = {5.0f, 0.0f, 5.0f};
+        MvBox &sb = staticAt(out, 0);
+        for (int a = 0; a < 3; ++a) { sb.c[a] = tr[a] + 0.0f; sb.h[a] = std::sqrt(sc[a] * sc[a] + 0.0f * 0.0f + 0.0f * 0.0f) * 1.0f; }
+        sb.flags = MV_SOLID | MV_OPAQUE; sb.color = paletteIndex(C_BLUE);
+        out.drawSeq.push_back({DrawRef::STATIC, 0});
+    }
+    out.drawSeq.push_back({DrawRef::EYES, 0}); out.drawSeq.push_back({DrawRef::BARS, 0}); out.drawSeq.push_back({DrawRef::BODIES, 0});
+    L.n_static = 1; L.n_static_pre = 1; L.n_grid_static = 0;
+    L.n_terrain = 0; L.n_obj = 0; L.n_movable = 0; L.n_reward = 0; L.n_positive = 0;
+    L.episode_len = params_.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
     L.grid_org[0] = 0; L.grid_org[1] = 0; L.grid_org[2] = 0;
     L.grid_dim[0] = 1; L.grid_dim[1] = 1; L.grid_dim[2] = 1;
     out.solid.assign(1, 0u); out.exitBits.assign(1, 0u); out.lavaBits.assign(1, 0u);

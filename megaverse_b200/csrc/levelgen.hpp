@@ -50,6 +50,7 @@ private:
     void generateSokoban(LevelOut &out);
     void generateHexExplore(LevelOut &out);
     void generateHexMemory(LevelOut &out);
+    void generateEmpty(LevelOut &out);
     unsigned episodeSeed_ = 0;     // the value the env reseeded itself with at this reset
     void assignSlots(LevelOut &out);
     void fillPlanes(LevelOut &out, const void *voxMap);

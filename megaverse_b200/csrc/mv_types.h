@@ -34,6 +34,7 @@
 #define MV_SCENARIO_SOKOBAN 4
 #define MV_SCENARIO_HEX_EXPLORE 5
 #define MV_SCENARIO_HEX_MEMORY 6
+#define MV_SCENARIO_EMPTY 7   // one static box, no rules: the scenario of the reference README's 75 k FPS figure (scenario_empty.cpp)
 
 #define MV_MAX_DECO 1536    // static drawables that are not axis-aligned layout boxes (other meshes, rotated boxes); stored beside MvLevel
 #define MV_MAX_ARRANGEMENT 8

@@ -1087,7 +1087,7 @@ __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
                     e.episode_sec = e.episode_sec > t ? e.episode_sec : t;
                 }
             };
-            const bool hasStacking = L->scenario != MV_SCENARIO_SOKOBAN && L->scenario != MV_SCENARIO_HEX_EXPLORE && L->scenario != MV_SCENARIO_HEX_MEMORY;
+            const bool hasStacking = L->scenario != MV_SCENARIO_SOKOBAN && L->scenario != MV_SCENARIO_HEX_EXPLORE && L->scenario != MV_SCENARIO_HEX_MEMORY && L->scenario != MV_SCENARIO_EMPTY;
             for (int i = 0; i < A && hasStacking; ++i) {  // ObjectStackingComponent (Sokoban and the hex mazes have none)
                 if (!(P.actions[size_t(env) * A + i] & MV_A_INTERACT)) continue;
                 MvAgent &a = S.agents[i];

@@ -162,7 +162,7 @@ int orc_get_level(void *p, int envIdx, int32_t *out, int cap) {
         o.push_back(int(env.rewardSpawnPositions.size()));
         for (auto &c : env.rewardSpawnPositions)
             for (int x : {c.x, c.y, c.z}) o.push_back(x);
-        if (env.scenario == Env::S_HEX_EXPLORE || env.scenario == Env::S_HEX_MEMORY) {  // free-standing colliders (bit patterns)
+        if (env.scenario == Env::S_HEX_EXPLORE || env.scenario == Env::S_HEX_MEMORY || env.scenario == Env::S_EMPTY) {  // free-standing colliders (bit patterns)
             o.push_back(env.agentColliderBase);
             for (int i = 0; i < env.agentColliderBase; ++i) {
                 const Collider &c = env.colliders[size_t(i)];

@@ -128,7 +128,7 @@ using RewardShaping = std::map<std::string, float>;
 
 class Env {
 public:
-    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3, S_SOKOBAN = 4, S_HEX_EXPLORE = 5, S_HEX_MEMORY = 6 };
+    enum Scenario { S_TOWER = 0, S_OBSTACLES = 1, S_COLLECT = 2, S_REARRANGE = 3, S_SOKOBAN = 4, S_HEX_EXPLORE = 5, S_HEX_MEMORY = 6, S_EMPTY = 7 };
     enum SokobanTerrain { SOKO_EMPTY = 0, SOKO_WALL = 1, SOKO_GOAL = 2 };
     struct SokobanLevel { std::vector<std::string> rows; };
     enum PlatformType { PT_EMPTY, PT_WALL, PT_LAVA, PT_STEP, PT_GAP };
@@ -148,6 +148,7 @@ public:
         else if (n == "rearrange") scenario = S_REARRANGE;
         else if (n == "hexexplore") scenario = S_HEX_EXPLORE;
         else if (n == "hexmemory") scenario = S_HEX_MEMORY;
+        else if (n == "empty") scenario = S_EMPTY;  // scenario_empty.cpp
         else if (n == "sokoban") {  // scenario_sokoban.cpp:39-81, scenario_sokoban.hpp:50-54
             scenario = S_SOKOBAN;
             floatParams["episodeLengthSec"] = 80.0f;
@@ -212,6 +213,7 @@ public:
         if (scenario == S_HEX_MEMORY) return {{"memoryCollectGood", 1.0f}, {"memoryCollectBad", -1.0f}};  // scenario_hex_memory.hpp:43-49
         if (scenario == S_SOKOBAN)  // scenario_sokoban.hpp:41-48
             return {{"sokobanBoxOnTarget", 1.0f}, {"sokobanBoxLeavesTarget", -1.0f}, {"sokobanAllBoxesOnTarget", 10.0f}};
+        if (scenario == S_EMPTY) return {};  // scenario_empty.hpp:28
         if (scenario == S_REARRANGE)  // scenario_rearrange.hpp:91-97
             return {{"rearrangeOneMoreObjectCorrectPosition", 1.0f}, {"rearrangeAllObjectsCorrectPosition", 10.0f}};
         // scenario_tower_building.hpp:44-52
@@ -234,12 +236,18 @@ public:
 
         if (scenario == S_TOWER) towerReset(); else if (scenario == S_OBSTACLES) obstaclesReset(); else if (scenario == S_COLLECT) collectReset();
         else if (scenario == S_REARRANGE) rearrangeReset(); else if (scenario == S_SOKOBAN) sokobanReset(); else if (scenario == S_HEX_EXPLORE) hexExploreReset();
+        else if (scenario == S_EMPTY) {  // EmptyScenario::reset / agentStartingPositions (scenario_empty.cpp:15-22); no components
+            agentSpawnPositions.assign(size_t(numAgents), Vec3{1, 1, 1});
+            carryingObject.assign(size_t(numAgents), -1);  // (only read by the state dump)
+        }
         else hexMemoryReset();
         if (scenario == S_HEX_MEMORY) hexMemorySpawnAgents(); else
         spawnAgents();
         if (scenario == S_TOWER) towerAddEpisodeDrawables(); else if (scenario == S_OBSTACLES) obstaclesAddEpisodeDrawables();
         else if (scenario == S_COLLECT) collectAddEpisodeDrawables(); else if (scenario == S_REARRANGE) rearrangeAddEpisodeDrawables();
-        else if (scenario == S_SOKOBAN) sokobanAddEpisodeDrawables(); else if (scenario == S_HEX_EXPLORE) hexExploreAddEpisodeDrawables(); else hexMemoryAddEpisodeDrawables();
+        else if (scenario == S_SOKOBAN) sokobanAddEpisodeDrawables(); else if (scenario == S_HEX_EXPLORE) hexExploreAddEpisodeDrawables();
+        else if (scenario == S_EMPTY) addStaticCollidingBox(Vec3{10, 1, 10}, Vec3{5, 0, 5}, BLUE);  // scenario_empty.cpp:25-28
+        else hexMemoryAddEpisodeDrawables();
         addAgentsAndUI();
     }
 
@@ -1364,6 +1372,7 @@ public:
 
         if (scenario == S_TOWER) towerStep(); else if (scenario == S_OBSTACLES) obstaclesStep(); else if (scenario == S_COLLECT) collectStep();
         else if (scenario == S_REARRANGE) rearrangeStep(); else if (scenario == S_SOKOBAN) sokobanStep(); else if (scenario == S_HEX_EXPLORE) hexExploreStep();
+        else if (scenario == S_EMPTY) {}  // EmptyScenario::step (scenario_empty.hpp:20)
         else hexMemoryStep();
 
         currEpisodeSec += lastFrameDurationSec;
@@ -1376,14 +1385,14 @@ public:
 
     float episodeLengthSec() const {
         if (scenario == S_HEX_MEMORY) return floatParams.at("episodeLengthSec") + 3.0f * goodObjects.size();  // scenario_hex_memory.hpp:51-55
-        if (scenario == S_REARRANGE || scenario == S_SOKOBAN || scenario == S_HEX_EXPLORE) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
+        if (scenario == S_REARRANGE || scenario == S_SOKOBAN || scenario == S_HEX_EXPLORE || scenario == S_EMPTY) return floatParams.at("episodeLengthSec");  // Scenario::episodeLengthSec (scenario.hpp:174-178)
         if (scenario == S_COLLECT) return floatParams.at("episodeLengthSec") + 2.0f * rewardSpawnPositions.size();  // scenario_collect.hpp:52-56
         if (scenario == S_OBSTACLES)  // scenario_obstacles.cpp:262-266
             return std::max(floatParams.at("episodeLengthSec"), float(numPlatforms) * 35 + float(objectSpawnPositions.size()) * 1);
         return floatParams.at("episodeLengthSec") + 4.0f * float(objectSpawnPositions.size());  // scenario_tower_building.cpp:263-266
     }
     float remainingTimeFraction() const { const float len = episodeLengthSec(); return std::max(0.0f, (len - currEpisodeSec) / len); }  // env.hpp:224-228
-    float trueObjective(int) const { return scenario == S_TOWER ? float(highestTower) : float(solved); }
+    float trueObjective(int) const { return scenario == S_TOWER ? float(highestTower) : (scenario == S_EMPTY ? 0.0f : float(solved)); }
     void doneWithTimer(float remaining = 0.3f) { currEpisodeSec = std::max(currEpisodeSec, episodeLengthSec() - remaining); }
 
     void updateUI() {  // scenario_default.hpp:164-186 ; UIElement::rescale :33-37

@@ -24,6 +24,7 @@
 #include <env/scenario.hpp>
 #include <env/vector_env.hpp>
 #include <scenarios/scenario_collect.hpp>
+#include <scenarios/scenario_empty.hpp>
 #include <scenarios/scenario_hex_explore.hpp>
 #include <scenarios/scenario_hex_memory.hpp>
 #include <scenarios/scenario_obstacles.hpp>
@@ -72,6 +73,7 @@ void registerScenarios() {  // scenarios/init.hpp:28-56 without the experimental
     reg<RearrangeScenario>("Rearrange");
     reg<HexExploreScenario>("HexExplore");
     reg<HexMemoryScenario>("HexMemory");
+    reg<EmptyScenario>("Empty");
 }
 
 uint32_t bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }

@@ -5,6 +5,7 @@
 #include <env/scenario.hpp>
 
 #include <scenarios/scenario_collect.hpp>
+#include <scenarios/scenario_empty.hpp>
 #include <scenarios/scenario_hex_explore.hpp>
 #include <scenarios/scenario_hex_memory.hpp>
 #include <scenarios/scenario_obstacles.hpp>
@@ -20,6 +21,7 @@ inline void scenariosGlobalInit() {
     static bool initialized = false;
     if (initialized) return;
     initialized = true;
+    registerScenario<EmptyScenario>("Empty");
     registerScenario<TestScenario>("Test");
     registerScenario<TowerBuildingScenario>("TowerBuilding");
     registerScenario<ObstaclesEasyScenario>("ObstaclesEasy");

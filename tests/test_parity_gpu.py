@@ -745,3 +745,30 @@ def test_async_call_refuses_episodes_shorter_than_its_pipeline(built):
     torch.cuda.synchronize()
     assert g.fault_word() & 1  # MV_FAULT_LEVEL_NOT_READY
     g.close()
+
+
+@pytest.mark.parametrize("A", [1, 3])
+def test_empty_scenario_parity(built, A):
+    """the reference's debugging scenario (scenario_empty.cpp: one static box, all agents spawned on the same spot, no rules) -- the
+    workload of the one throughput figure the reference publishes (README.md:243-245)"""
+    E, steps = 5, 200
+    o, g = _pair("Empty", E, A, 9, params={"episodeLengthSec": 6.0})
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    rng = np.random.default_rng(4)
+    ndone = 0
+    for t in range(steps):
+        acts = helpers.purposeful_actions(rng, E * A, t)
+        o.step(acts); g.step(acts)
+        assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), "step %d" % t
+        assert np.array_equal(o.dones(), np.array(g.dones())), "step %d" % t
+        assert np.array_equal(o.true_objectives(), np.array(g.true_objectives())), "step %d" % t
+        ndone += int(o.dones().sum())
+        if t % 40 == 0 or o.dones().any():
+            _assert_same_state(o, g, E, "step %d" % t)
+            assert _assert_same_frame(o, g, "step %d" % t) == 1.0
+    assert ndone >= E
+    assert g.faults() == 0
+    o.close(); g.close()

@@ -667,6 +667,8 @@ def _full_run(R, O, scenario, A, seed, max_ticks, episodes=2, params=None, warp_
                                        "obstaclesMaxLava": 6, "obstaclesMinHeight": 1, "obstaclesMaxHeight": 4, "obstaclesNumAllowedMaxDifficulty": 2}),
     ("Collect", 8, 43, 300, 25, {"episodeLengthSec": 30.0}),
     ("TowerBuilding", 8, 44, 300, 25, None),
+    # the debugging scenario of the reference README's performance figure: one box, every agent spawned at the same spot
+    ("Empty", 1, 45, 400, 0, {"episodeLengthSec": 10.0}), ("Empty", 3, 46, 400, 25, {"episodeLengthSec": 10.0}),
 ])
 def test_reference_env_library_on_stand_in_bullet_matches_the_oracle(env_libs, scenario, A, seed, ticks, warp, params):
     R, O = env_libs
@@ -675,7 +677,7 @@ def test_reference_env_library_on_stand_in_bullet_matches_the_oracle(env_libs, s
 
 
 @pytest.mark.parametrize("scenario", ["TowerBuilding", "ObstaclesEasy", "ObstaclesMedium", "ObstaclesHard", "ObstaclesWalls", "ObstaclesSteps", "ObstaclesLava",
-                                      "Collect", "Sokoban", "Rearrange", "HexExplore", "HexMemory"])
+                                      "Collect", "Sokoban", "Rearrange", "HexExplore", "HexMemory", "Empty"])
 def test_default_reward_shaping_and_parameters_match_the_reference_scenarios(env_libs, scenario):
     """Scenario::init() of the real scenario classes (reward shaping incl. teamSpirit, float parameters) against the tables the product
     builds its engine from (host-only accessor, no GPU needed)"""

@@ -52,6 +52,9 @@ def main():
     dt = time.perf_counter() - t0
     frames = steps * E * A
     print("Avg FPS: %.1f (agent observations per second; %d frames in %.2f s), faults %d" % (frames / dt, frames, dt, eng.faults()))
+    published = {("empty", 64, 1): 75000, ("collect", 64, 1): 27000}.get((a.scenario.lower(), E, A))  # README.md:243-247, 10-core i9, its own GPU renderer
+    if published and a.performance_test and not a.hires:
+        print("reference README figure for this command line: approximately %d FPS" % published)
     eng.close()
 
 
