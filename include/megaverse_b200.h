@@ -157,9 +157,11 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
 /* rasteriser launch shape: out4 = {persistent grid size, CTAs per SM, dynamic shared memory per CTA in bytes, row bands per view} */
 int mv_debug_raster_config(mv_handle h, int32_t *out4);
-/* rasteriser work counters since the last enable: out8 = {work items, instances read, instances with visible items, items (box faces /
- * mesh triangles set up), items clipped at the near / far plane, triangles drawn, batches, -}; enable=1 arms / clears, 0 frees */
-int mv_debug_raster_stats(mv_handle h, unsigned long long *out8, int enable);
+/* rasteriser work counters since the last enable: out16 = {work items, instances read, instances with visible items, items (box faces /
+ * mesh triangles set up), items clipped at the near / far plane, triangles drawn, batches, -, then thread-0 cycle sums: head (work
+ * claim, env stamp, view matrix), TMA waits, instance passes, item passes, final tile pass, whole work item, -, -}; enable=1 arms /
+ * clears, 0 frees */
+int mv_debug_raster_stats(mv_handle h, unsigned long long *out16, int enable);
 /* host-only: colour tables of the generators + the rasteriser's palette (tests pin them against the reference's env/const.hpp) */
 int mv_debug_color_tables(uint32_t *out, int cap);
 /* host-only: default reward shaping ("R key=hexbits") and default float parameters ("P key=hexbits") of a scenario, one per line */

@@ -1099,16 +1099,16 @@ int mv_faults(mv_handle h, int32_t *out) {
     return MV_OK;
 }
 // totals since enable: {work items, instances read, instances with visible items, items, clipped items, triangles, batches, -}
-int mv_debug_raster_stats(mv_handle h, unsigned long long *out8, int enable) {
+int mv_debug_raster_stats(mv_handle h, unsigned long long *out16, int enable) {
     if (!h) return MV_ERR_ARG;
     DeviceGuard dg__(h->device);
     if (!dg__.ok) return MV_ERR_CUDA;
     cudaStreamSynchronize(h->stream);
-    if (out8 && h->d_rasterStats.p && cudaMemcpy(out8, h->d_rasterStats.p, 64, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
+    if (out16 && h->d_rasterStats.p && cudaMemcpy(out16, h->d_rasterStats.p, 128, cudaMemcpyDeviceToHost) != cudaSuccess) return MV_ERR_CUDA;
     if (enable && !h->d_rasterStats.p) {
-        if (h->d_rasterStats.alloc(8) != cudaSuccess) { h->setError("raster stats allocation failed"); return MV_ERR_CUDA; }
+        if (h->d_rasterStats.alloc(16) != cudaSuccess) { h->setError("raster stats allocation failed"); return MV_ERR_CUDA; }
     }
-    if (enable) cudaMemset(h->d_rasterStats.p, 0, 64);
+    if (enable) cudaMemset(h->d_rasterStats.p, 0, 128);
     else h->d_rasterStats.free();
     return MV_OK;
 }

@@ -89,7 +89,8 @@ struct ViewParams {
     const uint32_t *ready;       // [E] step-kernel completion stamps (nullptr: plain stream order)
     uint32_t readyStamp;         // value ready[env] holds once this step's state, instances and views of env are written
     uint32_t *consumed;          // optional [E]: += 1 when a work item of env has read the env's instance list and view (step/raster overlap)
-    unsigned long long *stats;   // optional [8]: work items, instances, visible instances, items, clipped items, triangles, batches, - (debug)
+    unsigned long long *stats;   // optional [16]: work items, instances, visible instances, items, clipped items, triangles, batches, -, then
+                                 // thread-0 cycles: head (claim, stamp, view), TMA waits, instance passes, item passes, final tile pass, whole item
     unsigned long long *spill;   // [gridDim.x][spillStride] per-CTA fragment slab for views drawn in several batches
     int spillStride;             // >= W * bandRows
     int viewBase, N;             // this launch draws views [viewBase, viewBase + N)
@@ -692,6 +693,8 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
     unsigned long long *frag = fragAll + warp * 128;
 
     for (;;) {
+        const long long tc0 = P.stats ? clock64() : 0;
+        long long tcWait = 0, tcInst = 0, tcItem = 0;
         if (tid == 0) M.claim = atomicAdd(P.workCounter, 1u) - P.counterBase;
         __syncthreads();
         const uint32_t claim = M.claim;
@@ -741,12 +744,16 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         SetupCtx cx;
         cx.cover = cover; cx.shade = shade; cx.nTris = &M.nTris; cx.nValid = &M.nValid; cx.triCap = P.triCap; cx.W = P.W; cx.H = P.H; cx.rowLo = rowLo; cx.rowHi = rowHi;
         int batch = 0, parity = 0;
+        const long long tc1 = P.stats ? clock64() : 0;
 
         for (int c = 0; c < nChunks; ++c) {
             const int buf = c & 1;
             const int cBase = c * kInstChunk, cCnt = min(kInstChunk, nInst - cBase);
+            const long long tw0 = P.stats ? clock64() : 0;
             mbarWait(&M.bar[buf], phase[buf]);
             phase[buf] ^= 1u;
+            const long long tw1 = P.stats ? clock64() : 0;
+            tcWait += tw1 - tw0;
             if (tid == 0 && c + 1 < nChunks) {  // the other buffer was last read before the barrier that closed chunk c-1's instance pass
                 const int nCnt = min(kInstChunk, nInst - (cBase + kInstChunk));
                 const uint32_t bytes = uint32_t(nCnt) * uint32_t(sizeof(MvInstance));
@@ -821,6 +828,8 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                 __syncthreads();
             }
             const int totalItems = off[kInstChunk];
+            const long long tw2 = P.stats ? clock64() : 0;
+            tcInst += tw2 - tw1;
             if (P.stats && tid == 0) { M.stat[1] += uint32_t(cCnt); M.stat[3] += uint32_t(totalItems); }
             // ---- item pass: one thread per visible box face / mesh triangle.  Items that do not fit the list wait for the next batch;
             // items crossing the near / far plane go to a short list that the warps then clip co-operatively (see slowItem)
@@ -952,11 +961,13 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                 }
             }
             __syncthreads();  // the transform table and the stage buffer are rewritten by the next chunk
+            if (P.stats) tcItem += clock64() - tw2;
         }
         if (P.consumed && tid == 0) {  // this item no longer needs the env's instance list or view matrix
             __threadfence();
             atomicAdd(P.consumed + env, 1u);
         }
+        const long long tc2 = P.stats ? clock64() : 0;
         tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
         if (P.stats && tid < 8) {
@@ -965,6 +976,12 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
             if (tid == 5) v += (unsigned long long)min(M.nTris, M.nValid);
             if (tid == 6) v = (unsigned long long)(batch + 1);
             atomicAdd(P.stats + tid, v);
+            if (tid == 0) {
+                const long long tc3 = clock64();
+                atomicAdd(P.stats + 8, (unsigned long long)(tc1 - tc0)); atomicAdd(P.stats + 9, (unsigned long long)tcWait);
+                atomicAdd(P.stats + 10, (unsigned long long)tcInst); atomicAdd(P.stats + 11, (unsigned long long)tcItem);
+                atomicAdd(P.stats + 12, (unsigned long long)(tc3 - tc2)); atomicAdd(P.stats + 13, (unsigned long long)(tc3 - tc0));
+            }
         }
     }
 }
