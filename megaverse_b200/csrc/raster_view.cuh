@@ -39,15 +39,15 @@ struct __align__(16) TriCover {  // what the coverage / depth loop reads (broadc
     float z[3];
     float invArea;
     uint32_t key;       // draw order + 1 (later wins depth ties: LESS_OR_EQUAL)
-    int32_t flags;      // bits 0..2: edge e is top-left (no bias was applied); bit 3: every edge function fits int32 in the viewport
+    int32_t flags;      // bits 0..2: edge e is top-left (no bias was applied); bit 3: every edge function fits int32 in the viewport;
+                        // bit 4: the three vertex normals are identical (box faces, cone and cylinder caps)
     uint32_t bx, by;    // pixel box, inclusive: x0 | x1 << 16, y0 | y1 << 16
 };
 struct __align__(16) TriShade {  // what deferred shading reads for the winning fragment
     float rw[3];
     float p[9];
-    float n[9];
-    int32_t color;
-    int32_t pad[2];
+    float n[9];        // fast shading, flat triangle (flags bit 4): n[0..2] is the UNIT normal
+    float diffuse[3];  // the material colour (palette entry), looked up once per triangle
 };
 static_assert(sizeof(TriCover) == 80 && sizeof(TriShade) == 96, "triangle record layout");
 
@@ -160,6 +160,8 @@ __device__ __forceinline__ void mbarWait(unsigned long long *bar, uint32_t parit
     } while (!done);
 }
 
+__constant__ float c_palette[22][3];
+
 struct ClipVert { float cx, cy, cz, cw, px, py, pz, nx, ny, nz; };  // clipNearFar indexes it as float[10]
 static_assert(sizeof(ClipVert) == 40, "ClipVert is ten floats");
 
@@ -218,6 +220,7 @@ __device__ __forceinline__ bool triBox(const SetupCtx &cx, const ScreenVert &a, 
     return true;
 }
 // edge / plane set-up of one visible triangle into list slot `slot`
+template <bool FAST>
 __device__ __forceinline__ void writeTri(const SetupCtx &cx, int slot, const ClipVert &va, const ClipVert &vb, const ClipVert &vc, const ScreenVert &a,
                                          const ScreenVert &b, const ScreenVert &c, const TriBox &tb, int color, uint32_t key) {
     TriCover cv;
@@ -242,12 +245,17 @@ __device__ __forceinline__ void writeTri(const SetupCtx &cx, int slot, const Cli
     s.rw[0] = a.rw; s.rw[1] = b.rw; s.rw[2] = c.rw;
     s.p[0] = va.px; s.p[1] = va.py; s.p[2] = va.pz; s.p[3] = vb.px; s.p[4] = vb.py; s.p[5] = vb.pz; s.p[6] = vc.px; s.p[7] = vc.py; s.p[8] = vc.pz;
     s.n[0] = va.nx; s.n[1] = va.ny; s.n[2] = va.nz; s.n[3] = vb.nx; s.n[4] = vb.ny; s.n[5] = vb.nz; s.n[6] = vc.nx; s.n[7] = vc.ny; s.n[8] = vc.nz;
+    const bool flat = va.nx == vb.nx && va.ny == vb.ny && va.nz == vb.nz && va.nx == vc.nx && va.ny == vc.ny && va.nz == vc.nz;
+    if (FAST && flat) {  // the fast fragment stage takes the unit normal as is (the exact one normalises the interpolated normal per pixel)
+        const float inv = rsqrtf(va.nx * va.nx + va.ny * va.ny + va.nz * va.nz);
+        s.n[0] = va.nx * inv; s.n[1] = va.ny * inv; s.n[2] = va.nz * inv;
+    }
     cv.invArea = 1.0f / float(-tb.area2);
     cv.key = key;
-    cv.flags = tl | (worst < (1ll << 30) ? 8 : 0);  // bit 3: every edge function fits int32 anywhere in the viewport
+    cv.flags = tl | (worst < (1ll << 30) ? 8 : 0) | (flat ? 16 : 0);
     cv.bx = tb.bx;
     cv.by = tb.by;
-    s.color = color; s.pad[0] = 0; s.pad[1] = 0;
+    s.diffuse[0] = c_palette[color][0]; s.diffuse[1] = c_palette[color][1]; s.diffuse[2] = c_palette[color][2];
     cx.cover[slot] = cv;
     cx.shade[slot] = s;
 }
@@ -257,6 +265,7 @@ __device__ __forceinline__ bool insideNearFar(const ClipVert &v) { return v.cz >
 enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appended (or invisible) / the list is full / crosses the near or far plane
 
 // one box face: four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern)
+template <bool FAST>
 __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, const ClipVert &v3, int color,
                                                  uint32_t keyBase) {
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) {
@@ -273,11 +282,12 @@ __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipV
     if (!n) return kSetupDone;
     int slot = reserveTris(cx, n);
     if (slot < 0) return kSetupFull;
-    if (vis0) writeTri(cx, slot++, v0, v1, v2, s0, s1, s2, b0, color, keyBase);
-    if (vis1) writeTri(cx, slot, v0, v2, v3, s0, s2, s3, b1, color, keyBase + 1u);
+    if (vis0) writeTri<FAST>(cx, slot++, v0, v1, v2, s0, s1, s2, b0, color, keyBase);
+    if (vis1) writeTri<FAST>(cx, slot, v0, v2, v3, s0, s2, s3, b1, color, keyBase + 1u);
     return kSetupDone;
 }
 // one mesh triangle
+template <bool FAST>
 __device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, int color, uint32_t key) {
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) {
         if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f) return kSetupDone;
@@ -290,7 +300,7 @@ __device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVe
     if (!triBox(cx, s0, s1, s2, b0)) return kSetupDone;
     const int slot = reserveTris(cx, 1);
     if (slot < 0) return kSetupFull;
-    writeTri(cx, slot, v0, v1, v2, s0, s1, s2, b0, color, key);
+    writeTri<FAST>(cx, slot, v0, v1, v2, s0, s1, s2, b0, color, key);
     return kSetupDone;
 }
 
@@ -373,8 +383,6 @@ __device__ __forceinline__ uint32_t toUnorm8(float c) {
     return uint32_t(floorf(c * 255.0f + 0.5f));
 }
 
-__constant__ float c_palette[22][3];
-
 template <bool FAST> __device__ __forceinline__ float invLen3(float x, float y, float z) {
     if (FAST) return rsqrtf(__fmaf_rn(z, z, __fmaf_rn(y, y, x * x)));
     return 1.0f / sqrtf((x * x + y * y) + z * z);
@@ -393,29 +401,47 @@ __device__ __forceinline__ ShadeRec loadShade(const TriShade *tp) {  // shared m
     r.a0 = q[0]; r.a1 = q[1]; r.a2 = q[2]; r.a3 = q[3]; r.a4 = q[4]; r.a5 = q[5];
     return r;
 }
-template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const ShadeRec &rec, float l0, float l1, float l2, float &wOut) {
+// The fast variant skips the normal interpolation on flat triangles (the record holds the unit normal) and the highlight where it
+// cannot reach a tenth of an LSB.  (Taking the camera-space position from the interpolated w instead of interpolating the vertex
+// positions was tried and dropped: the sub-pixel snap of the vertices moves ~0.5 % of the bytes by one LSB.)
+template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const ShadeRec &rec, float l0, float l1, float l2, bool flat, float &wOut) {
     const float4 a0 = rec.a0, a1 = rec.a1, a2 = rec.a2, a3 = rec.a3, a4 = rec.a4, a5 = rec.a5;
     const float rw0 = a0.x, rw1 = a0.y, rw2 = a0.z;
-    const float p[9] = {a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
-    const float n[9] = {a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w, a5.x};
-    const int color = __float_as_int(a5.y);
     const float k0 = l0 * rw0, k1 = l1 * rw1, k2 = l2 * rw2;
     const float s = (k0 + k1) + k2;
     const float r = 1.0f / s;
-    const float q0 = k0 * r, q1 = k1 * r, q2 = k2 * r;
-    float Pc[3], N[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        Pc[c] = dot3<FAST>(q0, q1, q2, p[c], p[3 + c], p[6 + c]);
-        N[c] = dot3<FAST>(q0, q1, q2, n[c], n[3 + c], n[6 + c]);
-    }
     wOut = r;
+    float Pc[3], nn0, nn1, nn2;
+    if (FAST) {
+        const float p[9] = {a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+        const float q0 = k0 * r, q1 = k1 * r, q2 = k2 * r;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Pc[c] = dot3<true>(q0, q1, q2, p[c], p[3 + c], p[6 + c]);
+        if (flat) {
+            nn0 = a3.x; nn1 = a3.y; nn2 = a3.z;
+        } else {
+            const float n[9] = {a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w, a5.x};
+            const float N0 = dot3<true>(q0, q1, q2, n[0], n[3], n[6]), N1 = dot3<true>(q0, q1, q2, n[1], n[4], n[7]), N2 = dot3<true>(q0, q1, q2, n[2], n[5], n[8]);
+            const float nni = invLen3<true>(N0, N1, N2);
+            nn0 = N0 * nni; nn1 = N1 * nni; nn2 = N2 * nni;
+        }
+    } else {
+        const float p[9] = {a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+        const float n[9] = {a3.x, a3.y, a3.z, a3.w, a4.x, a4.y, a4.z, a4.w, a5.x};
+        const float q0 = k0 * r, q1 = k1 * r, q2 = k2 * r;
+        float N[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Pc[c] = dot3<false>(q0, q1, q2, p[c], p[3 + c], p[6 + c]);
+            N[c] = dot3<false>(q0, q1, q2, n[c], n[3 + c], n[6 + c]);
+        }
+        const float nni = invLen3<false>(N[0], N[1], N[2]);
+        nn0 = N[0] * nni; nn1 = N[1] * nni; nn2 = N[2] * nni;
+    }
     const float cd0 = -Pc[0], cd1 = -Pc[1], cd2 = -Pc[2];
     const float ld0 = 0.0f + cd0, ld1 = 4.0f + cd1, ld2 = 2.0f + cd2;
     const float ldi = invLen3<FAST>(ld0, ld1, ld2);
     const float nl0 = ld0 * ldi, nl1 = ld1 * ldi, nl2 = ld2 * ldi;
-    const float nni = invLen3<FAST>(N[0], N[1], N[2]);
-    const float nn0 = N[0] * nni, nn1 = N[1] * nni, nn2 = N[2] * nni;
     const float ndl = dot3<FAST>(nn0, nn1, nn2, nl0, nl1, nl2);
     const float intensity = ndl > 0.0f ? ndl : 0.0f;
     float spec = 0.0f;
@@ -425,20 +451,22 @@ template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const ShadeR
         const float cdi = invLen3<FAST>(cd0, cd1, cd2);
         const float vdr = dot3<FAST>(cd0 * cdi, cd1 * cdi, cd2 * cdi, r0, r1, r2);
         const float base = vdr > 0.0f ? vdr : 0.0f;
-        spec = pow300(base);
-        spec = spec < 0.0f ? 0.0f : (spec > 1.0f ? 1.0f : spec);
+        if (!FAST || base > 0.97f) {  // 0.97^300 = 1.1e-4: three hundredths of an LSB
+            spec = pow300(base);
+            spec = spec < 0.0f ? 0.0f : (spec > 1.0f ? 1.0f : spec);
+        }
     }
+    const float diffuse[3] = {a5.y, a5.z, a5.w};
     uint32_t out = 0xff000000u;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float diffuse = c_palette[color][c];
         float Lo;
         if (FAST) {
-            Lo = __fmaf_rn((0.73f * diffuse) * 0.66f, intensity, 0.33f * diffuse) + spec;
+            Lo = __fmaf_rn((0.73f * diffuse[c]) * 0.66f, intensity, 0.33f * diffuse[c]) + spec;
             out |= __float2uint_rn(__saturatef(Lo) * 255.0f) << (8 * c);
         } else {
-            Lo = 0.33f * diffuse;
-            Lo = Lo + ((0.73f * diffuse) * 0.66f) * intensity;
+            Lo = 0.33f * diffuse[c];
+            Lo = Lo + ((0.73f * diffuse[c]) * 0.66f) * intensity;
             Lo = Lo + 1.0f * spec;
             out |= toUnorm8(Lo) << (8 * c);
         }
@@ -448,7 +476,7 @@ template <bool FAST> __device__ __forceinline__ uint32_t shadePixel(const ShadeR
 
 // ---------------------------------------------------------------------------------------------------- coverage
 struct EdgeEval {  // one triangle's edge functions
-    int A0, A1, A2, B0, B1, B2, u0, u1, u2, small;
+    int A0, A1, A2, B0, B1, B2, u0, u1, u2, small, flat;
     long long C0, C1, C2;
     float z0, z1, z2, invArea;
     uint32_t key;
@@ -464,6 +492,7 @@ __device__ __forceinline__ EdgeEval unpackCover(const int4 q0, const int4 q1, co
     const int fl = q4.y;
     e.u0 = (fl & 1) ? 0 : 1; e.u1 = (fl & 2) ? 0 : 1; e.u2 = (fl & 4) ? 0 : 1;  // undo the top-left bias for the barycentrics
     e.small = (fl >> 3) & 1;
+    e.flat = (fl >> 4) & 1;
     return e;
 }
 __device__ __forceinline__ EdgeEval loadCover(const TriCover *c) {  // shared memory
@@ -613,7 +642,7 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
                 l1 = float(e.C1 + (long long)e.A1 * sx + (long long)e.B1 * sy32 + e.u1) * e.invArea;
                 l2 = float(e.C2 + (long long)e.A2 * sx + (long long)e.B2 * sy32 + e.u2) * e.invArea;
             }
-            o[k] = shadePixel<FAST>(rec, l0, l1, l2, wv[k]);
+            o[k] = shadePixel<FAST>(rec, l0, l1, l2, e.flat != 0, wv[k]);
         }
         uint8_t *obsPix = P.obs + ((size_t(view) * P.H + size_t(py)) * P.W + px) * 4;
         float *depthPix = P.depth ? P.depth + (size_t(view) * P.H + size_t(py)) * P.W + px : nullptr;
@@ -861,14 +890,14 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                             ClipVert cvt[4];
 #pragma unroll
                             for (int k = 0; k < 4; ++k) cvt[k] = makeVert(mv, nm, meshV + (face * 4 + k) * 6, P.p00, P.p11, P.p22, P.p32);
-                            res = setupFace(cx, cvt[0], cvt[1], cvt[2], cvt[3], color, ii * 128u + uint32_t(face) * 2u + 1u);
+                            res = setupFace<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], color, ii * 128u + uint32_t(face) * 2u + 1u);
                         } else {
                             const int vBase = mesh == 1 ? kVCapsule : (mesh == 2 ? kVSphere : (mesh == 3 ? kVCone : kVCylinder));
                             const int iBase = mesh == 1 ? kICapsule : (mesh == 2 ? kISphere : (mesh == 3 ? kICone : kICylinder));
                             ClipVert cvt[3];
 #pragma unroll
                             for (int k = 0; k < 3; ++k) cvt[k] = makeVert(mv, nm, meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6, P.p00, P.p11, P.p22, P.p32);
-                            res = setupTri(cx, cvt[0], cvt[1], cvt[2], color, ii * 128u + uint32_t(sub) + 1u);
+                            res = setupTri<FAST>(cx, cvt[0], cvt[1], cvt[2], color, ii * 128u + uint32_t(sub) + 1u);
                         }
                         pending = res == kSetupFull;
                         if (res == kSetupClip) {
@@ -943,7 +972,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                             if (lane == 0) base = reserveTris(cx, __popc(vm));
                             base = __shfl_sync(0xffffffffu, base, 0);
                             if (base < 0) done = false;
-                            else if (vis) writeTri(cx, base + __popc(vm & ((1u << lane) - 1u)), pp[0], pp[k], pp[k + 1], sa, sb, sc, tb, color, keyBase + uint32_t(t));
+                            else if (vis) writeTri<FAST>(cx, base + __popc(vm & ((1u << lane) - 1u)), pp[0], pp[k], pp[k + 1], sa, sb, sc, tb, color, keyBase + uint32_t(t));
                         }
                         if (done) { if (lane == 0) slowList[sidx] = uint16_t(e | 0x8000); }
                         else slowFull = true;
