@@ -260,14 +260,40 @@ __device__ __forceinline__ void writeTri(const SetupCtx &cx, int slot, const Cli
     cx.shade[slot] = s;
 }
 
+// uber.vert:53-110 for one vertex, in two halves: position (camera space + clip space) and normal.  mv = rows 0..2 of the model-view
+// matrix's four columns, nm = inverse transpose of its 3x3.  The item pass computes the positions first and the normals only for
+// what survives the screen-space tests (most mesh triangles face away or cover no pixel centre).
+__device__ __forceinline__ void vertPosition(ClipVert &cv, const float mv[12], const float *vp, float p00, float p11, float p22, float p32) {
+    // Matrix4::transformPoint: accumulate from 0 over the four columns, the translation column times 1 last
+    { float acc = 0.0f; acc += mv[0] * vp[0]; acc += mv[3] * vp[1]; acc += mv[6] * vp[2]; acc += mv[9] * 1.0f; cv.px = acc; }
+    { float acc = 0.0f; acc += mv[1] * vp[0]; acc += mv[4] * vp[1]; acc += mv[7] * vp[2]; acc += mv[10] * 1.0f; cv.py = acc; }
+    { float acc = 0.0f; acc += mv[2] * vp[0]; acc += mv[5] * vp[1]; acc += mv[8] * vp[2]; acc += mv[11] * 1.0f; cv.pz = acc; }
+    cv.cx = cv.px * p00;
+    cv.cy = cv.py * p11;
+    cv.cz = cv.pz * p22 + p32;
+    cv.cw = -cv.pz;
+}
+__device__ __forceinline__ void vertNormal(ClipVert &cv, const float nm[9], const float *vp) {
+    cv.nx = nm[0] * vp[3] + nm[3] * vp[4] + nm[6] * vp[5];
+    cv.ny = nm[1] * vp[3] + nm[4] * vp[4] + nm[7] * vp[5];
+    cv.nz = nm[2] * vp[3] + nm[5] * vp[4] + nm[8] * vp[5];
+}
+__device__ __forceinline__ ClipVert makeVert(const float mv[12], const float nm[9], const float *vp, float p00, float p11, float p22, float p32) {
+    ClipVert cv;
+    vertPosition(cv, mv, vp, p00, p11, p22, p32);
+    vertNormal(cv, nm, vp);
+    return cv;
+}
+
 __device__ __forceinline__ bool insideNearFar(const ClipVert &v) { return v.cz >= 0.0f && (v.cw - v.cz) >= 0.0f; }
 
 enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appended (or invisible) / the list is full / crosses the near or far plane
 
 // one box face: four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern)
+// (v0..v3 carry positions only; vp = the face's four mesh vertices, six floats each, for the normals)
 template <bool FAST>
-__device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, const ClipVert &v3, int color,
-                                                 uint32_t keyBase) {
+__device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, ClipVert &v3, const float nm[9], const float *vp,
+                                                 int color, uint32_t keyBase) {
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) {
         // wholly behind the near plane or wholly beyond the far plane: clipping would leave nothing
         if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f && v3.cz < 0.0f) return kSetupDone;
@@ -282,13 +308,15 @@ __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, const ClipV
     if (!n) return kSetupDone;
     int slot = reserveTris(cx, n);
     if (slot < 0) return kSetupFull;
+    vertNormal(v0, nm, vp); vertNormal(v1, nm, vp + 6); vertNormal(v2, nm, vp + 12); vertNormal(v3, nm, vp + 18);
     if (vis0) writeTri<FAST>(cx, slot++, v0, v1, v2, s0, s1, s2, b0, color, keyBase);
     if (vis1) writeTri<FAST>(cx, slot, v0, v2, v3, s0, s2, s3, b1, color, keyBase + 1u);
     return kSetupDone;
 }
 // one mesh triangle
 template <bool FAST>
-__device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVert &v0, const ClipVert &v1, const ClipVert &v2, int color, uint32_t key) {
+__device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, const float nm[9], const float *vp0, const float *vp1,
+                                                const float *vp2, int color, uint32_t key) {
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) {
         if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f) return kSetupDone;
         if ((v0.cw - v0.cz) < 0.0f && (v1.cw - v1.cz) < 0.0f && (v2.cw - v2.cz) < 0.0f) return kSetupDone;
@@ -300,6 +328,7 @@ __device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, const ClipVe
     if (!triBox(cx, s0, s1, s2, b0)) return kSetupDone;
     const int slot = reserveTris(cx, 1);
     if (slot < 0) return kSetupFull;
+    vertNormal(v0, nm, vp0); vertNormal(v1, nm, vp1); vertNormal(v2, nm, vp2);
     writeTri<FAST>(cx, slot, v0, v1, v2, s0, s1, s2, b0, color, key);
     return kSetupDone;
 }
@@ -336,23 +365,6 @@ __device__ __forceinline__ int clipNearFar(float *bufA, float *bufB, int c, unsi
         if (n < 3) return 0;
     }
     return n;
-}
-
-// uber.vert:53-110 for one vertex; mv = rows 0..2 of the model-view matrix's four columns, nm = inverse transpose of its 3x3
-__device__ __forceinline__ ClipVert makeVert(const float mv[12], const float nm[9], const float *vp, float p00, float p11, float p22, float p32) {
-    ClipVert cv;
-    // Matrix4::transformPoint: accumulate from 0 over the four columns, the translation column times 1 last
-    { float acc = 0.0f; acc += mv[0] * vp[0]; acc += mv[3] * vp[1]; acc += mv[6] * vp[2]; acc += mv[9] * 1.0f; cv.px = acc; }
-    { float acc = 0.0f; acc += mv[1] * vp[0]; acc += mv[4] * vp[1]; acc += mv[7] * vp[2]; acc += mv[10] * 1.0f; cv.py = acc; }
-    { float acc = 0.0f; acc += mv[2] * vp[0]; acc += mv[5] * vp[1]; acc += mv[8] * vp[2]; acc += mv[11] * 1.0f; cv.pz = acc; }
-    cv.cx = cv.px * p00;
-    cv.cy = cv.py * p11;
-    cv.cz = cv.pz * p22 + p32;
-    cv.cw = -cv.pz;
-    cv.nx = nm[0] * vp[3] + nm[3] * vp[4] + nm[6] * vp[5];
-    cv.ny = nm[1] * vp[3] + nm[4] * vp[4] + nm[7] * vp[5];
-    cv.nz = nm[2] * vp[3] + nm[5] * vp[4] + nm[8] * vp[5];
-    return cv;
 }
 
 // Conservative instance-level frustum test: the bounding sphere of the instance's mesh in view space against the near plane and the
@@ -888,16 +900,21 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                         if (mesh == 0) {
                             const int face = __fns(unsigned(meta >> 8), 0, sub + 1);
                             ClipVert cvt[4];
+                            const float *vp = meshV + (face * 4) * 6;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) cvt[k] = makeVert(mv, nm, meshV + (face * 4 + k) * 6, P.p00, P.p11, P.p22, P.p32);
-                            res = setupFace<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], color, ii * 128u + uint32_t(face) * 2u + 1u);
+                            for (int k = 0; k < 4; ++k) vertPosition(cvt[k], mv, vp + k * 6, P.p00, P.p11, P.p22, P.p32);
+                            res = setupFace<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], nm, vp, color, ii * 128u + uint32_t(face) * 2u + 1u);
                         } else {
                             const int vBase = mesh == 1 ? kVCapsule : (mesh == 2 ? kVSphere : (mesh == 3 ? kVCone : kVCylinder));
                             const int iBase = mesh == 1 ? kICapsule : (mesh == 2 ? kISphere : (mesh == 3 ? kICone : kICylinder));
                             ClipVert cvt[3];
+                            const float *vp[3];
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) cvt[k] = makeVert(mv, nm, meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6, P.p00, P.p11, P.p22, P.p32);
-                            res = setupTri<FAST>(cx, cvt[0], cvt[1], cvt[2], color, ii * 128u + uint32_t(sub) + 1u);
+                            for (int k = 0; k < 3; ++k) {
+                                vp[k] = meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6;
+                                vertPosition(cvt[k], mv, vp[k], P.p00, P.p11, P.p22, P.p32);
+                            }
+                            res = setupTri<FAST>(cx, cvt[0], cvt[1], cvt[2], nm, vp[0], vp[1], vp[2], color, ii * 128u + uint32_t(sub) + 1u);
                         }
                         pending = res == kSetupFull;
                         if (res == kSetupClip) {
