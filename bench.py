@@ -397,9 +397,16 @@ def measure_mixed(hz, K, Wm, rank, cores, gather):
     hz.barrier()
     ms = hz.max_ms(ev0.elapsed_time(ev1))
     faults = sum(g.faults() for g in engines)
-    if gathered is not None:  # the gathered tensor holds every rank's frames: rank r's block equals what rank r rendered
-        mine = gathered[rank * n_local:(rank + 1) * n_local]
-        ok = bool(torch.equal(mine, obs))
+    if gathered is not None:  # the gathered tensor holds every rank's frames: block r equals what rank r rendered (checksums exchanged)
+        def checksum(t):
+            v = t.reshape(-1).view(torch.int32).to(torch.int64)
+            return torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, device=v.device, dtype=torch.int64) % 1000003).sum()])
+
+        mine = checksum(obs)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        ok = bool(torch.equal(gathered[rank * n_local:(rank + 1) * n_local], obs)) and all(
+            bool(torch.equal(checksum(gathered[r * n_local:(r + 1) * n_local]), every[r])) for r in range(world))
     else:
         ok = None
     for g in engines:
@@ -407,7 +414,7 @@ def measure_mixed(hz, K, Wm, rank, cores, gather):
     out = {"value": n_local * world * K / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / K, "envs_per_gpu": n_local, "faults": int(faults), "steps": K}
     if gathered is not None:
         recv = (world - 1) * n_local * OBS_BYTES  # bytes arriving at each GPU per step
-        out.update({"gathered_bytes_per_step_per_gpu": recv, "nvlink_rx_gbs_per_gpu": recv / (ms / K / 1e3) / 1e9, "own_block_matches": ok})
+        out.update({"gathered_bytes_per_step_per_gpu": recv, "nvlink_rx_gbs_per_gpu": recv / (ms / K / 1e3) / 1e9, "gathered_blocks_match_their_ranks": ok})
     return out
 
 

@@ -59,7 +59,11 @@ static_assert(sizeof(TriCover) == 80 && sizeof(TriShade) == 96, "triangle record
 #endif
 constexpr int kThreads = MV_VIEW_THREADS;     // per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kInstChunk = 128;   // instances per TMA chunk (one thread each in the instance pass)
+#ifndef MV_VIEW_INST_CHUNK
+#define MV_VIEW_INST_CHUNK 128
+#endif
+constexpr int kInstChunk = MV_VIEW_INST_CHUNK;   // instances per TMA chunk (one thread each in the instance pass)
+static_assert(kInstChunk <= kThreads && kInstChunk <= 128, "one thread per instance of a chunk; slow-list entries keep 7 bits of it");
 constexpr int kXfWords = 23;      // per instance: model-view (12: three rows of each column), normal matrix (9), colour, mesh | face mask << 8
 constexpr int kClipVerts = 6;     // a triangle clipped by two planes has at most 5 vertices
 constexpr int kSmallArea = 24;    // triangles covering at most this many pixels of a tile are evaluated by one lane
