@@ -111,7 +111,8 @@ struct ViewMisc {
     int32_t nTris;      // append counter of the current batch (may run past triCap: the excess is retried in the next batch)
     int32_t nValid;     // first refused list index of the current batch (INT_MAX: none)
     int32_t tileCtr;
-    uint32_t claim;
+    uint32_t claim;     // this work item; claimed (and, when its env was ready, its view / counts / first chunk fetched) during the previous tile pass
+    int32_t prefetched;
     int32_t wsum[kWarps];
     int32_t nSlow[2];   // entries of the two slow-item lists (alternating per item sub-pass)
     uint32_t stat[8];   // debug counters of the current work item
@@ -737,12 +738,13 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
     unsigned long long *spill = P.spill + size_t(blockIdx.x) * size_t(P.spillStride);
     unsigned long long *frag = fragAll + warp * 128;
 
+    if (tid == 0) { M.claim = atomicAdd(P.workCounter, 1u) - P.counterBase; M.prefetched = 0; }
     for (;;) {
         const long long tc0 = P.stats ? clock64() : 0;
         long long tcWait = 0, tcInst = 0, tcItem = 0;
-        if (tid == 0) M.claim = atomicAdd(P.workCounter, 1u) - P.counterBase;
         __syncthreads();
         const uint32_t claim = M.claim;
+        const bool prefetched = M.prefetched != 0;
         if (claim >= total) break;
         const int vrel = int(claim / uint32_t(bands)), band = int(claim - uint32_t(vrel) * uint32_t(bands));
         const int view = P.viewBase + vrel;
@@ -755,7 +757,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         // its env's completion stamp (release/acquire through L2) instead of for the whole step grid.  What the step kernel
         // produced is then read with L2-coherent loads (ld.global.cg) or by the TMA unit (which reads L2), never through L1.
         if (tid == 0) {
-            if (P.ready) {
+            if (P.ready && !prefetched) {
                 const uint32_t *flag = P.ready + env;
                 uint32_t v;
                 while (true) {
@@ -772,12 +774,14 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
             for (int q = 0; q < 8; ++q) M.stat[q] = 0;
         }
         __syncthreads();
-        if (tid < 16) M.view[tid] = __ldcg(P.views + size_t(view) * 16 + tid);
-        else if (tid < 24) M.counts[tid - 16] = __ldcg(P.instCounts + env * 8 + (tid - 16));
-        __syncthreads();
+        if (!prefetched) {
+            if (tid < 16) M.view[tid] = __ldcg(P.views + size_t(view) * 16 + tid);
+            else if (tid < 24) M.counts[tid - 16] = __ldcg(P.instCounts + env * 8 + (tid - 16));
+            __syncthreads();
+        }
         const int nInst = M.counts[1];
         const int nChunks = (nInst + kInstChunk - 1) / kInstChunk;
-        if (tid == 0 && nChunks > 0) {
+        if (tid == 0 && nChunks > 0 && !prefetched) {
             const uint32_t bytes = uint32_t(min(nInst, kInstChunk)) * uint32_t(sizeof(MvInstance));
             mbarExpectTx(&M.bar[0], bytes);
             bulkG2S(stage, inst, bytes, &M.bar[0]);
@@ -1018,6 +1022,42 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
             atomicAdd(P.consumed + env, 1u);
         }
         const long long tc2 = P.stats ? clock64() : 0;
+        // Claim the next work item now and, if its env's state is already published, fetch its view matrix, its counts and its first
+        // instance chunk while this item's tiles are drawn (the stage buffers, M.view and M.counts are idle during the tile pass): the
+        // global round trips of the item head then cost nothing.  One thread; its warp joins the tile pass a little later.
+        if (tid == 0) {
+            const uint32_t nc = atomicAdd(P.workCounter, 1u) - P.counterBase;
+            int pre = 0;
+            if (nc < total) {
+                const int nview = P.viewBase + int(nc / uint32_t(bands)), nenv = nview / P.A;
+                bool ready = true;
+                if (P.ready) {
+                    uint32_t v;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.ready + nenv) : "memory");
+                    ready = v == P.readyStamp;
+                    if (ready) asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                if (ready) {
+                    float vm[16];
+                    int32_t cn[8];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) vm[q] = __ldcg(P.views + size_t(nview) * 16 + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) cn[q] = __ldcg(P.instCounts + nenv * 8 + q);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) M.view[q] = vm[q];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) M.counts[q] = cn[q];
+                    if (cn[1] > 0) {
+                        const uint32_t bytes = uint32_t(min(cn[1], kInstChunk)) * uint32_t(sizeof(MvInstance));
+                        mbarExpectTx(&M.bar[0], bytes);
+                        bulkG2S(stage, P.instances + size_t(nenv) * size_t(P.instStride), bytes, &M.bar[0]);
+                    }
+                    pre = 1;
+                }
+            }
+            M.claim = nc; M.prefetched = pre;
+        }
         tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
         if (P.stats && tid < 8) {
