@@ -157,6 +157,8 @@ int mv_debug_generate_level(const char *scenario, int num_agents, int env_seed, 
 int mv_debug_step_profile(mv_handle h, uint32_t *out, int enable);
 /* rasteriser launch shape: out4 = {persistent grid size, CTAs per SM, dynamic shared memory per CTA in bytes, row bands per view} */
 int mv_debug_raster_config(mv_handle h, int32_t *out4);
+/* current size of the per-level static-box arrays (option "static_cap" at start, grows on demand) */
+int mv_debug_static_cap(mv_handle h);
 /* rasteriser work counters since the last enable: out16 = {work items, instances read, instances with visible items, items (box faces /
  * mesh triangles set up), items clipped at the near / far plane, triangles drawn, batches, -, then thread-0 cycle sums: head (work
  * claim, env stamp, view matrix), TMA waits, instance passes, item passes, final tile pass, whole work item, -, -}; enable=1 arms /

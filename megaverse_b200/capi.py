@@ -60,7 +60,7 @@ EXPORTS = [
     "mv_rewards", "mv_dones", "mv_true_objectives", "mv_get_reward_shaping", "mv_set_reward_shaping", "mv_set_option", "mv_step_device", "mv_set_obs_buffer",
     "mv_sync", "mv_fetch_obs", "mv_draw_hires", "mv_actions_device", "mv_obs_device", "mv_depth_device", "mv_rewards_device", "mv_dones_device", "mv_stream", "mv_faults", "mv_fault_word", "mv_kernel_launches",
     "mv_last_kernel_ms", "mv_close", "mv_debug_get_level", "mv_debug_get_state", "mv_debug_get_voxels", "mv_debug_get_instances", "mv_debug_get_view",
-    "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_raster_config", "mv_debug_raster_stats", "mv_debug_color_tables", "mv_debug_defaults", "mv_debug_count_unfit_levels", "mv_levels_skipped", "mv_debug_bzset", "mv_debug_generate_level",
+    "mv_debug_render_instances", "mv_debug_step_profile", "mv_debug_raster_config", "mv_debug_static_cap", "mv_debug_raster_stats", "mv_debug_color_tables", "mv_debug_defaults", "mv_debug_count_unfit_levels", "mv_levels_skipped", "mv_debug_bzset", "mv_debug_generate_level",
 ]
 
 
@@ -219,6 +219,10 @@ class Engine:
         lib().mv_debug_step_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         self._ck(lib().mv_debug_step_profile(self._h, out.ctypes.data if read else None, 1 if enable else 0))
         return out
+
+    def static_cap(self):
+        lib().mv_debug_static_cap.argtypes = [C.c_void_p]
+        return int(lib().mv_debug_static_cap(self._h))
 
     def raster_config(self):
         out = (C.c_int32 * 4)()

@@ -1112,6 +1112,7 @@ int mv_debug_raster_stats(mv_handle h, unsigned long long *out16, int enable) {
     else h->d_rasterStats.free();
     return MV_OK;
 }
+int mv_debug_static_cap(mv_handle h) { return h ? h->staticCap : MV_ERR_ARG; }  // current size of the per-level static-box arrays
 int mv_debug_raster_config(mv_handle h, int32_t *out4) {  // {persistent grid, CTAs per SM, dynamic shared memory bytes, row bands per view}
     if (!h || !out4) return MV_ERR_ARG;
     out4[0] = h->rasterGrid; out4[1] = h->rasterCtasPerSM; out4[2] = int32_t(h->rasterSmem); out4[3] = h->rasterBands;

@@ -191,6 +191,17 @@ struct SetupCtx {
 // All triangles of one item are appended with ONE reservation (all or nothing), so an item that does not fit leaves nothing behind and is
 // simply retried in the next batch; the first reservation of a batch always fits.  (The context travels by value, so the compiler no
 // longer sees that the counters live in shared memory: say it.)  Returns the first slot or -1.
+// index of the n-th (0-based) set bit of a six-bit face mask (__fns is a long software loop)
+__device__ __forceinline__ int nthFace(unsigned mask, int n) {
+    int face = 0, seen = 0;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        const int bit = int(mask >> f) & 1;
+        if (bit && seen == n) face = f;
+        seen += bit;
+    }
+    return face;
+}
 __device__ __forceinline__ int reserveTris(const SetupCtx &cx, int n) {
     int base;
     asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(base) : "r"(smemAddrOf(cx.nTris)), "r"(n) : "memory");
@@ -291,6 +302,12 @@ __device__ __forceinline__ ClipVert makeVert(const float mv[12], const float nm[
 }
 
 __device__ __forceinline__ bool insideNearFar(const ClipVert &v) { return v.cz >= 0.0f && (v.cw - v.cz) >= 0.0f; }
+// Bits of the four side planes a vertex is strictly outside of, in homogeneous clip space (x > w, x < -w, y > w, y < -w; the linear
+// inequalities hold for w <= 0 too).  A polygon whose vertices share a bit lies wholly beyond that plane -- clipped against near /
+// far or not -- and covers no pixel of the viewport: the reference's rasteriser scissors it away.
+__device__ __forceinline__ unsigned sideOutcode(const ClipVert &v) {
+    return (v.cx > v.cw ? 1u : 0u) | (v.cx < -v.cw ? 2u : 0u) | (v.cy > v.cw ? 4u : 0u) | (v.cy < -v.cw ? 8u : 0u);
+}
 
 enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appended (or invisible) / the list is full / crosses the near or far plane
 
@@ -299,6 +316,7 @@ enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appende
 template <bool FAST>
 __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, ClipVert &v3, const float nm[9], const float *vp,
                                                  int color, uint32_t keyBase) {
+    if (sideOutcode(v0) & sideOutcode(v1) & sideOutcode(v2) & sideOutcode(v3)) return kSetupDone;
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) {
         // wholly behind the near plane or wholly beyond the far plane: clipping would leave nothing
         if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f && v3.cz < 0.0f) return kSetupDone;
@@ -322,6 +340,7 @@ __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, ClipVert &v
 template <bool FAST>
 __device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, const float nm[9], const float *vp0, const float *vp1,
                                                 const float *vp2, int color, uint32_t key) {
+    if (sideOutcode(v0) & sideOutcode(v1) & sideOutcode(v2)) return kSetupDone;
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) {
         if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f) return kSetupDone;
         if ((v0.cw - v0.cz) < 0.0f && (v1.cw - v1.cz) < 0.0f && (v2.cw - v2.cz) < 0.0f) return kSetupDone;
@@ -906,7 +925,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                         const uint32_t ii = uint32_t(cBase + i);
                         SetupResult res;
                         if (mesh == 0) {
-                            const int face = __fns(unsigned(meta >> 8), 0, sub + 1);
+                            const int face = nthFace(unsigned(meta >> 8) & 63u, sub);
                             ClipVert cvt[4];
                             const float *vp = meshV + (face * 4) * 6;
 #pragma unroll
@@ -956,7 +975,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                         int nSrc;
                         uint32_t keyBase;
                         if (mesh == 0) {  // lanes 0..3: the face's vertices; source triangles (0,1,2) and (0,2,3)
-                            const int face = __fns(unsigned(meta >> 8), 0, sub + 1);
+                            const int face = nthFace(unsigned(meta >> 8) & 63u, sub);
                             nSrc = 2; keyBase = ii * 128u + uint32_t(face) * 2u + 1u;
                             if (lane < 4) {
                                 const ClipVert v = makeVert(mv, nm, meshV + (face * 4 + lane) * 6, P.p00, P.p11, P.p22, P.p32);

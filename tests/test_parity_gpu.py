@@ -681,28 +681,24 @@ def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
 @pytest.mark.parametrize("mode", ["host", "device"])
 def test_static_box_arrays_grow_on_demand(built, mode):
     """the number of static boxes of a level has no bound (component_voxel_grid.hpp:108-187): the engine's per-level arrays and the instance
-    lists that depend on them are re-pitched whenever a generated level needs more.  Started from 16 boxes, every Collect landscape forces
-    growth -- at reset and again at episode turnovers, on the host-facing and on the asynchronous path -- and one env is seeded with a
-    landscape of more than 768 boxes (the former fixed capacity).  State, rewards, dones and frames equal the oracle's throughout."""
+    lists that depend on them are re-pitched whenever a generated level needs more.  HexExplore mazes of random size with short episodes,
+    arrays started at 16 boxes: growth at reset and again at later turnovers, while the device holds live instance lists, on the host-facing
+    and on the asynchronous path.  State, rewards, dones and frames equal the oracle's throughout."""
     import torch
 
     import orc
     from megaverse_b200 import capi
 
-    E, A, steps = 6, 2, 75
-    params = {"episodeLengthSec": -1.0}
-    o = orc.Oracle("Collect", E, A, 128, 72, params=params)
-    g = capi.Engine("Collect", E, A, 128, 72, num_threads=3, params=params)
+    E, A, steps = 2, 2, 180  # (master seed 48: the first two mazes of both envs have < 100 walls, the third has ~280)
+    params = {"episodeLengthSec": 0.6}
+    o = orc.Oracle("HexExplore", E, A, 128, 72, params=params)
+    g = capi.Engine("HexExplore", E, A, 128, 72, num_threads=3, params=params)
     g.set_option("fast_shading", 0)
     g.set_option("static_cap", 16)
-    for e in range(E):
-        seed = 889027061 if e == 1 else 300 + e
-        o.seed_env(e, seed); g.seed_env(e, seed)
+    o.seed(48); g.seed(48)
     o.reset(); g.reset()
-    assert o.level(1)[0] > 768
-    for e in range(E):
-        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
-        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    cap0 = g.static_cap()
+    assert cap0 > 16
     assert _assert_same_frame(o, g, "reset") == 1.0
     rng = np.random.default_rng(8)
     acts = np.stack([helpers.purposeful_actions(rng, E * A, t) for t in range(steps)]).astype(np.int32)
@@ -723,7 +719,37 @@ def test_static_box_arrays_grow_on_demand(built, mode):
     if mode == "device":
         g.sync()
         g.fetch_obs()
-    assert ndone >= 3
+    assert ndone >= 10 * E
+    assert g.static_cap() > cap0, "the case is meant to grow the arrays during the rollout (%d -> %d)" % (cap0, g.static_cap())
+    _assert_same_state(o, g, E, "end")
+    assert _assert_same_frame(o, g, "end") == 1.0
+    assert g.faults() == 0
+    o.close(); g.close()
+
+
+def test_level_beyond_the_former_static_capacity(built):
+    """a Collect landscape of more than 768 static boxes (round 1 refused it): level, instances, frames and a short rollout equal the oracle's"""
+    import orc
+    from megaverse_b200 import capi
+
+    E, A = 3, 2
+    o = orc.Oracle("Collect", E, A, 128, 72)
+    g = capi.Engine("Collect", E, A, 128, 72, num_threads=2)
+    g.set_option("fast_shading", 0)
+    for e in range(E):
+        seed = 889027061 if e == 1 else 300 + e
+        o.seed_env(e, seed); g.seed_env(e, seed)
+    o.reset(); g.reset()
+    assert o.level(1)[0] > 768 and g.static_cap() >= o.level(1)[0]
+    for e in range(E):
+        assert np.array_equal(o.level(e), g.level(e)), "level %d" % e
+        assert np.array_equal(o.instances(e).view(np.uint32), g.instances(e).view(np.uint32)), "instances %d" % e
+    assert _assert_same_frame(o, g, "reset") == 1.0
+    rng = np.random.default_rng(8)
+    for t in range(40):
+        acts = helpers.purposeful_actions(rng, E * A, t)
+        o.step(acts); g.step(acts)
+        assert np.array_equal(o.rewards().view(np.uint32), np.array(g.rewards()).view(np.uint32)), "step %d" % t
     _assert_same_state(o, g, E, "end")
     assert _assert_same_frame(o, g, "end") == 1.0
     assert g.faults() == 0
