@@ -76,12 +76,11 @@ int mv_get_reward_shaping(mv_handle h, int env, int agent, const char **keys, fl
 int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *keys, const float *vals, int n);
 
 /* options: "depth" (0/1, before first reset), "obs_to_host" (0/1: whether mv_step delivers the observation tensor to host
- * memory; 1 by default), "zero_copy" (-1/0/1, default -1 = by size: host-facing steps either let the rasteriser store rows straight into the
- * pinned host buffer -- batches up to 24 MB of observations; the HBM tensor is then stale and mv_obs_device refuses it until the next
- * mv_step_device -- or rasterise into HBM in "host_slices" launches (0 = by size, one per ~12 MB) whose downloads run on the copy
- * engine while the next slice is drawn),
+ * memory; 1 by default), "zero_copy" (0/1, default 1: host-facing steps let the rasteriser store rows straight into the pinned host buffer, the
+ * PCIe writes overlapping the drawing -- the HBM tensor is then stale and mv_obs_device refuses it until the next mv_step_device; 0:
+ * rasterise into HBM in "host_slices" launches (0 = by size) whose downloads run on the copy engine while the next slice is drawn),
  * "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
- * "tri_cap" (32..1022, default 288: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
+ * "tri_cap" (32..1022, default 384: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
  * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
  * chosen from the number of views by default, results do not depend on it),
  * "static_cap" (before the first reset: initial size of the per-level static-box arrays, default 768; they grow whenever a

@@ -115,7 +115,7 @@ struct ViewMisc {
     int32_t prefetched;
     int32_t wsum[kWarps];
     int32_t nSlow[2];   // entries of the two slow-item lists (alternating per item sub-pass)
-    uint32_t stat[8];   // debug counters of the current work item
+    uint32_t stat[8];   // debug counters of the current work item ([7]: item sub-passes)
     alignas(8) unsigned long long bar[2];
 };
 __host__ __device__ inline SmemLayout smemLayout(int triCap) {
@@ -126,10 +126,12 @@ __host__ __device__ inline SmemLayout smemLayout(int triCap) {
     L.shade = o; o += uint32_t(triCap) * uint32_t(sizeof(TriShade));
     L.xf = o; o += uint32_t(kXfWords) * kInstChunk * 4u;
     L.off = o; o += (kInstChunk + 4u) * 4u;
+    // per warp: 128 fragments (tile pass) -- the same bytes hold the warp's clip polygons during the item pass (4 x kClipVerts x 40 B =
+    // 960 B <= 1024 B): neither keeps state across the other (fragments are zeroed per tile, polygons rebuilt per clipped item)
     L.frag = o; o += uint32_t(kWarps) * 128u * 8u;
     L.meshV = o; o += uint32_t(kMeshVerts) * 6u * 4u;
     L.meshI = o; o += (uint32_t(kMeshIdx) + 15u) & ~15u;
-    L.clip = o; o += uint32_t(kWarps) * 4u * kClipVerts * 40u;  // per warp: polygon + scratch of two source triangles (ClipVert = 40 B)
+    L.clip = L.frag;
     L.slow = o; o += 2u * kThreads * 2u;                        // two lists of at most one entry per thread
     L.misc = o; o += (uint32_t(sizeof(ViewMisc)) + 15u) & ~15u;
     L.total = o;
@@ -724,7 +726,8 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
     float *meshV = reinterpret_cast<float *>(smem + L.meshV);    // [kMeshVerts][6]
     uint8_t *meshI = smem + L.meshI;
     uint16_t *slowAll = reinterpret_cast<uint16_t *>(smem + L.slow);  // [2][kThreads]: instance-in-chunk | item << 7 | done << 15
-    ClipVert *clipScratch = reinterpret_cast<ClipVert *>(smem + L.clip) + (threadIdx.x >> 5) * 4 * kClipVerts;
+    ClipVert *clipScratch = reinterpret_cast<ClipVert *>(smem + L.clip + (threadIdx.x >> 5) * 1024u);
+    static_assert(4 * kClipVerts * sizeof(ClipVert) <= 1024, "a warp's clip polygons share its fragment buffer");
     ViewMisc &M = *reinterpret_cast<ViewMisc *>(smem + L.misc);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -904,7 +907,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
             for (int ibase = 0; ibase < totalItems; ibase += kThreads, parity ^= 1) {
                 const int j = ibase + tid;
                 uint16_t *slowList = slowAll + parity * kThreads;
-                if (tid == 0) M.nSlow[parity ^ 1] = 0;  // the other list: last read before the barrier that closed the previous sub-pass
+                if (tid == 0) { M.nSlow[parity ^ 1] = 0; if (P.stats) M.stat[7] += 1; }  // the other list: last read before the barrier that closed the previous sub-pass
                 bool pending = j < totalItems, pushed = false, again = false;
                 for (;;) {
                     if (pending) {

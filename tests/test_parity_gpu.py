@@ -600,7 +600,7 @@ def test_device_tensor_interface(built):
     g = capi.Engine("Collect", 4, 2, 128, 72, num_threads=2)
     g.seed(3); g.reset()
     g.step(np.full(8, 1 << 3, dtype=np.int32))
-    # a small batch is delivered by zero-copy stores into the host buffer: the HBM tensor is stale and the engine says so
+    # the default delivery is zero-copy stores into the host buffer: the HBM tensor is stale and the engine says so
     with pytest.raises(capi.MegaverseError):
         g.device_array("obs")
     host = np.array(g.obs()).copy()
