@@ -80,7 +80,7 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
  * PCIe writes overlapping the drawing -- the HBM tensor is then stale and mv_obs_device refuses it until the next mv_step_device; 0:
  * rasterise into HBM in "host_slices" launches (0 = by size) whose downloads run on the copy engine while the next slice is drawn),
  * "fast_shading" (0/1, default 1: +-1 LSB fragment maths),
- * "tri_cap" (32..1022, default 384: triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
+ * "tri_cap" (32..1022, default 368: the largest that leaves two CTAs per SM; triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
  * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
  * chosen from the number of views by default, results do not depend on it),
  * "static_cap" (before the first reset: initial size of the per-level static-box arrays, default 768; they grow whenever a

@@ -130,7 +130,7 @@ struct mv_engine {
     std::unique_ptr<WorkerPool> pool;
 
     int gridCells = 0, gridWords = 0;
-    int triCap = 384;              // triangle-list capacity of one raster CTA (shared memory); larger views are drawn in several batches
+    int triCap = 368;              // triangle-list capacity of one raster CTA (shared memory); larger views are drawn in several batches
     std::atomic<int> maxObjSeen{0};
     bool wantDepth = false, obsToHost = true, didReset = false, fastShading = true;
     bool hostStepPending = false;  // between mv_step_begin and mv_step_end

@@ -66,6 +66,7 @@ constexpr int kInstChunk = MV_VIEW_INST_CHUNK;   // instances per TMA chunk (one
 static_assert(kInstChunk <= kThreads && kInstChunk <= 128, "one thread per instance of a chunk; slow-list entries keep 7 bits of it");
 constexpr int kXfWords = 23;      // per instance: model-view (12: three rows of each column), normal matrix (9), colour, mesh | face mask << 8
 constexpr int kClipVerts = 6;     // a triangle clipped by two planes has at most 5 vertices
+constexpr int kSmallList = 128;   // small triangles of a tile collected before they are evaluated (32 at a time, one lane each)
 constexpr int kSmallArea = 24;    // triangles covering at most this many pixels of a tile are evaluated by one lane
 // a fragment is (~depth bits << 32) | (draw-order key << kIdxBits) | index in the CTA's triangle list
 constexpr int kIdxBits = 10;
@@ -104,7 +105,7 @@ struct ViewParams {
     float p00, p11, p22, p32;
 };
 
-struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, meshV, meshI, clip, slow, misc, total; };
+struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, small, meshV, meshI, clip, slow, misc, total; };
 struct ViewMisc {
     float view[16];
     int32_t counts[8];
@@ -132,6 +133,7 @@ __host__ __device__ inline SmemLayout smemLayout(int triCap) {
     L.meshV = o; o += uint32_t(kMeshVerts) * 6u * 4u;
     L.meshI = o; o += (uint32_t(kMeshIdx) + 15u) & ~15u;
     L.clip = L.frag;
+    L.small = o; o += uint32_t(kWarps) * kSmallList * 2u;       // per warp: list indices of the small triangles of the current tile
     L.slow = o; o += 2u * kThreads * 2u;                        // two lists of at most one entry per thread
     L.misc = o; o += (uint32_t(sizeof(ViewMisc)) + 15u) & ~15u;
     L.total = o;
@@ -313,11 +315,13 @@ __device__ __forceinline__ unsigned sideOutcode(const ClipVert &v) {
 
 enum SetupResult { kSetupDone = 0, kSetupFull = 1, kSetupClip = 2 };  // appended (or invisible) / the list is full / crosses the near or far plane
 
-// one box face: four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern)
-// (v0..v3 carry positions only; vp = the face's four mesh vertices, six floats each, for the normals)
+// One item: a box face -- four vertices, triangles (0,1,2) and (0,2,3) (Magnum cubeSolid index pattern), nTri = 2 -- or a mesh
+// triangle (nTri = 1, v3 repeats v2).  v0..v3 carry positions only; vp0..vp3 = the mesh vertices (six floats each) for the normals,
+// which are only computed for what survives the screen-space tests.  One copy of the set-up code serves both (code size: the kernel's
+// hot loops have to stay inside the instruction cache).
 template <bool FAST>
-__device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, ClipVert &v3, const float nm[9], const float *vp,
-                                                 int color, uint32_t keyBase) {
+__device__ __forceinline__ SetupResult setupItem(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, ClipVert &v3, int nTri, const float nm[9], const float *vp0,
+                                                 const float *vp1, const float *vp2, const float *vp3, int color, uint32_t keyBase) {
     if (sideOutcode(v0) & sideOutcode(v1) & sideOutcode(v2) & sideOutcode(v3)) return kSetupDone;
     if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2) && insideNearFar(v3))) {
         // wholly behind the near plane or wholly beyond the far plane: clipping would leave nothing
@@ -326,36 +330,24 @@ __device__ __forceinline__ SetupResult setupFace(const SetupCtx &cx, ClipVert &v
         return kSetupClip;
     }
     const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
-    const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh), s3 = projectVert(v3, hw, hh);
+    const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh);
+    ScreenVert s3 = s2;
+    if (nTri == 2) s3 = projectVert(v3, hw, hh);
     TriBox b0, b1;
-    const bool vis0 = triBox(cx, s0, s1, s2, b0), vis1 = triBox(cx, s0, s2, s3, b1);
+    const bool vis0 = triBox(cx, s0, s1, s2, b0), vis1 = nTri == 2 && triBox(cx, s0, s2, s3, b1);
     const int n = (vis0 ? 1 : 0) + (vis1 ? 1 : 0);
     if (!n) return kSetupDone;
     int slot = reserveTris(cx, n);
     if (slot < 0) return kSetupFull;
-    vertNormal(v0, nm, vp); vertNormal(v1, nm, vp + 6); vertNormal(v2, nm, vp + 12); vertNormal(v3, nm, vp + 18);
-    if (vis0) writeTri<FAST>(cx, slot++, v0, v1, v2, s0, s1, s2, b0, color, keyBase);
-    if (vis1) writeTri<FAST>(cx, slot, v0, v2, v3, s0, s2, s3, b1, color, keyBase + 1u);
-    return kSetupDone;
-}
-// one mesh triangle
-template <bool FAST>
-__device__ __forceinline__ SetupResult setupTri(const SetupCtx &cx, ClipVert &v0, ClipVert &v1, ClipVert &v2, const float nm[9], const float *vp0, const float *vp1,
-                                                const float *vp2, int color, uint32_t key) {
-    if (sideOutcode(v0) & sideOutcode(v1) & sideOutcode(v2)) return kSetupDone;
-    if (!(insideNearFar(v0) && insideNearFar(v1) && insideNearFar(v2))) {
-        if (v0.cz < 0.0f && v1.cz < 0.0f && v2.cz < 0.0f) return kSetupDone;
-        if ((v0.cw - v0.cz) < 0.0f && (v1.cw - v1.cz) < 0.0f && (v2.cw - v2.cz) < 0.0f) return kSetupDone;
-        return kSetupClip;
+    vertNormal(v0, nm, vp0); vertNormal(v1, nm, vp1); vertNormal(v2, nm, vp2); vertNormal(v3, nm, vp3);
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+        if (!(t ? vis1 : vis0)) continue;
+        const ClipVert vb = t ? v2 : v1, vc = t ? v3 : v2;
+        const ScreenVert sb = t ? s2 : s1, sc = t ? s3 : s2;
+        const TriBox tb = t ? b1 : b0;
+        writeTri<FAST>(cx, slot++, v0, vb, vc, s0, sb, sc, tb, color, keyBase + uint32_t(t));
     }
-    const float hw = float(cx.W) * 0.5f, hh = float(cx.H) * 0.5f;
-    const ScreenVert s0 = projectVert(v0, hw, hh), s1 = projectVert(v1, hw, hh), s2 = projectVert(v2, hw, hh);
-    TriBox b0;
-    if (!triBox(cx, s0, s1, s2, b0)) return kSetupDone;
-    const int slot = reserveTris(cx, 1);
-    if (slot < 0) return kSetupFull;
-    vertNormal(v0, nm, vp0); vertNormal(v1, nm, vp1); vertNormal(v2, nm, vp2);
-    writeTri<FAST>(cx, slot, v0, v1, v2, s0, s1, s2, b0, color, key);
     return kSetupDone;
 }
 
@@ -546,9 +538,24 @@ __device__ __forceinline__ unsigned long long packFrag(float z, uint32_t key, in
 // All tiles of the band against the current batch of `count` triangles.  batch 0 paints every pixel (background included); later
 // batches repaint only the pixels they win.  Unless `final`, the per-pixel best fragment is parked in the CTA's spill slab with its
 // list index replaced by kStaleIdx (the list is about to be overwritten).
+// out of line on purpose: the tile pass is called from two places (a full triangle list in mid-view, the end of the view) and two inlined
+// copies of it pushed the kernel's hot code out of the instruction cache (Collect 1024 x 4: 2.65 ms inlined, 1.70 ms called)
+#ifdef MV_TILE_FORCEINLINE
+#define MV_TILE_INLINE __forceinline__
+#else
+#define MV_TILE_INLINE __noinline__
+#endif
+extern __shared__ __align__(128) unsigned char g_viewSmem[];  // the CTA's dynamic shared memory (carved up by smemLayout)
+
 template <bool FAST>
-__device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *cover, const TriShade *shade, int count, unsigned long long *frag, int32_t *tileCtr,
-                                         unsigned long long *spill, int view, int rowLo, int bandTiles, int batch, bool final) {
+__device__ MV_TILE_INLINE void tilePass(const ViewParams &P, int count, unsigned long long *spill, int view, int rowLo, int bandTiles, int batch, bool final) {
+    // addresses derived from the shared-memory symbol itself, so that this out-of-line function keeps shared-space loads and atomics
+    const SmemLayout L = smemLayout(P.triCap);
+    const TriCover *cover = reinterpret_cast<const TriCover *>(g_viewSmem + L.cover);
+    const TriShade *shade = reinterpret_cast<const TriShade *>(g_viewSmem + L.shade);
+    unsigned long long *frag = reinterpret_cast<unsigned long long *>(g_viewSmem + L.frag) + (threadIdx.x >> 5) * 128;
+    uint16_t *smallList = reinterpret_cast<uint16_t *>(g_viewSmem + L.small) + (threadIdx.x >> 5) * kSmallList;
+    int32_t *tileCtr = &reinterpret_cast<ViewMisc *>(g_viewSmem + L.misc)->tileCtr;
     const int lane = threadIdx.x & 31;
     const int tilesX = P.W >> 5;
     for (;;) {
@@ -565,44 +572,66 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
         for (int k = 0; k < 4; ++k) frag[lane * 4 + k] = 0ull;
         __syncwarp();
 
-        for (int base = 0; base < count; base += 32) {
+        // Small triangles (at most kSmallArea pixels of the tile) are evaluated one lane per triangle; they are first COLLECTED over the
+        // whole list scan and then evaluated 32 at a time -- scattered over the scan they would cost a serial pixel walk per 32 list
+        // entries with one or two lanes busy.
+        int nSmall = 0;
+        auto evalSmall = [&](int n) {
+            __syncwarp();
+            for (int s0 = 0; s0 < n; s0 += 32) {
+                if (s0 + lane < n) {
+                    const int j = int(smallList[s0 + lane]);
+                    const uint2 bb = *reinterpret_cast<const uint2 *>(&cover[j].bx);
+                    const int bx0 = max(int(bb.x & 0xffffu), tx0), bx1 = min(int(bb.x >> 16), tx0 + 31);
+                    const int by0 = max(int(bb.y & 0xffffu), ty0), by1 = min(int(bb.y >> 16), ty0 + 3);
+                    const EdgeEval e = loadCover(cover + j);
+                    for (int y = by0; y <= by1; ++y) {
+                        const int sy = y * 256 + 128, sx0 = bx0 * 256 + 128;
+                        if (e.small) {
+                            int F0 = int(e.C0) + e.A0 * sx0 + e.B0 * sy, F1 = int(e.C1) + e.A1 * sx0 + e.B1 * sy, F2 = int(e.C2) + e.A2 * sx0 + e.B2 * sy;
+                            for (int x = bx0; x <= bx1; ++x) {
+                                if ((F0 | F1 | F2) >= 0) {
+                                    const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
+                                    const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
+                                    if (z <= 1.0f) atomicMax(&frag[(y - ty0) * 32 + (x - tx0)], packFrag(z, e.key, j));
+                                }
+                                F0 += e.A0 * 256; F1 += e.A1 * 256; F2 += e.A2 * 256;
+                            }
+                        } else {
+                            long long F0 = e.C0 + (long long)e.A0 * sx0 + (long long)e.B0 * sy, F1 = e.C1 + (long long)e.A1 * sx0 + (long long)e.B1 * sy,
+                                      F2 = e.C2 + (long long)e.A2 * sx0 + (long long)e.B2 * sy;
+                            for (int x = bx0; x <= bx1; ++x) {
+                                if ((F0 | F1 | F2) >= 0) {
+                                    const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
+                                    const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
+                                    if (z <= 1.0f) atomicMax(&frag[(y - ty0) * 32 + (x - tx0)], packFrag(z, e.key, j));
+                                }
+                                F0 += (long long)e.A0 * 256; F1 += (long long)e.A1 * 256; F2 += (long long)e.A2 * 256;
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        };
+        int base = 0;
+        do {  // (one call site of evalSmall: the scan pauses when the list could overflow)
+        nSmall = 0;
+        for (; base < count && nSmall + 32 <= kSmallList; base += 32) {
             const int j = base + lane;
             bool ov = false, small = false;
-            int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
             if (j < count) {
                 const uint2 bb = *reinterpret_cast<const uint2 *>(&cover[j].bx);
-                bx0 = max(int(bb.x & 0xffffu), tx0); bx1 = min(int(bb.x >> 16), tx0 + 31);
-                by0 = max(int(bb.y & 0xffffu), ty0); by1 = min(int(bb.y >> 16), ty0 + 3);
+                const int bx0 = max(int(bb.x & 0xffffu), tx0), bx1 = min(int(bb.x >> 16), tx0 + 31);
+                const int by0 = max(int(bb.y & 0xffffu), ty0), by1 = min(int(bb.y >> 16), ty0 + 3);
                 ov = bx0 <= bx1 && by0 <= by1;
                 small = ov && (bx1 - bx0 + 1) * (by1 - by0 + 1) <= kSmallArea;
             }
-            // ---- small triangles: one lane each
-            if (small) {
-                const EdgeEval e = loadCover(cover + j);
-                for (int y = by0; y <= by1; ++y) {
-                    const int sy = y * 256 + 128, sx0 = bx0 * 256 + 128;
-                    if (e.small) {
-                        int F0 = int(e.C0) + e.A0 * sx0 + e.B0 * sy, F1 = int(e.C1) + e.A1 * sx0 + e.B1 * sy, F2 = int(e.C2) + e.A2 * sx0 + e.B2 * sy;
-                        for (int x = bx0; x <= bx1; ++x) {
-                            if ((F0 | F1 | F2) >= 0) {
-                                const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
-                                const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
-                                if (z <= 1.0f) atomicMax(&frag[(y - ty0) * 32 + (x - tx0)], packFrag(z, e.key, j));
-                            }
-                            F0 += e.A0 * 256; F1 += e.A1 * 256; F2 += e.A2 * 256;
-                        }
-                    } else {
-                        long long F0 = e.C0 + (long long)e.A0 * sx0 + (long long)e.B0 * sy, F1 = e.C1 + (long long)e.A1 * sx0 + (long long)e.B1 * sy,
-                                  F2 = e.C2 + (long long)e.A2 * sx0 + (long long)e.B2 * sy;
-                        for (int x = bx0; x <= bx1; ++x) {
-                            if ((F0 | F1 | F2) >= 0) {
-                                const float l0 = float(F0 + e.u0) * e.invArea, l1 = float(F1 + e.u1) * e.invArea, l2 = float(F2 + e.u2) * e.invArea;
-                                const float z = (l0 * e.z0 + l1 * e.z1) + l2 * e.z2;
-                                if (z <= 1.0f) atomicMax(&frag[(y - ty0) * 32 + (x - tx0)], packFrag(z, e.key, j));
-                            }
-                            F0 += (long long)e.A0 * 256; F1 += (long long)e.A1 * 256; F2 += (long long)e.A2 * 256;
-                        }
-                    }
+            {
+                const unsigned sm = __ballot_sync(0xffffffffu, small);
+                if (sm) {
+                    if (small) smallList[nSmall + __popc(sm & ((1u << lane) - 1u))] = uint16_t(j);
+                    nSmall += __popc(sm);
                 }
             }
             // ---- larger triangles: whole warp, lane = 4 pixels, the record is broadcast from shared memory
@@ -641,7 +670,8 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
                 }
             }
         }
-        __syncwarp();
+        evalSmall(nSmall);
+        } while (base < count);
         // ---- merge both paths (and the earlier batches), recompute the winner's barycentrics, shade, store
         const int pixInTile = (lane >> 3) * 32 + (lane & 7) * 4;
         unsigned long long *sp = spill + size_t(tile) * 128 + pixInTile;
@@ -652,10 +682,9 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
         } else {
             f4[0] = f4[1] = f4[2] = f4[3] = 0ull;
         }
-        float wv[4];
-        uint32_t o[4];
-        bool fresh[4];
-        bool anyFresh = false;
+        // winners of the lane's four pixels (list index, 0xffff = nothing new to shade), then ONE copy of the fragment stage in a rolled
+        // loop: the kernel's hot code has to stay inside the instruction cache (unrolled four times it did not)
+        unsigned long long winners = 0ull;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const unsigned long long fs = frag[pixInTile + k];
@@ -663,10 +692,15 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
             f = f > f4[k] ? f : f4[k];
             f4[k] = f;
             const uint32_t ti = uint32_t(f) & kStaleIdx;
-            fresh[k] = f != 0ull && ti != kStaleIdx;
-            o[k] = 0xff000000u; wv[k] = 0.0f;
-            if (!fresh[k]) continue;
-            anyFresh = true;
+            const bool fresh = f != 0ull && ti != kStaleIdx;
+            winners |= (unsigned long long)(fresh ? ti : 0xffffu) << (16 * k);
+        }
+        uint32_t o0 = 0xff000000u, o1 = 0xff000000u, o2 = 0xff000000u, o3 = 0xff000000u;
+        float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t ti = uint32_t(winners >> (16 * k)) & 0xffffu;
+            if (ti == 0xffffu) continue;
             const ShadeRec rec = loadShade(shade + ti);
             const EdgeEval e = loadCover(cover + ti);
             const int sx = sx32 + k * 256;
@@ -680,26 +714,30 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
                 l1 = float(e.C1 + (long long)e.A1 * sx + (long long)e.B1 * sy32 + e.u1) * e.invArea;
                 l2 = float(e.C2 + (long long)e.A2 * sx + (long long)e.B2 * sy32 + e.u2) * e.invArea;
             }
-            o[k] = shadePixel<FAST>(rec, l0, l1, l2, e.flat != 0, wv[k]);
+            float w;
+            const uint32_t c = shadePixel<FAST>(rec, l0, l1, l2, e.flat != 0, w);
+            if (k == 0) { o0 = c; w0 = w; } else if (k == 1) { o1 = c; w1 = w; } else if (k == 2) { o2 = c; w2 = w; } else { o3 = c; w3 = w; }
         }
+        const bool fr0 = (winners & 0xffffull) != 0xffffull, fr1 = ((winners >> 16) & 0xffffull) != 0xffffull, fr2 = ((winners >> 32) & 0xffffull) != 0xffffull,
+                   fr3 = (winners >> 48) != 0xffffull;
         uint8_t *obsPix = P.obs + ((size_t(view) * P.H + size_t(py)) * P.W + px) * 4;
         float *depthPix = P.depth ? P.depth + (size_t(view) * P.H + size_t(py)) * P.W + px : nullptr;
         if (batch == 0) {
-            *reinterpret_cast<uint4 *>(obsPix) = make_uint4(o[0], o[1], o[2], o[3]);
-            if (depthPix) *reinterpret_cast<float4 *>(depthPix) = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        } else if (anyFresh) {  // a later batch won some of this lane's pixels: this lane wrote the others itself, earlier
+            *reinterpret_cast<uint4 *>(obsPix) = make_uint4(o0, o1, o2, o3);
+            if (depthPix) *reinterpret_cast<float4 *>(depthPix) = make_float4(w0, w1, w2, w3);
+        } else if (fr0 || fr1 || fr2 || fr3) {  // a later batch won some of this lane's pixels: this lane wrote the others itself, earlier
             uint4 old = *reinterpret_cast<const uint4 *>(obsPix);
-            if (fresh[0]) old.x = o[0];
-            if (fresh[1]) old.y = o[1];
-            if (fresh[2]) old.z = o[2];
-            if (fresh[3]) old.w = o[3];
+            if (fr0) old.x = o0;
+            if (fr1) old.y = o1;
+            if (fr2) old.z = o2;
+            if (fr3) old.w = o3;
             *reinterpret_cast<uint4 *>(obsPix) = old;
             if (depthPix) {
                 float4 od = *reinterpret_cast<const float4 *>(depthPix);
-                if (fresh[0]) od.x = wv[0];
-                if (fresh[1]) od.y = wv[1];
-                if (fresh[2]) od.z = wv[2];
-                if (fresh[3]) od.w = wv[3];
+                if (fr0) od.x = w0;
+                if (fr1) od.y = w1;
+                if (fr2) od.z = w2;
+                if (fr3) od.w = w3;
                 *reinterpret_cast<float4 *>(depthPix) = od;
             }
         }
@@ -715,14 +753,13 @@ __device__ __forceinline__ void tilePass(const ViewParams &P, const TriCover *co
 
 // ---------------------------------------------------------------------------------------------------- the kernel
 template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTAS) viewKernel(ViewParams P) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *smem = g_viewSmem;
     const SmemLayout L = smemLayout(P.triCap);
     MvInstance *stage = reinterpret_cast<MvInstance *>(smem + L.stage);
     TriCover *cover = reinterpret_cast<TriCover *>(smem + L.cover);
     TriShade *shade = reinterpret_cast<TriShade *>(smem + L.shade);
     float *xf = reinterpret_cast<float *>(smem + L.xf);          // [kXfWords][kInstChunk]
     int32_t *off = reinterpret_cast<int32_t *>(smem + L.off);    // exclusive item offsets of the chunk's instances, off[n] = total
-    unsigned long long *fragAll = reinterpret_cast<unsigned long long *>(smem + L.frag);
     float *meshV = reinterpret_cast<float *>(smem + L.meshV);    // [kMeshVerts][6]
     uint8_t *meshI = smem + L.meshI;
     uint16_t *slowAll = reinterpret_cast<uint16_t *>(smem + L.slow);  // [2][kThreads]: instance-in-chunk | item << 7 | done << 15
@@ -758,7 +795,6 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
     const uint32_t total = uint32_t(P.N) * uint32_t(bands);
     const int tilesX = P.W >> 5;
     unsigned long long *spill = P.spill + size_t(blockIdx.x) * size_t(P.spillStride);
-    unsigned long long *frag = fragAll + warp * 128;
 
     if (tid == 0) { M.claim = atomicAdd(P.workCounter, 1u) - P.counterBase; M.prefetched = 0; }
     for (;;) {
@@ -926,26 +962,26 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                         const int meta = __float_as_int(xf[22 * kInstChunk + i]);
                         const int mesh = meta & 255;
                         const uint32_t ii = uint32_t(cBase + i);
-                        SetupResult res;
+                        ClipVert cvt[4];
+                        const float *vpn[4];
+                        int nTri;
+                        uint32_t keyBase;
                         if (mesh == 0) {
                             const int face = nthFace(unsigned(meta >> 8) & 63u, sub);
-                            ClipVert cvt[4];
-                            const float *vp = meshV + (face * 4) * 6;
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) vertPosition(cvt[k], mv, vp + k * 6, P.p00, P.p11, P.p22, P.p32);
-                            res = setupFace<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], nm, vp, color, ii * 128u + uint32_t(face) * 2u + 1u);
+                            for (int k = 0; k < 4; ++k) vpn[k] = meshV + (face * 4 + k) * 6;
+                            nTri = 2; keyBase = ii * 128u + uint32_t(face) * 2u + 1u;
                         } else {
                             const int vBase = mesh == 1 ? kVCapsule : (mesh == 2 ? kVSphere : (mesh == 3 ? kVCone : kVCylinder));
                             const int iBase = mesh == 1 ? kICapsule : (mesh == 2 ? kISphere : (mesh == 3 ? kICone : kICylinder));
-                            ClipVert cvt[3];
-                            const float *vp[3];
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) {
-                                vp[k] = meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6;
-                                vertPosition(cvt[k], mv, vp[k], P.p00, P.p11, P.p22, P.p32);
-                            }
-                            res = setupTri<FAST>(cx, cvt[0], cvt[1], cvt[2], nm, vp[0], vp[1], vp[2], color, ii * 128u + uint32_t(sub) + 1u);
+                            for (int k = 0; k < 3; ++k) vpn[k] = meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6;
+                            vpn[3] = vpn[2];
+                            nTri = 1; keyBase = ii * 128u + uint32_t(sub) + 1u;
                         }
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) vertPosition(cvt[k], mv, vpn[k], P.p00, P.p11, P.p22, P.p32);
+                        const SetupResult res = setupItem<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], nTri, nm, vpn[0], vpn[1], vpn[2], vpn[3], color, keyBase);
                         pending = res == kSetupFull;
                         if (res == kSetupClip) {
                             int at;
@@ -1027,7 +1063,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                     }
                     if (!__syncthreads_or((pending || slowFull) ? 1 : 0)) break;
                     // the list is full: draw what it holds, then retry what did not fit
-                    tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, false);
+                    tilePass<FAST>(P, min(M.nTris, M.nValid), spill, view, rowLo, bandTiles, batch, false);
                     if (P.stats && tid == 0) M.stat[5] += uint32_t(min(M.nTris, M.nValid));
                     ++batch;
                     again = true;
@@ -1080,7 +1116,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
             }
             M.claim = nc; M.prefetched = pre;
         }
-        tilePass<FAST>(P, cover, shade, min(M.nTris, M.nValid), frag, &M.tileCtr, spill, view, rowLo, bandTiles, batch, true);
+        tilePass<FAST>(P, min(M.nTris, M.nValid), spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
         if (P.stats && tid < 8) {
             unsigned long long v = M.stat[tid];
