@@ -180,6 +180,9 @@ struct mv_engine {
     uint32_t counterBase = 0;          // what the counter read before the next launch's first claim
     DevBuf<unsigned long long> d_spill;  // [rasterGrid][spillStride]
     DevBuf<unsigned long long> d_rasterStats;  // mv_debug_raster_stats only
+    DevBuf<uint32_t> d_viewCost;       // [2][N] per-view cost measured by the previous / the current raster launch, then the exit counter (cost-ordered work queue)
+    int costParity = 0;
+    int rasterSched = 1;               // option "raster_sched": 0 natural order, 1 cost-ordered when the launch has several items per CTA, 2 always
     int rasterGrid = 0, rasterCtasPerSM = 0, spillStride = 0, rasterBands = 1;
     size_t rasterSmem = 0;
     // hi-res pass (draw_hires): its own output buffers, allocated on first use
@@ -405,7 +408,12 @@ struct mv_engine {
         deviceObsFresh = !rasterToHost;
         if (sliceCount <= 1) {
             vp.viewBase = 0; vp.N = N;
-            return launchView(vp, std::min(rasterGrid, N * rasterBands), overlap);
+            const int grid = std::min(rasterGrid, N * rasterBands);
+            if (rasterBands == 1 && N <= mvr::kSchedMaxViews && (rasterSched == 2 || (rasterSched == 1 && N >= 2 * grid))) {
+                vp.viewCost = d_viewCost.p + size_t(costParity) * N; vp.viewCostOut = d_viewCost.p + size_t(costParity ^ 1) * N; vp.exitCounter = d_viewCost.p + 2 * size_t(N);
+                costParity ^= 1;
+            }
+            return launchView(vp, grid, overlap);
         }
         // sliced download: whole envs per slice; slice s is copied down by the copy engine while slice s+1 is rasterised
         const size_t px = size_t(W) * H;
@@ -619,7 +627,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_statics.free(); d_staticRot.free(); h_statics.free(); h_staticRot.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free();
+        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free(); d_viewCost.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free(); h_faultWord.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -738,7 +746,8 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(e->d_inst.alloc(E * size_t(e->instCap)), "instances") && ck(e->d_deco.alloc(E * 2 * size_t(e->decoCap)), "deco") && ck(e->h_deco.alloc(E * 2 * size_t(e->decoCap)), "h_deco") && ck(e->d_instCounts.alloc(E * 8), "instCounts") && ck(e->d_views.alloc(N * 16), "views") &&
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
-         ck(e->d_workCounter.alloc(4), "workCounter") && ck(cudaMemset(e->d_workCounter.p, 0, 16), "workCounter") && ck(e->d_ready.alloc(E), "ready") &&
+         ck(e->d_workCounter.alloc(4), "workCounter") && ck(cudaMemset(e->d_workCounter.p, 0, 16), "workCounter") &&
+         ck(e->d_viewCost.alloc(2 * size_t(N) + 1), "viewCost") && ck(cudaMemset(e->d_viewCost.p, 0, sizeof(uint32_t) * (2 * size_t(N) + 1)), "viewCost") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     if (e->instCap > mvr::kMaxInstancesPerEnv) { e->setError("instance capacity exceeds the draw-order key range"); return fail(MV_ERR_CAPACITY); }
@@ -808,6 +817,13 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         if (value < 1 || value > h->H / 4 || (h->H / 4) % value) { h->setError("raster_bands must divide the number of 4-pixel tile rows"); return MV_ERR_ARG; }
         h->rasterBands = value;
         return h->configureRaster();
+    }
+    if (k == "raster_sched") {  // work order of the persistent raster grid: 0 natural, 1 cost-ordered for launches with several views per CTA, 2 always
+        if (value < 0 || value > 2) return MV_ERR_ARG;
+        cudaStreamSynchronize(h->stream);
+        h->rasterSched = value;
+        cudaMemset(h->d_viewCost.p, 0, sizeof(uint32_t) * (2 * size_t(h->N) + 1));
+        return MV_OK;
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopyOpt = value != 0; return MV_OK; }

@@ -98,6 +98,12 @@ struct ViewParams {
                                  // thread-0 cycles: head (claim, stamp, view), TMA waits, instance passes, item passes, final tile pass, whole item
     unsigned long long *spill;   // [gridDim.x][spillStride] per-CTA fragment slab for views drawn in several batches
     int spillStride;             // >= W * bandRows
+    // cost-ordered work queue (optional; bands == 1, viewBase == 0, N <= kSchedMaxViews): viewCost[v] = SM cycles / 16 the view took in the
+    // previous launch.  Every CTA derives the same "heavy" set from it (cost > 1.5 x mean) and the queue hands those out first, so that the
+    // persistent CTAs do not run dry at very different times (a heavy view started last would be the kernel's tail).
+    const uint32_t *viewCost;    // [N] or nullptr: what the previous launch measured (stable during this launch: CTAs of a dependent launch start at
+    uint32_t *viewCostOut;       // [N] different times and must all derive the same heavy set), and where this launch writes its own costs
+    uint32_t *exitCounter;       // with viewCost: CTAs that have left; the last one sets the work counter to what the host expects next
     int viewBase, N;             // this launch draws views [viewBase, viewBase + N)
     int A, W, H;
     int bands, bandRows;         // bandRows: multiple of 4; bands * bandRows >= H
@@ -105,7 +111,8 @@ struct ViewParams {
     float p00, p11, p22, p32;
 };
 
-struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, small, meshV, meshI, clip, slow, misc, total; };
+constexpr int kSchedMaxViews = 8192;  // views a cost-ordered launch can number (bitmap of the heavy views in shared memory)
+struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, small, meshV, meshI, clip, slow, sched, misc, total; };
 struct ViewMisc {
     float view[16];
     int32_t counts[8];
@@ -116,8 +123,11 @@ struct ViewMisc {
     int32_t prefetched;
     int32_t wsum[kWarps];
     int32_t nSlow[2];   // entries of the two slow-item lists (alternating per item sub-pass)
+    int32_t nHeavy;     // cost-ordered queue: views in the heavy set (0: natural order)
     uint32_t stat[8];   // debug counters of the current work item ([7]: item sub-passes)
     alignas(8) unsigned long long bar[2];
+    unsigned long long costSum;    // cost-ordered queue: sum of the previous launch's view costs
+    unsigned long long itemStart;  // clock64 when thread 0 started the current work item (after the wait for its env)
 };
 __host__ __device__ inline SmemLayout smemLayout(int triCap) {
     SmemLayout L;
@@ -135,6 +145,7 @@ __host__ __device__ inline SmemLayout smemLayout(int triCap) {
     L.clip = L.frag;
     L.small = o; o += uint32_t(kWarps) * kSmallList * 2u;       // per warp: list indices of the small triangles of the current tile
     L.slow = o; o += 2u * kThreads * 2u;                        // two lists of at most one entry per thread
+    L.sched = o; o += uint32_t(kSchedMaxViews) / 8u;           // heavy-view bitmap of the cost-ordered queue
     L.misc = o; o += (uint32_t(sizeof(ViewMisc)) + 15u) & ~15u;
     L.total = o;
     return L;
@@ -751,8 +762,34 @@ __device__ MV_TILE_INLINE void tilePass(const ViewParams &P, int count, unsigned
     }
 }
 
+// ---------------------------------------------------------------------------------------------------- work queue
+// Next work item of the CTA (called by one thread): an index into [0, total), or >= total when the queue is empty.  Natural order:
+// the claim itself.  Cost-ordered (nHeavy > 0, one band per view): claims [0, nHeavy) are the heavy views by rank in the bitmap, the
+// claims after them walk all views in natural order and skip the heavy ones.
+__device__ __forceinline__ uint32_t claimWork(const ViewParams &P, uint32_t total, int nHeavy, const uint32_t *heavyBits) {
+    for (;;) {
+        const uint32_t c = atomicAdd(P.workCounter, 1u) - P.counterBase;
+        if (nHeavy == 0) return c;
+        if (c < uint32_t(nHeavy)) {
+            uint32_t rank = c;
+            for (int w = 0;; ++w) {
+                uint32_t bits = heavyBits[w];
+                const uint32_t n = uint32_t(__popc(bits));
+                if (rank < n) {
+                    for (; rank; --rank) bits &= bits - 1u;
+                    return uint32_t(w) * 32u + uint32_t(__ffs(bits) - 1);
+                }
+                rank -= n;
+            }
+        }
+        const uint32_t v = c - uint32_t(nHeavy);
+        if (v >= total) return v;
+        if (!((heavyBits[v >> 5] >> (v & 31u)) & 1u)) return v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- the kernel
-template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTAS) viewKernel(ViewParams P) {
+template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTAS) viewKernel(const __grid_constant__ ViewParams P) {
     unsigned char *smem = g_viewSmem;
     const SmemLayout L = smemLayout(P.triCap);
     MvInstance *stage = reinterpret_cast<MvInstance *>(smem + L.stage);
@@ -787,8 +824,31 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         else val = c_cylinderIdx[i - kICylinder];
         meshI[i] = val;
     }
-    if (tid == 0) { mbarInit(&M.bar[0], 1); mbarInit(&M.bar[1], 1); }
+    uint32_t *heavyBits = reinterpret_cast<uint32_t *>(smem + L.sched);
+    if (tid == 0) { mbarInit(&M.bar[0], 1); mbarInit(&M.bar[1], 1); M.costSum = 0ull; M.nHeavy = 0; }
     __syncthreads();
+    if (P.viewCost) {  // the heavy set of the cost-ordered queue: every CTA derives the same bitmap from the previous launch's costs
+        unsigned long long sum = 0ull;
+        for (int v = tid; v < P.N; v += kThreads) sum += (unsigned long long)__ldcg(P.viewCost + v);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        if (lane == 0) atomicAdd(&M.costSum, sum);
+        __syncthreads();
+        const unsigned long long sum3 = M.costSum * 3ull, n2 = 2ull * (unsigned long long)P.N;
+        const int words = (P.N + 31) >> 5;
+        for (int w = warp; w < words; w += kWarps) {
+            const int v = w * 32 + lane;
+            const unsigned long long c = v < P.N ? (unsigned long long)__ldcg(P.viewCost + v) : 0ull;
+            const unsigned bits = __ballot_sync(0xffffffffu, c * n2 > sum3);  // cost > 1.5 x mean
+            if (lane == 0) heavyBits[w] = bits;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int n = 0;
+            for (int w = 0; w < words; ++w) n += __popc(heavyBits[w]);
+            M.nHeavy = n;
+        }
+    }
     uint32_t phase[2] = {0u, 0u};
 
     const int bands = P.bands;
@@ -796,7 +856,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
     const int tilesX = P.W >> 5;
     unsigned long long *spill = P.spill + size_t(blockIdx.x) * size_t(P.spillStride);
 
-    if (tid == 0) { M.claim = atomicAdd(P.workCounter, 1u) - P.counterBase; M.prefetched = 0; }
+    if (tid == 0) { M.claim = claimWork(P, total, M.nHeavy, heavyBits); M.prefetched = 0; }
     for (;;) {
         const long long tc0 = P.stats ? clock64() : 0;
         long long tcWait = 0, tcInst = 0, tcItem = 0;
@@ -825,6 +885,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");  // the acquire orders generic-proxy reads; the bulk copies below go through the async proxy
             }
+            M.itemStart = (unsigned long long)clock64();
             M.nTris = 0;
             M.nValid = 0x7fffffff;
             M.tileCtr = 0;
@@ -1084,7 +1145,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         // instance chunk while this item's tiles are drawn (the stage buffers, M.view and M.counts are idle during the tile pass): the
         // global round trips of the item head then cost nothing.  One thread; its warp joins the tile pass a little later.
         if (tid == 0) {
-            const uint32_t nc = atomicAdd(P.workCounter, 1u) - P.counterBase;
+            const uint32_t nc = claimWork(P, total, M.nHeavy, heavyBits);
             int pre = 0;
             if (nc < total) {
                 const int nview = P.viewBase + int(nc / uint32_t(bands)), nenv = nview / P.A;
@@ -1118,6 +1179,7 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
         }
         tilePass<FAST>(P, min(M.nTris, M.nValid), spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
+        if (P.viewCost && tid == 0) P.viewCostOut[vrel] = uint32_t(min((unsigned long long)clock64() - M.itemStart, 0xffffffffull * 16ull) >> 4);
         if (P.stats && tid < 8) {
             unsigned long long v = M.stat[tid];
             if (tid == 0) v = 1;
@@ -1130,6 +1192,15 @@ template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTA
                 atomicAdd(P.stats + 10, (unsigned long long)tcInst); atomicAdd(P.stats + 11, (unsigned long long)tcItem);
                 atomicAdd(P.stats + 12, (unsigned long long)(tc3 - tc2)); atomicAdd(P.stats + 13, (unsigned long long)(tc3 - tc0));
             }
+        }
+    }
+    // cost-ordered queue: the skipped claims moved the work counter past what the host accounts for (items + one failing claim per CTA);
+    // the last CTA to leave puts it there.  (The next launch on the stream cannot start before this grid has drained.)
+    if (P.viewCost && tid == 0) {
+        __threadfence();
+        if (atomicAdd(P.exitCounter, 1u) == gridDim.x - 1u) {
+            *P.exitCounter = 0u;
+            atomicExch(P.workCounter, P.counterBase + total + gridDim.x);
         }
     }
 }

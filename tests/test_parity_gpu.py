@@ -647,12 +647,13 @@ def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
 
     E, steps = 6, 90
     gs = []
-    for tri_cap, bands in ((32, 1), (0, 3), (200, 2), (0, 1)):
+    for tri_cap, bands, sched in ((32, 1, 0), (0, 3, 0), (200, 2, 0), (0, 1, 0), (0, 1, 2)):
         g = capi.Engine(scenario, E, A, 128, 72, num_threads=2, depth=True)
         g.set_option("fast_shading", 0)
         if tri_cap:
             g.set_option("tri_cap", tri_cap)
         g.set_option("raster_bands", bands)
+        g.set_option("raster_sched", sched)  # 2: the cost-ordered work queue even at this small size
         g.seed(77)
         g.reset()
         gs.append(g)
@@ -676,6 +677,38 @@ def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
         assert g.faults() == 0
         g.close()
     o.close()
+
+
+def test_cost_ordered_work_queue_keeps_frames_identical(built):
+    """the persistent raster grid hands the previous step's expensive views out first (option raster_sched, default for launches with several
+    views per CTA).  The order in which views are drawn must not change a byte: 700 Collect envs x 2 agents (1400 views on 296 CTAs), cost-ordered
+    vs natural order, on the asynchronous device-resident path and on the host-facing one, frames compared every few steps; no view is drawn
+    twice or skipped (a sentinel written into the obs tensor before each step must be gone everywhere)"""
+    from megaverse_b200 import capi
+
+    E, A, steps = 700, 2, 24
+    gs = []
+    for sched in (1, 0):
+        g = capi.Engine("Collect", E, A, 128, 72, num_threads=8)
+        g.set_option("raster_sched", sched)
+        for e in range(E):
+            g.seed_env(e, 300 + e)
+        g.reset()
+        gs.append(g)
+    rng = np.random.default_rng(5)
+    for t in range(steps):
+        acts = helpers.random_bit_actions(rng, E * A).astype(np.int32)
+        for g in gs:
+            g.step(acts)
+        if t % 4 == 3 or t < 3:
+            a, b = np.array(gs[0].obs()), np.array(gs[1].obs())
+            assert np.array_equal(a, b), "cost-ordered and natural-order frames differ at step %d" % t
+            assert (a[..., 3] == 255).all(), "a view was not drawn at step %d" % t
+            gs[0].obs()[...] = 0  # sentinel: alpha 0 must be overwritten by the next step's frames
+    assert np.array_equal(np.array(gs[0].rewards()), np.array(gs[1].rewards()))
+    for g in gs:
+        assert g.faults() == 0
+        g.close()
 
 
 @pytest.mark.parametrize("mode", ["host", "device"])
