@@ -708,6 +708,8 @@ __device__ MV_TILE_INLINE void tilePass(const ViewParams &P, int count, unsigned
         }
         uint32_t o0 = 0xff000000u, o1 = 0xff000000u, o2 = 0xff000000u, o3 = 0xff000000u;
         float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
+        // (keeping the records of the previous pixel's triangle in registers across the iterations -- the lane's four pixels mostly belong
+        // to one triangle -- was measured: 20 % SLOWER, the loop then spills)
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
             const uint32_t ti = uint32_t(winners >> (16 * k)) & 0xffffu;
@@ -789,7 +791,12 @@ __device__ __forceinline__ uint32_t claimWork(const ViewParams &P, uint32_t tota
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
-template <bool FAST> __global__ void __launch_bounds__(kThreads, MV_VIEW_MIN_CTAS) viewKernel(const __grid_constant__ ViewParams P) {
+#ifdef MV_VIEW_MAXNREG  // a register cap below what two CTAs per SM allow leaves room for a step-kernel CTA beside them
+#define MV_VIEW_BOUNDS __maxnreg__(MV_VIEW_MAXNREG)
+#else
+#define MV_VIEW_BOUNDS __launch_bounds__(kThreads, MV_VIEW_MIN_CTAS)
+#endif
+template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_constant__ ViewParams P) {
     unsigned char *smem = g_viewSmem;
     const SmemLayout L = smemLayout(P.triCap);
     MvInstance *stage = reinterpret_cast<MvInstance *>(smem + L.stage);
