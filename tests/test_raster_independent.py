@@ -250,3 +250,43 @@ def test_shared_edges_are_drawn_exactly_once():
     assert count[36, 64] == 1, "the shared vertex on a pixel centre belongs to exactly one triangle"
     interior = (sx - cx) ** 2 + (sy - cy) ** 2 < (25 * 256) ** 2
     assert (count[interior] == 1).all(), "a sample inside the fan was not covered"
+
+
+def _tie_scene(seed):
+    rng = np.random.default_rng(3000 + seed)
+    p00, p11, _, _ = _projection()
+    rows = []
+    for k in range(5):
+        z_front = -rng.uniform(3.0, 9.0)
+        half_z = rng.uniform(0.2, 0.6)
+        px0, py0 = int(rng.integers(4, 90)), int(rng.integers(4, 50))
+        wpx = int(rng.integers(6, 30)); hpx = wpx if k % 2 == 0 else int(rng.integers(6, 20))
+        x0, x1 = [((px + 0.5) - W / 2) / (W / 2) * (-z_front) / float(p00) for px in (px0, px0 + wpx)]
+        y0, y1 = [((py + 0.5) - H / 2) / (H / 2) * (-z_front) / float(p11) for py in (py0, py0 + hpx)]
+        m = np.eye(4)
+        m[0, 0], m[1, 1], m[2, 2] = abs(x1 - x0) / 2, abs(y1 - y0) / 2, half_z
+        m[:3, 3] = [(x0 + x1) / 2, (y0 + y1) / 2, z_front - half_z]
+        rows.append(np.concatenate([[0, k], m.T.reshape(-1)]))
+    return np.eye(4, dtype=F32).reshape(-1), np.array(rows, dtype=F32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,seed", [("far", 0), ("far", 1), ("ties", 0), ("ties", 1), ("near", 0)])
+def test_cuda_rasteriser_against_the_independent_rules(kind, seed):
+    """the CUDA kernel itself (mv_debug_render_instances: the product's viewKernel on one view) against this file's restatement of the
+    specification -- no oracle in between"""
+    from megaverse_b200 import capi
+
+    if kind == "ties":
+        view16, inst = _tie_scene(seed)
+    else:
+        rng = np.random.default_rng((1000 if kind == "far" else 2000) + seed)
+        view16, inst = _random_scene(rng, 6 if kind == "far" else 5, near_camera=(kind == "near"))
+    _, dev = capi.render_instances(view16, inst, W, H, want_depth=True)
+    mine, _ = _independent_depth(view16, inst)
+    cov_dev, cov_mine = dev > 0, mine > 0
+    mism = int((cov_dev != cov_mine).sum())
+    assert mism <= (8 if kind == "near" else 0), "coverage differs in %d pixels" % mism
+    both = cov_dev & cov_mine
+    rel = np.abs(dev[both].astype(np.float64) - mine[both]) / mine[both]
+    assert (rel > (1e-4 if kind == "near" else 2e-5)).sum() <= (8 if kind == "near" else 0)
