@@ -109,7 +109,7 @@ __device__ __forceinline__ M4 inverted4(const M4 &m) {
     return o;
 }
 // inverse-transpose of the upper 3x3 (cofactor matrix / determinant); n[col*3+row]
-__device__ __forceinline__ void normalMatrix(const M4 &mv, float n[9]) {
+__device__ __forceinline__ float normalMatrix(const M4 &mv, float n[9]) {  // returns the determinant of the 3x3
     const float a00 = mv.c[0], a01 = mv.c[1], a02 = mv.c[2];
     const float a10 = mv.c[4], a11 = mv.c[5], a12 = mv.c[6];
     const float a20 = mv.c[8], a21 = mv.c[9], a22 = mv.c[10];
@@ -121,6 +121,7 @@ __device__ __forceinline__ void normalMatrix(const M4 &mv, float n[9]) {
     n[0] = c00 * id; n[1] = c01 * id; n[2] = c02 * id;
     n[3] = c10 * id; n[4] = c11 * id; n[5] = c12 * id;
     n[6] = c20 * id; n[7] = c21 * id; n[8] = c22 * id;
+    return det;
 }
 
 }  // namespace dm

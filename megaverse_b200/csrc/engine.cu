@@ -180,8 +180,7 @@ struct mv_engine {
     uint32_t counterBase = 0;          // what the counter read before the next launch's first claim
     DevBuf<unsigned long long> d_spill;  // [rasterGrid][spillStride]
     DevBuf<unsigned long long> d_rasterStats;  // mv_debug_raster_stats only
-    DevBuf<uint32_t> d_viewCost;       // [2][N] per-view cost measured by the previous / the current raster launch, then the exit counter (cost-ordered work queue)
-    int costParity = 0;
+    DevBuf<uint32_t> d_viewCost;       // cost-ordered work queue: [N] per-view cost of the current raster launch, [N] view order for the next one, exit counter
     int rasterSched = 1;               // option "raster_sched": 0 natural order, 1 cost-ordered when the launch has several items per CTA, 2 always
     int rasterGrid = 0, rasterCtasPerSM = 0, spillStride = 0, rasterBands = 1;
     size_t rasterSmem = 0;
@@ -361,6 +360,7 @@ struct mv_engine {
         sp.prof = d_prof.p;
         sp.deco = d_deco.p; sp.decoCap = decoCap; sp.instStride = instCap;
         sp.ready = d_ready.p; sp.readyStamp = ++readyStamp;
+        sp.envOrder = rasterSched ? d_viewCost.p + N : nullptr;  // a permutation at all times (identity until a cost-ordered raster launch has sorted it)
         sp.maxObj = std::min(int(MV_MAX_OBJECTS), maxObjSeen.load());
         sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
         sp.k = consts;
@@ -395,6 +395,12 @@ struct mv_engine {
         launches += 1;
         return MV_OK;
     }
+    // the cost-ordered queue starts in natural order
+    cudaError_t resetViewOrder() {
+        std::vector<uint32_t> init(2 * size_t(N) + 1, 0u);  // [N] view costs, [E] env order (+ N - E unused), exit counter
+        for (int e = 0; e < E; ++e) init[size_t(N) + size_t(e)] = uint32_t(e);
+        return cudaMemcpy(d_viewCost.p, init.data(), sizeof(uint32_t) * init.size(), cudaMemcpyHostToDevice);
+    }
     int launchRaster() {
         mvr::ViewParams vp = {};
         vp.instances = d_inst.p; vp.instCounts = d_instCounts.p; vp.views = d_views.p; vp.instStride = instCap;
@@ -409,9 +415,8 @@ struct mv_engine {
         if (sliceCount <= 1) {
             vp.viewBase = 0; vp.N = N;
             const int grid = std::min(rasterGrid, N * rasterBands);
-            if (rasterBands == 1 && N <= mvr::kSchedMaxViews && (rasterSched == 2 || (rasterSched == 1 && N >= 2 * grid))) {
-                vp.viewCost = d_viewCost.p + size_t(costParity) * N; vp.viewCostOut = d_viewCost.p + size_t(costParity ^ 1) * N; vp.exitCounter = d_viewCost.p + 2 * size_t(N);
-                costParity ^= 1;
+            if (rasterBands == 1 && (rasterSched == 2 || (rasterSched == 1 && N >= 2 * grid))) {
+                vp.viewCost = d_viewCost.p; vp.order = d_viewCost.p + N; vp.exitCounter = d_viewCost.p + 2 * size_t(N);
             }
             return launchView(vp, grid, overlap);
         }
@@ -747,7 +752,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
          ck(e->d_workCounter.alloc(4), "workCounter") && ck(cudaMemset(e->d_workCounter.p, 0, 16), "workCounter") &&
-         ck(e->d_viewCost.alloc(2 * size_t(N) + 1), "viewCost") && ck(cudaMemset(e->d_viewCost.p, 0, sizeof(uint32_t) * (2 * size_t(N) + 1)), "viewCost") && ck(e->d_ready.alloc(E), "ready") &&
+         ck(e->d_viewCost.alloc(2 * size_t(N) + 1), "viewCost") && ck(e->resetViewOrder(), "viewOrder") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     if (e->instCap > mvr::kMaxInstancesPerEnv) { e->setError("instance capacity exceeds the draw-order key range"); return fail(MV_ERR_CAPACITY); }
@@ -822,8 +827,7 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         if (value < 0 || value > 2) return MV_ERR_ARG;
         cudaStreamSynchronize(h->stream);
         h->rasterSched = value;
-        cudaMemset(h->d_viewCost.p, 0, sizeof(uint32_t) * (2 * size_t(h->N) + 1));
-        return MV_OK;
+        return h->resetViewOrder() == cudaSuccess ? MV_OK : MV_ERR_CUDA;
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopyOpt = value != 0; return MV_OK; }

@@ -98,12 +98,14 @@ struct ViewParams {
                                  // thread-0 cycles: head (claim, stamp, view), TMA waits, instance passes, item passes, final tile pass, whole item
     unsigned long long *spill;   // [gridDim.x][spillStride] per-CTA fragment slab for views drawn in several batches
     int spillStride;             // >= W * bandRows
-    // cost-ordered work queue (optional; bands == 1, viewBase == 0, N <= kSchedMaxViews): viewCost[v] = SM cycles / 16 the view took in the
-    // previous launch.  Every CTA derives the same "heavy" set from it (cost > 1.5 x mean) and the queue hands those out first, so that the
-    // persistent CTAs do not run dry at very different times (a heavy view started last would be the kernel's tail).
-    const uint32_t *viewCost;    // [N] or nullptr: what the previous launch measured (stable during this launch: CTAs of a dependent launch start at
-    uint32_t *viewCostOut;       // [N] different times and must all derive the same heavy set), and where this launch writes its own costs
-    uint32_t *exitCounter;       // with viewCost: CTAs that have left; the last one sets the work counter to what the host expects next
+    // cost-ordered work queue (optional; one band per view, viewBase == 0, N = E * A): claim c draws agent c % A of env order[c / A].  Every
+    // CTA writes the SM cycles a view took into viewCost; the last CTA to leave sorts the ENVS by the cost of their views, descending
+    // (counting sort over 256 cost classes), into `order` for the next launch -- so the persistent CTAs do not run dry at very different
+    // times (an expensive view started last is the kernel's tail).  The step kernel steps the envs in the same order, so that the envs
+    // this grid asks for first are also the first to be ready.
+    uint32_t *viewCost;          // [N] or nullptr
+    uint32_t *order;             // [E] a permutation of the envs
+    uint32_t *exitCounter;       // CTAs that have left (the last one sorts)
     int viewBase, N;             // this launch draws views [viewBase, viewBase + N)
     int A, W, H;
     int bands, bandRows;         // bandRows: multiple of 4; bands * bandRows >= H
@@ -111,7 +113,6 @@ struct ViewParams {
     float p00, p11, p22, p32;
 };
 
-constexpr int kSchedMaxViews = 8192;  // views a cost-ordered launch can number (bitmap of the heavy views in shared memory)
 struct SmemLayout { uint32_t stage, cover, shade, xf, off, frag, small, meshV, meshI, clip, slow, sched, misc, total; };
 struct ViewMisc {
     float view[16];
@@ -121,12 +122,11 @@ struct ViewMisc {
     int32_t tileCtr;
     uint32_t claim;     // this work item; claimed (and, when its env was ready, its view / counts / first chunk fetched) during the previous tile pass
     int32_t prefetched;
+    int32_t lastCta;    // cost-ordered queue: this CTA is the last one to leave the grid (it sorts the views for the next launch)
     int32_t wsum[kWarps];
     int32_t nSlow[2];   // entries of the two slow-item lists (alternating per item sub-pass)
-    int32_t nHeavy;     // cost-ordered queue: views in the heavy set (0: natural order)
     uint32_t stat[8];   // debug counters of the current work item ([7]: item sub-passes)
     alignas(8) unsigned long long bar[2];
-    unsigned long long costSum;    // cost-ordered queue: sum of the previous launch's view costs
     unsigned long long itemStart;  // clock64 when thread 0 started the current work item (after the wait for its env)
 };
 __host__ __device__ inline SmemLayout smemLayout(int triCap) {
@@ -145,7 +145,7 @@ __host__ __device__ inline SmemLayout smemLayout(int triCap) {
     L.clip = L.frag;
     L.small = o; o += uint32_t(kWarps) * kSmallList * 2u;       // per warp: list indices of the small triangles of the current tile
     L.slow = o; o += 2u * kThreads * 2u;                        // two lists of at most one entry per thread
-    L.sched = o; o += uint32_t(kSchedMaxViews) / 8u;           // heavy-view bitmap of the cost-ordered queue
+    L.sched = o; o += 256u * 4u;                                // cost classes of the counting sort (last CTA of a cost-ordered launch)
     L.misc = o; o += (uint32_t(sizeof(ViewMisc)) + 15u) & ~15u;
     L.total = o;
     return L;
@@ -765,29 +765,12 @@ __device__ MV_TILE_INLINE void tilePass(const ViewParams &P, int count, unsigned
 }
 
 // ---------------------------------------------------------------------------------------------------- work queue
-// Next work item of the CTA (called by one thread): an index into [0, total), or >= total when the queue is empty.  Natural order:
-// the claim itself.  Cost-ordered (nHeavy > 0, one band per view): claims [0, nHeavy) are the heavy views by rank in the bitmap, the
-// claims after them walk all views in natural order and skip the heavy ones.
-__device__ __forceinline__ uint32_t claimWork(const ViewParams &P, uint32_t total, int nHeavy, const uint32_t *heavyBits) {
-    for (;;) {
-        const uint32_t c = atomicAdd(P.workCounter, 1u) - P.counterBase;
-        if (nHeavy == 0) return c;
-        if (c < uint32_t(nHeavy)) {
-            uint32_t rank = c;
-            for (int w = 0;; ++w) {
-                uint32_t bits = heavyBits[w];
-                const uint32_t n = uint32_t(__popc(bits));
-                if (rank < n) {
-                    for (; rank; --rank) bits &= bits - 1u;
-                    return uint32_t(w) * 32u + uint32_t(__ffs(bits) - 1);
-                }
-                rank -= n;
-            }
-        }
-        const uint32_t v = c - uint32_t(nHeavy);
-        if (v >= total) return v;
-        if (!((heavyBits[v >> 5] >> (v & 31u)) & 1u)) return v;
-    }
+// Next work item of the CTA (called by one thread): an index into [0, total), or >= total when the queue is empty.  Natural order: the
+// claim itself; cost-ordered: the view the previous launch's sort put at that position.
+__device__ __forceinline__ uint32_t claimWork(const ViewParams &P, uint32_t total) {
+    const uint32_t c = atomicAdd(P.workCounter, 1u) - P.counterBase;
+    if (P.viewCost && c < total) return __ldcg(P.order + c / uint32_t(P.A)) * uint32_t(P.A) + c % uint32_t(P.A);
+    return c;
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
@@ -831,31 +814,8 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
         else val = c_cylinderIdx[i - kICylinder];
         meshI[i] = val;
     }
-    uint32_t *heavyBits = reinterpret_cast<uint32_t *>(smem + L.sched);
-    if (tid == 0) { mbarInit(&M.bar[0], 1); mbarInit(&M.bar[1], 1); M.costSum = 0ull; M.nHeavy = 0; }
+    if (tid == 0) { mbarInit(&M.bar[0], 1); mbarInit(&M.bar[1], 1); }
     __syncthreads();
-    if (P.viewCost) {  // the heavy set of the cost-ordered queue: every CTA derives the same bitmap from the previous launch's costs
-        unsigned long long sum = 0ull;
-        for (int v = tid; v < P.N; v += kThreads) sum += (unsigned long long)__ldcg(P.viewCost + v);
-#pragma unroll
-        for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-        if (lane == 0) atomicAdd(&M.costSum, sum);
-        __syncthreads();
-        const unsigned long long sum3 = M.costSum * 3ull, n2 = 2ull * (unsigned long long)P.N;
-        const int words = (P.N + 31) >> 5;
-        for (int w = warp; w < words; w += kWarps) {
-            const int v = w * 32 + lane;
-            const unsigned long long c = v < P.N ? (unsigned long long)__ldcg(P.viewCost + v) : 0ull;
-            const unsigned bits = __ballot_sync(0xffffffffu, c * n2 > sum3);  // cost > 1.5 x mean
-            if (lane == 0) heavyBits[w] = bits;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int n = 0;
-            for (int w = 0; w < words; ++w) n += __popc(heavyBits[w]);
-            M.nHeavy = n;
-        }
-    }
     uint32_t phase[2] = {0u, 0u};
 
     const int bands = P.bands;
@@ -863,7 +823,7 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
     const int tilesX = P.W >> 5;
     unsigned long long *spill = P.spill + size_t(blockIdx.x) * size_t(P.spillStride);
 
-    if (tid == 0) { M.claim = claimWork(P, total, M.nHeavy, heavyBits); M.prefetched = 0; }
+    if (tid == 0) { M.claim = claimWork(P, total); M.prefetched = 0; }
     for (;;) {
         const long long tc0 = P.stats ? clock64() : 0;
         long long tcWait = 0, tcInst = 0, tcItem = 0;
@@ -950,7 +910,8 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
                 int meta = mesh;
                 if (instanceMayBeVisible(mv, mesh == 1 ? 2.0f : 1.0f, P.p00, P.p11)) {
                     float nm[9];
-                    normalMatrix(mv, nm);
+                    const float det = normalMatrix(mv, nm);
+                    if (!(det > 0.0f)) meta |= 1 << 16;  // a mirroring transform turns the winding round: no object-space face test for its triangles
                     if (mesh == 0) {
                         // a box face whose plane clearly faces away from the eye (the view-space origin) only yields triangles the
                         // winding test drops: outward normal n, face centre = origin + n (unit cube), cull when n_view . c_view > 0
@@ -1034,6 +995,7 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
                         const float *vpn[4];
                         int nTri;
                         uint32_t keyBase;
+                        bool facesAway = false;
                         if (mesh == 0) {
                             const int face = nthFace(unsigned(meta >> 8) & 63u, sub);
 #pragma unroll
@@ -1046,10 +1008,30 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
                             for (int k = 0; k < 3; ++k) vpn[k] = meshV + (vBase + int(meshI[iBase + sub * 3 + k])) * 6;
                             vpn[3] = vpn[2];
                             nTri = 1; keyBase = ii * 128u + uint32_t(sub) + 1u;
+#ifndef MV_NO_MESH_PRECULL
+                            // Half of a closed mesh faces away.  Those triangles would be dropped by the winding test after three vertex
+                            // transforms, three divisions and the 64-bit area; the same decision is available in object space for a
+                            // fraction: the eye there is -inverse(M3) t = -(normal matrix)^T t, and the triangle faces away when its plane
+                            // has the eye behind it.  Only CLEAR cases are skipped (sine of the angle to the plane beyond 0.02); the
+                            // rest take the exact path.
+                            if (!(meta & (1 << 16))) {
+                                const float t0 = mv[9], t1 = mv[10], t2 = mv[11];
+                                const float ex = -(nm[0] * t0 + nm[1] * t1 + nm[2] * t2), ey = -(nm[3] * t0 + nm[4] * t1 + nm[5] * t2), ez = -(nm[6] * t0 + nm[7] * t1 + nm[8] * t2);
+                                const float *pa = vpn[0], *pb = vpn[1], *pc = vpn[2];
+                                const float ux = pb[0] - pa[0], uy = pb[1] - pa[1], uz = pb[2] - pa[2], vx = pc[0] - pa[0], vy = pc[1] - pa[1], vz = pc[2] - pa[2];
+                                const float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+                                const float dx = ex - pa[0], dy = ey - pa[1], dz = ez - pa[2];
+                                const float sd = nx * dx + ny * dy + nz * dz;
+                                facesAway = sd < 0.0f && sd * sd > 4e-4f * ((nx * nx + ny * ny + nz * nz) * (dx * dx + dy * dy + dz * dz));
+                            }
+#endif
                         }
+                        SetupResult res = kSetupDone;
+                        if (!facesAway) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) vertPosition(cvt[k], mv, vpn[k], P.p00, P.p11, P.p22, P.p32);
-                        const SetupResult res = setupItem<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], nTri, nm, vpn[0], vpn[1], vpn[2], vpn[3], color, keyBase);
+                            for (int k = 0; k < 4; ++k) vertPosition(cvt[k], mv, vpn[k], P.p00, P.p11, P.p22, P.p32);
+                            res = setupItem<FAST>(cx, cvt[0], cvt[1], cvt[2], cvt[3], nTri, nm, vpn[0], vpn[1], vpn[2], vpn[3], color, keyBase);
+                        }
                         pending = res == kSetupFull;
                         if (res == kSetupClip) {
                             int at;
@@ -1152,7 +1134,7 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
         // instance chunk while this item's tiles are drawn (the stage buffers, M.view and M.counts are idle during the tile pass): the
         // global round trips of the item head then cost nothing.  One thread; its warp joins the tile pass a little later.
         if (tid == 0) {
-            const uint32_t nc = claimWork(P, total, M.nHeavy, heavyBits);
+            const uint32_t nc = claimWork(P, total);
             int pre = 0;
             if (nc < total) {
                 const int nview = P.viewBase + int(nc / uint32_t(bands)), nenv = nview / P.A;
@@ -1186,7 +1168,7 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
         }
         tilePass<FAST>(P, min(M.nTris, M.nValid), spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
-        if (P.viewCost && tid == 0) P.viewCostOut[vrel] = uint32_t(min((unsigned long long)clock64() - M.itemStart, 0xffffffffull * 16ull) >> 4);
+        if (P.viewCost && tid == 0) P.viewCost[vrel] = uint32_t(min((unsigned long long)clock64() - M.itemStart, 0xffffffffull * 16ull) >> 4);
         if (P.stats && tid < 8) {
             unsigned long long v = M.stat[tid];
             if (tid == 0) v = 1;
@@ -1201,13 +1183,71 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
             }
         }
     }
-    // cost-ordered queue: the skipped claims moved the work counter past what the host accounts for (items + one failing claim per CTA);
-    // the last CTA to leave puts it there.  (The next launch on the stream cannot start before this grid has drained.)
-    if (P.viewCost && tid == 0) {
-        __threadfence();
-        if (atomicAdd(P.exitCounter, 1u) == gridDim.x - 1u) {
-            *P.exitCounter = 0u;
-            atomicExch(P.workCounter, P.counterBase + total + gridDim.x);
+    // cost-ordered queue: the last CTA to leave knows every view's cost and sorts the views for the next launch, most expensive first -- a
+    // counting sort over 256 linear cost classes (order within a class is arbitrary: it cannot change a frame).  The next launch on the
+    // stream cannot start before this grid has drained, so `order` is never read while it is rewritten.
+    if (P.viewCost) {
+        if (tid == 0) {
+            __threadfence();
+            M.lastCta = atomicAdd(P.exitCounter, 1u) == gridDim.x - 1u ? 1 : 0;
+        }
+        __syncthreads();
+        if (M.lastCta) {
+            __threadfence();
+            uint32_t *bins = reinterpret_cast<uint32_t *>(smem + L.sched);
+            // per-env cost = sum over its views, gathered once into shared memory (the triangle list is free now); independent loads, four in flight
+            const int E = P.N / P.A;
+            uint32_t *costS = reinterpret_cast<uint32_t *>(smem + L.cover);
+            const int capS = int((L.xf - L.cover) / 4u);
+            const bool inSmem = E <= capS;
+            if (inSmem) {
+                for (int e = tid; e < E; e += kThreads) costS[e] = 0u;
+                __syncthreads();
+                const uint32_t A = uint32_t(P.A);
+                for (int v0 = tid; v0 < P.N; v0 += 4 * kThreads) {
+                    uint32_t c[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const int v = v0 + q * kThreads; c[q] = v < P.N ? __ldcg(P.viewCost + v) : 0u; }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const int v = v0 + q * kThreads; if (v < P.N) atomicAdd(&costS[uint32_t(v) / A], c[q]); }
+                }
+                __syncthreads();
+            }
+            auto envCost = [&](int e) {
+                if (inSmem) return costS[e];
+                uint32_t c = 0u;
+                for (int a = 0; a < P.A; ++a) c += __ldcg(P.viewCost + e * P.A + a);
+                return c;
+            };
+            uint32_t mx = 1u;
+            for (int e = tid; e < E; e += kThreads) mx = max(mx, envCost(e));
+#pragma unroll
+            for (int d = 16; d; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            if (lane == 0) M.wsum[warp] = int32_t(mx);
+            for (int b = tid; b < 256; b += kThreads) bins[b] = 0u;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) mx = max(mx, uint32_t(M.wsum[w]));
+            const float scale = 255.0f / float(mx);
+            for (int e = tid; e < E; e += kThreads) atomicAdd(&bins[255 - min(255, int(float(envCost(e)) * scale))], 1u);
+            __syncthreads();
+            if (warp == 0) {  // exclusive scan of the 256 class counts: eight per lane
+                uint32_t c8[8], sum = 0u;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { c8[q] = bins[lane * 8 + q]; sum += c8[q]; }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { bins[lane * 8 + q] = run; run += c8[q]; }
+            }
+            __syncthreads();
+            for (int e = tid; e < E; e += kThreads) {
+                const uint32_t at = atomicAdd(&bins[255 - min(255, int(float(envCost(e)) * scale))], 1u);
+                P.order[at] = uint32_t(e);
+            }
+            if (tid == 0) *P.exitCounter = 0u;
         }
     }
 }

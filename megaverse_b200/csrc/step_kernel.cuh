@@ -67,6 +67,7 @@ struct StepParams {
     int forceReset;              // mv_reset(): re-initialise every env from its live level slot, no physics
     uint32_t *ready;             // [E] completion stamps polled by the geometry kernel (programmatic dependent launch)
     uint32_t readyStamp;
+    const uint32_t *envOrder;  // optional [E]: warp w of the grid steps env envOrder[w] (the order in which the rasteriser will ask for the envs)
     int maxObj;                  // upper bound of n_obj over the live and staged levels (sizes the staging copy)
     uint32_t *prof;              // optional [E][16] per-phase cycle stamps (mv_debug_step_profile); nullptr in production
     MvConsts k;
@@ -859,10 +860,11 @@ __device__ void writeInstances(const WarpShared &S, const MvLevel &L, const MvBo
 __global__ void __launch_bounds__(128) stepKernel(StepParams P) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
+    const int slotInGrid = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
     // let the geometry kernel's blocks start right away: they synchronise per env on P.ready, not on this grid's completion
     asm volatile("griddepcontrol.launch_dependents;");
-    if (env >= P.E) return;
+    if (slotInGrid >= P.E) return;
+    const int env = P.envOrder ? int(__ldg(P.envOrder + slotInGrid)) : slotInGrid;
     WarpShared &S = reinterpret_cast<WarpShared *>(smemRaw)[warpInBlock];
     const int A = P.A;
     const float dt = P.k.dt;

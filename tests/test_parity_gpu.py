@@ -680,10 +680,11 @@ def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
 
 
 def test_cost_ordered_work_queue_keeps_frames_identical(built):
-    """the persistent raster grid hands the previous step's expensive views out first (option raster_sched, default for launches with several
-    views per CTA).  The order in which views are drawn must not change a byte: 700 Collect envs x 2 agents (1400 views on 296 CTAs), cost-ordered
-    vs natural order, on the asynchronous device-resident path and on the host-facing one, frames compared every few steps; no view is drawn
-    twice or skipped (a sentinel written into the obs tensor before each step must be gone everywhere)"""
+    """the persistent raster grid draws the envs in the order of what their views cost in the previous step, most expensive first (option
+    raster_sched, default for launches with several views per CTA; the step kernel steps the envs in the same order).  The order in which
+    views are drawn must not change a byte: 700 Collect envs x 2 agents (1400 views on 296 CTAs), cost-ordered vs natural order, frames
+    compared every few steps; no view is drawn twice or skipped (a sentinel written into the obs tensor before each step must be gone
+    everywhere)"""
     from megaverse_b200 import capi
 
     E, A, steps = 700, 2, 24

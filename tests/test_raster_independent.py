@@ -159,6 +159,7 @@ def _random_scene(rng, n, near_camera):
         t = np.array([rng.uniform(-1.2, 1.2) * depth, rng.uniform(-0.8, 0.8) * depth, -depth])
         m = np.eye(4); m[:3, :3] = rot; m[:3, 3] = t
         rows.append(np.concatenate([[mesh, rng.integers(0, 20)], m.T.reshape(-1)]))  # column-major
+    rows.sort(key=lambda r: r[0])  # draw order: by mesh type, boxes first (what the product's instance lists guarantee)
     roll = rng.uniform(-0.3, 0.3)
     v = np.eye(4); v[:2, :2] = [[np.cos(roll), -np.sin(roll)], [np.sin(roll), np.cos(roll)]]
     return v.T.reshape(-1).astype(F32), np.array(rows, dtype=F32)
