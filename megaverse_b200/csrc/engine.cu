@@ -180,7 +180,8 @@ struct mv_engine {
     uint32_t counterBase = 0;          // what the counter read before the next launch's first claim
     DevBuf<unsigned long long> d_spill;  // [rasterGrid][spillStride]
     DevBuf<unsigned long long> d_rasterStats;  // mv_debug_raster_stats only
-    DevBuf<uint32_t> d_viewCost;       // cost-ordered work queue: [N] per-view cost of the current raster launch, [N] view order for the next one, exit counter
+    DevBuf<uint32_t> d_viewCost;       // cost-ordered work queue: [N * H / 4] cost per work item of the current raster launch (N * bands used), [E] env order for the next one, exit counter
+    size_t costItems() const { return size_t(N) * size_t(H / 4); }
     int rasterSched = 1;               // option "raster_sched": 0 natural order, 1 cost-ordered when the launch has several items per CTA, 2 always
     int rasterGrid = 0, rasterCtasPerSM = 0, spillStride = 0, rasterBands = 1;
     size_t rasterSmem = 0;
@@ -360,7 +361,7 @@ struct mv_engine {
         sp.prof = d_prof.p;
         sp.deco = d_deco.p; sp.decoCap = decoCap; sp.instStride = instCap;
         sp.ready = d_ready.p; sp.readyStamp = ++readyStamp;
-        sp.envOrder = rasterSched ? d_viewCost.p + N : nullptr;  // a permutation at all times (identity until a cost-ordered raster launch has sorted it)
+        sp.envOrder = rasterSched ? d_viewCost.p + costItems() : nullptr;  // a permutation at all times (identity until a cost-ordered raster launch has sorted it)
         sp.maxObj = std::min(int(MV_MAX_OBJECTS), maxObjSeen.load());
         sp.E = E; sp.A = A; sp.gridCells = gridCells; sp.gridWords = gridWords; sp.forceReset = forceReset ? 1 : 0;
         sp.k = consts;
@@ -397,8 +398,8 @@ struct mv_engine {
     }
     // the cost-ordered queue starts in natural order
     cudaError_t resetViewOrder() {
-        std::vector<uint32_t> init(2 * size_t(N) + 1, 0u);  // [N] view costs, [E] env order (+ N - E unused), exit counter
-        for (int e = 0; e < E; ++e) init[size_t(N) + size_t(e)] = uint32_t(e);
+        std::vector<uint32_t> init(costItems() + size_t(E) + 1, 0u);  // item costs, env order, exit counter
+        for (int e = 0; e < E; ++e) init[costItems() + size_t(e)] = uint32_t(e);
         return cudaMemcpy(d_viewCost.p, init.data(), sizeof(uint32_t) * init.size(), cudaMemcpyHostToDevice);
     }
     int launchRaster() {
@@ -415,8 +416,8 @@ struct mv_engine {
         if (sliceCount <= 1) {
             vp.viewBase = 0; vp.N = N;
             const int grid = std::min(rasterGrid, N * rasterBands);
-            if (rasterBands == 1 && (rasterSched == 2 || (rasterSched == 1 && N >= 2 * grid))) {
-                vp.viewCost = d_viewCost.p; vp.order = d_viewCost.p + N; vp.exitCounter = d_viewCost.p + 2 * size_t(N);
+            if (rasterSched == 2 || (rasterSched == 1 && N * rasterBands > grid)) {  // more work items than CTAs: their order matters
+                vp.viewCost = d_viewCost.p; vp.order = d_viewCost.p + costItems(); vp.exitCounter = d_viewCost.p + costItems() + size_t(E);
             }
             return launchView(vp, grid, overlap);
         }
@@ -752,7 +753,7 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
          ck(e->d_workCounter.alloc(4), "workCounter") && ck(cudaMemset(e->d_workCounter.p, 0, 16), "workCounter") &&
-         ck(e->d_viewCost.alloc(2 * size_t(N) + 1), "viewCost") && ck(e->resetViewOrder(), "viewOrder") && ck(e->d_ready.alloc(E), "ready") &&
+         ck(e->d_viewCost.alloc(e->costItems() + size_t(E) + 1), "viewCost") && ck(e->resetViewOrder(), "viewOrder") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     if (e->instCap > mvr::kMaxInstancesPerEnv) { e->setError("instance capacity exceeds the draw-order key range"); return fail(MV_ERR_CAPACITY); }

@@ -98,12 +98,12 @@ struct ViewParams {
                                  // thread-0 cycles: head (claim, stamp, view), TMA waits, instance passes, item passes, final tile pass, whole item
     unsigned long long *spill;   // [gridDim.x][spillStride] per-CTA fragment slab for views drawn in several batches
     int spillStride;             // >= W * bandRows
-    // cost-ordered work queue (optional; one band per view, viewBase == 0, N = E * A): claim c draws agent c % A of env order[c / A].  Every
-    // CTA writes the SM cycles a view took into viewCost; the last CTA to leave sorts the ENVS by the cost of their views, descending
+    // cost-ordered work queue (optional; viewBase == 0, N = E * A): claim c draws item c % (A * bands) of env order[c / (A * bands)].  Every
+    // CTA writes the SM cycles a work item took into viewCost; the last CTA to leave sorts the ENVS by the cost of their items, descending
     // (counting sort over 256 cost classes), into `order` for the next launch -- so the persistent CTAs do not run dry at very different
     // times (an expensive view started last is the kernel's tail).  The step kernel steps the envs in the same order, so that the envs
     // this grid asks for first are also the first to be ready.
-    uint32_t *viewCost;          // [N] or nullptr
+    uint32_t *viewCost;          // [N * bands] (indexed like the work items: view * bands + band) or nullptr
     uint32_t *order;             // [E] a permutation of the envs
     uint32_t *exitCounter;       // CTAs that have left (the last one sorts)
     int viewBase, N;             // this launch draws views [viewBase, viewBase + N)
@@ -769,7 +769,10 @@ __device__ MV_TILE_INLINE void tilePass(const ViewParams &P, int count, unsigned
 // claim itself; cost-ordered: the view the previous launch's sort put at that position.
 __device__ __forceinline__ uint32_t claimWork(const ViewParams &P, uint32_t total) {
     const uint32_t c = atomicAdd(P.workCounter, 1u) - P.counterBase;
-    if (P.viewCost && c < total) return __ldcg(P.order + c / uint32_t(P.A)) * uint32_t(P.A) + c % uint32_t(P.A);
+    if (P.viewCost && c < total) {
+        const uint32_t perEnv = uint32_t(P.A) * uint32_t(P.bands);
+        return __ldcg(P.order + c / perEnv) * perEnv + c % perEnv;
+    }
     return c;
 }
 
@@ -1168,7 +1171,7 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
         }
         tilePass<FAST>(P, min(M.nTris, M.nValid), spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
-        if (P.viewCost && tid == 0) P.viewCost[vrel] = uint32_t(min((unsigned long long)clock64() - M.itemStart, 0xffffffffull * 16ull) >> 4);
+        if (P.viewCost && tid == 0) P.viewCost[claim] = uint32_t(min((unsigned long long)clock64() - M.itemStart, 0xffffffffull * 16ull) >> 4);
         if (P.stats && tid < 8) {
             unsigned long long v = M.stat[tid];
             if (tid == 0) v = 1;
@@ -1203,20 +1206,22 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
             if (inSmem) {
                 for (int e = tid; e < E; e += kThreads) costS[e] = 0u;
                 __syncthreads();
-                const uint32_t A = uint32_t(P.A);
-                for (int v0 = tid; v0 < P.N; v0 += 4 * kThreads) {
+                const uint32_t perEnv = uint32_t(P.A) * uint32_t(P.bands);
+                const int items = int(total);
+                for (int v0 = tid; v0 < items; v0 += 4 * kThreads) {
                     uint32_t c[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const int v = v0 + q * kThreads; c[q] = v < P.N ? __ldcg(P.viewCost + v) : 0u; }
+                    for (int q = 0; q < 4; ++q) { const int v = v0 + q * kThreads; c[q] = v < items ? __ldcg(P.viewCost + v) : 0u; }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { const int v = v0 + q * kThreads; if (v < P.N) atomicAdd(&costS[uint32_t(v) / A], c[q]); }
+                    for (int q = 0; q < 4; ++q) { const int v = v0 + q * kThreads; if (v < items) atomicAdd(&costS[uint32_t(v) / perEnv], c[q]); }
                 }
                 __syncthreads();
             }
             auto envCost = [&](int e) {
                 if (inSmem) return costS[e];
                 uint32_t c = 0u;
-                for (int a = 0; a < P.A; ++a) c += __ldcg(P.viewCost + e * P.A + a);
+                const int perEnv = P.A * P.bands;
+                for (int a = 0; a < perEnv; ++a) c += __ldcg(P.viewCost + e * perEnv + a);
                 return c;
             };
             uint32_t mx = 1u;

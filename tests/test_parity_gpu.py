@@ -647,7 +647,7 @@ def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
 
     E, steps = 6, 90
     gs = []
-    for tri_cap, bands, sched in ((32, 1, 0), (0, 3, 0), (200, 2, 0), (0, 1, 0), (0, 1, 2)):
+    for tri_cap, bands, sched in ((32, 1, 0), (0, 3, 2), (200, 2, 2), (0, 1, 0), (0, 1, 2)):
         g = capi.Engine(scenario, E, A, 128, 72, num_threads=2, depth=True)
         g.set_option("fast_shading", 0)
         if tri_cap:
