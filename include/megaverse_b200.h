@@ -83,6 +83,9 @@ int mv_set_reward_shaping(mv_handle h, int env, int agent, const char *const *ke
  * "tri_cap" (32..1022, default 368: the largest that leaves two CTAs per SM; triangles one raster CTA keeps in shared memory; a view with more is drawn in several batches,
  * results do not depend on it), "raster_bands" (row bands a view is cut into, one work item of the persistent raster grid each;
  * chosen from the number of views by default, results do not depend on it),
+ * "raster_sched" (0/1/2, default 1: launches with more work items than raster CTAs draw the envs in the order of what their views cost in
+ * the previous step, most expensive first, and the step kernel steps them in that order; 0 natural order, 2 always; results do not depend
+ * on it),
  * "static_cap" (before the first reset: initial size of the per-level static-box arrays, default 768; they grow whenever a
  * generated level has more boxes -- the reference has no bound, component_voxel_grid.hpp:108-187),
  * "skip_unfit_levels" (0/1, default 0: a generated level that exceeds one of the remaining fixed capacities -- movable objects, reward

@@ -757,8 +757,10 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
     if (e->instCap > mvr::kMaxInstancesPerEnv) { e->setError("instance capacity exceeds the draw-order key range"); return fail(MV_ERR_CAPACITY); }
-    // few views: split every view into row bands so that the persistent grid (2 CTAs per SM) has something to balance
-    e->rasterBands = N <= 160 ? 3 : (N <= 320 ? 2 : 1);
+    // few views: split every view into row bands so that the persistent grid (2 CTAs per SM) has something to balance.  With the
+    // cost-ordered queue finer items pay up to about two views per CTA (measured: 256 views 3 bands 0.128 ms per step, 2 bands 0.144, 6 bands
+    // 0.144; 512 views 2 bands 0.169, 1 band 0.188; 1024 views 1 band 0.241, 2 bands 0.273 -- every band repeats the view's geometry)
+    e->rasterBands = N <= 320 ? 3 : (N <= 640 ? 2 : 1);
     while (e->rasterBands > 1 && (h / 4) % e->rasterBands) --e->rasterBands;
     if (ok && e->configureRaster() != MV_OK) return fail(MV_ERR_CUDA);
     ok = ok && ck(e->h_levels.alloc(E * 2), "h_levels") && ck(e->h_solid.alloc(E * 2 * 3 * e->gridWords), "h_solid") && ck(e->h_actions.alloc(N), "h_actions") &&

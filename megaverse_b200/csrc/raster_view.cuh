@@ -574,8 +574,8 @@ __device__ MV_TILE_INLINE void tilePass(const ViewParams &P, int count, unsigned
         if (lane == 0) tile = atomicAdd(tileCtr, 1);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= bandTiles) break;
-        const int ty = tile / tilesX;
-        const int tx0 = (tile - ty * tilesX) * 32, ty0 = rowLo + ty * 4;
+        const int tk = tile / tilesX, ty = tk;  // (drawing the tile rows from the middle outwards -- horizon first, sky and floor last -- was measured: no effect)
+        const int tx0 = (tile - tk * tilesX) * 32, ty0 = rowLo + ty * 4;
         const int px = tx0 + (lane & 7) * 4, py = ty0 + (lane >> 3);
         const int sx32 = px * 256 + 128, sy32 = py * 256 + 128;
         unsigned long long best[4] = {0ull, 0ull, 0ull, 0ull};
