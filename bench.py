@@ -335,49 +335,57 @@ def measure_config(hz, cfg_id, K, Wm, rank, cores, sample_clocks=False):
             "roofline": roofline, "gpu_launches": int(launches), "faults": int(faults), "clocks": clocks, "raster": rcfg, "views_per_gpu": N}
 
 
-def measure_mixed(hz, K, Wm, rank, cores, gather):
+def measure_mixed(hz, K, Wm, rank, cores, gather, overlap_gather=False):
     """BASELINE configs[4]: the eight Megaverse scenarios mixed, MIXED_ENVS_PER_GPU envs per GPU (global env i runs scenario i % 8, so every
     GPU holds all eight).  One engine per scenario, each on its own stream, all rasterising into slices of ONE contiguous obs tensor (no
-    staging copy); with `gather` the tensor is all-gathered over NCCL after every step, ordered by events (no host synchronisation)."""
+    staging copy); with `gather` the tensor is all-gathered over NCCL after every step, ordered by events (no host synchronisation).
+    `overlap_gather`: the obs tensor is double-buffered (mv_set_obs_buffer switches every step), so the gather of step t runs while step
+    t+1 is stepped and drawn -- the consumer sees step t one step later, as a double-buffered sampler does."""
     from megaverse_b200 import capi, sharding
 
     torch, dist, world, local_rank = hz.torch, hz.dist, hz.world, hz.local_rank
     begin, end = sharding.shard_range(MIXED_ENVS_PER_GPU * world, world, rank)
     per = (end - begin) // len(MEGAVERSE8)
     n_local = per * len(MEGAVERSE8)
-    obs = torch.empty((n_local, H, W, 4), dtype=torch.uint8, device="cuda")
+    gathering = gather and world > 1
+    nbuf = 2 if (gathering and overlap_gather) else 1
+    obs_bufs = [torch.empty((n_local, H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
     engines, streams = [], []
     for k, scenario in enumerate(MEGAVERSE8):
         g = capi.Engine(scenario, per, 1, W, H, num_threads=max(1, min(16, cores // max(world, 1)) // 2), device=local_rank)
-        g.set_obs_buffer(obs[k * per:(k + 1) * per].data_ptr())
+        g.set_obs_buffer(obs_bufs[0][k * per:(k + 1) * per].data_ptr())
         for e in range(per):
             g.seed_env(e, 42 + begin + e * len(MEGAVERSE8) + k)  # global env i = begin + e*8 + k runs scenario k
         g.reset()
         engines.append(g)
         streams.append(torch.cuda.ExternalStream(g.stream(), device=local_rank))
     masks = torch.from_numpy(action_stream(64, n_local, 101 + rank)).cuda()
-    gathered = torch.empty((world * n_local, H, W, 4), dtype=torch.uint8, device="cuda") if gather and world > 1 else None
-    comm = torch.cuda.Stream(device=local_rank) if gathered is not None else None
+    gathered_bufs = [torch.empty((world * n_local, H, W, 4), dtype=torch.uint8, device="cuda") for _ in range(nbuf)] if gathering else None
+    comm = torch.cuda.Stream(device=local_rank) if gathering else None
+    read_done = [None] * nbuf  # per obs buffer: the gather that last read it
     torch.cuda.synchronize()
 
     def step(t):
+        b = t % nbuf
         for k, g in enumerate(engines):
+            if nbuf > 1:
+                g.set_obs_buffer(obs_bufs[b][k * per:(k + 1) * per].data_ptr())
+            if read_done[b] is not None:  # this step overwrites the send buffer of an earlier gather: wait for it, on the device
+                streams[k].wait_event(read_done[b])
             g.step_device(masks.data_ptr() + ((t % 64) * n_local + k * per) * 4)
-        if gathered is not None:
+        if gathering:
             for s in streams:  # the gather waits for every engine's raster kernel, on the device
                 comm.wait_event(s.record_event())
             with torch.cuda.stream(comm):
-                dist.all_gather_into_tensor(gathered.view(-1), obs.view(-1))
-            done = comm.record_event()
-            for s in streams:  # the next step may not overwrite the send buffer before the gather has read it
-                s.wait_event(done)
+                dist.all_gather_into_tensor(gathered_bufs[b].view(-1), obs_bufs[b].view(-1))
+            read_done[b] = comm.record_event()
 
     def sync():
         for g in engines:
             g.sync()
         torch.cuda.synchronize()
 
-    for t in range(max(Wm, 3)):
+    for t in range(max(Wm, 4)):
         step(t)
     sync()
     hz.barrier()
@@ -388,8 +396,9 @@ def measure_mixed(hz, K, Wm, rank, cores, gather):
     ev0.record(main)
     for s in streams:
         s.wait_event(ev0)
+    t0 = max(Wm, 4)
     for t in range(K):
-        step(t)
+        step(t0 + t)
     for s in streams + ([comm] if comm is not None else []):
         main.wait_event(s.record_event())
     ev1.record(main)
@@ -397,7 +406,10 @@ def measure_mixed(hz, K, Wm, rank, cores, gather):
     hz.barrier()
     ms = hz.max_ms(ev0.elapsed_time(ev1))
     faults = sum(g.faults() for g in engines)
-    if gathered is not None:  # the gathered tensor holds every rank's frames: block r equals what rank r rendered (checksums exchanged)
+    if gathering:  # the gathered tensor holds every rank's frames: block r equals what rank r rendered (checksums exchanged)
+        last = (t0 + K - 1) % nbuf
+        obs, gathered = obs_bufs[last], gathered_bufs[last]
+
         def checksum(t):
             v = t.reshape(-1).view(torch.int32).to(torch.int64)
             return torch.stack([v.sum(), (v * torch.arange(1, v.numel() + 1, device=v.device, dtype=torch.int64) % 1000003).sum()])
@@ -412,9 +424,10 @@ def measure_mixed(hz, K, Wm, rank, cores, gather):
     for g in engines:
         g.close()
     out = {"value": n_local * world * K / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / K, "envs_per_gpu": n_local, "faults": int(faults), "steps": K}
-    if gathered is not None:
+    if gathering:
         recv = (world - 1) * n_local * OBS_BYTES  # bytes arriving at each GPU per step
-        out.update({"gathered_bytes_per_step_per_gpu": recv, "nvlink_rx_gbs_per_gpu": recv / (ms / K / 1e3) / 1e9, "gathered_blocks_match_their_ranks": ok})
+        out.update({"gathered_bytes_per_step_per_gpu": recv, "nvlink_rx_gbs_per_gpu": recv / (ms / K / 1e3) / 1e9, "gathered_blocks_match_their_ranks": ok,
+                    "obs_tensor": "double-buffered: the gather of step t runs under step t+1" if nbuf > 1 else "single: step t+1 waits for the gather of step t"})
     return out
 
 
@@ -477,6 +490,7 @@ def main():
                    "no_gather": measure_mixed(hz, K, Wm, rank, cores, gather=False)}
         if world > 1:
             config5["nccl_all_gather"] = measure_mixed(hz, K, Wm, rank, cores, gather=True)
+            config5["nccl_all_gather_overlapped"] = measure_mixed(hz, K, Wm, rank, cores, gather=True, overlap_gather=True)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, n = run_cpu(head, cores, seconds=12.0)

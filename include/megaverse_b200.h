@@ -103,7 +103,9 @@ int mv_step_device(mv_handle h, const int32_t *d_masks);
 /* Redirect the HBM output of the rasteriser into caller-owned device memory: d_obs = uint8[N][h][w][4] (and d_depth = float[N][h][w]
  * when option depth is on; NULL keeps the engine's own).  Lets several engines -- one per scenario of a multi-task batch, reference
  * megaverse_env.py:27-39 -- write into slices of ONE contiguous tensor that a consumer or an NCCL gather reads without a staging copy.
- * NULL, NULL restores the engine's own buffers.  Valid in the engine stream's order (mv_stream). */
+ * NULL, NULL restores the engine's own buffers.  The pointer takes effect with the next step; steps already enqueued keep writing the
+ * previous buffer (no synchronisation: a consumer that double-buffers its tensor -- e.g. to gather step t over NCCL while step t+1 is
+ * drawn -- switches every step); mv_sync before freeing a buffer. */
 int mv_set_obs_buffer(mv_handle h, uint8_t *d_obs, float *d_depth);
 /* mv_step_device is ASYNCHRONOUS: it returns after enqueueing the step on the engine stream (device tensors are valid in
  * stream order).  mv_sync waits for everything enqueued and publishes the last step's rewards/dones/true objectives to the

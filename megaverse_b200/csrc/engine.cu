@@ -1065,7 +1065,8 @@ int mv_set_obs_buffer(mv_handle h, uint8_t *d_obs, float *d_depth) {
     if (!h) return MV_ERR_ARG;
     DeviceGuard dg__(h->device);
     if (!dg__.ok) { h->setError("cudaSetDevice failed"); return MV_ERR_CUDA; }
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    // the pointer is a launch parameter: steps already enqueued keep writing the previous buffer, the next step writes the new one.  No
+    // synchronisation here (a consumer that double-buffers its tensor switches every step); mv_sync before freeing a buffer.
     h->obsOut = d_obs ? d_obs : h->d_obs.p;
     h->depthOut = d_depth ? d_depth : h->d_depth.p;
     return MV_OK;
