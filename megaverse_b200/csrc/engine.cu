@@ -182,6 +182,7 @@ struct mv_engine {
     DevBuf<unsigned long long> d_rasterStats;  // mv_debug_raster_stats only
     DevBuf<uint32_t> d_viewCost;       // cost-ordered work queue: [N * H / 4] cost per work item of the current raster launch (N * bands used), [E] env order for the next one, exit counter
     size_t costItems() const { return size_t(N) * size_t(H / 4); }
+    int rasterGridCap = 0;             // option "raster_grid": upper bound of the raster grid (0: all CTAs the GPU holds) -- for several engines sharing one GPU
     int rasterSched = 1;               // option "raster_sched": 0 natural order, 1 cost-ordered when the launch has several items per CTA, 2 always
     int rasterGrid = 0, rasterCtasPerSM = 0, spillStride = 0, rasterBands = 1;
     size_t rasterSmem = 0;
@@ -415,7 +416,7 @@ struct mv_engine {
         deviceObsFresh = !rasterToHost;
         if (sliceCount <= 1) {
             vp.viewBase = 0; vp.N = N;
-            const int grid = std::min(rasterGrid, N * rasterBands);
+            const int grid = std::min(rasterGridCap > 0 ? std::min(rasterGrid, rasterGridCap) : rasterGrid, N * rasterBands);
             if (rasterSched == 2 || (rasterSched == 1 && N * rasterBands > grid)) {  // more work items than CTAs: their order matters
                 vp.viewCost = d_viewCost.p; vp.order = d_viewCost.p + costItems(); vp.exitCounter = d_viewCost.p + costItems() + size_t(E);
             }
@@ -831,6 +832,12 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         cudaStreamSynchronize(h->stream);
         h->rasterSched = value;
         return h->resetViewOrder() == cudaSuccess ? MV_OK : MV_ERR_CUDA;
+    }
+    if (k == "raster_grid") {  // CTAs of the persistent raster grid (0 = as many as the GPU holds): engines that share a GPU take a share each
+        if (value < 0) return MV_ERR_ARG;
+        cudaStreamSynchronize(h->stream);
+        h->rasterGridCap = value;
+        return MV_OK;
     }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopyOpt = value != 0; return MV_OK; }

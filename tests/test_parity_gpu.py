@@ -640,20 +640,21 @@ def test_many_agents_other_resolutions(built, scenario, A, w, h):
 @pytest.mark.parametrize("scenario,A", [("TowerBuilding", 2), ("HexExplore", 2), ("HexMemory", 1), ("Collect", 4), ("ObstaclesHard", 1), ("Rearrange", 2)])
 def test_raster_partitioning_keeps_frames_identical(built, scenario, A):
     """how the rasteriser splits its work must not change a single byte: a triangle list of 32 entries per CTA (every view is drawn in many
-    batches through the spill slab, repainting pixels that later batches win), the default list, and views cut into 1, 2 or 3 row bands --
-    engines on the same seeds and actions, frames and depth compared every step; each against the oracle at the end"""
+    batches through the spill slab, repainting pixels that later batches win), the default list, views cut into 1, 2 or 3 row bands, the
+    cost-ordered work queue, a raster grid of three or five CTAs -- engines on the same seeds and actions, frames and depth compared every step; each against the oracle at the end"""
     import orc
     from megaverse_b200 import capi
 
     E, steps = 6, 90
     gs = []
-    for tri_cap, bands, sched in ((32, 1, 0), (0, 3, 2), (200, 2, 2), (0, 1, 0), (0, 1, 2)):
+    for tri_cap, bands, sched, grid in ((32, 1, 0, 0), (0, 3, 2, 0), (200, 2, 2, 5), (0, 1, 0, 0), (0, 1, 2, 3)):
         g = capi.Engine(scenario, E, A, 128, 72, num_threads=2, depth=True)
         g.set_option("fast_shading", 0)
         if tri_cap:
             g.set_option("tri_cap", tri_cap)
         g.set_option("raster_bands", bands)
         g.set_option("raster_sched", sched)  # 2: the cost-ordered work queue even at this small size
+        g.set_option("raster_grid", grid)    # a handful of CTAs: every CTA draws many work items
         g.seed(77)
         g.reset()
         gs.append(g)
