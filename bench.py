@@ -335,7 +335,7 @@ def measure_config(hz, cfg_id, K, Wm, rank, cores, sample_clocks=False):
             "roofline": roofline, "gpu_launches": int(launches), "faults": int(faults), "clocks": clocks, "raster": rcfg, "views_per_gpu": N}
 
 
-def measure_mixed(hz, K, Wm, rank, cores, gather, overlap_gather=False, grid_share=True):
+def measure_mixed(hz, K, Wm, rank, cores, gather, overlap_gather=False, grid_share=False):
     """BASELINE configs[4]: the eight Megaverse scenarios mixed, MIXED_ENVS_PER_GPU envs per GPU (global env i runs scenario i % 8, so every
     GPU holds all eight).  One engine per scenario, each on its own stream, all rasterising into slices of ONE contiguous obs tensor (no
     staging copy); with `gather` the tensor is all-gathered over NCCL after every step, ordered by events (no host synchronisation).
@@ -354,7 +354,8 @@ def measure_mixed(hz, K, Wm, rank, cores, gather, overlap_gather=False, grid_sha
     for k, scenario in enumerate(MEGAVERSE8):
         g = capi.Engine(scenario, per, 1, W, H, num_threads=max(1, min(16, cores // max(world, 1)) // 2), device=local_rank)
         g.set_obs_buffer(obs_bufs[0][k * per:(k + 1) * per].data_ptr())
-        if grid_share:  # the eight engines' persistent raster grids share the GPU instead of queueing behind each other
+        if grid_share:  # the eight engines' persistent raster grids side by side instead of queueing behind each other (measured: slower --
+            # the maze scenarios then hold their eighth of the GPU long after the light ones have left theirs idle)
             g.set_option("raster_grid", max(8, g.raster_config()["grid"] // len(MEGAVERSE8)))
         for e in range(per):
             g.seed_env(e, 42 + begin + e * len(MEGAVERSE8) + k)  # global env i = begin + e*8 + k runs scenario k
@@ -426,7 +427,7 @@ def measure_mixed(hz, K, Wm, rank, cores, gather, overlap_gather=False, grid_sha
     for g in engines:
         g.close()
     out = {"value": n_local * world * K / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / K, "envs_per_gpu": n_local, "faults": int(faults), "steps": K,
-           "raster_grid_per_engine": "1/8 of the GPU's CTA slots" if grid_share else "all (the engines' grids queue behind each other)"}
+           "raster_grid_per_engine": "1/8 of the GPU's CTA slots (option raster_grid)" if grid_share else "all (the engines' grids queue behind each other)"}
     if gathering:
         recv = (world - 1) * n_local * OBS_BYTES  # bytes arriving at each GPU per step
         out.update({"gathered_bytes_per_step_per_gpu": recv, "nvlink_rx_gbs_per_gpu": recv / (ms / K / 1e3) / 1e9, "gathered_blocks_match_their_ranks": ok,
@@ -492,7 +493,7 @@ def main():
         config5 = {"workload": "Megaverse-8 mixed scenarios (%s), %d envs x 1 agent per GPU, 128x72 RGB (BASELINE.json configs[4])" % (", ".join(MEGAVERSE8), MIXED_ENVS_PER_GPU),
                    "no_gather": measure_mixed(hz, K, Wm, rank, cores, gather=False)}
         if world == 1:
-            config5["no_gather_full_grids"] = measure_mixed(hz, K, Wm, rank, cores, gather=False, grid_share=False)
+            config5["no_gather_grid_shares"] = measure_mixed(hz, K, Wm, rank, cores, gather=False, grid_share=True)
         if world > 1:
             config5["nccl_all_gather"] = measure_mixed(hz, K, Wm, rank, cores, gather=True)
             config5["nccl_all_gather_overlapped"] = measure_mixed(hz, K, Wm, rank, cores, gather=True, overlap_gather=True)
