@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--gather", action="store_true", help="all-gather the obs tensor over NCCL after every step")
+    ap.add_argument("--overlap", action="store_true", help="with --gather: double-buffer the obs tensor so that the gather of step t runs under step t+1")
+    ap.add_argument("--grid-shares", action="store_true", help="every engine's raster grid takes 1/8 of the GPU's CTA slots (option raster_grid)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -32,7 +34,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hz = bench.Harness(torch, dist, world, local)
-    rec = bench.measure_mixed(hz, a.steps, a.warmup, rank, os.cpu_count() or 1, gather=a.gather)
+    rec = bench.measure_mixed(hz, a.steps, a.warmup, rank, os.cpu_count() or 1, gather=a.gather, overlap_gather=a.overlap, grid_share=a.grid_shares)
     if rank == 0:
         print(json.dumps(rec))
     if world > 1:
