@@ -143,6 +143,14 @@ struct mv_engine {
     bool rasterToHost = false;
     bool deviceObsFresh = false;   // the HBM obs tensor holds the last step's frames (false after a zero-copy host-facing step)
     int sliceCount = 1;            // this launch: > 1 = sliced download on copyStream
+    // progressive delivery (option "host_progressive" = slices): ONE raster launch into HBM; the rasteriser counts finished work items per slice
+    // of whole envs (d_sliceDone, never reset: the host keeps the running targets), the copy stream waits on each counter in turn
+    // (cuStreamWaitValue32) and downloads that slice with the copy engine while the rest of the batch is still being drawn
+    int progSlicesOpt = 0, progSlices = 0;
+    DevBuf<uint32_t> d_sliceDone;
+    uint32_t sliceTarget[16] = {};
+    typedef int (*WaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+    WaitValue32Fn waitValue32 = nullptr;
     cudaStream_t copyStream = nullptr;
     std::vector<cudaEvent_t> sliceEv;
     int numSMs = 148;
@@ -420,7 +428,23 @@ struct mv_engine {
             if (rasterSched == 2 || (rasterSched == 1 && N * rasterBands > grid)) {  // more work items than CTAs: their order matters
                 vp.viewCost = d_viewCost.p; vp.order = d_viewCost.p + costItems(); vp.exitCounter = d_viewCost.p + costItems() + size_t(E);
             }
-            return launchView(vp, grid, overlap);
+            if (progSlices > 0) { vp.sliceDone = d_sliceDone.p; vp.envsPerSlice = (E + progSlices - 1) / progSlices; }
+            const int rcl = launchView(vp, grid, overlap);
+            if (rcl || progSlices <= 0) return rcl;
+            // downloads: slice k as soon as all of its work items are drawn (cyclic >= comparison on the device counter)
+            const size_t px = size_t(W) * H;
+            for (int k = 0, e0 = 0; e0 < E; ++k, e0 += vp.envsPerSlice) {
+                const int envs = std::min(vp.envsPerSlice, E - e0);
+                sliceTarget[k] += uint32_t(envs) * uint32_t(A) * uint32_t(rasterBands);
+                if (waitValue32(copyStream, (unsigned long long)(uintptr_t)(d_sliceDone.p + k), sliceTarget[k], 1u /* CU_STREAM_WAIT_VALUE_GEQ */) != 0) {
+                    setError("cuStreamWaitValue32 failed");
+                    return MV_ERR_CUDA;
+                }
+                const size_t v0 = size_t(e0) * A, cnt = size_t(envs) * A;
+                MV_CUDA(cudaMemcpyAsync(h_obs.p + v0 * px * 4, obsOut + v0 * px * 4, cnt * px * 4, cudaMemcpyDeviceToHost, copyStream));
+                if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + v0 * px, depthOut + v0 * px, sizeof(float) * cnt * px, cudaMemcpyDeviceToHost, copyStream));
+            }
+            return MV_OK;
         }
         // sliced download: whole envs per slice; slice s is copied down by the copy engine while slice s+1 is rasterised
         const size_t px = size_t(W) * H;
@@ -437,6 +461,13 @@ struct mv_engine {
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p + size_t(base) * px, depthOut + size_t(base) * px, sizeof(float) * size_t(cnt) * px, cudaMemcpyDeviceToHost, copyStream));
         }
         return MV_OK;
+    }
+    // decide how this host-facing launch delivers its frames
+    void chooseDelivery(bool copyObs) {
+        progSlices = 0;
+        if (copyObs && progSlicesOpt > 0 && waitValue32 && d_sliceDone.p) { rasterToHost = false; sliceCount = 1; progSlices = std::min({progSlicesOpt, E, 16}); return; }
+        const int d = copyObs ? hostDelivery() : 1;
+        rasterToHost = copyObs && d == 0; sliceCount = std::max(1, d);
     }
     // how a host-facing step delivers its obs: returns the slice count (0 = zero-copy stores, 1 = one copy after the raster)
     int hostDelivery() const {
@@ -530,13 +561,13 @@ struct mv_engine {
         MV_CUDA(cudaMemcpyAsync(h_rewards.p, d_rewards.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_dones.p, d_dones.p, E, cudaMemcpyDeviceToHost, stream));
         MV_CUDA(cudaMemcpyAsync(h_trueObj.p, d_trueObj.p, sizeof(float) * N, cudaMemcpyDeviceToHost, stream));
-        if (copyObs && !rasterToHost && sliceCount <= 1) {
+        if (copyObs && !rasterToHost && sliceCount <= 1 && progSlices <= 0) {
             MV_CUDA(cudaMemcpyAsync(h_obs.p, obsOut, size_t(N) * W * H * 4, cudaMemcpyDeviceToHost, stream));
             if (wantDepth) MV_CUDA(cudaMemcpyAsync(h_depth.p, depthOut, sizeof(float) * size_t(N) * W * H, cudaMemcpyDeviceToHost, stream));
         }
         if (!wait) return MV_OK;
         MV_CUDA(cudaStreamSynchronize(stream));
-        if (sliceCount > 1) MV_CUDA(cudaStreamSynchronize(copyStream));
+        if (sliceCount > 1 || progSlices > 0) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         return MV_OK;
     }
@@ -588,7 +619,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        rasterToHost = false; sliceCount = 1;
+        rasterToHost = false; sliceCount = 1; progSlices = 0;
         rc = launchStep(dActions, false, &slotP);  // rewards / dones / true objectives land in the ring slot straight from the kernel
         if (rc) return rc;
         MV_CUDA(cudaEventRecord(slotP.ev, stream));
@@ -609,7 +640,7 @@ struct mv_engine {
             MV_CUDA(cudaMemcpyAsync(d_rtable.p, h_rtable.p, sizeof(float) * N * MV_R_COUNT, cudaMemcpyHostToDevice, stream));
             rtableDirty = false;
         }
-        { const int d = copyObs ? hostDelivery() : 1; rasterToHost = copyObs && d == 0; sliceCount = std::max(1, d); }
+        chooseDelivery(copyObs);
         rc = launchStep(dActions, false);
         if (rc) return rc;
         rc = finishStep(copyObs, !split);
@@ -622,7 +653,7 @@ struct mv_engine {
     int stepEnd() {
         if (!hostStepPending) { setError("mv_step_end without mv_step_begin"); return MV_ERR_STATE; }
         MV_CUDA(cudaStreamSynchronize(stream));
-        if (sliceCount > 1) MV_CUDA(cudaStreamSynchronize(copyStream));
+        if (sliceCount > 1 || progSlices > 0) MV_CUDA(cudaStreamSynchronize(copyStream));
         readKernelTimes();
         hostStepPending = false;
         std::memset(h_actions.p, 0, sizeof(int32_t) * N);  // env.cpp:140-142: actions are cleared after every step
@@ -634,7 +665,7 @@ struct mv_engine {
         if (pool) { pool->waitAll(); pool.reset(); }
         d_levels.free(); d_statics.free(); d_staticRot.free(); h_statics.free(); h_staticRot.free(); d_solid.free(); d_objGrid.free(); d_envs.free(); d_agents.free(); d_objects.free(); d_inst.free(); d_instCounts.free();
         d_views.free(); d_actions.free(); d_rtable.free(); d_rewards.free(); d_dones.free(); d_trueObj.free(); d_obs.free(); d_depth.free(); d_faults.free();
-        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free(); d_viewCost.free();
+        hires.free(); d_deco.free(); h_deco.free(); d_prof.free(); d_ready.free(); d_workCounter.free(); d_spill.free(); d_rasterStats.free(); d_viewCost.free(); d_sliceDone.free();
         h_levels.free(); h_solid.free(); h_actions.free(); h_rtable.free(); h_rewards.free(); h_dones.free(); h_trueObj.free(); h_obs.free(); h_depth.free();
         h_faults.free(); h_faultWord.free();
         for (auto &e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -754,9 +785,18 @@ int mv_create(const char *scenario, int w, int h, int num_envs, int num_agents, 
          ck(e->d_actions.alloc(N), "actions") && ck(e->d_rtable.alloc(N * MV_R_COUNT), "rtable") && ck(e->d_rewards.alloc(N), "rewards") &&
          ck(e->d_dones.alloc(E), "dones") && ck(e->d_trueObj.alloc(N), "trueObj") && ck(e->d_obs.alloc(N * px * 4), "obs") && ck(e->d_faults.alloc(E), "faults") &&
          ck(e->d_workCounter.alloc(4), "workCounter") && ck(cudaMemset(e->d_workCounter.p, 0, 16), "workCounter") &&
+         ck(e->d_sliceDone.alloc(16), "sliceDone") && ck(cudaMemset(e->d_sliceDone.p, 0, 64), "sliceDone") &&
          ck(e->d_viewCost.alloc(e->costItems() + size_t(E) + 1), "viewCost") && ck(e->resetViewOrder(), "viewOrder") && ck(e->d_ready.alloc(E), "ready") &&
          ck(cudaMemset(e->d_ready.p, 0, sizeof(uint32_t) * size_t(E)), "ready");
     { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) e->numSMs = prop.multiProcessorCount; }
+    {   // stream memory operation of the driver API (no link dependency on libcuda): the copy stream of the progressive delivery waits on it
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess && fn)
+            e->waitValue32 = reinterpret_cast<mv_engine::WaitValue32Fn>(fn);
+        else
+            (void)cudaGetLastError();
+    }
     if (e->instCap > mvr::kMaxInstancesPerEnv) { e->setError("instance capacity exceeds the draw-order key range"); return fail(MV_ERR_CAPACITY); }
     // few views: split every view into row bands so that the persistent grid (2 CTAs per SM) has something to balance.  With the
     // cost-ordered queue finer items pay up to about two views per CTA (measured: 256 views 3 bands 0.128 ms per step, 2 bands 0.144, 6 bands
@@ -839,6 +879,12 @@ int mv_set_option(mv_handle h, const char *key, int value) {
         h->rasterGridCap = value;
         return MV_OK;
     }
+    if (k == "host_progressive") {  // slices of the progressive host delivery (0 = off): one raster launch, the copy engine follows it slice by slice
+        if (value < 0 || value > 16) return MV_ERR_ARG;
+        if (value > 0 && !h->waitValue32) { h->setError("host_progressive: cuStreamWaitValue32 is not available"); return MV_ERR_STATE; }
+        h->progSlicesOpt = value;
+        return MV_OK;
+    }
     if (k == "obs_to_host") { h->obsToHost = value != 0; return MV_OK; }
     if (k == "zero_copy") { h->zeroCopyOpt = value != 0; return MV_OK; }
     if (k == "host_slices") { if (value < 0 || value > 64) return MV_ERR_ARG; h->hostSlicesOpt = value; return MV_OK; }
@@ -903,7 +949,7 @@ int mv_reset(mv_handle h) {
         if (cudaMemcpyAsync(h->d_rtable.p, h->h_rtable.p, sizeof(float) * h->N * MV_R_COUNT, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) { h->setError("rtable upload failed"); return MV_ERR_CUDA; }
         h->rtableDirty = false;
     }
-    { const int d = h->obsToHost ? h->hostDelivery() : 1; h->rasterToHost = h->obsToHost && d == 0; h->sliceCount = std::max(1, d); }
+    h->chooseDelivery(h->obsToHost);
     rc = h->launchStep(h->d_actions.p, true);
     if (rc) return rc;
     rc = h->finishStep(h->obsToHost);

@@ -106,6 +106,11 @@ struct ViewParams {
     uint32_t *viewCost;          // [N * bands] (indexed like the work items: view * bands + band) or nullptr
     uint32_t *order;             // [E] a permutation of the envs
     uint32_t *exitCounter;       // CTAs that have left (the last one sorts)
+    // progressive host delivery (optional): sliceDone[env / envsPerSlice] += 1 when a work item is completely drawn (frames visible device-wide),
+    // so that a copy stream blocked on the counter can start downloading a slice of whole envs while the rest of the batch is still being
+    // drawn; the cost order is then slice-major (slices complete one after the other)
+    uint32_t *sliceDone;
+    int envsPerSlice;
     int viewBase, N;             // this launch draws views [viewBase, viewBase + N)
     int A, W, H;
     int bands, bandRows;         // bandRows: multiple of 4; bands * bandRows >= H
@@ -1171,6 +1176,7 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
         }
         tilePass<FAST>(P, min(M.nTris, M.nValid), spill, view, rowLo, bandTiles, batch, true);
         __syncthreads();
+        if (P.sliceDone && tid == 0) { __threadfence(); atomicAdd(P.sliceDone + env / P.envsPerSlice, 1u); }
         if (P.viewCost && tid == 0) P.viewCost[claim] = uint32_t(min((unsigned long long)clock64() - M.itemStart, 0xffffffffull * 16ull) >> 4);
         if (P.stats && tid < 8) {
             unsigned long long v = M.stat[tid];
@@ -1229,27 +1235,38 @@ template <bool FAST> __global__ void MV_VIEW_BOUNDS viewKernel(const __grid_cons
 #pragma unroll
             for (int d = 16; d; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
             if (lane == 0) M.wsum[warp] = int32_t(mx);
-            for (int b = tid; b < 256; b += kThreads) bins[b] = 0u;
+            // sort key: (slice of the progressive host delivery, if any) major, cost class descending minor
+            int nSlices = P.sliceDone ? (E + P.envsPerSlice - 1) / P.envsPerSlice : 1;
+            if (!inSmem || E + nSlices * 256 > capS) nSlices = 1;  // no room for the classes of every slice: plain cost order
+            const int envsPerSlice = nSlices > 1 ? P.envsPerSlice : E;
+            const int nBins = nSlices * 256;
+            uint32_t *kbins = nSlices > 1 ? costS + E : bins;
+            for (int b = tid; b < nBins; b += kThreads) kbins[b] = 0u;
             __syncthreads();
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) mx = max(mx, uint32_t(M.wsum[w]));
             const float scale = 255.0f / float(mx);
-            for (int e = tid; e < E; e += kThreads) atomicAdd(&bins[255 - min(255, int(float(envCost(e)) * scale))], 1u);
+            auto keyOf = [&](int e) { return (e / envsPerSlice) * 256 + 255 - min(255, int(float(envCost(e)) * scale)); };
+            for (int e = tid; e < E; e += kThreads) atomicAdd(&kbins[keyOf(e)], 1u);
             __syncthreads();
-            if (warp == 0) {  // exclusive scan of the 256 class counts: eight per lane
-                uint32_t c8[8], sum = 0u;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { c8[q] = bins[lane * 8 + q]; sum += c8[q]; }
+            {   // exclusive scan of the class counts: a run of consecutive classes per thread, then a scan over the threads
+                const int per = (nBins + kThreads - 1) / kThreads, b0 = min(nBins, tid * per), b1 = min(nBins, b0 + per);
+                uint32_t sum = 0u;
+                for (int b = b0; b < b1; ++b) sum += kbins[b];
                 uint32_t incl = sum;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+                __syncthreads();  // (M.wsum still holds the maxima some warp may be reading)
+                if (lane == 31) M.wsum[warp] = int32_t(incl);
+                __syncthreads();
                 uint32_t run = incl - sum;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { bins[lane * 8 + q] = run; run += c8[q]; }
+                for (int w = 0; w < kWarps; ++w) if (w < warp) run += uint32_t(M.wsum[w]);
+                for (int b = b0; b < b1; ++b) { const uint32_t c = kbins[b]; kbins[b] = run; run += c; }
             }
             __syncthreads();
             for (int e = tid; e < E; e += kThreads) {
-                const uint32_t at = atomicAdd(&bins[255 - min(255, int(float(envCost(e)) * scale))], 1u);
+                const uint32_t at = atomicAdd(&kbins[keyOf(e)], 1u);
                 P.order[at] = uint32_t(e);
             }
             if (tid == 0) *P.exitCounter = 0u;

@@ -713,6 +713,40 @@ def test_cost_ordered_work_queue_keeps_frames_identical(built):
         g.close()
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("scenario,E,A,depth,slices", [("Collect", 300, 2, False, 8), ("ObstaclesHard", 100, 1, True, 16), ("TowerBuilding", 7, 3, False, 4)])
+def test_progressive_host_delivery_matches_zero_copy(built, scenario, E, A, depth, slices):
+    """host delivery by the copy engine following ONE raster launch slice by slice (option host_progressive: the rasteriser counts finished
+    work items per slice of envs, the copy stream waits on the counters) against the default zero-copy stores: frames, depth, rewards and
+    dones identical every step, also when the number of envs is not a multiple of the slice count and when bands and the cost order are on"""
+    from megaverse_b200 import capi
+
+    gs = []
+    for prog in (0, slices):
+        g = capi.Engine(scenario, E, A, 128, 72, num_threads=4, depth=depth)
+        g.set_option("host_progressive", prog)
+        g.set_option("raster_sched", 2 if prog else 1)
+        for e in range(E):
+            g.seed_env(e, 900 + e)
+        g.reset()
+        gs.append(g)
+    assert np.array_equal(np.array(gs[0].obs()), np.array(gs[1].obs())), "first frame"
+    rng = np.random.default_rng(8)
+    for t in range(30):
+        acts = helpers.random_bit_actions(rng, E * A).astype(np.int32)
+        for g in gs:
+            g.step(acts)
+        a, b = np.array(gs[0].obs()), np.array(gs[1].obs())
+        assert np.array_equal(a, b), "frames differ at step %d (%d bytes)" % (t, int((a != b).sum()))
+        if depth:
+            assert np.array_equal(np.array(gs[0].depth()).view(np.uint32), np.array(gs[1].depth()).view(np.uint32)), "depth differs at step %d" % t
+        assert np.array_equal(np.array(gs[0].rewards()), np.array(gs[1].rewards())) and np.array_equal(np.array(gs[0].dones()), np.array(gs[1].dones()))
+        gs[1].obs()[...] = 0  # whatever the next step does not deliver stays black
+    for g in gs:
+        assert g.faults() == 0
+        g.close()
+
+
 @pytest.mark.parametrize("mode", ["host", "device"])
 def test_static_box_arrays_grow_on_demand(built, mode):
     """the number of static boxes of a level has no bound (component_voxel_grid.hpp:108-187): the engine's per-level arrays and the instance
