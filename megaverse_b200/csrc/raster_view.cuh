@@ -67,7 +67,10 @@ static_assert(kInstChunk <= kThreads && kInstChunk <= 128, "one thread per insta
 constexpr int kXfWords = 23;      // per instance: model-view (12: three rows of each column), normal matrix (9), colour, mesh | face mask << 8
 constexpr int kClipVerts = 6;     // a triangle clipped by two planes has at most 5 vertices
 constexpr int kSmallList = 128;   // small triangles of a tile collected before they are evaluated (32 at a time, one lane each)
-constexpr int kSmallArea = 24;    // triangles covering at most this many pixels of a tile are evaluated by one lane
+#ifndef MV_SMALL_AREA
+#define MV_SMALL_AREA 4
+#endif
+constexpr int kSmallArea = MV_SMALL_AREA;    // triangles covering at most this many pixels of a tile are evaluated by one lane
 // a fragment is (~depth bits << 32) | (draw-order key << kIdxBits) | index in the CTA's triangle list
 constexpr int kIdxBits = 10;
 constexpr uint32_t kStaleIdx = (1u << kIdxBits) - 1u;  // "already shaded in an earlier batch"
