@@ -1,17 +1,20 @@
 // K4: batched first-person rasteriser -- ONE persistent kernel, one CTA per (view, row band), everything between the
 // instance list and the finished pixels lives in shared memory.
 //
+//   The persistent grid (2 CTAs per SM) draws the envs in the order of what their views cost in the previous launch, most expensive
+//   first (the last CTA to leave counting-sorts them; the step kernel steps the envs in the same order).
 //   per work item (view, band), 256 threads:
 //     1. the env's instance list (MvInstance, 80 B each, draw order) arrives in chunks of 128 by TMA bulk copies
 //        (cp.async.bulk + mbarrier, double-buffered: chunk c+1 flies while chunk c is processed)
 //     2. instance pass, one thread per instance: model-view product, conservative frustum test of the bounding sphere,
 //        normal matrix, per-face back-face test of boxes -> struct-of-arrays transform table in shared memory
-//     3. item pass, one thread per (visible box face | mesh triangle): vertices, near/far clip, projection, 8-bit sub-pixel
+//     3. item pass, one thread per (visible box face | mesh triangle): object-space back-face test of mesh triangles, vertices,
+//        near/far clip, projection, 8-bit sub-pixel
 //        snap, integer edge set-up with the top-left rule folded into the constants -> TriCover / TriShade records appended
 //        to the CTA's triangle list IN SHARED MEMORY (no global scratch, no bins, no global atomics)
 //     4. tile pass, warps pull 32x4-pixel tiles of the band from a shared-memory counter: lanes scan the list's pixel boxes
-//        32 at a time; small triangles are evaluated one lane per triangle (packed 64-bit shared-memory atomicMax), larger
-//        ones by the whole warp (lane = 4 adjacent pixels, best fragment in registers); exact integer edge functions,
+//        32 at a time; triangles of at most kSmallArea pixels in the tile are evaluated one lane per triangle (packed 64-bit
+//        shared-memory atomicMax), the others by the whole warp (lane = 4 adjacent pixels, best fragment in registers); exact integer edge functions,
 //        nearest depth wins, later draw wins ties (LESS_OR_EQUAL); the single winner per pixel is shaded (deferred) and
 //        each lane stores its 4 pixels with one 128-bit store -- 8 lanes cover one full 128-byte line of the obs tensor
 //   A view with more triangles than the list holds is drawn in several batches: the per-pixel best fragment of earlier
@@ -70,7 +73,7 @@ constexpr int kSmallList = 128;   // small triangles of a tile collected before 
 #ifndef MV_SMALL_AREA
 #define MV_SMALL_AREA 4
 #endif
-constexpr int kSmallArea = MV_SMALL_AREA;    // triangles covering at most this many pixels of a tile are evaluated by one lane
+constexpr int kSmallArea = MV_SMALL_AREA;    // triangles covering at most this many pixels of a tile are evaluated by one lane (swept 0..64: profiles/r2e_summary.txt)
 // a fragment is (~depth bits << 32) | (draw-order key << kIdxBits) | index in the CTA's triangle list
 constexpr int kIdxBits = 10;
 constexpr uint32_t kStaleIdx = (1u << kIdxBits) - 1u;  // "already shaded in an earlier batch"
